@@ -1,0 +1,309 @@
+// Implicit-GEMM convolution (forward / data-gradient / transposed) on tcgen05 tensor cores.
+//
+//   D[128 x BN] (TMEM, fp32)  +=  A[128 x 64] (gathered activations, K-major, smem)
+//                                * B[BN x 64]^T (packed weights, K-major, smem)
+//
+// GEMM rows enumerate the q-grid of one parity class, the K index is (tap, channel).  Operand tiles are
+// gathered in 16-byte chunks with cp.async (zero-fill outside the image) straight into the 128B-swizzled
+// layout the UMMA descriptors expect, so stride, zero padding, transposed convolution (as parity classes)
+// and ragged channel counts all share this one kernel.  Reflection padding is materialised by the producer
+// of the activation (see instnorm.cu), never here.
+//
+// Warp roles (256 threads): warps 0-3 gather, warp 4 lane 0 issues tcgen05.mma, all 8 warps run the epilogue
+// (TMEM -> registers -> +bias / activation -> bf16 -> global).
+#include "gb_common.cuh"
+#include "gb_geometry.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+constexpr int LAG = 2;                // cp.async groups in flight before the oldest is published
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers, taps, bias*/;
+  static constexpr int MIN_CTAS = (BN == 256) ? 1 : 2;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, Cfg<BN>::MIN_CTAS) igemm_data_kernel(const __grid_constant__ gb_conv_params p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  // tail region after the stages
+  uint8_t* tail = smem + STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);             // full[STAGES], empty[STAGES], accum
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 128);
+  int8_t* taps_s = reinterpret_cast<int8_t*>(tail + 192);          // up to 128*4 = 512 B
+  // bias lives right after: tail + 704 .. needs BN*4 <= 1024 -> put it in its own static array instead
+  __shared__ float bias_s[BN];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int cls = blockIdx.z;
+  const gb_conv_class& cc = p.cls[cls];
+  int q[3];
+  gb_class_extents(p, cls, q);
+  const int64_t Mc = (int64_t)p.in.N * q[0] * q[1] * q[2];
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  if (m0 >= Mc) return;
+  const int n0 = blockIdx.y * BN;
+  const int KB = (cc.ntaps > 0) ? cc.kpad / BK : 0;
+
+  const uint32_t full_bar = smem_u32(bars);
+  const uint32_t empty_bar = smem_u32(bars + STAGES);
+  const uint32_t accum_bar = smem_u32(bars + 2 * STAGES);
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 4);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<C::TMEM_COLS>(smem_u32(tmem_slot));
+  for (int i = tid; i < cc.ntaps; i += 256)
+    *reinterpret_cast<uint32_t*>(taps_s + 4 * i) = *reinterpret_cast<const uint32_t*>(p.taps[cc.tap_begin + i]);
+  for (int i = tid; i < BN; i += 256) bias_s[i] = (p.bias != nullptr && n0 + i < p.ncols) ? p.bias[n0 + i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ gather producers
+    const int j = tid & 7;    // 16-byte chunk inside the 128-byte row
+    const int r0 = tid >> 3;  // first row handled by this thread (rows r0 + 16*i)
+    const int C8 = p.in.C >> 3;
+    int rbase[8], ryx[8], rz[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t m = m0 + r0 + 16 * i;
+      if (m < Mc) {
+        gb_row r = gb_decode_row(m, q);
+        const int gz = r.qz * p.in_mul[0], gy = r.qy * p.in_mul[1], gx = r.qx * p.in_mul[2];
+        rbase[i] = (int)gb_pix_offset(p.in, r.n, gz, gy, gx);
+        ryx[i] = (gy << 16) | (gx & 0xFFFF);
+        rz[i] = gz;
+      } else {
+        rbase[i] = 0;
+        ryx[i] = (int)0x80008000;  // y = x = -32768: always out of bounds
+        rz[i] = 0;
+      }
+    }
+    const __nv_bfloat16* in_ptr = reinterpret_cast<const __nv_bfloat16*>(p.in.ptr);
+    const __nv_bfloat16* w_ptr = reinterpret_cast<const __nv_bfloat16*>(p.wpacked) + cc.w_offset;
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % STAGES;
+      const int it = kb / STAGES;
+      if (it > 0) mbar_wait(empty_bar + 8 * s, (it - 1) & 1);
+      const uint32_t a_s = base + s * C::STAGE_BYTES;
+      const uint32_t b_s = a_s + A_BYTES;
+      const int k8 = kb * 8 + j;
+      const int tl = k8 / C8;
+      const int c8 = k8 - tl * C8;
+      const bool tap_ok = tl < cc.ntaps;
+      int dz = 0, dy = 0, dx = 0;
+      if (tap_ok) {
+        dz = taps_s[4 * tl + 0];
+        dy = taps_s[4 * tl + 1];
+        dx = taps_s[4 * tl + 2];
+      }
+      const int toff = (int)(dz * p.in.sz + dy * p.in.sy + dx * p.in.sx) + c8 * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = r0 + 16 * i;
+        const int z = rz[i] + dz;
+        const int y = (ryx[i] >> 16) + dy;
+        const int x = (int)(short)(ryx[i] & 0xFFFF) + dx;
+        const bool ok = tap_ok && gb_in_bounds(p.in, z, y, x);
+        const __nv_bfloat16* src = ok ? in_ptr + (rbase[i] + toff) : in_ptr;
+        cp_async16(a_s + swz128(row, j), src, ok);
+      }
+#pragma unroll
+      for (int i = 0; i < BN / 16; ++i) {
+        const int row = r0 + 16 * i;
+        const int n = n0 + row;
+        const bool ok = n < p.npad;
+        const __nv_bfloat16* src = ok ? w_ptr + ((int64_t)n * cc.kpad + kb * BK + j * 8) : w_ptr;
+        cp_async16(b_s + swz128(row, j), src, ok);
+      }
+      cp_async_commit();
+      if (kb >= LAG) {
+        cp_async_wait<LAG>();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar + 8 * ((kb - LAG) % STAGES));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      for (int kk = (KB > LAG ? KB - LAG : 0); kk < KB; ++kk) mbar_arrive(full_bar + 8 * (kk % STAGES));
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BN, 0, 0);
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % STAGES;
+      const int it = kb / STAGES;
+      mbar_wait(full_bar + 8 * s, it & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_s = base + s * C::STAGE_BYTES;
+        const uint32_t b_s = a_s + A_BYTES;
+        const uint64_t adesc = make_smem_desc(a_s, 16, 1024);
+        const uint64_t bdesc = make_smem_desc(b_s, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        umma_commit(empty_bar + 8 * s);
+      }
+      __syncwarp();
+    }
+    if (lane == 0 && KB > 0) umma_commit(accum_bar);
+    __syncwarp();
+  }
+
+  // -------------------------------------------------------------------- epilogue (all warps)
+  if (KB > 0) {
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+  }
+  {
+    const int lg = warp & 3;
+    const int half = warp >> 2;
+    const int row = lg * 32 + lane;
+    const int64_t m = m0 + row;
+    const bool row_ok = m < Mc;
+    __nv_bfloat16* optr = reinterpret_cast<__nv_bfloat16*>(p.out.ptr);
+    int64_t ooff = 0;
+    if (row_ok) {
+      gb_row r = gb_decode_row(m, q);
+      ooff = gb_pix_offset(p.out, r.n, r.qz * p.out_mul[0] + cc.off[0], r.qy * p.out_mul[1] + cc.off[1],
+                           r.qx * p.out_mul[2] + cc.off[2]);
+    }
+    constexpr int CH = (BN >= 64) ? 32 : 16;              // columns per TMEM load
+    constexpr int COLS_PER_HALF = (BN >= 64) ? BN / 2 : BN;
+    const bool active = (BN >= 64) || half == 0;
+    if (active) {
+      const int cbeg = (BN >= 64) ? half * COLS_PER_HALF : 0;
+#pragma unroll 1
+      for (int c0 = cbeg; c0 < cbeg + COLS_PER_HALF; c0 += CH) {
+        uint32_t acc[CH];
+        if (KB > 0) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
+          if constexpr (CH == 32) tmem_ld32(taddr, acc); else tmem_ld16(taddr, acc);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) acc[i] = 0u;
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < CH / 8; ++g) {
+            const int col = n0 + c0 + g * 8;
+            if (col < p.out.C) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float t = __uint_as_float(acc[g * 8 + e]) + bias_s[c0 + g * 8 + e];
+                if (p.act == GB_ACT_TANH) t = tanhf(t);
+                else if (p.act == GB_ACT_LEAKY) t = t > 0.f ? t : t * p.act_slope;
+                else if (p.act == GB_ACT_RELU) t = fmaxf(t, 0.f);
+                v[e] = t;
+              }
+              uint4 o;
+              o.x = pack_bf16x2(v[0], v[1]);
+              o.y = pack_bf16x2(v[2], v[3]);
+              o.z = pack_bf16x2(v[4], v[5]);
+              o.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(optr + ooff + col) = o;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+template <int BN>
+int launch(const gb_conv_params& p, int64_t max_mc, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GB_CUDA(cudaFuncSetAttribute(igemm_data_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  dim3 grid(gb_cdiv(max_mc, BM), gb_cdiv(p.ncols, BN), p.nclass);
+  igemm_data_kernel<BN><<<grid, 256, C::SMEM, st>>>(p);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int64_t view_max_offset(const gb_view& v) {
+  return (int64_t)(v.N - 1) * v.sn + (int64_t)(v.D - 1) * v.sz + (int64_t)(v.H - 1 + v.pad) * v.sy +
+         (int64_t)(v.W - 1 + v.pad) * v.sx + v.C;
+}
+
+}  // namespace
+
+extern "C" int gb_conv_data(const gb_conv_params* pp, void* stream) {
+  const gb_conv_params& p = *pp;
+  GB_CHECK(p.in.ptr && p.out.ptr && p.wpacked, "gb_conv_data: null pointer");
+  GB_CHECK(p.in.C % 8 == 0 && p.out.C % 8 == 0, "gb_conv_data: channel counts must be multiples of 8 (%d, %d)", p.in.C,
+           p.out.C);
+  GB_CHECK(p.nclass >= 1 && p.nclass <= GB_MAX_CLASSES, "gb_conv_data: bad class count %d", p.nclass);
+  GB_CHECK(p.ncols >= 1 && p.ncols <= p.out.C && p.npad % 16 == 0, "gb_conv_data: bad ncols/npad %d/%d", p.ncols,
+           p.npad);
+  GB_CHECK(p.in.N == p.out.N, "gb_conv_data: batch mismatch");
+  GB_CHECK(view_max_offset(p.in) < (1ll << 31) && view_max_offset(p.out) < (1ll << 31),
+           "gb_conv_data: tensor too large for 32-bit offsets");
+  GB_CHECK(p.in.H < 32768 && p.in.W < 32768, "gb_conv_data: spatial extent too large");
+  GB_CHECK(((uintptr_t)p.in.ptr & 15) == 0 && ((uintptr_t)p.out.ptr & 15) == 0 && ((uintptr_t)p.wpacked & 15) == 0,
+           "gb_conv_data: pointers must be 16-byte aligned");
+  int64_t max_mc = 0;
+  for (int c = 0; c < p.nclass; ++c) {
+    GB_CHECK(p.cls[c].kpad % 64 == 0, "gb_conv_data: kpad must be a multiple of 64");
+    GB_CHECK(p.cls[c].ntaps * p.in.C <= p.cls[c].kpad, "gb_conv_data: kpad too small");
+    GB_CHECK(p.cls[c].tap_begin + p.cls[c].ntaps <= GB_MAX_TAPS, "gb_conv_data: too many taps");
+    int q[3];
+    gb_class_extents(p, c, q);
+    int64_t mc = (int64_t)p.in.N * q[0] * q[1] * q[2];
+    if (mc > max_mc) max_mc = mc;
+  }
+  if (max_mc == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  // tile width: smallest BN covering the output channels, shrunk while the grid under-fills the 148 SMs
+  int bn = 16;
+  while (bn < p.ncols && bn < 256) bn *= 2;
+  if (g_gb_knobs[1] > 0) {
+    bn = g_gb_knobs[1];
+  } else {
+    const int64_t mt = (max_mc + BM - 1) / BM * p.nclass;
+    while (bn > 64 && mt * gb_cdiv(p.ncols, bn) < 148) bn /= 2;
+  }
+  switch (bn) {
+    case 16: return launch<16>(p, max_mc, st);
+    case 32: return launch<32>(p, max_mc, st);
+    case 64: return launch<64>(p, max_mc, st);
+    case 128: return launch<128>(p, max_mc, st);
+    case 256: return launch<256>(p, max_mc, st);
+  }
+  GB_CHECK(false, "gb_conv_data: bad tile width %d", bn);
+}

@@ -1,0 +1,266 @@
+// Weight-gradient implicit GEMM on tcgen05 tensor cores.
+//
+//   dW[128 rows x BN cols] (TMEM, fp32) += P[64 px x 128 ch]^T  *  G[64 px x BN kflat]
+//
+// The reduction dimension is the pixel index, so with channels-last activations both operands are
+// "MN-major": a tile row is one pixel's 64 consecutive channels (128 B), exactly the smem image the forward
+// kernel builds, only the UMMA descriptors say MN-major.  P ("plain") is the tensor whose channels index the
+// rows of dW (dOut for a convolution, the input for a transposed convolution); G ("gathered") is the other
+// tensor read through the tap offsets, its column index kflat = tap*C + c is the forward kernel's K index.
+// The pixel range is split across blockIdx.z and partial sums are combined with red.global.add.v4.f32.
+#include "gb_common.cuh"
+#include "gb_geometry.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BP = 64;                 // pixels per stage (MMA K = 16 -> 4 MMAs per stage)
+constexpr int ATOM = BP * 128;         // one [64 px][64 ch] swizzled atom = 8 KB
+constexpr int LAG = 2;
+
+template <int BN>
+struct WCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 4;
+  static constexpr int P_BYTES = 2 * ATOM;
+  static constexpr int G_BYTES = (BN / 64) * ATOM;
+  static constexpr int STAGE_BYTES = P_BYTES + G_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 1024;
+  static constexpr int MIN_CTAS = (BN == 256) ? 1 : 2;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, WCfg<BN>::MIN_CTAS) igemm_wgrad_kernel(const __grid_constant__ gb_wgrad_params p,
+                                                                              int blocks_per_split) {
+  using C = WCfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int NG = BN / 64;  // gathered atoms per stage
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint8_t* tail = smem + STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 128);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int kt = blockIdx.x;           // column tile (kflat)
+  const int rt = blockIdx.y * BM;      // first row (plain channel)
+  const int64_t Mq = (int64_t)p.plain.N * p.plain.D * p.plain.H * p.plain.W;
+  const int nblk = (int)((Mq + BP - 1) / BP);
+  const int b0 = blockIdx.z * blocks_per_split;
+  const int b1 = min(nblk, b0 + blocks_per_split);
+  const int KB = b1 - b0;
+  if (KB <= 0) return;
+
+  const uint32_t full_bar = smem_u32(bars);
+  const uint32_t empty_bar = smem_u32(bars + STAGES);
+  const uint32_t accum_bar = smem_u32(bars + 2 * STAGES);
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 4);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<BN>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    const int j = tid & 7;
+    const int r0 = tid >> 3;  // pixel rows r0 + 16*i, i < 4
+    const int q[3] = {p.plain.D, p.plain.H, p.plain.W};
+    const __nv_bfloat16* pl = reinterpret_cast<const __nv_bfloat16*>(p.plain.ptr);
+    const __nv_bfloat16* ga = reinterpret_cast<const __nv_bfloat16*>(p.gathered.ptr);
+    // per-atom constants of the gathered operand: which tap / channel chunk this thread's column chunk is
+    const int C8 = p.gathered.C >> 3;
+    int g_toff[NG], g_d[NG];
+    bool g_ok[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const int k8 = kt * (BN / 8) + g * 8 + j;
+      const int tl = k8 / C8;
+      const int c8 = k8 - tl * C8;
+      g_ok[g] = tl < p.ntaps && (k8 * 8) < p.kpad;
+      int dz = 0, dy = 0, dx = 0;
+      if (g_ok[g]) {
+        dz = p.taps[tl][0];
+        dy = p.taps[tl][1];
+        dx = p.taps[tl][2];
+      }
+      g_toff[g] = (int)(dz * p.gathered.sz + dy * p.gathered.sy + dx * p.gathered.sx) + c8 * 8;
+      g_d[g] = ((dz & 0xFF) << 16) | ((dy & 0xFF) << 8) | (dx & 0xFF);
+    }
+    // plain operand: channel of this thread's chunk in each of the two atoms
+    int p_ch[2];
+    bool p_ok[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      p_ch[a] = rt + (a * 8 + j) * 8;
+      p_ok[a] = p_ch[a] < p.plain.C;
+    }
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % STAGES;
+      const int it = kb / STAGES;
+      if (it > 0) mbar_wait(empty_bar + 8 * s, (it - 1) & 1);
+      const uint32_t p_s = base + s * C::STAGE_BYTES;
+      const uint32_t g_s = p_s + C::P_BYTES;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int prow = r0 + 16 * i;
+        const int64_t m = (int64_t)(b0 + kb) * BP + prow;
+        const bool pix_ok = m < Mq;
+        int poff = 0, goff = 0, gz = 0, gy = -100000, gx = 0;
+        if (pix_ok) {
+          gb_row r = gb_decode_row(m, q);
+          poff = (int)gb_pix_offset(p.plain, r.n, r.qz, r.qy, r.qx);
+          gz = r.qz * p.mul[0];
+          gy = r.qy * p.mul[1];
+          gx = r.qx * p.mul[2];
+          goff = (int)gb_pix_offset(p.gathered, r.n, gz, gy, gx);
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const bool ok = pix_ok && p_ok[a];
+          cp_async16(p_s + a * ATOM + swz128(prow, j), ok ? pl + (poff + p_ch[a]) : pl, ok);
+        }
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const int dz = (int)(signed char)(g_d[g] >> 16), dy = (int)(signed char)(g_d[g] >> 8),
+                    dx = (int)(signed char)(g_d[g]);
+          const bool ok = pix_ok && g_ok[g] && gb_in_bounds(p.gathered, gz + dz, gy + dy, gx + dx);
+          cp_async16(g_s + g * ATOM + swz128(prow, j), ok ? ga + (goff + g_toff[g]) : ga, ok);
+        }
+      }
+      cp_async_commit();
+      if (kb >= LAG) {
+        cp_async_wait<LAG>();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar + 8 * ((kb - LAG) % STAGES));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      for (int kk = (KB > LAG ? KB - LAG : 0); kk < KB; ++kk) mbar_arrive(full_bar + 8 * (kk % STAGES));
+    }
+  } else if (warp == 4) {
+    constexpr uint32_t idesc = make_idesc_bf16(BN, 1, 1);
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % STAGES;
+      const int it = kb / STAGES;
+      mbar_wait(full_bar + 8 * s, it & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t p_s = base + s * C::STAGE_BYTES;
+        const uint32_t g_s = p_s + C::P_BYTES;
+        // MN-major: LBO = stride between 64-wide atoms, SBO = stride between groups of 8 pixels (k)
+        const uint64_t adesc = make_smem_desc(p_s, ATOM, 1024);
+        const uint64_t bdesc = make_smem_desc(g_s, ATOM, 1024);
+#pragma unroll
+        for (int k = 0; k < BP / 16; ++k)
+          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2048 / 16), bdesc + (uint64_t)(k * 2048 / 16), idesc,
+                    (kb | k) ? 1u : 0u);
+        umma_commit(empty_bar + 8 * s);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) umma_commit(accum_bar);
+    __syncwarp();
+  }
+
+  mbar_wait(accum_bar, 0);
+  tc_fence_after();
+  {
+    const int lg = warp & 3;
+    const int half = warp >> 2;
+    const int row = rt + lg * 32 + lane;
+    const bool row_ok = row < p.rows;
+    float* drow = p.dw + (int64_t)row * p.kpad + (int64_t)kt * BN;
+    const int cbeg = half * (BN / 2);
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 32) {
+      uint32_t acc[32];
+      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, acc);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (kt * BN + c0 + g * 4 < p.kpad)
+            red_add_v4(drow + c0 + g * 4, __uint_as_float(acc[g * 4 + 0]), __uint_as_float(acc[g * 4 + 1]),
+                       __uint_as_float(acc[g * 4 + 2]), __uint_as_float(acc[g * 4 + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<BN>(tmem_base);
+}
+
+template <int BN>
+int launch(const gb_wgrad_params& p, cudaStream_t st) {
+  using C = WCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GB_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  const int64_t Mq = (int64_t)p.plain.N * p.plain.D * p.plain.H * p.plain.W;
+  const int nblk = gb_cdiv(Mq, BP);
+  const int tiles = gb_cdiv(p.kpad, BN) * gb_cdiv(p.rows, BM);
+  int splits = p.splits;
+  if (splits <= 0) {
+    // fill ~2 waves of the 148 SMs, but keep at least 4 pixel blocks per CTA
+    splits = (2 * 148 + tiles - 1) / tiles;
+    if (splits > nblk / 4) splits = nblk / 4;
+    if (splits < 1) splits = 1;
+  }
+  const int bps = gb_cdiv(nblk, splits);
+  splits = gb_cdiv(nblk, bps);
+  dim3 grid(gb_cdiv(p.kpad, BN), gb_cdiv(p.rows, BM), splits);
+  igemm_wgrad_kernel<BN><<<grid, 256, C::SMEM, st>>>(p, bps);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int64_t view_max_offset(const gb_view& v) {
+  return (int64_t)(v.N - 1) * v.sn + (int64_t)(v.D - 1) * v.sz + (int64_t)(v.H - 1 + v.pad) * v.sy +
+         (int64_t)(v.W - 1 + v.pad) * v.sx + v.C;
+}
+
+}  // namespace
+
+extern "C" int gb_conv_wgrad(const gb_wgrad_params* pp, void* stream) {
+  const gb_wgrad_params& p = *pp;
+  GB_CHECK(p.plain.ptr && p.gathered.ptr && p.dw, "gb_conv_wgrad: null pointer");
+  GB_CHECK(p.plain.C % 8 == 0 && p.gathered.C % 8 == 0, "gb_conv_wgrad: channel counts must be multiples of 8");
+  GB_CHECK(p.kpad % 64 == 0 && p.ntaps * p.gathered.C <= p.kpad, "gb_conv_wgrad: bad kpad %d", p.kpad);
+  GB_CHECK(p.ntaps >= 1 && p.ntaps <= GB_MAX_TAPS, "gb_conv_wgrad: bad tap count %d", p.ntaps);
+  GB_CHECK(p.rows >= 1 && p.rows <= p.plain.C, "gb_conv_wgrad: bad row count %d", p.rows);
+  GB_CHECK(p.plain.N == p.gathered.N, "gb_conv_wgrad: batch mismatch");
+  GB_CHECK(view_max_offset(p.plain) < (1ll << 31) && view_max_offset(p.gathered) < (1ll << 31),
+           "gb_conv_wgrad: tensor too large for 32-bit offsets");
+  GB_CHECK(((uintptr_t)p.plain.ptr & 15) == 0 && ((uintptr_t)p.gathered.ptr & 15) == 0 && ((uintptr_t)p.dw & 15) == 0,
+           "gb_conv_wgrad: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  int bn = p.kpad >= 256 ? 256 : (p.kpad >= 128 ? 128 : 64);
+  if (g_gb_knobs[2] > 0) bn = g_gb_knobs[2];
+  switch (bn) {
+    case 64: return launch<64>(p, st);
+    case 128: return launch<128>(p, st);
+    case 256: return launch<256>(p, st);
+  }
+  GB_CHECK(false, "gb_conv_wgrad: bad tile width %d", bn);
+}

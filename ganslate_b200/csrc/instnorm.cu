@@ -1,0 +1,369 @@
+// InstanceNorm (affine=False) fused with the following activation / residual add, forward and backward,
+// on channels-last bf16 views.  HBM-bound: every kernel moves 16 bytes per thread per pixel, a warp covers
+// consecutive channels of the same pixel (coalesced 128..512 B), statistics are fp32.
+//
+// Forward:  gb_in_stats (sum, sum^2 per (n,c))  ->  gb_in_fwd (normalise + act + residual, also writes the
+//           reflection border of the destination so the next convolution needs no padding pass).
+// Backward: reduce (sum g, sum g*xhat) -> apply dx = rstd * (g - mean(g) - xhat * mean(g*xhat)).
+//           The incoming gradient may arrive on the padded domain (dgrad of a reflection-padded conv); the
+//           border is folded back onto the interior while it is read.
+#include "gb_common.cuh"
+#include "gb_geometry.h"
+
+namespace {
+
+struct Pix {
+  int z, y, x;
+};
+__device__ __forceinline__ Pix decode_pix(int64_t pix, const gb_view& v) {
+  Pix r;
+  r.x = (int)(pix % v.W);
+  pix /= v.W;
+  r.y = (int)(pix % v.H);
+  r.z = (int)(pix / v.H);
+  return r;
+}
+__device__ __forceinline__ void load8(const gb_view& v, int n, int z, int y, int x, int cg, float (&f)[8]) {
+  const __nv_bfloat16* ptr = reinterpret_cast<const __nv_bfloat16*>(v.ptr);
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(ptr + gb_pix_offset(v, n, z, y, x) + cg * 8));
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+__device__ __forceinline__ void store8(const gb_view& v, int n, int z, int y, int x, int cg, const uint4& o) {
+  __nv_bfloat16* ptr = reinterpret_cast<__nv_bfloat16*>(v.ptr);
+  *reinterpret_cast<uint4*>(ptr + gb_pix_offset(v, n, z, y, x) + cg * 8) = o;
+}
+// store to (y,x) and to every border position that reflects onto it
+__device__ __forceinline__ void store8_reflect(const gb_view& v, int n, int z, int y, int x, int cg, const uint4& o) {
+  const int p = v.pad;
+  int ys[3], xs[3], ny = 1, nx = 1;
+  ys[0] = y;
+  xs[0] = x;
+  if (p > 0) {
+    if (y >= 1 && y <= p) ys[ny++] = -y;
+    if (y <= v.H - 2 && y >= v.H - 1 - p) ys[ny++] = 2 * (v.H - 1) - y;
+    if (x >= 1 && x <= p) xs[nx++] = -x;
+    if (x <= v.W - 2 && x >= v.W - 1 - p) xs[nx++] = 2 * (v.W - 1) - x;
+  }
+  for (int a = 0; a < ny; ++a)
+    for (int b = 0; b < nx; ++b) store8(v, n, z, ys[a], xs[b], cg, o);
+}
+// gradient on the padded domain folded back to interior pixel (y,x)
+__device__ __forceinline__ void load8_fold(const gb_view& v, int n, int z, int y, int x, int cg, float (&f)[8]) {
+  const int p = v.pad;
+  int ys[3], xs[3], ny = 1, nx = 1;
+  ys[0] = y;
+  xs[0] = x;
+  if (p > 0) {
+    if (y >= 1 && y <= p) ys[ny++] = -y;
+    if (y <= v.H - 2 && y >= v.H - 1 - p) ys[ny++] = 2 * (v.H - 1) - y;
+    if (x >= 1 && x <= p) xs[nx++] = -x;
+    if (x <= v.W - 2 && x >= v.W - 1 - p) xs[nx++] = 2 * (v.W - 1) - x;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[e] = 0.f;
+  for (int a = 0; a < ny; ++a)
+    for (int b = 0; b < nx; ++b) {
+      float t[8];
+      load8(v, n, z, ys[a], xs[b], cg, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += t[e];
+    }
+}
+
+__device__ __forceinline__ float act_fwd(float v, int act, float slope) {
+  switch (act) {
+    case GB_ACT_RELU: return fmaxf(v, 0.f);
+    case GB_ACT_LEAKY:
+    case GB_ACT_PRELU: return v > 0.f ? v : v * slope;
+    case GB_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- statistics
+__global__ void in_stats_kernel(gb_view x, float* __restrict__ stats, int pix_per_block) {
+  extern __shared__ float red[];  // [slots][2C]
+  const int C8 = x.C >> 3;
+  const int slots = blockDim.x / C8;
+  const int cg = threadIdx.x % C8;
+  const int slot = threadIdx.x / C8;
+  const int n = blockIdx.y;
+  const int64_t P = (int64_t)x.D * x.H * x.W;
+  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p1 = min(P, p0 + pix_per_block);
+  float s[8], ss[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
+  if (slot < slots) {
+    for (int64_t pix = p0 + slot; pix < p1; pix += slots) {
+      const Pix q = decode_pix(pix, x);
+      float f[8];
+      load8(x, n, q.z, q.y, q.x, cg, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s[e] += f[e];
+        ss[e] += f[e] * f[e];
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      red[(slot * x.C + cg * 8 + e) * 2 + 0] = s[e];
+      red[(slot * x.C + cg * 8 + e) * 2 + 1] = ss[e];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * x.C; c += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < slots; ++k) t += red[k * 2 * x.C + c];
+    atomicAdd(stats + (int64_t)n * 2 * x.C + c, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- forward
+__global__ void in_fwd_kernel(const __grid_constant__ gb_in_fwd_params p, int pix_per_block) {
+  const gb_view& x = p.x;
+  const int C8 = x.C >> 3;
+  const int slots = blockDim.x / C8;
+  const int cg = threadIdx.x % C8;
+  const int slot = threadIdx.x / C8;
+  if (slot >= slots) return;
+  const int n = blockIdx.y;
+  const int64_t P = (int64_t)x.D * x.H * x.W;
+  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p1 = min(P, p0 + pix_per_block);
+  float mean[8], rstd[8], slope[8];
+  const float invP = 1.f / (float)P;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = cg * 8 + e;
+    if (p.stats) {
+      const float s = p.stats[((int64_t)n * x.C + c) * 2], ss = p.stats[((int64_t)n * x.C + c) * 2 + 1];
+      const float m = s * invP;
+      const float var = fmaxf(ss * invP - m * m, 0.f);
+      mean[e] = m;
+      rstd[e] = rsqrtf(var + p.eps);
+    } else {
+      mean[e] = 0.f;
+      rstd[e] = 1.f;
+    }
+    slope[e] = (p.act == GB_ACT_PRELU) ? p.prelu[c] : p.act_slope;
+  }
+  const bool has_res = p.res.ptr != nullptr;
+  for (int64_t pix = p0 + slot; pix < p1; pix += slots) {
+    const Pix q = decode_pix(pix, x);
+    float f[8], r[8];
+    load8(x, n, q.z, q.y, q.x, cg, f);
+    if (has_res) load8(p.res, n, q.z, q.y, q.x, cg, r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = (f[e] - mean[e]) * rstd[e];
+      if (has_res && p.res_before_act) v += r[e];
+      v = act_fwd(v, p.act, slope[e]);
+      if (has_res && !p.res_before_act) v += r[e];
+      f[e] = v;
+    }
+    const uint4 o = pack8(f);
+    if (p.y.pad > 0) store8_reflect(p.y, n, q.z, q.y, q.x, cg, o);
+    else store8(p.y, n, q.z, q.y, q.x, cg, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- backward
+// g = act'(.) * (dy_a + fold(dy_b));  MODE 0: reduce (sum g, sum g*xhat), optionally write dy_sum
+//                                     MODE 1: apply dx = rstd * (g - m1 - xhat*m2)
+template <int MODE>
+__global__ void in_bwd_kernel(const __grid_constant__ gb_in_bwd_params p, int pix_per_block) {
+  extern __shared__ float red[];
+  const gb_view& x = p.x;
+  const int C8 = x.C >> 3;
+  const int slots = blockDim.x / C8;
+  const int cg = threadIdx.x % C8;
+  const int slot = threadIdx.x / C8;
+  const int n = blockIdx.y;
+  const int64_t P = (int64_t)x.D * x.H * x.W;
+  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p1 = min(P, p0 + pix_per_block);
+  const bool norm = p.stats != nullptr;
+  float mean[8], rstd[8], slope[8], m1[8], m2[8], s1[8], s2[8], sp[8];
+  const float invP = 1.f / (float)P;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = cg * 8 + e;
+    mean[e] = 0.f; rstd[e] = 1.f; m1[e] = 0.f; m2[e] = 0.f; s1[e] = 0.f; s2[e] = 0.f; sp[e] = 0.f;
+    if (norm) {
+      const float s = p.stats[((int64_t)n * x.C + c) * 2], ss = p.stats[((int64_t)n * x.C + c) * 2 + 1];
+      const float m = s * invP;
+      mean[e] = m;
+      rstd[e] = rsqrtf(fmaxf(ss * invP - m * m, 0.f) + p.eps);
+      if (MODE == 1) {
+        m1[e] = p.bstats[((int64_t)n * x.C + c) * 2] * invP;
+        m2[e] = p.bstats[((int64_t)n * x.C + c) * 2 + 1] * invP;
+      }
+    }
+    slope[e] = (p.act == GB_ACT_PRELU) ? p.prelu[c] : p.act_slope;
+  }
+  const bool has_a = p.dy_a.ptr != nullptr, has_b = p.dy_b.ptr != nullptr;
+  const bool use_sum = MODE == 1 && p.dy_sum.ptr != nullptr && norm;  // reduce pass already materialised a+fold(b)
+  if (slot < slots) {
+    for (int64_t pix = p0 + slot; pix < p1; pix += slots) {
+      const Pix q = decode_pix(pix, x);
+      float g[8], xv[8], t[8];
+      if (use_sum) {
+        load8(p.dy_sum, n, q.z, q.y, q.x, cg, g);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] = 0.f;
+        if (has_a) {
+          load8(p.dy_a, n, q.z, q.y, q.x, cg, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[e] += t[e];
+        }
+        if (has_b) {
+          load8_fold(p.dy_b, n, q.z, q.y, q.x, cg, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[e] += t[e];
+        }
+        if (p.dy_sum.ptr != nullptr && (MODE == 0 || !norm)) store8(p.dy_sum, n, q.z, q.y, q.x, cg, pack8(g));
+      }
+      // activation derivative
+      if (norm) {
+        load8(x, n, q.z, q.y, q.x, cg, xv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xv[e] = (xv[e] - mean[e]) * rstd[e];  // xhat
+        if (p.act == GB_ACT_RELU || p.act == GB_ACT_LEAKY || p.act == GB_ACT_PRELU) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (!(xv[e] > 0.f)) {
+              if (MODE == 0 && p.act == GB_ACT_PRELU) sp[e] += g[e] * xv[e];
+              g[e] *= (p.act == GB_ACT_RELU) ? 0.f : slope[e];
+            }
+          }
+        }
+      } else {
+        // activation only: derivative from the forward OUTPUT y
+        if (p.act != GB_ACT_NONE) {
+          load8(p.y, n, q.z, q.y, q.x, cg, xv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (p.act == GB_ACT_TANH) g[e] *= (1.f - xv[e] * xv[e]);
+            else if (!(xv[e] > 0.f)) g[e] *= (p.act == GB_ACT_RELU) ? 0.f : slope[e];
+          }
+        }
+      }
+      if (MODE == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          s1[e] += g[e];
+          s2[e] += g[e] * xv[e];
+        }
+      } else {
+        float d[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] = norm ? rstd[e] * (g[e] - m1[e] - xv[e] * m2[e]) : g[e];
+        store8(p.dx, n, q.z, q.y, q.x, cg, pack8(d));
+      }
+    }
+  }
+  if (MODE == 0) {
+    if (slot < slots) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        red[(slot * x.C + cg * 8 + e) * 3 + 0] = s1[e];
+        red[(slot * x.C + cg * 8 + e) * 3 + 1] = s2[e];
+        red[(slot * x.C + cg * 8 + e) * 3 + 2] = sp[e];
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < x.C; c += blockDim.x) {
+      float a = 0.f, b = 0.f, d = 0.f;
+      for (int k = 0; k < slots; ++k) {
+        a += red[(k * x.C + c) * 3 + 0];
+        b += red[(k * x.C + c) * 3 + 1];
+        d += red[(k * x.C + c) * 3 + 2];
+      }
+      atomicAdd(p.bstats + ((int64_t)n * x.C + c) * 2 + 0, a);
+      atomicAdd(p.bstats + ((int64_t)n * x.C + c) * 2 + 1, b);
+      if (p.dprelu != nullptr) atomicAdd(p.dprelu + c, d);
+    }
+  }
+}
+
+struct Launch {
+  int threads, slots, ppb;
+  dim3 grid;
+};
+Launch plan(const gb_view& x) {
+  Launch L;
+  const int C8 = x.C / 8;
+  L.threads = 256;
+  if (C8 > 256) L.threads = ((C8 + 31) / 32) * 32;
+  L.slots = L.threads / C8;
+  const int64_t P = (int64_t)x.D * x.H * x.W;
+  // ~4 waves of 148 SMs x 4 resident blocks, but at least `slots` pixels (one pass) per block
+  int64_t blocks = (148 * 16 + x.N - 1) / x.N;
+  int64_t ppb = (P + blocks - 1) / blocks;
+  if (ppb < 4 * L.slots) ppb = 4 * L.slots;
+  L.ppb = (int)ppb;
+  L.grid = dim3((unsigned)((P + ppb - 1) / ppb), x.N);
+  return L;
+}
+
+bool same_extents(const gb_view& a, const gb_view& b) {
+  return a.N == b.N && a.D == b.D && a.H == b.H && a.W == b.W && a.C == b.C;
+}
+
+}  // namespace
+
+extern "C" int gb_in_stats(const gb_view* x, float* stats, void* stream) {
+  GB_CHECK(x && x->ptr && stats, "gb_in_stats: null pointer");
+  GB_CHECK(x->C % 8 == 0 && x->C <= 2048, "gb_in_stats: bad channel count %d", x->C);
+  Launch L = plan(*x);
+  in_stats_kernel<<<L.grid, L.threads, sizeof(float) * 2 * L.slots * x->C, (cudaStream_t)stream>>>(*x, stats, L.ppb);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gb_in_fwd(const gb_in_fwd_params* p, void* stream) {
+  GB_CHECK(p && p->x.ptr && p->y.ptr, "gb_in_fwd: null pointer");
+  GB_CHECK(p->x.C % 8 == 0 && p->x.C <= 2048, "gb_in_fwd: bad channel count %d", p->x.C);
+  GB_CHECK(same_extents(p->x, p->y), "gb_in_fwd: x/y extents differ");
+  GB_CHECK(p->res.ptr == nullptr || same_extents(p->x, p->res), "gb_in_fwd: residual extents differ");
+  GB_CHECK(p->act != GB_ACT_PRELU || p->prelu != nullptr, "gb_in_fwd: prelu slopes missing");
+  GB_CHECK(p->y.pad == 0 || (p->y.H > p->y.pad && p->y.W > p->y.pad), "gb_in_fwd: reflection border larger than image");
+  Launch L = plan(p->x);
+  in_fwd_kernel<<<L.grid, L.threads, 0, (cudaStream_t)stream>>>(*p, L.ppb);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gb_in_bwd(const gb_in_bwd_params* p, void* stream) {
+  GB_CHECK(p && p->x.ptr && p->dx.ptr, "gb_in_bwd: null pointer");
+  GB_CHECK(p->dy_a.ptr || p->dy_b.ptr, "gb_in_bwd: no incoming gradient");
+  GB_CHECK(p->x.C % 8 == 0 && p->x.C <= 2048, "gb_in_bwd: bad channel count %d", p->x.C);
+  GB_CHECK(same_extents(p->x, p->dx), "gb_in_bwd: x/dx extents differ");
+  GB_CHECK(p->dy_a.ptr == nullptr || same_extents(p->x, p->dy_a), "gb_in_bwd: dy_a extents differ");
+  GB_CHECK(p->dy_b.ptr == nullptr || same_extents(p->x, p->dy_b), "gb_in_bwd: dy_b extents differ");
+  GB_CHECK(p->stats == nullptr || p->bstats != nullptr, "gb_in_bwd: bstats workspace missing");
+  GB_CHECK(p->stats != nullptr || p->act == GB_ACT_NONE || p->y.ptr != nullptr, "gb_in_bwd: forward output missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  Launch L = plan(p->x);
+  if (p->stats != nullptr) {
+    in_bwd_kernel<0><<<L.grid, L.threads, sizeof(float) * 3 * L.slots * p->x.C, st>>>(*p, L.ppb);
+    GB_CUDA(cudaGetLastError());
+  }
+  in_bwd_kernel<1><<<L.grid, L.threads, 0, st>>>(*p, L.ppb);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,459 @@
+"""Host-side operators over the C ABI: channels-last bf16 buffers, convolution geometry, autograd glue.
+
+Activations inside a network are bf16 tensors of shape (N, D, H+2p, W+2p, C) -- "buffers" -- where p is a
+reflection border materialised by the kernel that produced the buffer and C is padded to a multiple of 8.
+A convolution that follows ReflectionPad(p) simply reads the whole buffer with padding 0, and its data
+gradient is a buffer of the same (padded) shape whose border is folded back by the consumer.
+"""
+import ctypes as C
+import itertools
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import (ACT_LEAKY, ACT_NONE, ACT_PRELU, ACT_RELU, ACT_TANH, ConvParams, InBwdParams, InFwdParams,
+                    PackParams, View, WgradParams)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"ganslate_b200: {what} must live on a CUDA device -- there is no CPU path "
+                           "(the CPU oracle lives under oracle/ and is test infrastructure only)")
+
+
+def pad8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+def make_view(t: torch.Tensor, pad: int = 0) -> View:
+    """View of the interior of a contiguous (N, D, Hb, Wb, C) bf16 buffer with reflection border `pad`."""
+    assert t.dim() == 5 and t.is_contiguous(), (t.shape, t.stride())
+    N, D, Hb, Wb, Cc = t.shape
+    v = View()
+    esz = t.element_size()
+    v.ptr = t.data_ptr() + ((pad * Wb + pad) * Cc) * esz
+    v.sn, v.sz, v.sy, v.sx = D * Hb * Wb * Cc, Hb * Wb * Cc, Wb * Cc, Cc
+    v.N, v.D, v.H, v.W, v.C, v.pad = N, D, Hb - 2 * pad, Wb - 2 * pad, Cc, pad
+    return v
+
+
+def null_view() -> View:
+    return View()
+
+
+@dataclass
+class DataSpec:
+    """Class/tap decomposition of one implicit GEMM (see gb_conv_params)."""
+    in_mul: Tuple[int, int, int]
+    out_mul: Tuple[int, int, int]
+    classes: List[dict]            # each: off(3), taps [(dz,dy,dx)], tap_ids [int]
+    # filled by finalize()
+    kpads: List[int] = field(default_factory=list)
+    w_offsets: List[int] = field(default_factory=list)
+    total_elems: int = 0
+
+    def finalize(self, chans_pad: int, rows_pad: int):
+        off = 0
+        self.kpads, self.w_offsets = [], []
+        for c in self.classes:
+            kp = max(64, (len(c["taps"]) * chans_pad + 63) // 64 * 64)
+            self.kpads.append(kp)
+            self.w_offsets.append(off)
+            off += rows_pad * kp
+        self.total_elems = off
+        ntaps = sum(len(c["taps"]) for c in self.classes)
+        if ntaps > _cabi.GB_MAX_TAPS:
+            raise ValueError(f"convolution needs {ntaps} taps, the C ABI allows {_cabi.GB_MAX_TAPS}")
+        if len(self.classes) > _cabi.GB_MAX_CLASSES:
+            raise ValueError("too many parity classes")
+
+
+def strided_spec(kernel, stride, padding) -> DataSpec:
+    """out[o] = sum_r in[o*s + r - p] W[r]  (forward convolution / data gradient of a transposed convolution)."""
+    taps, ids = [], []
+    for i, r in enumerate(itertools.product(*[range(k) for k in kernel])):
+        taps.append(tuple(r[d] - padding[d] for d in range(3)))
+        ids.append(i)
+    return DataSpec(tuple(stride), (1, 1, 1), [dict(off=(0, 0, 0), taps=taps, tap_ids=ids)])
+
+
+def transposed_spec(kernel, stride, padding) -> DataSpec:
+    """out[o] = sum_r in[(o + p - r)/s] W[r] where divisible (transposed convolution / data gradient of a
+    convolution), decomposed by output parity so no zero-insertion is ever multiplied."""
+    classes = []
+    for par in itertools.product(*[range(s) for s in stride]):
+        taps, ids = [], []
+        for i, r in enumerate(itertools.product(*[range(k) for k in kernel])):
+            ok = all((par[d] + padding[d] - r[d]) % stride[d] == 0 for d in range(3))
+            if ok:
+                taps.append(tuple((par[d] + padding[d] - r[d]) // stride[d] for d in range(3)))
+                ids.append(i)
+        classes.append(dict(off=par, taps=taps, tap_ids=ids))
+    return DataSpec((1, 1, 1), tuple(stride), classes)
+
+
+class ConvOp:
+    """Geometry + packed-weight cache + launch helpers of one (transposed) convolution layer.
+
+    Mirrors torch.nn.Conv{2,3}d / ConvTranspose{2,3}d semantics (weight layouts (Cout,Cin,k..) / (Cin,Cout,k..)),
+    which is what the reference builds its networks from (e.g. ganslate/nn/generators/resnet/resnet2d.py:24-57).
+    """
+
+    def __init__(self, cin, cout, kernel, stride, padding, transposed=False, output_padding=(0, 0, 0)):
+        self.cin, self.cout = cin, cout
+        self.kernel, self.stride, self.padding = tuple(kernel), tuple(stride), tuple(padding)
+        self.transposed, self.output_padding = transposed, tuple(output_padding)
+        self.cin_pad, self.cout_pad = pad8(cin), pad8(cout)
+        self.T = kernel[0] * kernel[1] * kernel[2]
+        if transposed:
+            self.fwd = transposed_spec(kernel, stride, padding)
+            self.dgrad = strided_spec(kernel, stride, padding)
+            # weight (Cin, Cout, T): fwd rows=cout, k-chans=cin ; dgrad rows=cin, k-chans=cout
+            self.fwd_strides = (self.T, cout * self.T, 1)
+            self.dgrad_strides = (cout * self.T, self.T, 1)
+        else:
+            self.fwd = strided_spec(kernel, stride, padding)
+            self.dgrad = transposed_spec(kernel, stride, padding)
+            # weight (Cout, Cin, T)
+            self.fwd_strides = (cin * self.T, self.T, 1)
+            self.dgrad_strides = (self.T, cin * self.T, 1)
+        self.fwd_rows_pad = (cout + 15) // 16 * 16
+        self.dgrad_rows_pad = (cin + 15) // 16 * 16
+        self.fwd.finalize(self.cin_pad, self.fwd_rows_pad)
+        self.dgrad.finalize(self.cout_pad, self.dgrad_rows_pad)
+        # wgrad: rows come from the "plain" tensor, columns (tap, c) from the gathered one
+        self.wg_taps = [tuple(r[d] - padding[d] for d in range(3))
+                        for r in itertools.product(*[range(k) for k in kernel])]
+        if self.T > _cabi.GB_MAX_TAPS:
+            raise ValueError("kernel too large")
+        g_pad = self.cout_pad if transposed else self.cin_pad
+        self.wg_kpad = max(64, (self.T * g_pad + 63) // 64 * 64)
+        self.wg_rows = cin if transposed else cout
+        self.wg_rows_pad = (self.wg_rows + 127) // 128 * 128
+        self._packed = {}
+
+    # ------------------------------------------------------------------ shapes
+    def out_extent(self, ext):
+        o = []
+        for d in range(3):
+            if self.transposed:
+                o.append((ext[d] - 1) * self.stride[d] - 2 * self.padding[d] + self.kernel[d] + self.output_padding[d])
+            else:
+                o.append((ext[d] + 2 * self.padding[d] - self.kernel[d]) // self.stride[d] + 1)
+        return tuple(o)
+
+    # ------------------------------------------------------------------ packing
+    def packed(self, weight: torch.Tensor, which: str) -> torch.Tensor:
+        key = (which, weight.data_ptr(), weight._version, weight.device)
+        hit = self._packed.get(which)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        spec = self.fwd if which == "fwd" else self.dgrad
+        rows, rows_pad = (self.cout, self.fwd_rows_pad) if which == "fwd" else (self.cin, self.dgrad_rows_pad)
+        chans, chans_pad = (self.cin, self.cin_pad) if which == "fwd" else (self.cout, self.cout_pad)
+        sn, sc, st = self.fwd_strides if which == "fwd" else self.dgrad_strides
+        dst = hit[1] if hit is not None else torch.empty(spec.total_elems, dtype=torch.bfloat16, device=weight.device)
+        w = weight.detach()
+        assert w.is_contiguous() and w.dtype == torch.float32
+        p = PackParams()
+        p.src, p.dst = w.data_ptr(), dst.data_ptr()
+        p.sn, p.sc, p.st = sn, sc, st
+        p.rows, p.rows_pad, p.chans, p.chans_pad = rows, rows_pad, chans, chans_pad
+        p.nclass = len(spec.classes)
+        tb = 0
+        for i, c in enumerate(spec.classes):
+            p.ntaps[i], p.kpad[i], p.w_offset[i], p.tap_begin[i] = len(c["taps"]), spec.kpads[i], spec.w_offsets[i], tb
+            for j, t in enumerate(c["tap_ids"]):
+                p.tap_id[tb + j] = t
+            tb += len(c["taps"])
+        _cabi.check(_cabi.lib().gb_pack_weights(C.byref(p), _stream()), "gb_pack_weights")
+        self._packed[which] = (key, dst)
+        return dst
+
+    # ------------------------------------------------------------------ launches
+    def _fill(self, spec: DataSpec, p: ConvParams):
+        p.nclass = len(spec.classes)
+        tb = 0
+        for i, c in enumerate(spec.classes):
+            k = p.cls[i]
+            k.off[0], k.off[1], k.off[2] = c["off"]
+            k.ntaps, k.tap_begin, k.kpad, k.w_offset = len(c["taps"]), tb, spec.kpads[i], spec.w_offsets[i]
+            for j, t in enumerate(c["taps"]):
+                p.taps[tb + j][0], p.taps[tb + j][1], p.taps[tb + j][2] = t
+            tb += len(c["taps"])
+        for d in range(3):
+            p.in_mul[d], p.out_mul[d] = spec.in_mul[d], spec.out_mul[d]
+
+    def _params(self, which):
+        cache = self.__dict__.setdefault("_ptemplates", {})
+        if which not in cache:
+            p = ConvParams()
+            self._fill(self.fwd if which == "fwd" else self.dgrad, p)
+            cache[which] = p
+        return cache[which]
+
+    def run_fwd(self, x, weight, bias, act=ACT_NONE, slope=0.0):
+        """x: plain buffer (N,D,H,W,cin_pad) -> (N,D,Ho,Wo,cout_pad)."""
+        N, D, H, W, Cc = x.shape
+        assert Cc == self.cin_pad, (Cc, self.cin_pad)
+        od, oh, ow = self.out_extent((D, H, W))
+        y = torch.empty((N, od, oh, ow, self.cout_pad), dtype=torch.bfloat16, device=x.device)
+        p = self._params("fwd")
+        p.inp, p.out = make_view(x), make_view(y)
+        wp = self.packed(weight, "fwd")
+        p.wpacked = wp.data_ptr()
+        p.bias = bias.data_ptr() if bias is not None else None
+        p.ncols, p.npad = self.cout, self.fwd_rows_pad
+        p.act, p.act_slope = act, slope
+        _cabi.check(_cabi.lib().gb_conv_data(C.byref(p), _stream()), "gb_conv_data(fwd)")
+        return y
+
+    def run_dgrad(self, dy, weight, in_shape):
+        """dy: (N,D,Ho,Wo,cout_pad) -> gradient wrt the input buffer, shape in_shape."""
+        dx = torch.empty(in_shape, dtype=torch.bfloat16, device=dy.device)
+        p = self._params("dgrad")
+        p.inp, p.out = make_view(dy), make_view(dx)
+        wp = self.packed(weight, "dgrad")
+        p.wpacked = wp.data_ptr()
+        p.bias = None
+        p.ncols, p.npad = self.cin, self.dgrad_rows_pad
+        p.act, p.act_slope = ACT_NONE, 0.0
+        _cabi.check(_cabi.lib().gb_conv_data(C.byref(p), _stream()), "gb_conv_data(dgrad)")
+        return dx
+
+    def run_wgrad(self, x, dy, weight_shape):
+        """fp32 weight gradient in the PyTorch layout of `weight_shape`."""
+        plain, gathered = (x, dy) if self.transposed else (dy, x)
+        ws = torch.zeros((self.wg_rows_pad, self.wg_kpad), dtype=torch.float32, device=x.device)
+        cache = self.__dict__.setdefault("_ptemplates", {})
+        p = cache.get("wgrad")
+        if p is None:
+            p = WgradParams()
+            p.ntaps = self.T
+            for j, t in enumerate(self.wg_taps):
+                p.taps[j][0], p.taps[j][1], p.taps[j][2] = t
+            for d in range(3):
+                p.mul[d] = self.stride[d]
+            p.rows, p.kpad, p.splits = self.wg_rows, self.wg_kpad, 0
+            cache["wgrad"] = p
+        p.plain, p.gathered, p.dw = make_view(plain), make_view(gathered), ws.data_ptr()
+        _cabi.check(_cabi.lib().gb_conv_wgrad(C.byref(p), _stream()), "gb_conv_wgrad")
+        dw = torch.empty(weight_shape, dtype=torch.float32, device=x.device)
+        cols = self.cout if self.transposed else self.cin
+        cols_pad = self.cout_pad if self.transposed else self.cin_pad
+        _cabi.check(_cabi.lib().gb_unpack_wgrad(ws.data_ptr(), dw.data_ptr(), cols * self.T, self.T, 1, self.wg_rows, cols,
+                                                cols_pad, self.T, self.wg_kpad, _stream()), "gb_unpack_wgrad")
+        return dw
+
+
+def colsum(t: torch.Tensor, n: int) -> torch.Tensor:
+    out = torch.empty(t.shape[-1], dtype=torch.float32, device=t.device)
+    v = make_view(t)
+    _cabi.check(_cabi.lib().gb_colsum(C.byref(v), out.data_ptr(), _stream()), "gb_colsum")
+    return out[:n]
+
+
+def act_backward(dy: torch.Tensor, y: torch.Tensor, act: int, slope: float) -> torch.Tensor:
+    """dx = dy * act'(.) computed from the forward output y (epilogue activations: tanh / leaky)."""
+    dx = torch.empty_like(y)
+    p = InBwdParams()
+    p.x, p.y, p.dy_a, p.dx = make_view(y), make_view(y), make_view(dy), make_view(dx)
+    p.act, p.act_slope, p.eps = act, slope, 1e-5
+    _cabi.check(_cabi.lib().gb_in_bwd(C.byref(p), _stream()), "gb_in_bwd(act)")
+    return dx
+
+
+class ConvFn(torch.autograd.Function):
+    """y = act(conv(x) + b) on channels-last bf16 buffers; backward = dgrad / wgrad / bias colsum kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, op: ConvOp, act, slope):
+        _require_cuda(x, "convolution input")
+        x = x.contiguous()
+        y = op.run_fwd(x, weight, bias, act, slope)
+        ctx.op, ctx.act, ctx.slope = op, act, slope
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        op = ctx.op
+        dy = dy.contiguous()
+        if ctx.act != ACT_NONE:
+            dy = act_backward(dy, y, ctx.act, ctx.slope)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = op.run_dgrad(dy, weight, x.shape)
+        if ctx.needs_input_grad[1]:
+            dw = op.run_wgrad(x, dy, weight.shape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy, op.cout)
+        return dx, dw, db, None, None, None
+
+
+class NormActFn(torch.autograd.Function):
+    """buffer = reflect_border( act(instance_norm(raw)) [+ residual] ).
+
+    norm=False degenerates to activation / copy-with-border. Replaces nn.InstanceNorm + nn.ReLU/LeakyReLU (+ the
+    residual add of ResidualBlock, ganslate/nn/generators/resnet/resnet2d.py:93) and the following nn.ReflectionPad2d.
+    """
+
+    @staticmethod
+    def forward(ctx, raw, residual, norm, act, slope, out_pad, res_pad, eps):
+        _require_cuda(raw, "normalisation input")
+        raw = raw.contiguous()
+        N, D, H, W, Cc = raw.shape
+        lib = _cabi.lib()
+        stats = None
+        xv = make_view(raw)
+        if norm:
+            stats = torch.zeros((N, Cc, 2), dtype=torch.float32, device=raw.device)
+            _cabi.check(lib.gb_in_stats(C.byref(xv), stats.data_ptr(), _stream()), "gb_in_stats")
+        out = torch.empty((N, D, H + 2 * out_pad, W + 2 * out_pad, Cc), dtype=torch.bfloat16, device=raw.device)
+        p = InFwdParams()
+        p.x, p.y = xv, make_view(out, out_pad)
+        if residual is not None:
+            p.res = make_view(residual, res_pad)
+        p.stats = stats.data_ptr() if norm else None
+        p.eps, p.act, p.act_slope, p.res_before_act = eps, act, slope, 0
+        _cabi.check(lib.gb_in_fwd(C.byref(p), _stream()), "gb_in_fwd")
+        ctx.cfg = (norm, act, slope, out_pad, res_pad, eps)
+        ctx.res_shape = residual.shape if residual is not None else None
+        ctx.save_for_backward(raw, stats, out if (not norm and act != ACT_NONE) else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        raw, stats, out = ctx.saved_tensors
+        norm, act, slope, out_pad, res_pad, eps = ctx.cfg
+        dout = dout.contiguous()
+        lib = _cabi.lib()
+        N, D, H, W, Cc = raw.shape
+        p = InBwdParams()
+        p.x = make_view(raw)
+        p.dy_b = make_view(dout, out_pad)
+        dres = None
+        if ctx.res_shape is not None and ctx.needs_input_grad[1]:
+            dres = torch.zeros(ctx.res_shape, dtype=torch.bfloat16, device=raw.device)
+            p.dy_sum = make_view(dres, res_pad)
+        draw = None
+        if ctx.needs_input_grad[0]:
+            draw = torch.empty_like(raw)
+            p.dx = make_view(draw)
+            if norm:
+                bstats = torch.zeros((N, Cc, 2), dtype=torch.float32, device=raw.device)
+                p.stats, p.bstats = stats.data_ptr(), bstats.data_ptr()
+            elif act != ACT_NONE:
+                p.y = make_view(out, out_pad)
+            p.eps, p.act, p.act_slope = eps, act, slope
+            _cabi.check(lib.gb_in_bwd(C.byref(p), _stream()), "gb_in_bwd")
+        elif dres is not None:
+            # only the residual branch needs a gradient: fold the border into a scratch dx-less pass
+            scratch = torch.empty_like(raw)
+            p.dx = make_view(scratch)
+            p.act, p.eps = ACT_NONE, eps
+            _cabi.check(lib.gb_in_bwd(C.byref(p), _stream()), "gb_in_bwd(res)")
+        return draw, dres, None, None, None, None, None, None
+
+
+class ToChannelsLastFn(torch.autograd.Function):
+    """NC(D)HW fp32 -> bf16 buffer with reflection border `pad` (cyclegan.py:89-90 hands NCHW fp32 to the nets)."""
+
+    @staticmethod
+    def forward(ctx, x, pad):
+        _require_cuda(x, "network input")
+        x = x.contiguous().float()
+        if x.dim() == 4:
+            N, Cc, H, W = x.shape
+            D = 1
+        else:
+            N, Cc, D, H, W = x.shape
+        out = torch.empty((N, D, H + 2 * pad, W + 2 * pad, pad8(Cc)), dtype=torch.bfloat16, device=x.device)
+        v = make_view(out, pad)
+        _cabi.check(_cabi.lib().gb_nchw_to_cl(x.data_ptr(), Cc, C.byref(v), _stream()), "gb_nchw_to_cl")
+        ctx.pad, ctx.shape = pad, x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        dx = torch.empty(ctx.shape, dtype=torch.float32, device=dout.device)
+        v = make_view(dout, ctx.pad)
+        _cabi.check(_cabi.lib().gb_cl_to_nchw(C.byref(v), dx.data_ptr(), ctx.shape[1], 1, _stream()), "gb_cl_to_nchw")
+        return dx, None
+
+
+class FromChannelsLastFn(torch.autograd.Function):
+    """bf16 plain buffer (N,D,H,W,Cpad) -> NC(D)HW fp32 with the first `channels` channels."""
+
+    @staticmethod
+    def forward(ctx, x, channels, is_3d):
+        x = x.contiguous()
+        N, D, H, W, Cc = x.shape
+        shape = (N, channels, D, H, W) if is_3d else (N, channels, H, W)
+        out = torch.empty(shape, dtype=torch.float32, device=x.device)
+        v = make_view(x)
+        _cabi.check(_cabi.lib().gb_cl_to_nchw(C.byref(v), out.data_ptr(), channels, 0, _stream()), "gb_cl_to_nchw")
+        ctx.in_shape, ctx.channels = x.shape, channels
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous().float()
+        dx = torch.empty(ctx.in_shape, dtype=torch.bfloat16, device=dout.device)
+        v = make_view(dx)
+        _cabi.check(_cabi.lib().gb_nchw_to_cl(dout.data_ptr(), ctx.channels, C.byref(v), _stream()), "gb_nchw_to_cl")
+        return dx, None, None
+
+
+class MseConstFn(torch.autograd.Function):
+    """mean((pred - target)^2) with the gradient produced in the same pass (adversarial_loss.py:60-62)."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        _require_cuda(pred, "prediction")
+        pred = pred.contiguous().float()
+        loss = torch.zeros((), dtype=torch.float32, device=pred.device)
+        grad = torch.empty_like(pred) if ctx.needs_input_grad[0] else None
+        _cabi.check(_cabi.lib().gb_mse_const(pred.data_ptr(), float(target), pred.numel(), loss.data_ptr(),
+                                             grad.data_ptr() if grad is not None else None, _stream()), "gb_mse_const")
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad,) = ctx.saved_tensors
+        return (grad * dloss if grad is not None else None), None
+
+
+class L1Fn(torch.autograd.Function):
+    """mean(|a - b|), gradient wrt a produced in the same pass (cyclegan_losses.py:64,73)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        _require_cuda(a, "L1 operand")
+        a = a.contiguous().float()
+        b = b.contiguous().float()
+        loss = torch.zeros((), dtype=torch.float32, device=a.device)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        grad = torch.empty_like(a) if need else None
+        _cabi.check(_cabi.lib().gb_l1(a.data_ptr(), b.data_ptr(), a.numel(), loss.data_ptr(),
+                                      grad.data_ptr() if grad is not None else None, _stream()), "gb_l1")
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad,) = ctx.saved_tensors
+        if grad is None:
+            return None, None
+        g = grad * dloss
+        return (g if ctx.needs_input_grad[0] else None), (-g if ctx.needs_input_grad[1] else None)

@@ -1,0 +1,188 @@
+/*
+ * ganslate_b200 -- C ABI of the B200 (sm_100a) hot path.
+ *
+ * The reference (ganslate-team/ganslate) is pure Python/PyTorch and has no FFI
+ * of its own: every hot-path op is a torch.nn library call that dispatches to
+ * cuDNN / ATen.  Each entry point below therefore cites the reference call
+ * site whose library call it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C: raw device pointers + sizes, no torch types.
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as
+ *     void*); no implicit synchronisation, no default-stream use.
+ *   - the library owns no device memory: outputs, workspaces and saved
+ *     statistics are allocated by the caller.
+ *   - return 0 on success, non-zero on error; gb_last_error() returns a
+ *     thread-local message.  Nothing throws across the ABI.
+ *   - activations are channels-last (N, D, H, W, C) bf16 "views": pointer to
+ *     the interior origin + element strides, so that a reflection-padded
+ *     buffer and its interior are the same allocation.  C is the physical
+ *     channel count (multiple of 8); channel stride is 1.
+ */
+#ifndef GANSLATE_B200_H
+#define GANSLATE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB_VERSION 100
+#define GB_MAX_TAPS 128
+#define GB_MAX_CLASSES 8
+
+/* channels-last bf16 (or fp32 where stated) tensor view */
+typedef struct gb_view {
+  void* ptr;                 /* element (n=0,z=0,y=0,x=0,c=0) of the interior */
+  int64_t sn, sz, sy, sx;    /* element strides; channel stride is 1 */
+  int32_t N, D, H, W, C;     /* interior extents; C = physical channels (%8==0) */
+  int32_t pad;               /* reflection border (in y and x) materialised around the interior */
+} gb_view;
+
+enum { GB_ACT_NONE = 0, GB_ACT_RELU = 1, GB_ACT_LEAKY = 2, GB_ACT_TANH = 3, GB_ACT_PRELU = 4 };
+
+/* One parity class of an implicit-GEMM "data" convolution.
+ * Rows of the GEMM enumerate a q-grid (n,qz,qy,qx); the output pixel is
+ * q*out_mul + off, the gathered input pixel for tap t is q*in_mul + d[t]. */
+typedef struct gb_conv_class {
+  int32_t off[3];            /* output offset (z,y,x) of this class */
+  int32_t ntaps;             /* taps contributing to this class */
+  int32_t tap_begin;         /* first entry in gb_conv_params.taps */
+  int32_t kpad;              /* padded K (multiple of 64) of this class' weight matrix */
+  int64_t w_offset;          /* element offset of the class matrix inside wpacked */
+} gb_conv_class;
+
+/* Implicit-GEMM convolution on tcgen05 tensor cores.
+ *   out[q*out_mul+off][n] = act( sum_{t,c} in[q*in_mul + d_t][c] * W[n][t][c] + bias[n] )
+ * Replaces: torch.nn.Conv2d/Conv3d forward (ganslate/nn/generators/resnet/resnet2d.py:24-35,81-86,
+ * ganslate/nn/discriminators/patchgan/patchgan2d.py:29-62, patchgan3d.py:28-61,
+ * ganslate/nn/generators/vnet/vnet3d.py:158-266), torch.nn.ConvTranspose2d/3d forward
+ * (resnet2d.py:52-57, vnet3d.py:224-228) and the autograd data-gradient of each (cuDNN
+ * bwd-data), which are the same implicit GEMM with the roles of Cin/Cout swapped. */
+typedef struct gb_conv_params {
+  gb_view in;                /* gathered operand (bf16) */
+  gb_view out;               /* destination (bf16) */
+  const void* wpacked;       /* bf16, per class [npad][kpad], K index = tap_local*in.C + c */
+  const float* bias;         /* [ncols] fp32 or NULL */
+  int32_t ncols;             /* real output channels (<= out.C) */
+  int32_t npad;              /* rows of each packed class matrix (multiple of 16) */
+  int32_t in_mul[3];         /* gather multiplier (z,y,x): conv stride, or 1 for class-decomposed */
+  int32_t out_mul[3];        /* output multiplier: 1, or the stride for class-decomposed */
+  int32_t nclass;
+  gb_conv_class cls[GB_MAX_CLASSES];
+  int8_t taps[GB_MAX_TAPS][4]; /* (dz,dy,dx,unused) */
+  int32_t act;               /* GB_ACT_NONE / GB_ACT_TANH / GB_ACT_LEAKY applied in the epilogue */
+  float act_slope;
+} gb_conv_params;
+
+int gb_conv_data(const gb_conv_params* p, void* stream);
+
+/* Weight-gradient implicit GEMM (tcgen05, both operands MN-major, split over pixels).
+ *   dw[r][t*gathered.C + c] += sum_q plain[q][r] * gathered[q*mul + d_t][c]
+ * dw is fp32 [rows_pad][kpad], accumulated with red.global.add -- zero it first.
+ * Replaces the autograd weight-gradient (cuDNN bwd-filter) of every conv above. */
+typedef struct gb_wgrad_params {
+  gb_view plain;             /* rows of dw come from its channels; its extents are the q-grid */
+  gb_view gathered;
+  float* dw;                 /* fp32 [rows_pad][kpad] */
+  int32_t rows;              /* real rows (plain channels used) */
+  int32_t kpad;              /* multiple of 64 */
+  int32_t ntaps;
+  int32_t mul[3];
+  int8_t taps[GB_MAX_TAPS][4];
+  int32_t splits;            /* 0 = choose */
+} gb_wgrad_params;
+
+int gb_conv_wgrad(const gb_wgrad_params* p, void* stream);
+
+/* Pack fp32 weights into the bf16 class matrices gb_conv_data reads.
+ * dst[cls][n][tl][c] = src[n*sn + c*sc + tap_id[cls][tl]*st] (zero padded).
+ * Replaces nothing in the reference (cuDNN consumes the fp32 weights directly). */
+typedef struct gb_pack_params {
+  const float* src;
+  void* dst;                 /* bf16 */
+  int64_t sn, sc, st;        /* strides of (row, k-channel, tap) in src */
+  int32_t rows, rows_pad;    /* real / padded rows */
+  int32_t chans, chans_pad;  /* real / padded k-channels (chans_pad = gathered view C) */
+  int32_t nclass;
+  int32_t ntaps[GB_MAX_CLASSES];
+  int32_t kpad[GB_MAX_CLASSES];
+  int64_t w_offset[GB_MAX_CLASSES];
+  int32_t tap_begin[GB_MAX_CLASSES];
+  int32_t tap_id[GB_MAX_TAPS]; /* source tap index of each (class-local) tap */
+} gb_pack_params;
+
+int gb_pack_weights(const gb_pack_params* p, void* stream);
+
+/* dst[r*dsr + c*dsc + t*dst_t] = scale * dw[r][t*chans_pad + c]   (fp32 -> fp32, PyTorch layout) */
+int gb_unpack_wgrad(const float* dw, float* dst, int64_t dsr, int64_t dsc, int64_t dst_t, int rows,
+                    int chans, int chans_pad, int ntaps, int kpad, void* stream);
+
+/* per-channel sum over all pixels of a bf16 view -> fp32 out[C] (bias gradients). out is overwritten. */
+int gb_colsum(const gb_view* x, float* out, void* stream);
+
+/* ---- InstanceNorm (+activation, +residual), HBM-bound --------------------------------------
+ * Replaces torch.nn.InstanceNorm2d/3d (affine=False, eps=1e-5; selected at ganslate/nn/utils.py:53-68)
+ * and the following nn.ReLU / nn.LeakyReLU(0.2) / nn.PReLU / residual add
+ * (resnet2d.py:26-27,36-37,83-87,93; patchgan2d.py:45-46,58-59; vnet3d.py:160-168,193-203). */
+
+/* stats[n][c] = (sum x, sum x^2) in fp32; stats must be zeroed by the caller. */
+int gb_in_stats(const gb_view* x, float* stats, void* stream);
+
+typedef struct gb_in_fwd_params {
+  gb_view x;                 /* raw conv output (bf16) */
+  gb_view y;                 /* destination; if y.pad>0 the reflected border is written as well */
+  gb_view res;               /* optional residual added AFTER the activation (ptr==NULL: none) */
+  const float* stats;        /* [N][C][2] from gb_in_stats; NULL = no normalisation (activation only) */
+  const float* prelu;        /* [C] slopes for GB_ACT_PRELU */
+  float eps;
+  int32_t act;
+  float act_slope;
+  int32_t res_before_act;    /* 1: y = act(norm(x) + res)  (V-Net), 0: y = act(norm(x)) + res */
+} gb_in_fwd_params;
+
+int gb_in_fwd(const gb_in_fwd_params* p, void* stream);
+
+typedef struct gb_in_bwd_params {
+  gb_view x;                 /* raw conv output saved by forward (bf16) */
+  gb_view y;                 /* forward output (needed for tanh / no-norm activations), may be NULL ptr */
+  gb_view dy_a;              /* gradient wrt y, plain view (ptr NULL: absent) */
+  gb_view dy_b;              /* gradient wrt the reflection-PADDED y (pad>0: border folded in); ptr NULL: absent */
+  gb_view dy_sum;            /* optional: dy_a + fold(dy_b) is written here (residual chain); ptr NULL: skip */
+  gb_view dx;                /* gradient wrt x (bf16) */
+  const float* stats;        /* forward stats; NULL = no normalisation */
+  float* bstats;             /* [N][C][2] workspace (sum g, sum g*xhat), zeroed by caller */
+  const float* prelu;
+  float* dprelu;             /* [C] fp32 accumulated (zeroed by caller) or NULL */
+  float eps;
+  int32_t act;
+  float act_slope;
+} gb_in_bwd_params;
+
+/* two launches: reduction then apply */
+int gb_in_bwd(const gb_in_bwd_params* p, void* stream);
+
+/* ---- layout conversion at the network boundary (set_input / module outputs; cyclegan.py:89-90) ---- */
+/* NC(D)HW fp32 -> channels-last bf16 view (zero-fills padded channels, writes reflected border if dst.pad>0) */
+int gb_nchw_to_cl(const float* src, int C, const gb_view* dst, void* stream);
+/* channels-last bf16 view (border folded in when src.pad>0 and fold!=0) -> NC(D)HW fp32 */
+int gb_cl_to_nchw(const gb_view* src, float* dst, int C, int fold, void* stream);
+
+/* ---- losses --------------------------------------------------------------------------------
+ * LSGAN: mean((p - t)^2) (ganslate/nn/losses/adversarial_loss.py:29,60-62); grad = 2(p-t)/n.
+ * L1: mean(|a-b|) (ganslate/nn/losses/cyclegan_losses.py:64,73,97; pix2pix_losses.py:15); grad = sign(a-b)/n.
+ * loss is a single fp32 (zeroed by the caller); grad may be NULL. */
+int gb_mse_const(const float* pred, float target, int64_t n, float* loss, float* grad, void* stream);
+int gb_l1(const float* a, const float* b, int64_t n, float* loss, float* grad_a, void* stream);
+
+/* ---- misc ---- */
+int gb_version(void);
+const char* gb_last_error(void);
+/* debug knobs for bring-up (e.g. descriptor variants); returns previous value */
+int gb_debug_knob(int knob, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
