@@ -19,7 +19,7 @@ __device__ __forceinline__ void reflect_targets(const gb_view& v, int y, int x, 
   }
 }
 
-__global__ void nchw_to_cl_kernel(const float* __restrict__ src, int C, gb_view dst) {
+__global__ void nchw_to_cl_kernel(const float* __restrict__ src, int C, gb_view dst, gb_view pre) {
   const int64_t P = (int64_t)dst.D * dst.H * dst.W;
   const int64_t total = (int64_t)dst.N * P;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(dst.ptr);
@@ -38,6 +38,16 @@ __global__ void nchw_to_cl_kernel(const float* __restrict__ src, int C, gb_view 
         const int c = cg * 8 + e;
         f[e] = c < C ? __ldg(src + ((int64_t)n * C + c) * P + pix) : 0.f;
       }
+      if (pre.ptr != nullptr) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(pre.ptr) +
+                                                             gb_pix_offset(pre, n, z, y, x) + cg * 8));
+        float2 t;
+        float th;
+        t = unpack_bf16x2(u.x); th = tanhf(t.x); f[0] *= 1.f - th * th; th = tanhf(t.y); f[1] *= 1.f - th * th;
+        t = unpack_bf16x2(u.y); th = tanhf(t.x); f[2] *= 1.f - th * th; th = tanhf(t.y); f[3] *= 1.f - th * th;
+        t = unpack_bf16x2(u.z); th = tanhf(t.x); f[4] *= 1.f - th * th; th = tanhf(t.y); f[5] *= 1.f - th * th;
+        t = unpack_bf16x2(u.w); th = tanhf(t.x); f[6] *= 1.f - th * th; th = tanhf(t.y); f[7] *= 1.f - th * th;
+      }
       uint4 o;
       o.x = pack_bf16x2(f[0], f[1]);
       o.y = pack_bf16x2(f[2], f[3]);
@@ -50,7 +60,7 @@ __global__ void nchw_to_cl_kernel(const float* __restrict__ src, int C, gb_view 
   }
 }
 
-__global__ void cl_to_nchw_kernel(gb_view src, float* __restrict__ dst, int C, int fold) {
+__global__ void cl_to_nchw_kernel(gb_view src, float* __restrict__ dst, int C, int fold, int act) {
   const int64_t P = (int64_t)src.D * src.H * src.W;
   const int64_t total = (int64_t)src.N * P;
   const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(src.ptr);
@@ -78,7 +88,7 @@ __global__ void cl_to_nchw_kernel(gb_view src, float* __restrict__ dst, int C, i
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int c = cg * 8 + e;
-        if (c < C) dst[((int64_t)n * C + c) * P + pix] = f[e];
+        if (c < C) dst[((int64_t)n * C + c) * P + pix] = (act == GB_ACT_TANH) ? tanhf(f[e]) : f[e];
       }
     }
   }
@@ -86,7 +96,7 @@ __global__ void cl_to_nchw_kernel(gb_view src, float* __restrict__ dst, int C, i
 
 }  // namespace
 
-extern "C" int gb_nchw_to_cl(const float* src, int C, const gb_view* dst, void* stream) {
+extern "C" int gb_nchw_to_cl(const float* src, int C, const gb_view* dst, const gb_view* pre, void* stream) {
   GB_CHECK(src && dst && dst->ptr, "gb_nchw_to_cl: null pointer");
   GB_CHECK(dst->C % 8 == 0 && C <= dst->C && C >= 1, "gb_nchw_to_cl: bad channel counts %d -> %d", C, dst->C);
   GB_CHECK(dst->pad == 0 || (dst->H > dst->pad && dst->W > dst->pad), "gb_nchw_to_cl: border larger than image");
@@ -94,19 +104,21 @@ extern "C" int gb_nchw_to_cl(const float* src, int C, const gb_view* dst, void* 
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  nchw_to_cl_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, C, *dst);
+  gb_view pv = {};
+  if (pre != nullptr) pv = *pre;
+  nchw_to_cl_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, C, *dst, pv);
   GB_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int gb_cl_to_nchw(const gb_view* src, float* dst, int C, int fold, void* stream) {
+extern "C" int gb_cl_to_nchw(const gb_view* src, float* dst, int C, int fold, int act, void* stream) {
   GB_CHECK(src && src->ptr && dst, "gb_cl_to_nchw: null pointer");
   GB_CHECK(src->C % 8 == 0 && C <= src->C && C >= 1, "gb_cl_to_nchw: bad channel counts %d <- %d", C, src->C);
   const int64_t total = (int64_t)src->N * src->D * src->H * src->W;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  cl_to_nchw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*src, dst, C, fold);
+  cl_to_nchw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*src, dst, C, fold, act);
   GB_CUDA(cudaGetLastError());
   return 0;
 }

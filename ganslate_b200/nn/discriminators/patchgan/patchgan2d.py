@@ -46,7 +46,4 @@ class PatchGAN2D(nn.Module):
         self.model = nn.Sequential(*sequence)
 
     def forward(self, input):
-        mods = list(self.model)
-        b = layers.to_buf(input, layers.first_pad(mods))
-        b = layers.run_sequence(mods, b)
-        return layers.from_buf(b)
+        return layers.run_network(list(self.model), input)

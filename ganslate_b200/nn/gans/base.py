@@ -1,0 +1,168 @@
+"""GAN recipe base class -- the API of ganslate/nn/gans/base.py:16-321 (set_input / forward /
+optimize_parameters / infer / checkpoints / DDP wrap / set_requires_grad) on top of the B200 modules.
+
+Mixed precision: the reference's option is NVIDIA Apex AMP fp16 (base.py:118-126), off in every shipped config.
+Here bf16 storage with fp32 accumulation IS the compute path of the kernels; the Apex switch is rejected."""
+import logging
+import os
+from abc import ABC, abstractmethod
+from pathlib import Path
+
+import torch
+from torch.nn.parallel import DistributedDataParallel
+
+from ganslate_b200.nn.utils import get_scheduler
+from ganslate_b200.utils import communication
+from ganslate_b200.utils.builders import build_D, build_G
+
+
+class TrainingMetricsLite:
+    """The step-path part of ganslate/utils/metrics/train_metrics.py:56-67: mean discriminator outputs."""
+
+    def __init__(self, conf):
+        m = conf.train.get("metrics", None)
+        self.output_distributions = bool(m and m.get("discriminator_evolution", False))
+        if m and m.get("ssim", False):
+            raise NotImplementedError("train.metrics.ssim is not on the B200 path (SURVEY.md section 8f rank 2)")
+
+    def compute_metrics_D(self, name, pred_real, pred_fake):
+        if not self.output_distributions:
+            return {}
+        if isinstance(pred_real, dict):
+            pred_real, pred_fake = pred_real[next(iter(pred_real))], pred_fake[next(iter(pred_fake))]
+        return {f"{name}_real": pred_real.detach().mean(), f"{name}_fake": pred_fake.detach().mean()}
+
+    def compute_metrics_G(self, visuals):
+        return {}
+
+
+class BaseGAN(ABC):
+
+    def __init__(self, conf):
+        self.logger = logging.getLogger("ganslate_b200")
+        self.conf = conf
+        self.is_train = self.conf.mode == "train"
+        self.device = self._specify_device()
+        self.output_dir = conf[conf.mode].output_dir
+        self.visuals, self.metrics, self.losses, self.optimizers, self.networks = {}, {}, {}, {}, {}
+
+    def init_networks(self):
+        """base.py:49-67: names starting with G/D, suffix _BA / _A selects direction / domain."""
+        for name in self.networks.keys():
+            if name.startswith('G'):
+                self.networks[name] = build_G(self.conf, 'BA' if name.endswith('_BA') else 'AB', self.device)
+            elif name.startswith('D'):
+                self.networks[name] = build_D(self.conf, 'A' if name.endswith('_A') else 'B', self.device)
+
+    @abstractmethod
+    def init_criterions(self):
+        """Initialize criterions (losses)"""
+
+    @abstractmethod
+    def init_optimizers(self):
+        """Initialize optimizers"""
+
+    def init_metrics(self):
+        self.training_metrics = TrainingMetricsLite(self.conf)
+
+    def init_schedulers(self):
+        self.schedulers = [get_scheduler(optim, self.conf) for optim in self.optimizers.values()]
+
+    def _specify_device(self):
+        if torch.distributed.is_initialized():
+            return torch.device(f"cuda:{communication.get_local_rank()}")
+        if self.conf[self.conf.mode].cuda:
+            return torch.device('cuda:0')
+        raise RuntimeError("ganslate_b200 has no CPU path: set `cuda: True` (the hot path is sm_100a CUDA only)")
+
+    @abstractmethod
+    def set_input(self, input):
+        """Unpack input data from the dataloader."""
+
+    @abstractmethod
+    def forward(self):
+        """Run forward pass."""
+
+    @abstractmethod
+    def optimize_parameters(self):
+        """Calculate losses, gradients, and update network weights; called in every training iteration"""
+
+    def setup(self):
+        """base.py:108-153: networks, criterions, optimizers, metrics, schedulers, checkpoint, DDP."""
+        if self.conf[self.conf.mode].mixed_precision:
+            raise NotImplementedError("Apex AMP is not used on the B200 path: the kernels already compute in "
+                                      "bf16 with fp32 accumulation. Set mixed_precision: False.")
+        self.init_networks()
+        if self.is_train:
+            self.init_criterions()
+            self.init_optimizers()
+            self.init_metrics()
+            self.init_schedulers()
+        else:
+            self.eval()
+            if len(self.networks.keys()) != 1:
+                raise ValueError("When inferring there should be only one network initialized - generator.")
+        if self.conf[self.conf.mode].checkpointing.load_iter:
+            self.load_networks(self.conf[self.conf.mode].checkpointing.load_iter)
+        num_devices = int(os.environ.get('WORLD_SIZE', torch.cuda.device_count()))
+        if num_devices > 1:
+            self.parallelize_networks()
+
+    def backward(self, loss, optimizer=None, retain_graph=False, loss_id=0):
+        loss.backward(retain_graph=retain_graph)
+
+    def parallelize_networks(self):
+        """base.py:172-189: one DistributedDataParallel wrapper per network, broadcast_buffers=False; the
+        bucketed NCCL all-reduce of the gradients overlaps with the rest of backward."""
+        for name in self.networks.keys():
+            if torch.distributed.is_initialized():
+                self.networks[name] = DistributedDataParallel(self.networks[name], device_ids=[self.device],
+                                                              output_device=self.device, broadcast_buffers=False)
+            elif self.conf[self.conf.mode].cuda and torch.cuda.device_count() > 1 and "WORLD_SIZE" in os.environ:
+                raise RuntimeError("Multi-GPU runs must be launched in distributed mode (torchrun).")
+
+    def update_learning_rate(self):
+        for scheduler in self.schedulers:
+            scheduler.step()
+
+    def save_checkpoint(self, iter_idx):
+        """base.py:226-251 -- same file layout ({name: state_dict}, optimizer_G, optimizer_D)."""
+        checkpoint = {}
+        path = Path(self.output_dir) / f"checkpoints/{iter_idx}.pth"
+        path.parent.mkdir(parents=True, exist_ok=True)
+        for name, net in self.networks.items():
+            checkpoint[name] = (net.module if isinstance(net, DistributedDataParallel) else net).state_dict()
+        checkpoint['optimizer_G'] = self.optimizers['G'].state_dict()
+        checkpoint['optimizer_D'] = self.optimizers['D'].state_dict()
+        torch.save(checkpoint, path)
+
+    def load_networks(self, iter_idx):
+        path = Path(self.output_dir).resolve() / f"checkpoints/{iter_idx}.pth"
+        checkpoint = torch.load(path, map_location=self.device)
+        for name in self.networks.keys():
+            net = self.networks[name]
+            (net.module if isinstance(net, DistributedDataParallel) else net).load_state_dict(checkpoint[name])
+        if self.is_train and self.conf[self.conf.mode].checkpointing.load_optimizers:
+            self.optimizers['G'].load_state_dict(checkpoint['optimizer_G'])
+            self.optimizers['D'].load_state_dict(checkpoint['optimizer_D'])
+
+    def set_requires_grad(self, networks, requires_grad=False):
+        if not isinstance(networks, list):
+            networks = [networks]
+        for net in networks:
+            if net is not None:
+                for param in net.parameters():
+                    param.requires_grad = requires_grad
+
+    def eval(self):
+        for name in self.networks.keys():
+            self.networks[name].eval()
+
+    def infer(self, input):
+        generator = 'G' if 'G' in self.networks.keys() else 'G_AB'
+        with torch.no_grad():
+            return self.networks[generator].forward(input)
+
+    def get_loggable_data(self):
+        learning_rates = {f"lr_{name}": optim.param_groups[0]['lr'] for name, optim in self.optimizers.items()}
+        return learning_rates, self.losses, self.visuals, self.metrics

@@ -59,10 +59,7 @@ class Resnet2D(nn.Module):
         self.model = nn.Sequential(*model)
 
     def forward(self, x):
-        mods = list(self.model)
-        b = layers.to_buf(x, layers.first_pad(mods))
-        b = layers.run_sequence(mods, b)
-        return layers.from_buf(b)
+        return layers.run_network(list(self.model), x)
 
 
 class ResidualBlock(nn.Module):

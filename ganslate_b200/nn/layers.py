@@ -110,10 +110,22 @@ def to_buf(x: torch.Tensor, pad: int) -> Buf:
     return Buf(ops.ToChannelsLastFn.apply(x, pad), pad, x.shape[1], x.dim() == 5)
 
 
-def from_buf(b: Buf) -> torch.Tensor:
+def from_buf(b: Buf, act: int = ACT_NONE) -> torch.Tensor:
     if b.pad != 0:
         raise RuntimeError("cannot export a bordered buffer")
-    return ops.FromChannelsLastFn.apply(b.t, b.channels, b.is_3d)
+    return ops.FromChannelsLastFn.apply(b.t, b.channels, b.is_3d, act)
+
+
+def run_network(mods: Sequence[nn.Module], x: torch.Tensor) -> torch.Tensor:
+    """NC(D)HW fp32 in -> NC(D)HW fp32 out through the fused kernels. A trailing nn.Tanh (generator output,
+    resnet2d.py:65) is evaluated in fp32 while the result is exported."""
+    mods = flatten_modules(mods)
+    act = ACT_NONE
+    if len(mods) and isinstance(mods[-1], Tanh):
+        mods, act = mods[:-1], ACT_TANH
+    b = to_buf(x, first_pad(mods))
+    b = run_sequence(mods, b)
+    return from_buf(b, act)
 
 
 def _is_norm(m):

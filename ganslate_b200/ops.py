@@ -378,7 +378,7 @@ class ToChannelsLastFn(torch.autograd.Function):
             N, Cc, D, H, W = x.shape
         out = torch.empty((N, D, H + 2 * pad, W + 2 * pad, pad8(Cc)), dtype=torch.bfloat16, device=x.device)
         v = make_view(out, pad)
-        _cabi.check(_cabi.lib().gb_nchw_to_cl(x.data_ptr(), Cc, C.byref(v), _stream()), "gb_nchw_to_cl")
+        _cabi.check(_cabi.lib().gb_nchw_to_cl(x.data_ptr(), Cc, C.byref(v), None, _stream()), "gb_nchw_to_cl")
         ctx.pad, ctx.shape = pad, x.shape
         return out
 
@@ -387,31 +387,39 @@ class ToChannelsLastFn(torch.autograd.Function):
         dout = dout.contiguous()
         dx = torch.empty(ctx.shape, dtype=torch.float32, device=dout.device)
         v = make_view(dout, ctx.pad)
-        _cabi.check(_cabi.lib().gb_cl_to_nchw(C.byref(v), dx.data_ptr(), ctx.shape[1], 1, _stream()), "gb_cl_to_nchw")
+        _cabi.check(_cabi.lib().gb_cl_to_nchw(C.byref(v), dx.data_ptr(), ctx.shape[1], 1, ACT_NONE, _stream()),
+                    "gb_cl_to_nchw")
         return dx, None
 
 
 class FromChannelsLastFn(torch.autograd.Function):
-    """bf16 plain buffer (N,D,H,W,Cpad) -> NC(D)HW fp32 with the first `channels` channels."""
+    """bf16 plain buffer (N,D,H,W,Cpad) -> NC(D)HW fp32 with the first `channels` channels.
+
+    act=ACT_TANH applies the generator's final nn.Tanh in fp32 during the export (and its derivative, from the
+    saved pre-activation, during the import of the gradient)."""
 
     @staticmethod
-    def forward(ctx, x, channels, is_3d):
+    def forward(ctx, x, channels, is_3d, act=ACT_NONE):
         x = x.contiguous()
         N, D, H, W, Cc = x.shape
         shape = (N, channels, D, H, W) if is_3d else (N, channels, H, W)
         out = torch.empty(shape, dtype=torch.float32, device=x.device)
         v = make_view(x)
-        _cabi.check(_cabi.lib().gb_cl_to_nchw(C.byref(v), out.data_ptr(), channels, 0, _stream()), "gb_cl_to_nchw")
-        ctx.in_shape, ctx.channels = x.shape, channels
+        _cabi.check(_cabi.lib().gb_cl_to_nchw(C.byref(v), out.data_ptr(), channels, 0, act, _stream()), "gb_cl_to_nchw")
+        ctx.in_shape, ctx.channels, ctx.act = x.shape, channels, act
+        ctx.save_for_backward(x if act == ACT_TANH else None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
+        (pre,) = ctx.saved_tensors
         dout = dout.contiguous().float()
         dx = torch.empty(ctx.in_shape, dtype=torch.bfloat16, device=dout.device)
         v = make_view(dx)
-        _cabi.check(_cabi.lib().gb_nchw_to_cl(dout.data_ptr(), ctx.channels, C.byref(v), _stream()), "gb_nchw_to_cl")
-        return dx, None, None
+        pv = make_view(pre) if pre is not None else None
+        _cabi.check(_cabi.lib().gb_nchw_to_cl(dout.data_ptr(), ctx.channels, C.byref(v),
+                                              C.byref(pv) if pv is not None else None, _stream()), "gb_nchw_to_cl")
+        return dx, None, None, None
 
 
 class MseConstFn(torch.autograd.Function):

@@ -164,10 +164,12 @@ typedef struct gb_in_bwd_params {
 int gb_in_bwd(const gb_in_bwd_params* p, void* stream);
 
 /* ---- layout conversion at the network boundary (set_input / module outputs; cyclegan.py:89-90) ---- */
-/* NC(D)HW fp32 -> channels-last bf16 view (zero-fills padded channels, writes reflected border if dst.pad>0) */
-int gb_nchw_to_cl(const float* src, int C, const gb_view* dst, void* stream);
-/* channels-last bf16 view (border folded in when src.pad>0 and fold!=0) -> NC(D)HW fp32 */
-int gb_cl_to_nchw(const gb_view* src, float* dst, int C, int fold, void* stream);
+/* NC(D)HW fp32 -> channels-last bf16 view (zero-fills padded channels, writes reflected border if dst.pad>0).
+ * If `pre` is non-NULL the value is multiplied by tanh'(pre) = 1 - tanh(pre)^2 (backward of the tanh export). */
+int gb_nchw_to_cl(const float* src, int C, const gb_view* dst, const gb_view* pre, void* stream);
+/* channels-last bf16 view (border folded in when src.pad>0 and fold!=0) -> NC(D)HW fp32.
+ * act = GB_ACT_TANH applies the generator's output nn.Tanh (resnet2d.py:65) in fp32 on the way out. */
+int gb_cl_to_nchw(const gb_view* src, float* dst, int C, int fold, int act, void* stream);
 
 /* ---- losses --------------------------------------------------------------------------------
  * LSGAN: mean((p - t)^2) (ganslate/nn/losses/adversarial_loss.py:29,60-62); grad = 2(p-t)/n.

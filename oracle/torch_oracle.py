@@ -1,0 +1,240 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU fp32 oracle of ganslate's training hot path.
+
+A restatement, in plain PyTorch on the CPU, of the reference's networks, losses and one CycleGAN / Pix2Pix
+training iteration.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module; the product path (ganslate_b200/) never does.
+
+Parity pin: the reference ships no golden vectors, so the oracle is pinned against the
+reference's own modules imported in the build container (tests/test_oracle_vs_reference.py) and against the
+fixtures under tests/golden/ that oracle/make_golden.py generated from those modules.
+
+Each function cites the reference lines it restates (paths relative to the reference root).
+"""
+import itertools
+import random
+from types import SimpleNamespace
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+# --------------------------------------------------------------------------------------------- networks
+def _norm2d(c):
+    # ganslate/nn/utils.py:53-59 -> nn.InstanceNorm2d defaults: eps 1e-5, affine=False, no running stats
+    return nn.InstanceNorm2d(c)
+
+
+class OracleResBlock(nn.Module):
+    """ganslate/nn/generators/resnet/resnet2d.py:73-93"""
+
+    def __init__(self, c):
+        super().__init__()
+        seq = []
+        for last in (False, True):
+            seq += [nn.ReflectionPad2d(1), nn.Conv2d(c, c, 3, bias=True), _norm2d(c)]
+            if not last:
+                seq.append(nn.ReLU(inplace=True))
+        self.conv_block = nn.Sequential(*seq)
+
+    def forward(self, x):
+        return x + self.conv_block(x)
+
+
+class OracleResnet2D(nn.Module):
+    """ganslate/nn/generators/resnet/resnet2d.py:14-70 (norm_type 'instance' => conv bias on, :20)"""
+
+    def __init__(self, in_channels, out_channels, n_residual_blocks=9):
+        super().__init__()
+        L = [nn.ReflectionPad2d(3), nn.Conv2d(in_channels, 64, 7), _norm2d(64), nn.ReLU(inplace=True)]
+        c = 64
+        for _ in range(2):  # :32-41
+            L += [nn.Conv2d(c, 2 * c, 3, stride=2, padding=1), _norm2d(2 * c), nn.ReLU(inplace=True)]
+            c *= 2
+        L += [OracleResBlock(c) for _ in range(n_residual_blocks)]  # :43-44
+        self.encoder = nn.ModuleList(L)  # :46 (aliases the same module objects)
+        for _ in range(2):  # :48-60
+            L += [nn.ConvTranspose2d(c, c // 2, 3, stride=2, padding=1, output_padding=1), _norm2d(c // 2),
+                  nn.ReLU(inplace=True)]
+            c //= 2
+        L += [nn.ReflectionPad2d(3), nn.Conv2d(64, out_channels, 7), nn.Tanh()]  # :63
+        self.model = nn.Sequential(*L)
+
+    def forward(self, x):
+        return self.model(x)
+
+
+class OraclePatchGAN2D(nn.Module):
+    """ganslate/nn/discriminators/patchgan/patchgan2d.py:17-66"""
+
+    def __init__(self, in_channels, ndf=64, n_layers=3, kernel_size=(4, 4)):
+        super().__init__()
+        k = tuple(kernel_size)
+        L = [nn.Conv2d(in_channels, ndf, k, stride=2, padding=1), nn.LeakyReLU(0.2, True)]
+        mult = 1
+        for n in range(1, n_layers):
+            prev, mult = mult, min(2**n, 8)
+            L += [nn.Conv2d(ndf * prev, ndf * mult, k, stride=2, padding=1), _norm2d(ndf * mult), nn.LeakyReLU(0.2, True)]
+        prev, mult = mult, min(2**n_layers, 8)
+        L += [nn.Conv2d(ndf * prev, ndf * mult, k, stride=1, padding=1), _norm2d(ndf * mult), nn.LeakyReLU(0.2, True)]
+        L += [nn.Conv2d(ndf * mult, 1, k, stride=1, padding=1)]
+        self.model = nn.Sequential(*L)
+
+    def forward(self, x):
+        return self.model(x)
+
+
+def init_weights(net, gain=0.02):
+    """ganslate/nn/utils.py:13-36 with weight_init_type='normal': N(0, gain) on every Conv/Linear weight in
+    module order, zero bias."""
+
+    def f(m):
+        name = type(m).__name__
+        if hasattr(m, "weight") and ("Conv" in name or "Linear" in name):
+            nn.init.normal_(m.weight.data, 0.0, gain)
+            if getattr(m, "bias", None) is not None:
+                nn.init.constant_(m.bias.data, 0.0)
+
+    net.apply(f)
+    return net
+
+
+# --------------------------------------------------------------------------------------------- losses
+def adversarial_lsgan(pred, target_is_real, real_label=1.0, fake_label=0.0):
+    """ganslate/nn/losses/adversarial_loss.py:34-62 (gan_mode 'lsgan'): MSE against the expanded constant label."""
+    t = torch.tensor(real_label if target_is_real else fake_label, dtype=pred.dtype, device=pred.device)
+    return F.mse_loss(pred, t.expand_as(pred))
+
+
+def cyclegan_losses(visuals, lambda_AB=10.0, lambda_BA=10.0, lambda_identity=0.0):
+    """ganslate/nn/losses/cyclegan_losses.py:31-58,73-101 with proportion_ssim = 0 (every shipped YAML)."""
+    out = {
+        "cycle_A": lambda_AB * F.l1_loss(visuals["rec_A"], visuals["real_A"]),
+        "cycle_B": lambda_BA * F.l1_loss(visuals["rec_B"], visuals["real_B"]),
+    }
+    if lambda_identity > 0:
+        out["idt_B"] = lambda_AB * (F.l1_loss(visuals["idt_B"], visuals["real_B"]) * lambda_identity)
+        out["idt_A"] = lambda_BA * (F.l1_loss(visuals["idt_A"], visuals["real_A"]) * lambda_identity)
+    return out
+
+
+class OracleImagePool:
+    """ganslate/data/utils/image_pool.py:24-60"""
+
+    def __init__(self, pool_size):
+        self.pool_size, self.num_imgs, self.images = pool_size, 0, []
+
+    def query(self, images):
+        if self.pool_size == 0:
+            return images
+        ret = []
+        for image in images:
+            image = torch.unsqueeze(image.data, 0)
+            if self.num_imgs < self.pool_size:
+                self.num_imgs += 1
+                self.images.append(image)
+                ret.append(image)
+            elif random.uniform(0, 1) > 0.5:
+                i = random.randint(0, self.pool_size - 1)
+                tmp = self.images[i].clone()
+                self.images[i] = image
+                ret.append(tmp)
+            else:
+                ret.append(image)
+        return torch.cat(ret, 0)
+
+
+# --------------------------------------------------------------------------------------------- CycleGAN step
+def default_cyclegan_conf(**kw):
+    c = dict(lambda_AB=10.0, lambda_BA=10.0, lambda_identity=0.0, lr_G=2e-4, lr_D=2e-4, beta1=0.5, beta2=0.999,
+             pool_size=50, n_residual_blocks=9, ndf=64, n_layers=3, in_channels=3, out_channels=3)
+    c.update(kw)
+    return SimpleNamespace(**c)
+
+
+class OracleCycleGAN:
+    """One training iteration as ganslate/nn/gans/unpaired/cyclegan.py:92-214 runs it (mixed_precision False)."""
+
+    def __init__(self, conf=None, seed=0, device="cpu"):
+        self.conf = conf or default_cyclegan_conf()
+        c = self.conf
+        torch.manual_seed(seed)
+        # construction + init order follows the dict order at cyclegan.py:52 / base.py:51-67
+        self.networks = {}
+        for name in ("G_AB", "G_BA", "D_B", "D_A"):
+            if name.startswith("G"):
+                net = OracleResnet2D(c.in_channels, c.out_channels, c.n_residual_blocks)
+            else:
+                net = OraclePatchGAN2D(c.in_channels, c.ndf, c.n_layers)
+            self.networks[name] = init_weights(net).to(device)
+        n = self.networks
+        self.optimizers = {  # cyclegan.py:70-82
+            "G": torch.optim.Adam(itertools.chain(n["G_AB"].parameters(), n["G_BA"].parameters()), lr=c.lr_G,
+                                  betas=(c.beta1, c.beta2)),
+            "D": torch.optim.Adam(itertools.chain(n["D_B"].parameters(), n["D_A"].parameters()), lr=c.lr_D,
+                                  betas=(c.beta1, c.beta2)),
+        }
+        self.fake_A_pool, self.fake_B_pool = OracleImagePool(c.pool_size), OracleImagePool(c.pool_size)
+        self.visuals, self.losses = {}, {}
+
+    @staticmethod
+    def _set_requires_grad(nets, flag):  # base.py:289-300
+        for net in nets:
+            for p in net.parameters():
+                p.requires_grad = flag
+
+    def forward(self):  # cyclegan.py:126-152
+        n, v = self.networks, self.visuals
+        v["fake_B"] = n["G_AB"](v["real_A"])
+        v["rec_A"] = n["G_BA"](v["fake_B"])
+        v["fake_A"] = n["G_BA"](v["real_B"])
+        v["rec_B"] = n["G_AB"](v["fake_A"])
+        v["idt_A"] = v["idt_B"] = None
+        if self.conf.lambda_identity > 0:
+            v["idt_B"] = n["G_AB"](v["real_B"])
+            v["idt_A"] = n["G_BA"](v["real_A"])
+
+    def backward_G(self):  # cyclegan.py:191-214
+        n, v, c = self.networks, self.visuals, self.conf
+        self.losses["G_AB"] = adversarial_lsgan(n["D_B"](v["fake_B"]), True)
+        self.losses["G_BA"] = adversarial_lsgan(n["D_A"](v["fake_A"]), True)
+        lg = cyclegan_losses(v, c.lambda_AB, c.lambda_BA, c.lambda_identity)
+        self.losses.update(lg)
+        (sum(lg.values()) + self.losses["G_AB"] + self.losses["G_BA"]).backward()
+
+    def backward_D(self, name):  # cyclegan.py:154-189
+        v = self.visuals
+        if name == "D_B":
+            real, fake = v["real_B"], self.fake_B_pool.query(v["fake_B"])
+        else:
+            real, fake = v["real_A"], self.fake_A_pool.query(v["fake_A"])
+        pred_real = self.networks[name](real)
+        pred_fake = self.networks[name](fake.detach())
+        self.losses[name] = adversarial_lsgan(pred_real, True) + adversarial_lsgan(pred_fake, False)
+        self.losses[name].backward()
+
+    def optimize_parameters(self, real_A, real_B, step_optimizers=True):  # cyclegan.py:84-124
+        self.visuals["real_A"], self.visuals["real_B"] = real_A, real_B
+        ds = [self.networks["D_B"], self.networks["D_A"]]
+        self.forward()
+        self._set_requires_grad(ds, False)
+        self.optimizers["G"].zero_grad(set_to_none=True)
+        self.backward_G()
+        if step_optimizers:
+            self.optimizers["G"].step()
+        self._set_requires_grad(ds, True)
+        self.optimizers["D"].zero_grad(set_to_none=True)
+        self.backward_D("D_B")
+        self.backward_D("D_A")
+        if step_optimizers:
+            self.optimizers["D"].step()
+        return {k: float(v) for k, v in self.losses.items() if v is not None}
+
+
+def synthetic_batch(batch, channels=3, size=256, seed=1, device="cpu", width=None):
+    """Inputs U(-1, 1) (images are normalised to [-1, 1] in the reference, utils/trackers/utils.py:81-82)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    w = width or size
+    a = torch.rand((batch, channels, size, w), generator=g) * 2 - 1
+    b = torch.rand((batch, channels, size, w), generator=g) * 2 - 1
+    return a.to(device), b.to(device)

@@ -39,10 +39,8 @@ def conv_case(name, cin, cout, k, s, p, H, W, N=1, transposed=False, op_pad=0, r
     shape = (N, cin, D, H, W) if D else (N, cin, H, W)
     x = bf(torch.randn(shape, device=dev)).requires_grad_(True)
     # ours
-    b = layers.to_buf(x, reflect)
     mods = ([layers.ReflectionPad2d(reflect)] if reflect else []) + [mod] + ([layers.Tanh()] if act == "tanh" else [])
-    ob = layers.run_sequence(mods, b)
-    y = layers.from_buf(ob)
+    y = layers.run_network(mods, x)
     # reference
     xr = x.detach().clone().requires_grad_(True)
     wr = mod.weight.detach().clone().requires_grad_(True)
