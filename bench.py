@@ -1,0 +1,250 @@
+#!/usr/bin/env python
+"""CycleGAN training throughput on B200 (BASELINE.json metric: CycleGAN train img/s at 1/2/4/8 B200).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+
+A step = one CycleGAN.optimize_parameters() (4 generator passes, G step, 2 discriminator steps, both Adam
+updates, DDP gradient all-reduce when N>1) on one synthetic batch of Resnet2D-9 + PatchGAN2D at 3x256x256.
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "CycleGAN train img/s"
+UNIT = "img/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("GB_BENCH_BATCH", 1)), help="per-GPU batch")
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"CycleGAN Resnet2D-9blk + PatchGAN2D(n_layers 3), synthetic 3x{args.size}x{args.size}, "
+                    f"batch {args.batch}/GPU, lambda 10, lsgan, Adam(2e-4, 0.5/0.999)",
+        "global_batch": args.batch * world, "image": [3, args.size, args.size],
+        "parallelism": f"dp{world}", "l2_policy": "activations+gradients per step exceed nothing cached across "
+                                                  "steps: 2 x 126 MB flush buffer written between timed steps",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_step_rate(size, batch, steps, warmup=1):
+    """The reference's algorithm (oracle port, fp32, torch CPU kernels) on all host cores."""
+    import torch
+    from oracle import torch_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = O.OracleCycleGAN(seed=0)
+    a, b = O.synthetic_batch(batch, 3, size, seed=1)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        model.optimize_parameters(a, b)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return batch / med, med, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    rate, med, cores = cpu_step_rate(args.size, args.batch, steps, warmup=min(args.warmup, 1))
+    world = 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} full CycleGAN steps (batch {args.batch}) of oracle/torch_oracle.py on the "
+                                   f"host CPU; the Python reference cannot travel to the GPU box"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], None, set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def conv_flops_per_step(batch):
+    """12 F_G + 16 F_D - 2 dgrad1(G) - 4 dgrad1(D) at 3x256x256, per sample pair."""
+    return 1287.1e9 * batch
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from ganslate_b200 import _cabi, profiler
+    from ganslate_b200.presets import cyclegan_resnet2d
+    from ganslate_b200.utils import communication
+    from ganslate_b200.utils.builders import build_gan
+    from oracle import torch_oracle as O  # synthetic_batch only (shared input generator)
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        communication.init_distributed()
+    dev = torch.device("cuda", local_rank)
+    lib = _cabi.lib()  # fails loudly if the CUDA extension is missing
+
+    torch.manual_seed(0)
+    conf = cyclegan_resnet2d(batch_size=args.batch, cuda_graph=not args.no_graph)
+    model = build_gan(conf)
+    a_host, b_host = O.synthetic_batch(args.batch, 3, args.size, seed=1 + rank)
+    a_host, b_host = a_host.pin_memory(), b_host.pin_memory()
+    a_dev, b_dev = a_host.to(dev), b_host.to(dev)
+    flush = torch.empty(2 * 126 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(resident=True):
+        if resident:
+            model.set_input({"A": a_dev, "B": b_dev})
+        else:
+            model.set_input({"A": a_host, "B": b_host})  # H2D from pinned memory inside the timed region
+        model.optimize_parameters()
+
+    def timed(n, resident):
+        evs = []
+        for _ in range(n):
+            flush.zero_()  # evict L2 between timed iterations
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step(resident)
+            if not resident:
+                _ = float(model.losses["cycle_A"])  # D2H read of a step result
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(e0.elapsed_time(e1) for e0, e1 in evs) / 1e3
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    l0 = lib.gb_launch_count()
+    barrier()
+    t = timed(args.steps, True)
+    barrier()
+    launches = lib.gb_launch_count() - l0
+    clocks = sampler.stop()
+    if getattr(model, "graph_launches_per_step", None):
+        launches = model.graph_launches_per_step * args.steps
+    # e2e: host buffers in, loss scalar out
+    barrier()
+    t_e2e = timed(args.steps, False)
+    barrier()
+    times = torch.tensor([t, t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t, t_e2e = times.tolist()
+
+    roof = None
+    if rank == 0 and not args.no_roofline:
+        roof = profiler.conv_roofline(model, a_dev, b_dev, steps=3)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        rate, med, cores = cpu_step_rate(args.size, args.batch, steps=3, warmup=1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"3 full CycleGAN steps (batch {args.batch}) of the CPU oracle after 1 warm-up, median"}
+    if rank == 0:
+        imgs = args.batch * world * args.steps
+        in_bytes = 2 * a_host.numel() * 4
+        line = {
+            "metric": METRIC, "value": imgs / t, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": t / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, world),
+            "e2e": {"value": imgs / t_e2e, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "conv_tflops_step": conv_flops_per_step(args.batch) * args.steps / t / 1e12,
+            "cuda_graph": not args.no_graph,
+        }
+        if roof is not None:
+            line["roofline"] = roof["dominant"]
+            line["roofline_detail"] = roof["detail"]
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -28,7 +28,7 @@ class ConvParams(C.Structure):
     _fields_ = [("inp", View), ("out", View), ("wpacked", C.c_void_p), ("bias", C.c_void_p), ("ncols", C.c_int32),
                 ("npad", C.c_int32), ("in_mul", C.c_int32 * 3), ("out_mul", C.c_int32 * 3), ("nclass", C.c_int32),
                 ("cls", ConvClass * GB_MAX_CLASSES), ("taps", (C.c_int8 * 4) * GB_MAX_TAPS), ("act", C.c_int32),
-                ("act_slope", C.c_float)]
+                ("act_slope", C.c_float), ("out_fp32", C.c_int32), ("accumulate", C.c_int32)]
 
 
 class WgradParams(C.Structure):
@@ -66,8 +66,8 @@ _SIGNATURES = {
     "gb_in_stats": [C.POINTER(View), C.c_void_p, C.c_void_p],
     "gb_in_fwd": [C.POINTER(InFwdParams), C.c_void_p],
     "gb_in_bwd": [C.POINTER(InBwdParams), C.c_void_p],
-    "gb_nchw_to_cl": [C.c_void_p, C.c_int, C.POINTER(View), C.POINTER(View), C.c_void_p],
-    "gb_cl_to_nchw": [C.POINTER(View), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p],
+    "gb_nchw_to_cl": [C.c_void_p, C.c_int, C.POINTER(View), C.POINTER(View), C.c_int, C.c_void_p],
+    "gb_cl_to_nchw": [C.POINTER(View), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "gb_mse_const": [C.c_void_p, C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     "gb_l1": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     "gb_version": [],
@@ -79,7 +79,7 @@ _lib = None
 
 def exported_symbols():
     """Every entry point include/ganslate_b200.h declares (checked by the CPU test-suite)."""
-    return list(_SIGNATURES) + ["gb_last_error"]
+    return list(_SIGNATURES) + ["gb_last_error", "gb_launch_count"]
 
 
 def lib():
@@ -95,6 +95,8 @@ def lib():
             fn.restype = C.c_int
         L.gb_last_error.argtypes = []
         L.gb_last_error.restype = C.c_char_p
+        L.gb_launch_count.argtypes = []
+        L.gb_launch_count.restype = C.c_ulonglong
         _lib = L
     return _lib
 

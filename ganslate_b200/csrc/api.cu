@@ -4,6 +4,7 @@
 
 static thread_local char g_err[512] = "";
 int g_gb_knobs[16] = {0};
+unsigned long long g_gb_launches = 0;
 
 void gb_set_error(const char* fmt, ...) {
   va_list ap;
@@ -20,3 +21,4 @@ extern "C" int gb_debug_knob(int knob, int value) {
   g_gb_knobs[knob] = value;
   return old;
 }
+extern "C" unsigned long long gb_launch_count(void) { return g_gb_launches; }

@@ -10,12 +10,19 @@
 // ---------------------------------------------------------------- error plumbing (host)
 void gb_set_error(const char* fmt, ...);
 extern int g_gb_knobs[16];
+extern unsigned long long g_gb_launches;  // kernels launched through the ABI (bench.py reports it)
 #define GB_CHECK(cond, ...)        \
   do {                             \
     if (!(cond)) {                 \
       gb_set_error(__VA_ARGS__);   \
       return 1;                    \
     }                              \
+  } while (0)
+ // checks the launch and counts it
+#define GB_LAUNCH_CHECK()                                 \
+  do {                                                    \
+    __atomic_fetch_add(&g_gb_launches, 1ull, __ATOMIC_RELAXED); \
+    GB_CUDA(cudaGetLastError());                          \
   } while (0)
 #define GB_CUDA(call)                                                               \
   do {                                                                              \

@@ -225,12 +225,24 @@ __global__ void __launch_bounds__(256, Cfg<BN>::MIN_CTAS) igemm_data_kernel(cons
                 else if (p.act == GB_ACT_RELU) t = fmaxf(t, 0.f);
                 v[e] = t;
               }
-              uint4 o;
-              o.x = pack_bf16x2(v[0], v[1]);
-              o.y = pack_bf16x2(v[2], v[3]);
-              o.z = pack_bf16x2(v[4], v[5]);
-              o.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(optr + ooff + col) = o;
+              if (p.out_fp32) {
+                float4* o32 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out.ptr) + ooff + col);
+                float4 a = make_float4(v[0], v[1], v[2], v[3]), b = make_float4(v[4], v[5], v[6], v[7]);
+                if (p.accumulate) {
+                  const float4 pa = o32[0], pb = o32[1];
+                  a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
+                  b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
+                }
+                o32[0] = a;
+                o32[1] = b;
+              } else {
+                uint4 o;
+                o.x = pack_bf16x2(v[0], v[1]);
+                o.y = pack_bf16x2(v[2], v[3]);
+                o.z = pack_bf16x2(v[4], v[5]);
+                o.w = pack_bf16x2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(optr + ooff + col) = o;
+              }
             }
           }
         }
@@ -252,7 +264,7 @@ int launch(const gb_conv_params& p, int64_t max_mc, cudaStream_t st) {
   }
   dim3 grid(gb_cdiv(max_mc, BM), gb_cdiv(p.ncols, BN), p.nclass);
   igemm_data_kernel<BN><<<grid, 256, C::SMEM, st>>>(p);
-  GB_CUDA(cudaGetLastError());
+  GB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -272,6 +284,7 @@ extern "C" int gb_conv_data(const gb_conv_params* pp, void* stream) {
   GB_CHECK(p.ncols >= 1 && p.ncols <= p.out.C && p.npad % 16 == 0, "gb_conv_data: bad ncols/npad %d/%d", p.ncols,
            p.npad);
   GB_CHECK(p.in.N == p.out.N, "gb_conv_data: batch mismatch");
+  GB_CHECK(!p.accumulate || p.out_fp32, "gb_conv_data: accumulate needs an fp32 output");
   GB_CHECK(view_max_offset(p.in) < (1ll << 31) && view_max_offset(p.out) < (1ll << 31),
            "gb_conv_data: tensor too large for 32-bit offsets");
   GB_CHECK(p.in.H < 32768 && p.in.W < 32768, "gb_conv_data: spatial extent too large");

@@ -231,7 +231,7 @@ int launch(const gb_wgrad_params& p, cudaStream_t st) {
   splits = gb_cdiv(nblk, bps);
   dim3 grid(gb_cdiv(p.kpad, BN), gb_cdiv(p.rows, BM), splits);
   igemm_wgrad_kernel<BN><<<grid, 256, C::SMEM, st>>>(p, bps);
-  GB_CUDA(cudaGetLastError());
+  GB_LAUNCH_CHECK();
   return 0;
 }
 

@@ -32,6 +32,17 @@ __device__ __forceinline__ void load8(const gb_view& v, int n, int z, int y, int
   t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
   t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
 }
+// fp32 view variants (activation gradients)
+__device__ __forceinline__ void load8f(const gb_view& v, int n, int z, int y, int x, int cg, float (&f)[8]) {
+  const float* ptr = reinterpret_cast<const float*>(v.ptr) + gb_pix_offset(v, n, z, y, x) + cg * 8;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(ptr)), b = __ldg(reinterpret_cast<const float4*>(ptr) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store8f(const gb_view& v, int n, int z, int y, int x, int cg, const float (&f)[8]) {
+  float* ptr = reinterpret_cast<float*>(v.ptr) + gb_pix_offset(v, n, z, y, x) + cg * 8;
+  reinterpret_cast<float4*>(ptr)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(ptr)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 o;
   o.x = pack_bf16x2(f[0], f[1]);
@@ -76,7 +87,7 @@ __device__ __forceinline__ void load8_fold(const gb_view& v, int n, int z, int y
   for (int a = 0; a < ny; ++a)
     for (int b = 0; b < nx; ++b) {
       float t[8];
-      load8(v, n, z, ys[a], xs[b], cg, t);
+      load8f(v, n, z, ys[a], xs[b], cg, t);
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] += t[e];
     }
@@ -221,12 +232,12 @@ __global__ void in_bwd_kernel(const __grid_constant__ gb_in_bwd_params p, int pi
       const Pix q = decode_pix(pix, x);
       float g[8], xv[8], t[8];
       if (use_sum) {
-        load8(p.dy_sum, n, q.z, q.y, q.x, cg, g);
+        load8f(p.dy_sum, n, q.z, q.y, q.x, cg, g);
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) g[e] = 0.f;
         if (has_a) {
-          load8(p.dy_a, n, q.z, q.y, q.x, cg, t);
+          load8f(p.dy_a, n, q.z, q.y, q.x, cg, t);
 #pragma unroll
           for (int e = 0; e < 8; ++e) g[e] += t[e];
         }
@@ -235,7 +246,7 @@ __global__ void in_bwd_kernel(const __grid_constant__ gb_in_bwd_params p, int pi
 #pragma unroll
           for (int e = 0; e < 8; ++e) g[e] += t[e];
         }
-        if (p.dy_sum.ptr != nullptr && (MODE == 0 || !norm)) store8(p.dy_sum, n, q.z, q.y, q.x, cg, pack8(g));
+        if (p.dy_sum.ptr != nullptr && (MODE == 0 || !norm)) store8f(p.dy_sum, n, q.z, q.y, q.x, cg, g);
       }
       // activation derivative
       if (norm) {
@@ -331,7 +342,7 @@ extern "C" int gb_in_stats(const gb_view* x, float* stats, void* stream) {
   GB_CHECK(x->C % 8 == 0 && x->C <= 2048, "gb_in_stats: bad channel count %d", x->C);
   Launch L = plan(*x);
   in_stats_kernel<<<L.grid, L.threads, sizeof(float) * 2 * L.slots * x->C, (cudaStream_t)stream>>>(*x, stats, L.ppb);
-  GB_CUDA(cudaGetLastError());
+  GB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -344,7 +355,7 @@ extern "C" int gb_in_fwd(const gb_in_fwd_params* p, void* stream) {
   GB_CHECK(p->y.pad == 0 || (p->y.H > p->y.pad && p->y.W > p->y.pad), "gb_in_fwd: reflection border larger than image");
   Launch L = plan(p->x);
   in_fwd_kernel<<<L.grid, L.threads, 0, (cudaStream_t)stream>>>(*p, L.ppb);
-  GB_CUDA(cudaGetLastError());
+  GB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -361,9 +372,9 @@ extern "C" int gb_in_bwd(const gb_in_bwd_params* p, void* stream) {
   Launch L = plan(p->x);
   if (p->stats != nullptr) {
     in_bwd_kernel<0><<<L.grid, L.threads, sizeof(float) * 3 * L.slots * p->x.C, st>>>(*p, L.ppb);
-    GB_CUDA(cudaGetLastError());
+    GB_LAUNCH_CHECK();
   }
   in_bwd_kernel<1><<<L.grid, L.threads, 0, st>>>(*p, L.ppb);
-  GB_CUDA(cudaGetLastError());
+  GB_LAUNCH_CHECK();
   return 0;
 }

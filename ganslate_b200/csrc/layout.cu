@@ -19,7 +19,7 @@ __device__ __forceinline__ void reflect_targets(const gb_view& v, int y, int x, 
   }
 }
 
-__global__ void nchw_to_cl_kernel(const float* __restrict__ src, int C, gb_view dst, gb_view pre) {
+__global__ void nchw_to_cl_kernel(const float* __restrict__ src, int C, gb_view dst, gb_view pre, int dst_fp32) {
   const int64_t P = (int64_t)dst.D * dst.H * dst.W;
   const int64_t total = (int64_t)dst.N * P;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(dst.ptr);
@@ -54,13 +54,21 @@ __global__ void nchw_to_cl_kernel(const float* __restrict__ src, int C, gb_view 
       o.z = pack_bf16x2(f[4], f[5]);
       o.w = pack_bf16x2(f[6], f[7]);
       for (int a = 0; a < ny; ++a)
-        for (int b = 0; b < nx; ++b)
-          *reinterpret_cast<uint4*>(out + gb_pix_offset(dst, n, z, ys[a], xs[b]) + cg * 8) = o;
+        for (int b = 0; b < nx; ++b) {
+          if (dst_fp32) {
+            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst.ptr) +
+                                                   gb_pix_offset(dst, n, z, ys[a], xs[b]) + cg * 8);
+            o4[0] = make_float4(f[0], f[1], f[2], f[3]);
+            o4[1] = make_float4(f[4], f[5], f[6], f[7]);
+          } else {
+            *reinterpret_cast<uint4*>(out + gb_pix_offset(dst, n, z, ys[a], xs[b]) + cg * 8) = o;
+          }
+        }
     }
   }
 }
 
-__global__ void cl_to_nchw_kernel(gb_view src, float* __restrict__ dst, int C, int fold, int act) {
+__global__ void cl_to_nchw_kernel(gb_view src, float* __restrict__ dst, int C, int fold, int act, int src_fp32) {
   const int64_t P = (int64_t)src.D * src.H * src.W;
   const int64_t total = (int64_t)src.N * P;
   const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(src.ptr);
@@ -78,6 +86,14 @@ __global__ void cl_to_nchw_kernel(gb_view src, float* __restrict__ dst, int C, i
       float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       for (int a = 0; a < ny; ++a)
         for (int b = 0; b < nx; ++b) {
+          if (src_fp32) {
+            const float4* q4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src.ptr) +
+                                                               gb_pix_offset(src, n, z, ys[a], xs[b]) + cg * 8);
+            const float4 u0 = __ldg(q4), u1 = __ldg(q4 + 1);
+            f[0] += u0.x; f[1] += u0.y; f[2] += u0.z; f[3] += u0.w;
+            f[4] += u1.x; f[5] += u1.y; f[6] += u1.z; f[7] += u1.w;
+            continue;
+          }
           const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + gb_pix_offset(src, n, z, ys[a], xs[b]) + cg * 8));
           float2 t;
           t = unpack_bf16x2(u.x); f[0] += t.x; f[1] += t.y;
@@ -96,7 +112,8 @@ __global__ void cl_to_nchw_kernel(gb_view src, float* __restrict__ dst, int C, i
 
 }  // namespace
 
-extern "C" int gb_nchw_to_cl(const float* src, int C, const gb_view* dst, const gb_view* pre, void* stream) {
+extern "C" int gb_nchw_to_cl(const float* src, int C, const gb_view* dst, const gb_view* pre, int dst_fp32,
+                             void* stream) {
   GB_CHECK(src && dst && dst->ptr, "gb_nchw_to_cl: null pointer");
   GB_CHECK(dst->C % 8 == 0 && C <= dst->C && C >= 1, "gb_nchw_to_cl: bad channel counts %d -> %d", C, dst->C);
   GB_CHECK(dst->pad == 0 || (dst->H > dst->pad && dst->W > dst->pad), "gb_nchw_to_cl: border larger than image");
@@ -106,19 +123,19 @@ extern "C" int gb_nchw_to_cl(const float* src, int C, const gb_view* dst, const 
   if (blocks < 1) blocks = 1;
   gb_view pv = {};
   if (pre != nullptr) pv = *pre;
-  nchw_to_cl_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, C, *dst, pv);
-  GB_CUDA(cudaGetLastError());
+  nchw_to_cl_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, C, *dst, pv, dst_fp32);
+  GB_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int gb_cl_to_nchw(const gb_view* src, float* dst, int C, int fold, int act, void* stream) {
+extern "C" int gb_cl_to_nchw(const gb_view* src, float* dst, int C, int fold, int act, int src_fp32, void* stream) {
   GB_CHECK(src && src->ptr && dst, "gb_cl_to_nchw: null pointer");
   GB_CHECK(src->C % 8 == 0 && C <= src->C && C >= 1, "gb_cl_to_nchw: bad channel counts %d <- %d", C, src->C);
   const int64_t total = (int64_t)src->N * src->D * src->H * src->W;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  cl_to_nchw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*src, dst, C, fold, act);
-  GB_CUDA(cudaGetLastError());
+  cl_to_nchw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*src, dst, C, fold, act, src_fp32);
+  GB_LAUNCH_CHECK();
   return 0;
 }

@@ -77,13 +77,13 @@ int grid_for(int64_t n, int per_thread) {
 extern "C" int gb_mse_const(const float* pred, float target, int64_t n, float* loss, float* grad, void* stream) {
   GB_CHECK(pred && loss && n > 0, "gb_mse_const: bad arguments");
   mse_const_kernel<<<grid_for(n, 4), 256, 0, (cudaStream_t)stream>>>(pred, target, n, 1.f / (float)n, loss, grad);
-  GB_CUDA(cudaGetLastError());
+  GB_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int gb_l1(const float* a, const float* b, int64_t n, float* loss, float* grad_a, void* stream) {
   GB_CHECK(a && b && loss && n > 0, "gb_l1: bad arguments");
   l1_kernel<<<grid_for(n, 16), 256, 0, (cudaStream_t)stream>>>(a, b, n, 1.f / (float)n, loss, grad_a);
-  GB_CUDA(cudaGetLastError());
+  GB_LAUNCH_CHECK();
   return 0;
 }

@@ -89,7 +89,7 @@ extern "C" int gb_pack_weights(const gb_pack_params* pp, void* stream) {
   if (blocks > 2048) blocks = 2048;
   if (blocks < 1) blocks = 1;
   pack_kernel<<<dim3(blocks, p.nclass), 256, 0, (cudaStream_t)stream>>>(p);
-  GB_CUDA(cudaGetLastError());
+  GB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -101,7 +101,7 @@ extern "C" int gb_unpack_wgrad(const float* dw, float* dst, int64_t dsr, int64_t
   if (blocks > 4096) blocks = 4096;
   if (blocks < 1) blocks = 1;
   unpack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dw, dst, dsr, dsc, dst_t, rows, chans, chans_pad, ntaps, kpad);
-  GB_CUDA(cudaGetLastError());
+  GB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -120,6 +120,6 @@ extern "C" int gb_colsum(const gb_view* x, float* out, void* stream) {
   const int ppb = (int)((P + blocks - 1) / blocks);
   blocks = (P + ppb - 1) / ppb;
   colsum_kernel<<<(int)blocks, threads, sizeof(float) * slots * x->C, st>>>(*x, out, ppb);
-  GB_CUDA(cudaGetLastError());
+  GB_LAUNCH_CHECK();
   return 0;
 }

@@ -46,4 +46,4 @@ class PatchGAN2D(nn.Module):
         self.model = nn.Sequential(*sequence)
 
     def forward(self, input):
-        return layers.run_network(list(self.model), input)
+        return layers.run_network(self, list(self.model), input)

@@ -45,6 +45,11 @@ class BaseGAN(ABC):
         self.device = self._specify_device()
         self.output_dir = conf[conf.mode].output_dir
         self.visuals, self.metrics, self.losses, self.optimizers, self.networks = {}, {}, {}, {}, {}
+        # CUDA-graph replay of the training step (launch-bound at batch 1: ~1.4 k kernels per iteration)
+        self.use_cuda_graph = bool(conf[conf.mode].get("cuda_graph", False)) if self.is_train else False
+        self.graph_warmup_iters = int(conf[conf.mode].get("cuda_graph_warmup", 11)) if self.is_train else 0
+        self._graphs, self._static, self._graph_calls = {}, {}, 0
+        self.graph_launches_per_step = 0
 
     def init_networks(self):
         """base.py:49-67: names starting with G/D, suffix _BA / _A selects direction / domain."""
@@ -108,6 +113,48 @@ class BaseGAN(ABC):
         if num_devices > 1:
             self.parallelize_networks()
 
+    # ------------------------------------------------------------------ CUDA-graph plumbing
+    def make_adam(self, params, lr, betas):
+        """torch.optim.Adam as in the reference (cyclegan.py:81-82); capturable when the step is graph-replayed."""
+        if self.use_cuda_graph:
+            return torch.optim.Adam(params, lr=torch.tensor(float(lr), device=self.device), betas=betas, capturable=True)
+        return torch.optim.Adam(params, lr=lr, betas=betas)
+
+    def stage_input(self, name, tensor):
+        """Device-resident input. In graph mode the data is copied into a static buffer the graphs read."""
+        if not self.use_cuda_graph:
+            return tensor.to(self.device, non_blocking=True)
+        buf = self._static.get(name)
+        if buf is None or buf.shape != tensor.shape:
+            if self._graphs:
+                raise RuntimeError("input shape changed after CUDA-graph capture")
+            buf = torch.empty(tensor.shape, dtype=torch.float32, device=self.device)
+            self._static[name] = buf
+        buf.copy_(tensor, non_blocking=True)
+        return buf
+
+    def graph_mode(self, key):
+        """True once the eager warm-up iterations are done (DDP needs 11 before capture)."""
+        if not self.use_cuda_graph:
+            return False
+        if key == 'step':
+            self._graph_calls += 1
+        return self._graph_calls > self.graph_warmup_iters
+
+    def run_graphed(self, name, fn):
+        g = self._graphs.get(name)
+        if g is None:
+            from ganslate_b200 import _cabi
+            n0 = _cabi.lib().gb_launch_count()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            pool = next(iter(self._graphs.values())).pool() if self._graphs else None
+            with torch.cuda.graph(g, pool=pool):
+                fn()
+            self._graphs[name] = g
+            self.graph_launches_per_step += _cabi.lib().gb_launch_count() - n0
+        g.replay()
+
     def backward(self, loss, optimizer=None, retain_graph=False, loss_id=0):
         loss.backward(retain_graph=retain_graph)
 
@@ -124,6 +171,14 @@ class BaseGAN(ABC):
     def update_learning_rate(self):
         for scheduler in self.schedulers:
             scheduler.step()
+        if self.use_cuda_graph:
+            # keep lr a device tensor (graphs read it by address); LambdaLR assigns python floats
+            for optim in self.optimizers.values():
+                for group in optim.param_groups:
+                    if not torch.is_tensor(group['lr']):
+                        t = group.setdefault('_lr_tensor', torch.tensor(float(group['lr']), device=self.device))
+                        t.fill_(float(group['lr']))
+                        group['lr'] = t
 
     def save_checkpoint(self, iter_idx):
         """base.py:226-251 -- same file layout ({name: state_dict}, optimizer_G, optimizer_D)."""

@@ -48,14 +48,26 @@ class CycleGAN(BaseGAN):
         o = self.conf.train.gan.optimizer
         params_G = itertools.chain(self.networks['G_AB'].parameters(), self.networks['G_BA'].parameters())
         params_D = itertools.chain(self.networks['D_B'].parameters(), self.networks['D_A'].parameters())
-        self.optimizers['G'] = torch.optim.Adam(params_G, lr=o.lr_G, betas=(o.beta1, o.beta2))
-        self.optimizers['D'] = torch.optim.Adam(params_D, lr=o.lr_D, betas=(o.beta1, o.beta2))
+        self.optimizers['G'] = self.make_adam(params_G, o.lr_G, (o.beta1, o.beta2))
+        self.optimizers['D'] = self.make_adam(params_D, o.lr_D, (o.beta1, o.beta2))
 
     def set_input(self, input):
-        self.visuals['real_A'] = input['A'].to(self.device, non_blocking=True)
-        self.visuals['real_B'] = input['B'].to(self.device, non_blocking=True)
+        self.visuals['real_A'] = self.stage_input('real_A', input['A'])
+        self.visuals['real_B'] = self.stage_input('real_B', input['B'])
 
     def optimize_parameters(self):
+        """One iteration in the reference's order (cyclegan.py:92-124).  With `train.cuda_graph` the two halves
+        (forward + G step, D steps) are captured once and replayed; the ImagePool stays host logic in between."""
+        if self.graph_mode('step'):
+            self.run_graphed('G', self._phase_G)
+            fake_B = self.stage_input('pool_B', self.fake_B_pool.query(self.visuals['fake_B'].detach().clone()))
+            fake_A = self.stage_input('pool_A', self.fake_A_pool.query(self.visuals['fake_A'].detach().clone()))
+            self.run_graphed('D', lambda: self._phase_D(fake_B, fake_A))
+            return
+        self._phase_G()
+        self._phase_D(None, None)
+
+    def _phase_G(self):
         discriminators = [self.networks['D_B'], self.networks['D_A']]
         self.forward()
         self.metrics.update(self.training_metrics.compute_metrics_G(self.visuals))
@@ -64,12 +76,14 @@ class CycleGAN(BaseGAN):
         self.optimizers['G'].zero_grad(set_to_none=True)
         self.backward_G()
         self.optimizers['G'].step()
-        # ---- D_B and D_A
+
+    def _phase_D(self, fake_B, fake_A):
+        discriminators = [self.networks['D_B'], self.networks['D_A']]
         self.set_requires_grad(discriminators, True)
         self.optimizers['D'].zero_grad(set_to_none=True)
-        self.backward_D('D_B')
+        self.backward_D('D_B', fake_B)
         self.metrics.update(self.training_metrics.compute_metrics_D('D_B', self.pred_real, self.pred_fake))
-        self.backward_D('D_A')
+        self.backward_D('D_A', fake_A)
         self.metrics.update(self.training_metrics.compute_metrics_D('D_A', self.pred_real, self.pred_fake))
         self.optimizers['D'].step()
 
@@ -86,11 +100,14 @@ class CycleGAN(BaseGAN):
         self.visuals.update({'fake_B': fake_B, 'rec_A': rec_A, 'idt_A': idt_A, 'fake_A': fake_A, 'rec_B': rec_B,
                              'idt_B': idt_B})
 
-    def backward_D(self, discriminator):
+    def backward_D(self, discriminator, fake=None):
+        """`fake`: pooled fake images when the caller already queried the ImagePool (graph mode)."""
         if discriminator == 'D_B':
-            real, fake = self.visuals['real_B'], self.fake_B_pool.query(self.visuals['fake_B'])
+            real = self.visuals['real_B']
+            fake = self.fake_B_pool.query(self.visuals['fake_B']) if fake is None else fake
         elif discriminator == 'D_A':
-            real, fake = self.visuals['real_A'], self.fake_A_pool.query(self.visuals['fake_A'])
+            real = self.visuals['real_A']
+            fake = self.fake_A_pool.query(self.visuals['fake_A']) if fake is None else fake
         else:
             raise ValueError('The discriminator has to be either "D_A" or "D_B".')
         self.pred_real = self.networks[discriminator](real)

@@ -59,7 +59,7 @@ class Resnet2D(nn.Module):
         self.model = nn.Sequential(*model)
 
     def forward(self, x):
-        return layers.run_network(list(self.model), x)
+        return layers.run_network(self, list(self.model), x)
 
 
 class ResidualBlock(nn.Module):
@@ -83,9 +83,9 @@ class ResidualBlock(nn.Module):
     def gb_first_pad(self):
         return layers.first_pad(list(self.conv_block))
 
-    def gb_run(self, b, next_pad):
+    def gb_run(self, tape, b, next_pad):
         # x + conv_block(x): the add is fused into the second InstanceNorm kernel
-        return layers.run_sequence(list(self.conv_block), b, final_pad=next_pad, residual=b)
+        return layers.run_sequence(tape, list(self.conv_block), b, final_pad=next_pad, residual=b)
 
     def forward(self, x):
         raise RuntimeError("ResidualBlock is executed through Resnet2D.forward / run_sequence")

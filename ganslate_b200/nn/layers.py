@@ -6,6 +6,11 @@ e.g. ganslate/nn/generators/resnet/resnet2d.py:22-68).  To stay a drop-in -- ide
 "Conv") -- the layers here subclass the torch.nn classes for their parameter containers only.  Their compute is
 never torch's: `run_sequence` walks the list and fuses [ReflectionPad] -> Conv -> [InstanceNorm] ->
 [activation] -> [next ReflectionPad] into sm_100a kernel launches over channels-last bf16 buffers.
+
+A whole network is ONE torch.autograd.Function (`NetworkFn`): the forward pass records a tape of fused steps,
+the backward pass replays it in reverse.  Keeping the intermediate gradients out of autograd lets activation
+gradients stay fp32 (autograd would cast them to the bf16 dtype of the forward buffers) and lets residual
+branches accumulate into one gradient buffer inside the dgrad epilogue instead of through extra add kernels.
 """
 from typing import List, Optional, Sequence
 
@@ -99,33 +104,39 @@ class Tanh(_Marker, nn.Tanh):
 
 
 class Buf:
-    """A channels-last bf16 buffer travelling through a network: tensor + its reflection border + logical channels."""
-    __slots__ = ("t", "pad", "channels", "is_3d")
+    """A channels-last bf16 buffer travelling through a network.
 
-    def __init__(self, t, pad, channels, is_3d):
-        self.t, self.pad, self.channels, self.is_3d = t, pad, channels, is_3d
+    t: tensor (N, D, H+2*pad, W+2*pad, Cpad); pad: materialised reflection border; channels: logical channels;
+    raw: True if t is a bare convolution output (its gradient is the bf16 MMA operand of dgrad/wgrad),
+    False for an activation buffer (fp32 gradient)."""
+    __slots__ = ("t", "pad", "channels", "is_3d", "raw", "grad", "needs_grad_flag")
 
-
-def to_buf(x: torch.Tensor, pad: int) -> Buf:
-    return Buf(ops.ToChannelsLastFn.apply(x, pad), pad, x.shape[1], x.dim() == 5)
-
-
-def from_buf(b: Buf, act: int = ACT_NONE) -> torch.Tensor:
-    if b.pad != 0:
-        raise RuntimeError("cannot export a bordered buffer")
-    return ops.FromChannelsLastFn.apply(b.t, b.channels, b.is_3d, act)
+    def __init__(self, t, pad, channels, is_3d, raw=False):
+        self.t, self.pad, self.channels, self.is_3d, self.raw = t, pad, channels, is_3d, raw
+        self.grad = None  # filled during Tape.backward
+        self.needs_grad_flag = True  # False only for a network input that does not require grad
 
 
-def run_network(mods: Sequence[nn.Module], x: torch.Tensor) -> torch.Tensor:
-    """NC(D)HW fp32 in -> NC(D)HW fp32 out through the fused kernels. A trailing nn.Tanh (generator output,
-    resnet2d.py:65) is evaluated in fp32 while the result is exported."""
-    mods = flatten_modules(mods)
-    act = ACT_NONE
-    if len(mods) and isinstance(mods[-1], Tanh):
-        mods, act = mods[:-1], ACT_TANH
-    b = to_buf(x, first_pad(mods))
-    b = run_sequence(mods, b)
-    return from_buf(b, act)
+class Tape:
+    """Reverse-mode tape of fused steps; every step is a closure that consumes the gradient of its output
+    Buf(s) and produces / accumulates the gradients of its inputs."""
+
+    def __init__(self, param_needs_grad, input_needs_grad):
+        self.steps = []
+        self.param_needs_grad = param_needs_grad  # {id(param): bool}
+        self.input_needs_grad = input_needs_grad
+        self.param_grads = {}
+
+    def needs(self, p):
+        return p is not None and self.param_needs_grad.get(id(p), False)
+
+    def add_param_grad(self, p, g):
+        k = id(p)
+        self.param_grads[k] = g if k not in self.param_grads else self.param_grads[k] + g
+
+    def backward(self):
+        for step in reversed(self.steps):
+            step()
 
 
 def _is_norm(m):
@@ -164,7 +175,68 @@ def flatten_modules(mods) -> List[nn.Module]:
     return out
 
 
-def run_sequence(mods: Sequence[nn.Module], b: Buf, final_pad: int = 0, residual: Optional[Buf] = None) -> Buf:
+# ------------------------------------------------------------------------------------------------ fused steps
+def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0) -> Buf:
+    """conv (+bias, + optional epilogue activation).  Output: raw Buf (act NONE) or activation Buf."""
+    op = m.conv_op()
+    x = b.t
+    y = ops.conv_forward(op, x, m.weight, m.bias, act, slope)
+    out = Buf(y, 0, m.out_channels, b.is_3d, raw=(act == ACT_NONE))
+    weight, bias = m.weight, m.bias
+
+    def bwd():
+        g = out.grad
+        if g is None:
+            return
+        out.grad = None
+        if act != ACT_NONE:
+            g = ops.act_backward(g, y, act, slope)  # fp32 d_buf -> bf16 d_raw
+        if tape.needs(weight):
+            tape.add_param_grad(weight, op.run_wgrad(x, g, weight.shape))
+        if tape.needs(bias):
+            tape.add_param_grad(bias, ops.colsum(g, op.cout))
+        if b.grad is not None or b.needs_grad_flag:
+            b.grad = op.run_dgrad(g, weight, x.shape, into=b.grad)
+
+    if tape is not None:
+        tape.steps.append(bwd)
+    return out
+
+
+def step_norm_act(tape: Tape, raw: Buf, norm: bool, act: int, slope: float, out_pad: int, eps: float,
+                  residual: Optional[Buf] = None) -> Buf:
+    """[instance-norm] + activation [+ residual] + reflection border of the result."""
+    if not raw.raw and not (norm is False and act == ACT_NONE):
+        raise NotImplementedError("normalisation of a non-convolution output")
+    if not raw.raw:
+        raise NotImplementedError("explicit border copy of an activation buffer (no reference network needs it)")
+    t, stats = ops.norm_act_forward(raw.t, residual.t if residual is not None else None,
+                                    residual.pad if residual is not None else 0, norm, act, slope, out_pad, eps)
+    out = Buf(t, out_pad, raw.channels, raw.is_3d)
+    x = raw.t
+
+    def bwd():
+        g = out.grad
+        if g is None:
+            return
+        out.grad = None
+        dres = None
+        if residual is not None and residual.needs_grad_flag:
+            if residual.grad is not None:
+                raise NotImplementedError("residual gradient buffer already exists (unsupported topology)")
+            dres = torch.zeros(residual.t.shape, dtype=torch.float32, device=x.device)
+            residual.grad = dres
+        raw.grad = ops.norm_act_backward(x, stats, t, g, norm, act, slope, out_pad, eps, dres32=dres,
+                                         res_pad=residual.pad if residual is not None else 0,
+                                         need_draw=raw.needs_grad_flag)
+
+    if tape is not None:
+        tape.steps.append(bwd)
+    return out
+
+
+def run_sequence(tape: Tape, mods: Sequence[nn.Module], b: Buf, final_pad: int = 0,
+                 residual: Optional[Buf] = None) -> Buf:
     """Execute a list of layers on buffer `b`, fusing pad/conv/norm/activation groups.
 
     final_pad: reflection border wanted on the last produced buffer (what follows this sequence).
@@ -179,16 +251,14 @@ def run_sequence(mods: Sequence[nn.Module], b: Buf, final_pad: int = 0, residual
             if b.pad != m.pad_amount:
                 if b.pad != 0:
                     raise RuntimeError("buffer already carries a different reflection border")
-                # producer did not materialise the border: copy-with-border pass
-                t = ops.NormActFn.apply(b.t, None, False, ACT_NONE, 0.0, m.pad_amount, 0, 1e-5)
-                b = Buf(t, m.pad_amount, b.channels, b.is_3d)
+                # the producer did not materialise the border: copy-with-border pass
+                b = step_norm_act(tape, b, False, ACT_NONE, 0.0, m.pad_amount, 1e-5)
             i += 1
             pending_pad = m.pad_amount
             if i >= n or not isinstance(mods[i], _ConvMixin):
                 raise RuntimeError("ReflectionPad must be followed by a convolution")
             continue
         if isinstance(m, _ConvMixin):
-            op = m.conv_op()
             if b.pad != pending_pad:
                 raise RuntimeError(f"convolution input carries border {b.pad}, expected {pending_pad}")
             pending_pad = 0
@@ -203,32 +273,67 @@ def run_sequence(mods: Sequence[nn.Module], b: Buf, final_pad: int = 0, residual
             if act is not None:
                 j += 1
             act_id, slope = act if act is not None else (ACT_NONE, 0.0)
-            # border wanted by whatever consumes this group's output
-            nxt = first_pad(mods[j:]) if j < n else final_pad
-            is_last_group = j >= n
-            res = residual if (is_last_group and residual is not None) else None
-            x = b.t  # the whole (bordered) buffer is the convolution input; the border replaces ReflectionPad
+            nxt = first_pad(mods[j:]) if j < n else final_pad  # border wanted by the consumer of this group
+            res = residual if (j >= n and residual is not None) else None
             if norm or res is not None or nxt > 0:
-                raw = ops.ConvFn.apply(x, m.weight, m.bias, op, ACT_NONE, 0.0)
-                eps = mods[i + 1].eps if norm else 1e-5
-                t = ops.NormActFn.apply(raw, res.t if res is not None else None, norm, act_id, slope, nxt,
-                                        res.pad if res is not None else 0, eps)
-                b = Buf(t, nxt, m.out_channels, b.is_3d)
+                raw = step_conv(tape, b, m)
+                b = step_norm_act(tape, raw, norm, act_id, slope, nxt, mods[i + 1].eps if norm else 1e-5, res)
             else:
-                # no normalisation: bias + activation run in the convolution epilogue
-                t = ops.ConvFn.apply(x, m.weight, m.bias, op, act_id, slope)
-                b = Buf(t, 0, m.out_channels, b.is_3d)
+                b = step_conv(tape, b, m, act_id, slope)  # bias + activation in the convolution epilogue
             i = j
             continue
         if hasattr(m, "gb_run"):
             nxt = first_pad(mods[i + 1:]) if i + 1 < n else final_pad
-            b = m.gb_run(b, nxt)
+            b = m.gb_run(tape, b, nxt)
             i += 1
             continue
-        if isinstance(m, (nn.Identity,)):
+        if isinstance(m, nn.Identity):
             i += 1
             continue
         raise NotImplementedError(f"run_sequence: unsupported layer {type(m).__name__} at position {i}")
-    if residual is not None and not any(isinstance(m, _ConvMixin) for m in mods):
-        raise RuntimeError("residual requested on a sequence without convolutions")
     return b
+
+
+class NetworkFn(torch.autograd.Function):
+    """One network = one autograd node. forward(x NC(D)HW fp32) -> NC(D)HW fp32."""
+
+    @staticmethod
+    def forward(ctx, mods, x, *params):
+        needs = {id(p): ctx.needs_input_grad[2 + k] for k, p in enumerate(params)}
+        record = any(ctx.needs_input_grad[1:])
+        tape = Tape(needs, ctx.needs_input_grad[1]) if record else None
+        act = ACT_NONE
+        if len(mods) and isinstance(mods[-1], Tanh):
+            mods, act = mods[:-1], ACT_TANH
+        pad = first_pad(mods)
+        b0 = Buf(ops.to_channels_last(x, pad), pad, x.shape[1], x.dim() == 5)
+        b0.needs_grad_flag = bool(ctx.needs_input_grad[1])
+        b = run_sequence(tape, mods, b0)
+        if b.pad != 0:
+            raise RuntimeError("cannot export a bordered buffer")
+        y = ops.from_channels_last(b.t, b.channels, b.is_3d, act)
+        ctx.tape, ctx.params, ctx.b0, ctx.b_last, ctx.act = tape, params, b0, b, act
+        ctx.in_shape = tuple(x.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        tape, b0, b = ctx.tape, ctx.b0, ctx.b_last
+        tape.param_grads = {}
+        b.grad = ops.from_channels_last_backward(dy, b.t.shape, b.channels, pre=b.t if ctx.act == ACT_TANH else None,
+                                                 fp32=not b.raw)
+        tape.backward()
+        dx = None
+        if ctx.needs_input_grad[1] and b0.grad is not None:
+            dx = ops.to_channels_last_backward(b0.grad, b0.pad, ctx.in_shape)
+        b0.grad = None
+        grads = [tape.param_grads.get(id(p)) for p in ctx.params]
+        tape.param_grads = {}
+        return (None, dx, *grads)
+
+
+def run_network(net: nn.Module, mods: Sequence[nn.Module], x: torch.Tensor) -> torch.Tensor:
+    """NC(D)HW fp32 in -> NC(D)HW fp32 out through the fused kernels (a trailing nn.Tanh is evaluated in fp32
+    while the result is exported)."""
+    params = [p for p in net.parameters()]
+    return NetworkFn.apply(flatten_modules(mods), x, *params)

@@ -21,6 +21,22 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# Optional per-launch timing (bench.py roofline): a list that receives (family, work, unit, event0, event1).
+PROFILE = None
+
+
+def _call(family, work, unit, what, fn, *args):
+    """Launch through the C ABI; when profiling is on, bracket the launch with CUDA events on the launch stream."""
+    if PROFILE is None:
+        _cabi.check(fn(*args), what)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _cabi.check(fn(*args), what)
+    e1.record()
+    PROFILE.append((family, work, unit, e0, e1))
+
+
 def _require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise RuntimeError(f"ganslate_b200: {what} must live on a CUDA device -- there is no CPU path "
@@ -148,6 +164,12 @@ class ConvOp:
                 o.append((ext[d] + 2 * self.padding[d] - self.kernel[d]) // self.stride[d] + 1)
         return tuple(o)
 
+    def flops(self, in_ext, batch):
+        """Algorithmic FLOPs of one pass: 2 * positions * Cin * Cout * taps, positions =
+        output pixels for a convolution, input pixels for a transposed one; padded channels are not counted."""
+        ext = in_ext if self.transposed else self.out_extent(in_ext)
+        return 2.0 * batch * ext[0] * ext[1] * ext[2] * self.cin * self.cout * self.T
+
     # ------------------------------------------------------------------ packing
     def packed(self, weight: torch.Tensor, which: str) -> torch.Tensor:
         key = (which, weight.data_ptr(), weight._version, weight.device)
@@ -211,20 +233,24 @@ class ConvOp:
         p.bias = bias.data_ptr() if bias is not None else None
         p.ncols, p.npad = self.cout, self.fwd_rows_pad
         p.act, p.act_slope = act, slope
-        _cabi.check(_cabi.lib().gb_conv_data(C.byref(p), _stream()), "gb_conv_data(fwd)")
+        _call("conv_fwd", self.flops((D, H, W), N), "flop", "gb_conv_data(fwd)", _cabi.lib().gb_conv_data, C.byref(p),
+              _stream())
         return y
 
-    def run_dgrad(self, dy, weight, in_shape):
-        """dy: (N,D,Ho,Wo,cout_pad) -> gradient wrt the input buffer, shape in_shape."""
-        dx = torch.empty(in_shape, dtype=torch.bfloat16, device=dy.device)
+    def run_dgrad(self, dy, weight, in_shape, into=None):
+        """dy: bf16 (N,D,Ho,Wo,cout_pad) -> FP32 gradient wrt the input buffer (shape in_shape).
+        `into`: an existing fp32 gradient buffer to accumulate into (residual branches)."""
+        dx = into if into is not None else torch.empty(in_shape, dtype=torch.float32, device=dy.device)
         p = self._params("dgrad")
+        p.out_fp32, p.accumulate = 1, 1 if into is not None else 0
         p.inp, p.out = make_view(dy), make_view(dx)
         wp = self.packed(weight, "dgrad")
         p.wpacked = wp.data_ptr()
         p.bias = None
         p.ncols, p.npad = self.cin, self.dgrad_rows_pad
         p.act, p.act_slope = ACT_NONE, 0.0
-        _cabi.check(_cabi.lib().gb_conv_data(C.byref(p), _stream()), "gb_conv_data(dgrad)")
+        _call("conv_dgrad", self.flops(tuple(in_shape[1:4]), in_shape[0]), "flop", "gb_conv_data(dgrad)",
+              _cabi.lib().gb_conv_data, C.byref(p), _stream())
         return dx
 
     def run_wgrad(self, x, dy, weight_shape):
@@ -243,7 +269,8 @@ class ConvOp:
             p.rows, p.kpad, p.splits = self.wg_rows, self.wg_kpad, 0
             cache["wgrad"] = p
         p.plain, p.gathered, p.dw = make_view(plain), make_view(gathered), ws.data_ptr()
-        _cabi.check(_cabi.lib().gb_conv_wgrad(C.byref(p), _stream()), "gb_conv_wgrad")
+        _call("conv_wgrad", self.flops(tuple(x.shape[1:4]), x.shape[0]), "flop", "gb_conv_wgrad",
+              _cabi.lib().gb_conv_wgrad, C.byref(p), _stream())
         dw = torch.empty(weight_shape, dtype=torch.float32, device=x.device)
         cols = self.cout if self.transposed else self.cin
         cols_pad = self.cout_pad if self.transposed else self.cin_pad
@@ -259,167 +286,119 @@ def colsum(t: torch.Tensor, n: int) -> torch.Tensor:
     return out[:n]
 
 
-def act_backward(dy: torch.Tensor, y: torch.Tensor, act: int, slope: float) -> torch.Tensor:
-    """dx = dy * act'(.) computed from the forward output y (epilogue activations: tanh / leaky)."""
+# ------------------------------------------------------------------------------------------------------------
+# Plain (non-autograd) forward / backward helpers.  Gradient dtypes: the gradient wrt a RAW convolution output
+# is bf16 (it is an MMA operand of dgrad / wgrad); the gradient wrt an ACTIVATION buffer is fp32, because
+# InstanceNorm-backward subtracts its mean and bf16 rounding there costs 10-30 % error on real GAN gradients.
+# ------------------------------------------------------------------------------------------------------------
+def conv_forward(op: ConvOp, x, weight, bias, act=ACT_NONE, slope=0.0):
+    _require_cuda(x, "convolution input")
+    return op.run_fwd(x, weight, bias, act, slope)
+
+
+def act_backward(dy32: torch.Tensor, y: torch.Tensor, act: int, slope: float) -> torch.Tensor:
+    """bf16 d_raw = dy * act'(.) from the forward output y (epilogue activations), dy fp32."""
     dx = torch.empty_like(y)
     p = InBwdParams()
-    p.x, p.y, p.dy_a, p.dx = make_view(y), make_view(y), make_view(dy), make_view(dx)
+    p.x, p.y, p.dy_a, p.dx = make_view(y), make_view(y), make_view(dy32), make_view(dx)
     p.act, p.act_slope, p.eps = act, slope, 1e-5
     _cabi.check(_cabi.lib().gb_in_bwd(C.byref(p), _stream()), "gb_in_bwd(act)")
     return dx
 
 
-class ConvFn(torch.autograd.Function):
-    """y = act(conv(x) + b) on channels-last bf16 buffers; backward = dgrad / wgrad / bias colsum kernels."""
-
-    @staticmethod
-    def forward(ctx, x, weight, bias, op: ConvOp, act, slope):
-        _require_cuda(x, "convolution input")
-        x = x.contiguous()
-        y = op.run_fwd(x, weight, bias, act, slope)
-        ctx.op, ctx.act, ctx.slope = op, act, slope
-        ctx.has_bias = bias is not None
-        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
-        return y
-
-    @staticmethod
-    def backward(ctx, dy):
-        x, weight, y = ctx.saved_tensors
-        op = ctx.op
-        dy = dy.contiguous()
-        if ctx.act != ACT_NONE:
-            dy = act_backward(dy, y, ctx.act, ctx.slope)
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = op.run_dgrad(dy, weight, x.shape)
-        if ctx.needs_input_grad[1]:
-            dw = op.run_wgrad(x, dy, weight.shape)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dy, op.cout)
-        return dx, dw, db, None, None, None
+def norm_act_forward(raw, residual, res_pad, norm, act, slope, out_pad, eps):
+    """-> (buffer with reflection border out_pad, stats or None)"""
+    _require_cuda(raw, "normalisation input")
+    N, D, H, W, Cc = raw.shape
+    lib = _cabi.lib()
+    stats = None
+    xv = make_view(raw)
+    if norm:
+        stats = torch.zeros((N, Cc, 2), dtype=torch.float32, device=raw.device)
+        _call("in_stats", raw.numel() * 2, "byte", "gb_in_stats", lib.gb_in_stats, C.byref(xv), stats.data_ptr(), _stream())
+    out = torch.empty((N, D, H + 2 * out_pad, W + 2 * out_pad, Cc), dtype=torch.bfloat16, device=raw.device)
+    p = InFwdParams()
+    p.x, p.y = xv, make_view(out, out_pad)
+    if residual is not None:
+        p.res = make_view(residual, res_pad)
+    p.stats = stats.data_ptr() if norm else None
+    p.eps, p.act, p.act_slope, p.res_before_act = eps, act, slope, 0
+    _call("in_fwd", raw.numel() * 2 * (3 if residual is not None else 2), "byte", "gb_in_fwd", lib.gb_in_fwd,
+          C.byref(p), _stream())
+    return out, stats
 
 
-class NormActFn(torch.autograd.Function):
-    """buffer = reflect_border( act(instance_norm(raw)) [+ residual] ).
-
-    norm=False degenerates to activation / copy-with-border. Replaces nn.InstanceNorm + nn.ReLU/LeakyReLU (+ the
-    residual add of ResidualBlock, ganslate/nn/generators/resnet/resnet2d.py:93) and the following nn.ReflectionPad2d.
-    """
-
-    @staticmethod
-    def forward(ctx, raw, residual, norm, act, slope, out_pad, res_pad, eps):
-        _require_cuda(raw, "normalisation input")
-        raw = raw.contiguous()
-        N, D, H, W, Cc = raw.shape
-        lib = _cabi.lib()
-        stats = None
-        xv = make_view(raw)
+def norm_act_backward(raw, stats, out, dout32, norm, act, slope, out_pad, eps, dres32=None, res_pad=0, need_draw=True):
+    """dout32: fp32 gradient wrt the (bordered) output buffer. Returns bf16 d_raw.
+    dres32: fp32 gradient buffer of the residual input; its interior is OVERWRITTEN with fold(dout32)."""
+    lib = _cabi.lib()
+    N, D, H, W, Cc = raw.shape
+    p = InBwdParams()
+    p.x = make_view(raw)
+    p.dy_b = make_view(dout32, out_pad)
+    if dres32 is not None:
+        p.dy_sum = make_view(dres32, res_pad)
+    draw = torch.empty_like(raw)
+    p.dx = make_view(draw)
+    p.eps = eps
+    if need_draw:
         if norm:
-            stats = torch.zeros((N, Cc, 2), dtype=torch.float32, device=raw.device)
-            _cabi.check(lib.gb_in_stats(C.byref(xv), stats.data_ptr(), _stream()), "gb_in_stats")
-        out = torch.empty((N, D, H + 2 * out_pad, W + 2 * out_pad, Cc), dtype=torch.bfloat16, device=raw.device)
-        p = InFwdParams()
-        p.x, p.y = xv, make_view(out, out_pad)
-        if residual is not None:
-            p.res = make_view(residual, res_pad)
-        p.stats = stats.data_ptr() if norm else None
-        p.eps, p.act, p.act_slope, p.res_before_act = eps, act, slope, 0
-        _cabi.check(lib.gb_in_fwd(C.byref(p), _stream()), "gb_in_fwd")
-        ctx.cfg = (norm, act, slope, out_pad, res_pad, eps)
-        ctx.res_shape = residual.shape if residual is not None else None
-        ctx.save_for_backward(raw, stats, out if (not norm and act != ACT_NONE) else None)
-        return out
-
-    @staticmethod
-    def backward(ctx, dout):
-        raw, stats, out = ctx.saved_tensors
-        norm, act, slope, out_pad, res_pad, eps = ctx.cfg
-        dout = dout.contiguous()
-        lib = _cabi.lib()
-        N, D, H, W, Cc = raw.shape
-        p = InBwdParams()
-        p.x = make_view(raw)
-        p.dy_b = make_view(dout, out_pad)
-        dres = None
-        if ctx.res_shape is not None and ctx.needs_input_grad[1]:
-            dres = torch.zeros(ctx.res_shape, dtype=torch.bfloat16, device=raw.device)
-            p.dy_sum = make_view(dres, res_pad)
-        draw = None
-        if ctx.needs_input_grad[0]:
-            draw = torch.empty_like(raw)
-            p.dx = make_view(draw)
-            if norm:
-                bstats = torch.zeros((N, Cc, 2), dtype=torch.float32, device=raw.device)
-                p.stats, p.bstats = stats.data_ptr(), bstats.data_ptr()
-            elif act != ACT_NONE:
-                p.y = make_view(out, out_pad)
-            p.eps, p.act, p.act_slope = eps, act, slope
-            _cabi.check(lib.gb_in_bwd(C.byref(p), _stream()), "gb_in_bwd")
-        elif dres is not None:
-            # only the residual branch needs a gradient: fold the border into a scratch dx-less pass
-            scratch = torch.empty_like(raw)
-            p.dx = make_view(scratch)
-            p.act, p.eps = ACT_NONE, eps
-            _cabi.check(lib.gb_in_bwd(C.byref(p), _stream()), "gb_in_bwd(res)")
-        return draw, dres, None, None, None, None, None, None
+            bstats = torch.zeros((N, Cc, 2), dtype=torch.float32, device=raw.device)
+            p.stats, p.bstats = stats.data_ptr(), bstats.data_ptr()
+        elif act != ACT_NONE:
+            p.y = make_view(out, out_pad)
+        p.act, p.act_slope = act, slope
+    else:
+        p.act = ACT_NONE  # only the residual branch needs the (folded) gradient
+    # algorithmic bytes: reduce reads dy(4)+x(2); apply reads dy(4)+x(2), writes dx(2) [+ dres(4)]
+    nbytes = raw.numel() * ((6 if norm else 0) + 8 + (4 if dres32 is not None else 0))
+    _call("in_bwd", nbytes, "byte", "gb_in_bwd", lib.gb_in_bwd, C.byref(p), _stream())
+    return draw if need_draw else None
 
 
-class ToChannelsLastFn(torch.autograd.Function):
+def to_channels_last(x: torch.Tensor, pad: int) -> torch.Tensor:
     """NC(D)HW fp32 -> bf16 buffer with reflection border `pad` (cyclegan.py:89-90 hands NCHW fp32 to the nets)."""
-
-    @staticmethod
-    def forward(ctx, x, pad):
-        _require_cuda(x, "network input")
-        x = x.contiguous().float()
-        if x.dim() == 4:
-            N, Cc, H, W = x.shape
-            D = 1
-        else:
-            N, Cc, D, H, W = x.shape
-        out = torch.empty((N, D, H + 2 * pad, W + 2 * pad, pad8(Cc)), dtype=torch.bfloat16, device=x.device)
-        v = make_view(out, pad)
-        _cabi.check(_cabi.lib().gb_nchw_to_cl(x.data_ptr(), Cc, C.byref(v), None, _stream()), "gb_nchw_to_cl")
-        ctx.pad, ctx.shape = pad, x.shape
-        return out
-
-    @staticmethod
-    def backward(ctx, dout):
-        dout = dout.contiguous()
-        dx = torch.empty(ctx.shape, dtype=torch.float32, device=dout.device)
-        v = make_view(dout, ctx.pad)
-        _cabi.check(_cabi.lib().gb_cl_to_nchw(C.byref(v), dx.data_ptr(), ctx.shape[1], 1, ACT_NONE, _stream()),
-                    "gb_cl_to_nchw")
-        return dx, None
+    _require_cuda(x, "network input")
+    x = x.contiguous().float()
+    if x.dim() == 4:
+        N, Cc, H, W = x.shape
+        D = 1
+    else:
+        N, Cc, D, H, W = x.shape
+    out = torch.empty((N, D, H + 2 * pad, W + 2 * pad, pad8(Cc)), dtype=torch.bfloat16, device=x.device)
+    v = make_view(out, pad)
+    _cabi.check(_cabi.lib().gb_nchw_to_cl(x.data_ptr(), Cc, C.byref(v), None, 0, _stream()), "gb_nchw_to_cl")
+    return out
 
 
-class FromChannelsLastFn(torch.autograd.Function):
-    """bf16 plain buffer (N,D,H,W,Cpad) -> NC(D)HW fp32 with the first `channels` channels.
+def to_channels_last_backward(dbuf32: torch.Tensor, pad: int, shape) -> torch.Tensor:
+    """fp32 gradient of the bordered buffer -> NC(D)HW fp32 (border folded back)."""
+    dx = torch.empty(shape, dtype=torch.float32, device=dbuf32.device)
+    v = make_view(dbuf32, pad)
+    _cabi.check(_cabi.lib().gb_cl_to_nchw(C.byref(v), dx.data_ptr(), shape[1], 1, ACT_NONE, 1, _stream()), "gb_cl_to_nchw")
+    return dx
 
-    act=ACT_TANH applies the generator's final nn.Tanh in fp32 during the export (and its derivative, from the
-    saved pre-activation, during the import of the gradient)."""
 
-    @staticmethod
-    def forward(ctx, x, channels, is_3d, act=ACT_NONE):
-        x = x.contiguous()
-        N, D, H, W, Cc = x.shape
-        shape = (N, channels, D, H, W) if is_3d else (N, channels, H, W)
-        out = torch.empty(shape, dtype=torch.float32, device=x.device)
-        v = make_view(x)
-        _cabi.check(_cabi.lib().gb_cl_to_nchw(C.byref(v), out.data_ptr(), channels, 0, act, _stream()), "gb_cl_to_nchw")
-        ctx.in_shape, ctx.channels, ctx.act = x.shape, channels, act
-        ctx.save_for_backward(x if act == ACT_TANH else None)
-        return out
+def from_channels_last(x: torch.Tensor, channels: int, is_3d: bool, act: int = ACT_NONE) -> torch.Tensor:
+    """bf16 plain buffer (N,D,H,W,Cpad) -> NC(D)HW fp32; act=ACT_TANH evaluates the output tanh in fp32."""
+    N, D, H, W, Cc = x.shape
+    shape = (N, channels, D, H, W) if is_3d else (N, channels, H, W)
+    out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    v = make_view(x)
+    _cabi.check(_cabi.lib().gb_cl_to_nchw(C.byref(v), out.data_ptr(), channels, 0, act, 0, _stream()), "gb_cl_to_nchw")
+    return out
 
-    @staticmethod
-    def backward(ctx, dout):
-        (pre,) = ctx.saved_tensors
-        dout = dout.contiguous().float()
-        dx = torch.empty(ctx.in_shape, dtype=torch.bfloat16, device=dout.device)
-        v = make_view(dx)
-        pv = make_view(pre) if pre is not None else None
-        _cabi.check(_cabi.lib().gb_nchw_to_cl(dout.data_ptr(), ctx.channels, C.byref(v),
-                                              C.byref(pv) if pv is not None else None, _stream()), "gb_nchw_to_cl")
-        return dx, None, None, None
+
+def from_channels_last_backward(dout: torch.Tensor, buf_shape, channels: int, pre=None, fp32=False) -> torch.Tensor:
+    """NC(D)HW fp32 gradient -> channels-last gradient (bf16 d_raw, or fp32 for an activation buffer);
+    pre: the saved pre-activation when the export applied tanh."""
+    dout = dout.contiguous().float()
+    dx = torch.empty(buf_shape, dtype=torch.float32 if fp32 else torch.bfloat16, device=dout.device)
+    v = make_view(dx)
+    pv = make_view(pre) if pre is not None else None
+    _cabi.check(_cabi.lib().gb_nchw_to_cl(dout.data_ptr(), channels, C.byref(v), C.byref(pv) if pv is not None else None,
+                                          1 if fp32 else 0, _stream()), "gb_nchw_to_cl")
+    return dx
 
 
 class MseConstFn(torch.autograd.Function):

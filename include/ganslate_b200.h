@@ -74,6 +74,8 @@ typedef struct gb_conv_params {
   int8_t taps[GB_MAX_TAPS][4]; /* (dz,dy,dx,unused) */
   int32_t act;               /* GB_ACT_NONE / GB_ACT_TANH / GB_ACT_LEAKY applied in the epilogue */
   float act_slope;
+  int32_t out_fp32;          /* 1: `out` is an fp32 view (activation gradients are carried in fp32) */
+  int32_t accumulate;        /* 1: out += result (fp32 only; residual branches share one gradient buffer) */
 } gb_conv_params;
 
 int gb_conv_data(const gb_conv_params* p, void* stream);
@@ -147,9 +149,9 @@ int gb_in_fwd(const gb_in_fwd_params* p, void* stream);
 typedef struct gb_in_bwd_params {
   gb_view x;                 /* raw conv output saved by forward (bf16) */
   gb_view y;                 /* forward output (needed for tanh / no-norm activations), may be NULL ptr */
-  gb_view dy_a;              /* gradient wrt y, plain view (ptr NULL: absent) */
-  gb_view dy_b;              /* gradient wrt the reflection-PADDED y (pad>0: border folded in); ptr NULL: absent */
-  gb_view dy_sum;            /* optional: dy_a + fold(dy_b) is written here (residual chain); ptr NULL: skip */
+  gb_view dy_a;              /* FP32 gradient wrt y, plain view (ptr NULL: absent) */
+  gb_view dy_b;              /* FP32 gradient wrt the reflection-PADDED y (pad>0: border folded in); ptr NULL: absent */
+  gb_view dy_sum;            /* optional FP32: dy_a + fold(dy_b) is written here (residual chain); ptr NULL: skip */
   gb_view dx;                /* gradient wrt x (bf16) */
   const float* stats;        /* forward stats; NULL = no normalisation */
   float* bstats;             /* [N][C][2] workspace (sum g, sum g*xhat), zeroed by caller */
@@ -166,10 +168,10 @@ int gb_in_bwd(const gb_in_bwd_params* p, void* stream);
 /* ---- layout conversion at the network boundary (set_input / module outputs; cyclegan.py:89-90) ---- */
 /* NC(D)HW fp32 -> channels-last bf16 view (zero-fills padded channels, writes reflected border if dst.pad>0).
  * If `pre` is non-NULL the value is multiplied by tanh'(pre) = 1 - tanh(pre)^2 (backward of the tanh export). */
-int gb_nchw_to_cl(const float* src, int C, const gb_view* dst, const gb_view* pre, void* stream);
+int gb_nchw_to_cl(const float* src, int C, const gb_view* dst, const gb_view* pre, int dst_fp32, void* stream);
 /* channels-last bf16 view (border folded in when src.pad>0 and fold!=0) -> NC(D)HW fp32.
  * act = GB_ACT_TANH applies the generator's output nn.Tanh (resnet2d.py:65) in fp32 on the way out. */
-int gb_cl_to_nchw(const gb_view* src, float* dst, int C, int fold, int act, void* stream);
+int gb_cl_to_nchw(const gb_view* src, float* dst, int C, int fold, int act, int src_fp32, void* stream);
 
 /* ---- losses --------------------------------------------------------------------------------
  * LSGAN: mean((p - t)^2) (ganslate/nn/losses/adversarial_loss.py:29,60-62); grad = 2(p-t)/n.
@@ -181,6 +183,8 @@ int gb_l1(const float* a, const float* b, int64_t n, float* loss, float* grad_a,
 /* ---- misc ---- */
 int gb_version(void);
 const char* gb_last_error(void);
+/* number of kernels launched through this library since load (bench.py's gpu_launches) */
+unsigned long long gb_launch_count(void);
 /* debug knobs for bring-up (e.g. descriptor variants); returns previous value */
 int gb_debug_knob(int knob, int value);
 

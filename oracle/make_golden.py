@@ -1,0 +1,108 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.json from the REFERENCE's own modules.
+
+Run in the build container (needs /root/reference):  python oracle/make_golden.py
+The reference has no golden vectors of its own; these fixtures are produced by importing
+its nn modules (oracle/reference_import.py) and driving them through one CycleGAN iteration exactly as
+ganslate/nn/gans/unpaired/cyclegan.py:92-214 does (the recipe classes themselves do not import on py3.12).
+"""
+import itertools
+import json
+import os
+import random
+import sys
+from types import SimpleNamespace
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import reference_import as R  # noqa: E402
+
+
+def tensor_digest(t):
+    t = t.detach().double().flatten()
+    idx = torch.linspace(0, t.numel() - 1, 5).long()
+    return {"sum": t.sum().item(), "abs_sum": t.abs().sum().item(), "sq_sum": (t * t).sum().item(),
+            "samples": t[idx].tolist(), "numel": t.numel()}
+
+
+def reference_cyclegan_step(size, n_blocks, seed=0, data_seed=1, batch=1, lambda_identity=0.0):
+    m = R.modules()
+    torch.manual_seed(seed)
+    random.seed(0)
+    nets = {}
+    for name in ("G_AB", "G_BA", "D_B", "D_A"):  # cyclegan.py:52 order
+        net = m["Resnet2D"](3, 3, "instance", n_blocks) if name[0] == "G" else m["PatchGAN2D"](3, 64, 3, (4, 4), "instance")
+        m["init_weights"](net, "normal", 0.02)
+        nets[name] = net
+    conf = SimpleNamespace(train=SimpleNamespace(gan=SimpleNamespace(optimizer=SimpleNamespace(
+        lambda_AB=10.0, lambda_BA=10.0, lambda_identity=lambda_identity, proportion_ssim=0.0))))
+    crit_adv = m["AdversarialLoss"]("lsgan")
+    crit_G = m["CycleGANLosses"](conf)
+    opt_G = torch.optim.Adam(itertools.chain(nets["G_AB"].parameters(), nets["G_BA"].parameters()), lr=2e-4, betas=(0.5, 0.999))
+    opt_D = torch.optim.Adam(itertools.chain(nets["D_B"].parameters(), nets["D_A"].parameters()), lr=2e-4, betas=(0.5, 0.999))
+    pool_A, pool_B = m["ImagePool"](50), m["ImagePool"](50)
+    g = torch.Generator().manual_seed(data_seed)
+    real_A = torch.rand((batch, 3, size, size), generator=g) * 2 - 1
+    real_B = torch.rand((batch, 3, size, size), generator=g) * 2 - 1
+
+    def set_rg(ns, flag):
+        for n in ns:
+            for p in n.parameters():
+                p.requires_grad = flag
+
+    v = {"real_A": real_A, "real_B": real_B}
+    v["fake_B"] = nets["G_AB"](real_A)
+    v["rec_A"] = nets["G_BA"](v["fake_B"])
+    v["fake_A"] = nets["G_BA"](real_B)
+    v["rec_B"] = nets["G_AB"](v["fake_A"])
+    v["idt_A"] = v["idt_B"] = None
+    if crit_G.is_using_identity():
+        v["idt_B"] = nets["G_AB"](real_B)
+        v["idt_A"] = nets["G_BA"](real_A)
+    losses = {}
+    set_rg([nets["D_B"], nets["D_A"]], False)
+    opt_G.zero_grad(set_to_none=True)
+    losses["G_AB"] = crit_adv(nets["D_B"](v["fake_B"]), target_is_real=True)
+    losses["G_BA"] = crit_adv(nets["D_A"](v["fake_A"]), target_is_real=True)
+    lg = crit_G(v)
+    losses.update(lg)
+    (sum(lg.values()) + losses["G_AB"] + losses["G_BA"]).backward()
+    grads = {f"{n}.{k}": tensor_digest(p.grad) for n in ("G_AB", "G_BA") for k, p in nets[n].named_parameters()}
+    opt_G.step()
+    set_rg([nets["D_B"], nets["D_A"]], True)
+    opt_D.zero_grad(set_to_none=True)
+    for name, real, fake, pool in (("D_B", real_B, v["fake_B"], pool_B), ("D_A", real_A, v["fake_A"], pool_A)):
+        fake = pool.query(fake)
+        pr, pf = nets[name](real), nets[name](fake.detach())
+        losses[name] = crit_adv(pr, target_is_real=True) + crit_adv(pf, target_is_real=False)
+        losses[name].backward()
+    grads.update({f"{n}.{k}": tensor_digest(p.grad) for n in ("D_B", "D_A") for k, p in nets[n].named_parameters()})
+    opt_D.step()
+    weights = {f"{n}.{k}": tensor_digest(p) for n in nets for k, p in nets[n].named_parameters()}
+    return {
+        "config": {"size": size, "n_blocks": n_blocks, "seed": seed, "data_seed": data_seed, "batch": batch,
+                   "lambda_identity": lambda_identity},
+        "losses": {k: float(x) for k, x in losses.items()},
+        "visuals": {k: tensor_digest(v[k]) for k in ("fake_B", "rec_A", "fake_A", "rec_B")},
+        "grads": grads,
+        "weights_after_step": weights,
+        "state_dict_keys": {n: list(nets[n].state_dict().keys()) for n in nets},
+        "param_counts": {n: sum(p.numel() for p in nets[n].parameters()) for n in nets},
+    }
+
+
+def main():
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    cases = {"cyclegan_step_32px_2blk": dict(size=32, n_blocks=2),
+             "cyclegan_step_64px_3blk_idt": dict(size=64, n_blocks=3, lambda_identity=0.5, batch=2)}
+    for name, kw in cases.items():
+        rep = reference_cyclegan_step(**kw)
+        with open(os.path.join(out_dir, name + ".json"), "w") as f:
+            json.dump(rep, f)
+        print(name, {k: round(v, 6) for k, v in rep["losses"].items()})
+
+
+if __name__ == "__main__":
+    main()

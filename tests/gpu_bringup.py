@@ -11,6 +11,8 @@ import torch.nn.functional as F
 from ganslate_b200 import ops, _cabi
 from ganslate_b200.nn import layers
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = "cuda"
@@ -40,7 +42,7 @@ def conv_case(name, cin, cout, k, s, p, H, W, N=1, transposed=False, op_pad=0, r
     x = bf(torch.randn(shape, device=dev)).requires_grad_(True)
     # ours
     mods = ([layers.ReflectionPad2d(reflect)] if reflect else []) + [mod] + ([layers.Tanh()] if act == "tanh" else [])
-    y = layers.run_network(mods, x)
+    y = _Holder(mods).to(dev)(x)
     # reference
     xr = x.detach().clone().requires_grad_(True)
     wr = mod.weight.detach().clone().requires_grad_(True)
@@ -67,38 +69,60 @@ def conv_case(name, cin, cout, k, s, p, H, W, N=1, transposed=False, op_pad=0, r
     return ok
 
 
-def norm_case(name, C, H, W, N, act, reflect_out, residual):
-    torch.manual_seed(1)
-    x = bf(torch.randn(N, C, H, W, device=dev) * 2 + 0.5).requires_grad_(True)
-    r = bf(torch.randn(N, C, H, W, device=dev)).requires_grad_(True) if residual else None
-    bx = layers.to_buf(x, 0)
-    br = layers.to_buf(r, 1) if residual else None
-    act_id, slope = {"none": (0, 0.0), "relu": (1, 0.0), "leaky": (2, 0.2)}[act]
-    t = ops.NormActFn.apply(bx.t, br.t if br is not None else None, True, act_id, slope, reflect_out,
-                            1 if residual else 0, 1e-5)
-    # consume through a border-aware export: fold happens in ToChannelsLast backward only; use plain crop + pad check
-    full = t.float()  # (N,1,H+2p,W+2p,C)
+class _Holder(torch.nn.Module):
+    def __init__(self, mods):
+        super().__init__()
+        self.model = torch.nn.Sequential(*mods)
+
+    def forward(self, x):
+        return layers.run_network(self, list(self.model), x)
+
+
+def seq_case(name, ours_mods, ref_mods, shape, tol=2e-2):
+    """ours_mods / ref_mods: parallel module lists (ganslate_b200 layers vs torch.nn); weights copied ours -> ref."""
+    torch.manual_seed(3)
+    ours = _Holder(ours_mods).to(dev)
+    ref = torch.nn.Sequential(*ref_mods).to(dev)
+    with torch.no_grad():
+        for p in ours.parameters():
+            p.copy_(bf(torch.randn_like(p) * (0.05 if p.dim() > 1 else 0.1)))
+    ref.load_state_dict({k.replace("model.", "", 1): v for k, v in ours.state_dict().items()})
+    x = bf(torch.randn(shape, device=dev)).requires_grad_(True)
     xr = x.detach().clone().requires_grad_(True)
-    rr = r.detach().clone().requires_grad_(True) if residual else None
-    yr = F.instance_norm(xr, eps=1e-5)
-    if act == "relu":
-        yr = F.relu(yr)
-    elif act == "leaky":
-        yr = F.leaky_relu(yr, 0.2)
-    if residual:
-        yr = yr + rr
-    yrp = F.pad(yr, (reflect_out,) * 4, mode="reflect") if reflect_out else yr
-    ref_full = yrp.permute(0, 2, 3, 1).unsqueeze(1)
-    g = bf(torch.randn_like(ref_full))
-    e_y = rel(full[..., :C], ref_full)
-    t.backward(g.to(torch.bfloat16) if t.shape[-1] == C else F.pad(g, (0, t.shape[-1] - C)).to(torch.bfloat16))
-    ref_full.backward(g)
+    y = ours(x)
+    yr = ref(xr)
+    g = torch.randn_like(yr)
+    y.backward(g)
+    yr.backward(g)
     torch.cuda.synchronize()
-    e_dx = rel(x.grad, xr.grad)
-    e_dr = rel(r.grad, rr.grad) if residual else 0.0
-    ok = e_y < 1e-2 and e_dx < 2e-2 and e_dr < 1e-2
-    print(f"{'OK  ' if ok else 'FAIL'} {name:34s} y {e_y:.2e} dx {e_dx:.2e} dres {e_dr:.2e}", flush=True)
+    errs = {"y": rel(y, yr), "dx": rel(x.grad, xr.grad)}
+    for (k, p), (_, pr) in zip(ours.named_parameters(), ref.named_parameters()):
+        if pr.grad.abs().max() > 1e-4:
+            errs["d" + k.replace("model.", "")] = rel(p.grad, pr.grad)
+    ok = all(v < tol for v in errs.values())
+    print(f"{'OK  ' if ok else 'FAIL'} {name:34s} " + " ".join(f"{k} {v:.1e}" for k, v in errs.items()), flush=True)
     return ok
+
+
+def in_case(name, C, H, W, N, act, reflect_next):
+    L, nn = layers, torch.nn
+    a_o = {"relu": [L.ReLU(True)], "leaky": [L.LeakyReLU(0.2, True)], "none": []}[act]
+    a_r = {"relu": [nn.ReLU()], "leaky": [nn.LeakyReLU(0.2)], "none": []}[act]
+    tail_o = ([L.ReflectionPad2d(reflect_next)] if reflect_next else []) + [L.Conv2d(C, 16, 3, padding=0 if reflect_next else 1)]
+    tail_r = ([nn.ReflectionPad2d(reflect_next)] if reflect_next else []) + [nn.Conv2d(C, 16, 3, padding=0 if reflect_next else 1)]
+    return seq_case(name, [L.Conv2d(8, C, 3, padding=1), L.InstanceNorm2d(C)] + a_o + tail_o,
+                    [nn.Conv2d(8, C, 3, padding=1), nn.InstanceNorm2d(C)] + a_r + tail_r, (N, 8, H, W))
+
+
+def resblock_case():
+    from ganslate_b200.nn.generators.resnet.resnet2d import ResidualBlock
+    from oracle.torch_oracle import OracleResBlock
+    L, nn = layers, torch.nn
+    return seq_case("2 residual blocks C64 24x24", [L.Conv2d(8, 64, 3, padding=1), L.InstanceNorm2d(64), L.ReLU(True),
+                                                    ResidualBlock(64, "instance"), ResidualBlock(64, "instance"),
+                                                    L.Conv2d(64, 8, 3, padding=1)],
+                    [nn.Conv2d(8, 64, 3, padding=1), nn.InstanceNorm2d(64), nn.ReLU(), OracleResBlock(64), OracleResBlock(64),
+                     nn.Conv2d(64, 8, 3, padding=1)], (2, 8, 24, 24))
 
 
 def loss_case():
@@ -141,11 +165,12 @@ CASES = [
     lambda: conv_case("3d 2x2x2 s2 16->32 8x16x16", 16, 32, 2, 2, 0, 16, 16, D=8),
     lambda: conv_case("3d convT 2x2x2 s2 32->16", 32, 16, 2, 2, 0, 8, 8, D=4, transposed=True),
     lambda: conv_case("3d 4x4x4 s2 p1 1->64", 1, 64, 4, 2, 1, 32, 32, D=8),
-    lambda: norm_case("IN relu C64 32x32", 64, 32, 32, 2, "relu", 0, False),
-    lambda: norm_case("IN relu C256 border1", 256, 16, 16, 2, "relu", 1, False),
-    lambda: norm_case("IN none C256 residual border1", 256, 16, 16, 2, "none", 1, True),
-    lambda: norm_case("IN leaky C128 31x31", 128, 31, 31, 1, "leaky", 0, False),
-    lambda: norm_case("IN relu C64 border3", 64, 24, 24, 1, "relu", 3, False),
+    lambda: in_case("IN relu C64 32x32", 64, 32, 32, 2, "relu", 0),
+    lambda: in_case("IN relu C256 border1", 256, 16, 16, 2, "relu", 1),
+    lambda: in_case("IN leaky C128 31x31", 128, 31, 31, 1, "leaky", 0),
+    lambda: in_case("IN relu C64 border3", 64, 24, 24, 1, "relu", 3),
+    lambda: in_case("IN none C32 20x20", 32, 20, 20, 3, "none", 0),
+    resblock_case,
     loss_case,
 ]
 

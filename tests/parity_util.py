@@ -15,22 +15,30 @@ def max_rel(a, b):
     return ((a - b).abs().max() / (b.abs().max() + 1e-20)).item()
 
 
-def build_pair(size=256, batch=1, n_blocks=9, seed=0, lambda_identity=0.0):
+def cosine(a, b):
+    a, b = a.detach().float().cpu().flatten(), b.detach().float().cpu().flatten()
+    return (torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)).item()
+
+
+def build_pair(size=256, batch=1, n_blocks=9, seed=0, lambda_identity=0.0, matched=False):
     from oracle import torch_oracle as O
     from ganslate_b200.presets import cyclegan_resnet2d
     from ganslate_b200.utils.builders import build_gan
     random.seed(0)
-    oracle = O.OracleCycleGAN(O.default_cyclegan_conf(n_residual_blocks=n_blocks, lambda_identity=lambda_identity),
-                              seed=seed)
+    cls = O.OracleCycleGANBf16 if matched else O.OracleCycleGAN
+    oracle = cls(O.default_cyclegan_conf(n_residual_blocks=n_blocks, lambda_identity=lambda_identity), seed=seed)
     torch.manual_seed(seed)
     conf = cyclegan_resnet2d(batch_size=batch, n_residual_blocks=n_blocks, lambda_identity=lambda_identity)
     ours = build_gan(conf)
     return oracle, ours
 
 
-def step_report(size=256, batch=1, n_blocks=9, step_optimizers=False, lambda_identity=0.0, verbose=True):
+def step_report(size=256, batch=1, n_blocks=9, step_optimizers=False, lambda_identity=0.0, verbose=True,
+                matched=False):
+    """matched=False: fp32 oracle (what the reference computes).  matched=True: the same oracle with bf16
+    rounding at the B200 path's storage points (checks the kernels, not the precision choice)."""
     from oracle import torch_oracle as O
-    oracle, ours = build_pair(size, batch, n_blocks, lambda_identity=lambda_identity)
+    oracle, ours = build_pair(size, batch, n_blocks, lambda_identity=lambda_identity, matched=matched)
     rep = {}
     # same seed => same weights (init order and RNG consumption match the reference)
     worst = 0.0
@@ -61,7 +69,7 @@ def step_report(size=256, batch=1, n_blocks=9, step_optimizers=False, lambda_ide
             if po[k].grad is None:
                 continue
             grads[f"{name}.{k}"] = (rel_l2(pg[k].grad, po[k].grad), max_rel(pg[k].grad, po[k].grad),
-                                    po[k].grad.abs().max().item())
+                                    po[k].grad.abs().max().item(), cosine(pg[k].grad, po[k].grad))
     rep["grads"] = grads
     if step_optimizers:
         w = {}
@@ -81,7 +89,11 @@ def step_report(size=256, batch=1, n_blocks=9, step_optimizers=False, lambda_ide
         print("worst gradients by rel_l2 (rel_l2, max_rel, |ref|max):")
         for k, v in gl[:12]:
             print(f"  {k:42s} {v[0]:.3e} {v[1]:.3e} {v[2]:.3e}")
-        nz = [v for k, v in grads.items() if v[2] > 1e-6]
+        print("weight gradients in module order (rel_l2, max_rel, |ref|max, cosine):")
+        for k, v in grads.items():
+            if k.endswith("weight") and (k.startswith("G_AB") or k.startswith("D_B")):
+                print(f"  {k:42s} {v[0]:.3e} {v[1]:.3e} {v[2]:.3e} {v[3]:.5f}")
+        nz = [v for k, v in grads.items() if k.endswith("weight")]
         print("median rel_l2 over non-trivial grads:", sorted(x[0] for x in nz)[len(nz) // 2], "n", len(nz))
         if step_optimizers:
             print("post-Adam weights max abs diff:", rep["weights_max_abs_diff"])
@@ -93,4 +105,5 @@ if __name__ == "__main__":
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     size = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     nb = int(sys.argv[2]) if len(sys.argv) > 2 else 9
-    step_report(size=size, n_blocks=nb, step_optimizers=False)
+    matched = len(sys.argv) > 3 and sys.argv[3] == "matched"
+    step_report(size=size, n_blocks=nb, step_optimizers=False, matched=matched)
