@@ -53,7 +53,7 @@ class InFwdParams(C.Structure):
 class InBwdParams(C.Structure):
     _fields_ = [("x", View), ("y", View), ("dy_a", View), ("dy_b", View), ("dy_sum", View), ("dx", View),
                 ("stats", C.c_void_p), ("bstats", C.c_void_p), ("prelu", C.c_void_p), ("dprelu", C.c_void_p),
-                ("eps", C.c_float), ("act", C.c_int32), ("act_slope", C.c_float)]
+                ("dbias", C.c_void_p), ("eps", C.c_float), ("act", C.c_int32), ("act_slope", C.c_float)]
 
 
 _SIGNATURES = {

@@ -19,18 +19,61 @@ GB_HD void gb_class_extents(const gb_conv_params& p, int cls, int (&q)[3]) {
   }
 }
 
+// Division by a launch-invariant divisor without an integer divide (Granlund-Montgomery round-up method):
+//   x / d == (umulhi(x, mul) + x) >> shr   for 0 <= x < 2^31, 1 <= d < 2^31.
+struct gb_fastdiv {
+  uint32_t mul, shr, d, pad_;
+};
+inline gb_fastdiv gb_make_fastdiv(uint32_t d) {
+  gb_fastdiv f;
+  f.d = d ? d : 1;
+  uint32_t l = 0;
+  while ((1ull << l) < f.d) ++l;
+  f.mul = (uint32_t)(((1ull << 32) * ((1ull << l) - f.d)) / f.d + 1);
+  f.shr = l;
+  f.pad_ = 0;
+  return f;
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t gb_div(uint32_t x, const gb_fastdiv& f) { return (__umulhi(x, f.mul) + x) >> f.shr; }
+#endif
+
 struct gb_row {
   int n, qz, qy, qx;
 };
 
-GB_HD gb_row gb_decode_row(int64_t m, const int (&q)[3]) {
+#if defined(__CUDACC__)
+// decode with precomputed magic numbers: f[0..2] divide by the (z, y, x) extents of the grid
+__device__ __forceinline__ gb_row gb_decode_row_fast(uint32_t m, const gb_fastdiv* f) {
   gb_row r;
-  r.qx = (int)(m % q[2]);
-  m /= q[2];
-  r.qy = (int)(m % q[1]);
-  m /= q[1];
-  r.qz = (int)(m % q[0]);
-  r.n = (int)(m / q[0]);
+  uint32_t t = gb_div(m, f[2]);
+  r.qx = (int)(m - t * f[2].d);
+  m = t;
+  t = gb_div(m, f[1]);
+  r.qy = (int)(m - t * f[1].d);
+  m = t;
+  t = gb_div(m, f[0]);
+  r.qz = (int)(m - t * f[0].d);
+  r.n = (int)t;
+  return r;
+}
+#endif
+
+// 32-bit arithmetic on purpose: row indices are checked < 2^31 on the host and 64-bit integer division costs
+// ~100 instructions on the GPU (it dominated the first version of the wgrad producer loop).
+GB_HD gb_row gb_decode_row(int64_t m64, const int (&q)[3]) {
+  gb_row r;
+  uint32_t m = (uint32_t)m64;
+  const uint32_t q2 = (uint32_t)q[2], q1 = (uint32_t)q[1], q0 = (uint32_t)q[0];
+  uint32_t t = m / q2;
+  r.qx = (int)(m - t * q2);
+  m = t;
+  t = m / q1;
+  r.qy = (int)(m - t * q1);
+  m = t;
+  t = m / q0;
+  r.qz = (int)(m - t * q0);
+  r.n = (int)t;
   return r;
 }
 

@@ -1,0 +1,29 @@
+// TMA helpers shared by the TMA-fed kernels: tensor-map construction (host) and bulk-tensor loads (device).
+#pragma once
+#include <cuda.h>
+#include "gb_common.cuh"
+
+// true when cuTensorMapEncodeTiled could be resolved from the driver (false on a CPU-only box)
+bool gb_tma_available();
+// 5-D map {C, W, H, D, N} of a channels-last bf16 view with box {64 ch, tw, th, 1, 1}, 128B swizzle, zero OOB fill.
+// Returns 0 on success (maps are cached by view + box).
+int gb_tma_activation_map(const gb_view& v, int tw, int th, CUtensorMap* out);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+#endif

@@ -31,8 +31,13 @@ struct Cfg {
   static constexpr int MIN_CTAS = (BN == 256) ? 1 : 2;
 };
 
+struct ClassDivs {
+  gb_fastdiv f[GB_MAX_CLASSES][3];  // divide by the (z, y, x) q-grid extents of each class
+};
+
 template <int BN>
-__global__ void __launch_bounds__(256, Cfg<BN>::MIN_CTAS) igemm_data_kernel(const __grid_constant__ gb_conv_params p) {
+__global__ void __launch_bounds__(256, Cfg<BN>::MIN_CTAS) igemm_data_kernel(const __grid_constant__ gb_conv_params p,
+                                                                            const __grid_constant__ ClassDivs divs) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -58,7 +63,7 @@ __global__ void __launch_bounds__(256, Cfg<BN>::MIN_CTAS) igemm_data_kernel(cons
   const int64_t m0 = (int64_t)blockIdx.x * BM;
   if (m0 >= Mc) return;
   const int n0 = blockIdx.y * BN;
-  const int KB = (cc.ntaps > 0) ? cc.kpad / BK : 0;
+  const int KB = (cc.ntaps * p.in.C + BK - 1) / BK;  // kpad is only the row pitch of the packed class matrix
 
   const uint32_t full_bar = smem_u32(bars);
   const uint32_t empty_bar = smem_u32(bars + STAGES);
@@ -83,6 +88,10 @@ __global__ void __launch_bounds__(256, Cfg<BN>::MIN_CTAS) igemm_data_kernel(cons
 
   if (warp < 4) {
     // ------------------------------------------------------------------ gather producers
+    // Thread (r0, j) fills 16-byte chunk j of rows r0 + 16*i.  The warp is issue-latency bound (one warp per
+    // scheduler), so everything that does not change from stage to stage is hoisted: row decode, the swizzled
+    // smem offsets, and -- when a stage never straddles two taps (C % 64 == 0) -- the per-tap bounds mask and
+    // source offsets, which are recomputed only when the tap changes.
     const int j = tid & 7;    // 16-byte chunk inside the 128-byte row
     const int r0 = tid >> 3;  // first row handled by this thread (rows r0 + 16*i)
     const int C8 = p.in.C >> 3;
@@ -91,7 +100,7 @@ __global__ void __launch_bounds__(256, Cfg<BN>::MIN_CTAS) igemm_data_kernel(cons
     for (int i = 0; i < 8; ++i) {
       const int64_t m = m0 + r0 + 16 * i;
       if (m < Mc) {
-        gb_row r = gb_decode_row(m, q);
+        gb_row r = gb_decode_row_fast((uint32_t)m, divs.f[cls]);
         const int gz = r.qz * p.in_mul[0], gy = r.qy * p.in_mul[1], gx = r.qx * p.in_mul[2];
         rbase[i] = (int)gb_pix_offset(p.in, r.n, gz, gy, gx);
         ryx[i] = (gy << 16) | (gx & 0xFFFF);
@@ -104,40 +113,79 @@ __global__ void __launch_bounds__(256, Cfg<BN>::MIN_CTAS) igemm_data_kernel(cons
     }
     const __nv_bfloat16* in_ptr = reinterpret_cast<const __nv_bfloat16*>(p.in.ptr);
     const __nv_bfloat16* w_ptr = reinterpret_cast<const __nv_bfloat16*>(p.wpacked) + cc.w_offset;
+    // swizzled destination of this thread's chunk: (row & 7) == (r0 & 7) for all its rows
+    const uint32_t dst0 = (uint32_t)r0 * 128u + (uint32_t)((j ^ (r0 & 7)) << 4);
+    // weight rows
+    int boff[BN / 16 > 0 ? BN / 16 : 1];
+    uint32_t bmask = 0;
+#pragma unroll
+    for (int i = 0; i < BN / 16; ++i) {
+      const int n = n0 + r0 + 16 * i;
+      boff[i] = n * cc.kpad + j * 8;
+      if (n < p.npad) bmask |= 1u << i;
+    }
+    const bool fast = (C8 & 7) == 0;   // a 64-wide K block lies inside one tap
+    const int chunks_per_tap = C8 >> 3;
+    int tap = -1, cc_in_tap = 0;       // fast path state
+    uint32_t amask = 0;
+    int aoff[8];
     for (int kb = 0; kb < KB; ++kb) {
       const int s = kb % STAGES;
       const int it = kb / STAGES;
       if (it > 0) mbar_wait(empty_bar + 8 * s, (it - 1) & 1);
-      const uint32_t a_s = base + s * C::STAGE_BYTES;
+      const uint32_t a_s = base + s * C::STAGE_BYTES + dst0;
       const uint32_t b_s = a_s + A_BYTES;
-      const int k8 = kb * 8 + j;
-      const int tl = k8 / C8;
-      const int c8 = k8 - tl * C8;
-      const bool tap_ok = tl < cc.ntaps;
-      int dz = 0, dy = 0, dx = 0;
-      if (tap_ok) {
-        dz = taps_s[4 * tl + 0];
-        dy = taps_s[4 * tl + 1];
-        dx = taps_s[4 * tl + 2];
-      }
-      const int toff = (int)(dz * p.in.sz + dy * p.in.sy + dx * p.in.sx) + c8 * 8;
+      if (fast) {
+        if (tap < 0 || cc_in_tap == chunks_per_tap) {
+          ++tap;
+          cc_in_tap = 0;
+          const bool tap_ok = tap < cc.ntaps;
+          int dz = 0, dy = 0, dx = 0;
+          if (tap_ok) {
+            dz = taps_s[4 * tap + 0];
+            dy = taps_s[4 * tap + 1];
+            dx = taps_s[4 * tap + 2];
+          }
+          const int toff = (int)(dz * p.in.sz + dy * p.in.sy + dx * p.in.sx) + j * 8;
+          amask = 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = r0 + 16 * i;
-        const int z = rz[i] + dz;
-        const int y = (ryx[i] >> 16) + dy;
-        const int x = (int)(short)(ryx[i] & 0xFFFF) + dx;
-        const bool ok = tap_ok && gb_in_bounds(p.in, z, y, x);
-        const __nv_bfloat16* src = ok ? in_ptr + (rbase[i] + toff) : in_ptr;
-        cp_async16(a_s + swz128(row, j), src, ok);
+          for (int i = 0; i < 8; ++i) {
+            const int z = rz[i] + dz, y = (ryx[i] >> 16) + dy, x = (int)(short)(ryx[i] & 0xFFFF) + dx;
+            if (tap_ok && gb_in_bounds(p.in, z, y, x)) amask |= 1u << i;
+            aoff[i] = rbase[i] + toff;
+          }
+        }
+        const int coff = cc_in_tap * 64;
+        ++cc_in_tap;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool ok = (amask >> i) & 1u;
+          cp_async16(a_s + i * 2048, ok ? in_ptr + (aoff[i] + coff) : in_ptr, ok);
+        }
+      } else {
+        const int k8 = kb * 8 + j;
+        const int tl = k8 / C8;
+        const int c8 = k8 - tl * C8;
+        const bool tap_ok = tl < cc.ntaps;
+        int dz = 0, dy = 0, dx = 0;
+        if (tap_ok) {
+          dz = taps_s[4 * tl + 0];
+          dy = taps_s[4 * tl + 1];
+          dx = taps_s[4 * tl + 2];
+        }
+        const int toff = (int)(dz * p.in.sz + dy * p.in.sy + dx * p.in.sx) + c8 * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int z = rz[i] + dz, y = (ryx[i] >> 16) + dy, x = (int)(short)(ryx[i] & 0xFFFF) + dx;
+          const bool ok = tap_ok && gb_in_bounds(p.in, z, y, x);
+          cp_async16(a_s + i * 2048, ok ? in_ptr + (rbase[i] + toff) : in_ptr, ok);
+        }
       }
+      const int kcol = kb * BK;
 #pragma unroll
       for (int i = 0; i < BN / 16; ++i) {
-        const int row = r0 + 16 * i;
-        const int n = n0 + row;
-        const bool ok = n < p.npad;
-        const __nv_bfloat16* src = ok ? w_ptr + ((int64_t)n * cc.kpad + kb * BK + j * 8) : w_ptr;
-        cp_async16(b_s + swz128(row, j), src, ok);
+        const bool ok = (bmask >> i) & 1u;
+        cp_async16(b_s + i * 2048, ok ? w_ptr + (boff[i] + kcol) : w_ptr, ok);
       }
       cp_async_commit();
       if (kb >= LAG) {
@@ -191,7 +239,7 @@ __global__ void __launch_bounds__(256, Cfg<BN>::MIN_CTAS) igemm_data_kernel(cons
     __nv_bfloat16* optr = reinterpret_cast<__nv_bfloat16*>(p.out.ptr);
     int64_t ooff = 0;
     if (row_ok) {
-      gb_row r = gb_decode_row(m, q);
+      gb_row r = gb_decode_row_fast((uint32_t)m, divs.f[cls]);
       ooff = gb_pix_offset(p.out, r.n, r.qz * p.out_mul[0] + cc.off[0], r.qy * p.out_mul[1] + cc.off[1],
                            r.qx * p.out_mul[2] + cc.off[2]);
     }
@@ -255,7 +303,7 @@ __global__ void __launch_bounds__(256, Cfg<BN>::MIN_CTAS) igemm_data_kernel(cons
 }
 
 template <int BN>
-int launch(const gb_conv_params& p, int64_t max_mc, cudaStream_t st) {
+int launch(const gb_conv_params& p, const ClassDivs& divs, int64_t max_mc, cudaStream_t st) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -263,7 +311,7 @@ int launch(const gb_conv_params& p, int64_t max_mc, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(gb_cdiv(max_mc, BM), gb_cdiv(p.ncols, BN), p.nclass);
-  igemm_data_kernel<BN><<<grid, 256, C::SMEM, st>>>(p);
+  igemm_data_kernel<BN><<<grid, 256, C::SMEM, st>>>(p, divs);
   GB_LAUNCH_CHECK();
   return 0;
 }
@@ -274,6 +322,8 @@ int64_t view_max_offset(const gb_view& v) {
 }
 
 }  // namespace
+
+int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st);  // igemm_tma.cu: -1 = not applicable
 
 extern "C" int gb_conv_data(const gb_conv_params* pp, void* stream) {
   const gb_conv_params& p = *pp;
@@ -291,6 +341,7 @@ extern "C" int gb_conv_data(const gb_conv_params* pp, void* stream) {
   GB_CHECK(((uintptr_t)p.in.ptr & 15) == 0 && ((uintptr_t)p.out.ptr & 15) == 0 && ((uintptr_t)p.wpacked & 15) == 0,
            "gb_conv_data: pointers must be 16-byte aligned");
   int64_t max_mc = 0;
+  ClassDivs divs;
   for (int c = 0; c < p.nclass; ++c) {
     GB_CHECK(p.cls[c].kpad % 64 == 0, "gb_conv_data: kpad must be a multiple of 64");
     GB_CHECK(p.cls[c].ntaps * p.in.C <= p.cls[c].kpad, "gb_conv_data: kpad too small");
@@ -299,9 +350,16 @@ extern "C" int gb_conv_data(const gb_conv_params* pp, void* stream) {
     gb_class_extents(p, c, q);
     int64_t mc = (int64_t)p.in.N * q[0] * q[1] * q[2];
     if (mc > max_mc) max_mc = mc;
+    for (int d = 0; d < 3; ++d) divs.f[c][d] = gb_make_fastdiv((uint32_t)(q[d] > 0 ? q[d] : 1));
+    GB_CHECK((int64_t)p.npad * p.cls[c].kpad < (1ll << 31), "gb_conv_data: packed weight matrix too large");
   }
+  GB_CHECK(max_mc < (1ll << 31), "gb_conv_data: too many output positions");
   if (max_mc == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const int r = gb_conv_data_tma(p, st);  // TMA-fed kernel for unit-stride gathers with C % 64 == 0
+    if (r >= 0) return r;
+  }
   // tile width: smallest BN covering the output channels, shrunk while the grid under-fills the 148 SMs
   int bn = 16;
   while (bn < p.ncols && bn < 256) bn *= 2;
@@ -312,11 +370,11 @@ extern "C" int gb_conv_data(const gb_conv_params* pp, void* stream) {
     while (bn > 64 && mt * gb_cdiv(p.ncols, bn) < 148) bn /= 2;
   }
   switch (bn) {
-    case 16: return launch<16>(p, max_mc, st);
-    case 32: return launch<32>(p, max_mc, st);
-    case 64: return launch<64>(p, max_mc, st);
-    case 128: return launch<128>(p, max_mc, st);
-    case 256: return launch<256>(p, max_mc, st);
+    case 16: return launch<16>(p, divs, max_mc, st);
+    case 32: return launch<32>(p, divs, max_mc, st);
+    case 64: return launch<64>(p, divs, max_mc, st);
+    case 128: return launch<128>(p, divs, max_mc, st);
+    case 256: return launch<256>(p, divs, max_mc, st);
   }
   GB_CHECK(false, "gb_conv_data: bad tile width %d", bn);
 }

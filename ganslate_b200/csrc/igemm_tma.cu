@@ -1,0 +1,381 @@
+// TMA-fed variant of the implicit-GEMM convolution (forward / data gradient / transposed classes) for the
+// dominant case: unit gather multiplier (stride-1 convolutions and every parity class of a transposed or
+// strided-dgrad convolution) and a channel count that is a multiple of 64.
+//
+// A GEMM row tile is a TH x TW patch of output pixels (TH*TW = 128) of one image / depth slice.  For tap t and
+// 64-channel chunk c the A operand is then one 5-D TMA box {64 ch, TW, TH, 1, 1} of the channels-last input at
+// pixel offset d_t -- the hardware does the address generation, zero-fills outside the image (= zero padding)
+// and writes the 128B-swizzled K-major tile the UMMA descriptor expects.  B (packed weights) is a 2-D box
+// {64, BN}.  One elected thread issues both loads per stage; there is no per-thread gather work at all, which
+// is what bounded the cp.async kernel (igemm_data.cu: ~12 % tensor-pipe, producers issue-latency bound).
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), all 8 warps = epilogue.
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include "gb_common.cuh"
+#include "gb_geometry.h"
+#include "gb_tma.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * BK * 2;
+
+template <int BN>
+struct TCfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  // TMA latency is ~1 us: what matters is bytes in flight per SM, so use every stage that fits in ~200 KB
+  // (one CTA per SM)
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 1024;
+  static constexpr int MIN_CTAS = 1;
+};
+
+struct TileGeom {
+  gb_fastdiv tiles_x, tiles_y, tiles_z;  // decode tile index -> (n, z, ty, tx)
+  int tw, th, tw_shift;                  // TW is a power of two
+  int ntx, nty;
+  int ntiles;                            // per class (max over classes is the grid)
+};
+
+
+template <int BN>
+__global__ void __launch_bounds__(256, TCfg<BN>::MIN_CTAS)
+igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant__ CUtensorMap map_a,
+                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TileGeom tg) {
+  using C = TCfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint8_t* tail = smem + STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);  // full[STAGES], empty[STAGES], accum
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 128);
+  int8_t* taps_s = reinterpret_cast<int8_t*>(tail + 192);
+  __shared__ float bias_s[BN];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int cls = blockIdx.z;
+  const gb_conv_class& cc = p.cls[cls];
+  int q[3];
+  gb_class_extents(p, cls, q);
+  // tile -> (n, z, ty, tx); tiles of classes with smaller extents simply fall outside and exit
+  uint32_t t = blockIdx.x;
+  uint32_t u = gb_div(t, tg.tiles_x);
+  const int tx = (int)(t - u * tg.tiles_x.d);
+  t = u;
+  u = gb_div(t, tg.tiles_y);
+  const int ty = (int)(t - u * tg.tiles_y.d);
+  t = u;
+  u = gb_div(t, tg.tiles_z);
+  const int z0 = (int)(t - u * tg.tiles_z.d);
+  const int n = (int)u;
+  const int x0 = tx * tg.tw, y0 = ty * tg.th;
+  if (n >= p.in.N || z0 >= q[0] || y0 >= q[1] || x0 >= q[2]) return;
+  const int n0 = blockIdx.y * BN;
+  const int chunks = p.in.C >> 6;
+  const int KB = cc.ntaps * chunks;
+
+  const uint32_t full_bar = smem_u32(bars);
+  const uint32_t empty_bar = smem_u32(bars + STAGES);
+  const uint32_t accum_bar = smem_u32(bars + 2 * STAGES);
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(smem_u32(tmem_slot));
+  for (int i = tid; i < cc.ntaps; i += 256)
+    *reinterpret_cast<uint32_t*>(taps_s + 4 * i) = *reinterpret_cast<const uint32_t*>(p.taps[cc.tap_begin + i]);
+  for (int i = tid; i < BN; i += 256) bias_s[i] = (p.bias != nullptr && n0 + i < p.ncols) ? p.bias[n0 + i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one lane)
+    if (lane == 0) {
+      // packed weights of this class start at row (w_offset / kpad) of the 2-D weight map built per class
+      int kb = 0;
+      for (int tl = 0; tl < cc.ntaps; ++tl) {
+        const int dz = taps_s[4 * tl + 0], dy = taps_s[4 * tl + 1], dx = taps_s[4 * tl + 2];
+        for (int c = 0; c < chunks; ++c, ++kb) {
+          const int s = kb % STAGES;
+          const int it = kb / STAGES;
+          if (it > 0) mbar_wait(empty_bar + 8 * s, (it - 1) & 1);
+          const uint32_t a_s = base + s * C::STAGE_BYTES;
+          const uint32_t b_s = a_s + A_BYTES;
+          const uint32_t bar = full_bar + 8 * s;
+          mbar_expect_tx(bar, C::STAGE_BYTES);
+          tma_load_5d(a_s, &map_a, bar, c * 64, x0 + dx, y0 + dy, z0 + dz, n);
+          tma_load_2d(b_s, &map_b, bar, tl * p.in.C + c * 64, cls * p.npad + n0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BN, 0, 0);
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % STAGES;
+      const int it = kb / STAGES;
+      mbar_wait(full_bar + 8 * s, it & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_s = base + s * C::STAGE_BYTES;
+        const uint32_t b_s = a_s + A_BYTES;
+        const uint64_t adesc = make_smem_desc(a_s, 16, 1024);
+        const uint64_t bdesc = make_smem_desc(b_s, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        umma_commit(empty_bar + 8 * s);
+      }
+      __syncwarp();
+    }
+    if (lane == 0 && KB > 0) umma_commit(accum_bar);
+    __syncwarp();
+  }
+
+  // -------------------------------------------------------------------- epilogue (all warps)
+  if (KB > 0) {
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+  }
+  {
+    const int lg = warp & 3;
+    const int half = warp >> 2;
+    const int row = lg * 32 + lane;
+    const int h = row >> tg.tw_shift, w = row & (tg.tw - 1);
+    const int qy = y0 + h, qx = x0 + w;
+    const bool row_ok = qy < q[1] && qx < q[2];
+    __nv_bfloat16* optr = reinterpret_cast<__nv_bfloat16*>(p.out.ptr);
+    int64_t ooff = 0;
+    if (row_ok)
+      ooff = gb_pix_offset(p.out, n, z0 * p.out_mul[0] + cc.off[0], qy * p.out_mul[1] + cc.off[1],
+                           qx * p.out_mul[2] + cc.off[2]);
+    constexpr int CH = (BN >= 64) ? 32 : 16;
+    constexpr int COLS_PER_HALF = (BN >= 64) ? BN / 2 : BN;
+    const bool active = (BN >= 64) || half == 0;
+    if (active) {
+      const int cbeg = (BN >= 64) ? half * COLS_PER_HALF : 0;
+#pragma unroll 1
+      for (int c0 = cbeg; c0 < cbeg + COLS_PER_HALF; c0 += CH) {
+        uint32_t acc[CH];
+        if (KB > 0) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
+          if constexpr (CH == 32) tmem_ld32(taddr, acc); else tmem_ld16(taddr, acc);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) acc[i] = 0u;
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < CH / 8; ++g) {
+            const int col = n0 + c0 + g * 8;
+            if (col < p.out.C) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float tt = __uint_as_float(acc[g * 8 + e]) + bias_s[c0 + g * 8 + e];
+                if (p.act == GB_ACT_TANH) tt = tanhf(tt);
+                else if (p.act == GB_ACT_LEAKY) tt = tt > 0.f ? tt : tt * p.act_slope;
+                else if (p.act == GB_ACT_RELU) tt = fmaxf(tt, 0.f);
+                v[e] = tt;
+              }
+              if (p.out_fp32) {
+                float4* o32 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out.ptr) + ooff + col);
+                float4 a = make_float4(v[0], v[1], v[2], v[3]), b = make_float4(v[4], v[5], v[6], v[7]);
+                if (p.accumulate) {
+                  const float4 pa = o32[0], pb = o32[1];
+                  a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
+                  b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
+                }
+                o32[0] = a;
+                o32[1] = b;
+              } else {
+                uint4 o;
+                o.x = pack_bf16x2(v[0], v[1]);
+                o.y = pack_bf16x2(v[2], v[3]);
+                o.z = pack_bf16x2(v[4], v[5]);
+                o.w = pack_bf16x2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(optr + ooff + col) = o;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+std::mutex g_map_mutex;
+std::unordered_map<std::string, CUtensorMap> g_map_cache;
+
+}  // namespace
+
+bool gb_tma_available() { return encode_fn() != nullptr; }
+
+// 5-D activation map {C, W, H, D, N}, box {64, tw, th, 1, 1}
+int gb_tma_activation_map(const gb_view& v, int tw, int th, CUtensorMap* out) {
+  std::string key(reinterpret_cast<const char*>(&v), sizeof(gb_view));
+  key.append(reinterpret_cast<const char*>(&tw), sizeof(int)).append(reinterpret_cast<const char*>(&th), sizeof(int));
+  std::lock_guard<std::mutex> lk(g_map_mutex);
+  auto it = g_map_cache.find(key);
+  if (it != g_map_cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  cuuint64_t dims[5] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.D, (cuuint64_t)v.N};
+  cuuint64_t strides[4] = {(cuuint64_t)v.sx * 2, (cuuint64_t)v.sy * 2, (cuuint64_t)v.sz * 2, (cuuint64_t)v.sn * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)tw, (cuuint32_t)th, 1, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode_fn()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, v.ptr, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: %d", (int)r);
+  if (g_map_cache.size() > 4096) g_map_cache.clear();
+  g_map_cache[key] = *out;
+  return 0;
+}
+
+namespace {
+
+// 2-D weight map {kpad, nclass*npad}, box {64, bn}; all classes of one conv share kpad on this path
+int weight_map(const void* w, int kpad, int rows, int bn, CUtensorMap* out) {
+  struct {
+    const void* w;
+    int kpad, rows, bn;
+  } k = {w, kpad, rows, bn};
+  std::string key(reinterpret_cast<const char*>(&k), sizeof(k));
+  std::lock_guard<std::mutex> lk(g_map_mutex);
+  auto it = g_map_cache.find(key);
+  if (it != g_map_cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)bn};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = encode_fn()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  if (g_map_cache.size() > 4096) g_map_cache.clear();
+  g_map_cache[key] = *out;
+  return 0;
+}
+
+template <int BN>
+int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb, const TileGeom& tg, cudaStream_t st) {
+  using C = TCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GB_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  dim3 grid(tg.ntiles, gb_cdiv(p.ncols, BN), p.nclass);
+  igemm_tma_kernel<BN><<<grid, 256, C::SMEM, st>>>(p, ma, mb, tg);
+  GB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+// Returns -1 when this path does not apply (caller falls back to the gather kernel), 0 on success, >0 on error.
+int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st) {
+  if (g_gb_knobs[3] != 0) return -1;                 // knob 3: disable the TMA path
+  if (p.in.C % 64 != 0) return -1;
+  for (int d = 0; d < 3; ++d)
+    if (p.in_mul[d] != 1) return -1;
+  if (p.in.pad != 0) return -1;
+  if (encode_fn() == nullptr) return -1;
+  // every class must use the same padded K (true when every class has the same tap count) -- otherwise the 2-D
+  // weight map cannot address class matrices by row offset
+  int kpad = p.cls[0].kpad;
+  int64_t max_ext[3] = {0, 0, 0};
+  for (int c = 0; c < p.nclass; ++c) {
+    if (p.cls[c].kpad != kpad || p.cls[c].w_offset != (int64_t)c * p.npad * kpad) return -1;
+    if (p.cls[c].ntaps * p.in.C != p.cls[c].kpad && p.cls[c].ntaps * p.in.C > p.cls[c].kpad) return -1;
+    int q[3];
+    gb_class_extents(p, c, q);
+    for (int d = 0; d < 3; ++d) max_ext[d] = q[d] > max_ext[d] ? q[d] : max_ext[d];
+  }
+  if (max_ext[0] == 0 || max_ext[1] == 0 || max_ext[2] == 0) return 0;
+  if ((p.in.sx * 2) % 16 || (p.in.sy * 2) % 16 || (p.in.sz * 2) % 16 || (p.in.sn * 2) % 16) return -1;
+  // tile shape: TW = power of two in [8, 128] covering the row, TH = 128 / TW
+  int tw = 8;
+  while (tw < max_ext[2] && tw < 128) tw *= 2;
+  if (tw > 64 && max_ext[2] <= 96) tw = 64;
+  int th = BM / tw;
+  TileGeom tg;
+  tg.tw = tw;
+  tg.th = th;
+  tg.tw_shift = 0;
+  while ((1 << tg.tw_shift) < tw) ++tg.tw_shift;
+  tg.ntx = gb_cdiv(max_ext[2], tw);
+  tg.nty = gb_cdiv(max_ext[1], th);
+  tg.tiles_x = gb_make_fastdiv((uint32_t)tg.ntx);
+  tg.tiles_y = gb_make_fastdiv((uint32_t)tg.nty);
+  tg.tiles_z = gb_make_fastdiv((uint32_t)max_ext[0]);
+  const int64_t ntiles = (int64_t)tg.ntx * tg.nty * max_ext[0] * p.in.N;
+  if (ntiles >= (1ll << 31)) return -1;
+  tg.ntiles = (int)ntiles;
+  // tile width: like the gather kernel, shrink BN while the grid under-fills the chip
+  int bn = 16;
+  while (bn < p.ncols && bn < 256) bn *= 2;
+  if (g_gb_knobs[1] > 0) {
+    bn = g_gb_knobs[1];
+  } else {
+    while (bn > 64 && ntiles * p.nclass * gb_cdiv(p.ncols, bn) < 148) bn /= 2;
+  }
+  if (bn > p.nclass * p.npad) return -1;  // keep every TMA box inside its tensor
+  CUtensorMap ma, mb;
+  if (gb_tma_activation_map(p.in, tw, th, &ma)) return 1;
+  if (weight_map(p.wpacked, kpad, p.nclass * p.npad, bn, &mb)) return 1;
+  switch (bn) {
+    case 16: return launch<16>(p, ma, mb, tg, st);
+    case 32: return launch<32>(p, ma, mb, tg, st);
+    case 64: return launch<64>(p, ma, mb, tg, st);
+    case 128: return launch<128>(p, ma, mb, tg, st);
+    case 256: return launch<256>(p, ma, mb, tg, st);
+  }
+  return -1;
+}

@@ -8,8 +8,10 @@
 // rows of dW (dOut for a convolution, the input for a transposed convolution); G ("gathered") is the other
 // tensor read through the tap offsets, its column index kflat = tap*C + c is the forward kernel's K index.
 // The pixel range is split across blockIdx.z and partial sums are combined with red.global.add.v4.f32.
+#include <string.h>
 #include "gb_common.cuh"
 #include "gb_geometry.h"
+#include "gb_tma.h"
 
 namespace {
 
@@ -20,20 +22,30 @@ constexpr int LAG = 2;
 
 template <int BN>
 struct WCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 4;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int P_BYTES = 2 * ATOM;
   static constexpr int G_BYTES = (BN / 64) * ATOM;
   static constexpr int STAGE_BYTES = P_BYTES + G_BYTES;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 1024;
-  static constexpr int MIN_CTAS = (BN == 256) ? 1 : 2;
+  static constexpr int MIN_CTAS = 1;
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN>
+struct PixDivs {
+  gb_fastdiv f[3];  // divide by the (D, H, W) extents of the plain operand's pixel grid
+  // TMA variant: a 64-pixel K block is a th x tw patch; tile index -> (n, z, ty, tx)
+  gb_fastdiv tiles_x, tiles_y, tiles_z;
+  int tw, th, ntiles, use_tma;
+};
+
+template <int BN, bool TMA>
 __global__ void __launch_bounds__(256, WCfg<BN>::MIN_CTAS) igemm_wgrad_kernel(const __grid_constant__ gb_wgrad_params p,
+                                                                              const __grid_constant__ PixDivs divs,
+                                                                              const __grid_constant__ CUtensorMap map_p,
+                                                                              const __grid_constant__ CUtensorMap map_g,
                                                                               int blocks_per_split) {
   using C = WCfg<BN>;
   constexpr int STAGES = C::STAGES;
@@ -52,7 +64,7 @@ __global__ void __launch_bounds__(256, WCfg<BN>::MIN_CTAS) igemm_wgrad_kernel(co
   const int kt = blockIdx.x;           // column tile (kflat)
   const int rt = blockIdx.y * BM;      // first row (plain channel)
   const int64_t Mq = (int64_t)p.plain.N * p.plain.D * p.plain.H * p.plain.W;
-  const int nblk = (int)((Mq + BP - 1) / BP);
+  const int nblk = TMA ? divs.ntiles : (int)((Mq + BP - 1) / BP);
   const int b0 = blockIdx.z * blocks_per_split;
   const int b1 = min(nblk, b0 + blocks_per_split);
   const int KB = b1 - b0;
@@ -63,7 +75,7 @@ __global__ void __launch_bounds__(256, WCfg<BN>::MIN_CTAS) igemm_wgrad_kernel(co
   const uint32_t accum_bar = smem_u32(bars + 2 * STAGES);
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar + 8 * s, 4);
+      mbar_init(full_bar + 8 * s, TMA ? 1 : 4);
       mbar_init(empty_bar + 8 * s, 1);
     }
     mbar_init(accum_bar, 1);
@@ -75,10 +87,53 @@ __global__ void __launch_bounds__(256, WCfg<BN>::MIN_CTAS) igemm_wgrad_kernel(co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (TMA && warp < 4) {
+    // ------------------------------------------------------------------ TMA producer: one lane, (2 + NG) boxes/stage
+    if (warp == 0 && lane == 0) {
+      const int Cg = p.gathered.C;
+      int g_c0[NG], g_dz[NG], g_dy[NG], g_dx[NG];
+      bool g_ok[NG];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const int kflat = kt * BN + g * 64;
+        const int tl = kflat / Cg;
+        g_c0[g] = kflat - tl * Cg;
+        g_ok[g] = tl < p.ntaps && kflat < p.kpad;
+        g_dz[g] = g_ok[g] ? p.taps[tl][0] : 0;
+        g_dy[g] = g_ok[g] ? p.taps[tl][1] : 0;
+        g_dx[g] = g_ok[g] ? p.taps[tl][2] : 0;
+        if (!g_ok[g]) g_c0[g] = Cg;  // channel coordinate past the tensor: the whole box is zero-filled
+      }
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        const int it = kb / STAGES;
+        if (it > 0) mbar_wait(empty_bar + 8 * s, (it - 1) & 1);
+        uint32_t t = (uint32_t)(b0 + kb);
+        uint32_t u = gb_div(t, divs.tiles_x);
+        const int x0 = (int)(t - u * divs.tiles_x.d) * divs.tw;
+        t = u;
+        u = gb_div(t, divs.tiles_y);
+        const int y0 = (int)(t - u * divs.tiles_y.d) * divs.th;
+        t = u;
+        u = gb_div(t, divs.tiles_z);
+        const int z0 = (int)(t - u * divs.tiles_z.d);
+        const int n = (int)u;
+        const uint32_t p_s = base + s * C::STAGE_BYTES;
+        const uint32_t g_s = p_s + C::P_BYTES;
+        const uint32_t bar = full_bar + 8 * s;
+        mbar_expect_tx(bar, C::STAGE_BYTES);
+        tma_load_5d(p_s, &map_p, bar, rt, x0, y0, z0, n);
+        tma_load_5d(p_s + ATOM, &map_p, bar, rt + 64, x0, y0, z0, n);
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+          tma_load_5d(g_s + g * ATOM, &map_g, bar, g_c0[g], x0 * p.mul[2] + g_dx[g], y0 * p.mul[1] + g_dy[g],
+                      z0 * p.mul[0] + g_dz[g], n);
+      }
+    }
+    __syncwarp();
+  } else if (warp < 4) {
     const int j = tid & 7;
     const int r0 = tid >> 3;  // pixel rows r0 + 16*i, i < 4
-    const int q[3] = {p.plain.D, p.plain.H, p.plain.W};
     const __nv_bfloat16* pl = reinterpret_cast<const __nv_bfloat16*>(p.plain.ptr);
     const __nv_bfloat16* ga = reinterpret_cast<const __nv_bfloat16*>(p.gathered.ptr);
     // per-atom constants of the gathered operand: which tap / channel chunk this thread's column chunk is
@@ -108,20 +163,25 @@ __global__ void __launch_bounds__(256, WCfg<BN>::MIN_CTAS) igemm_wgrad_kernel(co
       p_ch[a] = rt + (a * 8 + j) * 8;
       p_ok[a] = p_ch[a] < p.plain.C;
     }
+    // all gathered atoms of this thread read the same tap when the column tile lies inside one tap
+    bool uniform = true;
+#pragma unroll
+    for (int g = 1; g < NG; ++g) uniform = uniform && (g_d[g] == g_d[0]) && (g_ok[g] == g_ok[0]);
+    const uint32_t dst0 = (uint32_t)r0 * 128u + (uint32_t)((j ^ (r0 & 7)) << 4);
+    const uint32_t Mq32 = (uint32_t)Mq;
     for (int kb = 0; kb < KB; ++kb) {
       const int s = kb % STAGES;
       const int it = kb / STAGES;
       if (it > 0) mbar_wait(empty_bar + 8 * s, (it - 1) & 1);
-      const uint32_t p_s = base + s * C::STAGE_BYTES;
+      const uint32_t p_s = base + s * C::STAGE_BYTES + dst0;
       const uint32_t g_s = p_s + C::P_BYTES;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int prow = r0 + 16 * i;
-        const int64_t m = (int64_t)(b0 + kb) * BP + prow;
-        const bool pix_ok = m < Mq;
+        const uint32_t m = (uint32_t)(b0 + kb) * BP + (uint32_t)(r0 + 16 * i);
+        const bool pix_ok = m < Mq32;
         int poff = 0, goff = 0, gz = 0, gy = -100000, gx = 0;
         if (pix_ok) {
-          gb_row r = gb_decode_row(m, q);
+          gb_row r = gb_decode_row_fast(m, divs.f);
           poff = (int)gb_pix_offset(p.plain, r.n, r.qz, r.qy, r.qx);
           gz = r.qz * p.mul[0];
           gy = r.qy * p.mul[1];
@@ -131,14 +191,22 @@ __global__ void __launch_bounds__(256, WCfg<BN>::MIN_CTAS) igemm_wgrad_kernel(co
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
           const bool ok = pix_ok && p_ok[a];
-          cp_async16(p_s + a * ATOM + swz128(prow, j), ok ? pl + (poff + p_ch[a]) : pl, ok);
+          cp_async16(p_s + a * ATOM + i * 2048, ok ? pl + (poff + p_ch[a]) : pl, ok);
         }
+        if (uniform) {
+          const int dz = (int)(signed char)(g_d[0] >> 16), dy = (int)(signed char)(g_d[0] >> 8),
+                    dx = (int)(signed char)(g_d[0]);
+          const bool ok = pix_ok && g_ok[0] && gb_in_bounds(p.gathered, gz + dz, gy + dy, gx + dx);
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          const int dz = (int)(signed char)(g_d[g] >> 16), dy = (int)(signed char)(g_d[g] >> 8),
-                    dx = (int)(signed char)(g_d[g]);
-          const bool ok = pix_ok && g_ok[g] && gb_in_bounds(p.gathered, gz + dz, gy + dy, gx + dx);
-          cp_async16(g_s + g * ATOM + swz128(prow, j), ok ? ga + (goff + g_toff[g]) : ga, ok);
+          for (int g = 0; g < NG; ++g) cp_async16(g_s + g * ATOM + i * 2048, ok ? ga + (goff + g_toff[g]) : ga, ok);
+        } else {
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            const int dz = (int)(signed char)(g_d[g] >> 16), dy = (int)(signed char)(g_d[g] >> 8),
+                      dx = (int)(signed char)(g_d[g]);
+            const bool ok = pix_ok && g_ok[g] && gb_in_bounds(p.gathered, gz + dz, gy + dy, gx + dx);
+            cp_async16(g_s + g * ATOM + i * 2048, ok ? ga + (goff + g_toff[g]) : ga, ok);
+          }
         }
       }
       cp_async_commit();
@@ -214,23 +282,53 @@ int launch(const gb_wgrad_params& p, cudaStream_t st) {
   using C = WCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    GB_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    GB_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    GB_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr_set = true;
   }
   const int64_t Mq = (int64_t)p.plain.N * p.plain.D * p.plain.H * p.plain.W;
-  const int nblk = gb_cdiv(Mq, BP);
+  PixDivs divs;
+  memset(&divs, 0, sizeof(divs));
+  // TMA-fed producer: unit gather multiplier, both channel counts multiples of 64 (gathered) / 8 (plain)
+  bool tma = g_gb_knobs[3] == 0 && gb_tma_available() && p.gathered.C % 64 == 0 && p.plain.C % 64 == 0 && p.mul[0] == 1 && p.mul[1] == 1 &&
+             p.mul[2] == 1 && p.plain.pad == 0 && p.gathered.pad == 0;
+  CUtensorMap map_p, map_g;
+  memset(&map_p, 0, sizeof(map_p));
+  memset(&map_g, 0, sizeof(map_g));
+  if (tma) {
+    int tw = 8;
+    while (tw < p.plain.W && tw < 64) tw *= 2;
+    const int th = BP / tw;
+    divs.tw = tw;
+    divs.th = th;
+    const int ntx = gb_cdiv(p.plain.W, tw), nty = gb_cdiv(p.plain.H, th);
+    divs.tiles_x = gb_make_fastdiv((uint32_t)ntx);
+    divs.tiles_y = gb_make_fastdiv((uint32_t)nty);
+    divs.tiles_z = gb_make_fastdiv((uint32_t)p.plain.D);
+    divs.ntiles = ntx * nty * p.plain.D * p.plain.N;
+    divs.use_tma = 1;
+    if (gb_tma_activation_map(p.plain, tw, th, &map_p) || gb_tma_activation_map(p.gathered, tw, th, &map_g)) return 1;
+  }
+  const int nblk = tma ? divs.ntiles : gb_cdiv(Mq, BP);
   const int tiles = gb_cdiv(p.kpad, BN) * gb_cdiv(p.rows, BM);
   int splits = p.splits;
   if (splits <= 0) {
-    // fill ~2 waves of the 148 SMs, but keep at least 4 pixel blocks per CTA
-    splits = (2 * 148 + tiles - 1) / tiles;
+    // one wave of the 148 SMs (every split costs a full tile of red.global.add traffic in the epilogue), and at
+    // least 4 pixel blocks per CTA
+    splits = 148 / tiles;
     if (splits > nblk / 4) splits = nblk / 4;
     if (splits < 1) splits = 1;
   }
   const int bps = gb_cdiv(nblk, splits);
   splits = gb_cdiv(nblk, bps);
   dim3 grid(gb_cdiv(p.kpad, BN), gb_cdiv(p.rows, BM), splits);
-  igemm_wgrad_kernel<BN><<<grid, 256, C::SMEM, st>>>(p, bps);
+  divs.f[0] = gb_make_fastdiv((uint32_t)p.plain.D);
+  divs.f[1] = gb_make_fastdiv((uint32_t)p.plain.H);
+  divs.f[2] = gb_make_fastdiv((uint32_t)p.plain.W);
+  if (tma)
+    igemm_wgrad_kernel<BN, true><<<grid, 256, C::SMEM, st>>>(p, divs, map_p, map_g, bps);
+  else
+    igemm_wgrad_kernel<BN, false><<<grid, 256, C::SMEM, st>>>(p, divs, map_p, map_g, bps);
   GB_LAUNCH_CHECK();
   return 0;
 }
@@ -250,6 +348,7 @@ extern "C" int gb_conv_wgrad(const gb_wgrad_params* pp, void* stream) {
   GB_CHECK(p.ntaps >= 1 && p.ntaps <= GB_MAX_TAPS, "gb_conv_wgrad: bad tap count %d", p.ntaps);
   GB_CHECK(p.rows >= 1 && p.rows <= p.plain.C, "gb_conv_wgrad: bad row count %d", p.rows);
   GB_CHECK(p.plain.N == p.gathered.N, "gb_conv_wgrad: batch mismatch");
+  GB_CHECK((int64_t)p.plain.N * p.plain.D * p.plain.H * p.plain.W < (1ll << 31) - 64, "gb_conv_wgrad: too many pixels");
   GB_CHECK(view_max_offset(p.plain) < (1ll << 31) && view_max_offset(p.gathered) < (1ll << 31),
            "gb_conv_wgrad: tensor too large for 32-bit offsets");
   GB_CHECK(((uintptr_t)p.plain.ptr & 15) == 0 && ((uintptr_t)p.gathered.ptr & 15) == 0 && ((uintptr_t)p.dw & 15) == 0,

@@ -15,12 +15,13 @@ namespace {
 struct Pix {
   int z, y, x;
 };
-__device__ __forceinline__ Pix decode_pix(int64_t pix, const gb_view& v) {
-  Pix r;
-  r.x = (int)(pix % v.W);
-  pix /= v.W;
-  r.y = (int)(pix % v.H);
-  r.z = (int)(pix / v.H);
+__device__ __forceinline__ Pix decode_pix(int64_t pix64, const gb_view& v) {
+  Pix r;  // 32-bit on purpose (pixel counts are checked < 2^31 on the host)
+  const uint32_t pix = (uint32_t)pix64, W = (uint32_t)v.W, H = (uint32_t)v.H;
+  const uint32_t t = pix / W;
+  r.x = (int)(pix - t * W);
+  r.z = (int)(t / H);
+  r.y = (int)(t - (uint32_t)r.z * H);
   return r;
 }
 __device__ __forceinline__ void load8(const gb_view& v, int n, int z, int y, int x, int cg, float (&f)[8]) {
@@ -208,6 +209,7 @@ __global__ void in_bwd_kernel(const __grid_constant__ gb_in_bwd_params p, int pi
   const int64_t p1 = min(P, p0 + pix_per_block);
   const bool norm = p.stats != nullptr;
   float mean[8], rstd[8], slope[8], m1[8], m2[8], s1[8], s2[8], sp[8];
+  const bool want_dbias = MODE == 1 && p.dbias != nullptr;
   const float invP = 1.f / (float)P;
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -283,7 +285,15 @@ __global__ void in_bwd_kernel(const __grid_constant__ gb_in_bwd_params p, int pi
         float d[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) d[e] = norm ? rstd[e] * (g[e] - m1[e] - xv[e] * m2[e]) : g[e];
-        store8(p.dx, n, q.z, q.y, q.x, cg, pack8(d));
+        const uint4 packed = pack8(d);
+        store8(p.dx, n, q.z, q.y, q.x, cg, packed);
+        if (want_dbias) {  // sum what the wgrad / dgrad kernels will actually read (the bf16-rounded values)
+          float2 t;
+          t = unpack_bf16x2(packed.x); s1[0] += t.x; s1[1] += t.y;
+          t = unpack_bf16x2(packed.y); s1[2] += t.x; s1[3] += t.y;
+          t = unpack_bf16x2(packed.z); s1[4] += t.x; s1[5] += t.y;
+          t = unpack_bf16x2(packed.w); s1[6] += t.x; s1[7] += t.y;
+        }
       }
     }
   }
@@ -307,6 +317,18 @@ __global__ void in_bwd_kernel(const __grid_constant__ gb_in_bwd_params p, int pi
       atomicAdd(p.bstats + ((int64_t)n * x.C + c) * 2 + 0, a);
       atomicAdd(p.bstats + ((int64_t)n * x.C + c) * 2 + 1, b);
       if (p.dprelu != nullptr) atomicAdd(p.dprelu + c, d);
+    }
+  }
+  if (want_dbias) {
+    if (slot < slots) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[slot * x.C + cg * 8 + e] = s1[e];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < x.C; c += blockDim.x) {
+      float a = 0.f;
+      for (int k = 0; k < slots; ++k) a += red[k * x.C + c];
+      atomicAdd(p.dbias + c, a);
     }
   }
 }
@@ -374,7 +396,7 @@ extern "C" int gb_in_bwd(const gb_in_bwd_params* p, void* stream) {
     in_bwd_kernel<0><<<L.grid, L.threads, sizeof(float) * 3 * L.slots * p->x.C, st>>>(*p, L.ppb);
     GB_LAUNCH_CHECK();
   }
-  in_bwd_kernel<1><<<L.grid, L.threads, 0, st>>>(*p, L.ppb);
+  in_bwd_kernel<1><<<L.grid, L.threads, p->dbias ? sizeof(float) * L.slots * p->x.C : 0, st>>>(*p, L.ppb);
   GB_LAUNCH_CHECK();
   return 0;
 }

@@ -126,7 +126,7 @@ class BaseGAN(ABC):
             return tensor.to(self.device, non_blocking=True)
         buf = self._static.get(name)
         if buf is None or buf.shape != tensor.shape:
-            if self._graphs:
+            if buf is not None and self._graphs:
                 raise RuntimeError("input shape changed after CUDA-graph capture")
             buf = torch.empty(tensor.shape, dtype=torch.float32, device=self.device)
             self._static[name] = buf
@@ -141,10 +141,40 @@ class BaseGAN(ABC):
             self._graph_calls += 1
         return self._graph_calls > self.graph_warmup_iters
 
+    def eager_stream(self):
+        """Eager iterations that precede a capture run on a side stream (PyTorch's whole-network-capture recipe):
+        autograd's AccumulateGrad nodes must not be bound to the legacy default stream."""
+        import contextlib
+        if not self.use_cuda_graph:
+            return contextlib.nullcontext()
+        if getattr(self, "_warm_stream", None) is None:
+            self._warm_stream = torch.cuda.Stream()
+
+        @contextlib.contextmanager
+        def ctx():
+            cur = torch.cuda.current_stream()
+            self._warm_stream.wait_stream(cur)
+            with torch.cuda.stream(self._warm_stream):
+                yield
+            cur.wait_stream(self._warm_stream)
+
+        return ctx()
+
     def run_graphed(self, name, fn):
         g = self._graphs.get(name)
         if g is None:
             from ganslate_b200 import _cabi
+            if not self._graphs:
+                # drop the last eager iteration's autograd graph (kept alive by losses / visuals)
+                for d in (self.losses, self.metrics):
+                    for k in list(d):
+                        d[k] = None
+                for k in list(self.visuals):
+                    if not k.startswith('real'):
+                        self.visuals[k] = None
+                self.pred_real = self.pred_fake = None
+                import gc
+                gc.collect()
             n0 = _cabi.lib().gb_launch_count()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()

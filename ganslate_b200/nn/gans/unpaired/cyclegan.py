@@ -64,8 +64,9 @@ class CycleGAN(BaseGAN):
             fake_A = self.stage_input('pool_A', self.fake_A_pool.query(self.visuals['fake_A'].detach().clone()))
             self.run_graphed('D', lambda: self._phase_D(fake_B, fake_A))
             return
-        self._phase_G()
-        self._phase_D(None, None)
+        with self.eager_stream():
+            self._phase_G()
+            self._phase_D(None, None)
 
     def _phase_G(self):
         discriminators = [self.networks['D_B'], self.networks['D_A']]

@@ -109,12 +109,14 @@ class Buf:
     t: tensor (N, D, H+2*pad, W+2*pad, Cpad); pad: materialised reflection border; channels: logical channels;
     raw: True if t is a bare convolution output (its gradient is the bf16 MMA operand of dgrad/wgrad),
     False for an activation buffer (fp32 gradient)."""
-    __slots__ = ("t", "pad", "channels", "is_3d", "raw", "grad", "needs_grad_flag")
+    __slots__ = ("t", "pad", "channels", "is_3d", "raw", "grad", "needs_grad_flag", "want_dbias", "dbias")
 
     def __init__(self, t, pad, channels, is_3d, raw=False):
         self.t, self.pad, self.channels, self.is_3d, self.raw = t, pad, channels, is_3d, raw
         self.grad = None  # filled during Tape.backward
         self.needs_grad_flag = True  # False only for a network input that does not require grad
+        self.want_dbias = False      # the producing conv's bias needs a gradient (fused into the consumer's backward)
+        self.dbias = None
 
 
 class Tape:
@@ -183,18 +185,23 @@ def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0) -> Buf:
     y = ops.conv_forward(op, x, m.weight, m.bias, act, slope)
     out = Buf(y, 0, m.out_channels, b.is_3d, raw=(act == ACT_NONE))
     weight, bias = m.weight, m.bias
+    out.want_dbias = tape is not None and tape.needs(bias)
 
     def bwd():
         g = out.grad
         if g is None:
             return
         out.grad = None
+        db = out.dbias
+        out.dbias = None
         if act != ACT_NONE:
-            g = ops.act_backward(g, y, act, slope)  # fp32 d_buf -> bf16 d_raw
+            if tape.needs(bias):
+                db = ops.zeros((y.shape[-1],), y.device)
+            g = ops.act_backward(g, y, act, slope, dbias=db)  # fp32 d_buf -> bf16 d_raw (+ bias gradient)
         if tape.needs(weight):
             tape.add_param_grad(weight, op.run_wgrad(x, g, weight.shape))
         if tape.needs(bias):
-            tape.add_param_grad(bias, ops.colsum(g, op.cout))
+            tape.add_param_grad(bias, db[:op.cout] if db is not None else ops.colsum(g, op.cout))
         if b.grad is not None or b.needs_grad_flag:
             b.grad = op.run_dgrad(g, weight, x.shape, into=b.grad)
 
@@ -224,11 +231,13 @@ def step_norm_act(tape: Tape, raw: Buf, norm: bool, act: int, slope: float, out_
         if residual is not None and residual.needs_grad_flag:
             if residual.grad is not None:
                 raise NotImplementedError("residual gradient buffer already exists (unsupported topology)")
-            dres = torch.zeros(residual.t.shape, dtype=torch.float32, device=x.device)
+            dres = ops.zeros(residual.t.shape, x.device)
             residual.grad = dres
+        if raw.want_dbias and raw.needs_grad_flag:
+            raw.dbias = ops.zeros((x.shape[-1],), x.device)
         raw.grad = ops.norm_act_backward(x, stats, t, g, norm, act, slope, out_pad, eps, dres32=dres,
                                          res_pad=residual.pad if residual is not None else 0,
-                                         need_draw=raw.needs_grad_flag)
+                                         need_draw=raw.needs_grad_flag, dbias=raw.dbias)
 
     if tape is not None:
         tape.steps.append(bwd)
@@ -306,12 +315,15 @@ class NetworkFn(torch.autograd.Function):
         if len(mods) and isinstance(mods[-1], Tanh):
             mods, act = mods[:-1], ACT_TANH
         pad = first_pad(mods)
+        ctx.arena_key = (id(mods[0]) if len(mods) else 0, tuple(x.shape), tuple(ctx.needs_input_grad))
+        ops.arena_begin(("fwd",) + ctx.arena_key, x.device)
         b0 = Buf(ops.to_channels_last(x, pad), pad, x.shape[1], x.dim() == 5)
         b0.needs_grad_flag = bool(ctx.needs_input_grad[1])
         b = run_sequence(tape, mods, b0)
         if b.pad != 0:
             raise RuntimeError("cannot export a bordered buffer")
         y = ops.from_channels_last(b.t, b.channels, b.is_3d, act)
+        ops.arena_end(("fwd",) + ctx.arena_key)
         ctx.tape, ctx.params, ctx.b0, ctx.b_last, ctx.act = tape, params, b0, b, act
         ctx.in_shape = tuple(x.shape)
         return y
@@ -320,6 +332,7 @@ class NetworkFn(torch.autograd.Function):
     def backward(ctx, dy):
         tape, b0, b = ctx.tape, ctx.b0, ctx.b_last
         tape.param_grads = {}
+        ops.arena_begin(("bwd",) + ctx.arena_key, dy.device)
         b.grad = ops.from_channels_last_backward(dy, b.t.shape, b.channels, pre=b.t if ctx.act == ACT_TANH else None,
                                                  fp32=not b.raw)
         tape.backward()
@@ -327,6 +340,7 @@ class NetworkFn(torch.autograd.Function):
         if ctx.needs_input_grad[1] and b0.grad is not None:
             dx = ops.to_channels_last_backward(b0.grad, b0.pad, ctx.in_shape)
         b0.grad = None
+        ops.arena_end(("bwd",) + ctx.arena_key)
         grads = [tape.param_grads.get(id(p)) for p in ctx.params]
         tape.param_grads = {}
         return (None, dx, *grads)

@@ -21,6 +21,54 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# ---- zero-initialised scratch (statistics, weight-gradient workspaces, residual gradient buffers) -------------
+# Every network pass needs ~100 small zeroed fp32 buffers; a fill kernel each would be ~400 launches per training
+# step. A pass opens an arena keyed by (network, phase, shapes): the first time the requests are served one by one
+# and their total is recorded, afterwards ONE zero fill serves them all as slices.
+class _Arena:
+    __slots__ = ("flat", "off", "need", "overflow")
+
+    def __init__(self, flat):
+        self.flat, self.off, self.need, self.overflow = flat, 0, 0, False
+
+
+_ARENA = None
+_ARENA_SIZES = {}
+
+
+def arena_begin(key, device):
+    global _ARENA
+    n = _ARENA_SIZES.get(key, 0)
+    flat = torch.zeros(n, dtype=torch.float32, device=device) if n > 0 else None
+    _ARENA = _Arena(flat)
+    return _ARENA
+
+
+def arena_end(key):
+    global _ARENA
+    a, _ARENA = _ARENA, None
+    if a is not None and (a.overflow or a.need != _ARENA_SIZES.get(key, 0)):
+        _ARENA_SIZES[key] = a.need
+
+
+def zeros(shape, device):
+    """fp32 zeros, 16-byte aligned, from the open arena when it has room."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    a = _ARENA
+    if a is None:
+        return torch.zeros(shape, dtype=torch.float32, device=device)
+    n4 = (n + 3) // 4 * 4
+    a.need += n4
+    if a.flat is not None and a.off + n4 <= a.flat.numel() and a.flat.device == torch.device(device):
+        t = a.flat[a.off:a.off + n].view(shape)
+        a.off += n4
+        return t
+    a.overflow = True
+    return torch.zeros(shape, dtype=torch.float32, device=device)
+
+
 # Optional per-launch timing (bench.py roofline): a list that receives (family, work, unit, event0, event1).
 PROFILE = None
 
@@ -77,8 +125,9 @@ class DataSpec:
     def finalize(self, chans_pad: int, rows_pad: int):
         off = 0
         self.kpads, self.w_offsets = [], []
+        # every class matrix uses the same row pitch (the largest class) so that one 2-D TMA map addresses them all
+        kp = max(64, max((len(c["taps"]) * chans_pad + 63) // 64 * 64 for c in self.classes))
         for c in self.classes:
-            kp = max(64, (len(c["taps"]) * chans_pad + 63) // 64 * 64)
             self.kpads.append(kp)
             self.w_offsets.append(off)
             off += rows_pad * kp
@@ -256,7 +305,7 @@ class ConvOp:
     def run_wgrad(self, x, dy, weight_shape):
         """fp32 weight gradient in the PyTorch layout of `weight_shape`."""
         plain, gathered = (x, dy) if self.transposed else (dy, x)
-        ws = torch.zeros((self.wg_rows_pad, self.wg_kpad), dtype=torch.float32, device=x.device)
+        ws = zeros((self.wg_rows_pad, self.wg_kpad), x.device)
         cache = self.__dict__.setdefault("_ptemplates", {})
         p = cache.get("wgrad")
         if p is None:
@@ -296,12 +345,14 @@ def conv_forward(op: ConvOp, x, weight, bias, act=ACT_NONE, slope=0.0):
     return op.run_fwd(x, weight, bias, act, slope)
 
 
-def act_backward(dy32: torch.Tensor, y: torch.Tensor, act: int, slope: float) -> torch.Tensor:
-    """bf16 d_raw = dy * act'(.) from the forward output y (epilogue activations), dy fp32."""
+def act_backward(dy32: torch.Tensor, y: torch.Tensor, act: int, slope: float, dbias=None) -> torch.Tensor:
+    """bf16 d_raw = dy * act'(.) from the forward output y (epilogue activations), dy fp32.
+    dbias: optional zeroed fp32 [C] that receives the per-channel sum of d_raw (bias gradient)."""
     dx = torch.empty_like(y)
     p = InBwdParams()
     p.x, p.y, p.dy_a, p.dx = make_view(y), make_view(y), make_view(dy32), make_view(dx)
     p.act, p.act_slope, p.eps = act, slope, 1e-5
+    p.dbias = dbias.data_ptr() if dbias is not None else None
     _cabi.check(_cabi.lib().gb_in_bwd(C.byref(p), _stream()), "gb_in_bwd(act)")
     return dx
 
@@ -314,7 +365,7 @@ def norm_act_forward(raw, residual, res_pad, norm, act, slope, out_pad, eps):
     stats = None
     xv = make_view(raw)
     if norm:
-        stats = torch.zeros((N, Cc, 2), dtype=torch.float32, device=raw.device)
+        stats = zeros((N, Cc, 2), raw.device)
         _call("in_stats", raw.numel() * 2, "byte", "gb_in_stats", lib.gb_in_stats, C.byref(xv), stats.data_ptr(), _stream())
     out = torch.empty((N, D, H + 2 * out_pad, W + 2 * out_pad, Cc), dtype=torch.bfloat16, device=raw.device)
     p = InFwdParams()
@@ -328,7 +379,8 @@ def norm_act_forward(raw, residual, res_pad, norm, act, slope, out_pad, eps):
     return out, stats
 
 
-def norm_act_backward(raw, stats, out, dout32, norm, act, slope, out_pad, eps, dres32=None, res_pad=0, need_draw=True):
+def norm_act_backward(raw, stats, out, dout32, norm, act, slope, out_pad, eps, dres32=None, res_pad=0, need_draw=True,
+                      dbias=None):
     """dout32: fp32 gradient wrt the (bordered) output buffer. Returns bf16 d_raw.
     dres32: fp32 gradient buffer of the residual input; its interior is OVERWRITTEN with fold(dout32)."""
     lib = _cabi.lib()
@@ -341,9 +393,10 @@ def norm_act_backward(raw, stats, out, dout32, norm, act, slope, out_pad, eps, d
     draw = torch.empty_like(raw)
     p.dx = make_view(draw)
     p.eps = eps
+    p.dbias = dbias.data_ptr() if (dbias is not None and need_draw) else None
     if need_draw:
         if norm:
-            bstats = torch.zeros((N, Cc, 2), dtype=torch.float32, device=raw.device)
+            bstats = zeros((N, Cc, 2), raw.device)
             p.stats, p.bstats = stats.data_ptr(), bstats.data_ptr()
         elif act != ACT_NONE:
             p.y = make_view(out, out_pad)

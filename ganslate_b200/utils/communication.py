@@ -11,8 +11,9 @@ def init_distributed():
     """communication.py:17-27: WORLD_SIZE>1 => NCCL process group from the environment + barrier."""
     num_gpu = int(os.environ.get("WORLD_SIZE", 1))
     if num_gpu > 1 and not dist.is_initialized():
-        torch.cuda.set_device(get_local_rank())
-        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        backend = "nccl" if torch.cuda.is_available() else "gloo"  # gloo only for the CPU host-logic tests
+        if backend == "nccl":
+            torch.cuda.set_device(get_local_rank())
         dist.init_process_group(backend=backend, init_method="env://")
         synchronize()
 

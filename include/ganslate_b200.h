@@ -157,6 +157,8 @@ typedef struct gb_in_bwd_params {
   float* bstats;             /* [N][C][2] workspace (sum g, sum g*xhat), zeroed by caller */
   const float* prelu;
   float* dprelu;             /* [C] fp32 accumulated (zeroed by caller) or NULL */
+  float* dbias;              /* [C] fp32 accumulated sum of dx over pixels = gradient of the conv bias that feeds x
+                                (zeroed by caller) or NULL */
   float eps;
   int32_t act;
   float act_slope;

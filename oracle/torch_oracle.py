@@ -228,7 +228,7 @@ class OracleCycleGAN:
         self.backward_D("D_A")
         if step_optimizers:
             self.optimizers["D"].step()
-        return {k: float(v) for k, v in self.losses.items() if v is not None}
+        return {k: float(v.detach()) for k, v in self.losses.items() if v is not None}
 
 
 def synthetic_batch(batch, channels=3, size=256, seed=1, device="cpu", width=None):
@@ -371,3 +371,41 @@ class OracleCycleGANBf16(OracleCycleGAN):
         super().__init__(*a, **k)
         for net in self.networks.values():
             net.forward = (lambda x, _n=net: forward_bf16_points(_n, x))
+
+
+# --------------------------------------------------------------------------------------------- Pix2Pix step
+class OraclePix2Pix:
+    """One iteration as ganslate/nn/gans/paired/pix2pix.py:76-152 runs it (Resnet2D generator, PatchGAN2D on
+    cat[A, B]); lambda_pix2pix * L1 (pix2pix_losses.py:14-19)."""
+
+    def __init__(self, lambda_pix2pix=30.0, n_residual_blocks=9, n_layers=4, seed=0, lr=2e-4, bf16_points=False):
+        torch.manual_seed(seed)
+        self.lam = lambda_pix2pix
+        self.networks = {"G": init_weights(OracleResnet2D(3, 3, n_residual_blocks)),      # dict order pix2pix.py:42
+                         "D": init_weights(OraclePatchGAN2D(6, 64, n_layers))}
+        if bf16_points:
+            for net in self.networks.values():
+                net.forward = (lambda x, _n=net: forward_bf16_points(_n, x))
+        self.optimizers = {k: torch.optim.Adam(self.networks[k].parameters(), lr=lr, betas=(0.5, 0.999)) for k in "GD"}
+        self.visuals, self.losses = {}, {}
+
+    def optimize_parameters(self, real_A, real_B, step_optimizers=True):
+        G, D = self.networks["G"], self.networks["D"]
+        fake_B = G(real_A)
+        self.visuals = {"real_A": real_A, "real_B": real_B, "fake_B": fake_B}
+        OracleCycleGAN._set_requires_grad([D], False)
+        self.optimizers["G"].zero_grad(set_to_none=True)
+        self.losses["G"] = adversarial_lsgan(D(torch.cat([real_A, fake_B], 1)), True)
+        self.losses["pix2pix"] = self.lam * F.l1_loss(fake_B, real_B)
+        (self.losses["G"] + self.losses["pix2pix"]).backward()
+        if step_optimizers:
+            self.optimizers["G"].step()
+        OracleCycleGAN._set_requires_grad([D], True)
+        self.optimizers["D"].zero_grad(set_to_none=True)
+        pred_real = D(torch.cat([real_A, real_B], 1))
+        pred_fake = D(torch.cat([real_A, fake_B.detach()], 1))
+        self.losses["D"] = adversarial_lsgan(pred_real, True) + adversarial_lsgan(pred_fake, False)
+        self.losses["D"].backward()
+        if step_optimizers:
+            self.optimizers["D"].step()
+        return {k: float(v.detach()) for k, v in self.losses.items()}

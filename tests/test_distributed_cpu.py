@@ -1,0 +1,65 @@
+"""world_size-2 gloo tests of the N>1 host path: process-group helpers and DDP gradient averaging as wired by
+BaseGAN.parallelize_networks (one DDP wrapper per network, broadcast_buffers=False)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from ganslate_b200.utils import communication as comm
+    from oracle import torch_oracle as O
+    comm.init_distributed()  # gloo on a CPU box
+    assert comm.get_world_size() == world and comm.get_rank() == rank and comm.get_local_rank() == rank
+    seed = comm.shared_random_seed()
+    red = comm.reduce({"a": torch.tensor(float(rank + 1)), "b": torch.tensor(2.0)}, average=True, all_reduce=True)
+    # DDP over a small discriminator: averaged gradient == mean of the per-rank gradients
+    torch.manual_seed(0)
+    net = O.init_weights(O.OraclePatchGAN2D(3, 8, 2))
+    ddp = torch.nn.parallel.DistributedDataParallel(net, broadcast_buffers=False)
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.rand((1, 3, 32, 32), generator=g)
+    O.adversarial_lsgan(ddp(x), True).backward()
+    grad = net.model[0].weight.grad.clone()
+    # reference value: both shards on one process
+    torch.manual_seed(0)
+    ref = O.init_weights(O.OraclePatchGAN2D(3, 8, 2))
+    tot = 0
+    for r in range(world):
+        gr = torch.Generator().manual_seed(100 + r)
+        tot = tot + O.adversarial_lsgan(ref(torch.rand((1, 3, 32, 32), generator=gr)), True)
+    (tot / world).backward()
+    q.put((rank, seed, float(red["a"]), float(red["b"]), float((grad - ref.model[0].weight.grad).abs().max())))
+    comm.synchronize()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_gloo_world2_helpers_and_ddp_average():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1]                      # shared seed agreed by broadcast
+    assert res[0][2] == pytest.approx(1.5) and res[0][3] == pytest.approx(2.0)
+    assert all(r[4] < 1e-6 for r in res)               # DDP average == single-process mean

@@ -1,0 +1,132 @@
+"""Host-side logic that needs no GPU: implicit-GEMM geometry (class / tap decomposition and weight packing
+strides) checked against torch's CPU convolutions, the config tree, and the plug-in builders."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from ganslate_b200 import ops
+from ganslate_b200.configs.utils import Conf, init_config
+from ganslate_b200.presets import cyclegan_resnet2d
+
+
+def emulate_data_gemm(spec, x, wmat_fn, out_ext, n_out):
+    """Evaluate a DataSpec literally as include/ganslate_b200.h defines gb_conv_data:
+    out[q*out_mul+off][n] = sum_{t,c} in[q*in_mul + d_t][c] * W[n][t][c], zero outside the input."""
+    N, C, D, H, W = x.shape
+    out = np.zeros((N, n_out) + tuple(out_ext), dtype=np.float64)
+    xn = x.numpy().astype(np.float64)
+    for cls in spec.classes:
+        off = cls["off"]
+        q_ext = [max(0, -(-(out_ext[d] - off[d]) // spec.out_mul[d])) for d in range(3)]
+        for q in itertools.product(*[range(e) for e in q_ext]):
+            o = tuple(q[d] * spec.out_mul[d] + off[d] for d in range(3))
+            for tl, (tap, tid) in enumerate(zip(cls["taps"], cls["tap_ids"])):
+                i = tuple(q[d] * spec.in_mul[d] + tap[d] for d in range(3))
+                if all(0 <= i[d] < (D, H, W)[d] for d in range(3)):
+                    out[:, :, o[0], o[1], o[2]] += xn[:, :, i[0], i[1], i[2]] @ wmat_fn(tid).T
+    return out
+
+
+CASES = [
+    dict(k=(1, 3, 3), s=(1, 1, 1), p=(0, 1, 1), transposed=False),
+    dict(k=(1, 3, 3), s=(1, 2, 2), p=(0, 1, 1), transposed=False),
+    dict(k=(1, 4, 4), s=(1, 2, 2), p=(0, 1, 1), transposed=False),
+    dict(k=(1, 7, 7), s=(1, 1, 1), p=(0, 0, 0), transposed=False),
+    dict(k=(1, 3, 3), s=(1, 2, 2), p=(0, 1, 1), transposed=True, op=(0, 1, 1)),
+    dict(k=(1, 4, 4), s=(1, 2, 2), p=(0, 1, 1), transposed=True, op=(0, 0, 0)),
+    dict(k=(2, 2, 2), s=(2, 2, 2), p=(0, 0, 0), transposed=False),
+    dict(k=(2, 2, 2), s=(2, 2, 2), p=(0, 0, 0), transposed=True, op=(0, 0, 0)),
+    dict(k=(3, 3, 3), s=(1, 1, 1), p=(1, 1, 1), transposed=False),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_specs_reproduce_torch_convolutions(case):
+    torch.manual_seed(0)
+    cin, cout = 3, 5
+    k, s, p = case["k"], case["s"], case["p"]
+    tr = case["transposed"]
+    op = ops.ConvOp(cin, cout, k, s, p, transposed=tr, output_padding=case.get("op", (0, 0, 0)))
+    x = torch.randn(2, cin, 1, 9, 8) if not tr else torch.randn(2, cin, 1, 4, 3)
+    if k[0] > 1:
+        x = torch.randn(2, cin, 4, 6, 6)
+    w = torch.randn((cin, cout) + k) if tr else torch.randn((cout, cin) + k)
+    x.requires_grad_(True)
+    if tr:
+        y = F.conv_transpose3d(x, w, None, s, p, case.get("op", (0, 0, 0)))
+    else:
+        y = F.conv3d(x, w, None, s, p)
+    assert tuple(y.shape[2:]) == op.out_extent(tuple(x.shape[2:]))
+    wn = w.numpy().astype(np.float64).reshape(w.shape[0], w.shape[1], -1)
+    # forward: rows = cout, k-channels = cin
+    fwd_w = (lambda tid: wn[:, :, tid].T) if tr else (lambda tid: wn[:, :, tid])
+    got = emulate_data_gemm(op.fwd, x.detach(), fwd_w, tuple(y.shape[2:]), cout)
+    np.testing.assert_allclose(got, y.detach().numpy(), rtol=1e-4, atol=1e-4)
+    # data gradient: rows = cin, k-channels = cout
+    g = torch.randn_like(y)
+    (dx,) = torch.autograd.grad(y, x, g)
+    dg_w = (lambda tid: wn[:, :, tid]) if tr else (lambda tid: wn[:, :, tid].T)
+    got = emulate_data_gemm(op.dgrad, g, dg_w, tuple(x.shape[2:]), cin)
+    np.testing.assert_allclose(got, dx.numpy(), rtol=1e-4, atol=1e-4)
+    # packing strides address the same elements as the emulation's matrices
+    sn, sc, st = op.fwd_strides
+    flat = w.contiguous().view(-1)
+    for n, c, t in [(0, 0, 0), (cout - 1, cin - 1, op.T - 1), (1, 2, op.T // 2)]:
+        assert flat[n * sn + c * sc + t * st].item() == pytest.approx(fwd_w(t)[n, c])
+    sn, sc, st = op.dgrad_strides
+    for n, c, t in [(0, 0, 0), (cin - 1, cout - 1, op.T - 1)]:
+        assert flat[n * sn + c * sc + t * st].item() == pytest.approx(dg_w(t)[n, c])
+
+
+def test_spec_padding_and_limits():
+    op = ops.ConvOp(3, 64, (1, 7, 7), (1, 1, 1), (0, 0, 0))
+    assert op.cin_pad == 8 and op.fwd.kpads == [448] and op.wg_kpad == 448
+    op = ops.ConvOp(256, 256, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    assert len(op.dgrad.classes) == 4 and sorted(len(c["taps"]) for c in op.dgrad.classes) == [1, 2, 2, 4]
+    with pytest.raises(ValueError):
+        ops.ConvOp(8, 8, (6, 6, 6), (1, 1, 1), (0, 0, 0))
+    assert op.flops((1, 128, 128), 1) == 2.0 * 64 * 64 * 256 * 256 * 9
+
+
+def test_config_tree_and_target_defaults():
+    conf = cyclegan_resnet2d(batch_size=2)
+    assert conf.mode == "train" and conf["train"].batch_size == 2
+    gan = conf.train.gan
+    assert gan.norm_type == "instance" and gan.weight_init_gain == 0.02 and gan.pool_size == 50
+    assert tuple(gan.generator.in_out_channels.BA) == (3, 3)          # BA <- AB (configs/base.py:30)
+    assert gan.discriminator.in_channels.A == 3                       # A <- B (configs/base.py:42)
+    assert gan.discriminator.kernel_size == (4, 4) and gan.discriminator.ndf == 64
+    assert gan.optimizer.beta1 == 0.5 and gan.optimizer.lambda_AB == 10.0
+    c2 = init_config(conf.to_dict(), overrides=["train.gan.optimizer.lr_G=0.001", "train.batch_size=4"])
+    assert c2.train.gan.optimizer.lr_G == 0.001 and c2.train.batch_size == 4
+    assert isinstance(conf.train, Conf) and "gan" in conf.train and dict(gan.discriminator)["n_layers"] == 3
+
+
+def test_builders_construct_networks_in_reference_order():
+    from ganslate_b200.utils.builders import build_D, build_G
+    conf = cyclegan_resnet2d()
+    torch.manual_seed(0)
+    g = build_G(conf, "AB", "cpu")
+    d = build_D(conf, "A", "cpu")
+    assert sum(p.numel() for p in g.parameters()) == 11378179
+    assert sum(p.numel() for p in d.parameters()) == 2764737
+    assert float(g.model[1].bias.abs().sum()) == 0.0 and 0.015 < float(g.model[1].weight.std()) < 0.025
+
+
+def test_scheduler_rule_matches_reference_formula():
+    from ganslate_b200.nn.utils import get_scheduler
+    conf = cyclegan_resnet2d(n_iters=10, n_iters_decay=10)
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.Adam([p], lr=1.0)
+    sch = get_scheduler(opt, conf)
+    lrs = []
+    for _ in range(22):
+        lrs.append(opt.param_groups[0]["lr"])
+        opt.step()
+        sch.step()
+    # lr_l = 1 - max(0, iter + 1 - n_iters) / (n_iters_decay + 1)   (ganslate/nn/utils.py:91-97)
+    want = [1.0 - max(0, i + 1 - 10) / 11.0 for i in range(22)]
+    assert lrs == pytest.approx(want)

@@ -1,0 +1,149 @@
+"""Pins the CPU oracle: against the golden fixtures generated from the reference's own modules
+(oracle/make_golden.py) and, when /root/reference is present, against those modules directly."""
+import json
+import os
+import random
+
+import pytest
+import torch
+
+from oracle import reference_import as R
+from oracle import torch_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def digest(t):
+    t = t.detach().double().flatten()
+    idx = torch.linspace(0, t.numel() - 1, 5).long()
+    return {"sum": t.sum().item(), "abs_sum": t.abs().sum().item(), "sq_sum": (t * t).sum().item(),
+            "samples": t[idx].tolist(), "numel": t.numel()}
+
+
+def close(a, b, rtol=2e-4, atol=1e-7):
+    return abs(a - b) <= atol + rtol * max(abs(a), abs(b))
+
+
+def assert_digest(got, ref, what, rtol=2e-4, atol=1e-6):
+    assert got["numel"] == ref["numel"], what
+    # sums of signed values cancel: compare against the magnitude scale (abs_sum)
+    assert abs(got["sum"] - ref["sum"]) <= atol + rtol * ref["abs_sum"], (what, got["sum"], ref["sum"])
+    assert close(got["abs_sum"], ref["abs_sum"], rtol, atol), (what, got["abs_sum"], ref["abs_sum"])
+    assert close(got["sq_sum"], ref["sq_sum"], 2 * rtol, atol), (what, got["sq_sum"], ref["sq_sum"])
+    scale = (ref["sq_sum"] / ref["numel"])**0.5
+    for g, r in zip(got["samples"], ref["samples"]):
+        assert abs(g - r) <= atol + 5 * rtol * max(scale, abs(r)), (what, g, r)
+
+
+@pytest.mark.parametrize("name", ["cyclegan_step_32px_2blk", "cyclegan_step_64px_3blk_idt"])
+def test_oracle_matches_reference_golden(name):
+    with open(os.path.join(GOLDEN, name + ".json")) as f:
+        gold = json.load(f)
+    c = gold["config"]
+    random.seed(0)
+    m = O.OracleCycleGAN(O.default_cyclegan_conf(n_residual_blocks=c["n_blocks"], lambda_identity=c["lambda_identity"]),
+                         seed=c["seed"])
+    for n, keys in gold["state_dict_keys"].items():
+        assert list(m.networks[n].state_dict().keys()) == keys
+        assert sum(p.numel() for p in m.networks[n].parameters()) == gold["param_counts"][n]
+    a, b = O.synthetic_batch(c["batch"], 3, c["size"], seed=c["data_seed"])
+    # snapshot the G gradients before the D phase exactly like the generator of the fixture did
+    losses = {}
+    m.visuals["real_A"], m.visuals["real_B"] = a, b
+    ds = [m.networks["D_B"], m.networks["D_A"]]
+    m.forward()
+    m._set_requires_grad(ds, False)
+    m.optimizers["G"].zero_grad(set_to_none=True)
+    m.backward_G()
+    grads = {f"{n}.{k}": digest(p.grad) for n in ("G_AB", "G_BA") for k, p in m.networks[n].named_parameters()}
+    m.optimizers["G"].step()
+    m._set_requires_grad(ds, True)
+    m.optimizers["D"].zero_grad(set_to_none=True)
+    m.backward_D("D_B")
+    m.backward_D("D_A")
+    grads.update({f"{n}.{k}": digest(p.grad) for n in ("D_B", "D_A") for k, p in m.networks[n].named_parameters()})
+    m.optimizers["D"].step()
+    losses = {k: float(v) for k, v in m.losses.items() if v is not None}
+    for k, v in gold["losses"].items():
+        assert close(losses[k], v, 1e-5), (k, losses[k], v)
+    for k, d in gold["visuals"].items():
+        assert_digest(digest(m.visuals[k]), d, k)
+    for k, d in gold["grads"].items():
+        assert_digest(grads[k], d, k, rtol=1e-3)
+    for n in m.networks:
+        for k, p in m.networks[n].named_parameters():
+            assert_digest(digest(p), gold["weights_after_step"][f"{n}.{k}"], f"weight {n}.{k}")
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference only exists in the build container")
+def test_oracle_networks_equal_reference_modules():
+    m = R.modules()
+    torch.manual_seed(3)
+    ref_g = m["Resnet2D"](3, 3, "instance", 2)
+    m["init_weights"](ref_g, "normal", 0.02)
+    torch.manual_seed(3)
+    ora_g = O.init_weights(O.OracleResnet2D(3, 3, 2))
+    assert list(ref_g.state_dict().keys()) == list(ora_g.state_dict().keys())
+    for (k, a), (_, b) in zip(ref_g.state_dict().items(), ora_g.state_dict().items()):
+        assert torch.equal(a, b), k
+    torch.manual_seed(4)
+    ref_d = m["PatchGAN2D"](3, 64, 3, (4, 4), "instance")
+    m["init_weights"](ref_d, "normal", 0.02)
+    torch.manual_seed(4)
+    ora_d = O.init_weights(O.OraclePatchGAN2D(3, 64, 3, (4, 4)))
+    for (k, a), (_, b) in zip(ref_d.state_dict().items(), ora_d.state_dict().items()):
+        assert torch.equal(a, b), k
+    x = torch.rand(2, 3, 48, 48) * 2 - 1
+    yg, yo = ref_g(x), ora_g(x)
+    assert torch.allclose(yg, yo, atol=1e-6)
+    assert torch.allclose(ref_d(yg), ora_d(yo), atol=1e-6)
+    crit = m["AdversarialLoss"]("lsgan")
+    for flag in (True, False):
+        assert torch.allclose(crit(ref_d(yg), target_is_real=flag), O.adversarial_lsgan(ora_d(yo), flag), atol=1e-7)
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference only exists in the build container")
+def test_b200_modules_mirror_reference_state_dict():
+    """Drop-in contract: same state_dict keys, parameter order, shapes and same-seed initial weights."""
+    from ganslate_b200.nn.discriminators import PatchGAN2D
+    from ganslate_b200.nn.generators import Resnet2D
+    from ganslate_b200.nn.utils import init_weights
+    m = R.modules()
+    for build_ref, build_ours in (
+        (lambda: m["Resnet2D"](3, 3, "instance", 9), lambda: Resnet2D(3, 3, "instance", 9)),
+        (lambda: m["PatchGAN2D"](3, 64, 3, (4, 4), "instance"), lambda: PatchGAN2D(3, 64, 3, (4, 4), "instance")),
+    ):
+        torch.manual_seed(11)
+        ref = build_ref()
+        m["init_weights"](ref, "normal", 0.02)
+        torch.manual_seed(11)
+        ours = build_ours()
+        init_weights(ours, "normal", 0.02)
+        assert list(ref.state_dict().keys()) == list(ours.state_dict().keys())
+        assert [n for n, _ in ref.named_parameters()] == [n for n, _ in ours.named_parameters()]
+        for (k, a), (_, b) in zip(ref.state_dict().items(), ours.state_dict().items()):
+            assert torch.equal(a, b), k
+        ours.load_state_dict(ref.state_dict())
+
+
+def test_bf16_point_oracle_is_close_to_fp32_oracle():
+    torch.manual_seed(0)
+    g = O.init_weights(O.OracleResnet2D(3, 3, 2))
+    x = torch.rand(1, 3, 32, 32) * 2 - 1
+    y, yb = g(x), O.forward_bf16_points(g, x)
+    assert ((y - yb).norm() / y.norm()).item() < 5e-2
+
+
+def test_image_pool_matches_reference_semantics():
+    random.seed(5)
+    pool = O.OracleImagePool(2)
+    a, b, c = torch.zeros(1, 1, 2, 2), torch.ones(1, 1, 2, 2), torch.full((1, 1, 2, 2), 2.0)
+    assert torch.equal(pool.query(a), a) and torch.equal(pool.query(b), b)  # filling: returns the input
+    out = pool.query(c)
+    assert out.shape == c.shape
+    from ganslate_b200.data.utils.image_pool import ImagePool
+    random.seed(5)
+    mine = ImagePool(2)
+    mine.query(a), mine.query(b)
+    assert torch.equal(mine.query(c), out)
