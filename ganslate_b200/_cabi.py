@@ -47,13 +47,16 @@ class PackParams(C.Structure):
 
 class InFwdParams(C.Structure):
     _fields_ = [("x", View), ("y", View), ("res", View), ("stats", C.c_void_p), ("prelu", C.c_void_p),
-                ("eps", C.c_float), ("act", C.c_int32), ("act_slope", C.c_float), ("res_before_act", C.c_int32)]
+                ("eps", C.c_float), ("act", C.c_int32), ("act_slope", C.c_float), ("res_before_act", C.c_int32),
+                ("out_scale", C.c_float)]
 
 
 class InBwdParams(C.Structure):
     _fields_ = [("x", View), ("y", View), ("dy_a", View), ("dy_b", View), ("dy_sum", View), ("dx", View),
                 ("stats", C.c_void_p), ("bstats", C.c_void_p), ("prelu", C.c_void_p), ("dprelu", C.c_void_p),
-                ("dbias", C.c_void_p), ("eps", C.c_float), ("act", C.c_int32), ("act_slope", C.c_float)]
+                ("dbias", C.c_void_p), ("eps", C.c_float), ("act", C.c_int32), ("act_slope", C.c_float),
+                ("res", View), ("res_before_act", C.c_int32), ("dy_sum_acc", C.c_int32), ("dx_fp32_acc", C.c_int32),
+                ("out_scale", C.c_float)]
 
 
 _SIGNATURES = {
@@ -70,6 +73,8 @@ _SIGNATURES = {
     "gb_cl_to_nchw": [C.POINTER(View), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
     "gb_mse_const": [C.c_void_p, C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     "gb_l1": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
+    "gb_patchnce_fwd": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
+    "gb_patchnce_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p],
     "gb_version": [],
     "gb_debug_knob": [C.c_int, C.c_int],
 }
@@ -98,6 +103,11 @@ def lib():
         L.gb_launch_count.argtypes = []
         L.gb_launch_count.restype = C.c_ulonglong
         _lib = L
+        # bring-up knobs: GB_KNOBS="4=1,1=128" -> gb_debug_knob(4, 1); gb_debug_knob(1, 128)
+        import os
+        for item in filter(None, os.environ.get("GB_KNOBS", "").split(",")):
+            k, v = item.split("=")
+            L.gb_debug_knob(int(k), int(v))
     return _lib
 
 

@@ -323,7 +323,8 @@ int64_t view_max_offset(const gb_view& v) {
 
 }  // namespace
 
-int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st);  // igemm_tma.cu: -1 = not applicable
+int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st);   // igemm_tma.cu: -1 = not applicable
+int gb_conv_data_halo(const gb_conv_params& p, cudaStream_t st);  // igemm_halo.cu: -1 = not applicable
 
 extern "C" int gb_conv_data(const gb_conv_params* pp, void* stream) {
   const gb_conv_params& p = *pp;
@@ -357,7 +358,9 @@ extern "C" int gb_conv_data(const gb_conv_params* pp, void* stream) {
   if (max_mc == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   {
-    const int r = gb_conv_data_tma(p, st);  // TMA-fed kernel for unit-stride gathers with C % 64 == 0
+    int r = gb_conv_data_halo(p, st);   // halo-reuse TMA kernel (dense tap windows, single class)
+    if (r >= 0) return r;
+    r = gb_conv_data_tma(p, st);        // TMA-fed kernel for unit-stride gathers with C % 64 == 0
     if (r >= 0) return r;
   }
   // tile width: smallest BN covering the output channels, shrunk while the grid under-fills the 148 SMs

@@ -275,10 +275,8 @@ int gb_tma_activation_map(const gb_view& v, int tw, int th, CUtensorMap* out) {
   return 0;
 }
 
-namespace {
-
 // 2-D weight map {kpad, nclass*npad}, box {64, bn}; all classes of one conv share kpad on this path
-int weight_map(const void* w, int kpad, int rows, int bn, CUtensorMap* out) {
+int gb_tma_weight_map(const void* w, int kpad, int rows, int bn, CUtensorMap* out) {
   struct {
     const void* w;
     int kpad, rows, bn;
@@ -302,6 +300,8 @@ int weight_map(const void* w, int kpad, int rows, int bn, CUtensorMap* out) {
   g_map_cache[key] = *out;
   return 0;
 }
+
+namespace {
 
 template <int BN>
 int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb, const TileGeom& tg, cudaStream_t st) {
@@ -340,10 +340,21 @@ int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st) {
   }
   if (max_ext[0] == 0 || max_ext[1] == 0 || max_ext[2] == 0) return 0;
   if ((p.in.sx * 2) % 16 || (p.in.sy * 2) % 16 || (p.in.sz * 2) % 16 || (p.in.sn * 2) % 16) return -1;
-  // tile shape: TW = power of two in [8, 128] covering the row, TH = 128 / TW
+  // tile shape: TW x TH = 128 pixels, TW a power of two in [8, 128]; pick the shape that wastes the fewest
+  // out-of-range pixels (e.g. the 66x66 padded domain of a reflection-padded dgrad: 16x8 tiles waste 32 %,
+  // 64x2 tiles 94 %), ties go to the wider tile (longer contiguous stores)
   int tw = 8;
-  while (tw < max_ext[2] && tw < 128) tw *= 2;
-  if (tw > 64 && max_ext[2] <= 96) tw = 64;
+  {
+    int64_t best = -1;
+    for (int cand = 8; cand <= 128; cand *= 2) {
+      const int ch = BM / cand;
+      const int64_t cost = (int64_t)gb_cdiv(max_ext[2], cand) * cand * gb_cdiv(max_ext[1], ch) * ch;
+      if (best < 0 || cost <= best) {
+        best = cost;
+        tw = cand;
+      }
+    }
+  }
   int th = BM / tw;
   TileGeom tg;
   tg.tw = tw;
@@ -369,7 +380,7 @@ int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st) {
   if (bn > p.nclass * p.npad) return -1;  // keep every TMA box inside its tensor
   CUtensorMap ma, mb;
   if (gb_tma_activation_map(p.in, tw, th, &ma)) return 1;
-  if (weight_map(p.wpacked, kpad, p.nclass * p.npad, bn, &mb)) return 1;
+  if (gb_tma_weight_map(p.wpacked, kpad, p.nclass * p.npad, bn, &mb)) return 1;
   switch (bn) {
     case 16: return launch<16>(p, ma, mb, tg, st);
     case 32: return launch<32>(p, ma, mb, tg, st);

@@ -71,22 +71,25 @@ __device__ __forceinline__ void store8_reflect(const gb_view& v, int n, int z, i
   for (int a = 0; a < ny; ++a)
     for (int b = 0; b < nx; ++b) store8(v, n, z, ys[a], xs[b], cg, o);
 }
-// gradient on the padded domain folded back to interior pixel (y,x)
-__device__ __forceinline__ void load8_fold(const gb_view& v, int n, int z, int y, int x, int cg, float (&f)[8]) {
+// gradient on the padded domain folded back to interior pixel (y,x): the centre value is loaded by the caller
+// (straight-line, batched across pixels); this adds the border positions that reflect onto (y,x) -- only pixels
+// within `pad` of an edge have any
+__device__ __forceinline__ void add_mirrors(const gb_view& v, int n, int z, int y, int x, int cg, float (&f)[8]) {
   const int p = v.pad;
+  if (p == 0) return;
+  const bool ynear = (y >= 1 && y <= p) || (y <= v.H - 2 && y >= v.H - 1 - p);
+  const bool xnear = (x >= 1 && x <= p) || (x <= v.W - 2 && x >= v.W - 1 - p);
+  if (!ynear && !xnear) return;
   int ys[3], xs[3], ny = 1, nx = 1;
   ys[0] = y;
   xs[0] = x;
-  if (p > 0) {
-    if (y >= 1 && y <= p) ys[ny++] = -y;
-    if (y <= v.H - 2 && y >= v.H - 1 - p) ys[ny++] = 2 * (v.H - 1) - y;
-    if (x >= 1 && x <= p) xs[nx++] = -x;
-    if (x <= v.W - 2 && x >= v.W - 1 - p) xs[nx++] = 2 * (v.W - 1) - x;
-  }
-#pragma unroll
-  for (int e = 0; e < 8; ++e) f[e] = 0.f;
+  if (y >= 1 && y <= p) ys[ny++] = -y;
+  if (y <= v.H - 2 && y >= v.H - 1 - p) ys[ny++] = 2 * (v.H - 1) - y;
+  if (x >= 1 && x <= p) xs[nx++] = -x;
+  if (x <= v.W - 2 && x >= v.W - 1 - p) xs[nx++] = 2 * (v.W - 1) - x;
   for (int a = 0; a < ny; ++a)
     for (int b = 0; b < nx; ++b) {
+      if (a == 0 && b == 0) continue;  // centre already loaded
       float t[8];
       load8f(v, n, z, ys[a], xs[b], cg, t);
 #pragma unroll
@@ -119,15 +122,27 @@ __global__ void in_stats_kernel(gb_view x, float* __restrict__ stats, int pix_pe
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
   if (slot < slots) {
-    for (int64_t pix = p0 + slot; pix < p1; pix += slots) {
-      const Pix q = decode_pix(pix, x);
-      float f[8];
-      load8(x, n, q.z, q.y, q.x, cg, f);
+    constexpr int U = 4;  // pixels in flight per thread (the kernel is latency bound otherwise)
+    for (int64_t pix = p0 + slot; pix < p1; pix += (int64_t)U * slots) {
+      float f[U][8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        s[e] += f[e];
-        ss[e] += f[e] * f[e];
+      for (int u = 0; u < U; ++u) {
+        const int64_t pu = pix + (int64_t)u * slots;
+        if (pu < p1) {
+          const Pix q = decode_pix(pu, x);
+          load8(x, n, q.z, q.y, q.x, cg, f[u]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[u][e] = 0.f;
+        }
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          s[e] += f[u][e];
+          ss[e] += f[u][e] * f[u][e];
+        }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -144,7 +159,7 @@ __global__ void in_stats_kernel(gb_view x, float* __restrict__ stats, int pix_pe
 }
 
 // ------------------------------------------------------------------------------------------- forward
-__global__ void in_fwd_kernel(const __grid_constant__ gb_in_fwd_params p, int pix_per_block) {
+__global__ void __launch_bounds__(256, 2) in_fwd_kernel(const __grid_constant__ gb_in_fwd_params p, int pix_per_block) {
   const gb_view& x = p.x;
   const int C8 = x.C >> 3;
   const int slots = blockDim.x / C8;
@@ -173,22 +188,37 @@ __global__ void in_fwd_kernel(const __grid_constant__ gb_in_fwd_params p, int pi
     slope[e] = (p.act == GB_ACT_PRELU) ? p.prelu[c] : p.act_slope;
   }
   const bool has_res = p.res.ptr != nullptr;
-  for (int64_t pix = p0 + slot; pix < p1; pix += slots) {
-    const Pix q = decode_pix(pix, x);
-    float f[8], r[8];
-    load8(x, n, q.z, q.y, q.x, cg, f);
-    if (has_res) load8(p.res, n, q.z, q.y, q.x, cg, r);
+  const float oscale = p.out_scale == 0.f ? 1.f : p.out_scale;
+  constexpr int U = 2;  // pixels in flight per thread
+  for (int64_t pix = p0 + slot; pix < p1; pix += (int64_t)U * slots) {
+    float f[U][8], r[U][8];
+    Pix q[U];
+    bool ok[U];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float v = (f[e] - mean[e]) * rstd[e];
-      if (has_res && p.res_before_act) v += r[e];
-      v = act_fwd(v, p.act, slope[e]);
-      if (has_res && !p.res_before_act) v += r[e];
-      f[e] = v;
+    for (int u = 0; u < U; ++u) {
+      const int64_t pu = pix + (int64_t)u * slots;
+      ok[u] = pu < p1;
+      if (ok[u]) {
+        q[u] = decode_pix(pu, x);
+        load8(x, n, q[u].z, q[u].y, q[u].x, cg, f[u]);
+        if (has_res) load8(p.res, n, q[u].z, q[u].y, q[u].x, cg, r[u]);
+      }
     }
-    const uint4 o = pack8(f);
-    if (p.y.pad > 0) store8_reflect(p.y, n, q.z, q.y, q.x, cg, o);
-    else store8(p.y, n, q.z, q.y, q.x, cg, o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float v = (f[u][e] - mean[e]) * rstd[e];
+        if (has_res && p.res_before_act) v += r[u][e];
+        v = act_fwd(v, p.act, slope[e]) * oscale;
+        if (has_res && !p.res_before_act) v += r[u][e];
+        f[u][e] = v;
+      }
+      const uint4 o = pack8(f[u]);
+      if (p.y.pad > 0) store8_reflect(p.y, n, q[u].z, q[u].y, q[u].x, cg, o);
+      else store8(p.y, n, q[u].z, q[u].y, q[u].x, cg, o);
+    }
   }
 }
 
@@ -196,7 +226,7 @@ __global__ void in_fwd_kernel(const __grid_constant__ gb_in_fwd_params p, int pi
 // g = act'(.) * (dy_a + fold(dy_b));  MODE 0: reduce (sum g, sum g*xhat), optionally write dy_sum
 //                                     MODE 1: apply dx = rstd * (g - m1 - xhat*m2)
 template <int MODE>
-__global__ void in_bwd_kernel(const __grid_constant__ gb_in_bwd_params p, int pix_per_block) {
+__global__ void __launch_bounds__(256, 2) in_bwd_kernel(const __grid_constant__ gb_in_bwd_params p, int pix_per_block) {
   extern __shared__ float red[];
   const gb_view& x = p.x;
   const int C8 = x.C >> 3;
@@ -210,6 +240,10 @@ __global__ void in_bwd_kernel(const __grid_constant__ gb_in_bwd_params p, int pi
   const bool norm = p.stats != nullptr;
   float mean[8], rstd[8], slope[8], m1[8], m2[8], s1[8], s2[8], sp[8];
   const bool want_dbias = MODE == 1 && p.dbias != nullptr;
+  const bool rba = p.res_before_act != 0 && p.res.ptr != nullptr;
+  const float oscale = p.out_scale == 0.f ? 1.f : p.out_scale;
+  // PReLU slope gradient without normalisation has no reduce pass: it is reduced in the apply pass
+  const bool want_dprelu1 = MODE == 1 && p.stats == nullptr && p.act == GB_ACT_PRELU && p.dprelu != nullptr;
   const float invP = 1.f / (float)P;
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -228,71 +262,142 @@ __global__ void in_bwd_kernel(const __grid_constant__ gb_in_bwd_params p, int pi
     slope[e] = (p.act == GB_ACT_PRELU) ? p.prelu[c] : p.act_slope;
   }
   const bool has_a = p.dy_a.ptr != nullptr, has_b = p.dy_b.ptr != nullptr;
-  const bool use_sum = MODE == 1 && p.dy_sum.ptr != nullptr && norm;  // reduce pass already materialised a+fold(b)
+  // reduce pass already materialised a+fold(b) (only when dy_sum holds exactly that: no accumulate, not masked)
+  const bool use_sum = MODE == 1 && p.dy_sum.ptr != nullptr && norm && !p.dy_sum_acc && !p.res_before_act;
   if (slot < slots) {
-    for (int64_t pix = p0 + slot; pix < p1; pix += slots) {
-      const Pix q = decode_pix(pix, x);
-      float g[8], xv[8], t[8];
-      if (use_sum) {
-        load8f(p.dy_sum, n, q.z, q.y, q.x, cg, g);
-      } else {
+    constexpr int U = 2;  // pixels in flight per thread: all loads of both pixels are issued before any math
+    for (int64_t pix0 = p0 + slot; pix0 < p1; pix0 += (int64_t)U * slots) {
+      float gU[U][8], xU[U][8];
+      Pix qU[U];
+      bool okU[U];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) g[e] = 0.f;
-        if (has_a) {
-          load8f(p.dy_a, n, q.z, q.y, q.x, cg, t);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) g[e] += t[e];
+      for (int u = 0; u < U; ++u) {
+        const int64_t pu = pix0 + (int64_t)u * slots;
+        okU[u] = pu < p1;
+        if (!okU[u]) continue;
+        const Pix q = decode_pix(pu, x);
+        qU[u] = q;
+        if (use_sum) {
+          load8f(p.dy_sum, n, q.z, q.y, q.x, cg, gU[u]);
+        } else {
+          if (has_b) load8f(p.dy_b, n, q.z, q.y, q.x, cg, gU[u]);
+          else load8f(p.dy_a, n, q.z, q.y, q.x, cg, gU[u]);
         }
-        if (has_b) {
-          load8_fold(p.dy_b, n, q.z, q.y, q.x, cg, t);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) g[e] += t[e];
+        if (norm || p.y.ptr == nullptr) {
+          if (norm || p.act != GB_ACT_NONE) load8(x, n, q.z, q.y, q.x, cg, xU[u]);
+        } else if (p.act != GB_ACT_NONE) {
+          load8(p.y, n, q.z, q.y, q.x, cg, xU[u]);
         }
-        if (p.dy_sum.ptr != nullptr && (MODE == 0 || !norm)) store8f(p.dy_sum, n, q.z, q.y, q.x, cg, g);
       }
-      // activation derivative
-      if (norm) {
-        load8(x, n, q.z, q.y, q.x, cg, xv);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) xv[e] = (xv[e] - mean[e]) * rstd[e];  // xhat
-        if (p.act == GB_ACT_RELU || p.act == GB_ACT_LEAKY || p.act == GB_ACT_PRELU) {
+      for (int u = 0; u < U; ++u) {
+        if (!okU[u]) continue;
+        const Pix q = qU[u];
+        float (&g)[8] = gU[u];
+        float (&xv)[8] = xU[u];
+        if (!use_sum) {
+          if (has_b) {
+            add_mirrors(p.dy_b, n, q.z, q.y, q.x, cg, g);
+            if (has_a) {
+              float t[8];
+              load8f(p.dy_a, n, q.z, q.y, q.x, cg, t);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            if (!(xv[e] > 0.f)) {
-              if (MODE == 0 && p.act == GB_ACT_PRELU) sp[e] += g[e] * xv[e];
-              g[e] *= (p.act == GB_ACT_RELU) ? 0.f : slope[e];
+              for (int e = 0; e < 8; ++e) g[e] += t[e];
+            }
+          }
+          // residual added AFTER the activation: its gradient is the unmasked total
+          if (!rba && p.dy_sum.ptr != nullptr && (MODE == 0 || !norm)) {
+            if (p.dy_sum_acc) {
+              float t[8];
+              load8f(p.dy_sum, n, q.z, q.y, q.x, cg, t);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) t[e] += g[e];
+              store8f(p.dy_sum, n, q.z, q.y, q.x, cg, t);
+            } else {
+              store8f(p.dy_sum, n, q.z, q.y, q.x, cg, g);
             }
           }
         }
-      } else {
-        // activation only: derivative from the forward OUTPUT y
-        if (p.act != GB_ACT_NONE) {
-          load8(p.y, n, q.z, q.y, q.x, cg, xv);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            if (p.act == GB_ACT_TANH) g[e] *= (1.f - xv[e] * xv[e]);
-            else if (!(xv[e] > 0.f)) g[e] *= (p.act == GB_ACT_RELU) ? 0.f : slope[e];
+        for (int e = 0; e < 8; ++e) g[e] *= oscale;
+        float rr[8];
+        if (rba) load8(p.res, n, q.z, q.y, q.x, cg, rr);
+        // activation derivative
+        if (norm) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xv[e] = (xv[e] - mean[e]) * rstd[e];  // xhat
+          if (p.act == GB_ACT_RELU || p.act == GB_ACT_LEAKY || p.act == GB_ACT_PRELU) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float pre = rba ? xv[e] + rr[e] : xv[e];
+              if (!(pre > 0.f)) {
+                if (MODE == 0 && p.act == GB_ACT_PRELU) sp[e] += g[e] * pre;
+                g[e] *= (p.act == GB_ACT_RELU) ? 0.f : slope[e];
+              }
+            }
+          }
+        } else if (p.act != GB_ACT_NONE) {
+          if (p.y.ptr != nullptr) {
+            // activation only: derivative from the forward OUTPUT y (loaded into xv)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              if (p.act == GB_ACT_TANH) g[e] *= (1.f - xv[e] * xv[e]);
+              else if (!(xv[e] > 0.f)) g[e] *= (p.act == GB_ACT_RELU) ? 0.f : slope[e];
+            }
+          } else {
+            // derivative from the pre-activation x (+ res)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float pre = rba ? xv[e] + rr[e] : xv[e];
+              if (p.act == GB_ACT_TANH) {
+                const float th = tanhf(pre);
+                g[e] *= (1.f - th * th);
+              } else if (!(pre > 0.f)) {
+                if (want_dprelu1) sp[e] += g[e] * pre;
+                g[e] *= (p.act == GB_ACT_RELU) ? 0.f : slope[e];
+              }
+            }
           }
         }
-      }
-      if (MODE == 0) {
+        // residual added BEFORE the activation: its gradient is the masked g
+        if (rba && p.dy_sum.ptr != nullptr && (MODE == 1 || !norm)) {
+          if (p.dy_sum_acc) {
+            float t[8];
+            load8f(p.dy_sum, n, q.z, q.y, q.x, cg, t);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          s1[e] += g[e];
-          s2[e] += g[e] * xv[e];
+            for (int e = 0; e < 8; ++e) t[e] += g[e];
+            store8f(p.dy_sum, n, q.z, q.y, q.x, cg, t);
+          } else {
+            store8f(p.dy_sum, n, q.z, q.y, q.x, cg, g);
+          }
         }
-      } else {
-        float d[8];
+        if (MODE == 0) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) d[e] = norm ? rstd[e] * (g[e] - m1[e] - xv[e] * m2[e]) : g[e];
-        const uint4 packed = pack8(d);
-        store8(p.dx, n, q.z, q.y, q.x, cg, packed);
-        if (want_dbias) {  // sum what the wgrad / dgrad kernels will actually read (the bf16-rounded values)
-          float2 t;
-          t = unpack_bf16x2(packed.x); s1[0] += t.x; s1[1] += t.y;
-          t = unpack_bf16x2(packed.y); s1[2] += t.x; s1[3] += t.y;
-          t = unpack_bf16x2(packed.z); s1[4] += t.x; s1[5] += t.y;
-          t = unpack_bf16x2(packed.w); s1[6] += t.x; s1[7] += t.y;
+          for (int e = 0; e < 8; ++e) {
+            s1[e] += g[e];
+            s2[e] += g[e] * xv[e];
+          }
+        } else {
+          float d[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d[e] = norm ? rstd[e] * (g[e] - m1[e] - xv[e] * m2[e]) : g[e];
+          if (p.dx_fp32_acc) {
+            float t[8];
+            load8f(p.dx, n, q.z, q.y, q.x, cg, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t[e] += d[e];
+            store8f(p.dx, n, q.z, q.y, q.x, cg, t);
+            continue;
+          }
+          const uint4 packed = pack8(d);
+          store8(p.dx, n, q.z, q.y, q.x, cg, packed);
+          if (want_dbias) {  // sum what the wgrad / dgrad kernels will actually read (the bf16-rounded values)
+            float2 t;
+            t = unpack_bf16x2(packed.x); s1[0] += t.x; s1[1] += t.y;
+            t = unpack_bf16x2(packed.y); s1[2] += t.x; s1[3] += t.y;
+            t = unpack_bf16x2(packed.z); s1[4] += t.x; s1[5] += t.y;
+            t = unpack_bf16x2(packed.w); s1[6] += t.x; s1[7] += t.y;
+          }
         }
       }
     }
@@ -319,16 +424,16 @@ __global__ void in_bwd_kernel(const __grid_constant__ gb_in_bwd_params p, int pi
       if (p.dprelu != nullptr) atomicAdd(p.dprelu + c, d);
     }
   }
-  if (want_dbias) {
+  if (want_dbias || want_dprelu1) {
     if (slot < slots) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) red[slot * x.C + cg * 8 + e] = s1[e];
+      for (int e = 0; e < 8; ++e) red[slot * x.C + cg * 8 + e] = want_dbias ? s1[e] : sp[e];
     }
     __syncthreads();
     for (int c = threadIdx.x; c < x.C; c += blockDim.x) {
       float a = 0.f;
       for (int k = 0; k < slots; ++k) a += red[k * x.C + c];
-      atomicAdd(p.dbias + c, a);
+      atomicAdd((want_dbias ? p.dbias : p.dprelu) + c, a);
     }
   }
 }
@@ -344,10 +449,14 @@ Launch plan(const gb_view& x) {
   if (C8 > 256) L.threads = ((C8 + 31) / 32) * 32;
   L.slots = L.threads / C8;
   const int64_t P = (int64_t)x.D * x.H * x.W;
-  // ~4 waves of 148 SMs x 4 resident blocks, but at least `slots` pixels (one pass) per block
-  int64_t blocks = (148 * 16 + x.N - 1) / x.N;
+  // ONE resident wave: 148 SMs x 2 blocks (the kernels need ~128 registers). Each block streams its share of
+  // the pixels with several loads in flight; more, shorter blocks only add per-block prologue / reduction tails
+  // (measured: 3.5 waves of 10 us blocks = 38 us for a tensor that one wave streams in a quarter of that).
+  int64_t blocks = (148 * 2 + x.N - 1) / x.N;
+  if (blocks < 1) blocks = 1;
   int64_t ppb = (P + blocks - 1) / blocks;
-  if (ppb < 4 * L.slots) ppb = 4 * L.slots;
+  const int64_t quantum = 2 * L.slots;  // two pixels in flight per thread
+  ppb = (ppb + quantum - 1) / quantum * quantum;
   L.ppb = (int)ppb;
   L.grid = dim3((unsigned)((P + ppb - 1) / ppb), x.N);
   return L;
@@ -389,14 +498,15 @@ extern "C" int gb_in_bwd(const gb_in_bwd_params* p, void* stream) {
   GB_CHECK(p->dy_a.ptr == nullptr || same_extents(p->x, p->dy_a), "gb_in_bwd: dy_a extents differ");
   GB_CHECK(p->dy_b.ptr == nullptr || same_extents(p->x, p->dy_b), "gb_in_bwd: dy_b extents differ");
   GB_CHECK(p->stats == nullptr || p->bstats != nullptr, "gb_in_bwd: bstats workspace missing");
-  GB_CHECK(p->stats != nullptr || p->act == GB_ACT_NONE || p->y.ptr != nullptr, "gb_in_bwd: forward output missing");
+  GB_CHECK(!(p->dbias && p->dprelu && p->stats == nullptr), "gb_in_bwd: dbias and dprelu cannot both be reduced without a norm");
+  GB_CHECK(!p->res_before_act || p->res.ptr == nullptr || same_extents(p->x, p->res), "gb_in_bwd: residual extents differ");
   cudaStream_t st = (cudaStream_t)stream;
   Launch L = plan(p->x);
   if (p->stats != nullptr) {
     in_bwd_kernel<0><<<L.grid, L.threads, sizeof(float) * 3 * L.slots * p->x.C, st>>>(*p, L.ppb);
     GB_LAUNCH_CHECK();
   }
-  in_bwd_kernel<1><<<L.grid, L.threads, p->dbias ? sizeof(float) * L.slots * p->x.C : 0, st>>>(*p, L.ppb);
+  in_bwd_kernel<1><<<L.grid, L.threads, (p->dbias || p->dprelu) ? sizeof(float) * L.slots * p->x.C : 0, st>>>(*p, L.ppb);
   GB_LAUNCH_CHECK();
   return 0;
 }

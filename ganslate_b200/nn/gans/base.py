@@ -49,6 +49,7 @@ class BaseGAN(ABC):
         self.use_cuda_graph = bool(conf[conf.mode].get("cuda_graph", False)) if self.is_train else False
         self.graph_warmup_iters = int(conf[conf.mode].get("cuda_graph_warmup", 11)) if self.is_train else 0
         self._graphs, self._static, self._graph_calls = {}, {}, 0
+        self.grad_syncs = None  # {optimizer name: FlatGradSync} when graphs + data parallel
         self.graph_launches_per_step = 0
 
     def init_networks(self):
@@ -191,6 +192,16 @@ class BaseGAN(ABC):
     def parallelize_networks(self):
         """base.py:172-189: one DistributedDataParallel wrapper per network, broadcast_buffers=False; the
         bucketed NCCL all-reduce of the gradients overlaps with the rest of backward."""
+        if torch.distributed.is_initialized() and self.use_cuda_graph:
+            # graph-replayed steps: explicit flat-bucket all-reduce per optimizer group instead of DDP's hooks
+            # (utils/grad_sync.py); same semantics -- rank-0 parameters at start, gradients averaged over ranks
+            from ganslate_b200.utils.grad_sync import FlatGradSync
+            self.grad_syncs = {}
+            for opt_name, optim in self.optimizers.items():
+                params = [p for g in optim.param_groups for p in g['params']]
+                self.grad_syncs[opt_name] = FlatGradSync(params, self.device)
+                self.grad_syncs[opt_name].broadcast_parameters()
+            return
         for name in self.networks.keys():
             if torch.distributed.is_initialized():
                 self.networks[name] = DistributedDataParallel(self.networks[name], device_ids=[self.device],

@@ -1,1 +1,2 @@
 from .cyclegan import CycleGAN  # noqa: F401
+from .cut import CUT  # noqa: F401

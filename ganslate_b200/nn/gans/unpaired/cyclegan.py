@@ -58,17 +58,36 @@ class CycleGAN(BaseGAN):
     def optimize_parameters(self):
         """One iteration in the reference's order (cyclegan.py:92-124).  With `train.cuda_graph` the two halves
         (forward + G step, D steps) are captured once and replayed; the ImagePool stays host logic in between."""
+        sync = self.grad_syncs  # data parallel + graphs: explicit all-reduce between the graph segments
         if self.graph_mode('step'):
-            self.run_graphed('G', self._phase_G)
+            self.run_graphed('G', lambda: self._phase_G(step=sync is None))
+            if sync:
+                sync['G'].launch()  # NCCL on a side stream, overlaps with the discriminator graph
             fake_B = self.stage_input('pool_B', self.fake_B_pool.query(self.visuals['fake_B'].detach().clone()))
             fake_A = self.stage_input('pool_A', self.fake_A_pool.query(self.visuals['fake_A'].detach().clone()))
-            self.run_graphed('D', lambda: self._phase_D(fake_B, fake_A))
+            self.run_graphed('D', lambda: self._phase_D(fake_B, fake_A, step=sync is None))
+            if sync:
+                # same result as the reference order (G step before the D phase): the D phase reads neither the
+                # generators' weights nor anything produced after `forward()`
+                sync['D'].launch()
+                sync['G'].finish()
+                self.run_graphed('stepG', self.optimizers['G'].step)
+                sync['D'].finish()
+                self.run_graphed('stepD', self.optimizers['D'].step)
             return
         with self.eager_stream():
-            self._phase_G()
-            self._phase_D(None, None)
+            self._phase_G(step=sync is None)
+            if sync:
+                sync['G'].launch()
+            self._phase_D(None, None, step=sync is None)
+            if sync:
+                sync['D'].launch()
+                sync['G'].finish()
+                self.optimizers['G'].step()
+                sync['D'].finish()
+                self.optimizers['D'].step()
 
-    def _phase_G(self):
+    def _phase_G(self, step=True):
         discriminators = [self.networks['D_B'], self.networks['D_A']]
         self.forward()
         self.metrics.update(self.training_metrics.compute_metrics_G(self.visuals))
@@ -76,9 +95,10 @@ class CycleGAN(BaseGAN):
         self.set_requires_grad(discriminators, False)
         self.optimizers['G'].zero_grad(set_to_none=True)
         self.backward_G()
-        self.optimizers['G'].step()
+        if step:
+            self.optimizers['G'].step()
 
-    def _phase_D(self, fake_B, fake_A):
+    def _phase_D(self, fake_B, fake_A, step=True):
         discriminators = [self.networks['D_B'], self.networks['D_A']]
         self.set_requires_grad(discriminators, True)
         self.optimizers['D'].zero_grad(set_to_none=True)
@@ -86,7 +106,8 @@ class CycleGAN(BaseGAN):
         self.metrics.update(self.training_metrics.compute_metrics_D('D_B', self.pred_real, self.pred_fake))
         self.backward_D('D_A', fake_A)
         self.metrics.update(self.training_metrics.compute_metrics_D('D_A', self.pred_real, self.pred_fake))
-        self.optimizers['D'].step()
+        if step:
+            self.optimizers['D'].step()
 
     def forward(self):
         real_A, real_B = self.visuals['real_A'], self.visuals['real_B']

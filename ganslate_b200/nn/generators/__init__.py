@@ -1,1 +1,2 @@
 from .resnet.resnet2d import Resnet2D  # noqa: F401
+from .vnet.vnet3d import Vnet3D  # noqa: F401

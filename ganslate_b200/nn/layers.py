@@ -18,7 +18,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from .._cabi import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH
+from .._cabi import ACT_LEAKY, ACT_NONE, ACT_PRELU, ACT_RELU, ACT_TANH
 
 
 def _t3(v):
@@ -103,20 +103,90 @@ class Tanh(_Marker, nn.Tanh):
     pass
 
 
+class PReLU(_Marker, nn.PReLU):
+    """Per-channel learnable slopes (V-Net, ganslate/nn/generators/vnet/vnet3d.py:160,196,231,251)."""
+
+
+class Storage:
+    """One channels-last bf16 allocation (N, D, H+2*pad, W+2*pad, C) plus, during backward, its gradient.
+
+    raw=True marks a bare convolution output: its gradient is the bf16 MMA operand of dgrad / wgrad and is produced
+    in one piece by the consumer's backward.  Every other buffer is an activation: its gradient is an FP32 tensor of
+    the same shape into which every consumer ACCUMULATES (convolution dgrad epilogues, residual branches, channel
+    slices of concatenations), so arbitrary fan-out / channel splits need no extra add kernels."""
+    __slots__ = ("t", "pad", "raw", "grad", "consumers")
+
+    def __init__(self, t, pad, raw=False):
+        self.t, self.pad, self.raw = t, pad, raw
+        self.grad = None
+        self.consumers = 0  # how many tape steps read this storage (decides zero-init vs overwrite in backward)
+
+
 class Buf:
-    """A channels-last bf16 buffer travelling through a network.
+    """Channel slice [c0, c0 + cw) of a Storage; `channels` logical channels (cw = channels rounded up to 8)."""
+    __slots__ = ("st", "c0", "cw", "channels", "is_3d", "needs_grad_flag", "want_dbias", "dbias")
 
-    t: tensor (N, D, H+2*pad, W+2*pad, Cpad); pad: materialised reflection border; channels: logical channels;
-    raw: True if t is a bare convolution output (its gradient is the bf16 MMA operand of dgrad/wgrad),
-    False for an activation buffer (fp32 gradient)."""
-    __slots__ = ("t", "pad", "channels", "is_3d", "raw", "grad", "needs_grad_flag", "want_dbias", "dbias")
-
-    def __init__(self, t, pad, channels, is_3d, raw=False):
-        self.t, self.pad, self.channels, self.is_3d, self.raw = t, pad, channels, is_3d, raw
-        self.grad = None  # filled during Tape.backward
+    def __init__(self, t, pad, channels, is_3d, raw=False, st=None, c0=0, cw=None):
+        self.st = st if st is not None else Storage(t, pad, raw)
+        self.c0 = c0
+        self.cw = cw if cw is not None else self.st.t.shape[-1]
+        self.channels, self.is_3d = channels, is_3d
         self.needs_grad_flag = True  # False only for a network input that does not require grad
         self.want_dbias = False      # the producing conv's bias needs a gradient (fused into the consumer's backward)
         self.dbias = None
+
+    # -- forward-side accessors
+    @property
+    def t(self):
+        return self.st.t
+
+    @property
+    def pad(self):
+        return self.st.pad
+
+    @property
+    def raw(self):
+        return self.st.raw
+
+    @property
+    def full(self):
+        return self.c0 == 0 and self.cw == self.st.t.shape[-1]
+
+    def slice(self, c0, channels):
+        """Sub-slice (channel offsets relative to this Buf)."""
+        return Buf(None, None, channels, self.is_3d, st=self.st, c0=self.c0 + c0, cw=ops.pad8(channels))
+
+    def view(self):
+        """Interior view of the slice."""
+        return ops.make_view(self.st.t, self.st.pad, self.c0, self.cw)
+
+    def plain_view(self):
+        """The slice of the WHOLE allocation (border included) as a plain tensor -- what a convolution reads."""
+        return ops.make_view(self.st.t, 0, self.c0, self.cw)
+
+    # -- backward-side accessors
+    def has_grad(self):
+        return self.st.grad is not None
+
+    def grad_tensor(self):
+        """FP32 gradient of the whole storage, zero-initialised on first use (consumers accumulate)."""
+        if self.st.grad is None:
+            self.st.grad = ops.zeros(self.st.t.shape, self.st.t.device)
+        return self.st.grad
+
+    def grad_view(self):
+        return ops.make_view(self.grad_tensor(), self.st.pad, self.c0, self.cw)
+
+    def grad_plain_view(self):
+        return ops.make_view(self.grad_tensor(), 0, self.c0, self.cw)
+
+    @property
+    def grad(self):  # used by NetworkFn for the input / seeded gradients
+        return self.st.grad
+
+    @grad.setter
+    def grad(self, g):
+        self.st.grad = g
 
 
 class Tape:
@@ -179,65 +249,110 @@ def flatten_modules(mods) -> List[nn.Module]:
 
 # ------------------------------------------------------------------------------------------------ fused steps
 def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0) -> Buf:
-    """conv (+bias, + optional epilogue activation).  Output: raw Buf (act NONE) or activation Buf."""
+    """conv (+bias, + optional epilogue activation) reading the whole (bordered) allocation of `b`'s channel slice.
+    Output: raw Buf (act NONE) or activation Buf."""
     op = m.conv_op()
-    x = b.t
-    y = ops.conv_forward(op, x, m.weight, m.bias, act, slope)
+    dev = b.t.device
+    ops._require_cuda(b.t, "convolution input")
+    y = op.run_fwd(b.plain_view(), dev, m.weight, m.bias, act, slope)
     out = Buf(y, 0, m.out_channels, b.is_3d, raw=(act == ACT_NONE))
     weight, bias = m.weight, m.bias
     out.want_dbias = tape is not None and tape.needs(bias)
+    b.st.consumers += 1
 
     def bwd():
-        g = out.grad
+        g = out.st.grad
         if g is None:
             return
-        out.grad = None
+        out.st.grad = None
         db = out.dbias
         out.dbias = None
         if act != ACT_NONE:
             if tape.needs(bias):
-                db = ops.zeros((y.shape[-1],), y.device)
-            g = ops.act_backward(g, y, act, slope, dbias=db)  # fp32 d_buf -> bf16 d_raw (+ bias gradient)
+                db = ops.zeros((y.shape[-1],), dev)
+            g = ops.act_backward(ops.make_view(g), y, act, slope, dbias=db)  # fp32 d_buf -> bf16 d_raw (+ bias grad)
+        gv = ops.make_view(g)
         if tape.needs(weight):
-            tape.add_param_grad(weight, op.run_wgrad(x, g, weight.shape))
+            tape.add_param_grad(weight, op.run_wgrad(b.plain_view(), gv, weight.shape, dev))
         if tape.needs(bias):
             tape.add_param_grad(bias, db[:op.cout] if db is not None else ops.colsum(g, op.cout))
-        if b.grad is not None or b.needs_grad_flag:
-            b.grad = op.run_dgrad(g, weight, x.shape, into=b.grad)
+        if b.needs_grad_flag:
+            if not b.has_grad() and b.st.consumers == 1 and b.full:
+                b.st.grad = torch.empty(b.st.t.shape, dtype=torch.float32, device=dev)  # sole consumer: overwrite
+                op.run_dgrad(gv, weight, b.grad_plain_view(), accumulate=False)
+            else:
+                op.run_dgrad(gv, weight, b.grad_plain_view(), accumulate=True)
 
     if tape is not None:
         tape.steps.append(bwd)
     return out
 
 
-def step_norm_act(tape: Tape, raw: Buf, norm: bool, act: int, slope: float, out_pad: int, eps: float,
-                  residual: Optional[Buf] = None) -> Buf:
-    """[instance-norm] + activation [+ residual] + reflection border of the result."""
-    if not raw.raw and not (norm is False and act == ACT_NONE):
+def step_norm_act(tape: Tape, x: Buf, norm: bool, act: int, slope: float, out_pad: int, eps: float,
+                  residual: Optional[Buf] = None, prelu=None, res_before_act=False, out_scale=1.0,
+                  out: Optional[Buf] = None) -> Buf:
+    """[instance-norm] + activation [+ residual] + reflection border of the result.
+
+    x: raw convolution output, or (norm=False) any activation Buf; out: optional existing Buf (channel slice of a
+    concatenation buffer) to write into instead of a fresh allocation; prelu: nn.PReLU module for learnable slopes."""
+    dev = x.t.device
+    ops._require_cuda(x.t, "normalisation input")
+    if norm and not x.raw:
         raise NotImplementedError("normalisation of a non-convolution output")
-    if not raw.raw:
-        raise NotImplementedError("explicit border copy of an activation buffer (no reference network needs it)")
-    t, stats = ops.norm_act_forward(raw.t, residual.t if residual is not None else None,
-                                    residual.pad if residual is not None else 0, norm, act, slope, out_pad, eps)
-    out = Buf(t, out_pad, raw.channels, raw.is_3d)
-    x = raw.t
+    if out is None:
+        N, D, H, W, _ = x.t.shape
+        H, W = H - 2 * x.pad, W - 2 * x.pad
+        t = torch.empty((N, D, H + 2 * out_pad, W + 2 * out_pad, x.cw), dtype=torch.bfloat16, device=dev)
+        out = Buf(t, out_pad, x.channels, x.is_3d)
+    elif out.pad != out_pad:
+        raise RuntimeError("destination buffer has a different reflection border")
+    slopes = prelu.weight if prelu is not None else None
+    if slopes is not None and slopes.numel() != x.cw:
+        if slopes.numel() != x.channels:
+            raise NotImplementedError("PReLU with a single shared slope")
+        slopes_p = torch.zeros(x.cw, dtype=torch.float32, device=dev)
+        slopes_p[:x.channels] = slopes.detach()
+    else:
+        slopes_p = slopes.detach() if slopes is not None else None
+    stats = ops.norm_act_forward(x.view(), out.view(), residual.view() if residual is not None else None, norm, act,
+                                 slope, eps, dev, prelu=slopes_p, res_before_act=res_before_act, out_scale=out_scale)
+    x.st.consumers += 1
+    if residual is not None:
+        residual.st.consumers += 1
 
     def bwd():
-        g = out.grad
-        if g is None:
+        if not out.has_grad():
             return
-        out.grad = None
-        dres = None
+        gview = out.grad_view()
+        need_dx = x.needs_grad_flag
+        dresv = None
         if residual is not None and residual.needs_grad_flag:
-            if residual.grad is not None:
-                raise NotImplementedError("residual gradient buffer already exists (unsupported topology)")
-            dres = ops.zeros(residual.t.shape, x.device)
-            residual.grad = dres
-        if raw.want_dbias and raw.needs_grad_flag:
-            raw.dbias = ops.zeros((x.shape[-1],), x.device)
-        raw.grad = ops.norm_act_backward(x, stats, t, g, norm, act, slope, out_pad, eps, dres32=dres,
-                                         res_pad=residual.pad if residual is not None else 0,
-                                         need_draw=raw.needs_grad_flag, dbias=raw.dbias)
+            dresv = residual.grad_view()  # zero-initialised, shared with the residual's other consumers
+        dprelu = ops.zeros((x.cw,), dev) if (slopes is not None and tape.needs(slopes)) else None
+        if x.raw:
+            if x.want_dbias and need_dx:
+                x.dbias = ops.zeros((x.cw,), dev)
+            seeded = x.st.grad  # gradient that arrived through a feature tap on the raw convolution output
+            draw = torch.empty_like(x.t)
+            ops.norm_act_backward(x.view(), stats, gview, ops.make_view(draw), norm, act, slope, eps, dev,
+                                  yv=out.view() if (not norm and act != ACT_NONE) else None,
+                                  resv=residual.view() if (residual is not None and res_before_act) else None,
+                                  dresv=dresv, prelu=slopes_p, dprelu=dprelu, dbias=x.dbias,
+                                  res_before_act=res_before_act, dres_acc=True, out_scale=out_scale, need_dx=need_dx)
+            if need_dx:
+                if seeded is not None:
+                    draw = draw + seeded
+                    if x.dbias is not None:
+                        x.dbias = x.dbias + seeded.float().sum(dim=(0, 1, 2, 3))
+                x.st.grad = draw
+        else:
+            # activation input (copy / add / activation of existing buffers): fp32 gradient, accumulated
+            ops.norm_act_backward(x.view(), None, gview, x.grad_view(), False, act, slope, eps, dev,
+                                  resv=residual.view() if (residual is not None and res_before_act) else None,
+                                  dresv=dresv, prelu=slopes_p, dprelu=dprelu, res_before_act=res_before_act,
+                                  dres_acc=True, dx_fp32_acc=True, out_scale=out_scale, need_dx=need_dx)
+        if dprelu is not None:
+            tape.add_param_grad(slopes, dprelu[:slopes.numel()].reshape(slopes.shape))
 
     if tape is not None:
         tape.steps.append(bwd)
@@ -245,13 +360,17 @@ def step_norm_act(tape: Tape, raw: Buf, norm: bool, act: int, slope: float, out_
 
 
 def run_sequence(tape: Tape, mods: Sequence[nn.Module], b: Buf, final_pad: int = 0,
-                 residual: Optional[Buf] = None) -> Buf:
+                 residual: Optional[Buf] = None, taps=None, sink=None) -> Buf:
     """Execute a list of layers on buffer `b`, fusing pad/conv/norm/activation groups.
 
     final_pad: reflection border wanted on the last produced buffer (what follows this sequence).
     residual:  added to the output of the LAST norm group (ResidualBlock: x + conv_block(x)).
     """
-    mods = flatten_modules(mods)
+    if taps is None:
+        mods = flatten_modules(mods)
+        taps = ()
+    # taps: module indices whose output is recorded into `sink` as (index, Buf, whole_buffer) -- CUT's feature
+    # extraction over `network.encoder` (ganslate/nn/gans/unpaired/cut.py:297-312)
     i, n = 0, len(mods)
     pending_pad = 0  # border announced by a ReflectionPad module for the next convolution
     while i < n:
@@ -262,6 +381,8 @@ def run_sequence(tape: Tape, mods: Sequence[nn.Module], b: Buf, final_pad: int =
                     raise RuntimeError("buffer already carries a different reflection border")
                 # the producer did not materialise the border: copy-with-border pass
                 b = step_norm_act(tape, b, False, ACT_NONE, 0.0, m.pad_amount, 1e-5)
+            if i in taps:
+                sink.append((i, b, True))  # the padded tensor itself is the feature
             i += 1
             pending_pad = m.pad_amount
             if i >= n or not isinstance(mods[i], _ConvMixin):
@@ -284,16 +405,30 @@ def run_sequence(tape: Tape, mods: Sequence[nn.Module], b: Buf, final_pad: int =
             act_id, slope = act if act is not None else (ACT_NONE, 0.0)
             nxt = first_pad(mods[j:]) if j < n else final_pad  # border wanted by the consumer of this group
             res = residual if (j >= n and residual is not None) else None
-            if norm or res is not None or nxt > 0:
+            tap_raw = i in taps and (norm or act is not None)
+            if norm or res is not None or nxt > 0 or tap_raw:
                 raw = step_conv(tape, b, m)
+                if i in taps:
+                    sink.append((i, raw, False))
                 b = step_norm_act(tape, raw, norm, act_id, slope, nxt, mods[i + 1].eps if norm else 1e-5, res)
             else:
                 b = step_conv(tape, b, m, act_id, slope)  # bias + activation in the convolution epilogue
+                if i in taps:
+                    sink.append((i, b, False))
+            for idx in range(i + 1, j):
+                if idx in taps:
+                    # a tap on the norm layer sees the in-place activation that follows it (reference quirk,
+                    # SURVEY.md appendix A.6); a tap on the activation sees the same tensor
+                    if _is_norm(mods[idx]) and act is not None and not getattr(mods[idx + 1], "inplace", False):
+                        raise NotImplementedError("feature tap on a norm layer followed by a non-inplace activation")
+                    sink.append((idx, b, False))
             i = j
             continue
         if hasattr(m, "gb_run"):
             nxt = first_pad(mods[i + 1:]) if i + 1 < n else final_pad
             b = m.gb_run(tape, b, nxt)
+            if i in taps:
+                sink.append((i, b, False))
             i += 1
             continue
         if isinstance(m, nn.Identity):
@@ -333,17 +468,87 @@ class NetworkFn(torch.autograd.Function):
         tape, b0, b = ctx.tape, ctx.b0, ctx.b_last
         tape.param_grads = {}
         ops.arena_begin(("bwd",) + ctx.arena_key, dy.device)
-        b.grad = ops.from_channels_last_backward(dy, b.t.shape, b.channels, pre=b.t if ctx.act == ACT_TANH else None,
-                                                 fp32=not b.raw)
+        b.st.grad = ops.from_channels_last_backward(dy, b.t.shape, b.channels,
+                                                    pre=b.t if ctx.act == ACT_TANH else None, fp32=not b.raw)
         tape.backward()
         dx = None
-        if ctx.needs_input_grad[1] and b0.grad is not None:
-            dx = ops.to_channels_last_backward(b0.grad, b0.pad, ctx.in_shape)
-        b0.grad = None
+        if ctx.needs_input_grad[1] and b0.st.grad is not None:
+            dx = ops.to_channels_last_backward(b0.st.grad, b0.pad, ctx.in_shape)
+        b0.st.grad = None
         ops.arena_end(("bwd",) + ctx.arena_key)
         grads = [tape.param_grads.get(id(p)) for p in ctx.params]
         tape.param_grads = {}
         return (None, dx, *grads)
+
+
+class RunnerFn(torch.autograd.Function):
+    """Like NetworkFn, but the network topology is an arbitrary callable `runner(tape, b0) -> (Buf, export_act)`
+    built from the step_* primitives (V-Net: channel splits, concatenations, additive couplings)."""
+
+    @staticmethod
+    def forward(ctx, runner, key, x, *params):
+        needs = {id(p): ctx.needs_input_grad[3 + k] for k, p in enumerate(params)}
+        record = any(ctx.needs_input_grad[2:])
+        tape = Tape(needs, ctx.needs_input_grad[2]) if record else None
+        ctx.arena_key = (key, tuple(x.shape), tuple(ctx.needs_input_grad))
+        ops.arena_begin(("run_fwd",) + ctx.arena_key, x.device)
+        b0 = Buf(ops.to_channels_last(x, 0), 0, x.shape[1], x.dim() == 5)
+        b0.needs_grad_flag = bool(ctx.needs_input_grad[2])
+        b, act = runner(tape, b0)
+        if b.pad != 0 or not b.full:
+            raise RuntimeError("cannot export a bordered / sliced buffer")
+        y = ops.from_channels_last(b.t, b.channels, b.is_3d, act)
+        ops.arena_end(("run_fwd",) + ctx.arena_key)
+        ctx.tape, ctx.params, ctx.b0, ctx.b_last, ctx.act = tape, params, b0, b, act
+        ctx.in_shape = tuple(x.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        tape, b0, b = ctx.tape, ctx.b0, ctx.b_last
+        tape.param_grads = {}
+        ops.arena_begin(("run_bwd",) + ctx.arena_key, dy.device)
+        b.st.grad = ops.from_channels_last_backward(dy, b.t.shape, b.channels,
+                                                    pre=b.t if ctx.act == ACT_TANH else None, fp32=not b.raw)
+        tape.backward()
+        dx = None
+        if ctx.needs_input_grad[2] and b0.st.grad is not None:
+            dx = ops.to_channels_last_backward(b0.st.grad, b0.pad, ctx.in_shape)
+        b0.st.grad = None
+        ops.arena_end(("run_bwd",) + ctx.arena_key)
+        grads = [tape.param_grads.get(id(p)) for p in ctx.params]
+        tape.param_grads = {}
+        return (None, None, dx, *grads)
+
+
+def step_channel_repeat(tape: Tape, b: Buf, n_repeats: int) -> Buf:
+    """x.repeat(1, n, 1, 1, 1) on the channel axis (V-Net InputBlock residual, vnet3d.py:164-166). The tensors are
+    the network INPUT (1-4 channels), so plain ATen indexing is used; backward sums the repeats."""
+    c = b.channels
+    out_c = c * n_repeats
+    src = b.t[..., b.c0:b.c0 + c]
+    t = torch.zeros(b.t.shape[:-1] + (ops.pad8(out_c),), dtype=torch.bfloat16, device=b.t.device)
+    t[..., :out_c] = src.repeat(1, 1, 1, 1, n_repeats)
+    out = Buf(t, 0, out_c, b.is_3d)
+    b.st.consumers += 1
+
+    def bwd():
+        if not out.has_grad() or not b.needs_grad_flag:
+            return
+        g = out.st.grad[..., :out_c]
+        g = g.reshape(g.shape[:-1] + (n_repeats, c)).sum(dim=-2)
+        b.grad_tensor()[..., b.c0:b.c0 + c] += g
+
+    if tape is not None:
+        tape.steps.append(bwd)
+    return out
+
+
+def new_like(b: Buf, channels: int) -> Buf:
+    """Fresh activation buffer with the spatial shape of `b` and `channels` channels (concatenation target)."""
+    N, D, Hb, Wb, _ = b.t.shape
+    t = torch.empty((N, D, Hb, Wb, ops.pad8(channels)), dtype=torch.bfloat16, device=b.t.device)
+    return Buf(t, b.pad, channels, b.is_3d)
 
 
 def run_network(net: nn.Module, mods: Sequence[nn.Module], x: torch.Tensor) -> torch.Tensor:
@@ -351,3 +556,61 @@ def run_network(net: nn.Module, mods: Sequence[nn.Module], x: torch.Tensor) -> t
     while the result is exported)."""
     params = [p for p in net.parameters()]
     return NetworkFn.apply(flatten_modules(mods), x, *params)
+
+
+class EncoderFn(torch.autograd.Function):
+    """Runs the first layers of a network and returns the features recorded at the module indices `taps`
+    (NC(D)HW fp32), with gradients flowing back into the network through every tap."""
+
+    @staticmethod
+    def forward(ctx, mods, taps, x, *params):
+        needs = {id(p): ctx.needs_input_grad[3 + k] for k, p in enumerate(params)}
+        record = any(ctx.needs_input_grad[2:])
+        tape = Tape(needs, ctx.needs_input_grad[2]) if record else None
+        taps = tuple(sorted(taps))
+        mods = list(mods)[:taps[-1] + 1]
+        if any(isinstance(m, nn.Sequential) for m in mods):
+            raise NotImplementedError("feature taps need a flat encoder list")
+        pad = first_pad(mods)
+        ctx.arena_key = (id(mods[0]), tuple(x.shape), tuple(ctx.needs_input_grad), taps)
+        ops.arena_begin(("enc_fwd",) + ctx.arena_key, x.device)
+        b0 = Buf(ops.to_channels_last(x, pad), pad, x.shape[1], x.dim() == 5)
+        b0.needs_grad_flag = bool(ctx.needs_input_grad[2])
+        sink = []
+        run_sequence(tape, mods, b0, taps=set(taps), sink=sink)
+        outs = []
+        for idx, b, whole in sink:
+            outs.append(ops.from_channels_last(b.t, b.channels, b.is_3d, ACT_NONE, 0 if whole else b.pad))
+        ops.arena_end(("enc_fwd",) + ctx.arena_key)
+        if len(outs) != len(taps):
+            raise RuntimeError(f"feature taps {taps} produced {len(outs)} features")
+        ctx.tape, ctx.params, ctx.b0, ctx.sink = tape, params, b0, sink
+        ctx.in_shape = tuple(x.shape)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        tape, b0 = ctx.tape, ctx.b0
+        tape.param_grads = {}
+        ops.arena_begin(("enc_bwd",) + ctx.arena_key, douts[0].device if douts[0] is not None else b0.t.device)
+        for (idx, b, whole), dy in zip(ctx.sink, douts):
+            if dy is None:
+                continue
+            g = ops.from_channels_last_backward(dy, b.t.shape, b.channels, fp32=not b.raw, pad=0 if whole else b.pad)
+            b.st.grad = g if b.st.grad is None else b.st.grad + g
+        tape.backward()
+        dx = None
+        if ctx.needs_input_grad[2] and b0.st.grad is not None:
+            dx = ops.to_channels_last_backward(b0.st.grad, b0.pad, ctx.in_shape)
+        b0.st.grad = None
+        ops.arena_end(("enc_bwd",) + ctx.arena_key)
+        grads = [tape.param_grads.get(id(p)) for p in ctx.params]
+        tape.param_grads = {}
+        return (None, None, dx, *grads)
+
+
+def run_encoder(net: nn.Module, mods: Sequence[nn.Module], x: torch.Tensor, taps) -> list:
+    """Features of `x` after the modules `taps` of the list `mods` (same semantics as iterating the layers and
+    recording `feat` after index i, including the in-place activation effect)."""
+    params = [p for p in net.parameters()]
+    return list(EncoderFn.apply(list(mods), tuple(taps), x, *params))

@@ -95,15 +95,18 @@ def pad8(c: int) -> int:
     return (c + 7) // 8 * 8
 
 
-def make_view(t: torch.Tensor, pad: int = 0) -> View:
-    """View of the interior of a contiguous (N, D, Hb, Wb, C) bf16 buffer with reflection border `pad`."""
+def make_view(t: torch.Tensor, pad: int = 0, c0: int = 0, cw: int = None) -> View:
+    """View of the interior of a contiguous (N, D, Hb, Wb, C) buffer with reflection border `pad`, optionally
+    restricted to the channel slice [c0, c0 + cw) (c0 and cw multiples of 8: 16-byte vectors)."""
     assert t.dim() == 5 and t.is_contiguous(), (t.shape, t.stride())
     N, D, Hb, Wb, Cc = t.shape
+    cw = Cc - c0 if cw is None else cw
+    assert c0 % 8 == 0 and cw % 8 == 0 and c0 + cw <= Cc, (c0, cw, Cc)
     v = View()
     esz = t.element_size()
-    v.ptr = t.data_ptr() + ((pad * Wb + pad) * Cc) * esz
+    v.ptr = t.data_ptr() + ((pad * Wb + pad) * Cc + c0) * esz
     v.sn, v.sz, v.sy, v.sx = D * Hb * Wb * Cc, Hb * Wb * Cc, Wb * Cc, Cc
-    v.N, v.D, v.H, v.W, v.C, v.pad = N, D, Hb - 2 * pad, Wb - 2 * pad, Cc, pad
+    v.N, v.D, v.H, v.W, v.C, v.pad = N, D, Hb - 2 * pad, Wb - 2 * pad, cw, pad
     return v
 
 
@@ -269,43 +272,42 @@ class ConvOp:
             cache[which] = p
         return cache[which]
 
-    def run_fwd(self, x, weight, bias, act=ACT_NONE, slope=0.0):
-        """x: plain buffer (N,D,H,W,cin_pad) -> (N,D,Ho,Wo,cout_pad)."""
-        N, D, H, W, Cc = x.shape
-        assert Cc == self.cin_pad, (Cc, self.cin_pad)
-        od, oh, ow = self.out_extent((D, H, W))
-        y = torch.empty((N, od, oh, ow, self.cout_pad), dtype=torch.bfloat16, device=x.device)
+    def run_fwd(self, xv: View, device, weight, bias, act=ACT_NONE, slope=0.0):
+        """xv: plain view (N,D,H,W,cin_pad) of the input (any border is part of it) -> new (N,D,Ho,Wo,cout_pad)."""
+        assert xv.C == self.cin_pad and xv.pad == 0, (xv.C, self.cin_pad, xv.pad)
+        od, oh, ow = self.out_extent((xv.D, xv.H, xv.W))
+        y = torch.empty((xv.N, od, oh, ow, self.cout_pad), dtype=torch.bfloat16, device=device)
         p = self._params("fwd")
-        p.inp, p.out = make_view(x), make_view(y)
+        p.inp, p.out = xv, make_view(y)
         wp = self.packed(weight, "fwd")
         p.wpacked = wp.data_ptr()
         p.bias = bias.data_ptr() if bias is not None else None
         p.ncols, p.npad = self.cout, self.fwd_rows_pad
         p.act, p.act_slope = act, slope
-        _call("conv_fwd", self.flops((D, H, W), N), "flop", "gb_conv_data(fwd)", _cabi.lib().gb_conv_data, C.byref(p),
-              _stream())
+        p.out_fp32, p.accumulate = 0, 0
+        _call("conv_fwd", self.flops((xv.D, xv.H, xv.W), xv.N), "flop", "gb_conv_data(fwd)", _cabi.lib().gb_conv_data,
+              C.byref(p), _stream())
         return y
 
-    def run_dgrad(self, dy, weight, in_shape, into=None):
-        """dy: bf16 (N,D,Ho,Wo,cout_pad) -> FP32 gradient wrt the input buffer (shape in_shape).
-        `into`: an existing fp32 gradient buffer to accumulate into (residual branches)."""
-        dx = into if into is not None else torch.empty(in_shape, dtype=torch.float32, device=dy.device)
+    def run_dgrad(self, dyv: View, weight, outv: View, accumulate: bool):
+        """dyv: bf16 view (N,D,Ho,Wo,cout_pad); the gradient wrt the input is written / accumulated into the FP32
+        view outv (plain view of the input buffer's gradient, channel slice allowed)."""
+        assert dyv.C == self.cout_pad and outv.C == self.cin_pad and outv.pad == 0
         p = self._params("dgrad")
-        p.out_fp32, p.accumulate = 1, 1 if into is not None else 0
-        p.inp, p.out = make_view(dy), make_view(dx)
+        p.out_fp32, p.accumulate = 1, 1 if accumulate else 0
+        p.inp, p.out = dyv, outv
         wp = self.packed(weight, "dgrad")
         p.wpacked = wp.data_ptr()
         p.bias = None
         p.ncols, p.npad = self.cin, self.dgrad_rows_pad
         p.act, p.act_slope = ACT_NONE, 0.0
-        _call("conv_dgrad", self.flops(tuple(in_shape[1:4]), in_shape[0]), "flop", "gb_conv_data(dgrad)",
+        _call("conv_dgrad", self.flops((outv.D, outv.H, outv.W), outv.N), "flop", "gb_conv_data(dgrad)",
               _cabi.lib().gb_conv_data, C.byref(p), _stream())
-        return dx
 
-    def run_wgrad(self, x, dy, weight_shape):
-        """fp32 weight gradient in the PyTorch layout of `weight_shape`."""
-        plain, gathered = (x, dy) if self.transposed else (dy, x)
-        ws = zeros((self.wg_rows_pad, self.wg_kpad), x.device)
+    def run_wgrad(self, xv: View, dyv: View, weight_shape, device):
+        """fp32 weight gradient in the PyTorch layout of `weight_shape` (xv: plain input view, dyv: bf16 d_raw)."""
+        plain, gathered = (xv, dyv) if self.transposed else (dyv, xv)
+        ws = zeros((self.wg_rows_pad, self.wg_kpad), device)
         cache = self.__dict__.setdefault("_ptemplates", {})
         p = cache.get("wgrad")
         if p is None:
@@ -317,10 +319,10 @@ class ConvOp:
                 p.mul[d] = self.stride[d]
             p.rows, p.kpad, p.splits = self.wg_rows, self.wg_kpad, 0
             cache["wgrad"] = p
-        p.plain, p.gathered, p.dw = make_view(plain), make_view(gathered), ws.data_ptr()
-        _call("conv_wgrad", self.flops(tuple(x.shape[1:4]), x.shape[0]), "flop", "gb_conv_wgrad",
+        p.plain, p.gathered, p.dw = plain, gathered, ws.data_ptr()
+        _call("conv_wgrad", self.flops((xv.D, xv.H, xv.W), xv.N), "flop", "gb_conv_wgrad",
               _cabi.lib().gb_conv_wgrad, C.byref(p), _stream())
-        dw = torch.empty(weight_shape, dtype=torch.float32, device=x.device)
+        dw = torch.empty(weight_shape, dtype=torch.float32, device=device)
         cols = self.cout if self.transposed else self.cin
         cols_pad = self.cout_pad if self.transposed else self.cin_pad
         _cabi.check(_cabi.lib().gb_unpack_wgrad(ws.data_ptr(), dw.data_ptr(), cols * self.T, self.T, 1, self.wg_rows, cols,
@@ -340,73 +342,69 @@ def colsum(t: torch.Tensor, n: int) -> torch.Tensor:
 # is bf16 (it is an MMA operand of dgrad / wgrad); the gradient wrt an ACTIVATION buffer is fp32, because
 # InstanceNorm-backward subtracts its mean and bf16 rounding there costs 10-30 % error on real GAN gradients.
 # ------------------------------------------------------------------------------------------------------------
-def conv_forward(op: ConvOp, x, weight, bias, act=ACT_NONE, slope=0.0):
-    _require_cuda(x, "convolution input")
-    return op.run_fwd(x, weight, bias, act, slope)
-
-
-def act_backward(dy32: torch.Tensor, y: torch.Tensor, act: int, slope: float, dbias=None) -> torch.Tensor:
-    """bf16 d_raw = dy * act'(.) from the forward output y (epilogue activations), dy fp32.
+def act_backward(dyv: View, y: torch.Tensor, act: int, slope: float, dbias=None) -> torch.Tensor:
+    """bf16 d_raw = dy * act'(.) from the forward output y (epilogue activations); dyv: fp32 gradient view.
     dbias: optional zeroed fp32 [C] that receives the per-channel sum of d_raw (bias gradient)."""
     dx = torch.empty_like(y)
     p = InBwdParams()
-    p.x, p.y, p.dy_a, p.dx = make_view(y), make_view(y), make_view(dy32), make_view(dx)
+    p.x, p.y, p.dy_a, p.dx = make_view(y), make_view(y), dyv, make_view(dx)
     p.act, p.act_slope, p.eps = act, slope, 1e-5
     p.dbias = dbias.data_ptr() if dbias is not None else None
     _cabi.check(_cabi.lib().gb_in_bwd(C.byref(p), _stream()), "gb_in_bwd(act)")
     return dx
 
 
-def norm_act_forward(raw, residual, res_pad, norm, act, slope, out_pad, eps):
-    """-> (buffer with reflection border out_pad, stats or None)"""
-    _require_cuda(raw, "normalisation input")
-    N, D, H, W, Cc = raw.shape
+def norm_act_forward(xv: View, yv: View, resv, norm, act, slope, eps, device, prelu=None, res_before_act=False,
+                     out_scale=1.0):
+    """yv <- [out_scale *] act(instance_norm(xv) [+ res]) [+ res] incl. the reflection border of yv. Returns stats."""
     lib = _cabi.lib()
     stats = None
-    xv = make_view(raw)
+    nbytes = xv.N * xv.D * xv.H * xv.W * xv.C * 2
     if norm:
-        stats = zeros((N, Cc, 2), raw.device)
-        _call("in_stats", raw.numel() * 2, "byte", "gb_in_stats", lib.gb_in_stats, C.byref(xv), stats.data_ptr(), _stream())
-    out = torch.empty((N, D, H + 2 * out_pad, W + 2 * out_pad, Cc), dtype=torch.bfloat16, device=raw.device)
+        stats = zeros((xv.N, xv.C, 2), device)
+        _call("in_stats", nbytes, "byte", "gb_in_stats", lib.gb_in_stats, C.byref(xv), stats.data_ptr(), _stream())
     p = InFwdParams()
-    p.x, p.y = xv, make_view(out, out_pad)
-    if residual is not None:
-        p.res = make_view(residual, res_pad)
+    p.x, p.y = xv, yv
+    if resv is not None:
+        p.res = resv
     p.stats = stats.data_ptr() if norm else None
-    p.eps, p.act, p.act_slope, p.res_before_act = eps, act, slope, 0
-    _call("in_fwd", raw.numel() * 2 * (3 if residual is not None else 2), "byte", "gb_in_fwd", lib.gb_in_fwd,
-          C.byref(p), _stream())
-    return out, stats
+    p.prelu = prelu.data_ptr() if prelu is not None else None
+    p.eps, p.act, p.act_slope = eps, act, slope
+    p.res_before_act, p.out_scale = 1 if res_before_act else 0, out_scale
+    _call("in_fwd", nbytes * (3 if resv is not None else 2), "byte", "gb_in_fwd", lib.gb_in_fwd, C.byref(p), _stream())
+    return stats
 
 
-def norm_act_backward(raw, stats, out, dout32, norm, act, slope, out_pad, eps, dres32=None, res_pad=0, need_draw=True,
-                      dbias=None):
-    """dout32: fp32 gradient wrt the (bordered) output buffer. Returns bf16 d_raw.
-    dres32: fp32 gradient buffer of the residual input; its interior is OVERWRITTEN with fold(dout32)."""
+def norm_act_backward(xv: View, stats, dyv: View, dxv: View, norm, act, slope, eps, device, yv=None, resv=None,
+                      dresv=None, prelu=None, dprelu=None, dbias=None, res_before_act=False, dres_acc=False,
+                      dx_fp32_acc=False, out_scale=1.0, need_dx=True):
+    """Backward of norm_act_forward. dyv: fp32 gradient of the (bordered) output; dxv: bf16 d_raw (or an fp32 view
+    accumulated into, when the forward input was an activation buffer); dresv: fp32 gradient view of the residual."""
     lib = _cabi.lib()
-    N, D, H, W, Cc = raw.shape
     p = InBwdParams()
-    p.x = make_view(raw)
-    p.dy_b = make_view(dout32, out_pad)
-    if dres32 is not None:
-        p.dy_sum = make_view(dres32, res_pad)
-    draw = torch.empty_like(raw)
-    p.dx = make_view(draw)
+    p.x, p.dy_b, p.dx = xv, dyv, dxv
+    if dresv is not None:
+        p.dy_sum = dresv
+    if resv is not None:
+        p.res = resv
     p.eps = eps
-    p.dbias = dbias.data_ptr() if (dbias is not None and need_draw) else None
-    if need_draw:
+    p.res_before_act, p.dy_sum_acc, p.dx_fp32_acc, p.out_scale = (1 if res_before_act else 0, 1 if dres_acc else 0,
+                                                                   1 if dx_fp32_acc else 0, out_scale)
+    if need_dx:
         if norm:
-            bstats = zeros((N, Cc, 2), raw.device)
+            bstats = zeros((xv.N, xv.C, 2), device)
             p.stats, p.bstats = stats.data_ptr(), bstats.data_ptr()
-        elif act != ACT_NONE:
-            p.y = make_view(out, out_pad)
+        elif yv is not None:
+            p.y = yv
         p.act, p.act_slope = act, slope
+        p.prelu = prelu.data_ptr() if prelu is not None else None
+        p.dprelu = dprelu.data_ptr() if dprelu is not None else None
+        p.dbias = dbias.data_ptr() if dbias is not None else None
     else:
         p.act = ACT_NONE  # only the residual branch needs the (folded) gradient
-    # algorithmic bytes: reduce reads dy(4)+x(2); apply reads dy(4)+x(2), writes dx(2) [+ dres(4)]
-    nbytes = raw.numel() * ((6 if norm else 0) + 8 + (4 if dres32 is not None else 0))
+    n = xv.N * xv.D * xv.H * xv.W * xv.C
+    nbytes = n * ((6 if norm else 0) + 8 + (4 if dresv is not None else 0))
     _call("in_bwd", nbytes, "byte", "gb_in_bwd", lib.gb_in_bwd, C.byref(p), _stream())
-    return draw if need_draw else None
 
 
 def to_channels_last(x: torch.Tensor, pad: int) -> torch.Tensor:
@@ -427,27 +425,34 @@ def to_channels_last(x: torch.Tensor, pad: int) -> torch.Tensor:
 def to_channels_last_backward(dbuf32: torch.Tensor, pad: int, shape) -> torch.Tensor:
     """fp32 gradient of the bordered buffer -> NC(D)HW fp32 (border folded back)."""
     dx = torch.empty(shape, dtype=torch.float32, device=dbuf32.device)
-    v = make_view(dbuf32, pad)
+    v = make_view(dbuf32, pad, 0, pad8(shape[1]))
     _cabi.check(_cabi.lib().gb_cl_to_nchw(C.byref(v), dx.data_ptr(), shape[1], 1, ACT_NONE, 1, _stream()), "gb_cl_to_nchw")
     return dx
 
 
-def from_channels_last(x: torch.Tensor, channels: int, is_3d: bool, act: int = ACT_NONE) -> torch.Tensor:
-    """bf16 plain buffer (N,D,H,W,Cpad) -> NC(D)HW fp32; act=ACT_TANH evaluates the output tanh in fp32."""
-    N, D, H, W, Cc = x.shape
+def from_channels_last(x: torch.Tensor, channels: int, is_3d: bool, act: int = ACT_NONE, pad: int = 0) -> torch.Tensor:
+    """bf16 buffer (N,D,H+2p,W+2p,Cpad) -> NC(D)HW fp32 of its interior; act=ACT_TANH evaluates the output tanh in
+    fp32."""
+    N, D, Hb, Wb, Cc = x.shape
+    H, W = Hb - 2 * pad, Wb - 2 * pad
     shape = (N, channels, D, H, W) if is_3d else (N, channels, H, W)
     out = torch.empty(shape, dtype=torch.float32, device=x.device)
-    v = make_view(x)
+    v = make_view(x, pad)
     _cabi.check(_cabi.lib().gb_cl_to_nchw(C.byref(v), out.data_ptr(), channels, 0, act, 0, _stream()), "gb_cl_to_nchw")
     return out
 
 
-def from_channels_last_backward(dout: torch.Tensor, buf_shape, channels: int, pre=None, fp32=False) -> torch.Tensor:
+def from_channels_last_backward(dout: torch.Tensor, buf_shape, channels: int, pre=None, fp32=False,
+                                pad: int = 0) -> torch.Tensor:
     """NC(D)HW fp32 gradient -> channels-last gradient (bf16 d_raw, or fp32 for an activation buffer);
-    pre: the saved pre-activation when the export applied tanh."""
+    pre: the saved pre-activation when the export applied tanh; pad: the gradient is written to the interior of a
+    zero-initialised bordered buffer."""
     dout = dout.contiguous().float()
-    dx = torch.empty(buf_shape, dtype=torch.float32 if fp32 else torch.bfloat16, device=dout.device)
-    v = make_view(dx)
+    if pad > 0:
+        dx = zeros(buf_shape, dout.device) if fp32 else torch.zeros(buf_shape, dtype=torch.bfloat16, device=dout.device)
+    else:
+        dx = torch.empty(buf_shape, dtype=torch.float32 if fp32 else torch.bfloat16, device=dout.device)
+    v = make_view(dx, pad)
     pv = make_view(pre) if pre is not None else None
     _cabi.check(_cabi.lib().gb_nchw_to_cl(dout.data_ptr(), channels, C.byref(v), C.byref(pv) if pv is not None else None,
                                           1 if fp32 else 0, _stream()), "gb_nchw_to_cl")
@@ -497,3 +502,33 @@ class L1Fn(torch.autograd.Function):
             return None, None
         g = grad * dloss
         return (g if ctx.needs_input_grad[0] else None), (-g if ctx.needs_input_grad[1] else None)
+
+
+class PatchNCEFn(torch.autograd.Function):
+    """Per-row PatchNCE loss of (feat_q, feat_k) -- fused logits / mask / temperature / CE kernel
+    (ganslate/nn/losses/cut_losses.py:14-43; feat_k is detached there, so only feat_q receives a gradient)."""
+
+    @staticmethod
+    def forward(ctx, feat_q, feat_k, batch, temperature):
+        _require_cuda(feat_q, "PatchNCE features")
+        q = feat_q.contiguous().float()
+        k = feat_k.detach().contiguous().float()
+        R, D = q.shape
+        P = R // batch
+        loss = torch.empty(R, dtype=torch.float32, device=q.device)
+        probs = torch.empty((R, P + 1), dtype=torch.float32, device=q.device)
+        _cabi.check(_cabi.lib().gb_patchnce_fwd(q.data_ptr(), k.data_ptr(), batch, P, D, float(temperature),
+                                                loss.data_ptr(), probs.data_ptr(), _stream()), "gb_patchnce_fwd")
+        ctx.save_for_backward(k, probs)
+        ctx.cfg = (batch, P, D, float(temperature))
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        k, probs = ctx.saved_tensors
+        batch, P, D, T = ctx.cfg
+        dq = torch.empty((batch * P, D), dtype=torch.float32, device=k.device)
+        dloss = dloss.contiguous().float()
+        _cabi.check(_cabi.lib().gb_patchnce_bwd(k.data_ptr(), probs.data_ptr(), dloss.data_ptr(), batch, P, D, T,
+                                                dq.data_ptr(), _stream()), "gb_patchnce_bwd")
+        return dq, None, None, None

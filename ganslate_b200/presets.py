@@ -44,3 +44,23 @@ def pix2pix_resnet2d(batch_size=8, lambda_pix2pix=30.0, n_residual_blocks=9, n_l
     }
     conf["train"].update(train_overrides)
     return init_config(conf)
+
+
+def cut_resnet2d(batch_size=1, n_residual_blocks=9, **train_overrides):
+    """CUT defaults of ganslate/nn/gans/unpaired/cut.py:16-40 on Resnet2D + PatchGAN2D."""
+    conf = {
+        "mode": "train",
+        "train": {
+            "batch_size": batch_size, "cuda": True, "mixed_precision": False, "n_iters": 200000, "n_iters_decay": 0,
+            "gan": {
+                "_target_": "ganslate_b200.nn.gans.unpaired.CUT",
+                "generator": {"_target_": "ganslate_b200.nn.generators.Resnet2D",
+                              "n_residual_blocks": n_residual_blocks, "in_out_channels": {"AB": [3, 3]}},
+                "discriminator": {"_target_": "ganslate_b200.nn.discriminators.PatchGAN2D", "n_layers": 3,
+                                  "in_channels": {"B": 3}},
+                "optimizer": {"lr_D": 0.0002, "lr_G": 0.0002},
+            },
+        },
+    }
+    conf["train"].update(train_overrides)
+    return init_config(conf)

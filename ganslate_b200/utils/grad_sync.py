@@ -1,0 +1,54 @@
+"""Flat-bucket gradient all-reduce for the CUDA-graph training path.
+
+The reference wraps every network in DistributedDataParallel (ganslate/nn/gans/base.py:172-189) and that wrap is
+kept for eager execution.  DDP's reducer hooks do not survive being captured into the replayed graphs on this
+stack (the capture dead-locks), so when `train.cuda_graph` is on the same average-all-reduce is issued explicitly:
+after a backward graph has run, the gradients of one optimizer group are packed into one fp32 buffer and reduced
+with NCCL on a side stream, overlapping with the next graph (the discriminator phase); the optimizer step waits for
+it.  Semantics are DDP's: mean over ranks, parameters broadcast from rank 0 at start.
+"""
+import torch
+import torch.distributed as dist
+
+
+class FlatGradSync:
+
+    def __init__(self, params, device):
+        seen, self.params = set(), []
+        for p in params:
+            if id(p) not in seen:
+                seen.add(id(p))
+                self.params.append(p)
+        self.device = device
+        self.flat = torch.empty(sum(p.numel() for p in self.params), dtype=torch.float32, device=device)
+        self.views, off = [], 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        self.stream = torch.cuda.Stream(device=device)
+        self.world = dist.get_world_size()
+        self._pending = False
+
+    def broadcast_parameters(self):
+        for p in self.params:
+            dist.broadcast(p.data, src=0)
+
+    def launch(self):
+        """Call after backward on the compute stream: pack and start the all-reduce on the side stream."""
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+        torch._foreach_copy_(self.views, grads)
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.mul_(1.0 / self.world)
+        self._pending = True
+
+    def finish(self):
+        """Call before the optimizer step: wait for the reduction and write the averaged gradients back."""
+        if not self._pending:
+            return
+        torch.cuda.current_stream().wait_stream(self.stream)
+        grads = [p.grad for p in self.params if p.grad is not None]
+        views = [v for p, v in zip(self.params, self.views) if p.grad is not None]
+        torch._foreach_copy_(grads, views)
+        self._pending = False

@@ -141,7 +141,8 @@ typedef struct gb_in_fwd_params {
   float eps;
   int32_t act;
   float act_slope;
-  int32_t res_before_act;    /* 1: y = act(norm(x) + res)  (V-Net), 0: y = act(norm(x)) + res */
+  int32_t res_before_act;    /* 1: y = act(norm(x) + res)  (V-Net), 0: y = out_scale * act(norm(x)) + res */
+  float out_scale;           /* 1, or -1 for the inverse of an additive coupling (x2 = y2 - G(y1)); 0 is read as 1 */
 } gb_in_fwd_params;
 
 int gb_in_fwd(const gb_in_fwd_params* p, void* stream);
@@ -162,6 +163,12 @@ typedef struct gb_in_bwd_params {
   float eps;
   int32_t act;
   float act_slope;
+  gb_view res;               /* forward residual; needed when res_before_act (the activation mask depends on it) */
+  int32_t res_before_act;    /* forward was act(norm(x) + res): dy_sum receives the MASKED gradient g */
+  int32_t dy_sum_acc;        /* 1: dy_sum += (several consumers share the gradient buffer), 0: dy_sum = */
+  int32_t dx_fp32_acc;       /* 1: dx is an FP32 view and is accumulated (x was an activation buffer, not a raw
+                                convolution output) */
+  float out_scale;           /* forward was out_scale * act(norm(x)) + res; 0 is read as 1 */
 } gb_in_bwd_params;
 
 /* two launches: reduction then apply */
@@ -181,6 +188,14 @@ int gb_cl_to_nchw(const gb_view* src, float* dst, int C, int fold, int act, int 
  * loss is a single fp32 (zeroed by the caller); grad may be NULL. */
 int gb_mse_const(const float* pred, float target, int64_t n, float* loss, float* grad, void* stream);
 int gb_l1(const float* a, const float* b, int64_t n, float* loss, float* grad_a, void* stream);
+
+/* PatchNCE (CUT): q, k are [B*P][D] fp32 (k is detached in the reference, ganslate/nn/losses/cut_losses.py:16);
+ * loss[r] = CE(cat(q_r.k_r, q_r.K_b^T with the own patch masked to -10) / T, 0); probs [B*P][P+1] is saved for
+ * gb_patchnce_bwd, which writes dq = d loss / d q scaled by dloss[r]. */
+int gb_patchnce_fwd(const float* q, const float* k, int B, int P, int D, float T, float* loss, float* probs,
+                    void* stream);
+int gb_patchnce_bwd(const float* k, const float* probs, const float* dloss, int B, int P, int D, float T, float* dq,
+                    void* stream);
 
 /* ---- misc ---- */
 int gb_version(void);

@@ -409,3 +409,106 @@ class OraclePix2Pix:
         if step_optimizers:
             self.optimizers["D"].step()
         return {k: float(v.detach()) for k, v in self.losses.items()}
+
+
+# --------------------------------------------------------------------------------------------- CUT step
+class OracleFeaturePatchMLP(nn.Module):
+    """ganslate/nn/gans/unpaired/cut.py:229-294 (FeaturePatchMLP + LNorm)."""
+
+    def __init__(self, channels_per_feature, num_patches=256, nc=256):
+        super().__init__()
+        self.num_patches = num_patches
+        self.mlps = nn.ModuleList(
+            [nn.Sequential(nn.Linear(c, nc), nn.ReLU(), nn.Linear(nc, nc)) for c in channels_per_feature])
+
+    def forward(self, feats, patch_ids=None):
+        out, ids = [], []
+        for i, feat in enumerate(feats):
+            feat = feat.permute(0, 2, 3, 1).flatten(1, 2)                       # :257-262 (2-D)
+            pid = patch_ids[i] if patch_ids is not None else torch.randperm(feat.shape[1])[:self.num_patches]
+            x = self.mlps[i](feat[:, pid, :].flatten(0, 1))                     # :270-275
+            x = x / (x.pow(2).sum(1, keepdim=True).pow(0.5) + 1e-7)             # LNorm :290-294
+            out.append(x)
+            ids.append(pid)
+        return out, ids
+
+
+def patchnce_loss(feat_q, feat_k, batch_size, nce_T=0.07):
+    """ganslate/nn/losses/cut_losses.py:14-43"""
+    bs, dim = feat_q.shape[:2]
+    feat_k = feat_k.detach()
+    l_pos = torch.bmm(feat_q.view(bs, 1, -1), feat_k.view(bs, -1, 1)).view(bs, 1)
+    q = feat_q.view(batch_size, -1, dim)
+    k = feat_k.view(batch_size, -1, dim)
+    n = q.size(1)
+    l_neg = torch.bmm(q, k.transpose(2, 1))
+    l_neg.masked_fill_(torch.eye(n, dtype=torch.bool)[None, :, :], -10.0)
+    out = torch.cat((l_pos, l_neg.view(-1, n)), dim=1) / nce_T
+    return F.cross_entropy(out, torch.zeros(out.size(0), dtype=torch.long), reduction="none")
+
+
+def extract_features(x, net, layer_ids):
+    """cut.py:297-312 -- iterate `net.encoder`, record after the listed indices (in-place ReLUs included)."""
+    feats, feat = [], x
+    for i, layer in enumerate(net.encoder):
+        feat = layer(feat)
+        if i in layer_ids:
+            feats.append(feat)
+    return feats
+
+
+class OracleCUT:
+    """One iteration as ganslate/nn/gans/unpaired/cut.py:113-226 runs it (Resnet2D + PatchGAN2D, lsgan)."""
+
+    def __init__(self, n_residual_blocks=9, nce_layers=(0, 4, 8, 12, 16), num_patches=256, mlp_nc=256, batch_size=1,
+                 lambda_adv=1.0, lambda_nce=1.0, lambda_nce_idt=0.5, nce_T=0.07, lr=2e-4, seed=0):
+        torch.manual_seed(seed)
+        self.nce_layers, self.batch_size, self.nce_T = tuple(nce_layers), batch_size, nce_T
+        self.l_adv, self.l_nce, self.l_idt = lambda_adv, lambda_nce, lambda_nce_idt
+        G = init_weights(OracleResnet2D(3, 3, n_residual_blocks))          # network dict order cut.py:72: G, D, mlp
+        D = init_weights(OraclePatchGAN2D(3))
+        with torch.no_grad():                                              # probe_network_channels cut.py:315-333
+            chans = [f.shape[1] for f in extract_features(torch.zeros(1, 3, 64, 64), G, self.nce_layers)]
+        mlp = init_weights(OracleFeaturePatchMLP(chans, num_patches, mlp_nc))
+        self.networks = {"G": G, "D": D, "mlp": mlp}
+        self.optimizers = {k: torch.optim.Adam(v.parameters(), lr=lr, betas=(0.5, 0.999)) for k, v in self.networks.items()}
+        self.visuals, self.losses = {}, {}
+
+    def _nce(self, source, target, patch_ids):
+        G, mlp = self.networks["G"], self.networks["mlp"]
+        sf = extract_features(source, G, self.nce_layers)
+        tf = extract_features(target, G, self.nce_layers)
+        sp, ids = mlp(sf, patch_ids)
+        tp, _ = mlp(tf, ids)
+        total = 0
+        for t, s in zip(tp, sp):
+            total = total + (patchnce_loss(t, s, self.batch_size, self.nce_T) * self.l_nce).mean()
+        return total / len(self.nce_layers), ids
+
+    def optimize_parameters(self, real_A, real_B, patch_ids=None, step_optimizers=True):
+        G, D = self.networks["G"], self.networks["D"]
+        fake_B = G(real_A)
+        idt_B = G(real_B) if self.l_idt > 0 else None
+        self.visuals = {"real_A": real_A, "real_B": real_B, "fake_B": fake_B, "idt_B": idt_B}
+        OracleCycleGAN._set_requires_grad([D], True)
+        self.optimizers["D"].zero_grad(set_to_none=True)
+        self.losses["D"] = adversarial_lsgan(D(real_B), True) + adversarial_lsgan(D(fake_B.detach()), False)
+        self.losses["D"].backward()
+        if step_optimizers:
+            self.optimizers["D"].step()
+        OracleCycleGAN._set_requires_grad([D], False)
+        self.optimizers["G"].zero_grad(set_to_none=True)
+        self.optimizers["mlp"].zero_grad(set_to_none=True)
+        self.losses["G"] = adversarial_lsgan(D(fake_B), True) * self.l_adv
+        nce, ids = self._nce(real_A, fake_B, patch_ids)
+        self.losses["NCE"] = nce
+        total_nce = nce
+        if self.l_idt > 0:
+            nce_idt, _ = self._nce(real_B, idt_B, ids if patch_ids is None else patch_ids)
+            self.losses["NCE_idt"] = self.l_idt * nce_idt
+            total_nce = (1 - self.l_idt) * nce + self.losses["NCE_idt"]
+        (self.losses["G"] + total_nce).backward()
+        if step_optimizers:
+            self.optimizers["G"].step()
+            self.optimizers["mlp"].step()
+        return {k: float(v.detach()) for k, v in self.losses.items()}, ids

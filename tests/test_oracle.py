@@ -147,3 +147,42 @@ def test_image_pool_matches_reference_semantics():
     mine = ImagePool(2)
     mine.query(a), mine.query(b)
     assert torch.equal(mine.query(c), out)
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference only exists in the build container")
+def test_oracle_losses_equal_reference_classes():
+    """PatchNCELoss, CycleGANLosses, Pix2PixLoss of the reference vs their oracle restatements."""
+    from types import SimpleNamespace
+    m = R.modules()
+    conf = SimpleNamespace(train=SimpleNamespace(batch_size=2, gan=SimpleNamespace(optimizer=SimpleNamespace(
+        nce_T=0.07, lambda_AB=10.0, lambda_BA=5.0, lambda_identity=0.5, proportion_ssim=0.0, lambda_pix2pix=30.0))))
+    torch.manual_seed(0)
+    q, k = torch.randn(2 * 64, 32), torch.randn(2 * 64, 32)
+    assert torch.allclose(m["PatchNCELoss"](conf)(q, k), O.patchnce_loss(q, k, 2, 0.07), atol=1e-6)
+    v = {n: torch.rand(2, 3, 8, 8) for n in ("real_A", "real_B", "fake_A", "fake_B", "rec_A", "rec_B", "idt_A", "idt_B")}
+    ref = m["CycleGANLosses"](conf)(v)
+    ora = O.cyclegan_losses(v, 10.0, 5.0, 0.5)
+    assert set(ref) == set(ora)
+    for n in ref:
+        assert torch.allclose(ref[n], ora[n], atol=1e-6), n
+    assert torch.allclose(m["Pix2PixLoss"](conf)(v["fake_B"], v["real_B"]), 30.0 * torch.nn.functional.l1_loss(v["fake_B"], v["real_B"]))
+
+
+def test_b200_cut_modules_match_oracle_structure():
+    """FeaturePatchMLP state_dict keys / init order equal the oracle's (and hence the reference's cut.py:244-250)."""
+    from ganslate_b200.nn.gans.unpaired.cut import FeaturePatchMLP
+    from ganslate_b200.nn.utils import init_weights
+    torch.manual_seed(3)
+    a = O.init_weights(O.OracleFeaturePatchMLP([3, 128, 256], 256, 64))
+    torch.manual_seed(3)
+    b = FeaturePatchMLP([3, 128, 256], 256, 64)
+    init_weights(b, "normal", 0.02)
+    assert list(a.state_dict().keys()) == list(b.state_dict().keys())
+    for (k, x), (_, y) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(x, y), k
+    feats = [torch.rand(2, c, 8, 8) for c in (3, 128, 256)]
+    ids = [torch.arange(0, 64, 2)] * 3
+    fa, _ = a(feats, ids)
+    fb, _ = b(feats, ids)
+    for x, y in zip(fa, fb):
+        assert torch.allclose(x, y, atol=1e-6)
