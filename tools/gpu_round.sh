@@ -1,0 +1,38 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, bench line, ncu launch list, ncu --set full of the top kernels.
+# Usage (under gpurun): [BATCH=8] bash tools/gpu_round.sh <tag> [tests|smoke|bench|launches|full ...]
+tag=${1:-r01}; shift
+what=${*:-tests bench launches full}
+B=${BATCH:-1}
+out=gpurun_out/$tag
+mkdir -p $out
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $out/gpu.txt 2>&1
+python -c "import os;print('cpus',os.cpu_count())" >> $out/gpu.txt
+for w in $what; do
+case $w in
+tests)
+  timeout 1500 python -m pytest tests -m gpu -x -q > $out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $out/pytest_gpu.log
+  tail -5 $out/pytest_gpu.log ;;
+smoke)
+  timeout 600 python __graft_entry__.py smoke > $out/smoke.log 2>&1; tail -3 $out/smoke.log ;;
+bench)
+  timeout 900 python bench.py --batch $B > $out/bench_b$B.json 2> $out/bench_b$B.err; tail -c 3500 $out/bench_b$B.json
+  tail -3 $out/bench_b$B.err ;;
+benchref)
+  timeout 600 python bench.py --impl reference --steps 3 --warmup 1 --batch $B > $out/bench_ref_b$B.json 2>> $out/bench_b$B.err; cat $out/bench_ref_b$B.json ;;
+launches)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file $out/launches_b$B.csv \
+     python bench.py --batch $B --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-roofline > $out/launches_run.log 2>&1
+  python tools/launch_summary.py $out/launches_b$B.csv 5 --md > $out/launch_summary_b$B.md 2>&1; head -42 $out/launch_summary_b$B.md ;;
+full)
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${KREGEX:-igemm|in_fwd|in_bwd|in_stats}" \
+     --launch-skip ${KSKIP:-300} -c ${KCOUNT:-16} -o $out/top_kernels_b$B -f \
+     python bench.py --batch $B --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-roofline > $out/full_run.log 2>&1
+  python tools/ncu_summary.py $out/top_kernels_b$B.ncu-rep > $out/ncu_full_summary_b$B.md 2>&1
+  ncu -i $out/top_kernels_b$B.ncu-rep --page raw --csv > $out/ncu_full_raw_b$B.csv 2>/dev/null
+  sz=$(stat -c %s $out/top_kernels_b$B.ncu-rep 2>/dev/null || echo 0)
+  if [ "$sz" -gt 40000000 ]; then rm -f $out/top_kernels_b$B.ncu-rep; echo "ncu-rep too large ($sz), removed" ; fi
+  grep -E "^###|duration|tensor pipe|DRAM read|DRAM write|L2 -> SM" $out/ncu_full_summary_b$B.md | head -120 ;;
+esac
+done
+du -sh gpurun_out
