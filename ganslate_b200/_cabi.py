@@ -28,7 +28,7 @@ class ConvParams(C.Structure):
     _fields_ = [("inp", View), ("out", View), ("wpacked", C.c_void_p), ("bias", C.c_void_p), ("ncols", C.c_int32),
                 ("npad", C.c_int32), ("in_mul", C.c_int32 * 3), ("out_mul", C.c_int32 * 3), ("nclass", C.c_int32),
                 ("cls", ConvClass * GB_MAX_CLASSES), ("taps", (C.c_int8 * 4) * GB_MAX_TAPS), ("act", C.c_int32),
-                ("act_slope", C.c_float), ("out_fp32", C.c_int32), ("accumulate", C.c_int32)]
+                ("act_slope", C.c_float), ("out_fp32", C.c_int32), ("accumulate", C.c_int32), ("stats", C.c_void_p)]
 
 
 class WgradParams(C.Structure):
@@ -43,6 +43,32 @@ class PackParams(C.Structure):
                 ("nclass", C.c_int32), ("ntaps", C.c_int32 * GB_MAX_CLASSES), ("kpad", C.c_int32 * GB_MAX_CLASSES),
                 ("w_offset", C.c_int64 * GB_MAX_CLASSES), ("tap_begin", C.c_int32 * GB_MAX_CLASSES),
                 ("tap_id", C.c_int32 * GB_MAX_TAPS)]
+
+
+GB_UNPACK_BATCH = 56
+
+
+class UnpackItem(C.Structure):
+    _fields_ = [("dw", C.c_void_p), ("dst", C.c_void_p), ("dsr", C.c_int64), ("dsc", C.c_int64), ("dst_t", C.c_int64),
+                ("rows", C.c_int32), ("chans", C.c_int32), ("chans_pad", C.c_int32), ("ntaps", C.c_int32),
+                ("kpad", C.c_int32), ("accumulate", C.c_int32)]
+
+
+class UnpackBatch(C.Structure):
+    _fields_ = [("count", C.c_int32), ("pad_", C.c_int32), ("item", UnpackItem * GB_UNPACK_BATCH)]
+
+
+GB_ADAM_BATCH = 96
+
+
+class AdamItem(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int32),
+                ("vec4", C.c_int32)]
+
+
+class AdamBatch(C.Structure):
+    _fields_ = [("lr", C.c_void_p), ("step", C.c_void_p), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("count", C.c_int32), ("item", AdamItem * GB_ADAM_BATCH)]
 
 
 class InFwdParams(C.Structure):
@@ -63,8 +89,11 @@ _SIGNATURES = {
     "gb_conv_data": [C.POINTER(ConvParams), C.c_void_p],
     "gb_conv_wgrad": [C.POINTER(WgradParams), C.c_void_p],
     "gb_pack_weights": [C.POINTER(PackParams), C.c_void_p],
+    "gb_pack_weights_multi": [C.c_void_p, C.c_int, C.c_int64, C.c_void_p],
+    "gb_unpack_wgrad_multi": [C.POINTER(UnpackBatch), C.c_void_p],
     "gb_unpack_wgrad": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                         C.c_int, C.c_void_p],
+    "gb_adam_multi": [C.POINTER(AdamBatch), C.c_void_p],
     "gb_colsum": [C.POINTER(View), C.c_void_p, C.c_void_p],
     "gb_in_stats": [C.POINTER(View), C.c_void_p, C.c_void_p],
     "gb_in_fwd": [C.POINTER(InFwdParams), C.c_void_p],

@@ -13,6 +13,7 @@
 // (TMEM -> registers -> +bias / activation -> bf16 -> global).
 #include "gb_common.cuh"
 #include "gb_geometry.h"
+#include "gb_epilogue.cuh"
 
 namespace {
 
@@ -231,71 +232,18 @@ __global__ void __launch_bounds__(256, Cfg<BN>::MIN_CTAS) igemm_data_kernel(cons
     tc_fence_after();
   }
   {
-    const int lg = warp & 3;
-    const int half = warp >> 2;
-    const int row = lg * 32 + lane;
+    const int row = (warp & 3) * 32 + lane;
     const int64_t m = m0 + row;
     const bool row_ok = m < Mc;
-    __nv_bfloat16* optr = reinterpret_cast<__nv_bfloat16*>(p.out.ptr);
     int64_t ooff = 0;
+    int row_n = 0;
     if (row_ok) {
       gb_row r = gb_decode_row_fast((uint32_t)m, divs.f[cls]);
+      row_n = r.n;
       ooff = gb_pix_offset(p.out, r.n, r.qz * p.out_mul[0] + cc.off[0], r.qy * p.out_mul[1] + cc.off[1],
                            r.qx * p.out_mul[2] + cc.off[2]);
     }
-    constexpr int CH = (BN >= 64) ? 32 : 16;              // columns per TMEM load
-    constexpr int COLS_PER_HALF = (BN >= 64) ? BN / 2 : BN;
-    const bool active = (BN >= 64) || half == 0;
-    if (active) {
-      const int cbeg = (BN >= 64) ? half * COLS_PER_HALF : 0;
-#pragma unroll 1
-      for (int c0 = cbeg; c0 < cbeg + COLS_PER_HALF; c0 += CH) {
-        uint32_t acc[CH];
-        if (KB > 0) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
-          if constexpr (CH == 32) tmem_ld32(taddr, acc); else tmem_ld16(taddr, acc);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int i = 0; i < CH; ++i) acc[i] = 0u;
-        }
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < CH / 8; ++g) {
-            const int col = n0 + c0 + g * 8;
-            if (col < p.out.C) {
-              float v[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float t = __uint_as_float(acc[g * 8 + e]) + bias_s[c0 + g * 8 + e];
-                if (p.act == GB_ACT_TANH) t = tanhf(t);
-                else if (p.act == GB_ACT_LEAKY) t = t > 0.f ? t : t * p.act_slope;
-                else if (p.act == GB_ACT_RELU) t = fmaxf(t, 0.f);
-                v[e] = t;
-              }
-              if (p.out_fp32) {
-                float4* o32 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out.ptr) + ooff + col);
-                float4 a = make_float4(v[0], v[1], v[2], v[3]), b = make_float4(v[4], v[5], v[6], v[7]);
-                if (p.accumulate) {
-                  const float4 pa = o32[0], pb = o32[1];
-                  a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
-                  b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
-                }
-                o32[0] = a;
-                o32[1] = b;
-              } else {
-                uint4 o;
-                o.x = pack_bf16x2(v[0], v[1]);
-                o.y = pack_bf16x2(v[2], v[3]);
-                o.z = pack_bf16x2(v[4], v[5]);
-                o.w = pack_bf16x2(v[6], v[7]);
-                *reinterpret_cast<uint4*>(optr + ooff + col) = o;
-              }
-            }
-          }
-        }
-      }
-    }
+    gb_conv_epilogue<BN>(p, tmem_base, warp, lane, KB > 0, row_ok, ooff, n0, bias_s, row_n);
   }
   tc_fence_before();
   __syncthreads();

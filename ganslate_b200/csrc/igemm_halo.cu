@@ -12,6 +12,7 @@
 #include <cuda.h>
 #include "gb_common.cuh"
 #include "gb_geometry.h"
+#include "gb_epilogue.cuh"
 #include "gb_tma.h"
 
 namespace {
@@ -23,12 +24,17 @@ constexpr int MAX_HH = 24;               // halo rows (TH + kh - 1), kh <= 9
 
 template <int BN>
 struct HCfg {
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;            // one tap x 64 channels of weights
+  // narrow tiles (the 7x7 -> 3 channel layers) are bound by the barrier round trip per tap, not by data: a B stage
+  // carries TG taps (one wait / commit per TG*4 MMAs) and two CTAs share an SM so that one CTA's halo load and
+  // epilogue overlap the other's MMAs
+  static constexpr int TG = (BN <= 32) ? (16 * 1024 / B_BYTES > 8 ? 8 : 16 * 1024 / B_BYTES) : 1;
   static constexpr int A_BYTES_MAX = HW * MAX_HH * 128;  // 48 KB
-  static constexpr int A_STAGES = 2;
-  static constexpr int B_STAGES = (BN == 256) ? 3 : (BN == 128 ? 6 : 8);
+  static constexpr int A_STAGES = (BN <= 32) ? 1 : 2;
+  static constexpr int B_STAGES = (BN <= 32) ? 3 : ((BN == 256) ? 3 : (BN == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  static constexpr int SMEM = A_STAGES * A_BYTES_MAX + B_STAGES * B_BYTES + 1024 + 1024;
+  static constexpr int SMEM = A_STAGES * A_BYTES_MAX + B_STAGES * TG * B_BYTES + 1024 + 1024;
+  static constexpr int MIN_CTAS = (BN <= 32) ? 2 : 1;
 };
 
 struct HaloGeom {
@@ -56,7 +62,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_bo(uint32_t saddr, uint32_t s
 }
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, HCfg<BN>::MIN_CTAS)
 igemm_halo_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant__ CUtensorMap map_a,
                   const __grid_constant__ CUtensorMap map_b, const __grid_constant__ HaloGeom hg, int base_offset_mode) {
   using C = HCfg<BN>;
@@ -65,8 +71,10 @@ igemm_halo_kernel(const __grid_constant__ gb_conv_params p, const __grid_constan
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const uint32_t a_base = base;
+  constexpr int TG = C::TG;
+  constexpr int BS_BYTES = TG * C::B_BYTES;  // bytes of one B stage
   const uint32_t b_base = base + C::A_STAGES * C::A_BYTES_MAX;
-  uint8_t* tail = smem + C::A_STAGES * C::A_BYTES_MAX + C::B_STAGES * C::B_BYTES;
+  uint8_t* tail = smem + C::A_STAGES * C::A_BYTES_MAX + C::B_STAGES * BS_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   // layout: a_full[2], a_empty[2], b_full[B_STAGES], b_empty[B_STAGES], accum
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 256);
@@ -131,11 +139,14 @@ igemm_halo_kernel(const __grid_constant__ gb_conv_params p, const __grid_constan
           mbar_expect_tx(a_full + 8 * as, (uint32_t)hg.a_bytes);
           tma_load_5d(a_base + as * C::A_BYTES_MAX, &map_a, a_full + 8 * as, c * 64, x0 + hg.dx_min, y0 + hg.dy_min,
                       z0 + dz, n);
-          for (int tl = hg.group_begin[g]; tl < hg.group_begin[g + 1]; ++tl, ++bi) {
+          for (int tl = hg.group_begin[g]; tl < hg.group_begin[g + 1]; tl += TG, ++bi) {
             const int bs = bi % C::B_STAGES, bit = bi / C::B_STAGES;
+            const int nt = min(TG, hg.group_begin[g + 1] - tl);
             if (bit > 0) mbar_wait(b_empty + 8 * bs, (bit - 1) & 1);
-            mbar_expect_tx(b_full + 8 * bs, C::B_BYTES);
-            tma_load_2d(b_base + bs * C::B_BYTES, &map_b, b_full + 8 * bs, tl * p.in.C + c * 64, cls * p.npad + n0);
+            mbar_expect_tx(b_full + 8 * bs, (uint32_t)(nt * C::B_BYTES));
+            for (int j = 0; j < nt; ++j)
+              tma_load_2d(b_base + bs * BS_BYTES + j * C::B_BYTES, &map_b, b_full + 8 * bs, (tl + j) * p.in.C + c * 64,
+                          cls * p.npad + n0);
           }
         }
       }
@@ -149,20 +160,23 @@ igemm_halo_kernel(const __grid_constant__ gb_conv_params p, const __grid_constan
       for (int c = 0; c < chunks; ++c, ++ai) {
         const int as = ai % C::A_STAGES, ait = ai / C::A_STAGES;
         mbar_wait(a_full + 8 * as, ait & 1);
-        for (int tl = hg.group_begin[g]; tl < hg.group_begin[g + 1]; ++tl, ++bi) {
+        for (int tl = hg.group_begin[g]; tl < hg.group_begin[g + 1]; tl += TG, ++bi) {
           const int bs = bi % C::B_STAGES, bit = bi / C::B_STAGES;
+          const int nt = min(TG, hg.group_begin[g + 1] - tl);
           mbar_wait(b_full + 8 * bs, bit & 1);
           tc_fence_after();
           if (lane == 0) {
-            const int ry = taps_s[4 * tl + 1] - hg.dy_min, rx = taps_s[4 * tl + 2] - hg.dx_min;
-            const uint32_t a_s = a_base + as * C::A_BYTES_MAX + (uint32_t)(ry * HW + rx) * 128u;
-            const uint32_t bo = base_offset_mode ? ((a_s >> 7) & 7u) : 0u;
-            const uint64_t adesc = make_smem_desc_bo(a_s, HW * 128, bo);
-            const uint64_t bdesc = make_smem_desc(b_base + bs * C::B_BYTES, 16, 1024);
+            for (int j = 0; j < nt; ++j) {
+              const int ry = taps_s[4 * (tl + j) + 1] - hg.dy_min, rx = taps_s[4 * (tl + j) + 2] - hg.dx_min;
+              const uint32_t a_s = a_base + as * C::A_BYTES_MAX + (uint32_t)(ry * HW + rx) * 128u;
+              const uint32_t bo = base_offset_mode ? ((a_s >> 7) & 7u) : 0u;
+              const uint64_t adesc = make_smem_desc_bo(a_s, HW * 128, bo);
+              const uint64_t bdesc = make_smem_desc(b_base + bs * BS_BYTES + j * C::B_BYTES, 16, 1024);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, first ? 0u : 1u);
-              first = 0;
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, first ? 0u : 1u);
+                first = 0;
+              }
             }
             umma_commit(b_empty + 8 * bs);
           }
@@ -181,71 +195,15 @@ igemm_halo_kernel(const __grid_constant__ gb_conv_params p, const __grid_constan
     tc_fence_after();
   }
   {
-    const int lg = warp & 3;
-    const int half = warp >> 2;
-    const int row = lg * 32 + lane;
+    const int row = (warp & 3) * 32 + lane;
     const int h = row >> 3, w = row & 7;
     const int qy = y0 + h, qx = x0 + w;
     const bool row_ok = qy < q[1] && qx < q[2];
-    __nv_bfloat16* optr = reinterpret_cast<__nv_bfloat16*>(p.out.ptr);
     int64_t ooff = 0;
     if (row_ok)
       ooff = gb_pix_offset(p.out, n, z0 * p.out_mul[0] + cc.off[0], qy * p.out_mul[1] + cc.off[1],
                            qx * p.out_mul[2] + cc.off[2]);
-    constexpr int CH = (BN >= 64) ? 32 : 16;
-    constexpr int COLS_PER_HALF = (BN >= 64) ? BN / 2 : BN;
-    const bool active = (BN >= 64) || half == 0;
-    const bool have_acc = cc.ntaps > 0;
-    if (active) {
-      const int cbeg = (BN >= 64) ? half * COLS_PER_HALF : 0;
-#pragma unroll 1
-      for (int c0 = cbeg; c0 < cbeg + COLS_PER_HALF; c0 += CH) {
-        uint32_t acc[CH];
-        if (have_acc) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
-          if constexpr (CH == 32) tmem_ld32(taddr, acc); else tmem_ld16(taddr, acc);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int i = 0; i < CH; ++i) acc[i] = 0u;
-        }
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < CH / 8; ++g) {
-            const int col = n0 + c0 + g * 8;
-            if (col < p.out.C) {
-              float v[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float tt = __uint_as_float(acc[g * 8 + e]) + bias_s[c0 + g * 8 + e];
-                if (p.act == GB_ACT_TANH) tt = tanhf(tt);
-                else if (p.act == GB_ACT_LEAKY) tt = tt > 0.f ? tt : tt * p.act_slope;
-                else if (p.act == GB_ACT_RELU) tt = fmaxf(tt, 0.f);
-                v[e] = tt;
-              }
-              if (p.out_fp32) {
-                float4* o32 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out.ptr) + ooff + col);
-                float4 a = make_float4(v[0], v[1], v[2], v[3]), b = make_float4(v[4], v[5], v[6], v[7]);
-                if (p.accumulate) {
-                  const float4 pa = o32[0], pb = o32[1];
-                  a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
-                  b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
-                }
-                o32[0] = a;
-                o32[1] = b;
-              } else {
-                uint4 o;
-                o.x = pack_bf16x2(v[0], v[1]);
-                o.y = pack_bf16x2(v[2], v[3]);
-                o.z = pack_bf16x2(v[4], v[5]);
-                o.w = pack_bf16x2(v[6], v[7]);
-                *reinterpret_cast<uint4*>(optr + ooff + col) = o;
-              }
-            }
-          }
-        }
-      }
-    }
+    gb_conv_epilogue<BN>(p, tmem_base, warp, lane, cc.ntaps > 0, row_ok, ooff, n0, bias_s, n);
   }
   tc_fence_before();
   __syncthreads();
@@ -270,11 +228,15 @@ int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb
 
 int gb_tma_weight_map(const void* w, int kpad, int rows, int bn, CUtensorMap* out);  // igemm_tma.cu
 
-// -1: not applicable, 0: launched, >0 error.  OFF by default (knob 4 = 1 enables it): measured on B200 it is
-// correct but 5-15 % SLOWER than the per-tap TMA kernel on every layer of the workloads (profiles/launches_r01_b8_halo.md)
-// -- the per-tap kernel is bound by the MMA issue / barrier round trip per stage, not by L2 traffic.
+// -1: not applicable, 0: launched, >0 error.
+// Used by default only for narrow outputs with many taps (the generators' 7x7 convolutions to / from 3 channels:
+// BN <= 32), where the per-tap kernel re-reads the same 64-channel pixels 49 times from L2 for an MMA of 8 cycles
+// (measured: 424 us at batch 8 for a layer whose tensors stream in 20 us).  For wide tiles the first version of
+// this kernel measured 5-15 % slower than the per-tap kernel (one barrier round trip per tap, one CTA per SM), so
+// those stay on igemm_tma unless knob 4 = 1 forces this path; knob 4 = 2 disables it.
 int gb_conv_data_halo(const gb_conv_params& p, cudaStream_t st) {
-  if (g_gb_knobs[4] != 1 || g_gb_knobs[3] != 0) return -1;
+  if (g_gb_knobs[4] == 2 || g_gb_knobs[3] != 0) return -1;
+  if (g_gb_knobs[4] != 1 && !(p.ncols <= 32 && p.nclass == 1 && p.cls[0].ntaps >= 16)) return -1;
   if (p.in.C % 64 != 0 || p.in.pad != 0 || !gb_tma_available()) return -1;
   for (int d = 0; d < 3; ++d)
     if (p.in_mul[d] != 1) return -1;

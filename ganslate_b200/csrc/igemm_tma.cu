@@ -16,6 +16,7 @@
 #include <string>
 #include "gb_common.cuh"
 #include "gb_geometry.h"
+#include "gb_epilogue.cuh"
 #include "gb_tma.h"
 
 namespace {
@@ -41,6 +42,7 @@ struct TileGeom {
   int tw, th, tw_shift;                  // TW is a power of two
   int ntx, nty;
   int ntiles;                            // per class (max over classes is the grid)
+  int nstages;                           // depth of the smem ring (<= TCfg::STAGES); small rings let two CTAs share an SM
 };
 
 
@@ -49,14 +51,15 @@ __global__ void __launch_bounds__(256, TCfg<BN>::MIN_CTAS)
 igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant__ CUtensorMap map_a,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TileGeom tg) {
   using C = TCfg<BN>;
-  constexpr int STAGES = C::STAGES;
+  constexpr int MAXS = 8;  // barrier slots (TCfg::STAGES <= 8)
+  const int STAGES = tg.nstages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   uint8_t* tail = smem + STAGES * C::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);  // full[STAGES], empty[STAGES], accum
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 144);
   int8_t* taps_s = reinterpret_cast<int8_t*>(tail + 192);
   __shared__ float bias_s[BN];
 
@@ -85,8 +88,8 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
   const int KB = cc.ntaps * chunks;
 
   const uint32_t full_bar = smem_u32(bars);
-  const uint32_t empty_bar = smem_u32(bars + STAGES);
-  const uint32_t accum_bar = smem_u32(bars + 2 * STAGES);
+  const uint32_t empty_bar = smem_u32(bars + MAXS);
+  const uint32_t accum_bar = smem_u32(bars + 2 * MAXS);
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar + 8 * s, 1);
@@ -108,12 +111,10 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
     // ------------------------------------------------------------------ TMA producer (one lane)
     if (lane == 0) {
       // packed weights of this class start at row (w_offset / kpad) of the 2-D weight map built per class
-      int kb = 0;
+      int s = 0, it = 0;
       for (int tl = 0; tl < cc.ntaps; ++tl) {
         const int dz = taps_s[4 * tl + 0], dy = taps_s[4 * tl + 1], dx = taps_s[4 * tl + 2];
-        for (int c = 0; c < chunks; ++c, ++kb) {
-          const int s = kb % STAGES;
-          const int it = kb / STAGES;
+        for (int c = 0; c < chunks; ++c) {
           if (it > 0) mbar_wait(empty_bar + 8 * s, (it - 1) & 1);
           const uint32_t a_s = base + s * C::STAGE_BYTES;
           const uint32_t b_s = a_s + A_BYTES;
@@ -121,6 +122,10 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
           mbar_expect_tx(bar, C::STAGE_BYTES);
           tma_load_5d(a_s, &map_a, bar, c * 64, x0 + dx, y0 + dy, z0 + dz, n);
           tma_load_2d(b_s, &map_b, bar, tl * p.in.C + c * 64, cls * p.npad + n0);
+          if (++s == STAGES) {
+            s = 0;
+            ++it;
+          }
         }
       }
     }
@@ -128,9 +133,8 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc_bf16(BN, 0, 0);
+    int s = 0, it = 0;
     for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % STAGES;
-      const int it = kb / STAGES;
       mbar_wait(full_bar + 8 * s, it & 1);
       tc_fence_after();
       if (lane == 0) {
@@ -144,6 +148,10 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
         umma_commit(empty_bar + 8 * s);
       }
       __syncwarp();
+      if (++s == STAGES) {
+        s = 0;
+        ++it;
+      }
     }
     if (lane == 0 && KB > 0) umma_commit(accum_bar);
     __syncwarp();
@@ -155,70 +163,15 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
     tc_fence_after();
   }
   {
-    const int lg = warp & 3;
-    const int half = warp >> 2;
-    const int row = lg * 32 + lane;
+    const int row = (warp & 3) * 32 + lane;
     const int h = row >> tg.tw_shift, w = row & (tg.tw - 1);
     const int qy = y0 + h, qx = x0 + w;
     const bool row_ok = qy < q[1] && qx < q[2];
-    __nv_bfloat16* optr = reinterpret_cast<__nv_bfloat16*>(p.out.ptr);
     int64_t ooff = 0;
     if (row_ok)
       ooff = gb_pix_offset(p.out, n, z0 * p.out_mul[0] + cc.off[0], qy * p.out_mul[1] + cc.off[1],
                            qx * p.out_mul[2] + cc.off[2]);
-    constexpr int CH = (BN >= 64) ? 32 : 16;
-    constexpr int COLS_PER_HALF = (BN >= 64) ? BN / 2 : BN;
-    const bool active = (BN >= 64) || half == 0;
-    if (active) {
-      const int cbeg = (BN >= 64) ? half * COLS_PER_HALF : 0;
-#pragma unroll 1
-      for (int c0 = cbeg; c0 < cbeg + COLS_PER_HALF; c0 += CH) {
-        uint32_t acc[CH];
-        if (KB > 0) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
-          if constexpr (CH == 32) tmem_ld32(taddr, acc); else tmem_ld16(taddr, acc);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int i = 0; i < CH; ++i) acc[i] = 0u;
-        }
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < CH / 8; ++g) {
-            const int col = n0 + c0 + g * 8;
-            if (col < p.out.C) {
-              float v[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float tt = __uint_as_float(acc[g * 8 + e]) + bias_s[c0 + g * 8 + e];
-                if (p.act == GB_ACT_TANH) tt = tanhf(tt);
-                else if (p.act == GB_ACT_LEAKY) tt = tt > 0.f ? tt : tt * p.act_slope;
-                else if (p.act == GB_ACT_RELU) tt = fmaxf(tt, 0.f);
-                v[e] = tt;
-              }
-              if (p.out_fp32) {
-                float4* o32 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out.ptr) + ooff + col);
-                float4 a = make_float4(v[0], v[1], v[2], v[3]), b = make_float4(v[4], v[5], v[6], v[7]);
-                if (p.accumulate) {
-                  const float4 pa = o32[0], pb = o32[1];
-                  a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
-                  b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
-                }
-                o32[0] = a;
-                o32[1] = b;
-              } else {
-                uint4 o;
-                o.x = pack_bf16x2(v[0], v[1]);
-                o.y = pack_bf16x2(v[2], v[3]);
-                o.z = pack_bf16x2(v[4], v[5]);
-                o.w = pack_bf16x2(v[6], v[7]);
-                *reinterpret_cast<uint4*>(optr + ooff + col) = o;
-              }
-            }
-          }
-        }
-      }
-    }
+    gb_conv_epilogue<BN>(p, tmem_base, warp, lane, KB > 0, row_ok, ooff, n0, bias_s, n);
   }
   tc_fence_before();
   __syncthreads();
@@ -312,7 +265,19 @@ int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb
     attr_set = true;
   }
   dim3 grid(tg.ntiles, gb_cdiv(p.ncols, BN), p.nclass);
-  igemm_tma_kernel<BN><<<grid, 256, C::SMEM, st>>>(p, ma, mb, tg);
+  // ring depth: never deeper than the K loop; for narrow tiles on grids of two or more waves a ring of <= ~100 KB
+  // lets two CTAs share an SM, so that one CTA's prologue / epilogue overlaps the other's main loop (the K loops of
+  // the parity-class and first / last layers are only 2..16 blocks long: per-CTA fixed cost dominated them)
+  int kb_max = 1;
+  for (int c = 0; c < p.nclass; ++c) kb_max = p.cls[c].ntaps * (p.in.C >> 6) > kb_max ? p.cls[c].ntaps * (p.in.C >> 6) : kb_max;
+  TileGeom tgl = tg;
+  int ns = C::STAGES < kb_max ? C::STAGES : kb_max;
+  const int64_t ctas = (int64_t)grid.x * grid.y * grid.z;
+  const int shallow = (100 * 1024) / C::STAGE_BYTES;
+  if (BN <= 128 && ctas >= 2 * 148 && kb_max <= 18 && shallow >= 3 && g_gb_knobs[8] == 0) ns = ns < shallow ? ns : shallow;
+  if (ns < 1) ns = 1;
+  tgl.nstages = ns;
+  igemm_tma_kernel<BN><<<grid, 256, ns * C::STAGE_BYTES + 2048, st>>>(p, ma, mb, tgl);
   GB_LAUNCH_CHECK();
   return 0;
 }
@@ -369,13 +334,27 @@ int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st) {
   const int64_t ntiles = (int64_t)tg.ntx * tg.nty * max_ext[0] * p.in.N;
   if (ntiles >= (1ll << 31)) return -1;
   tg.ntiles = (int)ntiles;
-  // tile width: like the gather kernel, shrink BN while the grid under-fills the chip
+  // tile width: the widest BN covering the output channels, then narrower tiles while that lowers the modelled
+  // time  waves(148 SMs) x (K blocks x stage bytes + fixed per-CTA cost).  45 row tiles x 256 columns: BN = 128 is
+  // one wave of 90 CTAs, BN = 64 would be 180 CTAs = two waves (measured 27.6 us vs 14.9 us for the 128-CTA case).
   int bn = 16;
   while (bn < p.ncols && bn < 256) bn *= 2;
   if (g_gb_knobs[1] > 0) {
     bn = g_gb_knobs[1];
   } else {
-    while (bn > 64 && ntiles * p.nclass * gb_cdiv(p.ncols, bn) < 148) bn /= 2;
+    const int64_t kblocks = (int64_t)(kpad / 64);
+    int best_bn = bn;
+    int64_t best_cost = -1;
+    for (int cand = bn; cand >= 64; cand /= 2) {
+      const int64_t ctas = ntiles * p.nclass * gb_cdiv(p.ncols, cand);
+      const int64_t waves = (ctas + 147) / 148;
+      const int64_t cost = waves * (kblocks * (16 + cand / 8) + 500);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_bn = cand;
+      }
+    }
+    bn = best_bn;
   }
   if (bn > p.nclass * p.npad) return -1;  // keep every TMA box inside its tensor
   CUtensorMap ma, mb;

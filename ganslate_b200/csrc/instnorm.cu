@@ -468,6 +468,9 @@ bool same_extents(const gb_view& a, const gb_view& b) {
 
 }  // namespace
 
+int gb_in_fwd_fast(const gb_in_fwd_params& p, cudaStream_t st);  // instnorm_fast.cu: -1 = not covered
+int gb_in_bwd_fast(const gb_in_bwd_params& p, cudaStream_t st);
+
 extern "C" int gb_in_stats(const gb_view* x, float* stats, void* stream) {
   GB_CHECK(x && x->ptr && stats, "gb_in_stats: null pointer");
   GB_CHECK(x->C % 8 == 0 && x->C <= 2048, "gb_in_stats: bad channel count %d", x->C);
@@ -484,6 +487,10 @@ extern "C" int gb_in_fwd(const gb_in_fwd_params* p, void* stream) {
   GB_CHECK(p->res.ptr == nullptr || same_extents(p->x, p->res), "gb_in_fwd: residual extents differ");
   GB_CHECK(p->act != GB_ACT_PRELU || p->prelu != nullptr, "gb_in_fwd: prelu slopes missing");
   GB_CHECK(p->y.pad == 0 || (p->y.H > p->y.pad && p->y.W > p->y.pad), "gb_in_fwd: reflection border larger than image");
+  {
+    const int r = gb_in_fwd_fast(*p, (cudaStream_t)stream);
+    if (r >= 0) return r;
+  }
   Launch L = plan(p->x);
   in_fwd_kernel<<<L.grid, L.threads, 0, (cudaStream_t)stream>>>(*p, L.ppb);
   GB_LAUNCH_CHECK();
@@ -501,6 +508,10 @@ extern "C" int gb_in_bwd(const gb_in_bwd_params* p, void* stream) {
   GB_CHECK(!(p->dbias && p->dprelu && p->stats == nullptr), "gb_in_bwd: dbias and dprelu cannot both be reduced without a norm");
   GB_CHECK(!p->res_before_act || p->res.ptr == nullptr || same_extents(p->x, p->res), "gb_in_bwd: residual extents differ");
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const int r = gb_in_bwd_fast(*p, st);
+    if (r >= 0) return r;
+  }
   Launch L = plan(p->x);
   if (p->stats != nullptr) {
     in_bwd_kernel<0><<<L.grid, L.threads, sizeof(float) * 3 * L.slots * p->x.C, st>>>(*p, L.ppb);

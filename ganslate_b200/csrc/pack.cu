@@ -4,23 +4,49 @@
 
 namespace {
 
-__global__ void pack_kernel(const __grid_constant__ gb_pack_params p) {
-  const int cls = blockIdx.y;
+__device__ __forceinline__ void pack_class(const gb_pack_params& p, int cls, int64_t first, int64_t step) {
   const int kpad = p.kpad[cls];
   const int64_t total = (int64_t)p.rows_pad * kpad;
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.dst) + p.w_offset[cls];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  const int ntaps = p.ntaps[cls], tb = p.tap_begin[cls];
+  for (int64_t i = first; i < total; i += step) {
     const int n = (int)(i / kpad);
     const int k = (int)(i - (int64_t)n * kpad);
     const int tl = k / p.chans_pad;
     const int c = k - tl * p.chans_pad;
     float v = 0.f;
-    if (n < p.rows && tl < p.ntaps[cls] && c < p.chans) {
-      const int t = p.tap_id[p.tap_begin[cls] + tl];
+    if (n < p.rows && tl < ntaps && c < p.chans) {
+      const int t = p.tap_id[tb + tl];
       v = p.src[(int64_t)n * p.sn + (int64_t)c * p.sc + (int64_t)t * p.st];
     }
     dst[i] = __float2bfloat16_rn(v);
   }
+}
+
+// one launch for every convolution of a network: the table lives in device memory (built once per network, the
+// parameter / packed-buffer addresses never change), blockIdx.y selects the entry
+__global__ void pack_multi_kernel(const gb_pack_params* __restrict__ table) {
+  const gb_pack_params& p = table[blockIdx.y];
+  for (int cls = 0; cls < p.nclass; ++cls)
+    pack_class(p, cls, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+}
+
+__global__ void unpack_multi_kernel(const __grid_constant__ gb_unpack_batch b) {
+  const gb_unpack_item& it = b.item[blockIdx.y];
+  const int64_t total = (int64_t)it.rows * it.chans * it.ntaps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % it.ntaps);
+    const int64_t rc = i / it.ntaps;
+    const int c = (int)(rc % it.chans);
+    const int r = (int)(rc / it.chans);
+    const float v = it.dw[(int64_t)r * it.kpad + (int64_t)t * it.chans_pad + c];
+    float* d = it.dst + (int64_t)r * it.dsr + (int64_t)c * it.dsc + (int64_t)t * it.dst_t;
+    *d = it.accumulate ? *d + v : v;
+  }
+}
+
+__global__ void pack_kernel(const __grid_constant__ gb_pack_params p) {
+  pack_class(p, blockIdx.y, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 
 __global__ void unpack_kernel(const float* __restrict__ dw, float* __restrict__ dst, int64_t dsr, int64_t dsc,
@@ -89,6 +115,33 @@ extern "C" int gb_pack_weights(const gb_pack_params* pp, void* stream) {
   if (blocks > 2048) blocks = 2048;
   if (blocks < 1) blocks = 1;
   pack_kernel<<<dim3(blocks, p.nclass), 256, 0, (cudaStream_t)stream>>>(p);
+  GB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int gb_pack_weights_multi(const gb_pack_params* table_dev, int count, int64_t max_elems, void* stream) {
+  GB_CHECK(table_dev && count >= 1 && count <= 65535, "gb_pack_weights_multi: bad table (%d entries)", count);
+  int blocks = (int)((max_elems + 1023) / 1024);
+  if (blocks > 592) blocks = 592;
+  if (blocks < 1) blocks = 1;
+  pack_multi_kernel<<<dim3(blocks, count), 256, 0, (cudaStream_t)stream>>>(table_dev);
+  GB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int gb_unpack_wgrad_multi(const gb_unpack_batch* b, void* stream) {
+  GB_CHECK(b && b->count >= 1 && b->count <= GB_UNPACK_BATCH, "gb_unpack_wgrad_multi: bad item count");
+  int64_t mx = 0;
+  for (int i = 0; i < b->count; ++i) {
+    const gb_unpack_item& it = b->item[i];
+    GB_CHECK(it.dw && it.dst, "gb_unpack_wgrad_multi: null pointer in item %d", i);
+    const int64_t total = (int64_t)it.rows * it.chans * it.ntaps;
+    mx = total > mx ? total : mx;
+  }
+  int blocks = (int)((mx + 1023) / 1024);
+  if (blocks > 592) blocks = 592;
+  if (blocks < 1) blocks = 1;
+  unpack_multi_kernel<<<dim3(blocks, b->count), 256, 0, (cudaStream_t)stream>>>(*b);
   GB_LAUNCH_CHECK();
   return 0;
 }

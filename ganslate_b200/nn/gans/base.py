@@ -116,10 +116,19 @@ class BaseGAN(ABC):
 
     # ------------------------------------------------------------------ CUDA-graph plumbing
     def make_adam(self, params, lr, betas):
-        """torch.optim.Adam as in the reference (cyclegan.py:81-82); capturable when the step is graph-replayed."""
+        """Adam as in the reference (cyclegan.py:81-82): a torch.optim.Adam subclass (same state_dict layout, same
+        scheduler interface) whose step() is one multi-tensor sm_100a launch per 96 parameters.  With CUDA graphs the
+        learning rate lives in a device scalar the captured launch reads.  `train.fused_adam: False` selects
+        torch's own implementation."""
+        if not bool(self.conf[self.conf.mode].get("fused_adam", True)):
+            if self.use_cuda_graph:
+                return torch.optim.Adam(params, lr=torch.tensor(float(lr), device=self.device), betas=betas,
+                                        capturable=True)
+            return torch.optim.Adam(params, lr=lr, betas=betas)
+        from ganslate_b200.optim import FusedAdam
         if self.use_cuda_graph:
-            return torch.optim.Adam(params, lr=torch.tensor(float(lr), device=self.device), betas=betas, capturable=True)
-        return torch.optim.Adam(params, lr=lr, betas=betas)
+            return FusedAdam(params, lr=torch.tensor(float(lr), device=self.device), betas=betas)
+        return FusedAdam(params, lr=lr, betas=betas)
 
     def stage_input(self, name, tensor):
         """Device-resident input. In graph mode the data is copied into a static buffer the graphs read."""

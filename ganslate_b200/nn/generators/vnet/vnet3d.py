@@ -11,7 +11,7 @@ from typing import Tuple
 import torch
 from torch import nn
 
-from ganslate_b200 import configs
+from ganslate_b200 import configs, ops
 from ganslate_b200._cabi import ACT_NONE, ACT_PRELU, ACT_TANH
 from ganslate_b200.nn import invertible, layers
 from ganslate_b200.nn.utils import get_norm_layer_3d, is_bias_before_norm
@@ -29,7 +29,7 @@ class Vnet3DConfig(configs.base.BaseGeneratorConfig):
 
 def _conv_norm_prelu(tape, b, seq, out=None):
     """[conv, norm, PReLU] group."""
-    raw = layers.step_conv(tape, b, seq[0])
+    raw = layers.step_conv(tape, b, seq[0], want_stats=True)
     return layers.step_norm_act(tape, raw, True, ACT_PRELU, 0.0, 0, seq[1].eps, prelu=seq[2], out=out)
 
 
@@ -92,6 +92,8 @@ class Vnet3D(nn.Module):
         if inverse and not self.use_inverse:
             raise ValueError("Trying to perform inverse forward while `use_inverse` flag is turned off.")
         params = list(self.parameters())
+        ops._require_cuda(x, "network input")
+        ops.ensure_packed(self)
         return layers.RunnerFn.apply(lambda tape, b0: self._run(tape, b0, inverse), (id(self), bool(inverse)), x, *params)
 
 
@@ -106,7 +108,7 @@ class InputBlock(nn.Module):
 
     def gb_run(self, tape, b):
         # PReLU(IN(conv(x)) + x repeated over channels)
-        raw = layers.step_conv(tape, b, self.conv1)
+        raw = layers.step_conv(tape, b, self.conv1, want_stats=True)
         rep = layers.step_channel_repeat(tape, b, self.n_repeats)
         return layers.step_norm_act(tape, raw, True, ACT_PRELU, 0.0, 0, self.bn1.eps, residual=rep, prelu=self.relu,
                                     res_before_act=True)
@@ -158,7 +160,7 @@ class UpBlock(nn.Module):
     def gb_run(self, tape, b, skip, inverse=False):
         seq = self.up_conv_ba if inverse else self.up_conv_ab
         half = self.out_channels // 2
-        raw = layers.step_conv(tape, b, seq[0])
+        raw = layers.step_conv(tape, b, seq[0], want_stats=True)
         # torch.cat((up, skipx), 1) without a cat kernel: both halves are written into one buffer
         N, D, H, W, _ = raw.t.shape
         xcat = layers.Buf(torch.empty((N, D, H, W, self.out_channels), dtype=torch.bfloat16, device=raw.t.device), 0,
@@ -181,7 +183,7 @@ class OutBlock(nn.Module):
         self.tanh = layers.Tanh()
 
     def gb_run(self, tape, b):
-        raw = layers.step_conv(tape, b, self.conv1)
+        raw = layers.step_conv(tape, b, self.conv1, want_stats=True)
         a = layers.step_norm_act(tape, raw, True, ACT_PRELU, 0.0, 0, self.bn1.eps, prelu=self.relu1)
         return layers.step_conv(tape, a, self.conv2)  # tanh is evaluated in fp32 while exporting
 

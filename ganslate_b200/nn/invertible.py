@@ -59,7 +59,7 @@ class InvertibleSequence(nn.Module):
 def _branch(tape, src, seq, residual, out, out_scale):
     """out = residual + out_scale * PReLU(IN(conv(src)))   with seq = [conv, norm, PReLU]"""
     conv, norm, prelu = seq[0], seq[1], seq[2]
-    raw = layers.step_conv(tape, src, conv)
+    raw = layers.step_conv(tape, src, conv, want_stats=True)
     layers.step_norm_act(tape, raw, True, ACT_PRELU, 0.0, 0, norm.eps, residual=residual, prelu=prelu,
                          out_scale=out_scale, out=out)
 

@@ -124,7 +124,7 @@ class Storage:
 
 class Buf:
     """Channel slice [c0, c0 + cw) of a Storage; `channels` logical channels (cw = channels rounded up to 8)."""
-    __slots__ = ("st", "c0", "cw", "channels", "is_3d", "needs_grad_flag", "want_dbias", "dbias")
+    __slots__ = ("st", "c0", "cw", "channels", "is_3d", "needs_grad_flag", "want_dbias", "dbias", "stats")
 
     def __init__(self, t, pad, channels, is_3d, raw=False, st=None, c0=0, cw=None):
         self.st = st if st is not None else Storage(t, pad, raw)
@@ -134,6 +134,7 @@ class Buf:
         self.needs_grad_flag = True  # False only for a network input that does not require grad
         self.want_dbias = False      # the producing conv's bias needs a gradient (fused into the consumer's backward)
         self.dbias = None
+        self.stats = None            # InstanceNorm statistics written by the producing convolution's epilogue
 
     # -- forward-side accessors
     @property
@@ -198,17 +199,22 @@ class Tape:
         self.param_needs_grad = param_needs_grad  # {id(param): bool}
         self.input_needs_grad = input_needs_grad
         self.param_grads = {}
+        self.unpack = ops.UnpackQueue()  # weight-gradient workspaces -> PyTorch layout, one launch per pass
 
     def needs(self, p):
         return p is not None and self.param_needs_grad.get(id(p), False)
 
     def add_param_grad(self, p, g):
         k = id(p)
-        self.param_grads[k] = g if k not in self.param_grads else self.param_grads[k] + g
+        if k in self.param_grads:
+            self.unpack.flush()  # the earlier contribution may still be waiting in the queue
+            g = self.param_grads[k] + g
+        self.param_grads[k] = g
 
     def backward(self):
         for step in reversed(self.steps):
             step()
+        self.unpack.flush()
 
 
 def _is_norm(m):
@@ -248,14 +254,17 @@ def flatten_modules(mods) -> List[nn.Module]:
 
 
 # ------------------------------------------------------------------------------------------------ fused steps
-def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0) -> Buf:
+def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0, want_stats=False) -> Buf:
     """conv (+bias, + optional epilogue activation) reading the whole (bordered) allocation of `b`'s channel slice.
-    Output: raw Buf (act NONE) or activation Buf."""
+    Output: raw Buf (act NONE) or activation Buf.  want_stats: an InstanceNorm follows -- its statistics are
+    accumulated by the convolution epilogue (Buf.stats) instead of a separate pass over the output."""
     op = m.conv_op()
     dev = b.t.device
     ops._require_cuda(b.t, "convolution input")
-    y = op.run_fwd(b.plain_view(), dev, m.weight, m.bias, act, slope)
+    stats = ops.zeros((b.t.shape[0], op.cout_pad, 2), dev) if (want_stats and act == ACT_NONE) else None
+    y = op.run_fwd(b.plain_view(), dev, m.weight, m.bias, act, slope, stats=stats)
     out = Buf(y, 0, m.out_channels, b.is_3d, raw=(act == ACT_NONE))
+    out.stats = stats
     weight, bias = m.weight, m.bias
     out.want_dbias = tape is not None and tape.needs(bias)
     b.st.consumers += 1
@@ -273,7 +282,7 @@ def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0) -> Buf:
             g = ops.act_backward(ops.make_view(g), y, act, slope, dbias=db)  # fp32 d_buf -> bf16 d_raw (+ bias grad)
         gv = ops.make_view(g)
         if tape.needs(weight):
-            tape.add_param_grad(weight, op.run_wgrad(b.plain_view(), gv, weight.shape, dev))
+            tape.add_param_grad(weight, op.run_wgrad(b.plain_view(), gv, weight.shape, dev, pending=tape.unpack))
         if tape.needs(bias):
             tape.add_param_grad(bias, db[:op.cout] if db is not None else ops.colsum(g, op.cout))
         if b.needs_grad_flag:
@@ -315,7 +324,8 @@ def step_norm_act(tape: Tape, x: Buf, norm: bool, act: int, slope: float, out_pa
     else:
         slopes_p = slopes.detach() if slopes is not None else None
     stats = ops.norm_act_forward(x.view(), out.view(), residual.view() if residual is not None else None, norm, act,
-                                 slope, eps, dev, prelu=slopes_p, res_before_act=res_before_act, out_scale=out_scale)
+                                 slope, eps, dev, prelu=slopes_p, res_before_act=res_before_act, out_scale=out_scale,
+                                 stats=x.stats if (norm and x.full) else None)
     x.st.consumers += 1
     if residual is not None:
         residual.st.consumers += 1
@@ -407,7 +417,7 @@ def run_sequence(tape: Tape, mods: Sequence[nn.Module], b: Buf, final_pad: int =
             res = residual if (j >= n and residual is not None) else None
             tap_raw = i in taps and (norm or act is not None)
             if norm or res is not None or nxt > 0 or tap_raw:
-                raw = step_conv(tape, b, m)
+                raw = step_conv(tape, b, m, want_stats=norm)
                 if i in taps:
                     sink.append((i, raw, False))
                 b = step_norm_act(tape, raw, norm, act_id, slope, nxt, mods[i + 1].eps if norm else 1e-5, res)
@@ -555,6 +565,8 @@ def run_network(net: nn.Module, mods: Sequence[nn.Module], x: torch.Tensor) -> t
     """NC(D)HW fp32 in -> NC(D)HW fp32 out through the fused kernels (a trailing nn.Tanh is evaluated in fp32
     while the result is exported)."""
     params = [p for p in net.parameters()]
+    ops._require_cuda(x, "network input")
+    ops.ensure_packed(net)
     return NetworkFn.apply(flatten_modules(mods), x, *params)
 
 
@@ -613,4 +625,6 @@ def run_encoder(net: nn.Module, mods: Sequence[nn.Module], x: torch.Tensor, taps
     """Features of `x` after the modules `taps` of the list `mods` (same semantics as iterating the layers and
     recording `feat` after index i, including the in-place activation effect)."""
     params = [p for p in net.parameters()]
+    ops._require_cuda(x, "network input")
+    ops.ensure_packed(net)
     return list(EncoderFn.apply(list(mods), tuple(taps), x, *params))

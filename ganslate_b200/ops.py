@@ -204,6 +204,19 @@ class ConvOp:
         self.wg_kpad = max(64, (self.T * g_pad + 63) // 64 * 64)
         self.wg_rows = cin if transposed else cout
         self.wg_rows_pad = (self.wg_rows + 127) // 128 * 128
+        # Operand swap for unit-stride convolutions with few output channels (the generators' last 7x7 -> 3 layer,
+        # PatchGAN's -> 1 layer): rows of the gradient matrix come from the INPUT channels and the columns are
+        # (tap, output channel) gathered through the negated taps,
+        #   dW'[c][t*cout_pad + r] = sum_q' x[q'][c] * dOut[q' - d_t][r],
+        # which wastes pad128(cin) x pad64(T*cout_pad) MMA work instead of pad128(cout) x pad64(T*cin_pad).
+        self.wg_swap = False
+        if not transposed and all(s == 1 for s in self.stride):
+            sw_kpad = max(64, (self.T * self.cout_pad + 63) // 64 * 64)
+            sw_rows_pad = (cin + 127) // 128 * 128
+            if sw_rows_pad * sw_kpad * 2 <= self.wg_rows_pad * self.wg_kpad:
+                self.wg_swap = True
+                self.wg_kpad, self.wg_rows, self.wg_rows_pad = sw_kpad, cin, sw_rows_pad
+                self.wg_taps = [tuple(-v for v in t) for t in self.wg_taps]
         self._packed = {}
 
     # ------------------------------------------------------------------ shapes
@@ -223,16 +236,21 @@ class ConvOp:
         return 2.0 * batch * ext[0] * ext[1] * ext[2] * self.cin * self.cout * self.T
 
     # ------------------------------------------------------------------ packing
-    def packed(self, weight: torch.Tensor, which: str) -> torch.Tensor:
-        key = (which, weight.data_ptr(), weight._version, weight.device)
+    def _pack_key(self, weight, which):
+        return (which, weight.data_ptr(), weight._version, weight.device)
+
+    def pack_params(self, weight: torch.Tensor, which: str):
+        """(gb_pack_params, destination buffer) of one orientation; the destination is allocated once."""
         hit = self._packed.get(which)
-        if hit is not None and hit[0] == key:
-            return hit[1]
         spec = self.fwd if which == "fwd" else self.dgrad
         rows, rows_pad = (self.cout, self.fwd_rows_pad) if which == "fwd" else (self.cin, self.dgrad_rows_pad)
         chans, chans_pad = (self.cin, self.cin_pad) if which == "fwd" else (self.cout, self.cout_pad)
         sn, sc, st = self.fwd_strides if which == "fwd" else self.dgrad_strides
-        dst = hit[1] if hit is not None else torch.empty(spec.total_elems, dtype=torch.bfloat16, device=weight.device)
+        if hit is not None and hit[1].device == weight.device:
+            dst = hit[1]
+        else:
+            dst = torch.empty(spec.total_elems, dtype=torch.bfloat16, device=weight.device)
+            self._packed[which] = (None, dst)
         w = weight.detach()
         assert w.is_contiguous() and w.dtype == torch.float32
         p = PackParams()
@@ -246,6 +264,14 @@ class ConvOp:
             for j, t in enumerate(c["tap_ids"]):
                 p.tap_id[tb + j] = t
             tb += len(c["taps"])
+        return p, dst, rows_pad * max(spec.kpads)
+
+    def packed(self, weight: torch.Tensor, which: str) -> torch.Tensor:
+        key = self._pack_key(weight, which)
+        hit = self._packed.get(which)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        p, dst, _ = self.pack_params(weight, which)
         _cabi.check(_cabi.lib().gb_pack_weights(C.byref(p), _stream()), "gb_pack_weights")
         self._packed[which] = (key, dst)
         return dst
@@ -272,8 +298,10 @@ class ConvOp:
             cache[which] = p
         return cache[which]
 
-    def run_fwd(self, xv: View, device, weight, bias, act=ACT_NONE, slope=0.0):
-        """xv: plain view (N,D,H,W,cin_pad) of the input (any border is part of it) -> new (N,D,Ho,Wo,cout_pad)."""
+    def run_fwd(self, xv: View, device, weight, bias, act=ACT_NONE, slope=0.0, stats=None):
+        """xv: plain view (N,D,H,W,cin_pad) of the input (any border is part of it) -> new (N,D,Ho,Wo,cout_pad).
+        stats: optional zeroed fp32 (N, cout_pad, 2) that receives the InstanceNorm statistics of the output
+        (sum, sum of squares per image and channel) from the convolution epilogue."""
         assert xv.C == self.cin_pad and xv.pad == 0, (xv.C, self.cin_pad, xv.pad)
         od, oh, ow = self.out_extent((xv.D, xv.H, xv.W))
         y = torch.empty((xv.N, od, oh, ow, self.cout_pad), dtype=torch.bfloat16, device=device)
@@ -285,6 +313,7 @@ class ConvOp:
         p.ncols, p.npad = self.cout, self.fwd_rows_pad
         p.act, p.act_slope = act, slope
         p.out_fp32, p.accumulate = 0, 0
+        p.stats = stats.data_ptr() if stats is not None else None
         _call("conv_fwd", self.flops((xv.D, xv.H, xv.W), xv.N), "flop", "gb_conv_data(fwd)", _cabi.lib().gb_conv_data,
               C.byref(p), _stream())
         return y
@@ -295,6 +324,7 @@ class ConvOp:
         assert dyv.C == self.cout_pad and outv.C == self.cin_pad and outv.pad == 0
         p = self._params("dgrad")
         p.out_fp32, p.accumulate = 1, 1 if accumulate else 0
+        p.stats = None
         p.inp, p.out = dyv, outv
         wp = self.packed(weight, "dgrad")
         p.wpacked = wp.data_ptr()
@@ -304,9 +334,25 @@ class ConvOp:
         _call("conv_dgrad", self.flops((outv.D, outv.H, outv.W), outv.N), "flop", "gb_conv_data(dgrad)",
               _cabi.lib().gb_conv_data, C.byref(p), _stream())
 
-    def run_wgrad(self, xv: View, dyv: View, weight_shape, device):
+    def wgrad_plan(self):
+        """Host-side description of the weight-gradient GEMM (include/ganslate_b200.h, gb_wgrad_params) and of the
+        copy of its fp32 workspace into the PyTorch weight layout; tests/test_host_logic.py evaluates it literally."""
+        if self.wg_swap:
+            # workspace rows = input channel c, columns = (tap, output channel r); weight layout (cout, cin, T)
+            cols, cols_pad, dsr, dsc = self.cout, self.cout_pad, self.T, self.cin * self.T
+        else:
+            cols = self.cout if self.transposed else self.cin
+            cols_pad = self.cout_pad if self.transposed else self.cin_pad
+            dsr, dsc = cols * self.T, self.T
+        return dict(plain_is_input=self.transposed or self.wg_swap, taps=self.wg_taps, mul=self.stride,
+                    rows=self.wg_rows, rows_pad=self.wg_rows_pad, kpad=self.wg_kpad,
+                    unpack=dict(dsr=dsr, dsc=dsc, dst_t=1, rows=self.wg_rows, chans=cols, chans_pad=cols_pad,
+                                ntaps=self.T, kpad=self.wg_kpad))
+
+    def run_wgrad(self, xv: View, dyv: View, weight_shape, device, pending=None):
         """fp32 weight gradient in the PyTorch layout of `weight_shape` (xv: plain input view, dyv: bf16 d_raw)."""
-        plain, gathered = (xv, dyv) if self.transposed else (dyv, xv)
+        plan = self.wgrad_plan()
+        plain, gathered = (xv, dyv) if plan["plain_is_input"] else (dyv, xv)
         ws = zeros((self.wg_rows_pad, self.wg_kpad), device)
         cache = self.__dict__.setdefault("_ptemplates", {})
         p = cache.get("wgrad")
@@ -323,11 +369,94 @@ class ConvOp:
         _call("conv_wgrad", self.flops((xv.D, xv.H, xv.W), xv.N), "flop", "gb_conv_wgrad",
               _cabi.lib().gb_conv_wgrad, C.byref(p), _stream())
         dw = torch.empty(weight_shape, dtype=torch.float32, device=device)
-        cols = self.cout if self.transposed else self.cin
-        cols_pad = self.cout_pad if self.transposed else self.cin_pad
-        _cabi.check(_cabi.lib().gb_unpack_wgrad(ws.data_ptr(), dw.data_ptr(), cols * self.T, self.T, 1, self.wg_rows, cols,
-                                                cols_pad, self.T, self.wg_kpad, _stream()), "gb_unpack_wgrad")
+        u = plan["unpack"]
+        if pending is not None:
+            # the workspace -> PyTorch-layout copies of a whole backward pass go out in one launch (UnpackQueue)
+            pending.add(ws, dw, u["dsr"], u["dsc"], u["dst_t"], u["rows"], u["chans"], u["chans_pad"], u["ntaps"], u["kpad"])
+            return dw
+        _cabi.check(_cabi.lib().gb_unpack_wgrad(ws.data_ptr(), dw.data_ptr(), u["dsr"], u["dsc"], u["dst_t"], u["rows"],
+                                                u["chans"], u["chans_pad"], u["ntaps"], u["kpad"], _stream()),
+                    "gb_unpack_wgrad")
         return dw
+
+
+class UnpackQueue:
+    """Weight-gradient workspaces waiting for their copy into the PyTorch layout; flush() issues ONE launch per
+    GB_UNPACK_BATCH entries (the batch travels by value as a kernel parameter: CUDA-graph safe)."""
+
+    def __init__(self):
+        self.batch = _cabi.UnpackBatch()
+        self.keep = []
+
+    def add(self, ws, dw, dsr, dsc, dst_t, rows, chans, chans_pad, ntaps, kpad, accumulate=False):
+        if self.batch.count == _cabi.GB_UNPACK_BATCH:
+            self.flush()
+        it = self.batch.item[self.batch.count]
+        it.dw, it.dst, it.dsr, it.dsc, it.dst_t = ws.data_ptr(), dw.data_ptr(), dsr, dsc, dst_t
+        it.rows, it.chans, it.chans_pad, it.ntaps, it.kpad, it.accumulate = (rows, chans, chans_pad, ntaps, kpad,
+                                                                             1 if accumulate else 0)
+        self.batch.count += 1
+        self.keep.append((ws, dw))
+
+    def flush(self):
+        if self.batch.count:
+            _call("unpack", 0, "byte", "gb_unpack_wgrad_multi", _cabi.lib().gb_unpack_wgrad_multi, C.byref(self.batch),
+                  _stream())
+            self.batch.count = 0
+            self.keep = []
+
+
+class PackGroup:
+    """Every packed (bf16, class-matrix) weight of one network, refreshed by ONE launch when any parameter changed.
+    The table of gb_pack_params lives in device memory; it is rebuilt only when a parameter moved."""
+
+    def __init__(self, convs):
+        self.convs = list(convs)  # [(ConvOp, weight Parameter)]
+        self.table = None
+        self.ptrs = None
+
+    def _build(self):
+        entries, self.items, mx = [], [], 0
+        for op, w in self.convs:
+            for which in ("fwd", "dgrad"):
+                p, dst, n = op.pack_params(w, which)
+                entries.append(bytes(p))
+                self.items.append((op, w, which, dst))
+                mx = max(mx, n)
+        dev = self.convs[0][1].device
+        self.table = torch.frombuffer(bytearray(b"".join(entries)), dtype=torch.uint8).to(dev)
+        self.max_elems = mx
+        self.ptrs = [w.data_ptr() for _, w in self.convs]
+
+    def refresh(self):
+        if not self.convs:
+            return
+        if self.ptrs is None or self.ptrs != [w.data_ptr() for _, w in self.convs]:
+            self._build()
+        stale = False
+        for op, w, which, dst in self.items:
+            hit = op._packed.get(which)
+            if hit is None or hit[0] != op._pack_key(w, which) or hit[1] is not dst:
+                stale = True
+                break
+        if not stale:
+            return
+        _call("pack", 0, "byte", "gb_pack_weights_multi", _cabi.lib().gb_pack_weights_multi, self.table.data_ptr(),
+              len(self.items), self.max_elems, _stream())
+        for op, w, which, dst in self.items:
+            op._packed[which] = (op._pack_key(w, which), dst)
+
+
+def ensure_packed(net):
+    """Refresh the packed weights of every convolution of `net` (one launch, only when a parameter changed)."""
+    g = net.__dict__.get("_gb_pack_group")
+    if g is None:
+        convs = [(m.conv_op(), m.weight) for m in net.modules() if hasattr(m, "conv_op")]
+        for _, w in convs:
+            _require_cuda(w, "network parameters")
+        g = PackGroup(convs)
+        net.__dict__["_gb_pack_group"] = g
+    g.refresh()
 
 
 def colsum(t: torch.Tensor, n: int) -> torch.Tensor:
@@ -355,12 +484,13 @@ def act_backward(dyv: View, y: torch.Tensor, act: int, slope: float, dbias=None)
 
 
 def norm_act_forward(xv: View, yv: View, resv, norm, act, slope, eps, device, prelu=None, res_before_act=False,
-                     out_scale=1.0):
+                     out_scale=1.0, stats=None):
     """yv <- [out_scale *] act(instance_norm(xv) [+ res]) [+ res] incl. the reflection border of yv. Returns stats."""
     lib = _cabi.lib()
-    stats = None
     nbytes = xv.N * xv.D * xv.H * xv.W * xv.C * 2
-    if norm:
+    if not norm:
+        stats = None
+    elif stats is None:
         stats = zeros((xv.N, xv.C, 2), device)
         _call("in_stats", nbytes, "byte", "gb_in_stats", lib.gb_in_stats, C.byref(xv), stats.data_ptr(), _stream())
     p = InFwdParams()
@@ -392,7 +522,7 @@ def norm_act_backward(xv: View, stats, dyv: View, dxv: View, norm, act, slope, e
                                                                    1 if dx_fp32_acc else 0, out_scale)
     if need_dx:
         if norm:
-            bstats = zeros((xv.N, xv.C, 2), device)
+            bstats = zeros((xv.N * xv.C * 2 + 4,), device)  # + grid-barrier words of the single-launch path
             p.stats, p.bstats = stats.data_ptr(), bstats.data_ptr()
         elif yv is not None:
             p.y = yv

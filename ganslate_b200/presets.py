@@ -64,3 +64,42 @@ def cut_resnet2d(batch_size=1, n_residual_blocks=9, **train_overrides):
     }
     conf["train"].update(train_overrides)
     return init_config(conf)
+
+
+def _vnet3d_conf(target, channels, use_inverse, batch_size, first_layer_channels, down_blocks, up_blocks, ndf, n_layers,
+                 train_overrides):
+    conf = {
+        "mode": "train",
+        "train": {
+            "batch_size": batch_size, "cuda": True, "mixed_precision": False, "n_iters": 200000, "n_iters_decay": 0,
+            "gan": {
+                "_target_": target,
+                "pool_size": 50,
+                "generator": {"_target_": "ganslate_b200.nn.generators.Vnet3D", "use_memory_saving": False,
+                              "use_inverse": use_inverse, "first_layer_channels": first_layer_channels,
+                              "down_blocks": list(down_blocks), "up_blocks": list(up_blocks),
+                              "in_out_channels": {"AB": [channels, channels]}},
+                "discriminator": {"_target_": "ganslate_b200.nn.discriminators.PatchGAN3D", "n_layers": n_layers,
+                                  "ndf": ndf, "kernel_size": [4, 4, 4], "in_channels": {"B": channels}},
+                "optimizer": {"lambda_AB": 10.0, "lambda_BA": 10.0, "lambda_identity": 0.0, "proportion_ssim": 0.0,
+                              "lr_D": 0.0002, "lr_G": 0.0002},
+            },
+        },
+    }
+    conf["train"].update(train_overrides)
+    return init_config(conf)
+
+
+def cyclegan_vnet3d(channels=1, batch_size=1, first_layer_channels=16, down_blocks=(1, 2, 3, 2), up_blocks=(2, 2, 1, 1),
+                    ndf=64, n_layers=3, **train_overrides):
+    """BASELINE config 4: CycleGAN with two Vnet3D generators (invertible layers disabled) + PatchGAN3D on
+    1x32x256x256 CBCT -> CT shaped patches (projects/maastro_lung_proton_cbct_to_ct)."""
+    return _vnet3d_conf("ganslate_b200.nn.gans.unpaired.CycleGAN", channels, False, batch_size, first_layer_channels,
+                        down_blocks, up_blocks, ndf, n_layers, train_overrides)
+
+
+def revgan_vnet3d(channels=4, batch_size=1, first_layer_channels=16, down_blocks=(1, 2, 3, 2), up_blocks=(2, 2, 1, 1),
+                  ndf=64, n_layers=3, **train_overrides):
+    """BASELINE config 5: RevGAN, one partially invertible Vnet3D (use_inverse) + PatchGAN3D on 4x128^3 patches."""
+    return _vnet3d_conf("ganslate_b200.nn.gans.unpaired.RevGAN", channels, True, batch_size, first_layer_channels,
+                        down_blocks, up_blocks, ndf, n_layers, train_overrides)

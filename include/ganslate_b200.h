@@ -76,6 +76,9 @@ typedef struct gb_conv_params {
   float act_slope;
   int32_t out_fp32;          /* 1: `out` is an fp32 view (activation gradients are carried in fp32) */
   int32_t accumulate;        /* 1: out += result (fp32 only; residual branches share one gradient buffer) */
+  float* stats;              /* optional [N][out.C][2] fp32 (zeroed by the caller): the epilogue adds (sum, sum^2) of the
+                                bf16-rounded outputs per (image, channel) -- the InstanceNorm statistics of the
+                                layer that follows, so no separate pass reads the tensor (bf16 output only) */
 } gb_conv_params;
 
 int gb_conv_data(const gb_conv_params* p, void* stream);
@@ -117,9 +120,29 @@ typedef struct gb_pack_params {
 
 int gb_pack_weights(const gb_pack_params* p, void* stream);
 
+/* Every convolution of a network in ONE launch: `table_dev` is an array of `count` gb_pack_params in DEVICE
+ * memory (parameter and packed-buffer addresses are stable, so the host builds it once per network);
+ * max_elems = largest rows_pad*kpad of any class (sizes the grid). */
+int gb_pack_weights_multi(const gb_pack_params* table_dev, int count, int64_t max_elems, void* stream);
+
 /* dst[r*dsr + c*dsc + t*dst_t] = scale * dw[r][t*chans_pad + c]   (fp32 -> fp32, PyTorch layout) */
 int gb_unpack_wgrad(const float* dw, float* dst, int64_t dsr, int64_t dsc, int64_t dst_t, int rows,
                     int chans, int chans_pad, int ntaps, int kpad, void* stream);
+
+/* The weight gradients of a whole backward pass in one launch (the batch is passed by value, so the call can be
+ * captured in a CUDA graph).  accumulate=1: dst += (a parameter used twice in one pass). */
+#define GB_UNPACK_BATCH 56
+typedef struct gb_unpack_item {
+  const float* dw;
+  float* dst;
+  int64_t dsr, dsc, dst_t;
+  int32_t rows, chans, chans_pad, ntaps, kpad, accumulate;
+} gb_unpack_item;
+typedef struct gb_unpack_batch {
+  int32_t count, pad_;
+  gb_unpack_item item[GB_UNPACK_BATCH];
+} gb_unpack_batch;
+int gb_unpack_wgrad_multi(const gb_unpack_batch* b, void* stream);
 
 /* per-channel sum over all pixels of a bf16 view -> fp32 out[C] (bias gradients). out is overwritten. */
 int gb_colsum(const gb_view* x, float* out, void* stream);
@@ -155,7 +178,8 @@ typedef struct gb_in_bwd_params {
   gb_view dy_sum;            /* optional FP32: dy_a + fold(dy_b) is written here (residual chain); ptr NULL: skip */
   gb_view dx;                /* gradient wrt x (bf16) */
   const float* stats;        /* forward stats; NULL = no normalisation */
-  float* bstats;             /* [N][C][2] workspace (sum g, sum g*xhat), zeroed by caller */
+  float* bstats;             /* [N][C][2] workspace (sum g, sum g*xhat) followed by 4 spare words, all zeroed by the
+                                caller (the spare words hold the grid-barrier counter of the single-launch path) */
   const float* prelu;
   float* dprelu;             /* [C] fp32 accumulated (zeroed by caller) or NULL */
   float* dbias;              /* [C] fp32 accumulated sum of dx over pixels = gradient of the conv bias that feeds x
@@ -196,6 +220,29 @@ int gb_patchnce_fwd(const float* q, const float* k, int B, int P, int D, float T
                     void* stream);
 int gb_patchnce_bwd(const float* k, const float* probs, const float* dloss, int B, int P, int D, float T, float* dq,
                     void* stream);
+
+/* ---- optimizer -------------------------------------------------------------------------------
+ * Multi-tensor Adam step with torch.optim.Adam semantics (betas, eps; no weight decay / amsgrad), replacing the
+ * optimizer.step() calls at ganslate/nn/gans/unpaired/cyclegan.py:108,121 (optimizers built at :76-82).
+ * `lr` and `step` are DEVICE pointers (one float each; step already holds this step's count) so the launch can be
+ * replayed in a CUDA graph.  The batch travels by value. */
+#define GB_ADAM_BATCH 96
+typedef struct gb_adam_item {
+  float* p;                  /* parameter (fp32 master) */
+  const float* g;            /* gradient */
+  float* m;                  /* exp_avg */
+  float* v;                  /* exp_avg_sq */
+  int32_t n;                 /* elements */
+  int32_t vec4;              /* 1: all four pointers are 16-byte aligned */
+} gb_adam_item;
+typedef struct gb_adam_batch {
+  const float* lr;
+  const float* step;
+  float beta1, beta2, eps;
+  int32_t count;
+  gb_adam_item item[GB_ADAM_BATCH];
+} gb_adam_batch;
+int gb_adam_multi(const gb_adam_batch* b, void* stream);
 
 /* ---- misc ---- */
 int gb_version(void);

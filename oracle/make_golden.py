@@ -92,9 +92,35 @@ def reference_cyclegan_step(size, n_blocks, seed=0, data_seed=1, batch=1, lambda
     }
 
 
+def reference_3d_small():
+    """Reference Vnet3D (both directions, over the memcnn stand-in) and PatchGAN3D on a 1x1x8x16x16 volume (PatchGAN3D: 1x1x16x16x16):
+    outputs and input gradients of sum(y^2)."""
+    m = R.modules()
+    g = m["Vnet3D"](1, 1, "instance", first_layer_channels=8, down_blocks=(1, 1), up_blocks=(1, 1),
+                    use_memory_saving=False, use_inverse=True)
+    torch.manual_seed(0)
+    m["init_weights"](g, "normal", 0.02)
+    d = m["PatchGAN3D"](1, 16, 2, (4, 4, 4), "instance")
+    torch.manual_seed(0)
+    m["init_weights"](d, "normal", 0.02)
+    gen = torch.Generator().manual_seed(3)
+    x = (torch.rand((1, 1, 8, 16, 16), generator=gen) * 2 - 1).requires_grad_(True)
+    out = {"vnet_keys": list(g.state_dict().keys()), "patchgan_keys": list(d.state_dict().keys()), "vnet": {}}
+    for inverse in (False, True):
+        y = g(x, inverse=inverse)
+        (gx,) = torch.autograd.grad(y.square().sum(), x)
+        out["vnet"][str(inverse)] = {"y": tensor_digest(y), "dx": tensor_digest(gx)}
+    xd = torch.rand((1, 1, 16, 16, 16), generator=gen) * 2 - 1
+    out["patchgan"] = {"y": tensor_digest(d(xd))}
+    return out
+
+
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "vnet3d_patchgan3d_small.json"), "w") as f:
+        json.dump(reference_3d_small(), f)
+    print("vnet3d_patchgan3d_small written")
     cases = {"cyclegan_step_32px_2blk": dict(size=32, n_blocks=2),
              "cyclegan_step_64px_3blk_idt": dict(size=64, n_blocks=3, lambda_identity=0.5, batch=2)}
     for name, kw in cases.items():

@@ -36,9 +36,9 @@ def test_struct_sizes_match_header():
     import subprocess
     import tempfile
     from ganslate_b200 import _cabi
-    src = '#include <stdio.h>\n#include "ganslate_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",' \
+    src = '#include <stdio.h>\n#include "ganslate_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(gb_view),sizeof(gb_conv_class),sizeof(gb_conv_params),sizeof(gb_wgrad_params),sizeof(gb_pack_params),' \
-          'sizeof(gb_in_fwd_params),sizeof(gb_in_bwd_params));return 0;}\n'
+          'sizeof(gb_in_fwd_params),sizeof(gb_in_bwd_params),sizeof(gb_unpack_item),sizeof(gb_unpack_batch),sizeof(gb_adam_item),sizeof(gb_adam_batch));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         open(c, "w").write(src)
@@ -46,7 +46,7 @@ def test_struct_sizes_match_header():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     mine = [ctypes.sizeof(t) for t in (_cabi.View, _cabi.ConvClass, _cabi.ConvParams, _cabi.WgradParams, _cabi.PackParams,
-                                       _cabi.InFwdParams, _cabi.InBwdParams)]
+                                       _cabi.InFwdParams, _cabi.InBwdParams, _cabi.UnpackItem, _cabi.UnpackBatch, _cabi.AdamItem, _cabi.AdamBatch)]
     assert sizes == mine
 
 

@@ -81,6 +81,53 @@ def test_specs_reproduce_torch_convolutions(case):
         assert flat[n * sn + c * sc + t * st].item() == pytest.approx(dg_w(t)[n, c])
 
 
+def emulate_wgrad(op, x, g):
+    """Evaluate ConvOp.wgrad_plan() literally as include/ganslate_b200.h defines gb_conv_wgrad and gb_unpack_wgrad:
+    dw[r][t*Cg + c] = sum_q plain[q][r] * gathered[q*mul + d_t][c] (zero outside), then
+    dst[r*dsr + c*dsc + t*dst_t] = dw[r][t*chans_pad + c]."""
+    plan = op.wgrad_plan()
+    xn, gn = x.numpy().astype(np.float64), g.numpy().astype(np.float64)
+    plain, gathered = (xn, gn) if plan["plain_is_input"] else (gn, xn)
+    u = plan["unpack"]
+    Cg_pad = u["chans_pad"]
+    dw = np.zeros((plan["rows_pad"], plan["kpad"]))
+    N, _, D, H, W = plain.shape
+    ext_g = gathered.shape[2:]
+    for q in itertools.product(range(D), range(H), range(W)):
+        for t, tap in enumerate(plan["taps"]):
+            i = tuple(q[d] * plan["mul"][d] + tap[d] for d in range(3))
+            if all(0 <= i[d] < ext_g[d] for d in range(3)):
+                # [rows] x [gathered channels], summed over the batch
+                blk = plain[:, :, q[0], q[1], q[2]].T @ gathered[:, :, i[0], i[1], i[2]]
+                dw[:blk.shape[0], t * Cg_pad:t * Cg_pad + blk.shape[1]] += blk
+    dst = np.zeros(op.cout * op.cin * op.T)
+    for r in range(u["rows"]):
+        for c in range(u["chans"]):
+            for t in range(u["ntaps"]):
+                dst[r * u["dsr"] + c * u["dsc"] + t * u["dst_t"]] = dw[r, t * Cg_pad + c]
+    return dst
+
+
+@pytest.mark.parametrize("cin,cout,k,s,p,tr", [
+    (3, 5, (1, 3, 3), (1, 1, 1), (0, 1, 1), False),
+    (3, 5, (1, 4, 4), (1, 2, 2), (0, 1, 1), False),
+    (40, 3, (1, 3, 3), (1, 1, 1), (0, 0, 0), False),    # few output channels: operand swap
+    (136, 1, (1, 4, 4), (1, 1, 1), (0, 1, 1), False),   # PatchGAN's last layer shape class: operand swap
+    (5, 3, (1, 3, 3), (1, 2, 2), (0, 1, 1), True),
+])
+def test_wgrad_plan_reproduces_torch_weight_gradient(cin, cout, k, s, p, tr):
+    torch.manual_seed(0)
+    op = ops.ConvOp(cin, cout, k, s, p, transposed=tr, output_padding=(0, 1, 1) if tr else (0, 0, 0))
+    x = torch.randn(2, cin, 1, 6, 5)
+    w = (torch.randn((cin, cout) + k) if tr else torch.randn((cout, cin) + k)).requires_grad_(True)
+    y = F.conv_transpose3d(x, w, None, s, p, (0, 1, 1)) if tr else F.conv3d(x, w, None, s, p)
+    g = torch.randn_like(y)
+    (dw,) = torch.autograd.grad(y, w, g)
+    got = emulate_wgrad(op, x, g)
+    np.testing.assert_allclose(got, dw.numpy().reshape(-1), rtol=1e-4, atol=1e-4)
+    assert op.wg_swap == (cout <= 3 and not tr and s == (1, 1, 1) and cin >= 40)
+
+
 def test_spec_padding_and_limits():
     op = ops.ConvOp(3, 64, (1, 7, 7), (1, 1, 1), (0, 0, 0))
     assert op.cin_pad == 8 and op.fwd.kpads == [448] and op.wg_kpad == 448

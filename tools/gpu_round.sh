@@ -25,14 +25,19 @@ launches)
      python bench.py --batch $B --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-roofline > $out/launches_run.log 2>&1
   python tools/launch_summary.py $out/launches_b$B.csv 5 --md > $out/launch_summary_b$B.md 2>&1; head -42 $out/launch_summary_b$B.md ;;
 full)
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${KREGEX:-igemm|in_fwd|in_bwd|in_stats}" \
-     --launch-skip ${KSKIP:-300} -c ${KCOUNT:-16} -o $out/top_kernels_b$B -f \
-     python bench.py --batch $B --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-roofline > $out/full_run.log 2>&1
-  python tools/ncu_summary.py $out/top_kernels_b$B.ncu-rep > $out/ncu_full_summary_b$B.md 2>&1
-  ncu -i $out/top_kernels_b$B.ncu-rep --page raw --csv > $out/ncu_full_raw_b$B.csv 2>/dev/null
-  sz=$(stat -c %s $out/top_kernels_b$B.ncu-rep 2>/dev/null || echo 0)
-  if [ "$sz" -gt 40000000 ]; then rm -f $out/top_kernels_b$B.ncu-rep; echo "ncu-rep too large ($sz), removed" ; fi
-  grep -E "^###|duration|tensor pipe|DRAM read|DRAM write|L2 -> SM" $out/ncu_full_summary_b$B.md | head -120 ;;
+  # FULLSPECS="regex:skip:count ..." -- one ncu --set full capture per spec (kept small: reports come home)
+  i=0
+  for spec in ${FULLSPECS:-"igemm|in_fwd|in_bwd:300:12"}; do
+    i=$((i+1))
+    rx=${spec%%:*}; rest=${spec#*:}; sk=${rest%%:*}; ct=${rest#*:}
+    rep=$out/full${i}_b$B
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$rx" --launch-skip $sk -c $ct -o $rep -f \
+       python bench.py --batch $B --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-roofline > $out/full_run.log 2>&1
+    python tools/ncu_summary.py $rep.ncu-rep > $rep.md 2>&1
+    sz=$(stat -c %s $rep.ncu-rep 2>/dev/null || echo 0)
+    if [ "$sz" -gt 30000000 ]; then rm -f $rep.ncu-rep; echo "ncu-rep too large ($sz), removed" ; fi
+    grep -E "^###|duration|DRAM read|DRAM write|DRAM throughput|tensor pipe|occupancy|stall" $rep.md | head -60
+  done ;;
 esac
 done
 du -sh gpurun_out
