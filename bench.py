@@ -29,7 +29,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("GB_BENCH_BATCH", 1)), help="per-GPU batch")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("GB_BENCH_BATCH", 8)),
+                    help="per-GPU batch (8 = the per-GPU batch BASELINE.json's GPU configs name; the reference's "
+                         "own CPU case is batch 1: --batch 1)")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")

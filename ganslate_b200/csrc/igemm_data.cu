@@ -260,6 +260,7 @@ int launch(const gb_conv_params& p, const ClassDivs& divs, int64_t max_mc, cudaS
   }
   dim3 grid(gb_cdiv(max_mc, BM), gb_cdiv(p.ncols, BN), p.nclass);
   igemm_data_kernel<BN><<<grid, 256, C::SMEM, st>>>(p, divs);
+  g_gb_knobs[15] = 1;
   GB_LAUNCH_CHECK();
   return 0;
 }
@@ -273,6 +274,7 @@ int64_t view_max_offset(const gb_view& v) {
 
 int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st);   // igemm_tma.cu: -1 = not applicable
 int gb_conv_data_halo(const gb_conv_params& p, cudaStream_t st);  // igemm_halo.cu: -1 = not applicable
+int gb_conv_data_pair(const gb_conv_params& p, cudaStream_t st);  // igemm_pair.cu: -1 = not applicable
 
 extern "C" int gb_conv_data(const gb_conv_params* pp, void* stream) {
   const gb_conv_params& p = *pp;
@@ -307,6 +309,8 @@ extern "C" int gb_conv_data(const gb_conv_params* pp, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   {
     int r = gb_conv_data_halo(p, st);   // halo-reuse TMA kernel (dense tap windows, single class)
+    if (r >= 0) return r;
+    r = gb_conv_data_pair(p, st);       // two patches per CTA + halo reuse: wide stride-1 layers on full launches
     if (r >= 0) return r;
     r = gb_conv_data_tma(p, st);        // TMA-fed kernel for unit-stride gathers with C % 64 == 0
     if (r >= 0) return r;

@@ -20,10 +20,13 @@ constexpr int BP = 64;                 // pixels per stage (MMA K = 16 -> 4 MMAs
 constexpr int ATOM = BP * 128;         // one [64 px][64 ch] swizzled atom = 8 KB
 constexpr int LAG = 2;
 
-template <int BN>
+// RT = row tiles (of 128 plain channels) per CTA.  RT = 2 shares every gathered tile G between two accumulators:
+// a stage is 32 KB (P) + 32 KB (G) for 1024 MMA cycles instead of 16 + 32 KB for 512 (the launch is bound by the
+// ~42 B/clk/SM the L2 delivers, see igemm_pair.cu), at the price of the whole TMEM (2 x 256 columns).
+template <int BN, int RT = 1>
 struct WCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int P_BYTES = 2 * ATOM;
+  static constexpr int STAGES = (RT == 2) ? 3 : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int P_BYTES = RT * 2 * ATOM;
   static constexpr int G_BYTES = (BN / 64) * ATOM;
   static constexpr int STAGE_BYTES = P_BYTES + G_BYTES;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 1024;
@@ -41,13 +44,14 @@ struct PixDivs {
   int tw, th, ntiles, use_tma;
 };
 
-template <int BN, bool TMA>
-__global__ void __launch_bounds__(256, WCfg<BN>::MIN_CTAS) igemm_wgrad_kernel(const __grid_constant__ gb_wgrad_params p,
+template <int BN, bool TMA, int RT = 1>
+__global__ void __launch_bounds__(256, WCfg<BN, RT>::MIN_CTAS) igemm_wgrad_kernel(const __grid_constant__ gb_wgrad_params p,
                                                                               const __grid_constant__ PixDivs divs,
                                                                               const __grid_constant__ CUtensorMap map_p,
                                                                               const __grid_constant__ CUtensorMap map_g,
                                                                               int blocks_per_split) {
-  using C = WCfg<BN>;
+  using C = WCfg<BN, RT>;
+  static_assert(RT == 1 || TMA, "two row tiles per CTA only on the TMA-fed path");
   constexpr int STAGES = C::STAGES;
   constexpr int NG = BN / 64;  // gathered atoms per stage
   extern __shared__ uint8_t smem_raw[];
@@ -62,7 +66,7 @@ __global__ void __launch_bounds__(256, WCfg<BN>::MIN_CTAS) igemm_wgrad_kernel(co
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const int kt = blockIdx.x;           // column tile (kflat)
-  const int rt = blockIdx.y * BM;      // first row (plain channel)
+  const int rt = blockIdx.y * BM * RT; // first row (plain channel)
   const int64_t Mq = (int64_t)p.plain.N * p.plain.D * p.plain.H * p.plain.W;
   const int nblk = TMA ? divs.ntiles : (int)((Mq + BP - 1) / BP);
   const int b0 = blockIdx.z * blocks_per_split;
@@ -81,7 +85,7 @@ __global__ void __launch_bounds__(256, WCfg<BN>::MIN_CTAS) igemm_wgrad_kernel(co
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc<BN>(smem_u32(tmem_slot));
+  if (warp == 4) tmem_alloc<BN * RT>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -122,8 +126,9 @@ __global__ void __launch_bounds__(256, WCfg<BN>::MIN_CTAS) igemm_wgrad_kernel(co
         const uint32_t g_s = p_s + C::P_BYTES;
         const uint32_t bar = full_bar + 8 * s;
         mbar_expect_tx(bar, C::STAGE_BYTES);
-        tma_load_5d(p_s, &map_p, bar, rt, x0, y0, z0, n);
-        tma_load_5d(p_s + ATOM, &map_p, bar, rt + 64, x0, y0, z0, n);
+#pragma unroll
+        for (int a = 0; a < 2 * RT; ++a)  // channels past the tensor are zero-filled by the TMA unit
+          tma_load_5d(p_s + a * ATOM, &map_p, bar, rt + a * 64, x0, y0, z0, n);
 #pragma unroll
         for (int g = 0; g < NG; ++g)
           tma_load_5d(g_s + g * ATOM, &map_g, bar, g_c0[g], x0 * p.mul[2] + g_dx[g], y0 * p.mul[1] + g_dy[g],
@@ -131,7 +136,7 @@ __global__ void __launch_bounds__(256, WCfg<BN>::MIN_CTAS) igemm_wgrad_kernel(co
       }
     }
     __syncwarp();
-  } else if (warp < 4) {
+  } else if (RT == 1 && warp < 4) {
     const int j = tid & 7;
     const int r0 = tid >> 3;  // pixel rows r0 + 16*i, i < 4
     const __nv_bfloat16* pl = reinterpret_cast<const __nv_bfloat16*>(p.plain.ptr);
@@ -234,12 +239,15 @@ __global__ void __launch_bounds__(256, WCfg<BN>::MIN_CTAS) igemm_wgrad_kernel(co
         const uint32_t p_s = base + s * C::STAGE_BYTES;
         const uint32_t g_s = p_s + C::P_BYTES;
         // MN-major: LBO = stride between 64-wide atoms, SBO = stride between groups of 8 pixels (k)
-        const uint64_t adesc = make_smem_desc(p_s, ATOM, 1024);
         const uint64_t bdesc = make_smem_desc(g_s, ATOM, 1024);
 #pragma unroll
-        for (int k = 0; k < BP / 16; ++k)
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2048 / 16), bdesc + (uint64_t)(k * 2048 / 16), idesc,
-                    (kb | k) ? 1u : 0u);
+        for (int r = 0; r < RT; ++r) {
+          const uint64_t adesc = make_smem_desc(p_s + r * 2 * ATOM, ATOM, 1024);
+#pragma unroll
+          for (int k = 0; k < BP / 16; ++k)
+            umma_bf16(tmem_base + (uint32_t)(r * BN), adesc + (uint64_t)(k * 2048 / 16), bdesc + (uint64_t)(k * 2048 / 16),
+                      idesc, (kb | k) ? 1u : 0u);
+        }
         umma_commit(empty_bar + 8 * s);
       }
       __syncwarp();
@@ -250,17 +258,18 @@ __global__ void __launch_bounds__(256, WCfg<BN>::MIN_CTAS) igemm_wgrad_kernel(co
 
   mbar_wait(accum_bar, 0);
   tc_fence_after();
-  {
+#pragma unroll 1
+  for (int r = 0; r < RT; ++r) {
     const int lg = warp & 3;
     const int half = warp >> 2;
-    const int row = rt + lg * 32 + lane;
+    const int row = rt + r * BM + lg * 32 + lane;
     const bool row_ok = row < p.rows;
     float* drow = p.dw + (int64_t)row * p.kpad + (int64_t)kt * BN;
     const int cbeg = half * (BN / 2);
 #pragma unroll 1
     for (int c0 = cbeg; c0 < cbeg + BN / 2; c0 += 32) {
       uint32_t acc[32];
-      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, acc);
+      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(r * BN + c0), acc);
       tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
@@ -274,7 +283,7 @@ __global__ void __launch_bounds__(256, WCfg<BN>::MIN_CTAS) igemm_wgrad_kernel(co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<BN>(tmem_base);
+  if (warp == 4) tmem_dealloc<BN * RT>(tmem_base);
 }
 
 template <int BN>
@@ -284,6 +293,9 @@ int launch(const gb_wgrad_params& p, cudaStream_t st) {
   if (!attr_set) {
     GB_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     GB_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    if (BN == 256)
+      GB_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   WCfg<256, 2>::SMEM));
     attr_set = true;
   }
   const int64_t Mq = (int64_t)p.plain.N * p.plain.D * p.plain.H * p.plain.W;
@@ -310,7 +322,10 @@ int launch(const gb_wgrad_params& p, cudaStream_t st) {
     if (gb_tma_activation_map(p.plain, tw, th, &map_p) || gb_tma_activation_map(p.gathered, tw, th, &map_g)) return 1;
   }
   const int nblk = tma ? divs.ntiles : gb_cdiv(Mq, BP);
-  const int tiles = gb_cdiv(p.kpad, BN) * gb_cdiv(p.rows, BM);
+  // two row tiles per CTA when there are at least two and the launch still fills the machine (knob 12 = 1: never)
+  const bool rt2 = tma && BN == 256 && p.rows > BM && g_gb_knobs[12] != 1 &&
+                   (int64_t)gb_cdiv(p.kpad, BN) * gb_cdiv(p.rows, 2 * BM) * (nblk / 4) >= 96;
+  const int tiles = gb_cdiv(p.kpad, BN) * gb_cdiv(p.rows, rt2 ? 2 * BM : BM);
   int splits = p.splits;
   if (splits <= 0) {
     // one wave of the 148 SMs (every split costs a full tile of red.global.add traffic in the epilogue), and at
@@ -321,14 +336,17 @@ int launch(const gb_wgrad_params& p, cudaStream_t st) {
   }
   const int bps = gb_cdiv(nblk, splits);
   splits = gb_cdiv(nblk, bps);
-  dim3 grid(gb_cdiv(p.kpad, BN), gb_cdiv(p.rows, BM), splits);
+  dim3 grid(gb_cdiv(p.kpad, BN), gb_cdiv(p.rows, rt2 ? 2 * BM : BM), splits);
   divs.f[0] = gb_make_fastdiv((uint32_t)p.plain.D);
   divs.f[1] = gb_make_fastdiv((uint32_t)p.plain.H);
   divs.f[2] = gb_make_fastdiv((uint32_t)p.plain.W);
-  if (tma)
+  if (rt2)
+    igemm_wgrad_kernel<256, true, 2><<<grid, 256, WCfg<256, 2>::SMEM, st>>>(p, divs, map_p, map_g, bps);
+  else if (tma)
     igemm_wgrad_kernel<BN, true><<<grid, 256, C::SMEM, st>>>(p, divs, map_p, map_g, bps);
   else
     igemm_wgrad_kernel<BN, false><<<grid, 256, C::SMEM, st>>>(p, divs, map_p, map_g, bps);
+  g_gb_knobs[14] = rt2 ? 2 : (tma ? 1 : 0);  // read-back slot: which wgrad variant served the last call (tests)
   GB_LAUNCH_CHECK();
   return 0;
 }

@@ -87,4 +87,7 @@ class FusedAdam(torch.optim.Adam):
             if n:
                 batch.count = n
                 _cabi.check(lib.gb_adam_multi(C.byref(batch), stream), "gb_adam_multi")
+            # the kernel wrote the parameters through raw pointers: tell autograd (and the packed-weight cache of
+            # ganslate_b200.ops, which keys on Tensor._version) that they changed
+            torch.autograd.graph.increment_version(params)
         return loss

@@ -97,6 +97,29 @@ def test_first_adam_step_moves_weights_by_lr_at_full_size():
                 assert (d > 0.9 * lr).float().mean().item() > 0.95, (n, k)
 
 
+def test_second_iteration_uses_updated_weights():
+    """Two consecutive iterations with optimizer steps: the second iteration's losses must follow the oracle's,
+    i.e. the convolutions read the weights Adam just wrote (the packed bf16 copies are refreshed).  The first Adam
+    step moves the adversarial losses by far more than the tolerance, so stale packed weights cannot pass."""
+    from parity_util import build_pair
+    from oracle import torch_oracle as O
+    oracle, ours = build_pair(size=64, batch=1, n_blocks=2)
+    a, b = O.synthetic_batch(1, 3, 64, seed=1)
+    first = None
+    for it in range(2):
+        lo = oracle.optimize_parameters(a, b, step_optimizers=True)
+        ours.set_input({"A": a, "B": b})
+        ours.optimize_parameters()
+        torch.cuda.synchronize()
+        got = {k: float(ours.losses[k]) for k in lo}
+        if it == 0:
+            first = dict(lo)
+        for k in lo:
+            assert abs(got[k] - lo[k]) <= 3e-2 * abs(lo[k]) + 1e-3, (it, k, lo[k], got[k])
+    # the check has teeth: the adversarial losses of the two iterations differ by much more than the tolerance
+    assert abs(lo["G_AB"] - first["G_AB"]) > 0.2 * abs(first["G_AB"])
+
+
 def test_cuda_graph_step_equals_eager_step():
     """A graph-replayed iteration computes what an eager iteration computes from the same weights and inputs
     (same kernels, same order). Long runs are not compared: fp32 atomics make two runs of ANY mode drift apart."""

@@ -23,8 +23,11 @@ def test_fused_adam_matches_torch_adam():
             for grp in list(ref.param_groups) + list(ours.param_groups):
                 grp["lr"] = 1e-4   # what LambdaLR does between iterations
         ref.step()
+        versions = [b._version for b in our_p]
         ours.step()
         torch.cuda.synchronize()
+        # raw-pointer writes must still bump the version counters (the packed-weight cache keys on them)
+        assert all(b._version > v for b, v in zip(our_p, versions))
         for a, b in zip(ref_p, our_p):
             assert (a - b).abs().max().item() <= 2e-6 * max(a.abs().max().item(), 1e-3), it
     sd = ours.state_dict()

@@ -1,0 +1,103 @@
+"""Times single convolution launches (forward / data gradient / weight gradient) of the layers that dominate a
+CycleGAN step, under bring-up knob variants, with CUDA events on the launch stream.  Not a bench value: this is the
+A/B tool used to pick kernel heuristics (results are copied into profiles/ by hand).
+
+    python tools/conv_microbench.py [batch]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from ganslate_b200 import _cabi, ops
+
+dev = "cuda"
+
+
+def time_us(fn, reps=20, warm=3):
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def layer(name, cin, cout, k, stride, pad, H, W, N, border=0, transposed=False, op_pad=0):
+    """border: materialised reflection border of the input buffer (the conv itself then has padding 0)."""
+    op = ops.ConvOp(cin, cout, (1, k, k), (1, stride, stride), (0, pad, pad), transposed=transposed,
+                    output_padding=(0, op_pad, op_pad))
+    wshape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
+    w = (torch.randn(wshape, device=dev) * 0.02)
+    bias = torch.zeros(cout, device=dev)
+    x = torch.randn(N, 1, H + 2 * border, W + 2 * border, op.cin_pad, device=dev).to(torch.bfloat16)
+    xv = ops.make_view(x)
+    od, oh, ow = op.out_extent((1, H + 2 * border, W + 2 * border))
+    dy = torch.randn(N, od, oh, ow, op.cout_pad, device=dev).to(torch.bfloat16)
+    dx = torch.zeros(N, 1, H + 2 * border, W + 2 * border, op.cin_pad, device=dev, dtype=torch.float32)
+    stats = torch.zeros(N, op.cout_pad, 2, device=dev)
+    fl = op.flops((1, H + 2 * border, W + 2 * border), N)
+    return dict(name=name, op=op, w=w, bias=bias, xv=xv, x=x, dy=dy, dyv=ops.make_view(dy), dxv=ops.make_view(dx), dx=dx,
+                stats=stats, flops=fl)
+
+
+def run(L, what):
+    op = L["op"]
+    if what == "fwd":
+        return lambda: op.run_fwd(L["xv"], dev, L["w"], L["bias"], stats=L["stats"])
+    if what == "dgrad":
+        return lambda: op.run_dgrad(L["dyv"], L["w"], L["dxv"], accumulate=False)
+    return lambda: op.run_wgrad(L["xv"], L["dyv"], L["w"].shape, dev)
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    lib = _cabi.lib()
+    layers = [
+        layer("res 3x3 256->256 64x64 (+border 1)", 256, 256, 3, 1, 0, 64, 64, B, border=1),
+        layer("D 4x4 s1 256->512 32->31", 256, 512, 4, 1, 1, 32, 32, B),
+        layer("down 3x3 s2 64->128 256->128", 64, 128, 3, 2, 1, 256, 256, B),
+        layer("down 3x3 s2 128->256 128->64", 128, 256, 3, 2, 1, 128, 128, B),
+        layer("up convT 3x3 s2 256->128 64->128", 256, 128, 3, 2, 1, 64, 64, B, transposed=True, op_pad=1),
+        layer("up convT 3x3 s2 128->64 128->256", 128, 64, 3, 2, 1, 128, 128, B, transposed=True, op_pad=1),
+    ]
+    variants = [
+        ("per-tap TMA kernel (pair off)", {9: 1, 12: 1}),
+        ("default", {}),
+        ("pair bn256", {9: 2, 11: 256}),
+        ("pair bn128", {9: 2, 11: 128}),
+        ("pair bn64", {9: 2, 11: 64}),
+        ("pair bn256 pitch16", {9: 2, 11: 256, 10: 1}),
+        ("pair bn256 1 A stage", {9: 2, 11: 256, 13: 1}),
+        ("pair bn128 pitch16", {9: 2, 11: 128, 10: 1}),
+    ]
+    print(f"batch {B}; us per launch (median of 20, L2 flushed), TFLOP/s algorithmic")
+    for L in layers:
+        print(f"--- {L['name']}  ({L['flops'] / 1e9:.2f} GFLOP)")
+        for vname, knobs in variants:
+            old = {k: lib.gb_debug_knob(k, v) for k, v in knobs.items()}
+            try:
+                row = []
+                for what in ("fwd", "dgrad", "wgrad"):
+                    lib.gb_debug_knob(15, 0)
+                    lib.gb_debug_knob(14, 0)
+                    t = time_us(run(L, what))
+                    path = lib.gb_debug_knob(14, 0) if what == "wgrad" else lib.gb_debug_knob(15, 0)
+                    row.append(f"{what} {t:7.1f}us {L['flops'] / t / 1e6:6.0f}TF [k{path}]")
+                print(f"  {vname:32s} " + "  ".join(row), flush=True)
+            finally:
+                for k, v in old.items():
+                    lib.gb_debug_knob(k, v)
+
+
+if __name__ == "__main__":
+    main()
