@@ -27,7 +27,7 @@ constexpr int TW = 8, TH = 16;   // one patch = 16 rows x 8 columns of output pi
 constexpr int NSUB = 2;          // patches (accumulators) per CTA
 constexpr int MAX_B_STAGES = 8;
 constexpr int MAX_A_STAGES = 2;
-constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int SMEM_LIMIT = 227 * 1024 - 2048;  // dynamic part: leaves room for the static bias_s
 
 struct PairGeom {
   gb_fastdiv tiles_x, tiles_y, tiles_z;  // patch index -> (n, z, ty, tx)
@@ -231,7 +231,7 @@ int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb
   }
   // smem plan: tail 2 KB (alignment slack + barriers + taps); A double-buffered when at least 3 weight stages
   // still fit, else single; the rest goes to weight stages (TMA latency ~1 us: bytes in flight matter)
-  const int budget = SMEM_LIMIT - 2048 - 2048;  // (the second 2 KB: static bias_s + the runtime's per-CTA reserve)
+  const int budget = SMEM_LIMIT - 2048;
   const int a_stage = NSUB * pg.a_sub_stride;
   int a_stages = (budget - 2 * a_stage) / B_BYTES >= 3 ? 2 : 1;
   if (g_gb_knobs[13] == 1 || g_gb_knobs[13] == 2) a_stages = g_gb_knobs[13];
@@ -323,21 +323,18 @@ int gb_conv_data_pair(const gb_conv_params& p, cudaStream_t st) {
     bn = g_gb_knobs[11];
     if (bn > bn_max) bn = bn_max;
   } else {
-    const int64_t kiters = (int64_t)cc.ntaps * (p.in.C >> 6);
-    int64_t best = -1;
-    for (int cand = bn_max; cand >= 64; cand /= 2) {
-      const int64_t ctas = npairs * gb_cdiv(p.ncols, cand);
-      const int64_t rounds = (ctas + 147) / 148;
-      const int64_t cost = rounds * (kiters * NSUB * 4 * (cand / 2) + 6000);
-      if (best < 0 || cost < best) {
-        best = cost;
-        bn = cand;
-      }
-    }
+    bn = bn_max;
+  }
+  if (g_gb_knobs[9] != 2) {
+    // Measured (profiles/r01f_conv_microbench_b8.txt): both this kernel and the per-tap kernel are bound by the
+    // shared-memory operand reads of the single-CTA MMA (A 4 KB + B 8 KB per 128x256x16 instruction, ~54-60 %
+    // tensor-pipe active), not by L2, so sharing B and re-using the halo buys little, and with two patches per
+    // CTA a launch that is not ONE full wave loses more to wave quantisation than it gains.  Default: only the
+    // launches that are exactly one wave of 256-wide pair CTAs on patch grids without waste (the residual-block
+    // forward convolutions at batch 8: 128 CTAs, 45.9 us vs 48.1 us).
     const int64_t ctas = npairs * gb_cdiv(p.ncols, bn);
-    // waste from the 16x8 patch grid (e.g. 31x31 outputs) and from under-filled launches
-    const bool fits = (int64_t)ntx * TW * nty * TH * 100 <= (int64_t)q[2] * q[1] * 150;
-    if (g_gb_knobs[9] != 2 && (ctas < 96 || !fits)) return -1;
+    const bool fits = (int64_t)ntx * TW * nty * TH * 100 <= (int64_t)q[2] * q[1] * 110;
+    if (bn != 256 || ctas < 96 || ctas > 148 || !fits) return -1;
   }
   CUtensorMap ma, mb;
   if (gb_tma_activation_map(p.in, pg.hw, pg.hh, &ma)) return 1;

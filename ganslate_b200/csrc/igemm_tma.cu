@@ -2,7 +2,9 @@
 // dominant case: unit gather multiplier (stride-1 convolutions and every parity class of a transposed or
 // strided-dgrad convolution) and a channel count that is a multiple of 64.
 //
-// A GEMM row tile is a TH x TW patch of output pixels (TH*TW = 128) of one image / depth slice.  For tap t and
+// A GEMM row tile is a TH x TW patch of output pixels (TH*TW <= 128, any TW: an 11 x 11 patch covers the 66 x 66
+// reflection-padded domain of the residual-block data gradients with 36 tiles per image instead of the 45 that
+// 16 x 8 patches need) of one image / depth slice.  For tap t and
 // 64-channel chunk c the A operand is then one 5-D TMA box {64 ch, TW, TH, 1, 1} of the channels-last input at
 // pixel offset d_t -- the hardware does the address generation, zero-fills outside the image (= zero padding)
 // and writes the 128B-swizzled K-major tile the UMMA descriptor expects.  B (packed weights) is a 2-D box
@@ -39,7 +41,8 @@ struct TCfg {
 
 struct TileGeom {
   gb_fastdiv tiles_x, tiles_y, tiles_z;  // decode tile index -> (n, z, ty, tx)
-  int tw, th, tw_shift;                  // TW is a power of two
+  int tw, th;
+  gb_fastdiv div_tw;                     // tile row -> (h, w) = (row / tw, row % tw); rows >= tw * th are unused
   int ntx, nty;
   int ntiles;                            // per class (max over classes is the grid)
   int nstages;                           // depth of the smem ring (<= TCfg::STAGES); small rings let two CTAs share an SM
@@ -119,7 +122,7 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
           const uint32_t a_s = base + s * C::STAGE_BYTES;
           const uint32_t b_s = a_s + A_BYTES;
           const uint32_t bar = full_bar + 8 * s;
-          mbar_expect_tx(bar, C::STAGE_BYTES);
+          mbar_expect_tx(bar, (uint32_t)(tg.tw * tg.th * 128 + C::B_BYTES));
           tma_load_5d(a_s, &map_a, bar, c * 64, x0 + dx, y0 + dy, z0 + dz, n);
           tma_load_2d(b_s, &map_b, bar, tl * p.in.C + c * 64, cls * p.npad + n0);
           if (++s == STAGES) {
@@ -164,9 +167,9 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
   }
   {
     const int row = (warp & 3) * 32 + lane;
-    const int h = row >> tg.tw_shift, w = row & (tg.tw - 1);
+    const int h = (int)gb_div((uint32_t)row, tg.div_tw), w = row - h * tg.tw;
     const int qy = y0 + h, qx = x0 + w;
-    const bool row_ok = qy < q[1] && qx < q[2];
+    const bool row_ok = h < tg.th && qy < q[1] && qx < q[2];
     int64_t ooff = 0;
     if (row_ok)
       ooff = gb_pix_offset(p.out, n, z0 * p.out_mul[0] + cc.off[0], qy * p.out_mul[1] + cc.off[1],
@@ -306,27 +309,29 @@ int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st) {
   }
   if (max_ext[0] == 0 || max_ext[1] == 0 || max_ext[2] == 0) return 0;
   if ((p.in.sx * 2) % 16 || (p.in.sy * 2) % 16 || (p.in.sz * 2) % 16 || (p.in.sn * 2) % 16) return -1;
-  // tile shape: TW x TH = 128 pixels, TW a power of two in [8, 128]; pick the shape that wastes the fewest
-  // out-of-range pixels (e.g. the 66x66 padded domain of a reflection-padded dgrad: 16x8 tiles waste 32 %,
-  // 64x2 tiles 94 %), ties go to the wider tile (longer contiguous stores)
-  int tw = 8;
+  // tile shape: TW x TH <= 128 pixels.  Fewest tiles first (every tile costs a full 128-row MMA pass whatever it
+  // covers: 66x66 -> 11x11 patches, 36 tiles, instead of 16x8, 45 tiles), then the fewest unused rows, then the
+  // wider tile (longer contiguous stores).  Knob 0 = 1 restricts TW to powers of two with TW*TH = 128.
+  int tw = 8, th = 16;
   {
-    int64_t best = -1;
-    for (int cand = 8; cand <= 128; cand *= 2) {
+    int64_t best_tiles = -1, best_waste = 0;
+    for (int cand = 4; cand <= 128; ++cand) {
+      if (g_gb_knobs[0] == 1 && ((cand & (cand - 1)) != 0 || cand < 8)) continue;
       const int ch = BM / cand;
-      const int64_t cost = (int64_t)gb_cdiv(max_ext[2], cand) * cand * gb_cdiv(max_ext[1], ch) * ch;
-      if (best < 0 || cost <= best) {
-        best = cost;
+      const int64_t tiles = (int64_t)gb_cdiv(max_ext[2], cand) * gb_cdiv(max_ext[1], ch);
+      const int64_t unused = BM - cand * ch;  // rows of the MMA tile no pixel maps to
+      if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && unused <= best_waste)) {
+        best_tiles = tiles;
+        best_waste = unused;
         tw = cand;
+        th = ch;
       }
     }
   }
-  int th = BM / tw;
   TileGeom tg;
   tg.tw = tw;
   tg.th = th;
-  tg.tw_shift = 0;
-  while ((1 << tg.tw_shift) < tw) ++tg.tw_shift;
+  tg.div_tw = gb_make_fastdiv((uint32_t)tw);
   tg.ntx = gb_cdiv(max_ext[2], tw);
   tg.nty = gb_cdiv(max_ext[1], th);
   tg.tiles_x = gb_make_fastdiv((uint32_t)tg.ntx);

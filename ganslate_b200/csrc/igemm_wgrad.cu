@@ -322,8 +322,10 @@ int launch(const gb_wgrad_params& p, cudaStream_t st) {
     if (gb_tma_activation_map(p.plain, tw, th, &map_p) || gb_tma_activation_map(p.gathered, tw, th, &map_g)) return 1;
   }
   const int nblk = tma ? divs.ntiles : gb_cdiv(Mq, BP);
-  // two row tiles per CTA when there are at least two and the launch still fills the machine (knob 12 = 1: never)
-  const bool rt2 = tma && BN == 256 && p.rows > BM && g_gb_knobs[12] != 1 &&
+  // two row tiles per CTA: knob 12 = 2 only.  Measured slower than one (42.5 us vs 37.7 us on the residual-block
+  // layer at batch 8): the launch is bound by the MMA's shared-memory operand reads, which RT = 2 does not reduce,
+  // while it doubles the splits (and red.global.add traffic) needed to fill 148 SMs.
+  const bool rt2 = tma && BN == 256 && p.rows > BM && g_gb_knobs[12] == 2 &&
                    (int64_t)gb_cdiv(p.kpad, BN) * gb_cdiv(p.rows, 2 * BM) * (nblk / 4) >= 96;
   const int tiles = gb_cdiv(p.kpad, BN) * gb_cdiv(p.rows, rt2 ? 2 * BM : BM);
   int splits = p.splits;

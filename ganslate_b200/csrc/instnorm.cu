@@ -391,12 +391,10 @@ __global__ void __launch_bounds__(256, 2) in_bwd_kernel(const __grid_constant__ 
           }
           const uint4 packed = pack8(d);
           store8(p.dx, n, q.z, q.y, q.x, cg, packed);
-          if (want_dbias) {  // sum what the wgrad / dgrad kernels will actually read (the bf16-rounded values)
-            float2 t;
-            t = unpack_bf16x2(packed.x); s1[0] += t.x; s1[1] += t.y;
-            t = unpack_bf16x2(packed.y); s1[2] += t.x; s1[3] += t.y;
-            t = unpack_bf16x2(packed.z); s1[4] += t.x; s1[5] += t.y;
-            t = unpack_bf16x2(packed.w); s1[6] += t.x; s1[7] += t.y;
+          if (want_dbias) {  // bias gradient = sum over pixels of the fp32 dx (before the bf16 rounding of the
+                             // stored operand: the sum of rounding errors is a random walk, not a gradient)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s1[e] += d[e];
           }
         }
       }

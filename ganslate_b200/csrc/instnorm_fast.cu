@@ -189,7 +189,7 @@ in_fwd_fast_kernel(const __grid_constant__ gb_in_fwd_params p, const __grid_cons
 // ------------------------------------------------------------------------------------------------ backward
 // g = dy (folded from the padded domain when dy.pad > 0);  residual gradient: dy_sum += g (unmasked);
 // g *= (xhat > 0 ? 1 : neg_slope);  pass 0: bstats += (sum g, sum g*xhat);
-// pass 1: dx = rstd * (g - mean(g) - xhat * mean(g*xhat)) -> bf16, dbias += column sums of the rounded dx.
+// pass 1: dx = rstd * (g - mean(g) - xhat * mean(g*xhat)) -> bf16, dbias += column sums of the fp32 dx.
 // PASS 0 / 1 = the two passes as separate launches, PASS 2 = both in one launch around a grid barrier.
 template <bool RES, bool LINEAR>
 __device__ __forceinline__ void in_bwd_fast_pass(const gb_in_bwd_params& p, const FastGeom& g, float neg_slope, int pass,
@@ -278,10 +278,9 @@ __device__ __forceinline__ void in_bwd_fast_pass(const gb_in_bwd_params& p, cons
             for (int e = 0; e < 4; ++e) d[e] = rstd[e] * (gg[e] - m1[e] - xv[e] * m2[e]);
             const uint2 o = pack4(d);
             st4_bf16(p.dx.ptr, pix_off<LINEAR>(p.dx, n, pix, yy[u], xx[u]) + c, o);
-            if (want_dbias) {  // sum what wgrad / dgrad will read: the bf16-rounded values
-              float2 t;
-              t = unpack_bf16x2(o.x); s1[0] += t.x; s1[1] += t.y;
-              t = unpack_bf16x2(o.y); s1[2] += t.x; s1[3] += t.y;
+            if (want_dbias) {  // bias gradient: sum of the fp32 dx (not of its bf16 rounding, see instnorm.cu)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) s1[e] += d[e];
             }
           }
         }

@@ -43,7 +43,7 @@ RESBLOCK = dict(name="3x3 reflect1 256->256 64x64 N=2", cin=256, cout=256, k=3, 
 @pytest.mark.parametrize("bn", [64, 128, 256])
 @pytest.mark.parametrize("pitch16", [0, 1])
 def test_pair_resblock_conv(bn, pitch16):
-    _run({9: 2, 10: pitch16, 11: bn}, expect_data=PAIR, expect_wgrad=RT2, **RESBLOCK)
+    _run({9: 2, 10: pitch16, 11: bn, 12: 2}, expect_data=PAIR, expect_wgrad=RT2, **RESBLOCK)
 
 
 @pytest.mark.parametrize("a_stages", [1, 2])
@@ -64,7 +64,7 @@ def test_pair_partial_column_tile():
 
 
 def test_pair_patchgan_4x4_stride1():
-    _run({9: 2, 11: 128}, expect_data=PAIR, expect_wgrad=RT2, name="4x4 s1 p1 256->512 32x32", cin=256, cout=512, k=4,
+    _run({9: 2, 11: 128, 12: 2}, expect_data=PAIR, expect_wgrad=RT2, name="4x4 s1 p1 256->512 32x32", cin=256, cout=512, k=4,
          s=1, p=1, H=32, W=32)
     _run({9: 2, 11: 256}, expect_data=PAIR, name="4x4 s1 p1 256->512 32x32 bn256", cin=256, cout=512, k=4, s=1, p=1,
          H=32, W=32)
@@ -74,11 +74,17 @@ def test_pair_3d_tap_groups():
     _run({9: 2}, expect_data=PAIR, name="3d 3x3x3 p1 64->64 4x16x16", cin=64, cout=64, k=3, s=1, p=1, H=16, W=16, D=4)
 
 
-def test_pair_default_heuristic_on_full_batch():
-    # no knobs: the batch-8 residual-block launch must pick the pair kernel and the two-row-tile wgrad by itself
+def test_default_heuristics_on_full_batch():
+    # no knobs, batch 8 residual-block layer: forward = one wave of pair CTAs, data gradient (66x66 padded domain,
+    # last gb_conv_data call of the case) = per-tap kernel with 11x11 patches, weight gradient = one row tile
     case = dict(RESBLOCK, name="3x3 reflect1 256->256 64x64 N=8", N=8)
-    _run({}, expect_data=PAIR, expect_wgrad=RT2, **case)
+    _run({}, expect_data=2, expect_wgrad=1, **case)
 
 
-def test_wgrad_two_row_tiles_off_matches():
-    _run({12: 1}, expect_wgrad=1, **RESBLOCK)
+def test_non_power_of_two_patches():
+    # per-tap TMA kernel on domains whose best patch is not a power of two (66x66 -> 11x11, 36x20 -> 18x7 ...),
+    # against the power-of-two restriction (knob 0 = 1) as the control
+    for knobs in ({9: 1}, {9: 1, 0: 1}):
+        _run(knobs, expect_data=2, **dict(RESBLOCK, name=f"resblock 11x11 patches {knobs}"))
+        _run(knobs, expect_data=2, name=f"3x3 p1 64->64 36x20 N=2 {knobs}", cin=64, cout=64, k=3, s=1, p=1, H=36, W=20, N=2)
+        _run(knobs, expect_data=2, name=f"3x3 p1 128->128 13x50 {knobs}", cin=128, cout=128, k=3, s=1, p=1, H=13, W=50)

@@ -60,7 +60,15 @@ def run(L, what):
 
 
 def main():
-    B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("batch", type=int, nargs="?", default=8)
+    ap.add_argument("--layers", default="", help="comma-separated layer indices (default: all)")
+    ap.add_argument("--variants", default="", help="comma-separated variant indices (default: all)")
+    ap.add_argument("--what", default="fwd,dgrad,wgrad")
+    ap.add_argument("--reps", type=int, default=20)
+    args = ap.parse_args()
+    B = args.batch
     lib = _cabi.lib()
     layers = [
         layer("res 3x3 256->256 64x64 (+border 1)", 256, 256, 3, 1, 0, 64, 64, B, border=1),
@@ -71,26 +79,29 @@ def main():
         layer("up convT 3x3 s2 128->64 128->256", 128, 64, 3, 2, 1, 128, 128, B, transposed=True, op_pad=1),
     ]
     variants = [
-        ("per-tap TMA kernel (pair off)", {9: 1, 12: 1}),
+        ("per-tap, power-of-two patches", {9: 1, 0: 1}),
+        ("per-tap, free patch shape", {9: 1}),
         ("default", {}),
         ("pair bn256", {9: 2, 11: 256}),
         ("pair bn128", {9: 2, 11: 128}),
-        ("pair bn64", {9: 2, 11: 64}),
         ("pair bn256 pitch16", {9: 2, 11: 256, 10: 1}),
-        ("pair bn256 1 A stage", {9: 2, 11: 256, 13: 1}),
-        ("pair bn128 pitch16", {9: 2, 11: 128, 10: 1}),
+        ("wgrad two row tiles", {12: 2}),
     ]
-    print(f"batch {B}; us per launch (median of 20, L2 flushed), TFLOP/s algorithmic")
+    if args.layers:
+        layers = [layers[int(i)] for i in args.layers.split(",")]
+    if args.variants:
+        variants = [variants[int(i)] for i in args.variants.split(",")]
+    print(f"batch {B}; us per launch (median of {args.reps}, L2 flushed), TFLOP/s algorithmic")
     for L in layers:
         print(f"--- {L['name']}  ({L['flops'] / 1e9:.2f} GFLOP)")
         for vname, knobs in variants:
             old = {k: lib.gb_debug_knob(k, v) for k, v in knobs.items()}
             try:
                 row = []
-                for what in ("fwd", "dgrad", "wgrad"):
+                for what in args.what.split(","):
                     lib.gb_debug_knob(15, 0)
                     lib.gb_debug_knob(14, 0)
-                    t = time_us(run(L, what))
+                    t = time_us(run(L, what), reps=args.reps, warm=1 if args.reps < 5 else 3)
                     path = lib.gb_debug_knob(14, 0) if what == "wgrad" else lib.gb_debug_knob(15, 0)
                     row.append(f"{what} {t:7.1f}us {L['flops'] / t / 1e6:6.0f}TF [k{path}]")
                 print(f"  {vname:32s} " + "  ".join(row), flush=True)
