@@ -28,13 +28,14 @@ class ConvParams(C.Structure):
     _fields_ = [("inp", View), ("out", View), ("wpacked", C.c_void_p), ("bias", C.c_void_p), ("ncols", C.c_int32),
                 ("npad", C.c_int32), ("in_mul", C.c_int32 * 3), ("out_mul", C.c_int32 * 3), ("nclass", C.c_int32),
                 ("cls", ConvClass * GB_MAX_CLASSES), ("taps", (C.c_int8 * 4) * GB_MAX_TAPS), ("act", C.c_int32),
-                ("act_slope", C.c_float), ("out_fp32", C.c_int32), ("accumulate", C.c_int32), ("stats", C.c_void_p)]
+                ("act_slope", C.c_float), ("out_fp32", C.c_int32), ("accumulate", C.c_int32), ("stats", C.c_void_p),
+                ("in_c_valid", C.c_int32)]
 
 
 class WgradParams(C.Structure):
     _fields_ = [("plain", View), ("gathered", View), ("dw", C.c_void_p), ("rows", C.c_int32), ("kpad", C.c_int32),
                 ("ntaps", C.c_int32), ("mul", C.c_int32 * 3), ("taps", (C.c_int8 * 4) * GB_MAX_TAPS),
-                ("splits", C.c_int32)]
+                ("splits", C.c_int32), ("gathered_c_valid", C.c_int32)]
 
 
 class PackParams(C.Structure):
@@ -105,6 +106,7 @@ _SIGNATURES = {
     "gb_patchnce_fwd": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
     "gb_patchnce_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p],
     "gb_version": [],
+    "gb_tma_window_supported": [],
     "gb_debug_knob": [C.c_int, C.c_int],
 }
 

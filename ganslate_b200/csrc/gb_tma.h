@@ -6,8 +6,10 @@
 // true when cuTensorMapEncodeTiled could be resolved from the driver (false on a CPU-only box)
 bool gb_tma_available();
 // 5-D map {C, W, H, D, N} of a channels-last bf16 view with box {64 ch, tw, th, 1, 1}, 128B swizzle, zero OOB fill.
-// Returns 0 on success (maps are cached by view + box).
-int gb_tma_activation_map(const gb_view& v, int tw, int th, CUtensorMap* out);
+// mul (optional, {z, y, x}): traversal strides -- the box delivers pixels c, c + mul, c + 2 mul ... (a strided
+// convolution's gather as one TMA box).  c_valid (optional): channels that exist in memory (the map's channel extent;
+// the 64-wide box zero-fills the rest).  Returns 0 on success (maps are cached by view + box + strides).
+int gb_tma_activation_map(const gb_view& v, int tw, int th, CUtensorMap* out, const int* mul = nullptr, int c_valid = 0);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {

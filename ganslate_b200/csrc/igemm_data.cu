@@ -312,9 +312,10 @@ extern "C" int gb_conv_data(const gb_conv_params* pp, void* stream) {
     if (r >= 0) return r;
     r = gb_conv_data_pair(p, st);       // two patches per CTA + halo reuse: wide stride-1 layers on full launches
     if (r >= 0) return r;
-    r = gb_conv_data_tma(p, st);        // TMA-fed kernel for unit-stride gathers with C % 64 == 0
+    r = gb_conv_data_tma(p, st);        // TMA-fed kernel for gathers with C % 64 == 0 (strided boxes for strides)
     if (r >= 0) return r;
   }
+  GB_CHECK(p.in_c_valid == 0, "gb_conv_data: in_c_valid (pixel-window views) needs a TMA-fed kernel");
   // tile width: smallest BN covering the output channels, shrunk while the grid under-fills the 148 SMs
   int bn = 16;
   while (bn < p.ncols && bn < 256) bn *= 2;

@@ -236,7 +236,7 @@ int gb_tma_weight_map(const void* w, int kpad, int rows, int bn, CUtensorMap* ou
 // this kernel measured 5-15 % slower than the per-tap kernel (one barrier round trip per tap, one CTA per SM), so
 // those stay on igemm_tma unless knob 4 = 1 forces this path; knob 4 = 2 disables it.
 int gb_conv_data_halo(const gb_conv_params& p, cudaStream_t st) {
-  if (g_gb_knobs[4] == 2 || g_gb_knobs[3] != 0) return -1;
+  if (g_gb_knobs[4] == 2 || g_gb_knobs[3] != 0 || p.in_c_valid != 0) return -1;
   if (g_gb_knobs[4] != 1 && !(p.ncols <= 32 && p.nclass == 1 && p.cls[0].ntaps >= 16)) return -1;
   if (p.in.C % 64 != 0 || p.in.pad != 0 || !gb_tma_available()) return -1;
   for (int d = 0; d < 3; ++d)

@@ -258,7 +258,7 @@ int gb_tma_weight_map(const void* w, int kpad, int rows, int bn, CUtensorMap* ou
 // knob 9: 1 = never use this kernel, 2 = use it whenever it applies (tests); knob 10: 1 = halo pitch 16 instead of
 // kw + 7; knob 11: force the tile width; knob 13: force the number of activation stages.
 int gb_conv_data_pair(const gb_conv_params& p, cudaStream_t st) {
-  if (g_gb_knobs[9] == 1 || g_gb_knobs[3] != 0) return -1;
+  if (g_gb_knobs[9] == 1 || g_gb_knobs[3] != 0 || p.in_c_valid != 0) return -1;
   if (p.in.C % 64 != 0 || p.in.pad != 0 || !gb_tma_available()) return -1;
   for (int d = 0; d < 3; ++d)
     if (p.in_mul[d] != 1) return -1;

@@ -123,7 +123,7 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
           const uint32_t b_s = a_s + A_BYTES;
           const uint32_t bar = full_bar + 8 * s;
           mbar_expect_tx(bar, (uint32_t)(tg.tw * tg.th * 128 + C::B_BYTES));
-          tma_load_5d(a_s, &map_a, bar, c * 64, x0 + dx, y0 + dy, z0 + dz, n);
+          tma_load_5d(a_s, &map_a, bar, c * 64, x0 * p.in_mul[2] + dx, y0 * p.in_mul[1] + dy, z0 * p.in_mul[0] + dz, n);
           tma_load_2d(b_s, &map_b, bar, tl * p.in.C + c * 64, cls * p.npad + n0);
           if (++s == STAGES) {
             s = 0;
@@ -209,19 +209,24 @@ std::unordered_map<std::string, CUtensorMap> g_map_cache;
 bool gb_tma_available() { return encode_fn() != nullptr; }
 
 // 5-D activation map {C, W, H, D, N}, box {64, tw, th, 1, 1}
-int gb_tma_activation_map(const gb_view& v, int tw, int th, CUtensorMap* out) {
+int gb_tma_activation_map(const gb_view& v, int tw, int th, CUtensorMap* out, const int* mul, int c_valid) {
+  const int m[3] = {mul ? mul[0] : 1, mul ? mul[1] : 1, mul ? mul[2] : 1};
   std::string key(reinterpret_cast<const char*>(&v), sizeof(gb_view));
   key.append(reinterpret_cast<const char*>(&tw), sizeof(int)).append(reinterpret_cast<const char*>(&th), sizeof(int));
+  key.append(reinterpret_cast<const char*>(m), sizeof(m)).append(reinterpret_cast<const char*>(&c_valid), sizeof(int));
   std::lock_guard<std::mutex> lk(g_map_mutex);
   auto it = g_map_cache.find(key);
   if (it != g_map_cache.end()) {
     *out = it->second;
     return 0;
   }
-  cuuint64_t dims[5] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.D, (cuuint64_t)v.N};
+  cuuint64_t dims[5] = {(cuuint64_t)(c_valid > 0 ? c_valid : v.C), (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.D,
+                        (cuuint64_t)v.N};
   cuuint64_t strides[4] = {(cuuint64_t)v.sx * 2, (cuuint64_t)v.sy * 2, (cuuint64_t)v.sz * 2, (cuuint64_t)v.sn * 2};
-  cuuint32_t box[5] = {64, (cuuint32_t)tw, (cuuint32_t)th, 1, 1};
-  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  // with a traversal stride s the box spans n*s coordinates and delivers n elements
+  cuuint32_t box[5] = {64, (cuuint32_t)(tw * m[2]), (cuuint32_t)(th * m[1]), (cuuint32_t)m[0], 1};
+  cuuint32_t es[5] = {1, (cuuint32_t)m[2], (cuuint32_t)m[1], (cuuint32_t)m[0], 1};
+  GB_CHECK(box[1] <= 256 && box[2] <= 256 && box[3] <= 256, "TMA box too large for the gather stride");
   CUresult r = encode_fn()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, v.ptr, dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -255,6 +260,23 @@ int gb_tma_weight_map(const void* w, int kpad, int rows, int bn, CUtensorMap* ou
   if (g_map_cache.size() > 4096) g_map_cache.clear();
   g_map_cache[key] = *out;
   return 0;
+}
+
+// Pixel-window views (8 pixels x 8 channels read as one 64-channel "pixel", pixel stride 16 B) need a tensor map
+// whose pixel stride is smaller than its channel extent; probe once whether the driver encodes it.
+extern "C" int gb_tma_window_supported(void) {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  if (encode_fn() == nullptr) return cached = 0;
+  alignas(64) static char dummy[1 << 16];
+  CUtensorMap m;
+  cuuint64_t dims[5] = {56, 32, 16, 1, 1};
+  cuuint64_t strides[4] = {16, 16 * 39, 16 * 39 * 16, 16 * 39 * 16};
+  cuuint32_t box[5] = {64, 8, 16, 1, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dummy, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return cached = (r == CUDA_SUCCESS ? 1 : 0);
 }
 
 namespace {
@@ -293,7 +315,7 @@ int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st) {
   if (g_gb_knobs[3] != 0) return -1;                 // knob 3: disable the TMA path
   if (p.in.C % 64 != 0) return -1;
   for (int d = 0; d < 3; ++d)
-    if (p.in_mul[d] != 1) return -1;
+    if (p.in_mul[d] < 1 || p.in_mul[d] > 4 || (p.in_mul[d] != 1 && g_gb_knobs[0] == 2)) return -1;  // knob 0 = 2: no strided boxes
   if (p.in.pad != 0) return -1;
   if (encode_fn() == nullptr) return -1;
   // every class must use the same padded K (true when every class has the same tap count) -- otherwise the 2-D
@@ -318,6 +340,7 @@ int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st) {
     for (int cand = 4; cand <= 128; ++cand) {
       if (g_gb_knobs[0] == 1 && ((cand & (cand - 1)) != 0 || cand < 8)) continue;
       const int ch = BM / cand;
+      if (cand * p.in_mul[2] > 256 || ch * p.in_mul[1] > 256) continue;
       const int64_t tiles = (int64_t)gb_cdiv(max_ext[2], cand) * gb_cdiv(max_ext[1], ch);
       const int64_t unused = BM - cand * ch;  // rows of the MMA tile no pixel maps to
       if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && unused <= best_waste)) {
@@ -364,7 +387,8 @@ int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st) {
   }
   if (bn > p.nclass * p.npad) return -1;  // keep every TMA box inside its tensor
   CUtensorMap ma, mb;
-  if (gb_tma_activation_map(p.in, tw, th, &ma)) return 1;
+  if (tw * p.in_mul[2] > 256 || th * p.in_mul[1] > 256) return -1;
+  if (gb_tma_activation_map(p.in, tw, th, &ma, p.in_mul, p.in_c_valid)) return 1;
   if (gb_tma_weight_map(p.wpacked, kpad, p.nclass * p.npad, bn, &mb)) return 1;
   switch (bn) {
     case 16: return launch<16>(p, ma, mb, tg, st);

@@ -302,14 +302,18 @@ int launch(const gb_wgrad_params& p, cudaStream_t st) {
   PixDivs divs;
   memset(&divs, 0, sizeof(divs));
   // TMA-fed producer: unit gather multiplier, both channel counts multiples of 64 (gathered) / 8 (plain)
-  bool tma = g_gb_knobs[3] == 0 && gb_tma_available() && p.gathered.C % 64 == 0 && p.plain.C % 64 == 0 && p.mul[0] == 1 && p.mul[1] == 1 &&
-             p.mul[2] == 1 && p.plain.pad == 0 && p.gathered.pad == 0;
+  // (strided gathers travel as TMA boxes with traversal strides; knob 0 = 2 keeps them on the cp.async producer)
+  const bool unit = p.mul[0] == 1 && p.mul[1] == 1 && p.mul[2] == 1;
+  bool tma = g_gb_knobs[3] == 0 && gb_tma_available() && p.gathered.C % 64 == 0 && p.plain.C % 64 == 0 &&
+             (unit || (g_gb_knobs[0] != 2 && p.mul[0] <= 4 && p.mul[1] <= 4 && p.mul[2] <= 4)) && p.plain.pad == 0 &&
+             p.gathered.pad == 0;
   CUtensorMap map_p, map_g;
   memset(&map_p, 0, sizeof(map_p));
   memset(&map_g, 0, sizeof(map_g));
   if (tma) {
     int tw = 8;
     while (tw < p.plain.W && tw < 64) tw *= 2;
+    while (tw * p.mul[2] > 256) tw /= 2;
     const int th = BP / tw;
     divs.tw = tw;
     divs.th = th;
@@ -319,7 +323,9 @@ int launch(const gb_wgrad_params& p, cudaStream_t st) {
     divs.tiles_z = gb_make_fastdiv((uint32_t)p.plain.D);
     divs.ntiles = ntx * nty * p.plain.D * p.plain.N;
     divs.use_tma = 1;
-    if (gb_tma_activation_map(p.plain, tw, th, &map_p) || gb_tma_activation_map(p.gathered, tw, th, &map_g)) return 1;
+    if (gb_tma_activation_map(p.plain, tw, th, &map_p) ||
+        gb_tma_activation_map(p.gathered, tw, th, &map_g, p.mul, p.gathered_c_valid))
+      return 1;
   }
   const int nblk = tma ? divs.ntiles : gb_cdiv(Mq, BP);
   // two row tiles per CTA: knob 12 = 2 only.  Measured slower than one (42.5 us vs 37.7 us on the residual-block
@@ -342,6 +348,7 @@ int launch(const gb_wgrad_params& p, cudaStream_t st) {
   divs.f[0] = gb_make_fastdiv((uint32_t)p.plain.D);
   divs.f[1] = gb_make_fastdiv((uint32_t)p.plain.H);
   divs.f[2] = gb_make_fastdiv((uint32_t)p.plain.W);
+  GB_CHECK(tma || p.gathered_c_valid == 0, "gb_conv_wgrad: gathered_c_valid (pixel-window views) needs the TMA path");
   if (rt2)
     igemm_wgrad_kernel<256, true, 2><<<grid, 256, WCfg<256, 2>::SMEM, st>>>(p, divs, map_p, map_g, bps);
   else if (tma)

@@ -16,8 +16,8 @@ __device__ __forceinline__ void pack_class(const gb_pack_params& p, int cls, int
     const int c = k - tl * p.chans_pad;
     float v = 0.f;
     if (n < p.rows && tl < ntaps && c < p.chans) {
-      const int t = p.tap_id[tb + tl];
-      v = p.src[(int64_t)n * p.sn + (int64_t)c * p.sc + (int64_t)t * p.st];
+      const int t = p.tap_id[tb + tl];  // < 0: a padding tap of a pixel-window layout (stays zero)
+      if (t >= 0) v = p.src[(int64_t)n * p.sn + (int64_t)c * p.sc + (int64_t)t * p.st];
     }
     dst[i] = __float2bfloat16_rn(v);
   }

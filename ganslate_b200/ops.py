@@ -72,6 +72,9 @@ def zeros(shape, device):
 # Optional per-launch timing (bench.py roofline): a list that receives (family, work, unit, event0, event1).
 PROFILE = None
 
+# Pixel-window formulation of small-channel unit-stride convolutions (ConvOp.window); tests switch it off for A/B.
+WINDOW_CONV = True
+
 
 def _call(family, work, unit, what, fn, *args):
     """Launch through the C ABI; when profiling is on, bracket the launch with CUDA events on the launch stream."""
@@ -193,7 +196,25 @@ class ConvOp:
             self.dgrad_strides = (self.T, cin * self.T, 1)
         self.fwd_rows_pad = (cout + 15) // 16 * 16
         self.dgrad_rows_pad = (cin + 15) // 16 * 16
-        self.fwd.finalize(self.cin_pad, self.fwd_rows_pad)
+        # Pixel-window formulation of a unit-stride convolution over <= 8 channels with no padding in x (the
+        # generators' 7x7 input layer behind its ReflectionPad): kw consecutive pixels x 8 channels are 112
+        # contiguous bytes, read as ONE 64-"channel" pixel of a view whose pixel stride is 16 B.  A (dz, dy) pair
+        # becomes one K block of 64 = (dx, c) (dx = 7: zero weights) and the TMA-fed kernels serve the layer,
+        # instead of kd*kh*kw gathers of 16 B per output pixel.  Forward and weight gradient; the data gradient
+        # keeps the tap formulation.
+        self.window = (bool(WINDOW_CONV) and not transposed and all(s == 1 for s in self.stride) and self.cin_pad == 8
+                       and 1 < kernel[2] <= 8 and self.padding[2] == 0 and self.cout_pad % 64 == 0
+                       and kernel[0] * kernel[1] <= _cabi.GB_MAX_TAPS // 8
+                       and (WINDOW_CONV == "force" or _cabi.lib().gb_tma_window_supported() == 1))
+        self.win_pack_ids = None
+        if self.window:
+            kd, kh, kw = self.kernel
+            taps = [(dz - self.padding[0], dy - self.padding[1], 0) for dz in range(kd) for dy in range(kh)]
+            self.fwd = DataSpec((1, 1, 1), (1, 1, 1), [dict(off=(0, 0, 0), taps=taps, tap_ids=list(range(len(taps))))])
+            # pack: pseudo-taps (dz, dy, dx in 0..7) of 8 channels each; dx >= kw -> zero
+            self.win_pack_ids = [((dz * kh + dy) * kw + dx) if dx < kw else -1
+                                 for dz in range(kd) for dy in range(kh) for dx in range(8)]
+        self.fwd.finalize(64 if self.window else self.cin_pad, self.fwd_rows_pad)
         self.dgrad.finalize(self.cout_pad, self.dgrad_rows_pad)
         # wgrad: rows come from the "plain" tensor, columns (tap, c) from the gathered one
         self.wg_taps = [tuple(r[d] - padding[d] for d in range(3))
@@ -201,7 +222,9 @@ class ConvOp:
         if self.T > _cabi.GB_MAX_TAPS:
             raise ValueError("kernel too large")
         g_pad = self.cout_pad if transposed else self.cin_pad
-        self.wg_kpad = max(64, (self.T * g_pad + 63) // 64 * 64)
+        if self.window:
+            self.wg_taps = [t for t in self.fwd.classes[0]["taps"]]
+        self.wg_kpad = self.kernel[0] * self.kernel[1] * 64 if self.window else max(64, (self.T * g_pad + 63) // 64 * 64)
         self.wg_rows = cin if transposed else cout
         self.wg_rows_pad = (self.wg_rows + 127) // 128 * 128
         # Operand swap for unit-stride convolutions with few output channels (the generators' last 7x7 -> 3 layer,
@@ -210,7 +233,7 @@ class ConvOp:
         #   dW'[c][t*cout_pad + r] = sum_q' x[q'][c] * dOut[q' - d_t][r],
         # which wastes pad128(cin) x pad64(T*cout_pad) MMA work instead of pad128(cout) x pad64(T*cin_pad).
         self.wg_swap = False
-        if not transposed and all(s == 1 for s in self.stride):
+        if not transposed and all(s == 1 for s in self.stride) and not self.window:
             sw_kpad = max(64, (self.T * self.cout_pad + 63) // 64 * 64)
             sw_rows_pad = (cin + 127) // 128 * 128
             if sw_rows_pad * sw_kpad * 2 <= self.wg_rows_pad * self.wg_kpad:
@@ -258,6 +281,12 @@ class ConvOp:
         p.sn, p.sc, p.st = sn, sc, st
         p.rows, p.rows_pad, p.chans, p.chans_pad = rows, rows_pad, chans, chans_pad
         p.nclass = len(spec.classes)
+        if which == "fwd" and self.window:
+            ids = self.win_pack_ids
+            p.ntaps[0], p.kpad[0], p.w_offset[0], p.tap_begin[0] = len(ids), spec.kpads[0], 0, 0
+            for j, t in enumerate(ids):
+                p.tap_id[j] = t
+            return p, dst, rows_pad * spec.kpads[0]
         tb = 0
         for i, c in enumerate(spec.classes):
             p.ntaps[i], p.kpad[i], p.w_offset[i], p.tap_begin[i] = len(c["taps"]), spec.kpads[i], spec.w_offsets[i], tb
@@ -306,7 +335,8 @@ class ConvOp:
         od, oh, ow = self.out_extent((xv.D, xv.H, xv.W))
         y = torch.empty((xv.N, od, oh, ow, self.cout_pad), dtype=torch.bfloat16, device=device)
         p = self._params("fwd")
-        p.inp, p.out = xv, make_view(y)
+        p.inp, p.out = (self.window_view(xv) if self.window else xv), make_view(y)
+        p.in_c_valid = self.kernel[2] * 8 if self.window else 0
         wp = self.packed(weight, "fwd")
         p.wpacked = wp.data_ptr()
         p.bias = bias.data_ptr() if bias is not None else None
@@ -349,8 +379,19 @@ class ConvOp:
                     unpack=dict(dsr=dsr, dsc=dsc, dst_t=1, rows=self.wg_rows, chans=cols, chans_pad=cols_pad,
                                 ntaps=self.T, kpad=self.wg_kpad))
 
+    def window_view(self, xv: View) -> View:
+        """The 8-channel plain view re-read as kw-pixel windows: C = 64 (kw*8 of them exist), pixel stride unchanged
+        (8 elements), one window per output column."""
+        assert xv.C == 8 and xv.sx == 8 and xv.pad == 0
+        wv = View()
+        C.memmove(C.byref(wv), C.byref(xv), C.sizeof(View))
+        wv.C, wv.W = 64, xv.W - self.kernel[2] + 1
+        return wv
+
     def run_wgrad(self, xv: View, dyv: View, weight_shape, device, pending=None):
         """fp32 weight gradient in the PyTorch layout of `weight_shape` (xv: plain input view, dyv: bf16 d_raw)."""
+        if self.window:
+            return self._run_wgrad_window(xv, dyv, weight_shape, device, pending)
         plan = self.wgrad_plan()
         plain, gathered = (xv, dyv) if plan["plain_is_input"] else (dyv, xv)
         ws = zeros((self.wg_rows_pad, self.wg_kpad), device)
@@ -380,6 +421,49 @@ class ConvOp:
         return dw
 
 
+def _conv_op_window_wgrad(self, xv, dyv, weight_shape, device, pending):
+    """Weight gradient of a pixel-window convolution: dW[r][(dz,dy)*64 + dx*8 + c] = sum_q dOut[q][r] * window[q + (dz,dy)]
+    [dx*8 + c]; one unpack item per (dz, dy) K block copies its kw x cin columns into the PyTorch layout."""
+    kd, kh, kw = self.kernel
+    ws = zeros((self.wg_rows_pad, self.wg_kpad), device)
+    cache = self.__dict__.setdefault("_ptemplates", {})
+    p = cache.get("wgrad")
+    if p is None:
+        p = WgradParams()
+        p.ntaps = len(self.wg_taps)
+        for j, t in enumerate(self.wg_taps):
+            p.taps[j][0], p.taps[j][1], p.taps[j][2] = t
+        for d in range(3):
+            p.mul[d] = 1
+        p.rows, p.kpad, p.splits = self.wg_rows, self.wg_kpad, 0
+        p.gathered_c_valid = kw * 8
+        cache["wgrad"] = p
+    p.plain, p.gathered, p.dw = dyv, self.window_view(xv), ws.data_ptr()
+    _call("conv_wgrad", self.flops((xv.D, xv.H, xv.W), xv.N), "flop", "gb_conv_wgrad", _cabi.lib().gb_conv_wgrad,
+          C.byref(p), _stream())
+    dw = torch.empty(weight_shape, dtype=torch.float32, device=device)
+    own = UnpackQueue() if pending is None else pending
+    wsf, dwf = ws.view(-1), dw.view(-1)
+    for it in self.window_unpack_items():
+        own.add(wsf[it["ws_off"]:], dwf[it["dst_off"]:], it["dsr"], it["dsc"], it["dst_t"], it["rows"], it["chans"],
+                it["chans_pad"], it["ntaps"], it["kpad"], keep=(ws, dw))
+    if pending is None:
+        own.flush()
+    return dw
+
+
+def _conv_op_window_unpack_items(self):
+    """gb_unpack_wgrad items of a pixel-window weight gradient: K block b = (dz, dy) holds kw taps of 8 channels;
+    PyTorch layout (cout, cin, kd*kh*kw): row stride cin*T, channel stride T, tap stride 1."""
+    kd, kh, kw = self.kernel
+    return [dict(ws_off=b * 64, dst_off=b * kw, dsr=self.cin * self.T, dsc=self.T, dst_t=1, rows=self.wg_rows,
+                 chans=self.cin, chans_pad=8, ntaps=kw, kpad=self.wg_kpad) for b in range(kd * kh)]
+
+
+ConvOp._run_wgrad_window = _conv_op_window_wgrad
+ConvOp.window_unpack_items = _conv_op_window_unpack_items
+
+
 class UnpackQueue:
     """Weight-gradient workspaces waiting for their copy into the PyTorch layout; flush() issues ONE launch per
     GB_UNPACK_BATCH entries (the batch travels by value as a kernel parameter: CUDA-graph safe)."""
@@ -388,7 +472,7 @@ class UnpackQueue:
         self.batch = _cabi.UnpackBatch()
         self.keep = []
 
-    def add(self, ws, dw, dsr, dsc, dst_t, rows, chans, chans_pad, ntaps, kpad, accumulate=False):
+    def add(self, ws, dw, dsr, dsc, dst_t, rows, chans, chans_pad, ntaps, kpad, accumulate=False, keep=None):
         if self.batch.count == _cabi.GB_UNPACK_BATCH:
             self.flush()
         it = self.batch.item[self.batch.count]
@@ -396,7 +480,7 @@ class UnpackQueue:
         it.rows, it.chans, it.chans_pad, it.ntaps, it.kpad, it.accumulate = (rows, chans, chans_pad, ntaps, kpad,
                                                                              1 if accumulate else 0)
         self.batch.count += 1
-        self.keep.append((ws, dw))
+        self.keep.append((ws, dw) if keep is None else keep)
 
     def flush(self):
         if self.batch.count:

