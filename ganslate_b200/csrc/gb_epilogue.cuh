@@ -31,10 +31,13 @@ __device__ __forceinline__ float gb_round_bf16(float x) { return __bfloat162floa
 // Called by all 8 warps.  Warp w reads TMEM lanes (w & 3) * 32 .. +31 (its row = lane), the two warp halves
 // (w >> 2) split the BN columns.  row_ok / ooff / row_n describe this thread's output row: valid, element offset of
 // its pixel in p.out, image index.
+// scratch != nullptr (kernels whose tile lies inside ONE image, BN >= 64): the statistics of the four row warps are
+// summed in shared memory first (scratch: 4 * BN * 2 floats, free pipeline smem) and leave the CTA as one atomic per
+// column and moment -- on the 256x256x64-channel layers 4096 CTAs otherwise queue 2 M atomics on 1024 addresses.
 template <int BN>
 __device__ __forceinline__ void gb_conv_epilogue(const gb_conv_params& p, uint32_t tmem_base, int warp, int lane,
                                                  bool have_acc, bool row_ok, int64_t ooff, int n0, const float* bias_s,
-                                                 int row_n) {
+                                                 int row_n, float* scratch = nullptr) {
   const int lg = warp & 3;
   const int half = warp >> 2;
   __nv_bfloat16* optr = reinterpret_cast<__nv_bfloat16*>(p.out.ptr);
@@ -43,6 +46,7 @@ __device__ __forceinline__ void gb_conv_epilogue(const gb_conv_params& p, uint32
   const bool active = (BN >= 64) || half == 0;
   if (!active) return;
   const bool want_stats = p.stats != nullptr && !p.out_fp32;
+  const bool cta_reduce = (BN >= 64) && want_stats && scratch != nullptr;
   // all valid rows of this warp belong to one image? (always true for the TMA tilings; the flat row tiling of
   // the gather kernel can straddle two images when an image is not a multiple of 32 pixels)
   bool uniform_n = true;
@@ -111,7 +115,17 @@ __device__ __forceinline__ void gb_conv_epilogue(const gb_conv_params& p, uint32
         }
       }
     }
-    if (want_stats) {
+    if (cta_reduce) {
+      float sq[CH];
+#pragma unroll
+      for (int i = 0; i < CH; ++i) sq[i] = sv[i] * sv[i];
+      const float s1 = gb_warp_colsum<CH>(sv, lane);
+      const float s2 = gb_warp_colsum<CH>(sq, lane);
+      if (lane < CH) {
+        scratch[(lg * BN + c0 + lane) * 2 + 0] = s1;
+        scratch[(lg * BN + c0 + lane) * 2 + 1] = s2;
+      }
+    } else if (want_stats) {
       if (uniform_n) {
         float sq[CH];
 #pragma unroll
@@ -136,5 +150,20 @@ __device__ __forceinline__ void gb_conv_epilogue(const gb_conv_params& p, uint32
         }
       }
     }
+  }
+  if (cta_reduce) {  // uniform across the CTA: every warp of a BN >= 64 tile gets here
+    __syncthreads();
+    for (int i = warp * 32 + lane; i < BN; i += 256) {
+      const int col = n0 + i;
+      if (col < p.ncols) {
+        const float a = scratch[i * 2] + scratch[(BN + i) * 2] + scratch[(2 * BN + i) * 2] + scratch[(3 * BN + i) * 2];
+        const float b = scratch[i * 2 + 1] + scratch[(BN + i) * 2 + 1] + scratch[(2 * BN + i) * 2 + 1] +
+                        scratch[(3 * BN + i) * 2 + 1];
+        float* dst = p.stats + ((int64_t)row_n * p.out.C + col) * 2;
+        atomicAdd(dst, a);
+        atomicAdd(dst + 1, b);
+      }
+    }
+    __syncthreads();  // scratch may be reused by a following call (second patch of the pair kernel)
   }
 }

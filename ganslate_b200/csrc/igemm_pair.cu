@@ -214,7 +214,8 @@ igemm_pair_kernel(const __grid_constant__ gb_conv_params p, const __grid_constan
     if (row_ok)
       ooff = gb_pix_offset(p.out, nn[j], z0[j] * p.out_mul[0] + cc.off[0], qy * p.out_mul[1] + cc.off[1],
                            qx * p.out_mul[2] + cc.off[2]);
-    gb_conv_epilogue<BN>(p, tmem_base + (uint32_t)(j * BN), warp, lane, true, row_ok, ooff, n0, bias_s, nn[j]);
+    gb_conv_epilogue<BN>(p, tmem_base + (uint32_t)(j * BN), warp, lane, true, row_ok, ooff, n0, bias_s, nn[j],
+                         reinterpret_cast<float*>(smem));
   }
   tc_fence_before();
   __syncthreads();

@@ -174,7 +174,8 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
     if (row_ok)
       ooff = gb_pix_offset(p.out, n, z0 * p.out_mul[0] + cc.off[0], qy * p.out_mul[1] + cc.off[1],
                            qx * p.out_mul[2] + cc.off[2]);
-    gb_conv_epilogue<BN>(p, tmem_base, warp, lane, KB > 0, row_ok, ooff, n0, bias_s, n);
+    // (stage 0 of the ring is free once the accumulator is complete: scratch of the CTA-level statistics sum)
+    gb_conv_epilogue<BN>(p, tmem_base, warp, lane, KB > 0, row_ok, ooff, n0, bias_s, n, reinterpret_cast<float*>(smem));
   }
   tc_fence_before();
   __syncthreads();

@@ -6,43 +6,57 @@
 // accumulation and the bias-gradient column sum.  PReLU, residual-before-activation, scaled outputs and fp32
 // destinations stay on the general kernels.
 //
-// Design: HBM-bound streaming.  A thread owns 4 consecutive channels (8 B of bf16, 16 B of fp32) so the per-channel
-// constants cost 16 registers instead of 32; FU pixels per thread are loaded back to back before any arithmetic
-// (all loads independent), three 256-thread blocks per SM are resident, and the grid is one resident wave.  The
-// backward reduction and apply passes run in ONE launch when the grid is co-resident: blocks publish their
-// partial sums with atomics, meet at a grid barrier (cooperative launch guarantees co-residency) and re-read the
-// tensors, which at the sizes where launch latency matters are still in L2.
+// Design: HBM-bound streaming.  Forward: a thread owns 8 consecutive channels (16 B of bf16), backward: 4 (8 B of
+// bf16, 16 B of fp32) so that the per-channel constants of both passes fit in registers.  U pixels per thread are
+// loaded back to back before any arithmetic (all loads independent), three 256-thread blocks per SM are resident
+// and the grid is one resident wave.  A thread walks its pixels with a running (row, column) cursor -- the first
+// version divided every pixel index by the row length and rebuilt 64-bit offsets per view, 28 instructions per
+// element, and was issue-bound at 24 % occupancy (profiles/r01j) -- and the reflection border / mirrored gradient
+// positions are a rarely taken branch.  Views are addressed as rows = D*H lines of W pixels (3-D views must be
+// row-linear: sz == H*sy; bordered views are 2-D).  The backward reduction and apply passes run in ONE launch when
+// the grid is co-resident: blocks publish their partial sums with atomics, meet at a grid barrier (cooperative
+// launch guarantees co-residency) and re-read the tensors, which at the sizes where launch latency matters are
+// still in L2.
 #include "gb_common.cuh"
 #include "gb_geometry.h"
 
 namespace {
 
-constexpr int FU = 8;        // pixels in flight per thread (forward: 8 B + 8 B per pixel)
+constexpr int FU = 4;        // forward: pixels in flight per thread (16 B + 16 B per pixel)
 constexpr int BU = 4;        // backward: 16 B + 8 B (+ 16 B) per pixel
 constexpr int FTHREADS = 256;
 constexpr int FBLOCKS_PER_SM = 3;
 
 struct FastGeom {
-  gb_fastdiv divW;           // pixel -> (row, x) for the 2-D (bordered) addressing mode
   int ppb;                   // pixels per block
   int nblocks;               // blocks per image
   int total_blocks;          // grid size (fused mode: barrier target)
 };
 
-__device__ __forceinline__ uint2 ld4_bf16(const void* base, int64_t off) {
-  return __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + off));
+struct Cursor {
+  int y, x;                  // row (over D*H) and column of the thread's current pixel
+};
+__device__ __forceinline__ void advance(Cursor& c, int step, int W) {
+  c.x += step;
+  while (c.x >= W) {
+    c.x -= W;
+    ++c.y;
+  }
 }
+// element offset of the cursor's pixel inside image n of view v (32-bit: tensors are checked < 2^31 elements)
+__device__ __forceinline__ int off_of(const gb_view& v, const Cursor& c) { return c.y * (int)v.sy + c.x * (int)v.sx; }
+
 __device__ __forceinline__ void unpack4(const uint2& u, float (&f)[4]) {
   float2 t;
   t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
   t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
 }
-// coherent (L2) variants: used for data another block of the same launch may have written before the grid barrier
-__device__ __forceinline__ float4 ld4_f32_cg(const void* base, int64_t off) {
-  return __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off));
-}
-__device__ __forceinline__ void st4_f32(void* base, int64_t off, const float (&f)[4]) {
-  *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off) = make_float4(f[0], f[1], f[2], f[3]);
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
 }
 __device__ __forceinline__ uint2 pack4(const float (&f)[4]) {
   uint2 o;
@@ -50,52 +64,46 @@ __device__ __forceinline__ uint2 pack4(const float (&f)[4]) {
   o.y = pack_bf16x2(f[2], f[3]);
   return o;
 }
-__device__ __forceinline__ void st4_bf16(void* base, int64_t off, const uint2& o) {
-  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = o;
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  return o;
 }
 
-// element offset of pixel `pix` (index inside image n, row-major over the interior) in view v.
-// LINEAR: every view is pixel-linear (no border, full rows): offset = n*sn + pix*sx.
-template <bool LINEAR>
-__device__ __forceinline__ int64_t pix_off(const gb_view& v, int n, uint32_t pix, int y, int x) {
-  if (LINEAR) return (int64_t)n * v.sn + (int64_t)pix * v.sx;
-  return (int64_t)n * v.sn + (int64_t)y * v.sy + (int64_t)x * v.sx;
+// border index that reflects onto interior index i of an axis of length n with border p, or NO_MIRROR.  The host
+// only takes this path when n > 2p + 1, so an index has at most one mirror image per axis.
+constexpr int NO_MIRROR = -(1 << 20);
+__device__ __forceinline__ int mirror_of(int i, int n, int p) {
+  if (i >= 1 && i <= p) return -i;
+  if (i <= n - 2 && i >= n - 1 - p) return 2 * (n - 1) - i;
+  return NO_MIRROR;
 }
 
 // gradient on a reflection-padded domain folded onto interior pixel (y, x): adds the border positions that mirror
-// onto it (the centre value is loaded by the caller)
-__device__ __forceinline__ void add_mirrors4(const gb_view& v, int n, int y, int x, int c, float (&f)[4]) {
-  const int p = v.pad;
-  const bool ynear = (y >= 1 && y <= p) || (y <= v.H - 2 && y >= v.H - 1 - p);
-  const bool xnear = (x >= 1 && x <= p) || (x <= v.W - 2 && x >= v.W - 1 - p);
-  if (!ynear && !xnear) return;
-  int ys[3], xs[3], ny = 1, nx = 1;
-  ys[0] = y;
-  xs[0] = x;
-  if (y >= 1 && y <= p) ys[ny++] = -y;
-  if (y <= v.H - 2 && y >= v.H - 1 - p) ys[ny++] = 2 * (v.H - 1) - y;
-  if (x >= 1 && x <= p) xs[nx++] = -x;
-  if (x <= v.W - 2 && x >= v.W - 1 - p) xs[nx++] = 2 * (v.W - 1) - x;
-  for (int a = 0; a < ny; ++a)
-    for (int b = 0; b < nx; ++b) {
-      if (a == 0 && b == 0) continue;
-      const float4 t = ld4_f32_cg(v.ptr, (int64_t)n * v.sn + (int64_t)ys[a] * v.sy + (int64_t)xs[b] * v.sx + c);
-      f[0] += t.x; f[1] += t.y; f[2] += t.z; f[3] += t.w;
-    }
+// onto it (the centre value is loaded by the caller); `img` points at channel c of image n
+__device__ __forceinline__ void add_mirrors4(const gb_view& v, const float* img, int y, int x, int my, int mx, float (&f)[4]) {
+  if (my != NO_MIRROR) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(img + my * (int)v.sy + x * (int)v.sx));
+    f[0] += t.x; f[1] += t.y; f[2] += t.z; f[3] += t.w;
+  }
+  if (mx != NO_MIRROR) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(img + y * (int)v.sy + mx * (int)v.sx));
+    f[0] += t.x; f[1] += t.y; f[2] += t.z; f[3] += t.w;
+  }
+  if (my != NO_MIRROR && mx != NO_MIRROR) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(img + my * (int)v.sy + mx * (int)v.sx));
+    f[0] += t.x; f[1] += t.y; f[2] += t.z; f[3] += t.w;
+  }
 }
 
-// store to (y, x) and to every border position that reflects onto it
-__device__ __forceinline__ void st4_reflect(const gb_view& v, int n, int y, int x, int c, const uint2& o) {
-  const int p = v.pad;
-  int ys[3], xs[3], ny = 1, nx = 1;
-  ys[0] = y;
-  xs[0] = x;
-  if (y >= 1 && y <= p) ys[ny++] = -y;
-  if (y <= v.H - 2 && y >= v.H - 1 - p) ys[ny++] = 2 * (v.H - 1) - y;
-  if (x >= 1 && x <= p) xs[nx++] = -x;
-  if (x <= v.W - 2 && x >= v.W - 1 - p) xs[nx++] = 2 * (v.W - 1) - x;
-  for (int a = 0; a < ny; ++a)
-    for (int b = 0; b < nx; ++b) st4_bf16(v.ptr, (int64_t)n * v.sn + (int64_t)ys[a] * v.sy + (int64_t)xs[b] * v.sx + c, o);
+// store to every border position that reflects onto (y, x) (the centre is stored by the caller)
+__device__ __forceinline__ void st8_mirrors(const gb_view& v, __nv_bfloat16* img, int y, int x, int my, int mx, const uint4& o) {
+  if (my != NO_MIRROR) *reinterpret_cast<uint4*>(img + my * (int)v.sy + x * (int)v.sx) = o;
+  if (mx != NO_MIRROR) *reinterpret_cast<uint4*>(img + y * (int)v.sy + mx * (int)v.sx) = o;
+  if (my != NO_MIRROR && mx != NO_MIRROR) *reinterpret_cast<uint4*>(img + my * (int)v.sy + mx * (int)v.sx) = o;
 }
 
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
@@ -114,73 +122,82 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 
 // ------------------------------------------------------------------------------------------------ forward
 // y = act((x - mean) * rstd) [+ res], act(v) = v > 0 ? v : v * neg_slope  (neg_slope 1 = identity, 0 = ReLU)
-template <bool RES, bool LINEAR>
-__global__ void __launch_bounds__(FTHREADS, LINEAR ? FBLOCKS_PER_SM : 2)
+template <bool RES>
+__global__ void __launch_bounds__(FTHREADS, FBLOCKS_PER_SM)
 in_fwd_fast_kernel(const __grid_constant__ gb_in_fwd_params p, const __grid_constant__ FastGeom g, float neg_slope) {
   const gb_view& x = p.x;
-  const int C4 = x.C >> 2;
-  const int slots = FTHREADS / C4;
-  const int cg = threadIdx.x % C4;
-  const int slot = threadIdx.x / C4;
+  const int C8 = x.C >> 3;
+  const int slots = FTHREADS / C8;
+  const int cg = threadIdx.x % C8;
+  const int slot = threadIdx.x / C8;
   if (slot >= slots) return;
-  const int c = cg * 4;
+  const int c = cg * 8;
   const int n = blockIdx.y;
+  const int W = x.W;
   const uint32_t P = (uint32_t)x.D * x.H * x.W;
   const uint32_t p0 = blockIdx.x * (uint32_t)g.ppb;
   const uint32_t p1 = min(P, p0 + (uint32_t)g.ppb);
-  float mean[4], rstd[4];
+  float mean[8], rstd[8];
   const float invP = 1.f / (float)P;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
+  for (int e = 0; e < 8; ++e) {
     mean[e] = 0.f;
     rstd[e] = 1.f;
   }
   if (p.stats != nullptr) {
-    const float4 a = *reinterpret_cast<const float4*>(p.stats + ((int64_t)n * x.C + c) * 2);
-    const float4 b = *reinterpret_cast<const float4*>(p.stats + ((int64_t)n * x.C + c) * 2 + 4);
-    const float s[4] = {a.x, a.z, b.x, b.z}, ss[4] = {a.y, a.w, b.y, b.w};
+    const float4* sp = reinterpret_cast<const float4*>(p.stats + ((int64_t)n * x.C + c) * 2);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float m = s[e] * invP;
-      mean[e] = m;
-      rstd[e] = rsqrtf(fmaxf(ss[e] * invP - m * m, 0.f) + p.eps);
+    for (int h = 0; h < 4; ++h) {  // (sum, sumsq) pairs of channels 2h, 2h+1
+      const float4 a = sp[h];
+      const float m0 = a.x * invP, m1 = a.z * invP;
+      mean[2 * h] = m0;
+      mean[2 * h + 1] = m1;
+      rstd[2 * h] = rsqrtf(fmaxf(a.y * invP - m0 * m0, 0.f) + p.eps);
+      rstd[2 * h + 1] = rsqrtf(fmaxf(a.w * invP - m1 * m1, 0.f) + p.eps);
     }
   }
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x.ptr) + (int64_t)n * x.sn + c;
+  const __nv_bfloat16* rb = RES ? reinterpret_cast<const __nv_bfloat16*>(p.res.ptr) + (int64_t)n * p.res.sn + c : nullptr;
+  __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + (int64_t)n * p.y.sn + c;
+  const int ypad = p.y.pad;
+  Cursor cur;
+  {
+    const uint32_t pix = p0 + (uint32_t)slot;
+    cur.y = (int)(pix / (uint32_t)W);
+    cur.x = (int)(pix - (uint32_t)cur.y * (uint32_t)W);
+  }
   for (uint32_t base = p0 + slot; base < p1; base += (uint32_t)(FU * slots)) {
-    uint2 fx[FU], fr[FU];
-    int yy[FU], xx[FU];
+    uint4 fx[FU], fr[FU];
+    int cc[FU];  // (row << 16) | column of pixel u (extents are checked < 65536 on the host)
 #pragma unroll
     for (int u = 0; u < FU; ++u) {
-      const uint32_t pix = base + (uint32_t)(u * slots);
-      if (pix < p1) {
-        if (!LINEAR) {
-          const uint32_t row = gb_div(pix, g.divW);
-          yy[u] = (int)row;
-          xx[u] = (int)(pix - row * g.divW.d);
-        } else {
-          yy[u] = xx[u] = 0;
-        }
-        fx[u] = ld4_bf16(x.ptr, pix_off<LINEAR>(x, n, pix, yy[u], xx[u]) + c);
-        if (RES) fr[u] = ld4_bf16(p.res.ptr, pix_off<LINEAR>(p.res, n, pix, yy[u], xx[u]) + c);
+      cc[u] = (cur.y << 16) | cur.x;
+      if (base + (uint32_t)(u * slots) < p1) {
+        fx[u] = __ldg(reinterpret_cast<const uint4*>(xb + off_of(x, cur)));
+        if (RES) fr[u] = __ldg(reinterpret_cast<const uint4*>(rb + off_of(p.res, cur)));
       }
+      advance(cur, slots, W);
     }
 #pragma unroll
     for (int u = 0; u < FU; ++u) {
-      const uint32_t pix = base + (uint32_t)(u * slots);
-      if (pix < p1) {
-        float f[4], r[4];
-        unpack4(fx[u], f);
-        if (RES) unpack4(fr[u], r);
+      if (base + (uint32_t)(u * slots) < p1) {
+        float f[8], r[8];
+        unpack8(fx[u], f);
+        if (RES) unpack8(fr[u], r);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < 8; ++e) {
           float v = (f[e] - mean[e]) * rstd[e];
           v = v > 0.f ? v : v * neg_slope;
           if (RES) v += r[e];
           f[e] = v;
         }
-        const uint2 o = pack4(f);
-        if (!LINEAR && p.y.pad > 0) st4_reflect(p.y, n, yy[u], xx[u], c, o);
-        else st4_bf16(p.y.ptr, pix_off<LINEAR>(p.y, n, pix, yy[u], xx[u]) + c, o);
+        const uint4 o = pack8(f);
+        const Cursor at = {cc[u] >> 16, cc[u] & 0xFFFF};
+        *reinterpret_cast<uint4*>(yb + off_of(p.y, at)) = o;
+        if (ypad > 0) {
+          const int my = mirror_of(at.y, p.y.H, ypad), mx = mirror_of(at.x, W, ypad);
+          if (my != NO_MIRROR || mx != NO_MIRROR) st8_mirrors(p.y, yb, at.y, at.x, my, mx, o);
+        }
       }
     }
   }
@@ -191,9 +208,10 @@ in_fwd_fast_kernel(const __grid_constant__ gb_in_fwd_params p, const __grid_cons
 // g *= (xhat > 0 ? 1 : neg_slope);  pass 0: bstats += (sum g, sum g*xhat);
 // pass 1: dx = rstd * (g - mean(g) - xhat * mean(g*xhat)) -> bf16, dbias += column sums of the fp32 dx.
 // PASS 0 / 1 = the two passes as separate launches, PASS 2 = both in one launch around a grid barrier.
-template <bool RES, bool LINEAR>
+template <bool RES>
 __device__ __forceinline__ void in_bwd_fast_pass(const gb_in_bwd_params& p, const FastGeom& g, float neg_slope, int pass,
                                                  bool first_pass_of_fused, float* red) {
+  constexpr int NU = RES ? 3 : BU;  // pixels in flight (the residual variant holds one more fp32 vector per pixel)
   const gb_view& x = p.x;
   const gb_view& dy = p.dy_b;
   const int C4 = x.C >> 2;
@@ -202,6 +220,7 @@ __device__ __forceinline__ void in_bwd_fast_pass(const gb_in_bwd_params& p, cons
   const int slot = threadIdx.x / C4;
   const int c = cg * 4;
   const int n = blockIdx.y;
+  const int W = x.W;
   const uint32_t P = (uint32_t)x.D * x.H * x.W;
   const uint32_t p0 = blockIdx.x * (uint32_t)g.ppb;
   const uint32_t p1 = min(P, p0 + (uint32_t)g.ppb);
@@ -228,38 +247,45 @@ __device__ __forceinline__ void in_bwd_fast_pass(const gb_in_bwd_params& p, cons
   const bool want_dbias = pass == 1 && p.dbias != nullptr;
   // the residual gradient is accumulated exactly once: in pass 0
   const bool do_res = RES && pass == 0;
+  const float* gb = reinterpret_cast<const float*>(dy.ptr) + (int64_t)n * dy.sn + c;
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x.ptr) + (int64_t)n * x.sn + c;
+  float* sb = RES ? reinterpret_cast<float*>(p.dy_sum.ptr) + (int64_t)n * p.dy_sum.sn + c : nullptr;
+  __nv_bfloat16* db = reinterpret_cast<__nv_bfloat16*>(p.dx.ptr) + (int64_t)n * p.dx.sn + c;
+  const int gpad = dy.pad;
   if (slot < slots) {
-    for (uint32_t base = p0 + slot; base < p1; base += (uint32_t)(BU * slots)) {
-      float4 lg[BU], lr[BU];
-      uint2 lx[BU];
-      int yy[BU], xx[BU];
+    Cursor cur;
+    {
+      const uint32_t pix = p0 + (uint32_t)slot;
+      cur.y = (int)(pix / (uint32_t)W);
+      cur.x = (int)(pix - (uint32_t)cur.y * (uint32_t)W);
+    }
+    for (uint32_t base = p0 + slot; base < p1; base += (uint32_t)(NU * slots)) {
+      float4 lg[NU], lr[NU];
+      uint2 lx[NU];
+      int cc[NU];  // (row << 16) | column
 #pragma unroll
-      for (int u = 0; u < BU; ++u) {
-        const uint32_t pix = base + (uint32_t)(u * slots);
-        if (pix < p1) {
-          if (!LINEAR) {
-            const uint32_t row = gb_div(pix, g.divW);
-            yy[u] = (int)row;
-            xx[u] = (int)(pix - row * g.divW.d);
-          } else {
-            yy[u] = xx[u] = 0;
-          }
-          lg[u] = ld4_f32_cg(dy.ptr, pix_off<LINEAR>(dy, n, pix, yy[u], xx[u]) + c);
-          lx[u] = ld4_bf16(x.ptr, pix_off<LINEAR>(x, n, pix, yy[u], xx[u]) + c);
-          if (do_res) lr[u] = ld4_f32_cg(p.dy_sum.ptr, pix_off<LINEAR>(p.dy_sum, n, pix, yy[u], xx[u]) + c);
+      for (int u = 0; u < NU; ++u) {
+        cc[u] = (cur.y << 16) | cur.x;
+        if (base + (uint32_t)(u * slots) < p1) {
+          lg[u] = __ldcg(reinterpret_cast<const float4*>(gb + off_of(dy, cur)));
+          lx[u] = __ldg(reinterpret_cast<const uint2*>(xb + off_of(x, cur)));
+          if (do_res) lr[u] = __ldcg(reinterpret_cast<const float4*>(sb + off_of(p.dy_sum, cur)));
         }
+        advance(cur, slots, W);
       }
 #pragma unroll
-      for (int u = 0; u < BU; ++u) {
-        const uint32_t pix = base + (uint32_t)(u * slots);
-        if (pix < p1) {
+      for (int u = 0; u < NU; ++u) {
+        if (base + (uint32_t)(u * slots) < p1) {
           float gg[4] = {lg[u].x, lg[u].y, lg[u].z, lg[u].w}, xv[4];
           unpack4(lx[u], xv);
-          if (!LINEAR && dy.pad > 0) add_mirrors4(dy, n, yy[u], xx[u], c, gg);
-          if (do_res) {
-            const float rs[4] = {lr[u].x + gg[0], lr[u].y + gg[1], lr[u].z + gg[2], lr[u].w + gg[3]};
-            st4_f32(p.dy_sum.ptr, pix_off<LINEAR>(p.dy_sum, n, pix, yy[u], xx[u]) + c, rs);
+          const Cursor at = {cc[u] >> 16, cc[u] & 0xFFFF};
+          if (gpad > 0) {
+            const int my = mirror_of(at.y, dy.H, gpad), mx = mirror_of(at.x, W, gpad);
+            if (my != NO_MIRROR || mx != NO_MIRROR) add_mirrors4(dy, gb, at.y, at.x, my, mx, gg);
           }
+          if (do_res)
+            *reinterpret_cast<float4*>(sb + off_of(p.dy_sum, at)) =
+                make_float4(lr[u].x + gg[0], lr[u].y + gg[1], lr[u].z + gg[2], lr[u].w + gg[3]);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float xh = (xv[e] - mean[e]) * rstd[e];
@@ -276,8 +302,7 @@ __device__ __forceinline__ void in_bwd_fast_pass(const gb_in_bwd_params& p, cons
             float d[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) d[e] = rstd[e] * (gg[e] - m1[e] - xv[e] * m2[e]);
-            const uint2 o = pack4(d);
-            st4_bf16(p.dx.ptr, pix_off<LINEAR>(p.dx, n, pix, yy[u], xx[u]) + c, o);
+            *reinterpret_cast<uint2*>(db + off_of(p.dx, at)) = pack4(d);
             if (want_dbias) {  // bias gradient: sum of the fp32 dx (not of its bf16 rounding, see instnorm.cu)
 #pragma unroll
               for (int e = 0; e < 4; ++e) s1[e] += d[e];
@@ -314,28 +339,31 @@ __device__ __forceinline__ void in_bwd_fast_pass(const gb_in_bwd_params& p, cons
   }
 }
 
-template <bool RES, bool LINEAR, int PASS>
-__global__ void __launch_bounds__(FTHREADS, LINEAR ? FBLOCKS_PER_SM : 2)
+template <bool RES, int PASS>
+__global__ void __launch_bounds__(FTHREADS, FBLOCKS_PER_SM)
 in_bwd_fast_kernel(const __grid_constant__ gb_in_bwd_params p, const __grid_constant__ FastGeom g, float neg_slope) {
   extern __shared__ float red[];  // [slots][C][2]
   if (PASS == 2) {
-    in_bwd_fast_pass<RES, LINEAR>(p, g, neg_slope, 0, true, red);
+    in_bwd_fast_pass<RES>(p, g, neg_slope, 0, true, red);
     unsigned int* counter = reinterpret_cast<unsigned int*>(p.bstats + (int64_t)p.x.N * p.x.C * 2);
     grid_barrier(counter, (unsigned int)g.total_blocks);
-    in_bwd_fast_pass<RES, LINEAR>(p, g, neg_slope, 1, false, red);
+    in_bwd_fast_pass<RES>(p, g, neg_slope, 1, false, red);
   } else {
-    in_bwd_fast_pass<RES, LINEAR>(p, g, neg_slope, PASS, true, red);
+    in_bwd_fast_pass<RES>(p, g, neg_slope, PASS, true, red);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-bool pixel_linear(const gb_view& v) {
-  return v.pad == 0 && v.sy == (int64_t)v.W * v.sx && (v.D == 1 || v.sz == (int64_t)v.H * v.sy);
+// rows = D*H lines of W pixels with one row stride: any 2-D view, 3-D views whose planes are row-contiguous
+bool row_addressable(const gb_view& v) { return v.D == 1 || (v.pad == 0 && v.sz == (int64_t)v.H * v.sy); }
+bool small_offsets(const gb_view& v) {  // 32-bit in-image offsets, 16-bit packed (row, column)
+  return ((int64_t)v.D * v.H + 2 * v.pad) * v.sy + (int64_t)(v.W + 2 * v.pad) * v.sx < (1ll << 31) &&
+         (int64_t)v.D * v.H < 32768 && v.W < 65536;
 }
-bool aligned(const gb_view& v, int elem_bytes) {
-  // 4-channel vectors: 8 B (bf16) / 16 B (fp32) alignment of every pixel's channel-slice start
-  const int64_t a = (elem_bytes == 2) ? 4 : 4;
-  return ((uintptr_t)v.ptr % (elem_bytes * 4)) == 0 && v.sx % a == 0 && v.sy % a == 0 && v.sz % a == 0 && v.sn % a == 0;
+bool aligned(const gb_view& v, int elem_bytes, int vec) {
+  // vec-channel vectors: every pixel's channel-slice start is aligned to vec elements
+  return ((uintptr_t)v.ptr % (elem_bytes * vec)) == 0 && v.sx % vec == 0 && v.sy % vec == 0 && v.sz % vec == 0 &&
+         v.sn % vec == 0;
 }
 
 int num_sms() {
@@ -350,9 +378,9 @@ int num_sms() {
 }
 
 // one resident wave: `cap` co-resident blocks shared by the N images
-FastGeom plan(const gb_view& x, int cap, bool* fits) {
+FastGeom plan(const gb_view& x, int cap, bool* fits, int vec) {
   FastGeom g;
-  const int C4 = x.C / 4;
+  const int C4 = x.C / vec;
   const int slots = FTHREADS / C4;
   const int64_t P = (int64_t)x.D * x.H * x.W;
   int nb = cap / x.N;
@@ -364,20 +392,19 @@ FastGeom plan(const gb_view& x, int cap, bool* fits) {
   g.ppb = (int)ppb;
   g.nblocks = (int)((P + ppb - 1) / ppb);
   g.total_blocks = g.nblocks * x.N;
-  g.divW = gb_make_fastdiv((uint32_t)x.W);
   return g;
 }
 
-template <bool RES, bool LINEAR>
+template <bool RES>
 int launch_fwd(const gb_in_fwd_params& p, float neg_slope, cudaStream_t st) {
   bool fits;
-  const FastGeom g = plan(p.x, num_sms() * (LINEAR ? FBLOCKS_PER_SM : 2), &fits);
-  in_fwd_fast_kernel<RES, LINEAR><<<dim3(g.nblocks, p.x.N), FTHREADS, 0, st>>>(p, g, neg_slope);
+  const FastGeom g = plan(p.x, num_sms() * FBLOCKS_PER_SM, &fits, 8);
+  in_fwd_fast_kernel<RES><<<dim3(g.nblocks, p.x.N), FTHREADS, 0, st>>>(p, g, neg_slope);
   GB_LAUNCH_CHECK();
   return 0;
 }
 
-template <bool RES, bool LINEAR>
+template <bool RES>
 int launch_bwd(const gb_in_bwd_params& p, float neg_slope, cudaStream_t st) {
   const int C4 = p.x.C / 4;
   const int slots = FTHREADS / C4;
@@ -386,17 +413,17 @@ int launch_bwd(const gb_in_bwd_params& p, float neg_slope, cudaStream_t st) {
   static size_t occ_smem = 0;
   if (occ < 0 || occ_smem != smem) {
     int o = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, in_bwd_fast_kernel<RES, LINEAR, 2>, FTHREADS, smem) != cudaSuccess) o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, in_bwd_fast_kernel<RES, 2>, FTHREADS, smem) != cudaSuccess) o = 0;
     cudaGetLastError();
     occ = o;
     occ_smem = smem;
   }
   bool fits = false;
-  FastGeom g = plan(p.x, num_sms() * (occ > 0 ? occ : (LINEAR ? FBLOCKS_PER_SM : 2)), &fits);
+  FastGeom g = plan(p.x, num_sms() * (occ > 0 ? occ : FBLOCKS_PER_SM), &fits, 4);
   const dim3 grid(g.nblocks, p.x.N);
   if (occ > 0 && fits && g_gb_knobs[6] == 0) {
     void* args[] = {(void*)&p, (void*)&g, (void*)&neg_slope};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)in_bwd_fast_kernel<RES, LINEAR, 2>, grid, dim3(FTHREADS), args,
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)in_bwd_fast_kernel<RES, 2>, grid, dim3(FTHREADS), args,
                                                 smem, st);
     if (e == cudaSuccess) {
       __atomic_fetch_add(&g_gb_launches, 1ull, __ATOMIC_RELAXED);
@@ -404,9 +431,9 @@ int launch_bwd(const gb_in_bwd_params& p, float neg_slope, cudaStream_t st) {
     }
     cudaGetLastError();  // cooperative launch not possible here: fall through to two launches
   }
-  in_bwd_fast_kernel<RES, LINEAR, 0><<<grid, FTHREADS, smem, st>>>(p, g, neg_slope);
+  in_bwd_fast_kernel<RES, 0><<<grid, FTHREADS, smem, st>>>(p, g, neg_slope);
   GB_LAUNCH_CHECK();
-  in_bwd_fast_kernel<RES, LINEAR, 1><<<grid, FTHREADS, smem, st>>>(p, g, neg_slope);
+  in_bwd_fast_kernel<RES, 1><<<grid, FTHREADS, smem, st>>>(p, g, neg_slope);
   GB_LAUNCH_CHECK();
   return 0;
 }
@@ -429,14 +456,15 @@ int gb_in_fwd_fast(const gb_in_fwd_params& p, cudaStream_t st) {
   if (!act_to_slope(p.act, p.act_slope, &ns)) return -1;
   if (p.res_before_act || (p.out_scale != 0.f && p.out_scale != 1.f)) return -1;
   const gb_view& x = p.x;
-  if (x.C % 4 != 0 || x.C / 4 > FTHREADS || (int64_t)x.D * x.H * x.W >= (1ll << 31)) return -1;
+  if (x.C % 8 != 0 || x.C / 8 > FTHREADS || (int64_t)x.D * x.H * x.W >= (1ll << 31)) return -1;
   const bool has_res = p.res.ptr != nullptr;
-  if (!aligned(x, 2) || !aligned(p.y, 2) || (has_res && !aligned(p.res, 2))) return -1;
-  if (p.stats != nullptr && ((uintptr_t)p.stats % 16 != 0 || (x.C * 2) % 4 != 0)) return -1;
-  const bool linear = pixel_linear(x) && pixel_linear(p.y) && (!has_res || pixel_linear(p.res));
-  if (!linear && x.D != 1) return -1;  // bordered addressing is 2-D
-  if (linear) return has_res ? launch_fwd<true, true>(p, ns, st) : launch_fwd<false, true>(p, ns, st);
-  return has_res ? launch_fwd<true, false>(p, ns, st) : launch_fwd<false, false>(p, ns, st);
+  if (!aligned(x, 2, 8) || !aligned(p.y, 2, 8) || (has_res && !aligned(p.res, 2, 8))) return -1;
+  if (p.stats != nullptr && (uintptr_t)p.stats % 16 != 0) return -1;
+  if (!row_addressable(x) || !row_addressable(p.y) || (has_res && !row_addressable(p.res))) return -1;
+  if (!small_offsets(x) || !small_offsets(p.y) || (has_res && !small_offsets(p.res))) return -1;
+  if (x.pad != 0 || (has_res && p.res.pad != 0)) return -1;
+  if (p.y.pad > 0 && (p.y.D != 1 || p.y.H <= 2 * p.y.pad + 1 || p.y.W <= 2 * p.y.pad + 1)) return -1;
+  return has_res ? launch_fwd<true>(p, ns, st) : launch_fwd<false>(p, ns, st);
 }
 
 int gb_in_bwd_fast(const gb_in_bwd_params& p, cudaStream_t st) {
@@ -451,10 +479,12 @@ int gb_in_bwd_fast(const gb_in_bwd_params& p, cudaStream_t st) {
   if (has_res && !p.dy_sum_acc) return -1;
   const gb_view& x = p.x;
   if (x.C % 4 != 0 || x.C / 4 > FTHREADS || (int64_t)x.D * x.H * x.W >= (1ll << 31)) return -1;
-  if (!aligned(x, 2) || !aligned(p.dx, 2) || !aligned(p.dy_b, 4) || (has_res && !aligned(p.dy_sum, 4))) return -1;
+  if (!aligned(x, 2, 4) || !aligned(p.dx, 2, 4) || !aligned(p.dy_b, 4, 4) || (has_res && !aligned(p.dy_sum, 4, 4))) return -1;
   if ((uintptr_t)p.stats % 16 != 0 || (uintptr_t)p.bstats % 16 != 0) return -1;
-  const bool linear = pixel_linear(x) && pixel_linear(p.dx) && pixel_linear(p.dy_b) && (!has_res || pixel_linear(p.dy_sum));
-  if (!linear && x.D != 1) return -1;
-  if (linear) return has_res ? launch_bwd<true, true>(p, ns, st) : launch_bwd<false, true>(p, ns, st);
-  return has_res ? launch_bwd<true, false>(p, ns, st) : launch_bwd<false, false>(p, ns, st);
+  if (!row_addressable(x) || !row_addressable(p.dx) || !row_addressable(p.dy_b) || (has_res && !row_addressable(p.dy_sum)))
+    return -1;
+  if (!small_offsets(x) || !small_offsets(p.dx) || !small_offsets(p.dy_b) || (has_res && !small_offsets(p.dy_sum))) return -1;
+  if (x.pad != 0 || p.dx.pad != 0 || (has_res && p.dy_sum.pad != 0)) return -1;
+  if (p.dy_b.pad > 0 && (p.dy_b.D != 1 || p.dy_b.H <= 2 * p.dy_b.pad + 1 || p.dy_b.W <= 2 * p.dy_b.pad + 1)) return -1;
+  return has_res ? launch_bwd<true>(p, ns, st) : launch_bwd<false>(p, ns, st);
 }

@@ -50,10 +50,13 @@ def layer(name, cin, cout, k, stride, pad, H, W, N, border=0, transposed=False, 
                 stats=stats, flops=fl)
 
 
+NO_STATS = False
+
+
 def run(L, what):
     op = L["op"]
     if what == "fwd":
-        return lambda: op.run_fwd(L["xv"], dev, L["w"], L["bias"], stats=L["stats"])
+        return lambda: op.run_fwd(L["xv"], dev, L["w"], L["bias"], stats=None if NO_STATS else L["stats"])
     if what == "dgrad":
         return lambda: op.run_dgrad(L["dyv"], L["w"], L["dxv"], accumulate=False)
     return lambda: op.run_wgrad(L["xv"], L["dyv"], L["w"].shape, dev)
@@ -67,8 +70,11 @@ def main():
     ap.add_argument("--variants", default="", help="comma-separated variant indices (default: all)")
     ap.add_argument("--what", default="fwd,dgrad,wgrad")
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--no-stats", action="store_true", help="forward without the InstanceNorm statistics epilogue")
     args = ap.parse_args()
     B = args.batch
+    global NO_STATS
+    NO_STATS = args.no_stats
     lib = _cabi.lib()
     layers = [
         layer("res 3x3 256->256 64x64 (+border 1)", 256, 256, 3, 1, 0, 64, 64, B, border=1),
@@ -77,6 +83,8 @@ def main():
         layer("down 3x3 s2 128->256 128->64", 128, 256, 3, 2, 1, 128, 128, B),
         layer("up convT 3x3 s2 256->128 64->128", 256, 128, 3, 2, 1, 64, 64, B, transposed=True, op_pad=1),
         layer("up convT 3x3 s2 128->64 128->256", 128, 64, 3, 2, 1, 128, 128, B, transposed=True, op_pad=1),
+        layer("first 7x7 3->64 256x256 (+border 3)", 3, 64, 7, 1, 0, 256, 256, B, border=3),
+        layer("last 7x7 64->3 256x256 (+border 3)", 64, 3, 7, 1, 0, 256, 256, B, border=3),
     ]
     variants = [
         ("per-tap, power-of-two patches", {9: 1, 0: 1}),
