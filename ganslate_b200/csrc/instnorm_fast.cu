@@ -462,7 +462,7 @@ int gb_in_fwd_fast(const gb_in_fwd_params& p, cudaStream_t st) {
   if (p.stats != nullptr && (uintptr_t)p.stats % 16 != 0) return -1;
   if (!row_addressable(x) || !row_addressable(p.y) || (has_res && !row_addressable(p.res))) return -1;
   if (!small_offsets(x) || !small_offsets(p.y) || (has_res && !small_offsets(p.res))) return -1;
-  if (x.pad != 0 || (has_res && p.res.pad != 0)) return -1;
+  // (x and res may be interior views of bordered buffers: only their interior is read)
   if (p.y.pad > 0 && (p.y.D != 1 || p.y.H <= 2 * p.y.pad + 1 || p.y.W <= 2 * p.y.pad + 1)) return -1;
   return has_res ? launch_fwd<true>(p, ns, st) : launch_fwd<false>(p, ns, st);
 }
@@ -484,7 +484,7 @@ int gb_in_bwd_fast(const gb_in_bwd_params& p, cudaStream_t st) {
   if (!row_addressable(x) || !row_addressable(p.dx) || !row_addressable(p.dy_b) || (has_res && !row_addressable(p.dy_sum)))
     return -1;
   if (!small_offsets(x) || !small_offsets(p.dx) || !small_offsets(p.dy_b) || (has_res && !small_offsets(p.dy_sum))) return -1;
-  if (x.pad != 0 || p.dx.pad != 0 || (has_res && p.dy_sum.pad != 0)) return -1;
+  // (x, dx and dy_sum may be interior views of bordered buffers: only their interior is touched)
   if (p.dy_b.pad > 0 && (p.dy_b.D != 1 || p.dy_b.H <= 2 * p.dy_b.pad + 1 || p.dy_b.W <= 2 * p.dy_b.pad + 1)) return -1;
   return has_res ? launch_bwd<true>(p, ns, st) : launch_bwd<false>(p, ns, st);
 }
