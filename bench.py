@@ -211,8 +211,11 @@ def run_b200(args):
     t, t_e2e = times.tolist()
 
     roof = None
-    if rank == 0 and not args.no_roofline:
+    if not args.no_roofline:
+        # every rank runs the profiled eager steps (they contain the gradient all-reduce: a rank that skipped them
+        # would leave the others waiting in NCCL); rank 0's timings are reported
         roof = profiler.conv_roofline(model, a_dev, b_dev, steps=3)
+        barrier()
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         rate, med, cores = cpu_step_rate(args.size, args.batch, steps=3, warmup=1)

@@ -14,7 +14,10 @@ def init_distributed():
         backend = "nccl" if torch.cuda.is_available() else "gloo"  # gloo only for the CPU host-logic tests
         if backend == "nccl":
             torch.cuda.set_device(get_local_rank())
-        dist.init_process_group(backend=backend, init_method="env://")
+            dist.init_process_group(backend=backend, init_method="env://",
+                                    device_id=torch.device("cuda", get_local_rank()))
+        else:
+            dist.init_process_group(backend=backend, init_method="env://")
         synchronize()
 
 
