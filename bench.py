@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--roofline-all-ranks", action="store_true", help="N>1: profile the per-kernel roofline too")
     return ap.parse_args()
 
 
@@ -211,13 +212,14 @@ def run_b200(args):
     t, t_e2e = times.tolist()
 
     roof = None
-    if not args.no_roofline:
-        # every rank runs the profiled eager steps (they contain the gradient all-reduce: a rank that skipped them
-        # would leave the others waiting in NCCL); rank 0's timings are reported
+    if not args.no_roofline and (world == 1 or args.roofline_all_ranks):
+        # per-kernel roofline: reported at N=1 (the kernels are the same at any N).  The profiled eager steps contain
+        # the gradient all-reduce, so at N>1 EVERY rank must run them (a rank-0-only run dead-locks NCCL: r01m);
+        # --roofline-all-ranks does that
         roof = profiler.conv_roofline(model, a_dev, b_dev, steps=3)
         barrier()
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, med, cores = cpu_step_rate(args.size, args.batch, steps=3, warmup=1)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"3 full CycleGAN steps (batch {args.batch}) of the CPU oracle after 1 warm-up, median"}

@@ -1,2 +1,3 @@
 from .resnet.resnet2d import Resnet2D  # noqa: F401
+from .unet.unet2d import Unet2D  # noqa: F401
 from .vnet.vnet3d import Vnet3D  # noqa: F401

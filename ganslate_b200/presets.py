@@ -46,6 +46,17 @@ def pix2pix_resnet2d(batch_size=8, lambda_pix2pix=30.0, n_residual_blocks=9, n_l
     return init_config(conf)
 
 
+def pix2pix_unet2d(batch_size=8, lambda_pix2pix=30.0, num_downs=7, ngf=128, use_dropout=True, n_layers=4,
+                   **train_overrides):
+    """projects/cityscapes_label2photo/experiments/pix2pix.yaml: Unet2D(num_downs 7, ngf 128, dropout) + PatchGAN2D
+    (n_layers 4) on cat[A, B], lambda 30."""
+    conf = pix2pix_resnet2d(batch_size, lambda_pix2pix, 9, n_layers, **train_overrides)
+    conf.train.gan.generator = init_config({"g": {"_target_": "ganslate_b200.nn.generators.Unet2D", "num_downs": num_downs,
+                                                  "ngf": ngf, "use_dropout": use_dropout,
+                                                  "in_out_channels": {"AB": [3, 3]}}}).g
+    return conf
+
+
 def cut_resnet2d(batch_size=1, n_residual_blocks=9, **train_overrides):
     """CUT defaults of ganslate/nn/gans/unpaired/cut.py:16-40 on Resnet2D + PatchGAN2D."""
     conf = {

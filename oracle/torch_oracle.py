@@ -84,6 +84,52 @@ class OraclePatchGAN2D(nn.Module):
         return self.model(x)
 
 
+class OracleUnetBlock(nn.Module):
+    """ganslate/nn/generators/unet/unet2d.py:81-157 (norm_type 'instance': conv bias on except where the reference
+    leaves the ConvTranspose2d default, i.e. the outermost up-convolution, which is biased as well)."""
+
+    def __init__(self, outer_nc, inner_nc, in_channels=None, submodule=None, outermost=False, innermost=False,
+                 use_dropout=False):
+        super().__init__()
+        self.outermost = outermost
+        in_channels = outer_nc if in_channels is None else in_channels
+        downconv = nn.Conv2d(in_channels, inner_nc, kernel_size=4, stride=2, padding=1, bias=True)
+        downrelu, downnorm = nn.LeakyReLU(0.2), _norm2d(inner_nc)
+        uprelu, upnorm = nn.ReLU(), _norm2d(outer_nc)
+        if outermost:  # :123-127
+            upconv = nn.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1)
+            model = [downconv, submodule, uprelu, upconv, nn.Tanh()]
+        elif innermost:  # :128-137
+            upconv = nn.ConvTranspose2d(inner_nc, outer_nc, kernel_size=4, stride=2, padding=1, bias=True)
+            model = [downrelu, downconv, uprelu, upconv, upnorm]
+        else:  # :138-151
+            upconv = nn.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1, bias=True)
+            model = [downrelu, downconv, downnorm, submodule, uprelu, upconv, upnorm]
+            if use_dropout:
+                model.append(nn.Dropout(0.5))
+        self.model = nn.Sequential(*model)
+
+    def forward(self, x):  # :153-157
+        return self.model(x) if self.outermost else torch.cat([x, self.model(x)], 1)
+
+
+class OracleUnet2D(nn.Module):
+    """ganslate/nn/generators/unet/unet2d.py:17-78"""
+
+    def __init__(self, in_channels, out_channels, num_downs, ngf=64, use_dropout=False):
+        super().__init__()
+        b = OracleUnetBlock(ngf * 8, ngf * 8, innermost=True)
+        for _ in range(num_downs - 5):
+            b = OracleUnetBlock(ngf * 8, ngf * 8, submodule=b, use_dropout=use_dropout)
+        b = OracleUnetBlock(ngf * 4, ngf * 8, submodule=b)
+        b = OracleUnetBlock(ngf * 2, ngf * 4, submodule=b)
+        b = OracleUnetBlock(ngf, ngf * 2, submodule=b)
+        self.model = OracleUnetBlock(out_channels, ngf, in_channels=in_channels, submodule=b, outermost=True)
+
+    def forward(self, x):
+        return self.model(x)
+
+
 def init_weights(net, gain=0.02):
     """ganslate/nn/utils.py:13-36 with weight_init_type='normal': N(0, gain) on every Conv/Linear weight in
     module order, zero bias."""
@@ -378,10 +424,15 @@ class OraclePix2Pix:
     """One iteration as ganslate/nn/gans/paired/pix2pix.py:76-152 runs it (Resnet2D generator, PatchGAN2D on
     cat[A, B]); lambda_pix2pix * L1 (pix2pix_losses.py:14-19)."""
 
-    def __init__(self, lambda_pix2pix=30.0, n_residual_blocks=9, n_layers=4, seed=0, lr=2e-4, bf16_points=False):
+    def __init__(self, lambda_pix2pix=30.0, n_residual_blocks=9, n_layers=4, seed=0, lr=2e-4, bf16_points=False,
+                 unet=None):
+        """unet: None (Resnet2D generator) or dict(num_downs, ngf) for the Unet2D generator of
+        projects/cityscapes_label2photo/experiments/pix2pix.yaml (dropout off: parity needs determinism)."""
         torch.manual_seed(seed)
         self.lam = lambda_pix2pix
-        self.networks = {"G": init_weights(OracleResnet2D(3, 3, n_residual_blocks)),      # dict order pix2pix.py:42
+        gen = OracleResnet2D(3, 3, n_residual_blocks) if unet is None else OracleUnet2D(3, 3, unet["num_downs"],
+                                                                                          ngf=unet["ngf"])
+        self.networks = {"G": init_weights(gen),                                          # dict order pix2pix.py:42
                          "D": init_weights(OraclePatchGAN2D(6, 64, n_layers))}
         if bf16_points:
             for net in self.networks.values():

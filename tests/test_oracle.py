@@ -267,3 +267,37 @@ def test_oracle3d_coupling_is_invertible_and_revgan_step_runs():
     assert set(losses) == {"G_AB", "G_BA", "cycle_A", "cycle_B", "D_B", "D_A"}
     assert all(torch.isfinite(torch.tensor(v)) for v in losses.values())
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.networks["G"].parameters())
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("num_downs,use_dropout", [(5, False), (7, True)])
+def test_oracle_unet2d_equals_reference_module(num_downs, use_dropout):
+    """OracleUnet2D (oracle/torch_oracle.py) against ganslate/nn/generators/unet/unet2d.py: same keys, same-seed
+    weights, identical outputs and gradients (eval mode when the blocks carry Dropout), and the B200 module mirrors
+    the state_dict and the initialisation."""
+    from ganslate_b200.nn.generators import Unet2D
+    from ganslate_b200.nn.utils import init_weights as b200_init
+    m = R.modules()
+    torch.manual_seed(5)
+    ref = m["Unet2D"](3, 2, num_downs, "instance", ngf=8, use_dropout=use_dropout)
+    m["init_weights"](ref, "normal", 0.02)
+    torch.manual_seed(5)
+    ora = O.init_weights(O.OracleUnet2D(3, 2, num_downs, ngf=8, use_dropout=use_dropout))
+    torch.manual_seed(5)
+    ours = Unet2D(3, 2, num_downs, "instance", ngf=8, use_dropout=use_dropout)
+    b200_init(ours, "normal", 0.02)
+    for other in (ora, ours):
+        assert list(ref.state_dict().keys()) == list(other.state_dict().keys())
+        for (k, a), (_, b) in zip(ref.state_dict().items(), other.state_dict().items()):
+            assert torch.equal(a, b), k
+    ref.eval(), ora.eval()
+    size = 2 ** num_downs
+    x = (torch.rand(2, 3, size, size) * 2 - 1).requires_grad_(True)
+    xo = x.detach().clone().requires_grad_(True)
+    yr, yo = ref(x), ora(xo)
+    assert yr.shape == (2, 2, size, size) and torch.allclose(yr, yo, atol=1e-6)
+    g = torch.randn_like(yr)
+    yr.backward(g), yo.backward(g)
+    assert torch.allclose(x.grad, xo.grad, atol=1e-6)
+    for (k, a), (_, b) in zip(ref.named_parameters(), ora.named_parameters()):
+        assert torch.allclose(a.grad, b.grad, atol=1e-5), k
