@@ -8,7 +8,7 @@ CSRC = ROOT / "csrc"
 LIB_DIR = ROOT / "_lib"
 LIB_PATH = LIB_DIR / "libganslate_b200.so"
 SOURCES = ["api.cu", "pack.cu", "layout.cu", "loss.cu", "instnorm.cu", "instnorm_fast.cu", "igemm_data.cu", "igemm_tma.cu", "igemm_halo.cu", "igemm_pair.cu", "igemm_wgrad.cu", "patchnce.cu",
-           "adam.cu"]
+           "adam.cu", "ssim.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",

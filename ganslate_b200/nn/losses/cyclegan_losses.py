@@ -1,5 +1,5 @@
 """Cycle-consistency and identity losses -- API of ganslate/nn/losses/cyclegan_losses.py:7-101.
-L1 terms run the fused value+gradient kernel (gb_l1)."""
+L1 terms run the fused value+gradient kernel (gb_l1), the SSIM term the stencil kernels (gb_ssim_fwd / _bwd)."""
 from ganslate_b200 import ops
 
 
@@ -29,14 +29,20 @@ class CycleGANLosses:
 
 
 class CycleLoss:
+    """cyclegan_losses.py:60-91: L1, or alpha * SSIM-distance((x + 1) / 2) + (1 - alpha) * L1 when proportion_ssim > 0
+    (the SSIM stencil runs in csrc/ssim.cu)."""
 
     def __init__(self, proportion_ssim):
-        if proportion_ssim > 0:
-            # the SSIM stencil kernel is a "next" row; every shipped YAML sets 0.
-            raise NotImplementedError("proportion_ssim > 0 (SSIM cycle loss) is not on the B200 path yet")
+        self.alpha = float(proportion_ssim)
+        self.beta = 1.0 - self.alpha
 
     def __call__(self, real, reconstructed):
-        return ops.L1Fn.apply(reconstructed, real)
+        cycle_loss_l1 = ops.L1Fn.apply(reconstructed, real)
+        if self.alpha > 0:
+            # (x + 1) / 2 folded into the kernel's input mapping; data_range 1 (cyclegan_losses.py:84-88)
+            cycle_loss_ssim = ops.SsimFn.apply(reconstructed, real, 0.5, 0.5, 1.0)
+            return self.alpha * cycle_loss_ssim + self.beta * cycle_loss_l1
+        return cycle_loss_l1
 
 
 class IdentityLoss:

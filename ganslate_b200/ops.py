@@ -718,6 +718,39 @@ class L1Fn(torch.autograd.Function):
         return (g if ctx.needs_input_grad[0] else None), (-g if ctx.needs_input_grad[1] else None)
 
 
+class SsimFn(torch.autograd.Function):
+    """SSIM distance of (x, y) mapped by (v + 1) / 2 (ganslate/nn/losses/cyclegan_losses.py:84-91 ->
+    nn/losses/utils/ssim.py:64-99): one stencil kernel forward, one backward; gradient wrt x only (y is the real
+    image in the reference's call)."""
+
+    @staticmethod
+    def forward(ctx, x, y, in_scale, in_shift, data_range):
+        _require_cuda(x, "SSIM operand")
+        if x.shape != y.shape or x.dim() not in (4, 5):
+            raise ValueError("SSIM operands must be two NxCxHxW or NxCxDxHxW tensors of the same shape")
+        xc, yc = x.contiguous().float(), y.detach().contiguous().float()
+        H, W = xc.shape[-2:]
+        planes = xc.numel() // (H * W)
+        loss = torch.zeros((), dtype=torch.float32, device=x.device)
+        _cabi.check(_cabi.lib().gb_ssim_fwd(xc.data_ptr(), yc.data_ptr(), planes, H, W, float(in_scale), float(in_shift),
+                                            float(data_range), loss.data_ptr(), _stream()), "gb_ssim_fwd")
+        ctx.save_for_backward(xc, yc)
+        ctx.args = (planes, H, W, float(in_scale), float(in_shift), float(data_range))
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None, None
+        xc, yc = ctx.saved_tensors
+        planes, H, W, sc, sh, dr = ctx.args
+        dl = dloss.detach().contiguous().float().reshape(1)
+        grad = torch.empty_like(xc)
+        _cabi.check(_cabi.lib().gb_ssim_bwd(xc.data_ptr(), yc.data_ptr(), planes, H, W, sc, sh, dr, dl.data_ptr(),
+                                            grad.data_ptr(), _stream()), "gb_ssim_bwd")
+        return grad, None, None, None, None
+
+
 class PatchNCEFn(torch.autograd.Function):
     """Per-row PatchNCE loss of (feat_q, feat_k) -- fused logits / mask / temperature / CE kernel
     (ganslate/nn/losses/cut_losses.py:14-43; feat_k is detached there, so only feat_q receives a gradient)."""

@@ -218,6 +218,17 @@ int gb_cl_to_nchw(const gb_view* src, float* dst, int C, int fold, int act, int 
 int gb_mse_const(const float* pred, float target, int64_t n, float* loss, float* grad, void* stream);
 int gb_l1(const float* a, const float* b, int64_t n, float* loss, float* grad_a, void* stream);
 
+/* SSIM distance loss, ganslate/nn/losses/utils/ssim.py:51-99 (CycleLoss with proportion_ssim > 0,
+ * ganslate/nn/losses/cyclegan_losses.py:77-101): x, y are [planes][H][W] fp32 (planes = N*C, or N*C*D for 5-D inputs,
+ * whose depth slices the reference filters as channels), mapped by v = in * in_scale + in_shift before use;
+ * 11-tap Gaussian (sigma 1.5), K = (0.01, 0.03).  loss (one fp32, zeroed by the caller) += mean over the valid
+ * (H-10) x (W-10) map of sqrt(relu(2 - S1 - S2)).  gb_ssim_bwd writes grad_x = dloss[0] * d loss / d x (x is the
+ * FIRST argument, the reconstructed image; dloss is a device scalar so the call can be captured in a CUDA graph). */
+int gb_ssim_fwd(const float* x, const float* y, int planes, int H, int W, float in_scale, float in_shift,
+                float data_range, float* loss, void* stream);
+int gb_ssim_bwd(const float* x, const float* y, int planes, int H, int W, float in_scale, float in_shift,
+                float data_range, const float* dloss, float* grad_x, void* stream);
+
 /* PatchNCE (CUT): q, k are [B*P][D] fp32 (k is detached in the reference, ganslate/nn/losses/cut_losses.py:16);
  * loss[r] = CE(cat(q_r.k_r, q_r.K_b^T with the own patch masked to -10) / T, 0); probs [B*P][P+1] is saved for
  * gb_patchnce_bwd, which writes dq = d loss / d q scaled by dloss[r]. */

@@ -152,11 +152,42 @@ def adversarial_lsgan(pred, target_is_real, real_label=1.0, fake_label=0.0):
     return F.mse_loss(pred, t.expand_as(pred))
 
 
-def cyclegan_losses(visuals, lambda_AB=10.0, lambda_BA=10.0, lambda_identity=0.0):
-    """ganslate/nn/losses/cyclegan_losses.py:31-58,73-101 with proportion_ssim = 0 (every shipped YAML)."""
+def ssim_distance(X, Y, data_range=1.0, win_size=11, win_sigma=1.5, K=(0.01, 0.03)):
+    """ganslate/nn/losses/utils/ssim.py:22-99: separable Gaussian ("valid") moments, S1 * S2-style terms, mean of
+    sqrt(relu(2 - S1 - S2)).  5-D inputs are viewed as (N*C) x D x H x W (:70-72): depth slices act as channels."""
+    if X.ndim == 5:
+        X, Y = X.reshape(-1, *X.shape[2:]), Y.reshape(-1, *Y.shape[2:])
+    ch = X.shape[1]
+    coords = torch.arange(win_size, dtype=X.dtype).float() - win_size // 2     # :36-41
+    g = torch.exp(-(coords ** 2) / (2 * win_sigma ** 2))
+    g = (g / g.sum()).to(X.dtype)
+    win = g.view(1, 1, 1, -1).repeat(ch, 1, 1, 1)
+
+    def blur(t):                                                                 # :44-49
+        t = F.conv2d(t, win, groups=ch)
+        return F.conv2d(t, win.transpose(2, 3), groups=ch)
+
+    C1, C2 = (K[0] * data_range) ** 2, (K[1] * data_range) ** 2                  # :80-81
+    mu1, mu2 = blur(X), blur(Y)
+    s1, s2, s12 = blur(X * X) - mu1 ** 2, blur(Y * Y) - mu2 ** 2, blur(X * Y) - mu1 * mu2
+    S1 = (2 * mu1 * mu2 + C1) / (mu1 ** 2 + mu2 ** 2 + C1)
+    S2 = (2 * s12 + C2) / (s1 + s2 + C2)
+    return torch.sqrt(torch.relu(2 - (S1 + S2))).mean()                          # :95-99
+
+
+def cycle_loss(real, rec, proportion_ssim=0.0):
+    """CycleLoss, ganslate/nn/losses/cyclegan_losses.py:60-91."""
+    l1 = F.l1_loss(rec, real)
+    if proportion_ssim > 0:
+        return proportion_ssim * ssim_distance((rec + 1) / 2, (real + 1) / 2, 1.0) + (1 - proportion_ssim) * l1
+    return l1
+
+
+def cyclegan_losses(visuals, lambda_AB=10.0, lambda_BA=10.0, lambda_identity=0.0, proportion_ssim=0.0):
+    """ganslate/nn/losses/cyclegan_losses.py:31-58,73-101 (proportion_ssim = 0 in every shipped YAML)."""
     out = {
-        "cycle_A": lambda_AB * F.l1_loss(visuals["rec_A"], visuals["real_A"]),
-        "cycle_B": lambda_BA * F.l1_loss(visuals["rec_B"], visuals["real_B"]),
+        "cycle_A": lambda_AB * cycle_loss(visuals["real_A"], visuals["rec_A"], proportion_ssim),
+        "cycle_B": lambda_BA * cycle_loss(visuals["real_B"], visuals["rec_B"], proportion_ssim),
     }
     if lambda_identity > 0:
         out["idt_B"] = lambda_AB * (F.l1_loss(visuals["idt_B"], visuals["real_B"]) * lambda_identity)

@@ -301,3 +301,27 @@ def test_oracle_unet2d_equals_reference_module(num_downs, use_dropout):
     assert torch.allclose(x.grad, xo.grad, atol=1e-6)
     for (k, a), (_, b) in zip(ref.named_parameters(), ora.named_parameters()):
         assert torch.allclose(a.grad, b.grad, atol=1e-5), k
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("shape", [(2, 3, 40, 37), (1, 2, 4, 24, 30)])
+def test_oracle_ssim_equals_reference(shape):
+    """oracle ssim_distance / cycle_loss against ganslate/nn/losses/utils/ssim.py and CycleLoss (values and gradients)."""
+    R.setup()
+    from ganslate.nn.losses.utils.ssim import SSIMLoss
+    from ganslate.nn.losses.cyclegan_losses import CycleLoss
+    torch.manual_seed(0)
+    real = torch.rand(shape) * 2 - 1
+    rec = (0.8 * real + 0.2 * (torch.rand(shape) * 2 - 1))
+    a, b = rec.clone().requires_grad_(True), rec.clone().requires_grad_(True)
+    lr = SSIMLoss()((a + 1) / 2, (real + 1) / 2, data_range=1)
+    lo = O.ssim_distance((b + 1) / 2, (real + 1) / 2, 1.0)
+    assert torch.allclose(lr, lo, atol=1e-7)
+    lr.backward(), lo.backward()
+    assert torch.allclose(a.grad, b.grad, atol=1e-8)
+    a.grad = b.grad = None
+    cr = CycleLoss(0.84)(real, a)
+    co = O.cycle_loss(real, b, 0.84)
+    assert torch.allclose(cr, co, atol=1e-7)
+    cr.backward(), co.backward()
+    assert torch.allclose(a.grad, b.grad, atol=1e-8)
