@@ -142,7 +142,6 @@ def run_b200(args):
     from ganslate_b200.presets import cyclegan_resnet2d
     from ganslate_b200.utils import communication
     from ganslate_b200.utils.builders import build_gan
-    from oracle import torch_oracle as O  # synthetic_batch only (shared input generator)
 
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
@@ -157,7 +156,10 @@ def run_b200(args):
     torch.manual_seed(0)
     conf = cyclegan_resnet2d(batch_size=args.batch, cuda_graph=not args.no_graph)
     model = build_gan(conf)
-    a_host, b_host = O.synthetic_batch(args.batch, 3, args.size, seed=1 + rank)
+    # synthetic inputs U(-1, 1) (images are normalised to [-1, 1] in the reference); each rank draws its own shard
+    gen = torch.Generator(device="cpu").manual_seed(1 + rank)
+    a_host = torch.rand((args.batch, 3, args.size, args.size), generator=gen) * 2 - 1
+    b_host = torch.rand((args.batch, 3, args.size, args.size), generator=gen) * 2 - 1
     a_host, b_host = a_host.pin_memory(), b_host.pin_memory()
     a_dev, b_dev = a_host.to(dev), b_host.to(dev)
     flush = torch.empty(2 * 126 * 1024 * 1024, dtype=torch.uint8, device=dev)

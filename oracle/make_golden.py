@@ -115,9 +115,43 @@ def reference_3d_small():
     return out
 
 
+def reference_unet2d_ssim():
+    """Reference Unet2D (ganslate/nn/generators/unet/unet2d.py, dropout off) output / gradients on a fixed input, and
+    reference SSIMLoss / CycleLoss(0.84) values and gradients (nn/losses/utils/ssim.py, cyclegan_losses.py:60-91)."""
+    m = R.modules()
+    from ganslate.nn.losses.utils.ssim import SSIMLoss
+    from ganslate.nn.losses.cyclegan_losses import CycleLoss
+    out = {}
+    torch.manual_seed(5)
+    net = m["Unet2D"](3, 2, 5, "instance", ngf=8, use_dropout=False)
+    m["init_weights"](net, "normal", 0.02)
+    gen = torch.Generator().manual_seed(7)
+    x = (torch.rand((2, 3, 32, 64), generator=gen) * 2 - 1).requires_grad_(True)
+    y = net(x)
+    y.square().sum().backward()
+    out["unet2d"] = {"config": dict(in_channels=3, out_channels=2, num_downs=5, ngf=8, seed=5, data_seed=7, shape=[2, 3, 32, 64]),
+                     "keys": list(net.state_dict().keys()), "y": tensor_digest(y), "dx": tensor_digest(x.grad),
+                     "grads": {k: tensor_digest(p.grad) for k, p in net.named_parameters()}}
+    out["ssim"] = []
+    for shape in ([2, 3, 40, 37], [1, 2, 4, 24, 30]):
+        gen = torch.Generator().manual_seed(11)
+        real = torch.rand(shape, generator=gen) * 2 - 1
+        rec = (0.8 * real + 0.2 * (torch.rand(shape, generator=gen) * 2 - 1)).requires_grad_(True)
+        l_ssim = SSIMLoss()((rec + 1) / 2, (real + 1) / 2, data_range=1)
+        (g_ssim,) = torch.autograd.grad(l_ssim, rec)
+        l_cyc = CycleLoss(0.84)(real, rec)
+        (g_cyc,) = torch.autograd.grad(l_cyc, rec)
+        out["ssim"].append({"shape": shape, "data_seed": 11, "ssim": float(l_ssim), "d_ssim": tensor_digest(g_ssim),
+                            "cycle_084": float(l_cyc), "d_cycle_084": tensor_digest(g_cyc)})
+    return out
+
+
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "unet2d_ssim.json"), "w") as f:
+        json.dump(reference_unet2d_ssim(), f)
+    print("unet2d_ssim written")
     with open(os.path.join(out_dir, "vnet3d_patchgan3d_small.json"), "w") as f:
         json.dump(reference_3d_small(), f)
     print("vnet3d_patchgan3d_small written")

@@ -325,3 +325,35 @@ def test_oracle_ssim_equals_reference(shape):
     assert torch.allclose(cr, co, atol=1e-7)
     cr.backward(), co.backward()
     assert torch.allclose(a.grad, b.grad, atol=1e-8)
+
+
+def test_oracle_unet2d_and_ssim_match_reference_golden():
+    """tests/golden/unet2d_ssim.json was produced by the reference's Unet2D / SSIMLoss / CycleLoss
+    (oracle/make_golden.py::reference_unet2d_ssim); this check needs no reference tree."""
+    with open(os.path.join(GOLDEN, "unet2d_ssim.json")) as f:
+        gold = json.load(f)
+    u = gold["unet2d"]
+    c = u["config"]
+    torch.manual_seed(c["seed"])
+    net = O.init_weights(O.OracleUnet2D(c["in_channels"], c["out_channels"], c["num_downs"], ngf=c["ngf"]))
+    assert list(net.state_dict().keys()) == u["keys"]
+    gen = torch.Generator().manual_seed(c["data_seed"])
+    x = (torch.rand(tuple(c["shape"]), generator=gen) * 2 - 1).requires_grad_(True)
+    y = net(x)
+    y.square().sum().backward()
+    assert_digest(digest(y), u["y"], "unet y")
+    assert_digest(digest(x.grad), u["dx"], "unet dx", rtol=1e-3)
+    for k, p in net.named_parameters():
+        assert_digest(digest(p.grad), u["grads"][k], k, rtol=1e-3)
+    for case in gold["ssim"]:
+        gen = torch.Generator().manual_seed(case["data_seed"])
+        real = torch.rand(tuple(case["shape"]), generator=gen) * 2 - 1
+        rec = (0.8 * real + 0.2 * (torch.rand(tuple(case["shape"]), generator=gen) * 2 - 1)).requires_grad_(True)
+        l = O.ssim_distance((rec + 1) / 2, (real + 1) / 2, 1.0)
+        (g,) = torch.autograd.grad(l, rec)
+        assert close(float(l), case["ssim"], 1e-5), (float(l), case["ssim"])
+        assert_digest(digest(g), case["d_ssim"], "d ssim", rtol=1e-3, atol=1e-9)
+        lc = O.cycle_loss(real, rec, 0.84)
+        (gc,) = torch.autograd.grad(lc, rec)
+        assert close(float(lc), case["cycle_084"], 1e-5)
+        assert_digest(digest(gc), case["d_cycle_084"], "d cycle", rtol=1e-3, atol=1e-9)
