@@ -13,7 +13,7 @@ from torch import nn
 from ganslate_b200 import configs, ops
 from ganslate_b200._cabi import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH
 from ganslate_b200.nn import layers
-from ganslate_b200.nn.utils import get_norm_layer_2d, is_bias_before_norm
+from ganslate_b200.nn.utils import get_norm_layer_2d, get_norm_layer_3d, is_bias_before_norm
 
 
 @dataclass
@@ -67,29 +67,32 @@ def step_dropout(tape, b, p):
 
 
 class UnetSkipConnectionBlock(nn.Module):
+    _dims = 2  # the 3-D generator (unet3d.py) is the same block over Conv3d / ConvTranspose3d / InstanceNorm3d
 
     def __init__(self, outer_nc, inner_nc, norm_type, in_channels=None, submodule=None, outermost=False,
                  innermost=False, use_dropout=False):
         super().__init__()
         self.outermost, self.innermost = outermost, innermost
-        norm_layer = get_norm_layer_2d(norm_type)
+        norm_layer = get_norm_layer_2d(norm_type) if self._dims == 2 else get_norm_layer_3d(norm_type)
+        Conv = layers.Conv2d if self._dims == 2 else layers.Conv3d
+        ConvT = layers.ConvTranspose2d if self._dims == 2 else layers.ConvTranspose3d
         use_bias = is_bias_before_norm(norm_type)
         if in_channels is None:
             in_channels = outer_nc
         self.in_nc, self.outer_nc = in_channels, outer_nc
-        downconv = layers.Conv2d(in_channels, inner_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
+        downconv = Conv(in_channels, inner_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
         downrelu = layers.LeakyReLU(0.2)
         downnorm = norm_layer(inner_nc)
         uprelu = layers.ReLU()
         upnorm = norm_layer(outer_nc)
         if outermost:
-            upconv = layers.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1)
+            upconv = ConvT(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1)
             model = [downconv] + [submodule] + [uprelu, upconv, layers.Tanh()]
         elif innermost:
-            upconv = layers.ConvTranspose2d(inner_nc, outer_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
+            upconv = ConvT(inner_nc, outer_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
             model = [downrelu, downconv] + [uprelu, upconv, upnorm]
         else:
-            upconv = layers.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
+            upconv = ConvT(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
             model = [downrelu, downconv, downnorm] + [submodule] + [uprelu, upconv, upnorm]
             if use_dropout:
                 model = model + [Dropout(0.5)]

@@ -281,6 +281,9 @@ def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0, want_stats=False) 
                 db = ops.zeros((y.shape[-1],), dev)
             g = ops.act_backward(ops.make_view(g), y, act, slope, dbias=db)  # fp32 d_buf -> bf16 d_raw (+ bias grad)
         gv = ops.make_view(g)
+        if op.bwd_window and (tape.needs(weight) or b.needs_grad_flag):
+            # gradient-side pixel windows (ops.ConvOp.bwd_window): dOut rows with zero pixels on both sides
+            gv = torch.nn.functional.pad(g, (0, 0, ops.BWD_BORDER, ops.BWD_BORDER))
         if tape.needs(weight):
             tape.add_param_grad(weight, op.run_wgrad(b.plain_view(), gv, weight.shape, dev, pending=tape.unpack))
         if tape.needs(bias):

@@ -72,8 +72,10 @@ def zeros(shape, device):
 # Optional per-launch timing (bench.py roofline): a list that receives (family, work, unit, event0, event1).
 PROFILE = None
 
-# Pixel-window formulation of small-channel unit-stride convolutions (ConvOp.window); tests switch it off for A/B.
+# Pixel-window formulation of small-channel unit-stride convolutions (ConvOp.window / .bwd_window); tests switch it
+# off for A/B.
 WINDOW_CONV = True
+BWD_BORDER = 8  # zero pixels left and right of every dOut row in bwd_window mode (>= kw - 1)
 
 
 def _call(family, work, unit, what, fn, *args):
@@ -240,6 +242,27 @@ class ConvOp:
                 self.wg_swap = True
                 self.wg_kpad, self.wg_rows, self.wg_rows_pad = sw_kpad, cin, sw_rows_pad
                 self.wg_taps = [tuple(-v for v in t) for t in self.wg_taps]
+        # Pixel windows on the GRADIENT side of a unit-stride convolution with <= 8 output channels (the generators'
+        # 7x7 -> 3 output layer): both its data gradient and its (operand-swapped) weight gradient gather dOut
+        # through the taps p - r, i.e. kw consecutive pixels of a dOut row per (dz, dy) -- with dOut copied into a
+        # buffer that has BWD_BORDER zero pixels left and right of every row, the window never leaves the row and both
+        # GEMMs run on the TMA-fed kernels (K blocks (j, co), j = window position <-> rx = kw - 1 - j).
+        self.bwd_window = (bool(WINDOW_CONV) and self.wg_swap and not transposed and all(s == 1 for s in self.stride)
+                           and self.cout_pad == 8 and 1 < kernel[2] <= 8 and self.cin_pad % 64 == 0
+                           and self.padding[2] <= 1 and kernel[0] * kernel[1] <= _cabi.GB_MAX_TAPS // 8
+                           and (WINDOW_CONV == "force" or _cabi.lib().gb_tma_window_supported() == 1))
+        if self.bwd_window:
+            kd, kh, kw = self.kernel
+            pz, py, px = self.padding
+            blocks = [(rz, ry) for rz in range(kd) for ry in range(kh)]
+            # TMA x offset of a window: first tap column (px - kw + 1) shifted by the left border of the buffer
+            self.bw_taps = [(pz - rz, py - ry, px - kw + 1 + BWD_BORDER) for rz, ry in blocks]
+            self.bw_pack_ids = [((rz * kh + ry) * kw + (kw - 1 - j)) if j < kw else -1 for rz, ry in blocks for j in range(8)]
+            self.bw_kpad = len(blocks) * 64
+            self.dgrad = DataSpec((1, 1, 1), (1, 1, 1), [dict(off=(0, 0, 0), taps=self.bw_taps,
+                                                              tap_ids=list(range(len(blocks))))])
+            self.dgrad.finalize(64, self.dgrad_rows_pad)
+            self.wg_taps, self.wg_kpad = list(self.bw_taps), self.bw_kpad
         self._packed = {}
 
     # ------------------------------------------------------------------ shapes
@@ -281,8 +304,8 @@ class ConvOp:
         p.sn, p.sc, p.st = sn, sc, st
         p.rows, p.rows_pad, p.chans, p.chans_pad = rows, rows_pad, chans, chans_pad
         p.nclass = len(spec.classes)
-        if which == "fwd" and self.window:
-            ids = self.win_pack_ids
+        if (which == "fwd" and self.window) or (which == "dgrad" and self.bwd_window):
+            ids = self.win_pack_ids if which == "fwd" else self.bw_pack_ids
             p.ntaps[0], p.kpad[0], p.w_offset[0], p.tap_begin[0] = len(ids), spec.kpads[0], 0, 0
             for j, t in enumerate(ids):
                 p.tap_id[j] = t
@@ -348,11 +371,26 @@ class ConvOp:
               C.byref(p), _stream())
         return y
 
-    def run_dgrad(self, dyv: View, weight, outv: View, accumulate: bool):
+    def bwd_window_view(self, gw: torch.Tensor) -> View:
+        """gw: dOut copied into a (N, D, Ho, Wo + 2*BWD_BORDER, 8) buffer with zero borders -> the 64-"channel" window
+        view over the WHOLE rows (origin = buffer start; the taps carry the border shift)."""
+        N, D, H, Wb, Cc = gw.shape
+        assert Cc == 8 and gw.is_contiguous()
+        v = View()
+        v.ptr = gw.data_ptr()
+        v.sn, v.sz, v.sy, v.sx = D * H * Wb * 8, H * Wb * 8, Wb * 8, 8
+        v.N, v.D, v.H, v.W, v.C, v.pad = N, D, H, Wb - self.kernel[2] + 1, 64, 0
+        return v
+
+    def run_dgrad(self, dyv, weight, outv: View, accumulate: bool):
         """dyv: bf16 view (N,D,Ho,Wo,cout_pad); the gradient wrt the input is written / accumulated into the FP32
-        view outv (plain view of the input buffer's gradient, channel slice allowed)."""
-        assert dyv.C == self.cout_pad and outv.C == self.cin_pad and outv.pad == 0
+        view outv (plain view of the input buffer's gradient, channel slice allowed).  In bwd_window mode dyv is the
+        zero-bordered TENSOR (see bwd_window_view)."""
+        if self.bwd_window:
+            dyv = self.bwd_window_view(dyv)
+        assert (self.bwd_window or dyv.C == self.cout_pad) and outv.C == self.cin_pad and outv.pad == 0
         p = self._params("dgrad")
+        p.in_c_valid = self.kernel[2] * 8 if self.bwd_window else 0
         p.out_fp32, p.accumulate = 1, 1 if accumulate else 0
         p.stats = None
         p.inp, p.out = dyv, outv
@@ -390,7 +428,7 @@ class ConvOp:
 
     def run_wgrad(self, xv: View, dyv: View, weight_shape, device, pending=None):
         """fp32 weight gradient in the PyTorch layout of `weight_shape` (xv: plain input view, dyv: bf16 d_raw)."""
-        if self.window:
+        if self.window or self.bwd_window:
             return self._run_wgrad_window(xv, dyv, weight_shape, device, pending)
         plan = self.wgrad_plan()
         plain, gathered = (xv, dyv) if plan["plain_is_input"] else (dyv, xv)
@@ -438,7 +476,10 @@ def _conv_op_window_wgrad(self, xv, dyv, weight_shape, device, pending):
         p.rows, p.kpad, p.splits = self.wg_rows, self.wg_kpad, 0
         p.gathered_c_valid = kw * 8
         cache["wgrad"] = p
-    p.plain, p.gathered, p.dw = dyv, self.window_view(xv), ws.data_ptr()
+    if self.bwd_window:   # operand-swapped: rows = input channels, gathered = dOut windows (dyv: zero-bordered tensor)
+        p.plain, p.gathered, p.dw = xv, self.bwd_window_view(dyv), ws.data_ptr()
+    else:
+        p.plain, p.gathered, p.dw = dyv, self.window_view(xv), ws.data_ptr()
     _call("conv_wgrad", self.flops((xv.D, xv.H, xv.W), xv.N), "flop", "gb_conv_wgrad", _cabi.lib().gb_conv_wgrad,
           C.byref(p), _stream())
     dw = torch.empty(weight_shape, dtype=torch.float32, device=device)
@@ -456,6 +497,11 @@ def _conv_op_window_unpack_items(self):
     """gb_unpack_wgrad items of a pixel-window weight gradient: K block b = (dz, dy) holds kw taps of 8 channels;
     PyTorch layout (cout, cin, kd*kh*kw): row stride cin*T, channel stride T, tap stride 1."""
     kd, kh, kw = self.kernel
+    if self.bwd_window:
+        # workspace rows = input channel, columns (block, j, co) with rx = kw - 1 - j: walk the taps backwards
+        return [dict(ws_off=b * 64, dst_off=b * kw + kw - 1, dsr=self.T, dsc=self.cin * self.T, dst_t=-1,
+                     rows=self.wg_rows, chans=self.cout, chans_pad=8, ntaps=kw, kpad=self.wg_kpad)
+                for b in range(kd * kh)]
     return [dict(ws_off=b * 64, dst_off=b * kw, dsr=self.cin * self.T, dsc=self.T, dst_t=1, rows=self.wg_rows,
                  chans=self.cin, chans_pad=8, ntaps=kw, kpad=self.wg_kpad) for b in range(kd * kh)]
 

@@ -85,25 +85,27 @@ class OraclePatchGAN2D(nn.Module):
 
 
 class OracleUnetBlock(nn.Module):
-    """ganslate/nn/generators/unet/unet2d.py:81-157 (norm_type 'instance': conv bias on except where the reference
-    leaves the ConvTranspose2d default, i.e. the outermost up-convolution, which is biased as well)."""
+    """ganslate/nn/generators/unet/unet2d.py:81-157 and unet3d.py:81-157 (the same block over 2-D / 3-D layers;
+    norm_type 'instance': conv bias on, the outermost up-convolution keeps the ConvTranspose default = biased)."""
 
     def __init__(self, outer_nc, inner_nc, in_channels=None, submodule=None, outermost=False, innermost=False,
-                 use_dropout=False):
+                 use_dropout=False, dims=2):
         super().__init__()
         self.outermost = outermost
+        Conv, ConvT = (nn.Conv2d, nn.ConvTranspose2d) if dims == 2 else (nn.Conv3d, nn.ConvTranspose3d)
+        norm = _norm2d if dims == 2 else nn.InstanceNorm3d
         in_channels = outer_nc if in_channels is None else in_channels
-        downconv = nn.Conv2d(in_channels, inner_nc, kernel_size=4, stride=2, padding=1, bias=True)
-        downrelu, downnorm = nn.LeakyReLU(0.2), _norm2d(inner_nc)
-        uprelu, upnorm = nn.ReLU(), _norm2d(outer_nc)
+        downconv = Conv(in_channels, inner_nc, kernel_size=4, stride=2, padding=1, bias=True)
+        downrelu, downnorm = nn.LeakyReLU(0.2), norm(inner_nc)
+        uprelu, upnorm = nn.ReLU(), norm(outer_nc)
         if outermost:  # :123-127
-            upconv = nn.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1)
+            upconv = ConvT(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1)
             model = [downconv, submodule, uprelu, upconv, nn.Tanh()]
         elif innermost:  # :128-137
-            upconv = nn.ConvTranspose2d(inner_nc, outer_nc, kernel_size=4, stride=2, padding=1, bias=True)
+            upconv = ConvT(inner_nc, outer_nc, kernel_size=4, stride=2, padding=1, bias=True)
             model = [downrelu, downconv, uprelu, upconv, upnorm]
         else:  # :138-151
-            upconv = nn.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1, bias=True)
+            upconv = ConvT(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1, bias=True)
             model = [downrelu, downconv, downnorm, submodule, uprelu, upconv, upnorm]
             if use_dropout:
                 model.append(nn.Dropout(0.5))
@@ -114,20 +116,26 @@ class OracleUnetBlock(nn.Module):
 
 
 class OracleUnet2D(nn.Module):
-    """ganslate/nn/generators/unet/unet2d.py:17-78"""
+    """ganslate/nn/generators/unet/unet2d.py:17-78 (dims=3: unet3d.py:17-78)"""
 
-    def __init__(self, in_channels, out_channels, num_downs, ngf=64, use_dropout=False):
+    def __init__(self, in_channels, out_channels, num_downs, ngf=64, use_dropout=False, dims=2):
         super().__init__()
-        b = OracleUnetBlock(ngf * 8, ngf * 8, innermost=True)
+        b = OracleUnetBlock(ngf * 8, ngf * 8, innermost=True, dims=dims)
         for _ in range(num_downs - 5):
-            b = OracleUnetBlock(ngf * 8, ngf * 8, submodule=b, use_dropout=use_dropout)
-        b = OracleUnetBlock(ngf * 4, ngf * 8, submodule=b)
-        b = OracleUnetBlock(ngf * 2, ngf * 4, submodule=b)
-        b = OracleUnetBlock(ngf, ngf * 2, submodule=b)
-        self.model = OracleUnetBlock(out_channels, ngf, in_channels=in_channels, submodule=b, outermost=True)
+            b = OracleUnetBlock(ngf * 8, ngf * 8, submodule=b, use_dropout=use_dropout, dims=dims)
+        b = OracleUnetBlock(ngf * 4, ngf * 8, submodule=b, dims=dims)
+        b = OracleUnetBlock(ngf * 2, ngf * 4, submodule=b, dims=dims)
+        b = OracleUnetBlock(ngf, ngf * 2, submodule=b, dims=dims)
+        self.model = OracleUnetBlock(out_channels, ngf, in_channels=in_channels, submodule=b, outermost=True, dims=dims)
 
     def forward(self, x):
         return self.model(x)
+
+
+class OracleUnet3D(OracleUnet2D):
+
+    def __init__(self, in_channels, out_channels, num_downs, ngf=64, use_dropout=False):
+        super().__init__(in_channels, out_channels, num_downs, ngf, use_dropout, dims=3)
 
 
 def init_weights(net, gain=0.02):

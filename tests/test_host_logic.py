@@ -239,3 +239,70 @@ def test_pixel_window_formulation_reproduces_torch():
                     dst[it["dst_off"] + r * it["dsr"] + c * it["dsc"] + t * it["dst_t"]] = \
                         dw[r, it["ws_off"] + t * it["chans_pad"] + c]
     np.testing.assert_allclose(dst.reshape(cout, cin, 7, 7), w.grad.numpy()[:, :, 0], rtol=1e-4, atol=1e-4)
+
+
+def test_gradient_side_pixel_windows_reproduce_torch():
+    """ConvOp.bwd_window (7x7 convolution 64 -> 3 channels): data gradient and operand-swapped weight gradient
+    gathered as 7-pixel windows of the zero-bordered dOut rows, evaluated literally, against torch autograd."""
+    torch.manual_seed(1)
+    old = ops.WINDOW_CONV
+    ops.WINDOW_CONV = "force"
+    try:
+        op = ops.ConvOp(64, 3, (1, 7, 7), (1, 1, 1), (0, 0, 0))
+    finally:
+        ops.WINDOW_CONV = old
+    assert op.bwd_window and not op.window and op.wg_swap
+    N, Hin, Win, cin, cout, kw, T, BL = 2, 10, 12, 64, 3, 7, 49, ops.BWD_BORDER
+    Ho, Wo = Hin - 6, Win - 6
+    x = torch.randn(N, cin, 1, Hin, Win, requires_grad=True)
+    w = torch.randn(cout, cin, 1, 7, 7, requires_grad=True)
+    y = F.conv3d(x, w)
+    g = torch.randn_like(y)
+    y.backward(g)
+    # zero-bordered channels-last dOut: (N, Ho, Wo + 2*BL, 8), flat, NaN sentinel behind it
+    gw = np.zeros((N, Ho, Wo + 2 * BL, 8))
+    gw[:, :, BL:BL + Wo, :cout] = g.numpy()[:, :, 0].transpose(0, 2, 3, 1)
+    Wb = Wo + 2 * BL
+    flat = np.concatenate([gw.reshape(-1), np.full(64, np.nan)])
+
+    def window(n, yy, xs):  # window at row yy, start column xs of the buffer; rows outside the tensor read as zero
+        if not (0 <= yy < Ho):
+            return np.zeros(64)
+        assert 0 <= xs <= Wb - kw, xs
+        base = ((n * Ho + yy) * Wb + xs) * 8
+        return np.concatenate([flat[base:base + kw * 8], np.zeros(64 - kw * 8)])
+
+    # packed data-gradient weights as pack_class() builds them from bw_pack_ids and dgrad_strides
+    sn, sc, st = op.dgrad_strides
+    wflat = w.detach().numpy().reshape(-1)
+    kp = op.dgrad.kpads[0]
+    wp = np.zeros((cin, kp))
+    for k in range(kp):
+        tl, c = divmod(k, 8)
+        tid = op.bw_pack_ids[tl] if tl < len(op.bw_pack_ids) else -1
+        if tid >= 0 and c < cout:
+            wp[:, k] = [wflat[n * sn + c * sc + tid * st] for n in range(cin)]
+    taps = op.dgrad.classes[0]["taps"]
+    dx = np.zeros((N, cin, Hin, Win))
+    for n in range(N):
+        for yy in range(Hin):
+            for xx in range(Win):
+                a = np.concatenate([window(n, yy + t[1], xx + t[2]) for t in taps])
+                dx[n, :, yy, xx] = wp @ a
+    np.testing.assert_allclose(dx, x.grad.numpy()[:, :, 0], rtol=1e-4, atol=1e-4)
+    # swapped weight gradient: dw[ci][blk*64 + j*8 + co] = sum_q' x[q'][ci] * window[q' + tap_blk][j*8 + co]
+    xn = x.detach().numpy()[:, :, 0]
+    dw = np.zeros((op.wg_rows_pad, op.wg_kpad))
+    for n in range(N):
+        for yy in range(Hin):
+            for xx in range(Win):
+                a = np.concatenate([window(n, yy + t[1], xx + t[2]) for t in op.wg_taps])
+                dw[:cin] += np.outer(xn[n, :, yy, xx], a)
+    dst = np.zeros(cout * cin * T)
+    for it in op.window_unpack_items():
+        for r in range(it["rows"]):
+            for c in range(it["chans"]):
+                for t in range(it["ntaps"]):
+                    dst[it["dst_off"] + r * it["dsr"] + c * it["dsc"] + t * it["dst_t"]] = \
+                        dw[r, it["ws_off"] + t * it["chans_pad"] + c]
+    np.testing.assert_allclose(dst.reshape(cout, cin, 7, 7), w.grad.numpy()[:, :, 0], rtol=1e-4, atol=1e-4)

@@ -357,3 +357,31 @@ def test_oracle_unet2d_and_ssim_match_reference_golden():
         (gc,) = torch.autograd.grad(lc, rec)
         assert close(float(lc), case["cycle_084"], 1e-5)
         assert_digest(digest(gc), case["d_cycle_084"], "d cycle", rtol=1e-3, atol=1e-9)
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference only exists in the build container")
+def test_oracle_unet3d_equals_reference_module():
+    from ganslate_b200.nn.generators import Unet3D
+    from ganslate_b200.nn.utils import init_weights as b200_init
+    R.setup()
+    from ganslate.nn.generators.unet.unet3d import Unet3D as RefUnet3D
+    m = R.modules()
+    torch.manual_seed(6)
+    ref = RefUnet3D(1, 1, 5, "instance", ngf=8)
+    m["init_weights"](ref, "normal", 0.02)
+    torch.manual_seed(6)
+    ora = O.init_weights(O.OracleUnet3D(1, 1, 5, ngf=8))
+    torch.manual_seed(6)
+    ours = Unet3D(1, 1, 5, "instance", ngf=8)
+    b200_init(ours, "normal", 0.02)
+    for other in (ora, ours):
+        assert list(ref.state_dict().keys()) == list(other.state_dict().keys())
+        for (k, a), (_, b) in zip(ref.state_dict().items(), other.state_dict().items()):
+            assert torch.equal(a, b), k
+    x = (torch.rand(1, 1, 32, 32, 32) * 2 - 1).requires_grad_(True)
+    xo = x.detach().clone().requires_grad_(True)
+    yr, yo = ref(x), ora(xo)
+    assert torch.allclose(yr, yo, atol=1e-6)
+    g = torch.randn_like(yr)
+    yr.backward(g), yo.backward(g)
+    assert torch.allclose(x.grad, xo.grad, atol=1e-6)

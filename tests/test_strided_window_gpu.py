@@ -89,3 +89,25 @@ def test_window_forward_is_tma_fed():
     ref = torch.nn.functional.conv2d(x[:, 0, :, :, :3].permute(0, 3, 1, 2).float(), w.to(torch.bfloat16).float())
     got = y[:, 0].permute(0, 3, 1, 2).float()
     assert ((got - ref).abs().max() / ref.abs().max()).item() < 1e-2
+
+
+BWD_WINDOW = [
+    dict(name="7x7 reflect3 64->3 tanh 64x64", cin=64, cout=3, k=7, s=1, p=0, H=64, W=64, reflect=3, act="tanh"),
+    dict(name="7x7 reflect3 64->3 37x53 N=3", cin=64, cout=3, k=7, s=1, p=0, H=37, W=53, N=3, reflect=3),
+    dict(name="7x7 p0 128->1 40x40", cin=128, cout=1, k=7, s=1, p=0, H=40, W=40, N=2),
+    dict(name="5x5 p1 64->8 24x31", cin=64, cout=8, k=5, s=1, p=1, H=24, W=31),
+]
+
+
+@pytest.mark.parametrize("case", BWD_WINDOW, ids=[c["name"] for c in BWD_WINDOW])
+def test_gradient_side_pixel_windows(case):
+    """Output layers with <= 8 channels: data gradient and operand-swapped weight gradient through 7-pixel windows of
+    the zero-bordered dOut (ops.ConvOp.bwd_window) -- both TMA-fed; control = the tap formulation on the gather path."""
+    from ganslate_b200 import ops
+    _run({}, expect_data=TMA, expect_wgrad=1, **case)
+    old = ops.WINDOW_CONV
+    ops.WINDOW_CONV = False
+    try:
+        _run({}, expect_wgrad=0, **dict(case, name=case["name"] + " (control: tap formulation)"))
+    finally:
+        ops.WINDOW_CONV = old

@@ -98,3 +98,32 @@ def test_pix2pix_unet_step_vs_oracle():
         for k in po:
             if k.endswith("weight"):
                 assert cosine(pg[k].grad, po[k].grad) > 0.9, (name, k)
+
+
+def test_unet3d_vs_oracle():
+    """Unet3D (ganslate/nn/generators/unet/unet3d.py): the same block over 3-D layers (k4 s2 p1 convolutions and
+    transposed convolutions = 8 parity classes of 8 taps, InstanceNorm3d, channel-slice concatenation)."""
+    from ganslate_b200.nn.generators import Unet3D
+    from oracle import torch_oracle as O
+    from parity_util import cosine, rel_l2
+    torch.manual_seed(0)
+    ref = O.init_weights(O.OracleUnet3D(1, 1, 5, ngf=8))
+    ours = Unet3D(1, 1, 5, "instance", ngf=8).cuda()
+    _load(ours, ref)
+    g0 = torch.Generator().manual_seed(9)
+    x = torch.rand((1, 1, 32, 32, 64), generator=g0) * 2 - 1
+    xr, xo = x.clone().requires_grad_(True), x.clone().cuda().requires_grad_(True)
+    yr, yo = ref(xr), ours(xo)
+    assert yo.shape == yr.shape and rel_l2(yo, yr) <= 3e-2, rel_l2(yo, yr)
+    g = torch.randn_like(yr)
+    yr.backward(g)
+    yo.backward(g.cuda())
+    torch.cuda.synchronize()
+    assert cosine(xo.grad, xr.grad) >= 0.95
+    bad = []
+    for (k, p), (_, q) in zip(ref.named_parameters(), ours.named_parameters()):
+        if k.endswith("weight"):
+            c = cosine(q.grad, p.grad)
+            if c < 0.95:
+                bad.append((k, c))
+    assert not bad, bad
