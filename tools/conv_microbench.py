@@ -46,7 +46,10 @@ def layer(name, cin, cout, k, stride, pad, H, W, N, border=0, transposed=False, 
     dx = torch.zeros(N, 1, H + 2 * border, W + 2 * border, op.cin_pad, device=dev, dtype=torch.float32)
     stats = torch.zeros(N, op.cout_pad, 2, device=dev)
     fl = op.flops((1, H + 2 * border, W + 2 * border), N)
-    return dict(name=name, op=op, w=w, bias=bias, xv=xv, x=x, dy=dy, dyv=ops.make_view(dy), dxv=ops.make_view(dx), dx=dx,
+    # gradient-side pixel windows read dOut from a zero-bordered copy (the pad kernel is part of the real step, not of
+    # this launch timing)
+    dyv = torch.nn.functional.pad(dy, (0, 0, ops.BWD_BORDER, ops.BWD_BORDER)) if op.bwd_window else ops.make_view(dy)
+    return dict(name=name, op=op, w=w, bias=bias, xv=xv, x=x, dy=dy, dyv=dyv, dxv=ops.make_view(dx), dx=dx,
                 stats=stats, flops=fl)
 
 
