@@ -7,6 +7,7 @@ gradient is a buffer of the same (padded) shape whose border is folded back by t
 """
 import ctypes as C
 import itertools
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Tuple
 
@@ -75,6 +76,10 @@ PROFILE = None
 # Pixel-window formulation of small-channel unit-stride convolutions (ConvOp.window / .bwd_window); tests switch it
 # off for A/B.
 WINDOW_CONV = True
+# The gradient-side windows (ConvOp.bwd_window) are verified on the CPU against torch (tests/test_host_logic.py) but
+# have not run on a B200 yet: opt-in (GB_BWD_WINDOW=1, or WINDOW_CONV = "force") until the GPU parity tests
+# (tests/test_strided_window_gpu.py::test_gradient_side_pixel_windows, GB_EXPERIMENTAL=1) have passed there.
+BWD_WINDOW_CONV = os.environ.get("GB_BWD_WINDOW", "0") == "1"
 BWD_BORDER = 8  # zero pixels left and right of every dOut row in bwd_window mode (>= kw - 1)
 
 
@@ -247,7 +252,7 @@ class ConvOp:
         # through the taps p - r, i.e. kw consecutive pixels of a dOut row per (dz, dy) -- with dOut copied into a
         # buffer that has BWD_BORDER zero pixels left and right of every row, the window never leaves the row and both
         # GEMMs run on the TMA-fed kernels (K blocks (j, co), j = window position <-> rx = kw - 1 - j).
-        self.bwd_window = (bool(WINDOW_CONV) and self.wg_swap and not transposed and all(s == 1 for s in self.stride)
+        self.bwd_window = (bool(WINDOW_CONV) and (BWD_WINDOW_CONV or WINDOW_CONV == "force") and self.wg_swap and not transposed and all(s == 1 for s in self.stride)
                            and self.cout_pad == 8 and 1 < kernel[2] <= 8 and self.cin_pad % 64 == 0
                            and self.padding[2] <= 1 and kernel[0] * kernel[1] <= _cabi.GB_MAX_TAPS // 8
                            and (WINDOW_CONV == "force" or _cabi.lib().gb_tma_window_supported() == 1))

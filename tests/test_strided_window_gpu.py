@@ -99,12 +99,17 @@ BWD_WINDOW = [
 ]
 
 
+@pytest.mark.experimental
 @pytest.mark.parametrize("case", BWD_WINDOW, ids=[c["name"] for c in BWD_WINDOW])
 def test_gradient_side_pixel_windows(case):
     """Output layers with <= 8 channels: data gradient and operand-swapped weight gradient through 7-pixel windows of
     the zero-bordered dOut (ops.ConvOp.bwd_window) -- both TMA-fed; control = the tap formulation on the gather path."""
     from ganslate_b200 import ops
-    _run({}, expect_data=TMA, expect_wgrad=1, **case)
+    old_bw, ops.BWD_WINDOW_CONV = ops.BWD_WINDOW_CONV, True
+    try:
+        _run({}, expect_data=TMA, expect_wgrad=1, **case)
+    finally:
+        ops.BWD_WINDOW_CONV = old_bw
     old = ops.WINDOW_CONV
     ops.WINDOW_CONV = False
     try:
