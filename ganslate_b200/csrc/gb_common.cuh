@@ -9,7 +9,7 @@
 
 // ---------------------------------------------------------------- error plumbing (host)
 void gb_set_error(const char* fmt, ...);
-extern int g_gb_knobs[16];
+extern int g_gb_knobs[32];
 extern unsigned long long g_gb_launches;  // kernels launched through the ABI (bench.py reports it)
 #define GB_CHECK(cond, ...)        \
   do {                             \
