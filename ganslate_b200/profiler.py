@@ -20,6 +20,24 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_traffic(family, batch):
+    """DRAM bytes per launch of the family's dominant kernel from the committed ncu --set full capture
+    (profiles/ncu_traffic_r*.json, latest round), or (None, None) when no capture of this batch size exists."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prof = os.path.join(here, "profiles")
+    try:
+        names = sorted(n for n in os.listdir(prof) if n.startswith("ncu_traffic_r") and n.endswith(".json"))
+    except OSError:
+        return None, None
+    for name in reversed(names):
+        with open(os.path.join(prof, name)) as f:
+            d = json.load(f)
+        if d.get("batch") == batch and family in d:
+            e = d[family]
+            return e["bytes_per_launch"], f"{e['kernel']}: {e['source']}"
+    return None, None
+
+
 def conv_roofline(model, a_dev, b_dev, steps=3):
     """Run `steps` EAGER training steps with every C-ABI launch bracketed by CUDA events and aggregate per
     family. Returns {"dominant": roofline object of the family with the largest share, "detail": {...}}."""
@@ -72,4 +90,7 @@ def conv_roofline(model, a_dev, b_dev, steps=3):
         "share_of_kernel_time": round(t_conv / total_t, 4),
         "how": "algorithmic FLOPs (SURVEY 8d) / CUDA-event time around each launch, eager steps",
     }
+    traffic, src = ncu_traffic("conv", int(a_dev.shape[0]))
+    if traffic is not None:
+        dominant["traffic"], dominant["traffic_source"] = traffic, src
     return {"dominant": dominant, "detail": detail}
