@@ -101,6 +101,8 @@ _SIGNATURES = {
     "gb_in_bwd": [C.POINTER(InBwdParams), C.c_void_p],
     "gb_nchw_to_cl": [C.c_void_p, C.c_int, C.POINTER(View), C.POINTER(View), C.c_int, C.c_void_p],
     "gb_cl_to_nchw": [C.POINTER(View), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p],
+    "gb_replicate_pad_fwd": [C.POINTER(View), C.POINTER(View), C.c_int, C.c_int, C.c_int, C.c_void_p],
+    "gb_replicate_pad_bwd": [C.POINTER(View), C.POINTER(View), C.c_int, C.c_int, C.c_int, C.c_void_p],
     "gb_mse_const": [C.c_void_p, C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     "gb_l1": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     "gb_ssim_fwd": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p,

@@ -14,7 +14,8 @@ from torch import nn
 from ganslate_b200 import configs, ops
 from ganslate_b200._cabi import ACT_NONE, ACT_PRELU, ACT_TANH
 from ganslate_b200.nn import invertible, layers
-from ganslate_b200.nn.utils import get_norm_layer_3d, is_bias_before_norm
+from ganslate_b200.nn.utils import (get_conv_layer_3d, get_conv_transpose_layer_3d, get_norm_layer_3d,
+                                    is_bias_before_norm)
 
 
 @dataclass
@@ -29,7 +30,7 @@ class Vnet3DConfig(configs.base.BaseGeneratorConfig):
 
 def _conv_norm_prelu(tape, b, seq, out=None):
     """[conv, norm, PReLU] group."""
-    raw = layers.step_conv(tape, b, seq[0], want_stats=True)
+    raw = layers.step_conv_any(tape, b, seq[0], want_stats=True)
     return layers.step_norm_act(tape, raw, True, ACT_PRELU, 0.0, 0, seq[1].eps, prelu=seq[2], out=out)
 
 
@@ -38,8 +39,6 @@ class Vnet3D(nn.Module):
     def __init__(self, in_channels, out_channels, norm_type, first_layer_channels=16, down_blocks=(1, 2, 3, 2),
                  up_blocks=(2, 2, 1, 1), use_memory_saving=True, use_inverse=True, is_separable=False):
         super().__init__()
-        if is_separable:
-            raise NotImplementedError("is_separable=True (SeparableConv3d) is out of scope (SURVEY.md section 2a #26)")
         disable_invertibles = use_memory_saving is False and use_inverse is False
         if first_layer_channels % in_channels:
             raise ValueError("`first_layer_channels` has to be divisible by `in_channels`.")
@@ -51,28 +50,28 @@ class Vnet3D(nn.Module):
         self.use_inverse = use_inverse
         c0 = first_layer_channels
 
-        self.in_ab = InputBlock(in_channels, c0, norm_layer, use_bias)
+        self.in_ab = InputBlock(in_channels, c0, norm_layer, use_bias, is_separable)
         if use_inverse:
-            self.in_ba = InputBlock(in_channels, c0, norm_layer, use_bias)
-        self.out_ab = OutBlock(c0 * 2, out_channels, norm_layer, use_bias)
+            self.in_ba = InputBlock(in_channels, c0, norm_layer, use_bias, is_separable)
+        self.out_ab = OutBlock(c0 * 2, out_channels, norm_layer, use_bias, is_separable)
         if use_inverse:
-            self.out_ba = OutBlock(c0 * 2, out_channels, norm_layer, use_bias)
+            self.out_ba = OutBlock(c0 * 2, out_channels, norm_layer, use_bias, is_separable)
 
         downs, factors = [], []
         for i, num_convs in enumerate(down_blocks):
             factor = 2**i
             downs.append(DownBlock(c0 * factor, num_convs, norm_layer, use_bias, keep_input, use_inverse,
-                                   disable_invertibles))
+                                   disable_invertibles, is_separable))
             factors.append(factor)
         self.downs = nn.ModuleList(downs)
         self.encoder = nn.ModuleList([self.in_ab]).extend(self.downs)  # vnet3d.py:89 (same module objects)
 
         up_factors = [f * 2 for f in reversed(factors)]
         ups = [UpBlock(c0 * up_factors[0], c0 * up_factors[0], up_blocks[0], norm_layer, use_bias, keep_input,
-                       use_inverse, disable_invertibles)]
+                       use_inverse, disable_invertibles, is_separable)]
         for i, num_convs in enumerate(up_blocks[1:]):
             ups.append(UpBlock(c0 * up_factors[i], c0 * up_factors[i + 1], num_convs, norm_layer, use_bias, keep_input,
-                               use_inverse, disable_invertibles))
+                               use_inverse, disable_invertibles, is_separable))
         self.ups = nn.ModuleList(ups)
 
     def _run(self, tape, b0, inverse):
@@ -99,16 +98,16 @@ class Vnet3D(nn.Module):
 
 class InputBlock(nn.Module):
 
-    def __init__(self, in_channels, out_channels, norm_layer, use_bias):
+    def __init__(self, in_channels, out_channels, norm_layer, use_bias, is_separable=False):
         super().__init__()
         self.n_repeats = out_channels // in_channels
-        self.conv1 = layers.Conv3d(in_channels, out_channels, kernel_size=5, padding=2, bias=use_bias)
+        self.conv1 = get_conv_layer_3d(is_separable)(in_channels, out_channels, kernel_size=5, padding=2, bias=use_bias)
         self.bn1 = norm_layer(out_channels)
         self.relu = layers.PReLU(out_channels)
 
     def gb_run(self, tape, b):
         # PReLU(IN(conv(x)) + x repeated over channels)
-        raw = layers.step_conv(tape, b, self.conv1, want_stats=True)
+        raw = layers.step_conv_any(tape, b, self.conv1, want_stats=True)
         rep = layers.step_channel_repeat(tape, b, self.n_repeats)
         return layers.step_norm_act(tape, raw, True, ACT_PRELU, 0.0, 0, self.bn1.eps, residual=rep, prelu=self.relu,
                                     res_before_act=True)
@@ -116,19 +115,21 @@ class InputBlock(nn.Module):
 
 class DownBlock(nn.Module):
 
-    def __init__(self, in_channels, n_conv_blocks, norm_layer, use_bias, keep_input, use_inverse, disable_invertibles):
+    def __init__(self, in_channels, n_conv_blocks, norm_layer, use_bias, keep_input, use_inverse, disable_invertibles,
+                 is_separable=False):
         super().__init__()
+        self.is_separable = is_separable
         out_channels = 2 * in_channels
         self.down_conv_ab = self.build_down_conv(in_channels, out_channels, norm_layer, use_bias)
         if use_inverse:
             self.down_conv_ba = self.build_down_conv(in_channels, out_channels, norm_layer, use_bias)
-        inv_block = _base_inv_block(out_channels, norm_layer, use_bias)
+        inv_block = _base_inv_block(out_channels, norm_layer, use_bias, is_separable)
         self.core = invertible.InvertibleSequence(inv_block, n_conv_blocks, keep_input, disable_invertibles)
         self.relu = layers.PReLU(out_channels)
 
-    @staticmethod
-    def build_down_conv(in_channels, out_channels, norm_layer, use_bias):
-        return nn.Sequential(layers.Conv3d(in_channels, out_channels, kernel_size=2, stride=2, bias=use_bias),
+    def build_down_conv(self, in_channels, out_channels, norm_layer, use_bias):
+        conv_layer = get_conv_layer_3d(self.is_separable)
+        return nn.Sequential(conv_layer(in_channels, out_channels, kernel_size=2, stride=2, bias=use_bias),
                              norm_layer(out_channels), layers.PReLU(out_channels))
 
     def gb_run(self, tape, b, inverse=False):
@@ -142,25 +143,26 @@ class DownBlock(nn.Module):
 class UpBlock(nn.Module):
 
     def __init__(self, in_channels, out_channels, n_conv_blocks, norm_layer, use_bias, keep_input, use_inverse,
-                 disable_invertibles):
+                 disable_invertibles, is_separable=False):
         super().__init__()
+        self.is_separable = is_separable
         self.out_channels = out_channels
         self.up_conv_ab = self.build_up_conv(in_channels, out_channels, norm_layer, use_bias)
         if use_inverse:
             self.up_conv_ba = self.build_up_conv(in_channels, out_channels, norm_layer, use_bias)
-        inv_block = _base_inv_block(out_channels, norm_layer, use_bias)
+        inv_block = _base_inv_block(out_channels, norm_layer, use_bias, is_separable)
         self.core = invertible.InvertibleSequence(inv_block, n_conv_blocks, keep_input, disable_invertibles)
         self.relu = layers.PReLU(out_channels)
 
-    @staticmethod
-    def build_up_conv(in_channels, out_channels, norm_layer, use_bias):
-        return nn.Sequential(layers.ConvTranspose3d(in_channels, out_channels // 2, kernel_size=2, stride=2, bias=use_bias),
+    def build_up_conv(self, in_channels, out_channels, norm_layer, use_bias):
+        conv_transp_layer = get_conv_transpose_layer_3d(self.is_separable)
+        return nn.Sequential(conv_transp_layer(in_channels, out_channels // 2, kernel_size=2, stride=2, bias=use_bias),
                              norm_layer(out_channels // 2), layers.PReLU(out_channels // 2))
 
     def gb_run(self, tape, b, skip, inverse=False):
         seq = self.up_conv_ba if inverse else self.up_conv_ab
         half = self.out_channels // 2
-        raw = layers.step_conv(tape, b, seq[0], want_stats=True)
+        raw = layers.step_conv_any(tape, b, seq[0], want_stats=True)
         # torch.cat((up, skipx), 1) without a cat kernel: both halves are written into one buffer
         N, D, H, W, _ = raw.t.shape
         xcat = layers.Buf(torch.empty((N, D, H, W, self.out_channels), dtype=torch.bfloat16, device=raw.t.device), 0,
@@ -174,21 +176,22 @@ class UpBlock(nn.Module):
 
 class OutBlock(nn.Module):
 
-    def __init__(self, in_channels, out_channels, norm_layer, use_bias):
+    def __init__(self, in_channels, out_channels, norm_layer, use_bias, is_separable=False):
         super().__init__()
-        self.conv1 = layers.Conv3d(in_channels, in_channels, kernel_size=5, padding=2, bias=use_bias)
+        conv_layer = get_conv_layer_3d(is_separable)
+        self.conv1 = conv_layer(in_channels, in_channels, kernel_size=5, padding=2, bias=use_bias)
         self.bn1 = norm_layer(in_channels)
         self.relu1 = layers.PReLU(in_channels)
-        self.conv2 = layers.Conv3d(in_channels, out_channels, kernel_size=1)
+        self.conv2 = conv_layer(in_channels, out_channels, kernel_size=1)
         self.tanh = layers.Tanh()
 
     def gb_run(self, tape, b):
-        raw = layers.step_conv(tape, b, self.conv1, want_stats=True)
+        raw = layers.step_conv_any(tape, b, self.conv1, want_stats=True)
         a = layers.step_norm_act(tape, raw, True, ACT_PRELU, 0.0, 0, self.bn1.eps, prelu=self.relu1)
-        return layers.step_conv(tape, a, self.conv2)  # tanh is evaluated in fp32 while exporting
+        return layers.step_conv_any(tape, a, self.conv2)  # tanh is evaluated in fp32 while exporting
 
 
-def _base_inv_block(n_channels, norm_layer, use_bias):
+def _base_inv_block(n_channels, norm_layer, use_bias, is_separable=False):
     n_channels = n_channels // 2  # the coupling works on channel halves
-    return nn.Sequential(layers.Conv3d(n_channels, n_channels, kernel_size=5, padding=2, bias=use_bias),
+    return nn.Sequential(get_conv_layer_3d(is_separable)(n_channels, n_channels, kernel_size=5, padding=2, bias=use_bias),
                          norm_layer(n_channels), layers.PReLU(n_channels))

@@ -57,11 +57,27 @@ class InvertibleSequence(nn.Module):
 
 
 def _branch(tape, src, seq, residual, out, out_scale):
-    """out = residual + out_scale * PReLU(IN(conv(src)))   with seq = [conv, norm, PReLU]"""
-    conv, norm, prelu = seq[0], seq[1], seq[2]
-    raw = layers.step_conv(tape, src, conv, want_stats=True)
-    layers.step_norm_act(tape, raw, True, ACT_PRELU, 0.0, 0, norm.eps, residual=residual, prelu=prelu,
-                         out_scale=out_scale, out=out)
+    """out = residual + out_scale * act(IN(conv(head(src)))).
+
+    V-Net (vnet3d.py:261-267): seq = [conv, norm, PReLU].  Piresnet3D (piresnet3d.py:114-119): seq = [norm,
+    ReplicationPad3d, conv, norm, ReLU] -- the layers in front of the last convolution run as ordinary steps, the
+    tail is fused with the coupling's add."""
+    seq = list(seq)
+    k = max(i for i, m in enumerate(seq) if isinstance(m, layers._ConvMixin) or hasattr(m, "gb_pair"))
+    head, conv, tail = seq[:k], seq[k], seq[k + 1:]
+    if len(tail) != 2 or not layers._is_norm(tail[0]):
+        raise NotImplementedError("coupling branch must end with [conv, norm, activation]")
+    if head:
+        src = layers.run_sequence(tape, head, src)
+    norm, actm = tail
+    raw = layers.step_conv_any(tape, src, conv, want_stats=True)
+    if isinstance(actm, layers.PReLU):
+        layers.step_norm_act(tape, raw, True, ACT_PRELU, 0.0, 0, norm.eps, residual=residual, prelu=actm,
+                             out_scale=out_scale, out=out)
+    else:
+        act_id, slope = layers._act_of(actm)
+        layers.step_norm_act(tape, raw, True, act_id, slope, 0, norm.eps, residual=residual, out_scale=out_scale,
+                             out=out)
 
 
 def coupling_forward(tape, x, fn):

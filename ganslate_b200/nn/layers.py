@@ -16,6 +16,7 @@ from typing import List, Optional, Sequence
 
 import torch
 from torch import nn
+from torch.nn.modules.utils import _triple
 
 from .. import ops
 from .._cabi import ACT_LEAKY, ACT_NONE, ACT_PRELU, ACT_RELU, ACT_TANH
@@ -68,6 +69,45 @@ class ConvTranspose3d(_ConvMixin, nn.ConvTranspose3d):
     _transposed = True
 
 
+class SeparableConv3d(nn.Module):
+    """ganslate/nn/separable.py:5-40: an in-plane (1, k, k) convolution followed by a through-plane (k, 1, 1) one
+    (both dense over channels, both biased); attribute names = the reference's state_dict keys."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=True):
+        super().__init__()
+        k, s, p = _triple(kernel_size), _triple(stride), _triple(padding)
+        self.conv_depthwise = Conv3d(in_channels, out_channels, kernel_size=(1, k[1], k[2]), stride=(1, s[1], s[2]),
+                                     padding=(0, p[1], p[2]), bias=bias)
+        self.conv_pointwise = Conv3d(out_channels, out_channels, kernel_size=(k[0], 1, 1), stride=(s[0], 1, 1),
+                                     padding=(p[0], 0, 0), bias=bias)
+        self.out_channels = out_channels
+
+    def gb_pair(self):
+        return self.conv_depthwise, self.conv_pointwise
+
+    def forward(self, x):  # noqa: D401
+        raise RuntimeError("ganslate_b200 layers are executed through their network's fused forward")
+
+
+class SeparableConvTranspose3d(nn.Module):
+    """ganslate/nn/separable.py:43-83 (transposed counterpart)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=True):
+        super().__init__()
+        k, s, p = _triple(kernel_size), _triple(stride), _triple(padding)
+        self.conv_transp_depthwise = ConvTranspose3d(in_channels, out_channels, kernel_size=(1, k[1], k[2]),
+                                                     stride=(1, s[1], s[2]), padding=(0, p[1], p[2]), bias=bias)
+        self.conv_transp_pointwise = ConvTranspose3d(out_channels, out_channels, kernel_size=(k[0], 1, 1),
+                                                     stride=(s[0], 1, 1), padding=(p[0], 0, 0), bias=bias)
+        self.out_channels = out_channels
+
+    def gb_pair(self):
+        return self.conv_transp_depthwise, self.conv_transp_pointwise
+
+    def forward(self, x):  # noqa: D401
+        raise RuntimeError("ganslate_b200 layers are executed through their network's fused forward")
+
+
 class _Marker:
     def forward(self, x):  # noqa: D401
         raise RuntimeError("ganslate_b200 layers are executed by run_sequence() on CUDA buffers; "
@@ -81,6 +121,17 @@ class ReflectionPad2d(_Marker, nn.ReflectionPad2d):
         if len(set(p)) != 1:
             raise NotImplementedError("asymmetric reflection padding")
         return int(p[0])
+
+
+class ReplicationPad3d(_Marker, nn.ReplicationPad3d):
+    """Materialised by a streaming copy (csrc/pad.cu): a TMA box cannot clamp its coordinates."""
+
+    @property
+    def pads_zyx(self):
+        l, r, t, b, f, k = self.padding  # (left, right, top, bottom, front, back)
+        if not (l == r and t == b and f == k):
+            raise NotImplementedError("asymmetric ReplicationPad3d")
+        return int(f), int(t), int(l)
 
 
 class InstanceNorm2d(_Marker, nn.InstanceNorm2d):
@@ -254,16 +305,18 @@ def flatten_modules(mods) -> List[nn.Module]:
 
 
 # ------------------------------------------------------------------------------------------------ fused steps
-def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0, want_stats=False) -> Buf:
+def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0, want_stats=False, as_activation=False) -> Buf:
     """conv (+bias, + optional epilogue activation) reading the whole (bordered) allocation of `b`'s channel slice.
     Output: raw Buf (act NONE) or activation Buf.  want_stats: an InstanceNorm follows -- its statistics are
-    accumulated by the convolution epilogue (Buf.stats) instead of a separate pass over the output."""
+    accumulated by the convolution epilogue (Buf.stats) instead of a separate pass over the output.
+    as_activation: the output feeds another convolution directly (SeparableConv3d: depthwise -> pointwise), so it
+    is an activation buffer whose FP32 gradient the consumer accumulates and this step converts to the bf16 operand."""
     op = m.conv_op()
     dev = b.t.device
     ops._require_cuda(b.t, "convolution input")
     stats = ops.zeros((b.t.shape[0], op.cout_pad, 2), dev) if (want_stats and act == ACT_NONE) else None
     y = op.run_fwd(b.plain_view(), dev, m.weight, m.bias, act, slope, stats=stats)
-    out = Buf(y, 0, m.out_channels, b.is_3d, raw=(act == ACT_NONE))
+    out = Buf(y, 0, m.out_channels, b.is_3d, raw=(act == ACT_NONE and not as_activation))
     out.stats = stats
     weight, bias = m.weight, m.bias
     out.want_dbias = tape is not None and tape.needs(bias)
@@ -276,7 +329,7 @@ def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0, want_stats=False) 
         out.st.grad = None
         db = out.dbias
         out.dbias = None
-        if act != ACT_NONE:
+        if act != ACT_NONE or as_activation:
             if tape.needs(bias):
                 db = ops.zeros((y.shape[-1],), dev)
             g = ops.act_backward(ops.make_view(g), y, act, slope, dbias=db)  # fp32 d_buf -> bf16 d_raw (+ bias grad)
@@ -300,6 +353,15 @@ def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0, want_stats=False) 
     return out
 
 
+def step_conv_any(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0, want_stats=False) -> Buf:
+    """step_conv for a plain or a separable (two chained convolutions) layer."""
+    if hasattr(m, "gb_pair"):
+        first, second = m.gb_pair()
+        b = step_conv(tape, b, first, as_activation=True)
+        return step_conv(tape, b, second, act, slope, want_stats)
+    return step_conv(tape, b, m, act, slope, want_stats)
+
+
 def step_norm_act(tape: Tape, x: Buf, norm: bool, act: int, slope: float, out_pad: int, eps: float,
                   residual: Optional[Buf] = None, prelu=None, res_before_act=False, out_scale=1.0,
                   out: Optional[Buf] = None) -> Buf:
@@ -309,8 +371,8 @@ def step_norm_act(tape: Tape, x: Buf, norm: bool, act: int, slope: float, out_pa
     concatenation buffer) to write into instead of a fresh allocation; prelu: nn.PReLU module for learnable slopes."""
     dev = x.t.device
     ops._require_cuda(x.t, "normalisation input")
-    if norm and not x.raw:
-        raise NotImplementedError("normalisation of a non-convolution output")
+    if norm and not x.raw and (residual is not None and res_before_act):
+        raise NotImplementedError("normalisation of an activation buffer with a residual before the activation")
     if out is None:
         N, D, H, W, _ = x.t.shape
         H, W = H - 2 * x.pad, W - 2 * x.pad
@@ -359,13 +421,41 @@ def step_norm_act(tape: Tape, x: Buf, norm: bool, act: int, slope: float, out_pa
                         x.dbias = x.dbias + seeded.float().sum(dim=(0, 1, 2, 3))
                 x.st.grad = draw
         else:
-            # activation input (copy / add / activation of existing buffers): fp32 gradient, accumulated
-            ops.norm_act_backward(x.view(), None, gview, x.grad_view(), False, act, slope, eps, dev,
+            # activation input (copy / add / activation of existing buffers, or an InstanceNorm that is not fed by a
+            # convolution -- piresnet3d.py:116): fp32 gradient, accumulated
+            ops.norm_act_backward(x.view(), stats if norm else None, gview, x.grad_view(), norm, act, slope, eps, dev,
                                   resv=residual.view() if (residual is not None and res_before_act) else None,
                                   dresv=dresv, prelu=slopes_p, dprelu=dprelu, res_before_act=res_before_act,
                                   dres_acc=True, dx_fp32_acc=True, out_scale=out_scale, need_dx=need_dx)
         if dprelu is not None:
             tape.add_param_grad(slopes, dprelu[:slopes.numel()].reshape(slopes.shape))
+
+    if tape is not None:
+        tape.steps.append(bwd)
+    return out
+
+
+def step_replicate_pad(tape: Tape, b: Buf, pads) -> Buf:
+    """ReplicationPad3d(b) as a new plain buffer (N, D+2pz, H+2py, W+2px, C); backward folds the FP32 gradient of the
+    padded buffer onto `b`'s gradient (accumulated, like every other consumer of an activation buffer)."""
+    pz, py, px = pads
+    if b.raw:
+        raise NotImplementedError("replicate padding of a raw convolution output")
+    dev = b.t.device
+    N, D, Hb, Wb, _ = b.t.shape
+    H, W = Hb - 2 * b.pad, Wb - 2 * b.pad
+    t = torch.empty((N, D + 2 * pz, H + 2 * py, W + 2 * px, b.cw), dtype=torch.bfloat16, device=dev)
+    out = Buf(t, 0, b.channels, b.is_3d)
+    ops.replicate_pad_forward(b.view(), out.view(), pads)
+    b.st.consumers += 1
+
+    def bwd():
+        if not out.has_grad():
+            return
+        g = out.st.grad
+        out.st.grad = None
+        if b.needs_grad_flag:
+            ops.replicate_pad_backward(ops.make_view(g), b.grad_view(), pads)
 
     if tape is not None:
         tape.steps.append(bwd)
@@ -400,6 +490,30 @@ def run_sequence(tape: Tape, mods: Sequence[nn.Module], b: Buf, final_pad: int =
             pending_pad = m.pad_amount
             if i >= n or not isinstance(mods[i], _ConvMixin):
                 raise RuntimeError("ReflectionPad must be followed by a convolution")
+            continue
+        if isinstance(m, ReplicationPad3d):
+            b = step_replicate_pad(tape, b, m.pads_zyx)
+            if i in taps:
+                sink.append((i, b, True))
+            i += 1
+            continue
+        if _is_norm(m):
+            # InstanceNorm that is not fed by a convolution (first layer of Piresnet3D's coupling branch,
+            # piresnet3d.py:116): statistics pass + normalisation of the activation buffer
+            if m.affine or m.track_running_stats:
+                raise NotImplementedError("InstanceNorm with affine/running stats (the reference uses neither)")
+            j = i + 1
+            act = _act_of(mods[j]) if j < n else None
+            if act is not None:
+                j += 1
+            act_id, slope = act if act is not None else (ACT_NONE, 0.0)
+            nxt = first_pad(mods[j:]) if j < n else final_pad
+            res = residual if (j >= n and residual is not None) else None
+            b = step_norm_act(tape, b, True, act_id, slope, nxt, m.eps, res)
+            for idx in range(i, j):
+                if idx in taps:
+                    sink.append((idx, b, False))
+            i = j
             continue
         if isinstance(m, _ConvMixin):
             if b.pad != pending_pad:

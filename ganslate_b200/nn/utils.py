@@ -37,6 +37,16 @@ def init_weights(net, weight_init_type='normal', gain=0.02):
     net.apply(init_func)
 
 
+def get_conv_layer_3d(is_separable=False):
+    """ganslate/nn/utils.py:39-43"""
+    return layers.SeparableConv3d if is_separable else layers.Conv3d
+
+
+def get_conv_transpose_layer_3d(is_separable=False):
+    """ganslate/nn/utils.py:46-50"""
+    return layers.SeparableConvTranspose3d if is_separable else layers.ConvTranspose3d
+
+
 def get_norm_layer_2d(norm_type='instance'):
     if norm_type == 'instance':
         return layers.InstanceNorm2d

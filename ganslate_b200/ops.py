@@ -672,6 +672,20 @@ def norm_act_backward(xv: View, stats, dyv: View, dxv: View, norm, act, slope, e
     _call("in_bwd", nbytes, "byte", "gb_in_bwd", lib.gb_in_bwd, C.byref(p), _stream())
 
 
+def replicate_pad_forward(srcv: View, dstv: View, pads):
+    """dstv (plain view of a buffer with extents srcv + 2*pads) <- ReplicationPad3d(srcv); pads = (pz, py, px)."""
+    nbytes = dstv.N * dstv.D * dstv.H * dstv.W * dstv.C * 2 * 2
+    _call("pad", nbytes, "byte", "gb_replicate_pad_fwd", _cabi.lib().gb_replicate_pad_fwd, C.byref(srcv), C.byref(dstv),
+          int(pads[0]), int(pads[1]), int(pads[2]), _stream())
+
+
+def replicate_pad_backward(ddstv: View, dsrcv: View, pads):
+    """dsrcv (FP32 view, accumulated) += fold of the FP32 gradient ddstv on the padded domain."""
+    nbytes = ddstv.N * ddstv.D * ddstv.H * ddstv.W * ddstv.C * 4 + dsrcv.N * dsrcv.D * dsrcv.H * dsrcv.W * dsrcv.C * 8
+    _call("pad", nbytes, "byte", "gb_replicate_pad_bwd", _cabi.lib().gb_replicate_pad_bwd, C.byref(ddstv), C.byref(dsrcv),
+          int(pads[0]), int(pads[1]), int(pads[2]), _stream())
+
+
 def to_channels_last(x: torch.Tensor, pad: int) -> torch.Tensor:
     """NC(D)HW fp32 -> bf16 buffer with reflection border `pad` (cyclegan.py:89-90 hands NCHW fp32 to the nets)."""
     _require_cuda(x, "network input")

@@ -211,6 +211,14 @@ int gb_nchw_to_cl(const float* src, int C, const gb_view* dst, const gb_view* pr
  * act = GB_ACT_TANH applies the generator's output nn.Tanh (resnet2d.py:65) in fp32 on the way out. */
 int gb_cl_to_nchw(const gb_view* src, float* dst, int C, int fold, int act, int src_fp32, void* stream);
 
+/* ---- replicate padding (torch.nn.ReplicationPad3d in ganslate/nn/generators/resnet/resnet3d.py:24,64,80,84 and
+ * piresnet3d.py:61,85,117) ----
+ * fwd: dst[n,z,y,x,:] = src[n, clamp(z-pz), clamp(y-py), clamp(x-px), :]  (bf16 views, dst extents = src + 2*pad)
+ * bwd: dsrc (FP32 view, accumulated) += sum of ddst (FP32 view on the padded domain) over the padded positions that
+ *      read each source element (autograd of ReplicationPad3d). */
+int gb_replicate_pad_fwd(const gb_view* src, const gb_view* dst, int pz, int py, int px, void* stream);
+int gb_replicate_pad_bwd(const gb_view* ddst, const gb_view* dsrc, int pz, int py, int px, void* stream);
+
 /* ---- losses --------------------------------------------------------------------------------
  * LSGAN: mean((p - t)^2) (ganslate/nn/losses/adversarial_loss.py:29,60-62); grad = 2(p-t)/n.
  * L1: mean(|a-b|) (ganslate/nn/losses/cyclegan_losses.py:64,73,97; pix2pix_losses.py:15); grad = sign(a-b)/n.

@@ -115,6 +115,38 @@ def reference_3d_small():
     return out
 
 
+def reference_piresnet_separable():
+    """Reference Piresnet3D (piresnet3d.py, both directions) and Vnet3D(is_separable=True) (separable.py) over the
+    memcnn stand-in: outputs and input gradients of sum(y^2) on small volumes."""
+    R.setup()
+    from ganslate.nn.generators.resnet.piresnet3d import Piresnet3D
+    m = R.modules()
+    out = {}
+    p = Piresnet3D(2, 2, "instance", depth=2, first_layer_channels=8, use_memory_saving=False, use_inverse=True)
+    torch.manual_seed(0)
+    m["init_weights"](p, "normal", 0.02)
+    gen = torch.Generator().manual_seed(5)
+    x = (torch.rand((1, 2, 8, 12, 12), generator=gen) * 2 - 1).requires_grad_(True)
+    out["piresnet"] = {"config": dict(in_channels=2, out_channels=2, depth=2, first_layer_channels=8, seed=0, data_seed=5,
+                                      shape=[1, 2, 8, 12, 12]), "keys": list(p.state_dict().keys())}
+    for inverse in (False, True):
+        y = p(x, inverse=inverse)
+        (gx,) = torch.autograd.grad(y.square().sum(), x)
+        out["piresnet"][str(inverse)] = {"y": tensor_digest(y), "dx": tensor_digest(gx)}
+    v = m["Vnet3D"](1, 1, "instance", first_layer_channels=8, down_blocks=(1, 1), up_blocks=(1, 1),
+                    use_memory_saving=False, use_inverse=True, is_separable=True)
+    torch.manual_seed(0)
+    m["init_weights"](v, "normal", 0.02)
+    gen = torch.Generator().manual_seed(6)
+    x = (torch.rand((1, 1, 8, 16, 16), generator=gen) * 2 - 1).requires_grad_(True)
+    out["vnet_separable"] = {"keys": list(v.state_dict().keys())}
+    for inverse in (False, True):
+        y = v(x, inverse=inverse)
+        (gx,) = torch.autograd.grad(y.square().sum(), x)
+        out["vnet_separable"][str(inverse)] = {"y": tensor_digest(y), "dx": tensor_digest(gx)}
+    return out
+
+
 def reference_unet2d_ssim():
     """Reference Unet2D (ganslate/nn/generators/unet/unet2d.py, dropout off) output / gradients on a fixed input, and
     reference SSIMLoss / CycleLoss(0.84) values and gradients (nn/losses/utils/ssim.py, cyclegan_losses.py:60-91)."""
@@ -152,6 +184,9 @@ def main():
     with open(os.path.join(out_dir, "unet2d_ssim.json"), "w") as f:
         json.dump(reference_unet2d_ssim(), f)
     print("unet2d_ssim written")
+    with open(os.path.join(out_dir, "piresnet3d_separable_small.json"), "w") as f:
+        json.dump(reference_piresnet_separable(), f)
+    print("piresnet3d_separable_small written")
     with open(os.path.join(out_dir, "vnet3d_patchgan3d_small.json"), "w") as f:
         json.dump(reference_3d_small(), f)
     print("vnet3d_patchgan3d_small written")

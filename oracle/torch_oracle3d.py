@@ -25,9 +25,32 @@ def _in3d(c):
     return nn.InstanceNorm3d(c)  # ganslate/nn/utils.py:62-68: eps 1e-5, affine=False, no running stats
 
 
-def _cnp(cin, cout, k, **kw):
+class _SepConv3d(nn.Module):
+    """ganslate/nn/separable.py:5-40: (1, k, k) in-plane convolution, then (k, 1, 1) through-plane convolution."""
+
+    def __init__(self, cin, cout, k, stride=1, padding=0, bias=True, transposed=False):
+        super().__init__()
+        conv = nn.ConvTranspose3d if transposed else nn.Conv3d
+        names = ("conv_transp_depthwise", "conv_transp_pointwise") if transposed else ("conv_depthwise", "conv_pointwise")
+        self._names = names
+        setattr(self, names[0], conv(cin, cout, (1, k, k), stride=(1, stride, stride), padding=(0, padding, padding),
+                                     bias=bias))
+        setattr(self, names[1], conv(cout, cout, (k, 1, 1), stride=(stride, 1, 1), padding=(padding, 0, 0), bias=bias))
+
+    def forward(self, x):
+        return getattr(self, self._names[1])(getattr(self, self._names[0])(x))
+
+
+def _conv3d(sep, cin, cout, k, transposed=False, **kw):
+    """ganslate/nn/utils.py:39-50: nn.Conv3d / nn.ConvTranspose3d or their separable counterparts."""
+    if sep:
+        return _SepConv3d(cin, cout, k, transposed=transposed, **kw)
+    return (nn.ConvTranspose3d if transposed else nn.Conv3d)(cin, cout, k, **kw)
+
+
+def _cnp(cin, cout, k, sep=False, **kw):
     """[conv, norm, PReLU] group used all over vnet3d.py (e.g. :186-189, :262-267)."""
-    return nn.Sequential(nn.Conv3d(cin, cout, k, bias=True, **kw), _in3d(cout), nn.PReLU(cout))
+    return nn.Sequential(_conv3d(sep, cin, cout, k, bias=True, **kw), _in3d(cout), nn.PReLU(cout))
 
 
 class _Coupling(nn.Module):
@@ -76,23 +99,23 @@ class _InvSequence(nn.Module):  # ganslate/nn/invertible.py:27-48
 
 
 class _In(nn.Module):  # vnet3d.py:151-167
-    def __init__(self, cin, cout):
+    def __init__(self, cin, cout, sep=False):
         super().__init__()
         self.n_repeats = cout // cin
-        self.conv1, self.bn1, self.relu = nn.Conv3d(cin, cout, 5, padding=2, bias=True), _in3d(cout), nn.PReLU(cout)
+        self.conv1, self.bn1, self.relu = _conv3d(sep, cin, cout, 5, padding=2, bias=True), _in3d(cout), nn.PReLU(cout)
 
     def forward(self, x):
         return self.relu(self.bn1(self.conv1(x)) + x.repeat(1, self.n_repeats, 1, 1, 1))
 
 
 class _Down(nn.Module):  # vnet3d.py:170-202
-    def __init__(self, cin, n_blocks, use_inverse):
+    def __init__(self, cin, n_blocks, use_inverse, sep=False):
         super().__init__()
         c = 2 * cin
-        self.down_conv_ab = _cnp(cin, c, 2, stride=2)
+        self.down_conv_ab = _cnp(cin, c, 2, sep, stride=2)
         if use_inverse:
-            self.down_conv_ba = _cnp(cin, c, 2, stride=2)
-        self.core = _InvSequence(_cnp(c // 2, c // 2, 5, padding=2), n_blocks)
+            self.down_conv_ba = _cnp(cin, c, 2, sep, stride=2)
+        self.core = _InvSequence(_cnp(c // 2, c // 2, 5, sep, padding=2), n_blocks)
         self.relu = nn.PReLU(c)
 
     def forward(self, x, inverse=False):
@@ -101,17 +124,17 @@ class _Down(nn.Module):  # vnet3d.py:170-202
 
 
 class _Up(nn.Module):  # vnet3d.py:205-240
-    def __init__(self, cin, cout, n_blocks, use_inverse):
+    def __init__(self, cin, cout, n_blocks, use_inverse, sep=False):
         super().__init__()
 
         def up():
-            return nn.Sequential(nn.ConvTranspose3d(cin, cout // 2, 2, stride=2, bias=True), _in3d(cout // 2),
+            return nn.Sequential(_conv3d(sep, cin, cout // 2, 2, transposed=True, stride=2, bias=True), _in3d(cout // 2),
                                  nn.PReLU(cout // 2))
 
         self.up_conv_ab = up()
         if use_inverse:
             self.up_conv_ba = up()
-        self.core = _InvSequence(_cnp(cout // 2, cout // 2, 5, padding=2), n_blocks)
+        self.core = _InvSequence(_cnp(cout // 2, cout // 2, 5, sep, padding=2), n_blocks)
         self.relu = nn.PReLU(cout)
 
     def forward(self, x, skip, inverse=False):
@@ -120,35 +143,36 @@ class _Up(nn.Module):  # vnet3d.py:205-240
 
 
 class _Out(nn.Module):  # vnet3d.py:243-259
-    def __init__(self, cin, cout):
+    def __init__(self, cin, cout, sep=False):
         super().__init__()
-        self.conv1, self.bn1, self.relu1 = nn.Conv3d(cin, cin, 5, padding=2, bias=True), _in3d(cin), nn.PReLU(cin)
-        self.conv2, self.tanh = nn.Conv3d(cin, cout, 1), nn.Tanh()
+        self.conv1, self.bn1, self.relu1 = _conv3d(sep, cin, cin, 5, padding=2, bias=True), _in3d(cin), nn.PReLU(cin)
+        self.conv2, self.tanh = _conv3d(sep, cin, cout, 1), nn.Tanh()
 
     def forward(self, x):
         return self.tanh(self.conv2(self.relu1(self.bn1(self.conv1(x)))))
 
 
 class OracleVnet3D(nn.Module):
-    """ganslate/nn/generators/vnet/vnet3d.py:27-148 (norm_type 'instance', is_separable False)."""
+    """ganslate/nn/generators/vnet/vnet3d.py:27-148 (norm_type 'instance')."""
 
     def __init__(self, in_channels, out_channels, first_layer_channels=16, down_blocks=(1, 2, 3, 2),
-                 up_blocks=(2, 2, 1, 1), use_inverse=True):
+                 up_blocks=(2, 2, 1, 1), use_inverse=True, is_separable=False):
         super().__init__()
         f = first_layer_channels
+        sep = is_separable
         self.use_inverse = use_inverse
-        self.in_ab = _In(in_channels, f)
+        self.in_ab = _In(in_channels, f, sep)
         if use_inverse:
-            self.in_ba = _In(in_channels, f)
-        self.out_ab = _Out(2 * f, out_channels)
+            self.in_ba = _In(in_channels, f, sep)
+        self.out_ab = _Out(2 * f, out_channels, sep)
         if use_inverse:
-            self.out_ba = _Out(2 * f, out_channels)
-        self.downs = nn.ModuleList([_Down(f * 2**i, n, use_inverse) for i, n in enumerate(down_blocks)])
+            self.out_ba = _Out(2 * f, out_channels, sep)
+        self.downs = nn.ModuleList([_Down(f * 2**i, n, use_inverse, sep) for i, n in enumerate(down_blocks)])
         self.encoder = nn.ModuleList([self.in_ab]).extend(self.downs)  # :88
         factors = [2 * 2**i for i in reversed(range(len(down_blocks)))]   # :91
-        ups = [_Up(f * factors[0], f * factors[0], up_blocks[0], use_inverse)]
+        ups = [_Up(f * factors[0], f * factors[0], up_blocks[0], use_inverse, sep)]
         for i, n in enumerate(up_blocks[1:]):
-            ups.append(_Up(f * factors[i], f * factors[i + 1], n, use_inverse))
+            ups.append(_Up(f * factors[i], f * factors[i + 1], n, use_inverse, sep))
         self.ups = nn.ModuleList(ups)
 
     def forward(self, x, inverse=False):  # :107-148
@@ -163,6 +187,35 @@ class OracleVnet3D(nn.Module):
         for i, u in enumerate(self.ups):
             out = u(out, out1 if i == len(self.ups) - 1 else rev[i + 1], inverse)
         return (self.out_ba if inverse else self.out_ab)(out)
+
+
+class OraclePiresnet3D(nn.Module):
+    """ganslate/nn/generators/resnet/piresnet3d.py:28-119 (norm_type 'instance')."""
+
+    def __init__(self, in_channels, out_channels, depth, first_layer_channels=64, use_inverse=True):
+        super().__init__()
+        c = first_layer_channels
+        self.use_inverse = use_inverse
+
+        def down():  # :58-75
+            return nn.Sequential(nn.ReplicationPad3d(2), nn.Conv3d(in_channels, c, 5, bias=True), _in3d(c), nn.ReLU(True),
+                                 nn.Conv3d(c, 2 * c, 3, stride=2, padding=1, bias=True), _in3d(2 * c), nn.ReLU(True))
+
+        def up():  # :77-87 (the last convolution keeps torch's default bias=True)
+            return nn.Sequential(nn.ConvTranspose3d(2 * c, c, 3, stride=2, padding=1, output_padding=1, bias=True),
+                                 _in3d(c), nn.ReLU(True), nn.ReplicationPad3d(2), nn.Conv3d(c, out_channels, 5), nn.Tanh())
+
+        self.downconv_ab, self.upconv_ab = down(), up()
+        if use_inverse:
+            self.downconv_ba, self.upconv_ba = down(), up()
+        inv = nn.Sequential(_in3d(c), nn.ReplicationPad3d(1), nn.Conv3d(c, c, 3, bias=True), _in3d(c), nn.ReLU(True))  # :114-119
+        self.core = _InvSequence(inv, depth)
+
+    def forward(self, x, inverse=False):  # :89-111
+        if inverse and not self.use_inverse:
+            raise ValueError("inverse pass requested but use_inverse is off")
+        down, up = (self.downconv_ba, self.upconv_ba) if inverse else (self.downconv_ab, self.upconv_ab)
+        return up(self.core(down(x), inverse))
 
 
 class OraclePatchGAN3D(nn.Module):

@@ -306,3 +306,34 @@ def test_gradient_side_pixel_windows_reproduce_torch():
                     dst[it["dst_off"] + r * it["dsr"] + c * it["dsc"] + t * it["dst_t"]] = \
                         dw[r, it["ws_off"] + t * it["chans_pad"] + c]
     np.testing.assert_allclose(dst.reshape(cout, cin, 7, 7), w.grad.numpy()[:, :, 0], rtol=1e-4, atol=1e-4)
+
+
+def test_replicate_pad_index_math_matches_torch():
+    """The index math of csrc/pad.cu restated in numpy: forward dst[z,y,x] = src[clamp(z-pz), clamp(y-py), clamp(x-px)];
+    backward dsrc[i] = sum of ddst over readers(i) = [0, p] for i = 0, [n-1+p, n-1+2p] for i = n-1, {i+p} otherwise
+    (per axis) -- against torch's ReplicationPad3d and its autograd, incl. extent-1 axes."""
+    def readers(i, n, p):
+        lo = 0 if i == 0 else i + p
+        hi = n - 1 + 2 * p if i == n - 1 else i + p
+        return range(lo, hi + 1)
+
+    for (D, H, W), (pz, py, px) in [((3, 4, 5), (1, 1, 1)), ((1, 6, 2), (2, 3, 1)), ((2, 1, 4), (0, 2, 2))]:
+        torch.manual_seed(D * 10 + W)
+        x = torch.randn(1, 1, D, H, W, dtype=torch.float64, requires_grad=True)
+        y = F.pad(x, (px, px, py, py, pz, pz), mode="replicate")
+        g = torch.randn_like(y)
+        y.backward(g)
+        xn, gn = x.detach().numpy()[0, 0], g.numpy()[0, 0]
+        fwd = np.empty((D + 2 * pz, H + 2 * py, W + 2 * px))
+        for z in range(D + 2 * pz):
+            for yy in range(H + 2 * py):
+                for xx in range(W + 2 * px):
+                    fwd[z, yy, xx] = xn[min(max(z - pz, 0), D - 1), min(max(yy - py, 0), H - 1), min(max(xx - px, 0), W - 1)]
+        np.testing.assert_array_equal(fwd, y.detach().numpy()[0, 0])
+        bwd = np.zeros((D, H, W))
+        for z in range(D):
+            for yy in range(H):
+                for xx in range(W):
+                    bwd[z, yy, xx] = sum(gn[a, b, c] for a in readers(z, D, pz) for b in readers(yy, H, py)
+                                         for c in readers(xx, W, px))
+        np.testing.assert_allclose(bwd, x.grad.numpy()[0, 0], rtol=1e-12, atol=1e-12)

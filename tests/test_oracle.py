@@ -251,6 +251,69 @@ def test_oracle3d_networks_equal_reference_modules():
     assert torch.allclose(od(xd), rd(xd), atol=1e-6)
 
 
+def test_oracle_piresnet3d_and_separable_vnet_match_golden():
+    """tests/golden/piresnet3d_separable_small.json: the REFERENCE's Piresnet3D (piresnet3d.py:28-119) and
+    Vnet3D(is_separable=True) (separable.py:5-83), generated by oracle/make_golden.py."""
+    from oracle import torch_oracle3d as O3
+    with open(os.path.join(GOLDEN, "piresnet3d_separable_small.json")) as f:
+        gold = json.load(f)
+    p = O3.OraclePiresnet3D(2, 2, 2, first_layer_channels=8, use_inverse=True)
+    torch.manual_seed(0)
+    O.init_weights(p)
+    assert list(p.state_dict().keys()) == gold["piresnet"]["keys"]
+    gen = torch.Generator().manual_seed(5)
+    x = (torch.rand((1, 2, 8, 12, 12), generator=gen) * 2 - 1).requires_grad_(True)
+    for inverse in (False, True):
+        y = p(x, inverse=inverse)
+        (gx,) = torch.autograd.grad(y.square().sum(), x)
+        assert_digest(_digest_small(y) | {"sq_sum": (y.double()**2).sum().item()}, gold["piresnet"][str(inverse)]["y"],
+                      f"piresnet y inverse={inverse}")
+        assert_digest(_digest_small(gx) | {"sq_sum": (gx.double()**2).sum().item()}, gold["piresnet"][str(inverse)]["dx"],
+                      f"piresnet dx inverse={inverse}", rtol=1e-3)
+    v = O3.OracleVnet3D(1, 1, first_layer_channels=8, down_blocks=(1, 1), up_blocks=(1, 1), use_inverse=True,
+                        is_separable=True)
+    torch.manual_seed(0)
+    O.init_weights(v)
+    assert list(v.state_dict().keys()) == gold["vnet_separable"]["keys"]
+    gen = torch.Generator().manual_seed(6)
+    x = (torch.rand((1, 1, 8, 16, 16), generator=gen) * 2 - 1).requires_grad_(True)
+    for inverse in (False, True):
+        y = v(x, inverse=inverse)
+        (gx,) = torch.autograd.grad(y.square().sum(), x)
+        assert_digest(_digest_small(y) | {"sq_sum": (y.double()**2).sum().item()},
+                      gold["vnet_separable"][str(inverse)]["y"], f"separable vnet y inverse={inverse}")
+        assert_digest(_digest_small(gx) | {"sq_sum": (gx.double()**2).sum().item()},
+                      gold["vnet_separable"][str(inverse)]["dx"], f"separable vnet dx inverse={inverse}", rtol=1e-3)
+
+
+def test_b200_piresnet3d_and_separable_vnet_mirror_reference_state_dict():
+    """Drop-in obligation: same state_dict keys, parameter order and shapes as the reference modules."""
+    from ganslate_b200.nn.generators import Piresnet3D, Vnet3D
+    from oracle import torch_oracle3d as O3
+    with open(os.path.join(GOLDEN, "piresnet3d_separable_small.json")) as f:
+        gold = json.load(f)
+    ours = Piresnet3D(2, 2, "instance", depth=2, first_layer_channels=8, use_memory_saving=False, use_inverse=True)
+    ref = O3.OraclePiresnet3D(2, 2, 2, first_layer_channels=8, use_inverse=True)
+    assert list(ours.state_dict().keys()) == gold["piresnet"]["keys"]
+    assert [tuple(p.shape) for p in ours.parameters()] == [tuple(p.shape) for p in ref.parameters()]
+    ours.load_state_dict(ref.state_dict())
+    ours = Vnet3D(1, 1, "instance", first_layer_channels=8, down_blocks=(1, 1), up_blocks=(1, 1), use_memory_saving=False,
+                  use_inverse=True, is_separable=True)
+    ref = O3.OracleVnet3D(1, 1, first_layer_channels=8, down_blocks=(1, 1), up_blocks=(1, 1), use_inverse=True,
+                          is_separable=True)
+    assert list(ours.state_dict().keys()) == gold["vnet_separable"]["keys"]
+    assert [tuple(p.shape) for p in ours.parameters()] == [tuple(p.shape) for p in ref.parameters()]
+    ours.load_state_dict(ref.state_dict())
+    # same seed -> same initial weights as the reference's init_weights (class names containing "Conv", module order)
+    from ganslate_b200.nn.utils import init_weights
+    torch.manual_seed(0)
+    init_weights(ours)
+    torch.manual_seed(0)
+    O.init_weights(ref)
+    for (k, a), (_, b) in zip(ours.state_dict().items(), ref.state_dict().items()):
+        assert torch.equal(a, b), k
+
+
 def test_oracle3d_coupling_is_invertible_and_revgan_step_runs():
     """The memcnn boundary has no reference golden values: pin it by invertibility of the shared core and by a
     complete RevGAN iteration producing finite losses and gradients for every generator parameter used."""
