@@ -97,6 +97,9 @@ def main():
         ("pair bn128", {9: 2, 11: 128}),
         ("pair bn256 pitch16", {9: 2, 11: 256, 10: 1}),
         ("wgrad two row tiles", {12: 2}),
+        ("cg2 pair-MMA persistent (knob 16)", {16: 1}),
+        ("cg2 bn128", {16: 1, 1: 128}),
+        ("cg2 3-stage ring", {16: 1, 17: 3}),
     ]
     if args.layers:
         layers = [layers[int(i)] for i in args.layers.split(",")]

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box visit: parity tests, bench line, ncu launch list, ncu --set full of the top kernels.
-# Usage (under gpurun): [BATCH=8] bash tools/gpu_round.sh <tag> [tests|smoke|bench|launches|full ...]
+# Usage (under gpurun): [BATCH=8] bash tools/gpu_round.sh <tag> [tests|smoke|bench|benchref|exp|launches|full ...]
 tag=${1:-r01}; shift
 what=${*:-tests bench launches full}
 B=${BATCH:-1}
@@ -18,6 +18,17 @@ smoke)
 bench)
   timeout 900 python bench.py --batch $B > $out/bench_b$B.json 2> $out/bench_b$B.err; tail -c 3500 $out/bench_b$B.json
   tail -3 $out/bench_b$B.err ;;
+exp)
+  # opt-in kernel paths that have not run on a B200 yet (cta_group::2 convolution, gradient-side pixel windows):
+  # every case in its own process under a timeout (tests/test_cg2_gpu.py), then the A/B microbench and a bench line
+  GB_EXPERIMENTAL=1 timeout 1500 python -m pytest tests/test_cg2_gpu.py tests/test_strided_window_gpu.py -m gpu -q \
+     > $out/pytest_exp.log 2>&1; echo "pytest exit $?" >> $out/pytest_exp.log; tail -15 $out/pytest_exp.log
+  timeout 600 python tools/conv_microbench.py 8 --layers 0,1,2,3,4,5 --variants 2,7,8,9 --what fwd,dgrad > $out/microbench_cg2.txt 2>&1
+  tail -40 $out/microbench_cg2.txt
+  GB_KNOBS=16=1 timeout 900 python bench.py --batch $B --no-cpu-baseline > $out/bench_cg2_b$B.json 2> $out/bench_cg2_b$B.err
+  tail -c 1500 $out/bench_cg2_b$B.json; tail -3 $out/bench_cg2_b$B.err
+  GB_BWD_WINDOW=1 timeout 900 python bench.py --batch $B --no-cpu-baseline --no-roofline > $out/bench_bwdwin_b$B.json 2> $out/bench_bwdwin_b$B.err
+  tail -c 600 $out/bench_bwdwin_b$B.json; tail -3 $out/bench_bwdwin_b$B.err ;;
 benchref)
   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 --batch $B > $out/bench_ref_b$B.json 2>> $out/bench_b$B.err; cat $out/bench_ref_b$B.json ;;
 launches)
