@@ -28,8 +28,9 @@
 //                 once the warp's tcgen05.ld of accumulator a have completed -> MMA issuer may overwrite it.
 //
 // STATUS: compiled for sm_100a and reviewed, NOT yet run on a B200 (the GPU budget of round 1 was spent when it was
-// written).  Off by default: gb_debug_knob(16, 1) routes eligible gb_conv_data calls here; the parity tests are
-// tests/test_cg2_gpu.py (GB_EXPERIMENTAL=1).
+// written).  Off by default: gb_debug_knob(16, 1) routes eligible gb_conv_data calls to the CTA-pair kernel,
+// gb_debug_knob(16, 2) to the single-CTA persistent variant (same structure, cta_group::1 primitives only); the parity
+// tests are tests/test_cg2_gpu.py (GB_EXPERIMENTAL=1).
 #include <cuda.h>
 #include "gb_common.cuh"
 #include "gb_geometry.h"
@@ -49,9 +50,9 @@ constexpr int EPI_THREADS = 256;
 constexpr int MAX_BIAS = 1024;          // output channels whose bias is staged in shared memory
 constexpr int MAXS = 8;                 // barrier slots of the smem ring
 
-template <int BN>
+template <int BN, bool PAIR>
 struct CCfg {
-  static constexpr int BH_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the B tile
+  static constexpr int BH_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;  // this CTA's part of the B tile (half in a pair)
   static constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;
   static constexpr int STAGES = (196 * 1024 / STAGE_BYTES) > MAXS ? MAXS : (196 * 1024 / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators
@@ -60,13 +61,16 @@ struct CCfg {
   static constexpr int SMEM = STAGES * STAGE_BYTES + SCRATCH_BYTES + TAIL_BYTES + 1024;
 };
 
+// PAIR = false: the same persistent, warp-specialised kernel on ONE CTA per SM (cta_group::1, M = 128, whole B tile per
+// CTA) -- knob 16 = 2.  It isolates the effect of persistence / epilogue overlap from that of the pair MMA, and is the
+// fallback should the pair variant misbehave on hardware.
 struct Cg2Geom {
   gb_fastdiv tiles_x, tiles_y, tiles_z;  // tile index -> (n, z, ty, tx)
   gb_fastdiv div_tw;                     // tile row -> (h, w)
   gb_fastdiv div_pairs, div_nb;          // item -> (cls, column block, pair)
   int tw, th;
   int ntiles;                            // row tiles of one class (max over classes)
-  int npairs;                            // ceil(ntiles / 2)
+  int npairs;                            // ceil(ntiles / 2) (PAIR) or ntiles
   int nb;                                // column blocks
   int nitems;                            // nclass * nb * npairs
   int nstages;
@@ -177,7 +181,7 @@ __device__ __forceinline__ bool tile_of(const gb_conv_params& p, const Cg2Geom& 
   return n < p.in.N && z0 < q[0] && y0 < q[1] && x0 < q[2];
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 __device__ __forceinline__ Item decode_item(const gb_conv_params& p, const Cg2Geom& g, uint32_t item, uint32_t rank) {
   Item it;
   uint32_t u = gb_div(item, g.div_pairs);
@@ -186,9 +190,9 @@ __device__ __forceinline__ Item decode_item(const gb_conv_params& p, const Cg2Ge
   it.n0 = (int)(u - v * g.div_nb.d) * BN;
   it.cls = (int)v;
   int x1, y1, z1, n1;
-  const uint32_t t_mine = 2 * pair + rank, t_other = 2 * pair + (rank ^ 1u);
+  const uint32_t t_mine = PAIR ? 2 * pair + rank : pair, t_other = 2 * pair + (rank ^ 1u);
   it.valid = t_mine < (uint32_t)g.ntiles && tile_of(p, g, it.cls, t_mine, it.x0, it.y0, it.z0, it.n);
-  const bool other = t_other < (uint32_t)g.ntiles && tile_of(p, g, it.cls, t_other, x1, y1, z1, n1);
+  const bool other = PAIR && t_other < (uint32_t)g.ntiles && tile_of(p, g, it.cls, t_other, x1, y1, z1, n1);
   it.any = it.valid || other;
   if (!it.valid) {  // a tile that does not exist still takes part in the pair MMA: load tile 0, store nothing
     it.x0 = it.y0 = it.z0 = it.n = 0;
@@ -196,11 +200,10 @@ __device__ __forceinline__ Item decode_item(const gb_conv_params& p, const Cg2Ge
   return it;
 }
 
-template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
-igemm_cg2_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant__ CUtensorMap map_a,
-                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Cg2Geom g) {
-  using C = CCfg<BN>;
+template <int BN, bool PAIR>
+__device__ __forceinline__ void cg_body(const gb_conv_params& p, const CUtensorMap& map_a, const CUtensorMap& map_b,
+                                        const Cg2Geom& g) {
+  using C = CCfg<BN, PAIR>;
   const int STAGES = g.nstages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -216,10 +219,10 @@ igemm_cg2_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
-  const uint32_t cluster_id = blockIdx.x >> 1;
-  const uint32_t nclusters = gridDim.x >> 1;
+  const uint32_t cluster_id = PAIR ? blockIdx.x >> 1 : blockIdx.x;
+  const uint32_t nclusters = PAIR ? gridDim.x >> 1 : gridDim.x;
   const int chunks = p.in.C >> 6;
 
   const uint32_t full_bar = smem_u32(bars);
@@ -233,28 +236,31 @@ igemm_cg2_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);
-      mbar_init(tempty_bar + 8 * a, 16);
+      mbar_init(tempty_bar + 8 * a, PAIR ? 16 : 8);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc2<C::TMEM_COLS>(smem_u32(tmem_slot));
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc2<C::TMEM_COLS>(smem_u32(tmem_slot));
+    else tmem_alloc<C::TMEM_COLS>(smem_u32(tmem_slot));
+  }
   for (int i = tid; i < GB_MAX_TAPS; i += NTHREADS)
     *reinterpret_cast<uint32_t*>(taps_s + 4 * i) = *reinterpret_cast<const uint32_t*>(p.taps[i]);
   for (int i = tid; i < MAX_BIAS; i += NTHREADS) bias_s[i] = (p.bias != nullptr && i < p.ncols) ? p.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();   // barrier inits and TMEM allocations of both CTAs are visible before any remote signal
+  if constexpr (PAIR) cluster_sync_all();  // barrier inits / TMEM allocations of both CTAs precede any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one lane per CTA)
     if (lane == 0) {
-      const uint32_t leader_full = map_to_cta(full_bar, 0);
-      const uint32_t tx_bytes = 2u * (uint32_t)(g.tw * g.th * 128 + C::BH_BYTES);
+      const uint32_t leader_full = PAIR ? map_to_cta(full_bar, 0) : full_bar;
+      const uint32_t tx_bytes = (PAIR ? 2u : 1u) * (uint32_t)(g.tw * g.th * 128 + C::BH_BYTES);
       int s = 0, round = 0;
       for (uint32_t item = cluster_id; item < (uint32_t)g.nitems; item += nclusters) {
-        const Item it = decode_item<BN>(p, g, item, rank);
+        const Item it = decode_item<BN, PAIR>(p, g, item, rank);
         if (!it.any) continue;
         const gb_conv_class& cc = p.cls[it.cls];
         for (int tl = 0; tl < cc.ntaps; ++tl) {
@@ -265,10 +271,16 @@ igemm_cg2_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
             const uint32_t a_s = base + s * C::STAGE_BYTES;
             const uint32_t b_s = a_s + A_BYTES;
             if (leader) mbar_expect_tx(full_bar + 8 * s, tx_bytes);
-            tma2_load_5d(a_s, &map_a, leader_full + 8 * s, c * 64, it.x0 * p.in_mul[2] + dx, it.y0 * p.in_mul[1] + dy,
-                         it.z0 * p.in_mul[0] + dz, it.n);
-            tma2_load_2d(b_s, &map_b, leader_full + 8 * s, tl * p.in.C + c * 64,
-                         it.cls * p.npad + it.n0 + (int)rank * (BN / 2));
+            if constexpr (PAIR) {
+              tma2_load_5d(a_s, &map_a, leader_full + 8 * s, c * 64, it.x0 * p.in_mul[2] + dx, it.y0 * p.in_mul[1] + dy,
+                           it.z0 * p.in_mul[0] + dz, it.n);
+              tma2_load_2d(b_s, &map_b, leader_full + 8 * s, tl * p.in.C + c * 64,
+                           it.cls * p.npad + it.n0 + (int)rank * (BN / 2));
+            } else {
+              tma_load_5d(a_s, &map_a, leader_full + 8 * s, c * 64, it.x0 * p.in_mul[2] + dx, it.y0 * p.in_mul[1] + dy,
+                          it.z0 * p.in_mul[0] + dz, it.n);
+              tma_load_2d(b_s, &map_b, leader_full + 8 * s, tl * p.in.C + c * 64, it.cls * p.npad + it.n0);
+            }
             if (++s == STAGES) {
               s = 0;
               ++round;
@@ -281,17 +293,18 @@ igemm_cg2_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA, one lane)
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_m256(BN);
+      constexpr uint32_t idesc = PAIR ? make_idesc_bf16_m256(BN) : make_idesc_bf16(BN, 0, 0);
       int s = 0, round = 0;
       uint32_t acc_it = 0;  // items issued so far: accumulator = acc_it & 1, its use count = acc_it >> 1
       for (uint32_t item = cluster_id; item < (uint32_t)g.nitems; item += nclusters) {
-        const Item it = decode_item<BN>(p, g, item, rank);
+        const Item it = decode_item<BN, PAIR>(p, g, item, rank);
         if (!it.any) continue;
         const gb_conv_class& cc = p.cls[it.cls];
         const int KB = cc.ntaps * chunks;
         const uint32_t a = acc_it & 1u, use = acc_it >> 1;
         if (use > 0) {  // the epilogue warps of both CTAs have drained the previous use of this accumulator
-          mbar_wait_cluster(tempty_bar + 8 * a, (use - 1) & 1);
+          if constexpr (PAIR) mbar_wait_cluster(tempty_bar + 8 * a, (use - 1) & 1);
+          else mbar_wait(tempty_bar + 8 * a, (use - 1) & 1);
           tc_fence_after();
         }
         const uint32_t d_tmem = tmem_base + a * BN;
@@ -303,14 +316,19 @@ igemm_cg2_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
           const uint64_t adesc = make_smem_desc(a_s, 16, 1024);
           const uint64_t bdesc = make_smem_desc(b_s, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
-          umma2_commit(empty_bar + 8 * s);
+          for (int k = 0; k < BK / 16; ++k) {
+            if constexpr (PAIR) umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
+          if constexpr (PAIR) umma2_commit(empty_bar + 8 * s);
+          else umma_commit(empty_bar + 8 * s);
           if (++s == STAGES) {
             s = 0;
             ++round;
           }
         }
-        umma2_commit(tfull_bar + 8 * a);
+        if constexpr (PAIR) umma2_commit(tfull_bar + 8 * a);
+        else umma_commit(tfull_bar + 8 * a);
         ++acc_it;
       }
     }
@@ -320,12 +338,12 @@ igemm_cg2_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
     const int lg = warp & 3;                    // TMEM lane group this warp may read
     const int half = (warp - EPI_WARP0) >> 2;   // which half of the BN columns
     const int etid = tid - EPI_WARP0 * 32;      // 0..255
-    const uint32_t leader_tempty = map_to_cta(tempty_bar, 0);
+    const uint32_t leader_tempty = PAIR ? map_to_cta(tempty_bar, 0) : tempty_bar;
     const bool want_stats = p.stats != nullptr && !p.out_fp32;
     __nv_bfloat16* optr = reinterpret_cast<__nv_bfloat16*>(p.out.ptr);
     uint32_t acc_it = 0;
     for (uint32_t item = cluster_id; item < (uint32_t)g.nitems; item += nclusters) {
-      const Item it = decode_item<BN>(p, g, item, rank);
+      const Item it = decode_item<BN, PAIR>(p, g, item, rank);
       if (!it.any) continue;
       const gb_conv_class& cc = p.cls[it.cls];
       const uint32_t a = acc_it & 1u, use = acc_it >> 1;
@@ -354,7 +372,10 @@ igemm_cg2_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
           // last TMEM read of this warp for this accumulator: hand it back to the MMA issuer before the stores
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(leader_tempty + 8 * a);
+          if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_cluster(leader_tempty + 8 * a);
+            else mbar_arrive(leader_tempty + 8 * a);
+          }
         }
         float sv[CH];
 #pragma unroll
@@ -436,46 +457,62 @@ igemm_cg2_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
   // -------------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // no CTA of the pair leaves (or frees TMEM) while the other may still signal / read it
-  if (warp == 1) tmem_dealloc2<C::TMEM_COLS>(tmem_base);
+  if constexpr (PAIR) cluster_sync_all();  // no CTA of the pair leaves (or frees TMEM) while the other may still signal it
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_dealloc2<C::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
 }
 
 template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+igemm_cg2_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant__ CUtensorMap map_a,
+                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Cg2Geom g) {
+  cg_body<BN, true>(p, map_a, map_b, g);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+igemm_persist_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant__ CUtensorMap map_a,
+                     const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Cg2Geom g) {
+  cg_body<BN, false>(p, map_a, map_b, g);
+}
+
+template <int BN, bool PAIR>
 int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb, Cg2Geom g, cudaStream_t st) {
-  using C = CCfg<BN>;
+  using C = CCfg<BN, PAIR>;
   static bool attr_set = false;
-  static int max_clusters = 0;
-  int kb_max = 1;
-  for (int c = 0; c < p.nclass; ++c) {
-    const int kb = p.cls[c].ntaps * (p.in.C >> 6);
-    kb_max = kb > kb_max ? kb : kb_max;
-  }
+  static int max_groups = 0;  // co-resident clusters (PAIR) or CTAs
   if (!attr_set) {
-    GB_CUDA(cudaFuncSetAttribute(igemm_cg2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * 74, 1, 1);
-    cfg.blockDim = dim3(NTHREADS, 1, 1);
-    cfg.dynamicSmemBytes = C::SMEM;
-    int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, igemm_cg2_kernel<BN>, &cfg) != cudaSuccess || nc <= 0) {
-      // clusters never wait for each other, so over-subscription is harmless: one pair per TPC
-      int dev = 0, sms = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      nc = sms / 2;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    if constexpr (PAIR) {
+      GB_CUDA(cudaFuncSetAttribute(igemm_cg2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(sms, 1, 1);
+      cfg.blockDim = dim3(NTHREADS, 1, 1);
+      cfg.dynamicSmemBytes = C::SMEM;
+      int nc = 0;
+      // clusters never wait for each other, so over-subscription is harmless: fall back to one pair per TPC
+      if (cudaOccupancyMaxActiveClusters(&nc, igemm_cg2_kernel<BN>, &cfg) != cudaSuccess || nc <= 0) nc = sms / 2;
+      cudaGetLastError();
+      max_groups = nc;
+    } else {
+      GB_CUDA(cudaFuncSetAttribute(igemm_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+      max_groups = sms;  // one CTA per SM (the smem ring allows no second one)
     }
-    cudaGetLastError();
-    max_clusters = nc;
     attr_set = true;
   }
-  if (max_clusters <= 0) return -1;  // no co-resident CTA pair fits on this device: single-CTA kernels
+  if (max_groups <= 0) return -1;
   // the ring may be deeper than one item's K loop: the producer runs ahead into the next item
   g.nstages = g_gb_knobs[17] > 0 && g_gb_knobs[17] <= C::STAGES ? g_gb_knobs[17] : C::STAGES;
-  (void)kb_max;
-  int nclusters = max_clusters < g.nitems ? max_clusters : g.nitems;
-  if (g_gb_knobs[18] > 0 && g_gb_knobs[18] < nclusters) nclusters = g_gb_knobs[18];
-  igemm_cg2_kernel<BN><<<dim3(2 * nclusters, 1, 1), NTHREADS, C::SMEM, st>>>(p, ma, mb, g);
-  g_gb_knobs[15] = 5;
+  int ngroups = max_groups < g.nitems ? max_groups : g.nitems;
+  if (g_gb_knobs[18] > 0 && g_gb_knobs[18] < ngroups) ngroups = g_gb_knobs[18];
+  if constexpr (PAIR) igemm_cg2_kernel<BN><<<dim3(2 * ngroups, 1, 1), NTHREADS, C::SMEM, st>>>(p, ma, mb, g);
+  else igemm_persist_kernel<BN><<<dim3(ngroups, 1, 1), NTHREADS, C::SMEM, st>>>(p, ma, mb, g);
+  g_gb_knobs[15] = PAIR ? 5 : 6;
   g_gb_knobs[19] += 1;  // launches served here (tests read and reset it)
   GB_LAUNCH_CHECK();
   return 0;
@@ -483,11 +520,14 @@ int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb
 
 }  // namespace
 
-// Returns -1 when this path does not apply or is switched off (knob 16 == 0), 0 on success, >0 on error.
+// Returns -1 when this path does not apply or is switched off (knob 16: 0 = off, 1 = CTA pair, 2 = persistent single
+// CTA), 0 on success, >0 on error.
 int gb_conv_data_cg2(const gb_conv_params& p, cudaStream_t st) {
-  if (g_gb_knobs[16] == 0 || g_gb_knobs[3] != 0) return -1;
+  const int mode = g_gb_knobs[16];
+  if (mode == 0 || g_gb_knobs[3] != 0) return -1;
+  const bool pair = mode == 1;
   if (p.in.C % 64 != 0 || p.in.pad != 0 || !gb_tma_available()) return -1;
-  if (p.ncols > MAX_BIAS || p.ncols < 33) return -1;  // narrow outputs stay on the single-CTA kernels
+  if (p.ncols > MAX_BIAS || p.ncols < 33) return -1;  // narrow outputs stay on the one-tile-per-CTA kernels
   for (int d = 0; d < 3; ++d)
     if (p.in_mul[d] < 1 || p.in_mul[d] > 4) return -1;
   const int kpad = p.cls[0].kpad;
@@ -529,13 +569,13 @@ int gb_conv_data_cg2(const gb_conv_params& p, cudaStream_t st) {
   const int64_t ntiles = (int64_t)ntx * nty * max_ext[0] * p.in.N;
   if (ntiles >= (1ll << 30)) return -1;
   g.ntiles = (int)ntiles;
-  g.npairs = (int)((ntiles + 1) / 2);
-  // column block: the widest pair-MMA N covering the output channels (<= 256); narrower blocks only when that
-  // shortens the modelled time  rounds(clusters) x K blocks x (bytes per stage)
+  g.npairs = pair ? (int)((ntiles + 1) / 2) : (int)ntiles;
+  // column block: the widest MMA N covering the output channels (<= 256); knob 1 overrides
   int bn = 64;
   while (bn < p.ncols && bn < 256) bn *= 2;
   if (g_gb_knobs[1] >= 64) bn = g_gb_knobs[1];
-  if (bn / 2 > p.nclass * p.npad) return -1;  // keep the weight box inside its tensor
+  const int box_rows = pair ? bn / 2 : bn;
+  if (box_rows > p.nclass * p.npad) return -1;  // keep the weight box inside its tensor
   g.nb = gb_cdiv(p.ncols, bn);
   const int64_t nitems = (int64_t)p.nclass * g.nb * g.npairs;
   if (nitems >= (1ll << 31)) return -1;
@@ -545,11 +585,19 @@ int gb_conv_data_cg2(const gb_conv_params& p, cudaStream_t st) {
   g.nstages = 0;
   CUtensorMap ma, mb;
   if (gb_tma_activation_map(p.in, tw, th, &ma, p.in_mul, p.in_c_valid)) return 1;
-  if (gb_tma_weight_map(p.wpacked, kpad, p.nclass * p.npad, bn / 2, &mb)) return 1;
-  switch (bn) {
-    case 64: return launch<64>(p, ma, mb, g, st);
-    case 128: return launch<128>(p, ma, mb, g, st);
-    case 256: return launch<256>(p, ma, mb, g, st);
+  if (gb_tma_weight_map(p.wpacked, kpad, p.nclass * p.npad, box_rows, &mb)) return 1;
+  if (pair) {
+    switch (bn) {
+      case 64: return launch<64, true>(p, ma, mb, g, st);
+      case 128: return launch<128, true>(p, ma, mb, g, st);
+      case 256: return launch<256, true>(p, ma, mb, g, st);
+    }
+  } else {
+    switch (bn) {
+      case 64: return launch<64, false>(p, ma, mb, g, st);
+      case 128: return launch<128, false>(p, ma, mb, g, st);
+      case 256: return launch<256, false>(p, ma, mb, g, st);
+    }
   }
   return -1;
 }

@@ -1,5 +1,5 @@
-"""CTA-pair persistent convolution kernel (ganslate_b200/csrc/igemm_cg2.cu, tcgen05 cta_group::2), opt-in through
-gb_debug_knob(16, 1).  The kernel was written after round 1's GPU budget was spent and has never run on a B200:
+"""Persistent warp-specialised convolution kernels (ganslate_b200/csrc/igemm_cg2.cu): the CTA-pair variant (tcgen05
+cta_group::2, gb_debug_knob(16, 1)) and the single-CTA variant (gb_debug_knob(16, 2)).  The kernel was written after round 1's GPU budget was spent and has never run on a B200:
 these tests are `experimental` (GB_EXPERIMENTAL=1 runs them).  Each case runs in its OWN process under a timeout --
 a mis-signalled mbarrier shows up as a hang, and a hang must cost one case, not the suite.
 
@@ -41,8 +41,8 @@ import torch
 import gpu_bringup
 from ganslate_b200 import _cabi
 lib = _cabi.lib()
-kind, kw = json.loads(sys.argv[1])
-lib.gb_debug_knob(16, 1)
+kind, kw, mode = json.loads(sys.argv[1])
+lib.gb_debug_knob(16, mode)
 lib.gb_debug_knob(19, 0)
 lib.gb_debug_knob(15, 0)
 if kind == "conv":
@@ -56,12 +56,14 @@ print("RESULT", json.dumps(dict(ok=bool(ok), last_data_path=lib.gb_debug_knob(15
 """
 
 
+@pytest.mark.parametrize("mode", [2, 1], ids=["persistent-1cta", "cta-pair"])
 @pytest.mark.parametrize("kind,kw,expect", CASES, ids=[c[1].get("name", c[0]) for c in CASES])
-def test_cg2_case(kind, kw, expect):
+def test_cg2_case(kind, kw, expect, mode):
+    """mode 2 = persistent warp-specialised kernel on one CTA per SM (cta_group::1), mode 1 = the CTA-pair variant."""
     code = DRIVER.format(here=HERE)
     env = dict(os.environ, PYTHONPATH=os.path.dirname(HERE) + os.pathsep + os.environ.get("PYTHONPATH", ""))
     try:
-        res = subprocess.run([sys.executable, "-c", code, json.dumps([kind, kw])], capture_output=True, text=True,
+        res = subprocess.run([sys.executable, "-c", code, json.dumps([kind, kw, mode])], capture_output=True, text=True,
                              timeout=240, env=env)
     except subprocess.TimeoutExpired as e:
         pytest.fail(f"cg2 case hung (killed after 240 s): {kind} {kw}\n{(e.stdout or b'')[-2000:]}")

@@ -100,6 +100,7 @@ def main():
         ("cg2 pair-MMA persistent (knob 16)", {16: 1}),
         ("cg2 bn128", {16: 1, 1: 128}),
         ("cg2 3-stage ring", {16: 1, 17: 3}),
+        ("persistent 1-CTA (knob 16 = 2)", {16: 2}),
     ]
     if args.layers:
         layers = [layers[int(i)] for i in args.layers.split(",")]

@@ -23,10 +23,12 @@ exp)
   # every case in its own process under a timeout (tests/test_cg2_gpu.py), then the A/B microbench and a bench line
   GB_EXPERIMENTAL=1 timeout 1500 python -m pytest tests/test_cg2_gpu.py tests/test_strided_window_gpu.py -m gpu -q \
      > $out/pytest_exp.log 2>&1; echo "pytest exit $?" >> $out/pytest_exp.log; tail -15 $out/pytest_exp.log
-  timeout 600 python tools/conv_microbench.py 8 --layers 0,1,2,3,4,5 --variants 2,7,8,9 --what fwd,dgrad > $out/microbench_cg2.txt 2>&1
+  timeout 600 python tools/conv_microbench.py 8 --layers 0,1,2,3,4,5 --variants 2,7,8,9,10 --what fwd,dgrad > $out/microbench_cg2.txt 2>&1
   tail -40 $out/microbench_cg2.txt
   GB_KNOBS=16=1 timeout 900 python bench.py --batch $B --no-cpu-baseline > $out/bench_cg2_b$B.json 2> $out/bench_cg2_b$B.err
   tail -c 1500 $out/bench_cg2_b$B.json; tail -3 $out/bench_cg2_b$B.err
+  GB_KNOBS=16=2 timeout 900 python bench.py --batch $B --no-cpu-baseline > $out/bench_persist_b$B.json 2> $out/bench_persist_b$B.err
+  tail -c 1500 $out/bench_persist_b$B.json; tail -3 $out/bench_persist_b$B.err
   GB_BWD_WINDOW=1 timeout 900 python bench.py --batch $B --no-cpu-baseline --no-roofline > $out/bench_bwdwin_b$B.json 2> $out/bench_bwdwin_b$B.err
   tail -c 600 $out/bench_bwdwin_b$B.json; tail -3 $out/bench_bwdwin_b$B.err ;;
 benchref)
