@@ -1,0 +1,136 @@
+"""Host logic of whole networks on the CPU: the modules of ganslate_b200.nn run forward + backward through
+tests/fake_cabi.py (a pointer-level CPU restatement of the C ABI, test infrastructure only) and are compared with the
+CPU oracle.  This checks everything ABOVE the ABI -- tape construction, fused-step selection, channel-slice views,
+reflection / replicate borders, gradient routing and accumulation, weight packing specs -- for every network
+family, including the ones whose CUDA path has not run on a B200 yet (Unet3D, Piresnet3D, separable V-Net).
+It says nothing about the CUDA kernels: those are covered by the `-m gpu` parity tests.
+
+Tolerances are the GPU tests' (bf16 storage points are reproduced by the fake backend): outputs relative L2 <= 3e-2,
+gradients cosine >= 0.9 against the fp32 oracle."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import fake_cabi  # noqa: E402
+from parity_util import cosine, rel_l2  # noqa: E402
+
+
+def _load(ours, oracle):
+    assert list(ours.state_dict().keys()) == list(oracle.state_dict().keys())
+    ours.load_state_dict(oracle.state_dict())
+
+
+def _compare(ref, ours, x, call_ref=None, call_ours=None, out_tol=3e-2, cos_tol=0.9):
+    call_ref = call_ref or (lambda m, t: m(t))
+    call_ours = call_ours or (lambda m, t: m(t))
+    xr, xo = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    yr, yo = call_ref(ref, xr), call_ours(ours, xo)
+    assert yo.shape == yr.shape and rel_l2(yo, yr) <= out_tol, rel_l2(yo, yr)
+    g = torch.randn_like(yr)
+    ref.zero_grad()
+    ours.zero_grad()
+    yr.backward(g)
+    yo.backward(g)
+    assert cosine(xo.grad, xr.grad) >= cos_tol, cosine(xo.grad, xr.grad)
+    pr, po = dict(ref.named_parameters()), dict(ours.named_parameters())
+    bad = []
+    for k, p in pr.items():
+        if p.grad is None:
+            assert po[k].grad is None or float(po[k].grad.abs().max()) == 0.0, k
+            continue
+        assert po[k].grad is not None, k
+        if p.dim() > 1 and p.grad.abs().max() > 0:
+            c = cosine(po[k].grad, p.grad)
+            if c < cos_tol:
+                bad.append((k, c))
+    assert not bad, bad
+
+
+def test_resnet2d_and_patchgan2d_host_logic(monkeypatch):
+    lib = fake_cabi.install(monkeypatch)
+    from ganslate_b200.nn.discriminators import PatchGAN2D
+    from ganslate_b200.nn.generators import Resnet2D
+    from oracle import torch_oracle as O
+    torch.manual_seed(0)
+    ref = O.init_weights(O.OracleResnet2D(3, 3, n_residual_blocks=2))
+    ours = Resnet2D(3, 3, "instance", n_residual_blocks=2)
+    _load(ours, ref)
+    x = torch.rand(1, 3, 32, 32) * 2 - 1
+    _compare(ref, ours, x)
+    assert lib.calls["gb_conv_data"] > 0 and lib.calls["gb_conv_wgrad"] > 0 and lib.calls["gb_in_bwd"] > 0
+    refd = O.init_weights(O.OraclePatchGAN2D(3, 16, 2))
+    oursd = PatchGAN2D(3, 16, 2, (4, 4), "instance")
+    _load(oursd, refd)
+    _compare(refd, oursd, torch.rand(2, 3, 32, 32) * 2 - 1)
+
+
+def test_unet2d_and_unet3d_host_logic(monkeypatch):
+    fake_cabi.install(monkeypatch)
+    from ganslate_b200.nn.generators import Unet2D, Unet3D
+    from oracle import torch_oracle as O
+    torch.manual_seed(1)
+    ref = O.init_weights(O.OracleUnet2D(3, 2, 5, ngf=8))
+    ours = Unet2D(3, 2, 5, "instance", ngf=8)
+    _load(ours, ref)
+    _compare(ref, ours, torch.rand(1, 3, 32, 64) * 2 - 1)
+    ref3 = O.init_weights(O.OracleUnet3D(1, 1, 5, ngf=8))
+    ours3 = Unet3D(1, 1, 5, "instance", ngf=8)
+    _load(ours3, ref3)
+    _compare(ref3, ours3, torch.rand(1, 1, 32, 32, 32) * 2 - 1)
+
+
+SMALL = dict(first_layer_channels=8, down_blocks=(1, 1), up_blocks=(1, 1))
+
+
+@pytest.mark.parametrize("separable", [False, True], ids=["dense", "separable"])
+def test_vnet3d_host_logic(monkeypatch, separable):
+    fake_cabi.install(monkeypatch)
+    from ganslate_b200.nn.generators import Vnet3D
+    from oracle import torch_oracle as O
+    from oracle import torch_oracle3d as O3
+    torch.manual_seed(0)
+    ref = O.init_weights(O3.OracleVnet3D(1, 1, use_inverse=True, is_separable=separable, **SMALL))
+    ours = Vnet3D(1, 1, "instance", use_memory_saving=False, use_inverse=True, is_separable=separable, **SMALL)
+    _load(ours, ref)
+    x, _ = O3.synthetic_volume(1, 1, 8, 16, seed=3)
+    for inverse in (False, True):
+        _compare(ref, ours, x, lambda m, t: m(t, inverse=inverse), lambda m, t: m(t, inverse=inverse))
+
+
+def test_piresnet3d_and_patchgan3d_host_logic(monkeypatch):
+    lib = fake_cabi.install(monkeypatch)
+    from ganslate_b200.nn.discriminators import PatchGAN3D
+    from ganslate_b200.nn.generators import Piresnet3D
+    from oracle import torch_oracle as O
+    from oracle import torch_oracle3d as O3
+    torch.manual_seed(0)
+    ref = O.init_weights(O3.OraclePiresnet3D(2, 2, 2, first_layer_channels=16, use_inverse=True))
+    ours = Piresnet3D(2, 2, "instance", depth=2, first_layer_channels=16, use_memory_saving=False, use_inverse=True)
+    _load(ours, ref)
+    x, _ = O3.synthetic_volume(1, 2, 8, 12, seed=3)
+    for inverse in (False, True):
+        _compare(ref, ours, x, lambda m, t: m(t, inverse=inverse), lambda m, t: m(t, inverse=inverse))
+    assert lib.calls["gb_replicate_pad_fwd"] > 0 and lib.calls["gb_replicate_pad_bwd"] > 0
+    refd = O.init_weights(O3.OraclePatchGAN3D(1, 16, 2, (4, 4, 4)))
+    oursd = PatchGAN3D(1, 16, 2, (4, 4, 4), "instance")
+    _load(oursd, refd)
+    xd, _ = O3.synthetic_volume(1, 1, 16, 16, seed=5)
+    _compare(refd, oursd, xd)
+
+
+def test_gradient_side_pixel_windows_host_logic(monkeypatch):
+    """The opt-in gradient-side windows (ops.BWD_WINDOW_CONV) through the whole Resnet2D backward."""
+    fake_cabi.install(monkeypatch)
+    from ganslate_b200 import ops
+    from ganslate_b200.nn.generators import Resnet2D
+    from oracle import torch_oracle as O
+    monkeypatch.setattr(ops, "BWD_WINDOW_CONV", True)
+    torch.manual_seed(0)
+    ref = O.init_weights(O.OracleResnet2D(3, 3, n_residual_blocks=1))
+    ours = Resnet2D(3, 3, "instance", n_residual_blocks=1)
+    _load(ours, ref)
+    assert ours.model[-2].conv_op().bwd_window
+    _compare(ref, ours, torch.rand(1, 3, 24, 24) * 2 - 1)
