@@ -42,9 +42,14 @@ class _ConvMixin:
                 raise NotImplementedError("ganslate_b200 convolutions support groups=1, dilation=1")
             if self.padding_mode != "zeros":
                 raise NotImplementedError("use an explicit ReflectionPad module (as the reference networks do)")
-            op = ops.ConvOp(self.in_channels, self.out_channels, _t3(self.kernel_size), _t3(self.stride),
-                            _p3(self.padding), transposed=self._transposed,
-                            output_padding=_p3(self.output_padding) if self._transposed else (0, 0, 0))
+            k3 = _t3(self.kernel_size)
+            if k3[0] * k3[1] * k3[2] > ops._cabi.GB_MAX_TAPS and not self._transposed:
+                # Resnet3D's 7x7x7 layers: kd depth slabs of kh*kw taps each (ops.SlabConv)
+                op = ops.SlabConv(self.in_channels, self.out_channels, k3, _t3(self.stride), _p3(self.padding))
+            else:
+                op = ops.ConvOp(self.in_channels, self.out_channels, k3, _t3(self.stride), _p3(self.padding),
+                                transposed=self._transposed,
+                                output_padding=_p3(self.output_padding) if self._transposed else (0, 0, 0))
             self.__dict__["_gb_op"] = op
         return op
 
@@ -342,7 +347,7 @@ def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0, want_stats=False, 
         if tape.needs(bias):
             tape.add_param_grad(bias, db[:op.cout] if db is not None else ops.colsum(g, op.cout))
         if b.needs_grad_flag:
-            if not b.has_grad() and b.st.consumers == 1 and b.full:
+            if not b.has_grad() and b.st.consumers == 1 and b.full and not getattr(op, "accumulates_dgrad", False):
                 b.st.grad = torch.empty(b.st.t.shape, dtype=torch.float32, device=dev)  # sole consumer: overwrite
                 op.run_dgrad(gv, weight, b.grad_plain_view(), accumulate=False)
             else:

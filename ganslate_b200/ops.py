@@ -183,24 +183,27 @@ class ConvOp:
     which is what the reference builds its networks from (e.g. ganslate/nn/generators/resnet/resnet2d.py:24-57).
     """
 
-    def __init__(self, cin, cout, kernel, stride, padding, transposed=False, output_padding=(0, 0, 0)):
+    def __init__(self, cin, cout, kernel, stride, padding, transposed=False, output_padding=(0, 0, 0), weight_taps=None):
+        """weight_taps: taps per (row, channel) of the PARAMETER's layout when this op reads a depth slice
+        `weight[:, :, dz]` of a larger kernel (SlabConv); default = this op's own tap count."""
         self.cin, self.cout = cin, cout
         self.kernel, self.stride, self.padding = tuple(kernel), tuple(stride), tuple(padding)
         self.transposed, self.output_padding = transposed, tuple(output_padding)
         self.cin_pad, self.cout_pad = pad8(cin), pad8(cout)
         self.T = kernel[0] * kernel[1] * kernel[2]
+        self.wT = wT = int(weight_taps) if weight_taps else self.T  # tap extent of the parameter's memory layout
         if transposed:
             self.fwd = transposed_spec(kernel, stride, padding)
             self.dgrad = strided_spec(kernel, stride, padding)
             # weight (Cin, Cout, T): fwd rows=cout, k-chans=cin ; dgrad rows=cin, k-chans=cout
-            self.fwd_strides = (self.T, cout * self.T, 1)
-            self.dgrad_strides = (cout * self.T, self.T, 1)
+            self.fwd_strides = (wT, cout * wT, 1)
+            self.dgrad_strides = (cout * wT, wT, 1)
         else:
             self.fwd = strided_spec(kernel, stride, padding)
             self.dgrad = transposed_spec(kernel, stride, padding)
             # weight (Cout, Cin, T)
-            self.fwd_strides = (cin * self.T, self.T, 1)
-            self.dgrad_strides = (self.T, cin * self.T, 1)
+            self.fwd_strides = (cin * wT, wT, 1)
+            self.dgrad_strides = (wT, cin * wT, 1)
         self.fwd_rows_pad = (cout + 15) // 16 * 16
         self.dgrad_rows_pad = (cin + 15) // 16 * 16
         # Pixel-window formulation of a unit-stride convolution over <= 8 channels with no padding in x (the
@@ -303,7 +306,8 @@ class ConvOp:
             dst = torch.empty(spec.total_elems, dtype=torch.bfloat16, device=weight.device)
             self._packed[which] = (None, dst)
         w = weight.detach()
-        assert w.is_contiguous() and w.dtype == torch.float32
+        # (a depth slice weight[:, :, dz] of a larger kernel is strided: the pack strides carry its layout)
+        assert (w.is_contiguous() or self.wT != self.T) and w.dtype == torch.float32
         p = PackParams()
         p.src, p.dst = w.data_ptr(), dst.data_ptr()
         p.sn, p.sc, p.st = sn, sc, st
@@ -362,19 +366,25 @@ class ConvOp:
         assert xv.C == self.cin_pad and xv.pad == 0, (xv.C, self.cin_pad, xv.pad)
         od, oh, ow = self.out_extent((xv.D, xv.H, xv.W))
         y = torch.empty((xv.N, od, oh, ow, self.cout_pad), dtype=torch.bfloat16, device=device)
+        self.run_fwd_into(xv, weight, bias, make_view(y), act, slope, stats)
+        return y
+
+    def run_fwd_into(self, xv: View, weight, bias, outv: View, act=ACT_NONE, slope=0.0, stats=None, out_fp32=False,
+                     accumulate=False):
+        """run_fwd into an existing view; out_fp32 / accumulate: FP32 destination that is added to (SlabConv sums the
+        depth slabs of a large kernel this way)."""
         p = self._params("fwd")
-        p.inp, p.out = (self.window_view(xv) if self.window else xv), make_view(y)
+        p.inp, p.out = (self.window_view(xv) if self.window else xv), outv
         p.in_c_valid = self.kernel[2] * 8 if self.window else 0
         wp = self.packed(weight, "fwd")
         p.wpacked = wp.data_ptr()
         p.bias = bias.data_ptr() if bias is not None else None
         p.ncols, p.npad = self.cout, self.fwd_rows_pad
         p.act, p.act_slope = act, slope
-        p.out_fp32, p.accumulate = 0, 0
+        p.out_fp32, p.accumulate = (1 if out_fp32 else 0), (1 if accumulate else 0)
         p.stats = stats.data_ptr() if stats is not None else None
         _call("conv_fwd", self.flops((xv.D, xv.H, xv.W), xv.N), "flop", "gb_conv_data(fwd)", _cabi.lib().gb_conv_data,
               C.byref(p), _stream())
-        return y
 
     def bwd_window_view(self, gw: torch.Tensor) -> View:
         """gw: dOut copied into a (N, D, Ho, Wo + 2*BWD_BORDER, 8) buffer with zero borders -> the 64-"channel" window
@@ -412,11 +422,11 @@ class ConvOp:
         copy of its fp32 workspace into the PyTorch weight layout; tests/test_host_logic.py evaluates it literally."""
         if self.wg_swap:
             # workspace rows = input channel c, columns = (tap, output channel r); weight layout (cout, cin, T)
-            cols, cols_pad, dsr, dsc = self.cout, self.cout_pad, self.T, self.cin * self.T
+            cols, cols_pad, dsr, dsc = self.cout, self.cout_pad, self.wT, self.cin * self.wT
         else:
             cols = self.cout if self.transposed else self.cin
             cols_pad = self.cout_pad if self.transposed else self.cin_pad
-            dsr, dsc = cols * self.T, self.T
+            dsr, dsc = cols * self.wT, self.wT
         return dict(plain_is_input=self.transposed or self.wg_swap, taps=self.wg_taps, mul=self.stride,
                     rows=self.wg_rows, rows_pad=self.wg_rows_pad, kpad=self.wg_kpad,
                     unpack=dict(dsr=dsr, dsc=dsc, dst_t=1, rows=self.wg_rows, chans=cols, chans_pad=cols_pad,
@@ -431,10 +441,11 @@ class ConvOp:
         wv.C, wv.W = 64, xv.W - self.kernel[2] + 1
         return wv
 
-    def run_wgrad(self, xv: View, dyv: View, weight_shape, device, pending=None):
-        """fp32 weight gradient in the PyTorch layout of `weight_shape` (xv: plain input view, dyv: bf16 d_raw)."""
+    def run_wgrad(self, xv: View, dyv: View, weight_shape, device, pending=None, dw_out=None):
+        """fp32 weight gradient in the PyTorch layout of `weight_shape` (xv: plain input view, dyv: bf16 d_raw).
+        dw_out: existing destination (a depth slice `dw[:, :, dz]` of a larger kernel's gradient, SlabConv)."""
         if self.window or self.bwd_window:
-            return self._run_wgrad_window(xv, dyv, weight_shape, device, pending)
+            return self._run_wgrad_window(xv, dyv, weight_shape, device, pending, dw_out)
         plan = self.wgrad_plan()
         plain, gathered = (xv, dyv) if plan["plain_is_input"] else (dyv, xv)
         ws = zeros((self.wg_rows_pad, self.wg_kpad), device)
@@ -452,7 +463,7 @@ class ConvOp:
         p.plain, p.gathered, p.dw = plain, gathered, ws.data_ptr()
         _call("conv_wgrad", self.flops((xv.D, xv.H, xv.W), xv.N), "flop", "gb_conv_wgrad",
               _cabi.lib().gb_conv_wgrad, C.byref(p), _stream())
-        dw = torch.empty(weight_shape, dtype=torch.float32, device=device)
+        dw = torch.empty(weight_shape, dtype=torch.float32, device=device) if dw_out is None else dw_out
         u = plan["unpack"]
         if pending is not None:
             # the workspace -> PyTorch-layout copies of a whole backward pass go out in one launch (UnpackQueue)
@@ -464,7 +475,12 @@ class ConvOp:
         return dw
 
 
-def _conv_op_window_wgrad(self, xv, dyv, weight_shape, device, pending):
+def _at(t: torch.Tensor, off: int) -> torch.Tensor:
+    """One-element alias of `t`'s storage `off` elements behind t's first element (its data_ptr is what matters)."""
+    return t.as_strided((1,), (1,), t.storage_offset() + off)
+
+
+def _conv_op_window_wgrad(self, xv, dyv, weight_shape, device, pending, dw_out=None):
     """Weight gradient of a pixel-window convolution: dW[r][(dz,dy)*64 + dx*8 + c] = sum_q dOut[q][r] * window[q + (dz,dy)]
     [dx*8 + c]; one unpack item per (dz, dy) K block copies its kw x cin columns into the PyTorch layout."""
     kd, kh, kw = self.kernel
@@ -487,11 +503,11 @@ def _conv_op_window_wgrad(self, xv, dyv, weight_shape, device, pending):
         p.plain, p.gathered, p.dw = dyv, self.window_view(xv), ws.data_ptr()
     _call("conv_wgrad", self.flops((xv.D, xv.H, xv.W), xv.N), "flop", "gb_conv_wgrad", _cabi.lib().gb_conv_wgrad,
           C.byref(p), _stream())
-    dw = torch.empty(weight_shape, dtype=torch.float32, device=device)
+    dw = torch.empty(weight_shape, dtype=torch.float32, device=device) if dw_out is None else dw_out
     own = UnpackQueue() if pending is None else pending
-    wsf, dwf = ws.view(-1), dw.view(-1)
+    wsf = ws.view(-1)
     for it in self.window_unpack_items():
-        own.add(wsf[it["ws_off"]:], dwf[it["dst_off"]:], it["dsr"], it["dsc"], it["dst_t"], it["rows"], it["chans"],
+        own.add(wsf[it["ws_off"]:], _at(dw, it["dst_off"]), it["dsr"], it["dsc"], it["dst_t"], it["rows"], it["chans"],
                 it["chans_pad"], it["ntaps"], it["kpad"], keep=(ws, dw))
     if pending is None:
         own.flush()
@@ -504,15 +520,88 @@ def _conv_op_window_unpack_items(self):
     kd, kh, kw = self.kernel
     if self.bwd_window:
         # workspace rows = input channel, columns (block, j, co) with rx = kw - 1 - j: walk the taps backwards
-        return [dict(ws_off=b * 64, dst_off=b * kw + kw - 1, dsr=self.T, dsc=self.cin * self.T, dst_t=-1,
+        return [dict(ws_off=b * 64, dst_off=b * kw + kw - 1, dsr=self.wT, dsc=self.cin * self.wT, dst_t=-1,
                      rows=self.wg_rows, chans=self.cout, chans_pad=8, ntaps=kw, kpad=self.wg_kpad)
                 for b in range(kd * kh)]
-    return [dict(ws_off=b * 64, dst_off=b * kw, dsr=self.cin * self.T, dsc=self.T, dst_t=1, rows=self.wg_rows,
+    return [dict(ws_off=b * 64, dst_off=b * kw, dsr=self.cin * self.wT, dsc=self.wT, dst_t=1, rows=self.wg_rows,
                  chans=self.cin, chans_pad=8, ntaps=kw, kpad=self.wg_kpad) for b in range(kd * kh)]
 
 
 ConvOp._run_wgrad_window = _conv_op_window_wgrad
 ConvOp.window_unpack_items = _conv_op_window_unpack_items
+
+
+def _shift_z(v: View, dz: int, depth: int, elem_bytes: int) -> View:
+    """The view `dz` planes deeper, `depth` planes long."""
+    w = View()
+    C.memmove(C.byref(w), C.byref(v), C.sizeof(View))
+    w.ptr = v.ptr + dz * v.sz * elem_bytes
+    w.D = depth
+    return w
+
+
+class SlabConv:
+    """A unit-stride, depth-unpadded 3-D convolution whose kd*kh*kw taps exceed GB_MAX_TAPS (the 7x7x7 layers of
+    ganslate/nn/generators/resnet/resnet3d.py:25,64: 343 taps against 128), evaluated as kd convolutions with kernel
+    (1, kh, kw) over depth-shifted views of the input:  y = sum_dz conv_(1,kh,kw)(x[z + dz], W[:, :, dz]).
+
+    Forward: the slabs accumulate into an FP32 buffer (the data kernel's out_fp32 / accumulate epilogue), which is then
+    rounded to the bf16 raw output once; InstanceNorm statistics come from gb_in_stats.  Data gradient: every slab
+    accumulates into its depth-shifted view of the FP32 input gradient.  Weight gradient: slab dz fills dW[:, :, dz].
+    Same interface as ConvOp as far as nn/layers.py::step_conv uses it."""
+    accumulates_dgrad = True   # run_dgrad always adds: the caller passes a zero-initialised gradient buffer
+    bwd_window = False
+    window = False
+    transposed = False
+
+    def __init__(self, cin, cout, kernel, stride, padding):
+        kd, kh, kw = kernel
+        if tuple(stride) != (1, 1, 1) or padding[0] != 0:
+            raise NotImplementedError("convolutions with more than GB_MAX_TAPS taps need unit stride and no depth padding "
+                                      "(pad with an explicit ReplicationPad3d / ReflectionPad module, as resnet3d.py does)")
+        if kh * kw > _cabi.GB_MAX_TAPS:
+            raise ValueError("kernel too large")
+        self.cin, self.cout, self.kernel = cin, cout, tuple(kernel)
+        self.cin_pad, self.cout_pad = pad8(cin), pad8(cout)
+        self.T = kd * kh * kw
+        self.slabs = [ConvOp(cin, cout, (1, kh, kw), (1, 1, 1), (0, padding[1], padding[2]), weight_taps=self.T)
+                      for _ in range(kd)]
+
+    def out_extent(self, ext):
+        _, oh, ow = self.slabs[0].out_extent((1, ext[1], ext[2]))
+        return (ext[0] - self.kernel[0] + 1, oh, ow)
+
+    def flops(self, in_ext, batch):
+        ext = self.out_extent(in_ext)
+        return 2.0 * batch * ext[0] * ext[1] * ext[2] * self.cin * self.cout * self.T
+
+    def run_fwd(self, xv: View, device, weight, bias, act=ACT_NONE, slope=0.0, stats=None):
+        if act != ACT_NONE:
+            raise NotImplementedError("epilogue activation on a slab-decomposed convolution")
+        assert xv.C == self.cin_pad and xv.pad == 0
+        od, oh, ow = self.out_extent((xv.D, xv.H, xv.W))
+        y32 = torch.empty((xv.N, od, oh, ow, self.cout_pad), dtype=torch.float32, device=device)
+        yv = make_view(y32)
+        for dz, slab in enumerate(self.slabs):
+            slab.run_fwd_into(_shift_z(xv, dz, od, 2), weight[:, :, dz], bias if dz == 0 else None, yv, out_fp32=True,
+                              accumulate=dz > 0)
+        # FP32 -> bf16 raw output (gb_in_bwd without norm / activation is a plain rounding copy)
+        y = act_backward(yv, torch.empty(y32.shape, dtype=torch.bfloat16, device=device), ACT_NONE, 0.0)
+        if stats is not None:
+            v = make_view(y)
+            _cabi.check(_cabi.lib().gb_in_stats(C.byref(v), stats.data_ptr(), _stream()), "gb_in_stats")
+        return y
+
+    def run_dgrad(self, dyv: View, weight, outv: View, accumulate: bool):
+        assert accumulate, "SlabConv.run_dgrad adds to a zero-initialised gradient buffer (accumulates_dgrad)"
+        for dz, slab in enumerate(self.slabs):
+            slab.run_dgrad(dyv, weight[:, :, dz], _shift_z(outv, dz, dyv.D, 4), accumulate=True)
+
+    def run_wgrad(self, xv: View, dyv: View, weight_shape, device, pending=None):
+        dw = torch.empty(weight_shape, dtype=torch.float32, device=device)
+        for dz, slab in enumerate(self.slabs):
+            slab.run_wgrad(_shift_z(xv, dz, dyv.D, 2), dyv, weight_shape, device, pending, dw_out=dw[:, :, dz])
+        return dw
 
 
 class UnpackQueue:
@@ -586,7 +675,14 @@ def ensure_packed(net):
     """Refresh the packed weights of every convolution of `net` (one launch, only when a parameter changed)."""
     g = net.__dict__.get("_gb_pack_group")
     if g is None:
-        convs = [(m.conv_op(), m.weight) for m in net.modules() if hasattr(m, "conv_op")]
+        convs = []
+        for m in net.modules():
+            if hasattr(m, "conv_op"):
+                op = m.conv_op()
+                if isinstance(op, SlabConv):  # one packed matrix pair per depth slab, read from weight[:, :, dz]
+                    convs += [(slab, m.weight[:, :, dz]) for dz, slab in enumerate(op.slabs)]
+                else:
+                    convs.append((op, m.weight))
         for _, w in convs:
             _require_cuda(w, "network parameters")
         g = PackGroup(convs)

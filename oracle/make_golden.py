@@ -133,6 +133,17 @@ def reference_piresnet_separable():
         y = p(x, inverse=inverse)
         (gx,) = torch.autograd.grad(y.square().sum(), x)
         out["piresnet"][str(inverse)] = {"y": tensor_digest(y), "dx": tensor_digest(gx)}
+    from ganslate.nn.generators.resnet.resnet3d import Resnet3D
+    r3 = Resnet3D(1, 2, "instance", n_residual_blocks=1)
+    torch.manual_seed(0)
+    m["init_weights"](r3, "normal", 0.02)
+    gen = torch.Generator().manual_seed(8)
+    x = (torch.rand((1, 1, 8, 8, 8), generator=gen) * 2 - 1).requires_grad_(True)
+    y = r3(x)
+    (gx,) = torch.autograd.grad(y.square().sum(), x)
+    out["resnet3d"] = {"config": dict(in_channels=1, out_channels=2, n_residual_blocks=1, seed=0, data_seed=8,
+                                      shape=[1, 1, 8, 8, 8]), "keys": list(r3.state_dict().keys()),
+                       "y": tensor_digest(y), "dx": tensor_digest(gx)}
     v = m["Vnet3D"](1, 1, "instance", first_layer_channels=8, down_blocks=(1, 1), up_blocks=(1, 1),
                     use_memory_saving=False, use_inverse=True, is_separable=True)
     torch.manual_seed(0)

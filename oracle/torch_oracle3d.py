@@ -189,6 +189,37 @@ class OracleVnet3D(nn.Module):
         return (self.out_ba if inverse else self.out_ab)(out)
 
 
+class _ResBlock3d(nn.Module):  # ganslate/nn/generators/resnet/resnet3d.py:72-91
+    def __init__(self, c):
+        super().__init__()
+        self.conv_block = nn.Sequential(nn.ReplicationPad3d(1), nn.Conv3d(c, c, 3, bias=True), _in3d(c), nn.ReLU(True),
+                                        nn.ReplicationPad3d(1), nn.Conv3d(c, c, 3, bias=True), _in3d(c))
+
+    def forward(self, x):
+        return x + self.conv_block(x)
+
+
+class OracleResnet3D(nn.Module):
+    """ganslate/nn/generators/resnet/resnet3d.py:14-69 (norm_type 'instance')."""
+
+    def __init__(self, in_channels, out_channels, n_residual_blocks=9):
+        super().__init__()
+        L = [nn.ReplicationPad3d(3), nn.Conv3d(in_channels, 64, 7, bias=True), _in3d(64), nn.ReLU(True)]
+        c = 64
+        for _ in range(2):  # :32-41
+            L += [nn.Conv3d(c, 2 * c, 3, stride=2, padding=1, bias=True), _in3d(2 * c), nn.ReLU(True)]
+            c *= 2
+        L += [_ResBlock3d(c) for _ in range(n_residual_blocks)]  # :44-45
+        for _ in range(2):  # :48-61 (ConvTranspose3d keeps torch's default bias=True)
+            L += [nn.ConvTranspose3d(c, c // 2, 3, stride=2, padding=1, output_padding=1), _in3d(c // 2), nn.ReLU(True)]
+            c //= 2
+        L += [nn.ReplicationPad3d(3), nn.Conv3d(64, out_channels, 7, bias=True), nn.Tanh()]  # :64
+        self.model = nn.Sequential(*L)
+
+    def forward(self, x):
+        return self.model(x)
+
+
 class OraclePiresnet3D(nn.Module):
     """ganslate/nn/generators/resnet/piresnet3d.py:28-119 (norm_type 'instance')."""
 

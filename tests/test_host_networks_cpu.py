@@ -134,3 +134,56 @@ def test_gradient_side_pixel_windows_host_logic(monkeypatch):
     _load(ours, ref)
     assert ours.model[-2].conv_op().bwd_window
     _compare(ref, ours, torch.rand(1, 3, 24, 24) * 2 - 1)
+
+
+def test_resnet3d_slab_convolutions_host_logic(monkeypatch):
+    """Resnet3D: the 7x7x7 layers (343 taps > GB_MAX_TAPS) run as seven (1,7,7) depth slabs accumulated in FP32
+    (ops.SlabConv: depth-shifted views, per-slab packed weights read from weight[:, :, dz], per-slab weight-gradient
+    unpack into dW[:, :, dz]); the first layer's slabs additionally use the pixel-window formulation."""
+    lib = fake_cabi.install(monkeypatch)
+    from ganslate_b200 import ops
+    from ganslate_b200.nn.generators import Resnet3D
+    from oracle import torch_oracle as O
+    from oracle import torch_oracle3d as O3
+    torch.manual_seed(0)
+    ref = O.init_weights(O3.OracleResnet3D(1, 2, n_residual_blocks=1))
+    ours = Resnet3D(1, 2, "instance", n_residual_blocks=1)
+    _load(ours, ref)
+    first, last = ours.model[1].conv_op(), ours.model[-2].conv_op()
+    assert isinstance(first, ops.SlabConv) and isinstance(last, ops.SlabConv) and len(first.slabs) == 7
+    assert first.slabs[0].window and not last.slabs[0].window
+    x = torch.rand(1, 1, 8, 8, 8) * 2 - 1
+    _compare(ref, ours, x)
+    assert lib.calls["gb_conv_data"] >= 2 * 7
+
+
+def test_slab_convolution_matches_torch_exactly_enough(monkeypatch):
+    """One SlabConv layer against torch.nn.functional.conv3d on bf16-valued inputs: forward, data gradient, weight and
+    bias gradient (tolerance 1e-2 max-relative, as tests/gpu_bringup.py uses on the GPU)."""
+    fake_cabi.install(monkeypatch)
+    from ganslate_b200.nn import layers
+    from parity_util import max_rel
+    torch.manual_seed(3)
+    conv = layers.Conv3d(16, 24, (5, 6, 6), padding=(0, 1, 2), bias=True)   # 180 taps -> 5 slabs of 36
+    with torch.no_grad():
+        conv.weight.copy_((torch.randn_like(conv.weight) * 0.05).to(torch.bfloat16).float())
+        conv.bias.copy_(torch.randn_like(conv.bias) * 0.1)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = torch.nn.Sequential(conv)
+
+        def forward(self, t):
+            return layers.run_network(self, list(self.model), t)
+
+    x = torch.randn(2, 16, 7, 9, 8).to(torch.bfloat16).float().requires_grad_(True)
+    y = Net()(x)
+    xr = x.detach().clone().requires_grad_(True)
+    wr, br = conv.weight.detach().clone().requires_grad_(True), conv.bias.detach().clone().requires_grad_(True)
+    yr = torch.nn.functional.conv3d(xr, wr, br, padding=(0, 1, 2))
+    g = torch.randn_like(yr).to(torch.bfloat16).float()
+    y.backward(g)
+    yr.backward(g)
+    assert max_rel(y, yr) < 1e-2 and max_rel(x.grad, xr.grad) < 1e-2
+    assert max_rel(conv.weight.grad, wr.grad) < 1e-2 and max_rel(conv.bias.grad, br.grad) < 1e-2

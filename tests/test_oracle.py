@@ -270,6 +270,17 @@ def test_oracle_piresnet3d_and_separable_vnet_match_golden():
                       f"piresnet y inverse={inverse}")
         assert_digest(_digest_small(gx) | {"sq_sum": (gx.double()**2).sum().item()}, gold["piresnet"][str(inverse)]["dx"],
                       f"piresnet dx inverse={inverse}", rtol=1e-3)
+    r3 = O3.OracleResnet3D(1, 2, n_residual_blocks=1)
+    torch.manual_seed(0)
+    O.init_weights(r3)
+    assert list(r3.state_dict().keys()) == gold["resnet3d"]["keys"]
+    gen = torch.Generator().manual_seed(8)
+    x = (torch.rand((1, 1, 8, 8, 8), generator=gen) * 2 - 1).requires_grad_(True)
+    y = r3(x)
+    (gx,) = torch.autograd.grad(y.square().sum(), x)
+    assert_digest(_digest_small(y) | {"sq_sum": (y.double()**2).sum().item()}, gold["resnet3d"]["y"], "resnet3d y")
+    assert_digest(_digest_small(gx) | {"sq_sum": (gx.double()**2).sum().item()}, gold["resnet3d"]["dx"], "resnet3d dx",
+                  rtol=1e-3)
     v = O3.OracleVnet3D(1, 1, first_layer_channels=8, down_blocks=(1, 1), up_blocks=(1, 1), use_inverse=True,
                         is_separable=True)
     torch.manual_seed(0)
@@ -288,10 +299,15 @@ def test_oracle_piresnet3d_and_separable_vnet_match_golden():
 
 def test_b200_piresnet3d_and_separable_vnet_mirror_reference_state_dict():
     """Drop-in obligation: same state_dict keys, parameter order and shapes as the reference modules."""
-    from ganslate_b200.nn.generators import Piresnet3D, Vnet3D
+    from ganslate_b200.nn.generators import Piresnet3D, Resnet3D, Vnet3D
     from oracle import torch_oracle3d as O3
     with open(os.path.join(GOLDEN, "piresnet3d_separable_small.json")) as f:
         gold = json.load(f)
+    ours = Resnet3D(1, 2, "instance", n_residual_blocks=1)
+    ref = O3.OracleResnet3D(1, 2, n_residual_blocks=1)
+    assert list(ours.state_dict().keys()) == gold["resnet3d"]["keys"]
+    assert [tuple(p.shape) for p in ours.parameters()] == [tuple(p.shape) for p in ref.parameters()]
+    ours.load_state_dict(ref.state_dict())
     ours = Piresnet3D(2, 2, "instance", depth=2, first_layer_channels=8, use_memory_saving=False, use_inverse=True)
     ref = O3.OraclePiresnet3D(2, 2, 2, first_layer_channels=8, use_inverse=True)
     assert list(ours.state_dict().keys()) == gold["piresnet"]["keys"]

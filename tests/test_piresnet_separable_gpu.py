@@ -22,8 +22,9 @@ def _compare(ref, ours, x, inverse, out_tol=3e-2, cos_tol=0.9):
     from parity_util import cosine, rel_l2
     xr = x.clone().requires_grad_(True)
     xo = x.clone().cuda().requires_grad_(True)
-    yr = ref(xr, inverse=inverse)
-    yo = ours(xo, inverse=inverse)
+    kw = {} if inverse is None else {"inverse": inverse}
+    yr = ref(xr, **kw)
+    yo = ours(xo, **kw)
     assert yo.shape == yr.shape and rel_l2(yo, yr) <= out_tol, (inverse, rel_l2(yo, yr))
     g = torch.randn_like(yr)
     ref.zero_grad()
@@ -93,3 +94,16 @@ def test_separable_vnet3d_both_directions_vs_oracle():
     x, _ = O3.synthetic_volume(1, 1, 16, 32, seed=3)
     for inverse in (False, True):
         _compare(ref, ours, x, inverse)
+
+
+def test_resnet3d_slab_convolutions_vs_oracle():
+    """Resnet3D: 7x7x7 layers as seven depth slabs accumulated in FP32 (ops.SlabConv), replicate padding."""
+    from ganslate_b200.nn.generators import Resnet3D
+    from oracle import torch_oracle as O
+    from oracle import torch_oracle3d as O3
+    torch.manual_seed(0)
+    ref = O.init_weights(O3.OracleResnet3D(1, 2, n_residual_blocks=2))
+    ours = Resnet3D(1, 2, "instance", n_residual_blocks=2).cuda()
+    _load(ours, ref)
+    x, _ = O3.synthetic_volume(1, 1, 8, 16, seed=3)
+    _compare(ref, ours, x, None)
