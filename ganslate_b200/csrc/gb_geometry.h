@@ -34,9 +34,14 @@ inline gb_fastdiv gb_make_fastdiv(uint32_t d) {
   f.pad_ = 0;
   return f;
 }
-#if defined(__CUDACC__)
-__device__ __forceinline__ uint32_t gb_div(uint32_t x, const gb_fastdiv& f) { return (__umulhi(x, f.mul) + x) >> f.shr; }
+// one definition for device code and for host code / CPU tests that replay the kernels' tile decoding
+GB_HD uint32_t gb_div(uint32_t x, const gb_fastdiv& f) {
+#if defined(__CUDA_ARCH__)
+  return (__umulhi(x, f.mul) + x) >> f.shr;
+#else
+  return ((uint32_t)(((uint64_t)x * f.mul) >> 32) + x) >> f.shr;
 #endif
+}
 
 struct gb_row {
   int n, qz, qy, qx;

@@ -165,7 +165,7 @@ struct Item {
 };
 
 // item index -> this CTA's tile.  Identical arithmetic in every role of both CTAs.
-__device__ __forceinline__ bool tile_of(const gb_conv_params& p, const Cg2Geom& g, int cls, uint32_t t, int& x0, int& y0,
+GB_HD bool tile_of(const gb_conv_params& p, const Cg2Geom& g, int cls, uint32_t t, int& x0, int& y0,
                                         int& z0, int& n) {
   int q[3];
   gb_class_extents(p, cls, q);
@@ -182,7 +182,7 @@ __device__ __forceinline__ bool tile_of(const gb_conv_params& p, const Cg2Geom& 
 }
 
 template <int BN, bool PAIR>
-__device__ __forceinline__ Item decode_item(const gb_conv_params& p, const Cg2Geom& g, uint32_t item, uint32_t rank) {
+GB_HD Item decode_item(const gb_conv_params& p, const Cg2Geom& g, uint32_t item, uint32_t rank) {
   Item it;
   uint32_t u = gb_div(item, g.div_pairs);
   const uint32_t pair = item - u * g.div_pairs.d;
@@ -520,13 +520,9 @@ int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb
 
 }  // namespace
 
-// Returns -1 when this path does not apply or is switched off (knob 16: 0 = off, 1 = CTA pair, 2 = persistent single
-// CTA), 0 on success, >0 on error.
-int gb_conv_data_cg2(const gb_conv_params& p, cudaStream_t st) {
-  const int mode = g_gb_knobs[16];
-  if (mode == 0 || g_gb_knobs[3] != 0) return -1;
-  const bool pair = mode == 1;
-  if (p.in.C % 64 != 0 || p.in.pad != 0 || !gb_tma_available()) return -1;
+// Geometry of a launch: -1 = path does not apply, 0 = nothing to do, 1 = geometry filled.
+static int cg2_geometry(const gb_conv_params& p, bool pair, Cg2Geom* gout, int* bn_out, int* kpad_out) {
+  if (p.in.C % 64 != 0 || p.in.pad != 0) return -1;
   if (p.ncols > MAX_BIAS || p.ncols < 33) return -1;  // narrow outputs stay on the one-tile-per-CTA kernels
   for (int d = 0; d < 3; ++d)
     if (p.in_mul[d] < 1 || p.in_mul[d] > 4) return -1;
@@ -583,9 +579,26 @@ int gb_conv_data_cg2(const gb_conv_params& p, cudaStream_t st) {
   g.div_pairs = gb_make_fastdiv((uint32_t)g.npairs);
   g.div_nb = gb_make_fastdiv((uint32_t)g.nb);
   g.nstages = 0;
+  *gout = g;
+  *bn_out = bn;
+  *kpad_out = kpad;
+  return 1;
+}
+
+// Returns -1 when this path does not apply or is switched off (knob 16: 0 = off, 1 = CTA pair, 2 = persistent single
+// CTA), 0 on success, >0 on error.
+int gb_conv_data_cg2(const gb_conv_params& p, cudaStream_t st) {
+  const int mode = g_gb_knobs[16];
+  if (mode == 0 || g_gb_knobs[3] != 0) return -1;
+  const bool pair = mode == 1;
+  if (!gb_tma_available()) return -1;
+  Cg2Geom g;
+  int bn = 0, kpad = 0;
+  const int r = cg2_geometry(p, pair, &g, &bn, &kpad);
+  if (r <= 0) return r;
   CUtensorMap ma, mb;
-  if (gb_tma_activation_map(p.in, tw, th, &ma, p.in_mul, p.in_c_valid)) return 1;
-  if (gb_tma_weight_map(p.wpacked, kpad, p.nclass * p.npad, box_rows, &mb)) return 1;
+  if (gb_tma_activation_map(p.in, g.tw, g.th, &ma, p.in_mul, p.in_c_valid)) return 1;
+  if (gb_tma_weight_map(p.wpacked, kpad, p.nclass * p.npad, pair ? bn / 2 : bn, &mb)) return 1;
   if (pair) {
     switch (bn) {
       case 64: return launch<64, true>(p, ma, mb, g, st);
@@ -600,4 +613,40 @@ int gb_conv_data_cg2(const gb_conv_params& p, cudaStream_t st) {
     }
   }
   return -1;
+}
+
+// Host replay of the persistent kernels' work decomposition (no device needed): for item i and CTA rank r of the pair
+// (rank 0 only in mode 2) writes 8 ints {cls, n0, x0, y0, z0, n, valid, any} at out[(i * ranks + r) * 8], with the SAME
+// decode_item code the kernels run, and the patch shape / column block / item count into info[0..5] =
+// {tw, th, bn, nitems, ranks, ntiles}.  Returns the number of items (0 when out is too small: call with out = NULL
+// first), -1 when the launch would not take this path.  CPU tests check that every output pixel of every class and
+// column block is produced exactly once.
+extern "C" int gb_debug_cg2_plan(const gb_conv_params* pp, int mode, int32_t* info, int32_t* out, int64_t out_ints) {
+  if (pp == nullptr || info == nullptr || (mode != 1 && mode != 2)) return -1;
+  const bool pair = mode == 1;
+  Cg2Geom g;
+  int bn = 0, kpad = 0;
+  const int r = cg2_geometry(*pp, pair, &g, &bn, &kpad);
+  if (r < 0) return -1;
+  const int ranks = pair ? 2 : 1;
+  if (r == 0) {
+    info[0] = info[1] = info[2] = info[3] = info[5] = 0;
+    info[4] = ranks;
+    return 0;
+  }
+  info[0] = g.tw; info[1] = g.th; info[2] = bn; info[3] = g.nitems; info[4] = ranks; info[5] = g.ntiles;
+  if (out == nullptr || out_ints < (int64_t)g.nitems * ranks * 8) return 0;
+  for (int i = 0; i < g.nitems; ++i)
+    for (int rk = 0; rk < ranks; ++rk) {
+      Item it;
+      switch (bn) {  // n0 depends on the column-block width only through BN
+        case 64: it = pair ? decode_item<64, true>(*pp, g, (uint32_t)i, (uint32_t)rk) : decode_item<64, false>(*pp, g, (uint32_t)i, 0u); break;
+        case 128: it = pair ? decode_item<128, true>(*pp, g, (uint32_t)i, (uint32_t)rk) : decode_item<128, false>(*pp, g, (uint32_t)i, 0u); break;
+        default: it = pair ? decode_item<256, true>(*pp, g, (uint32_t)i, (uint32_t)rk) : decode_item<256, false>(*pp, g, (uint32_t)i, 0u); break;
+      }
+      int32_t* o = out + ((int64_t)i * ranks + rk) * 8;
+      o[0] = it.cls; o[1] = it.n0; o[2] = it.x0; o[3] = it.y0; o[4] = it.z0; o[5] = it.n; o[6] = it.valid ? 1 : 0;
+      o[7] = it.any ? 1 : 0;
+    }
+  return g.nitems;
 }

@@ -275,6 +275,10 @@ const char* gb_last_error(void);
 unsigned long long gb_launch_count(void);
 /* 1 when the driver accepts the overlapping-stride tensor map that pixel-window views need (gb_conv_params.in_c_valid) */
 int gb_tma_window_supported(void);
+/* Host-only replay of the work decomposition of the persistent convolution kernels (csrc/igemm_cg2.cu; mode 1 = CTA
+ * pair, 2 = single CTA): see the definition.  Used by the CPU tests; touches no device. */
+int gb_debug_cg2_plan(const gb_conv_params* p, int mode, int32_t* info, int32_t* out, int64_t out_ints);
+
 /* debug knobs for bring-up (e.g. descriptor variants); returns previous value */
 int gb_debug_knob(int knob, int value);
 
