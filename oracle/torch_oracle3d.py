@@ -287,7 +287,9 @@ class OracleRevGAN:
         torch.manual_seed(seed)
         self.networks = {}
         for name in ("G", "D_B", "D_A"):  # revgan.py:50, base.py:51-67
-            if name == "G":
+            if name == "G" and getattr(c, "piresnet_depth", 0):  # brats revgan.yaml:27-33
+                net = OraclePiresnet3D(c.in_channels, c.out_channels, c.piresnet_depth, c.first_layer_channels, True)
+            elif name == "G":
                 net = OracleVnet3D(c.in_channels, c.out_channels, c.first_layer_channels, c.down_blocks, c.up_blocks,
                                    use_inverse=True)
             else:

@@ -377,6 +377,23 @@ class FakeLib:
                 _flat(p.dbias, v.C, torch.float32).add_(d.sum(dim=(0, 1, 2, 3)))
         return 0
 
+    # ------------------------------------------------------------------ losses
+    def gb_mse_const(self, pred, target, n, loss, grad, stream):
+        self._count("gb_mse_const")
+        d = _flat(pred, n, torch.float32) - target
+        _flat(loss, 1, torch.float32).add_((d * d).sum() / n)
+        if grad:
+            _flat(grad, n, torch.float32).copy_(2.0 * d / n)
+        return 0
+
+    def gb_l1(self, a, b, n, loss, grad, stream):
+        self._count("gb_l1")
+        d = _flat(a, n, torch.float32) - _flat(b, n, torch.float32)
+        _flat(loss, 1, torch.float32).add_(d.abs().sum() / n)
+        if grad:
+            _flat(grad, n, torch.float32).copy_(torch.sign(d) / n)
+        return 0
+
     # ------------------------------------------------------------------ layout / padding
     def gb_nchw_to_cl(self, src, Cc, dst, pre, dst_fp32, stream):
         self._count("gb_nchw_to_cl")

@@ -187,3 +187,83 @@ def test_slab_convolution_matches_torch_exactly_enough(monkeypatch):
     yr.backward(g)
     assert max_rel(y, yr) < 1e-2 and max_rel(x.grad, xr.grad) < 1e-2
     assert max_rel(conv.weight.grad, wr.grad) < 1e-2 and max_rel(conv.bias.grad, br.grad) < 1e-2
+
+
+def test_cyclegan_iteration_host_logic(monkeypatch):
+    """One whole CycleGAN iteration (ganslate_b200.nn.gans.unpaired.CycleGAN built by the plug-in builders: 4 generator
+    passes, frozen-discriminator G step, two D steps with the ImagePool) through the fake backend against the CPU
+    oracle's iteration -- the recipe's host logic without a GPU.  Optimizer steps are skipped on both sides (FusedAdam
+    is a CUDA launch); losses, generated images and per-parameter gradients are compared."""
+    import random
+    fake_cabi.install(monkeypatch)
+    from ganslate_b200.nn.gans import base
+    from ganslate_b200.presets import cyclegan_resnet2d
+    from ganslate_b200.utils.builders import build_gan
+    from oracle import torch_oracle as O
+    monkeypatch.setattr(base.BaseGAN, "_specify_device", lambda self: torch.device("cpu"))
+    random.seed(0)
+    oracle = O.OracleCycleGAN(O.default_cyclegan_conf(n_residual_blocks=1), seed=0)
+    torch.manual_seed(0)
+    ours = build_gan(cyclegan_resnet2d(batch_size=1, n_residual_blocks=1))
+    for name in oracle.networks:  # same seed, same init order -> identical weights
+        for (k1, p1), (k2, p2) in zip(oracle.networks[name].state_dict().items(), ours.networks[name].state_dict().items()):
+            assert k1 == k2 and torch.equal(p1, p2), (name, k1)
+    a, b = O.synthetic_batch(1, 3, 64, seed=1)  # (PatchGAN's last InstanceNorm sees 7x7 positions at this size)
+    lo = oracle.optimize_parameters(a, b, step_optimizers=False)
+    for o in ours.optimizers.values():
+        monkeypatch.setattr(o, "step", lambda *args, **kw: None)
+    ours.set_input({"A": a, "B": b})
+    ours.optimize_parameters()
+    for k, ref in lo.items():
+        got = float(ours.losses[k].detach())
+        assert abs(ref - got) <= 2e-2 * max(abs(ref), 1e-3), (k, ref, got)
+    for k in ("fake_B", "rec_A", "fake_A", "rec_B"):
+        assert rel_l2(ours.visuals[k], oracle.visuals[k]) < 8e-2, (k, rel_l2(ours.visuals[k], oracle.visuals[k]))
+    bad = []
+    for name in oracle.networks:
+        po, pg = dict(oracle.networks[name].named_parameters()), dict(ours.networks[name].named_parameters())
+        for k, p in po.items():
+            if p.grad is None or p.dim() <= 1:
+                continue
+            c = cosine(pg[k].grad, p.grad)
+            if c < 0.9:
+                bad.append((name, k, c))
+    assert not bad, bad
+
+
+def test_revgan_piresnet3d_iteration_host_logic(monkeypatch):
+    """The shipped BraTS experiment's pairing (RevGAN + Piresnet3D + PatchGAN3D(n_layers 2), revgan.yaml:25-39) at a
+    small size: one whole iteration through the fake backend against the oracle's RevGAN iteration."""
+    import random
+    fake_cabi.install(monkeypatch)
+    from ganslate_b200.nn.gans import base
+    from ganslate_b200.presets import revgan_piresnet3d
+    from ganslate_b200.utils.builders import build_gan
+    from oracle import torch_oracle3d as O3
+    monkeypatch.setattr(base.BaseGAN, "_specify_device", lambda self: torch.device("cpu"))
+    random.seed(0)
+    oracle = O3.OracleRevGAN(O3.default_3d_conf(in_channels=1, out_channels=1, ndf=16, n_layers=2, first_layer_channels=16,
+                                                piresnet_depth=2), seed=0)
+    torch.manual_seed(0)
+    ours = build_gan(revgan_piresnet3d(channels=1, depth=2, first_layer_channels=16, ndf=16, n_layers=2))
+    for name in ("G", "D_B", "D_A"):
+        _load(ours.networks[name], oracle.networks[name])
+    a, b = O3.synthetic_volume(1, 1, 16, 32, seed=1)
+    lo = oracle.optimize_parameters(a, b, step_optimizers=False)
+    for o in ours.optimizers.values():
+        monkeypatch.setattr(o, "step", lambda *args, **kw: None)
+    ours.set_input({"A": a, "B": b})
+    ours.optimize_parameters()
+    for k, v in lo.items():
+        assert abs(float(ours.losses[k].detach()) - v) <= 2e-2 * abs(v) + 1e-4, (k, v, float(ours.losses[k].detach()))
+    for k, tol in (("fake_B", 3e-2), ("fake_A", 3e-2), ("rec_A", 1.2e-1), ("rec_B", 1.2e-1)):
+        assert rel_l2(ours.visuals[k], oracle.visuals[k]) <= tol, (k, rel_l2(ours.visuals[k], oracle.visuals[k]))
+    bad = []
+    for name in ("G", "D_B", "D_A"):
+        po, pg = dict(oracle.networks[name].named_parameters()), dict(ours.networks[name].named_parameters())
+        for k, p in po.items():
+            if k.endswith("weight") and p.dim() > 1 and p.grad is not None and p.grad.abs().max() > 0:
+                c = cosine(pg[k].grad, p.grad)
+                if c < 0.9:
+                    bad.append((name, k, c))
+    assert not bad, bad

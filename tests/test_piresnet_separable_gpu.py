@@ -107,3 +107,39 @@ def test_resnet3d_slab_convolutions_vs_oracle():
     _load(ours, ref)
     x, _ = O3.synthetic_volume(1, 1, 8, 16, seed=3)
     _compare(ref, ours, x, None)
+
+
+def test_revgan_piresnet3d_iteration_vs_oracle():
+    """The shipped BraTS experiment's pairing (RevGAN + Piresnet3D + PatchGAN3D(n_layers 2), revgan.yaml:25-39)."""
+    import random
+    from ganslate_b200.presets import revgan_piresnet3d
+    from ganslate_b200.utils.builders import build_gan
+    from oracle import torch_oracle3d as O3
+    from parity_util import cosine, rel_l2
+    random.seed(0)
+    oracle = O3.OracleRevGAN(O3.default_3d_conf(in_channels=1, out_channels=1, ndf=16, n_layers=2, first_layer_channels=16,
+                                                piresnet_depth=2), seed=0)
+    torch.manual_seed(0)
+    ours = build_gan(revgan_piresnet3d(channels=1, depth=2, first_layer_channels=16, ndf=16, n_layers=2))
+    for name in ("G", "D_B", "D_A"):
+        _load(ours.networks[name], oracle.networks[name])
+    a, b = O3.synthetic_volume(1, 1, 16, 32, seed=1)
+    lo = oracle.optimize_parameters(a, b, step_optimizers=False)
+    for o in ours.optimizers.values():
+        o.step = lambda *a, **k: None
+    ours.set_input({"A": a, "B": b})
+    ours.optimize_parameters()
+    torch.cuda.synchronize()
+    for k, v in lo.items():
+        assert abs(float(ours.losses[k]) - v) <= 2e-2 * abs(v) + 1e-4, (k, v, float(ours.losses[k]))
+    for k, tol in (("fake_B", 3e-2), ("fake_A", 3e-2), ("rec_A", 1.2e-1), ("rec_B", 1.2e-1)):
+        assert rel_l2(ours.visuals[k], oracle.visuals[k]) <= tol, (k, rel_l2(ours.visuals[k], oracle.visuals[k]))
+    bad = []
+    for name in ("G", "D_B", "D_A"):
+        po, pg = dict(oracle.networks[name].named_parameters()), dict(ours.networks[name].named_parameters())
+        for k, p in po.items():
+            if k.endswith("weight") and p.dim() > 1 and p.grad is not None and p.grad.abs().max() > 0:
+                c = cosine(pg[k].grad, p.grad)
+                if c < 0.9:
+                    bad.append((name, k, c))
+    assert not bad, bad
