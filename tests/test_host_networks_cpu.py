@@ -267,3 +267,16 @@ def test_revgan_piresnet3d_iteration_host_logic(monkeypatch):
                 if c < 0.9:
                     bad.append((name, k, c))
     assert not bad, bad
+
+
+def test_bringup_cases_through_fake_backend(monkeypatch):
+    """Every single-operator case of tests/gpu_bringup.py (the cases the GPU suite runs against torch: 1x1 ... 7x7,
+    strided, transposed, 3-D convolutions incl. pixel windows; InstanceNorm groups with and without borders; residual
+    blocks) through the fake backend on the CPU with the same tolerances -- this is what pins tests/fake_cabi.py to
+    the semantics the GPU kernels are tested for."""
+    fake_cabi.install(monkeypatch)
+    import gpu_bringup
+    monkeypatch.setattr(gpu_bringup, "dev", "cpu")
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    bad = [i for i, case in enumerate(gpu_bringup.CASES[:-1]) if not case()]  # (the last entry is the loss kernels)
+    assert not bad, bad
