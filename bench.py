@@ -22,6 +22,19 @@ sys.path.insert(0, ROOT)
 METRIC = "CycleGAN train img/s"
 UNIT = "img/s"
 
+# The five configurations BASELINE.json names.  The default (config 1 at batch 8 per GPU) is the bench line the driver
+# reads; the others are selected with --workload for the per-shape throughput table (`tools/gpu_round.sh ... shapes`).
+#   name: (metric, preset, per-GPU batch default, input shape after the batch axis, CUDA-graph replay supported)
+WORKLOADS = {
+    "cyclegan2d": ("CycleGAN train img/s", "cyclegan_resnet2d", 8, None, True),
+    "pix2pix_resnet": ("Pix2Pix Resnet2D train img/s", "pix2pix_resnet2d", 8, (3, 256, 512), True),
+    "pix2pix_unet": ("Pix2Pix Unet2D train img/s", "pix2pix_unet2d", 8, (3, 256, 512), True),
+    "cut": ("CUT train img/s", "cut_resnet2d", 1, (3, 256, 256), False),
+    "cyclegan3d": ("CycleGAN 3D Vnet3D train patches/s", "cyclegan_vnet3d", 1, (1, 32, 256, 256), False),
+    "revgan3d": ("RevGAN 3D Vnet3D train patches/s", "revgan_vnet3d", 1, (4, 128, 128, 128), False),
+    "revgan_piresnet3d": ("RevGAN 3D Piresnet3D train patches/s", "revgan_piresnet3d", 1, (1, 32, 176, 176), False),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -33,14 +46,25 @@ def parse():
                     help="per-GPU batch (8 = the per-GPU batch BASELINE.json's GPU configs name; the reference's "
                          "own CPU case is batch 1: --batch 1)")
     ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--workload", default="cyclegan2d", choices=sorted(WORKLOADS),
+                    help="which BASELINE.json configuration to time (default: the CycleGAN headline configuration)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--roofline-all-ranks", action="store_true", help="N>1: profile the per-kernel roofline too")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.workload != "cyclegan2d" and "--batch" not in sys.argv and "GB_BENCH_BATCH" not in os.environ:
+        args.batch = WORKLOADS[args.workload][2]
+    return args
 
 
 def workload_config(args, world):
+    if args.workload != "cyclegan2d":
+        metric, preset, _, shape, graph = WORKLOADS[args.workload]
+        return {"workload": f"{metric.replace(' train img/s', '').replace(' train patches/s', '')} "
+                            f"(ganslate_b200.presets.{preset}), synthetic {'x'.join(map(str, shape))}, batch {args.batch}/GPU",
+                "global_batch": args.batch * world, "image": list(shape), "parallelism": f"dp{world}",
+                "l2_policy": "2 x 126 MB flush buffer written between timed steps"}
     return {
         "workload": f"CycleGAN Resnet2D-9blk + PatchGAN2D(n_layers 3), synthetic 3x{args.size}x{args.size}, "
                     f"batch {args.batch}/GPU, lambda 10, lsgan, Adam(2e-4, 0.5/0.999)",
@@ -73,6 +97,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    if args.workload != "cyclegan2d":
+        raise SystemExit("--impl reference times the headline configuration (--workload cyclegan2d) only")
     steps = max(1, min(args.steps, 5))
     rate, med, cores = cpu_step_rate(args.size, args.batch, steps, warmup=min(args.warmup, 1))
     world = 1
@@ -139,7 +165,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from ganslate_b200 import _cabi, profiler
-    from ganslate_b200.presets import cyclegan_resnet2d
+    from ganslate_b200 import presets
     from ganslate_b200.utils import communication
     from ganslate_b200.utils.builders import build_gan
 
@@ -154,12 +180,18 @@ def run_b200(args):
     lib = _cabi.lib()  # fails loudly if the CUDA extension is missing
 
     torch.manual_seed(0)
-    conf = cyclegan_resnet2d(batch_size=args.batch, cuda_graph=not args.no_graph)
+    metric, preset, _, shape, graph_ok = WORKLOADS[args.workload]
+    default_wl = args.workload == "cyclegan2d"
+    if shape is None:
+        shape = (3, args.size, args.size)
+    if not graph_ok:
+        args.no_graph = True  # CUT / RevGAN recipes run eagerly (their step is not captured)
+    conf = getattr(presets, preset)(batch_size=args.batch, cuda_graph=not args.no_graph)
     model = build_gan(conf)
     # synthetic inputs U(-1, 1) (images are normalised to [-1, 1] in the reference); each rank draws its own shard
     gen = torch.Generator(device="cpu").manual_seed(1 + rank)
-    a_host = torch.rand((args.batch, 3, args.size, args.size), generator=gen) * 2 - 1
-    b_host = torch.rand((args.batch, 3, args.size, args.size), generator=gen) * 2 - 1
+    a_host = torch.rand((args.batch,) + tuple(shape), generator=gen) * 2 - 1
+    b_host = torch.rand((args.batch,) + tuple(shape), generator=gen) * 2 - 1
     a_host, b_host = a_host.pin_memory(), b_host.pin_memory()
     a_dev, b_dev = a_host.to(dev), b_host.to(dev)
     flush = torch.empty(2 * 126 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -184,7 +216,7 @@ def run_b200(args):
             e0.record()
             step(resident)
             if not resident:
-                _ = float(model.losses["cycle_A"])  # D2H read of a step result
+                _ = float(next(iter(model.losses.values())))  # D2H read of a step result
             e1.record()
             evs.append((e0, e1))
         torch.cuda.synchronize()
@@ -192,6 +224,8 @@ def run_b200(args):
 
     # graph mode: 11 eager iterations precede the capture (PyTorch's DDP + CUDA-graph recipe), then 2 replays
     n_warm = max(args.warmup, 3) + (0 if args.no_graph else model.graph_warmup_iters + 2)
+    if not default_wl:
+        args.no_cpu_baseline = True  # the CPU leg times the headline configuration only
     for _ in range(n_warm):
         step()
     barrier()
@@ -218,7 +252,7 @@ def run_b200(args):
         # per-kernel roofline: reported at N=1 (the kernels are the same at any N).  The profiled eager steps contain
         # the gradient all-reduce, so at N>1 EVERY rank must run them (a rank-0-only run dead-locks NCCL: r01m);
         # --roofline-all-ranks does that
-        roof = profiler.conv_roofline(model, a_dev, b_dev, steps=3)
+        roof = profiler.conv_roofline(model, a_dev, b_dev, steps=3, with_traffic=default_wl)
         barrier()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -229,15 +263,16 @@ def run_b200(args):
         imgs = args.batch * world * args.steps
         in_bytes = 2 * a_host.numel() * 4
         line = {
-            "metric": METRIC, "value": imgs / t, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric, "value": imgs / t, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, world),
             "e2e": {"value": imgs / t_e2e, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": clocks,
-            "conv_tflops_step": conv_flops_per_step(args.batch) * args.steps / t / 1e12,
             "cuda_graph": not args.no_graph,
         }
+        if default_wl and args.size == 256:
+            line["conv_tflops_step"] = conv_flops_per_step(args.batch) * args.steps / t / 1e12
         if roof is not None:
             line["roofline"] = roof["dominant"]
             line["roofline_detail"] = roof["detail"]

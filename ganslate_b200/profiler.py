@@ -38,7 +38,7 @@ def ncu_traffic(family, batch):
     return None, None
 
 
-def conv_roofline(model, a_dev, b_dev, steps=3):
+def conv_roofline(model, a_dev, b_dev, steps=3, with_traffic=True):
     """Run `steps` EAGER training steps with every C-ABI launch bracketed by CUDA events and aggregate per
     family. Returns {"dominant": roofline object of the family with the largest share, "detail": {...}}."""
     was_graph = getattr(model, "use_cuda_graph", False)
@@ -90,7 +90,7 @@ def conv_roofline(model, a_dev, b_dev, steps=3):
         "share_of_kernel_time": round(t_conv / total_t, 4),
         "how": "algorithmic FLOPs (SURVEY 8d) / CUDA-event time around each launch, eager steps",
     }
-    traffic, src = ncu_traffic("conv", int(a_dev.shape[0]))
+    traffic, src = ncu_traffic("conv", int(a_dev.shape[0])) if with_traffic else (None, None)
     if traffic is not None:
         dominant["traffic"], dominant["traffic_source"] = traffic, src
     return {"dominant": dominant, "detail": detail}

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box visit: parity tests, bench line, ncu launch list, ncu --set full of the top kernels.
-# Usage (under gpurun): [BATCH=8] bash tools/gpu_round.sh <tag> [tests|smoke|bench|benchref|exp|launches|full ...]
+# Usage (under gpurun): [BATCH=8] bash tools/gpu_round.sh <tag> [tests|smoke|bench|benchref|exp|shapes|launches|full ...]
 tag=${1:-r01}; shift
 what=${*:-tests bench launches full}
 B=${BATCH:-1}
@@ -31,6 +31,12 @@ exp)
   tail -c 1500 $out/bench_persist_b$B.json; tail -3 $out/bench_persist_b$B.err
   GB_BWD_WINDOW=1 timeout 900 python bench.py --batch $B --no-cpu-baseline --no-roofline > $out/bench_bwdwin_b$B.json 2> $out/bench_bwdwin_b$B.err
   tail -c 600 $out/bench_bwdwin_b$B.json; tail -3 $out/bench_bwdwin_b$B.err ;;
+shapes)
+  # throughput of every BASELINE.json configuration (one short bench line each; not the headline number)
+  for wl in pix2pix_resnet pix2pix_unet cut cyclegan3d revgan3d revgan_piresnet3d; do
+    timeout 900 python bench.py --workload $wl --steps 5 --warmup 3 --no-roofline > $out/bench_$wl.json 2> $out/bench_$wl.err
+    tail -c 700 $out/bench_$wl.json; tail -2 $out/bench_$wl.err
+  done ;;
 benchref)
   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 --batch $B > $out/bench_ref_b$B.json 2>> $out/bench_b$B.err; cat $out/bench_ref_b$B.json ;;
 launches)
