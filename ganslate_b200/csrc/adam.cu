@@ -10,6 +10,7 @@
 namespace {
 
 __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__ gb_adam_batch b) {
+  gb_pdl_enter();
   const gb_adam_item& it = b.item[blockIdx.y];
   const float lr = *b.lr;
   const float t = *b.step;  // already incremented for this step
@@ -66,7 +67,7 @@ extern "C" int gb_adam_multi(const gb_adam_batch* b, void* stream) {
   int blocks = (int)((mx / 4 + 255) / 256);
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
-  adam_multi_kernel<<<dim3(blocks, b->count), 256, 0, (cudaStream_t)stream>>>(*b);
+  gb_klaunch(adam_multi_kernel, dim3(blocks, b->count), 256, 0, (cudaStream_t)stream, *b);
   GB_LAUNCH_CHECK();
   return 0;
 }

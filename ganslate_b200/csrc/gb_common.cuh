@@ -36,6 +36,36 @@ extern unsigned long long g_gb_launches;  // kernels launched through the ABI (b
 static inline int gb_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 #ifdef __CUDACC__
+// ---------------------------------------------------------------- programmatic dependent launch (opt-in: knob 20)
+// Every kernel starts with gb_pdl_enter(): wait until the preceding kernel of the stream has completed and its
+// memory is visible, then allow the NEXT kernel's blocks to be scheduled while this one runs (they park at their own
+// wait).  Without the launch attribute both instructions are no-ops, so the default launches behave exactly as
+// before.  With knob 20 the launch gap and block ramp-up of kernel N+1 overlap the tail of kernel N (~960 dependent
+// launches per CycleGAN step).  Every block executes the wait first, so a kernel can never complete before its
+// predecessor did -- completion stays transitive along the stream.
+__device__ __forceinline__ void gb_pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline void gb_klaunch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  if (g_gb_knobs[20] == 0) {
+    kernel<<<grid, block, smem, st>>>(static_cast<Args&&>(args)...);
+    return;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);  // errors surface in GB_LAUNCH_CHECK (cudaGetLastError)
+}
+
 // ---------------------------------------------------------------- smem / mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -468,6 +468,7 @@ template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 igemm_cg2_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant__ CUtensorMap map_a,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Cg2Geom g) {
+  gb_pdl_enter();
   cg_body<BN, true>(p, map_a, map_b, g);
 }
 
@@ -475,6 +476,7 @@ template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 igemm_persist_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant__ CUtensorMap map_a,
                      const __grid_constant__ CUtensorMap map_b, const __grid_constant__ Cg2Geom g) {
+  gb_pdl_enter();
   cg_body<BN, false>(p, map_a, map_b, g);
 }
 
@@ -510,8 +512,8 @@ int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb
   g.nstages = g_gb_knobs[17] > 0 && g_gb_knobs[17] <= C::STAGES ? g_gb_knobs[17] : C::STAGES;
   int ngroups = max_groups < g.nitems ? max_groups : g.nitems;
   if (g_gb_knobs[18] > 0 && g_gb_knobs[18] < ngroups) ngroups = g_gb_knobs[18];
-  if constexpr (PAIR) igemm_cg2_kernel<BN><<<dim3(2 * ngroups, 1, 1), NTHREADS, C::SMEM, st>>>(p, ma, mb, g);
-  else igemm_persist_kernel<BN><<<dim3(ngroups, 1, 1), NTHREADS, C::SMEM, st>>>(p, ma, mb, g);
+  if constexpr (PAIR) gb_klaunch(igemm_cg2_kernel<BN>, dim3(2 * ngroups, 1, 1), NTHREADS, C::SMEM, st, p, ma, mb, g);
+  else gb_klaunch(igemm_persist_kernel<BN>, dim3(ngroups, 1, 1), NTHREADS, C::SMEM, st, p, ma, mb, g);
   g_gb_knobs[15] = PAIR ? 5 : 6;
   g_gb_knobs[19] += 1;  // launches served here (tests read and reset it)
   GB_LAUNCH_CHECK();

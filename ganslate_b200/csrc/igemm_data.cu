@@ -39,6 +39,7 @@ struct ClassDivs {
 template <int BN>
 __global__ void __launch_bounds__(256, Cfg<BN>::MIN_CTAS) igemm_data_kernel(const __grid_constant__ gb_conv_params p,
                                                                             const __grid_constant__ ClassDivs divs) {
+  gb_pdl_enter();
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -259,7 +260,7 @@ int launch(const gb_conv_params& p, const ClassDivs& divs, int64_t max_mc, cudaS
     attr_set = true;
   }
   dim3 grid(gb_cdiv(max_mc, BM), gb_cdiv(p.ncols, BN), p.nclass);
-  igemm_data_kernel<BN><<<grid, 256, C::SMEM, st>>>(p, divs);
+  gb_klaunch(igemm_data_kernel<BN>, grid, 256, C::SMEM, st, p, divs);
   g_gb_knobs[15] = 1;
   GB_LAUNCH_CHECK();
   return 0;

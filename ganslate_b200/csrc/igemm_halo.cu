@@ -65,6 +65,7 @@ template <int BN>
 __global__ void __launch_bounds__(256, HCfg<BN>::MIN_CTAS)
 igemm_halo_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant__ CUtensorMap map_a,
                   const __grid_constant__ CUtensorMap map_b, const __grid_constant__ HaloGeom hg, int base_offset_mode) {
+  gb_pdl_enter();
   using C = HCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -219,7 +220,7 @@ int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb
     attr_set = true;
   }
   dim3 grid(hg.ntiles, gb_cdiv(p.ncols, BN), p.nclass);
-  igemm_halo_kernel<BN><<<grid, 256, C::SMEM, st>>>(p, ma, mb, hg, g_gb_knobs[5] == 2 ? 1 : 0);
+  gb_klaunch(igemm_halo_kernel<BN>, grid, 256, C::SMEM, st, p, ma, mb, hg, g_gb_knobs[5] == 2 ? 1 : 0);
   g_gb_knobs[15] = 3;
   GB_LAUNCH_CHECK();
   return 0;

@@ -56,6 +56,7 @@ template <int BN>
 __global__ void __launch_bounds__(256, 1)
 igemm_pair_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant__ CUtensorMap map_a,
                   const __grid_constant__ CUtensorMap map_b, const __grid_constant__ PairGeom pg) {
+  gb_pdl_enter();
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int TMEM_COLS = NSUB * BN;  // 128 / 256 / 512
   extern __shared__ uint8_t smem_raw[];
@@ -245,7 +246,7 @@ int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb
   pg.b_stages = b_stages;
   const int smem = a_stages * a_stage + b_stages * B_BYTES + 2048;
   dim3 grid(gb_cdiv(pg.nsub, NSUB), gb_cdiv(p.ncols, BN), 1);
-  igemm_pair_kernel<BN><<<grid, 256, smem, st>>>(p, ma, mb, pg);
+  gb_klaunch(igemm_pair_kernel<BN>, grid, 256, smem, st, p, ma, mb, pg);
   g_gb_knobs[15] = 4;  // read-back slot: which data kernel served the last gb_conv_data call (tests)
   GB_LAUNCH_CHECK();
   return 0;

@@ -53,6 +53,7 @@ template <int BN>
 __global__ void __launch_bounds__(256, TCfg<BN>::MIN_CTAS)
 igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant__ CUtensorMap map_a,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TileGeom tg) {
+  gb_pdl_enter();
   using C = TCfg<BN>;
   constexpr int MAXS = 8;  // barrier slots (TCfg::STAGES <= 8)
   const int STAGES = tg.nstages;
@@ -303,7 +304,7 @@ int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb
   if (BN <= 128 && ctas >= 2 * 148 && kb_max <= 18 && shallow >= 3 && g_gb_knobs[8] == 0) ns = ns < shallow ? ns : shallow;
   if (ns < 1) ns = 1;
   tgl.nstages = ns;
-  igemm_tma_kernel<BN><<<grid, 256, ns * C::STAGE_BYTES + 2048, st>>>(p, ma, mb, tgl);
+  gb_klaunch(igemm_tma_kernel<BN>, grid, 256, ns * C::STAGE_BYTES + 2048, st, p, ma, mb, tgl);
   g_gb_knobs[15] = 2;
   GB_LAUNCH_CHECK();
   return 0;

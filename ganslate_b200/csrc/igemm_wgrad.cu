@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(256, WCfg<BN, RT>::MIN_CTAS) igemm_wgrad_kerne
                                                                               const __grid_constant__ CUtensorMap map_p,
                                                                               const __grid_constant__ CUtensorMap map_g,
                                                                               int blocks_per_split) {
+  gb_pdl_enter();
   using C = WCfg<BN, RT>;
   static_assert(RT == 1 || TMA, "two row tiles per CTA only on the TMA-fed path");
   constexpr int STAGES = C::STAGES;
@@ -350,11 +351,11 @@ int launch(const gb_wgrad_params& p, cudaStream_t st) {
   divs.f[2] = gb_make_fastdiv((uint32_t)p.plain.W);
   GB_CHECK(tma || p.gathered_c_valid == 0, "gb_conv_wgrad: gathered_c_valid (pixel-window views) needs the TMA path");
   if (rt2)
-    igemm_wgrad_kernel<256, true, 2><<<grid, 256, WCfg<256, 2>::SMEM, st>>>(p, divs, map_p, map_g, bps);
+    gb_klaunch(igemm_wgrad_kernel<256, true, 2>, grid, 256, WCfg<256, 2>::SMEM, st, p, divs, map_p, map_g, bps);
   else if (tma)
-    igemm_wgrad_kernel<BN, true><<<grid, 256, C::SMEM, st>>>(p, divs, map_p, map_g, bps);
+    gb_klaunch(igemm_wgrad_kernel<BN, true>, grid, 256, C::SMEM, st, p, divs, map_p, map_g, bps);
   else
-    igemm_wgrad_kernel<BN, false><<<grid, 256, C::SMEM, st>>>(p, divs, map_p, map_g, bps);
+    gb_klaunch(igemm_wgrad_kernel<BN, false>, grid, 256, C::SMEM, st, p, divs, map_p, map_g, bps);
   g_gb_knobs[14] = rt2 ? 2 : (tma ? 1 : 0);  // read-back slot: which wgrad variant served the last call (tests)
   GB_LAUNCH_CHECK();
   return 0;

@@ -109,6 +109,7 @@ __device__ __forceinline__ float act_fwd(float v, int act, float slope) {
 
 // ------------------------------------------------------------------------------------------- statistics
 __global__ void in_stats_kernel(gb_view x, float* __restrict__ stats, int pix_per_block) {
+  gb_pdl_enter();
   extern __shared__ float red[];  // [slots][2C]
   const int C8 = x.C >> 3;
   const int slots = blockDim.x / C8;
@@ -160,6 +161,7 @@ __global__ void in_stats_kernel(gb_view x, float* __restrict__ stats, int pix_pe
 
 // ------------------------------------------------------------------------------------------- forward
 __global__ void __launch_bounds__(256, 2) in_fwd_kernel(const __grid_constant__ gb_in_fwd_params p, int pix_per_block) {
+  gb_pdl_enter();
   const gb_view& x = p.x;
   const int C8 = x.C >> 3;
   const int slots = blockDim.x / C8;
@@ -227,6 +229,7 @@ __global__ void __launch_bounds__(256, 2) in_fwd_kernel(const __grid_constant__ 
 //                                     MODE 1: apply dx = rstd * (g - m1 - xhat*m2)
 template <int MODE>
 __global__ void __launch_bounds__(256, 2) in_bwd_kernel(const __grid_constant__ gb_in_bwd_params p, int pix_per_block) {
+  gb_pdl_enter();
   extern __shared__ float red[];
   const gb_view& x = p.x;
   const int C8 = x.C >> 3;
@@ -473,7 +476,7 @@ extern "C" int gb_in_stats(const gb_view* x, float* stats, void* stream) {
   GB_CHECK(x && x->ptr && stats, "gb_in_stats: null pointer");
   GB_CHECK(x->C % 8 == 0 && x->C <= 2048, "gb_in_stats: bad channel count %d", x->C);
   Launch L = plan(*x);
-  in_stats_kernel<<<L.grid, L.threads, sizeof(float) * 2 * L.slots * x->C, (cudaStream_t)stream>>>(*x, stats, L.ppb);
+  gb_klaunch(in_stats_kernel, L.grid, L.threads, sizeof(float) * 2 * L.slots * x->C, (cudaStream_t)stream, *x, stats, L.ppb);
   GB_LAUNCH_CHECK();
   return 0;
 }
@@ -490,7 +493,7 @@ extern "C" int gb_in_fwd(const gb_in_fwd_params* p, void* stream) {
     if (r >= 0) return r;
   }
   Launch L = plan(p->x);
-  in_fwd_kernel<<<L.grid, L.threads, 0, (cudaStream_t)stream>>>(*p, L.ppb);
+  gb_klaunch(in_fwd_kernel, L.grid, L.threads, 0, (cudaStream_t)stream, *p, L.ppb);
   GB_LAUNCH_CHECK();
   return 0;
 }
@@ -512,10 +515,10 @@ extern "C" int gb_in_bwd(const gb_in_bwd_params* p, void* stream) {
   }
   Launch L = plan(p->x);
   if (p->stats != nullptr) {
-    in_bwd_kernel<0><<<L.grid, L.threads, sizeof(float) * 3 * L.slots * p->x.C, st>>>(*p, L.ppb);
+    gb_klaunch(in_bwd_kernel<0>, L.grid, L.threads, sizeof(float) * 3 * L.slots * p->x.C, st, *p, L.ppb);
     GB_LAUNCH_CHECK();
   }
-  in_bwd_kernel<1><<<L.grid, L.threads, (p->dbias || p->dprelu) ? sizeof(float) * L.slots * p->x.C : 0, st>>>(*p, L.ppb);
+  gb_klaunch(in_bwd_kernel<1>, L.grid, L.threads, (p->dbias || p->dprelu) ? sizeof(float) * L.slots * p->x.C : 0, st, *p, L.ppb);
   GB_LAUNCH_CHECK();
   return 0;
 }

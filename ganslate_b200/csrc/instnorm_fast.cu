@@ -125,6 +125,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 template <bool RES>
 __global__ void __launch_bounds__(FTHREADS, FBLOCKS_PER_SM)
 in_fwd_fast_kernel(const __grid_constant__ gb_in_fwd_params p, const __grid_constant__ FastGeom g, float neg_slope) {
+  gb_pdl_enter();
   const gb_view& x = p.x;
   const int C8 = x.C >> 3;
   const int slots = FTHREADS / C8;
@@ -342,6 +343,7 @@ __device__ __forceinline__ void in_bwd_fast_pass(const gb_in_bwd_params& p, cons
 template <bool RES, int PASS>
 __global__ void __launch_bounds__(FTHREADS, FBLOCKS_PER_SM)
 in_bwd_fast_kernel(const __grid_constant__ gb_in_bwd_params p, const __grid_constant__ FastGeom g, float neg_slope) {
+  gb_pdl_enter();
   extern __shared__ float red[];  // [slots][C][2]
   if (PASS == 2) {
     in_bwd_fast_pass<RES>(p, g, neg_slope, 0, true, red);
@@ -399,7 +401,7 @@ template <bool RES>
 int launch_fwd(const gb_in_fwd_params& p, float neg_slope, cudaStream_t st) {
   bool fits;
   const FastGeom g = plan(p.x, num_sms() * FBLOCKS_PER_SM, &fits, 8);
-  in_fwd_fast_kernel<RES><<<dim3(g.nblocks, p.x.N), FTHREADS, 0, st>>>(p, g, neg_slope);
+  gb_klaunch(in_fwd_fast_kernel<RES>, dim3(g.nblocks, p.x.N), FTHREADS, 0, st, p, g, neg_slope);
   GB_LAUNCH_CHECK();
   return 0;
 }
@@ -431,9 +433,9 @@ int launch_bwd(const gb_in_bwd_params& p, float neg_slope, cudaStream_t st) {
     }
     cudaGetLastError();  // cooperative launch not possible here: fall through to two launches
   }
-  in_bwd_fast_kernel<RES, 0><<<grid, FTHREADS, smem, st>>>(p, g, neg_slope);
+  gb_klaunch(in_bwd_fast_kernel<RES, 0>, grid, FTHREADS, smem, st, p, g, neg_slope);
   GB_LAUNCH_CHECK();
-  in_bwd_fast_kernel<RES, 1><<<grid, FTHREADS, smem, st>>>(p, g, neg_slope);
+  gb_klaunch(in_bwd_fast_kernel<RES, 1>, grid, FTHREADS, smem, st, p, g, neg_slope);
   GB_LAUNCH_CHECK();
   return 0;
 }

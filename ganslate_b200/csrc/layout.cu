@@ -20,6 +20,7 @@ __device__ __forceinline__ void reflect_targets(const gb_view& v, int y, int x, 
 }
 
 __global__ void nchw_to_cl_kernel(const float* __restrict__ src, int C, gb_view dst, gb_view pre, int dst_fp32) {
+  gb_pdl_enter();
   const int64_t P = (int64_t)dst.D * dst.H * dst.W;
   const int64_t total = (int64_t)dst.N * P;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(dst.ptr);
@@ -69,6 +70,7 @@ __global__ void nchw_to_cl_kernel(const float* __restrict__ src, int C, gb_view 
 }
 
 __global__ void cl_to_nchw_kernel(gb_view src, float* __restrict__ dst, int C, int fold, int act, int src_fp32) {
+  gb_pdl_enter();
   const int64_t P = (int64_t)src.D * src.H * src.W;
   const int64_t total = (int64_t)src.N * P;
   const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(src.ptr);
@@ -123,7 +125,7 @@ extern "C" int gb_nchw_to_cl(const float* src, int C, const gb_view* dst, const 
   if (blocks < 1) blocks = 1;
   gb_view pv = {};
   if (pre != nullptr) pv = *pre;
-  nchw_to_cl_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, C, *dst, pv, dst_fp32);
+  gb_klaunch(nchw_to_cl_kernel, blocks, 256, 0, (cudaStream_t)stream, src, C, *dst, pv, dst_fp32);
   GB_LAUNCH_CHECK();
   return 0;
 }
@@ -135,7 +137,7 @@ extern "C" int gb_cl_to_nchw(const gb_view* src, float* dst, int C, int fold, in
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  cl_to_nchw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*src, dst, C, fold, act, src_fp32);
+  gb_klaunch(cl_to_nchw_kernel, blocks, 256, 0, (cudaStream_t)stream, *src, dst, C, fold, act, src_fp32);
   GB_LAUNCH_CHECK();
   return 0;
 }

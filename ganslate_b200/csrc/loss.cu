@@ -22,6 +22,7 @@ __device__ __forceinline__ float block_sum(float v) {
 
 __global__ void mse_const_kernel(const float* __restrict__ pred, float target, int64_t n, float inv_n,
                                  float* __restrict__ loss, float* __restrict__ grad) {
+  gb_pdl_enter();
   float acc = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float d = pred[i] - target;
@@ -34,6 +35,7 @@ __global__ void mse_const_kernel(const float* __restrict__ pred, float target, i
 
 __global__ void l1_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float inv_n,
                           float* __restrict__ loss, float* __restrict__ grad) {
+  gb_pdl_enter();
   float acc = 0.f;
   const int64_t n4 = n >> 2;
   const float4* a4 = reinterpret_cast<const float4*>(a);
@@ -76,14 +78,14 @@ int grid_for(int64_t n, int per_thread) {
 
 extern "C" int gb_mse_const(const float* pred, float target, int64_t n, float* loss, float* grad, void* stream) {
   GB_CHECK(pred && loss && n > 0, "gb_mse_const: bad arguments");
-  mse_const_kernel<<<grid_for(n, 4), 256, 0, (cudaStream_t)stream>>>(pred, target, n, 1.f / (float)n, loss, grad);
+  gb_klaunch(mse_const_kernel, grid_for(n, 4), 256, 0, (cudaStream_t)stream, pred, target, n, 1.f / (float)n, loss, grad);
   GB_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int gb_l1(const float* a, const float* b, int64_t n, float* loss, float* grad_a, void* stream) {
   GB_CHECK(a && b && loss && n > 0, "gb_l1: bad arguments");
-  l1_kernel<<<grid_for(n, 16), 256, 0, (cudaStream_t)stream>>>(a, b, n, 1.f / (float)n, loss, grad_a);
+  gb_klaunch(l1_kernel, grid_for(n, 16), 256, 0, (cudaStream_t)stream, a, b, n, 1.f / (float)n, loss, grad_a);
   GB_LAUNCH_CHECK();
   return 0;
 }

@@ -26,12 +26,14 @@ __device__ __forceinline__ void pack_class(const gb_pack_params& p, int cls, int
 // one launch for every convolution of a network: the table lives in device memory (built once per network, the
 // parameter / packed-buffer addresses never change), blockIdx.y selects the entry
 __global__ void pack_multi_kernel(const gb_pack_params* __restrict__ table) {
+  gb_pdl_enter();
   const gb_pack_params& p = table[blockIdx.y];
   for (int cls = 0; cls < p.nclass; ++cls)
     pack_class(p, cls, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 
 __global__ void unpack_multi_kernel(const __grid_constant__ gb_unpack_batch b) {
+  gb_pdl_enter();
   const gb_unpack_item& it = b.item[blockIdx.y];
   const int64_t total = (int64_t)it.rows * it.chans * it.ntaps;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -46,11 +48,13 @@ __global__ void unpack_multi_kernel(const __grid_constant__ gb_unpack_batch b) {
 }
 
 __global__ void pack_kernel(const __grid_constant__ gb_pack_params p) {
+  gb_pdl_enter();
   pack_class(p, blockIdx.y, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 
 __global__ void unpack_kernel(const float* __restrict__ dw, float* __restrict__ dst, int64_t dsr, int64_t dsc,
                               int64_t dst_t, int rows, int chans, int chans_pad, int ntaps, int kpad) {
+  gb_pdl_enter();
   const int64_t total = (int64_t)rows * chans * ntaps;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     // iterate in destination order (PyTorch layout is usually (r, c, t) contiguous) for coalesced writes
@@ -64,6 +68,7 @@ __global__ void unpack_kernel(const float* __restrict__ dw, float* __restrict__ 
 
 // per-channel sums of a channels-last bf16 view. Block = 256 threads; thread = (pixel slot, 8-channel group).
 __global__ void colsum_kernel(gb_view x, float* __restrict__ out, int pix_per_block) {
+  gb_pdl_enter();
   extern __shared__ float red[];  // [slots][C]
   const int C8 = x.C >> 3;
   const int slots = blockDim.x / C8;
@@ -114,7 +119,7 @@ extern "C" int gb_pack_weights(const gb_pack_params* pp, void* stream) {
   int blocks = (int)((mx + 255) / 256);
   if (blocks > 2048) blocks = 2048;
   if (blocks < 1) blocks = 1;
-  pack_kernel<<<dim3(blocks, p.nclass), 256, 0, (cudaStream_t)stream>>>(p);
+  gb_klaunch(pack_kernel, dim3(blocks, p.nclass), 256, 0, (cudaStream_t)stream, p);
   GB_LAUNCH_CHECK();
   return 0;
 }
@@ -124,7 +129,7 @@ extern "C" int gb_pack_weights_multi(const gb_pack_params* table_dev, int count,
   int blocks = (int)((max_elems + 1023) / 1024);
   if (blocks > 592) blocks = 592;
   if (blocks < 1) blocks = 1;
-  pack_multi_kernel<<<dim3(blocks, count), 256, 0, (cudaStream_t)stream>>>(table_dev);
+  gb_klaunch(pack_multi_kernel, dim3(blocks, count), 256, 0, (cudaStream_t)stream, table_dev);
   GB_LAUNCH_CHECK();
   return 0;
 }
@@ -141,7 +146,7 @@ extern "C" int gb_unpack_wgrad_multi(const gb_unpack_batch* b, void* stream) {
   int blocks = (int)((mx + 1023) / 1024);
   if (blocks > 592) blocks = 592;
   if (blocks < 1) blocks = 1;
-  unpack_multi_kernel<<<dim3(blocks, b->count), 256, 0, (cudaStream_t)stream>>>(*b);
+  gb_klaunch(unpack_multi_kernel, dim3(blocks, b->count), 256, 0, (cudaStream_t)stream, *b);
   GB_LAUNCH_CHECK();
   return 0;
 }
@@ -153,7 +158,7 @@ extern "C" int gb_unpack_wgrad(const float* dw, float* dst, int64_t dsr, int64_t
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4096) blocks = 4096;
   if (blocks < 1) blocks = 1;
-  unpack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dw, dst, dsr, dsc, dst_t, rows, chans, chans_pad, ntaps, kpad);
+  gb_klaunch(unpack_kernel, blocks, 256, 0, (cudaStream_t)stream, dw, dst, dsr, dsc, dst_t, rows, chans, chans_pad, ntaps, kpad);
   GB_LAUNCH_CHECK();
   return 0;
 }
@@ -172,7 +177,7 @@ extern "C" int gb_colsum(const gb_view* x, float* out, void* stream) {
   if (blocks > 148 * 8) blocks = 148 * 8;
   const int ppb = (int)((P + blocks - 1) / blocks);
   blocks = (P + ppb - 1) / ppb;
-  colsum_kernel<<<(int)blocks, threads, sizeof(float) * slots * x->C, st>>>(*x, out, ppb);
+  gb_klaunch(colsum_kernel, (int)blocks, threads, sizeof(float) * slots * x->C, st, *x, out, ppb);
   GB_LAUNCH_CHECK();
   return 0;
 }

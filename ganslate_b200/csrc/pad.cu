@@ -14,6 +14,7 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 
 // dst[n, z, y, x, :] = src[n, clamp(z - pz), clamp(y - py), clamp(x - px), :]
 __global__ void __launch_bounds__(256) replicate_pad_fwd_kernel(gb_view src, gb_view dst, int pz, int py, int px) {
+  gb_pdl_enter();
   const int C8 = dst.C >> 3;
   const int64_t total = (int64_t)dst.N * dst.D * dst.H * dst.W * C8;
   const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(src.ptr);
@@ -41,6 +42,7 @@ __device__ __forceinline__ void readers(int i, int n, int p, int& lo, int& hi) {
 
 // dsrc[n, z, y, x, :] += sum over padded positions (zz, yy, xx) that clamp onto (z, y, x) of ddst[n, zz, yy, xx, :]
 __global__ void __launch_bounds__(256) replicate_pad_bwd_kernel(gb_view ddst, gb_view dsrc, int pz, int py, int px) {
+  gb_pdl_enter();
   const int C4 = dsrc.C >> 2;
   const int64_t total = (int64_t)dsrc.N * dsrc.D * dsrc.H * dsrc.W * C4;
   const float* g = reinterpret_cast<const float*>(ddst.ptr);
@@ -96,7 +98,7 @@ extern "C" int gb_replicate_pad_fwd(const gb_view* src, const gb_view* dst, int 
   GB_CHECK(vec_ok(*src, 2) && vec_ok(*dst, 2), "gb_replicate_pad_fwd: views must be 16-byte aligned");
   const int64_t total = (int64_t)dst->N * dst->D * dst->H * dst->W * (dst->C / 8);
   if (total == 0) return 0;
-  replicate_pad_fwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(*src, *dst, pz, py, px);
+  gb_klaunch(replicate_pad_fwd_kernel, grid_for(total), 256, 0, (cudaStream_t)stream, *src, *dst, pz, py, px);
   GB_LAUNCH_CHECK();
   return 0;
 }
@@ -110,7 +112,7 @@ extern "C" int gb_replicate_pad_bwd(const gb_view* ddst, const gb_view* dsrc, in
   GB_CHECK(vec_ok(*dsrc, 4) && vec_ok(*ddst, 4), "gb_replicate_pad_bwd: views must be 16-byte aligned");
   const int64_t total = (int64_t)dsrc->N * dsrc->D * dsrc->H * dsrc->W * (dsrc->C / 4);
   if (total == 0) return 0;
-  replicate_pad_bwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(*ddst, *dsrc, pz, py, px);
+  gb_klaunch(replicate_pad_bwd_kernel, grid_for(total), 256, 0, (cudaStream_t)stream, *ddst, *dsrc, pz, py, px);
   GB_LAUNCH_CHECK();
   return 0;
 }

@@ -22,6 +22,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // grid = B*P rows, block = 256 threads. probs: [B*P][P+1] softmax of the logits (saved for backward).
 __global__ void patchnce_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, int P, int D, float inv_T,
                                     float* __restrict__ loss, float* __restrict__ probs) {
+  gb_pdl_enter();
   extern __shared__ float sh[];  // q row [D] | logits [P+1] | scratch [64]
   float* qs = sh;
   float* lg = sh + D;
@@ -72,6 +73,7 @@ __global__ void patchnce_fwd_kernel(const float* __restrict__ q, const float* __
 // dq_r = dloss_r / T * ( (p0 - 1) k_r + sum_{j != i} p_{1+j} k_(b,j) )
 __global__ void patchnce_bwd_kernel(const float* __restrict__ k, const float* __restrict__ probs,
                                     const float* __restrict__ dloss, int P, int D, float inv_T, float* __restrict__ dq) {
+  gb_pdl_enter();
   extern __shared__ float sh[];  // coefficients [P+1]
   const int r = blockIdx.x;
   const int b = r / P, i = r - b * P;
@@ -99,7 +101,7 @@ extern "C" int gb_patchnce_fwd(const float* q, const float* k, int B, int P, int
   GB_CHECK(B > 0 && P > 0 && D > 0 && D % 4 == 0 && T > 0.f, "gb_patchnce_fwd: bad sizes B=%d P=%d D=%d", B, P, D);
   const size_t smem = sizeof(float) * (D + P + 1 + 64);
   GB_CHECK(smem <= 48 * 1024, "gb_patchnce_fwd: P + D too large");
-  patchnce_fwd_kernel<<<B * P, 256, smem, (cudaStream_t)stream>>>(q, k, P, D, 1.f / T, loss, probs);
+  gb_klaunch(patchnce_fwd_kernel, B * P, 256, smem, (cudaStream_t)stream, q, k, P, D, 1.f / T, loss, probs);
   GB_LAUNCH_CHECK();
   return 0;
 }
@@ -110,7 +112,7 @@ extern "C" int gb_patchnce_bwd(const float* k, const float* probs, const float* 
   GB_CHECK(B > 0 && P > 0 && D > 0 && T > 0.f, "gb_patchnce_bwd: bad sizes");
   const size_t smem = sizeof(float) * (P + 1);
   GB_CHECK(smem <= 48 * 1024, "gb_patchnce_bwd: P too large");
-  patchnce_bwd_kernel<<<B * P, 256, smem, (cudaStream_t)stream>>>(k, probs, dloss, P, D, 1.f / T, dq);
+  gb_klaunch(patchnce_bwd_kernel, B * P, 256, smem, (cudaStream_t)stream, k, probs, dloss, P, D, 1.f / T, dq);
   GB_LAUNCH_CHECK();
   return 0;
 }

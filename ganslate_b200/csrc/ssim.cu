@@ -54,6 +54,7 @@ struct Moments {
 };
 
 __global__ void __launch_bounds__(256) ssim_fwd_kernel(const __grid_constant__ SsimArgs a, float* __restrict__ loss) {
+  gb_pdl_enter();
   __shared__ float sx[FT][FT + 1], sy[FT][FT + 1];
   __shared__ float hs[5][FT][TS + 1];
   __shared__ float red[8];
@@ -115,6 +116,7 @@ constexpr int BWD_SMEM_FLOATS = 2 * BT * SXP + 3 * FT * GP + 5 * BT * HP;
 
 __global__ void __launch_bounds__(256) ssim_bwd_kernel(const __grid_constant__ SsimArgs a, const float* __restrict__ dloss,
                                                        float* __restrict__ grad) {
+  gb_pdl_enter();
   extern __shared__ float sm[];
   float* sx = sm;
   float* sy = sx + BT * SXP;
@@ -252,7 +254,7 @@ extern "C" int gb_ssim_fwd(const float* x, const float* y, int planes, int H, in
   GB_CHECK(loss != nullptr, "gb_ssim_fwd: null loss");
   dim3 grid(gb_cdiv(W - R, TS), gb_cdiv(H - R, TS), planes);
   GB_CHECK(grid.z <= 65535, "gb_ssim_fwd: too many planes (%d)", planes);
-  ssim_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, loss);
+  gb_klaunch(ssim_fwd_kernel, grid, 256, 0, (cudaStream_t)stream, a, loss);
   GB_LAUNCH_CHECK();
   return 0;
 }
@@ -270,7 +272,7 @@ extern "C" int gb_ssim_bwd(const float* x, const float* y, int planes, int H, in
   }
   dim3 grid(gb_cdiv(W, TS), gb_cdiv(H, TS), planes);
   GB_CHECK(grid.z <= 65535, "gb_ssim_bwd: too many planes (%d)", planes);
-  ssim_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a, dloss, grad_x);
+  gb_klaunch(ssim_bwd_kernel, grid, 256, smem, (cudaStream_t)stream, a, dloss, grad_x);
   GB_LAUNCH_CHECK();
   return 0;
 }

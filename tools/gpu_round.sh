@@ -29,6 +29,11 @@ exp)
   tail -c 1500 $out/bench_cg2_b$B.json; tail -3 $out/bench_cg2_b$B.err
   GB_KNOBS=16=2 timeout 900 python bench.py --batch $B --no-cpu-baseline > $out/bench_persist_b$B.json 2> $out/bench_persist_b$B.err
   tail -c 1500 $out/bench_persist_b$B.json; tail -3 $out/bench_persist_b$B.err
+  # programmatic dependent launch (knob 20): the whole parity suite under it, then a bench line
+  GB_KNOBS=20=1 timeout 1500 python -m pytest tests -m gpu -q -x > $out/pytest_pdl.log 2>&1; echo "pytest exit $?" >> $out/pytest_pdl.log
+  tail -4 $out/pytest_pdl.log
+  GB_KNOBS=20=1 timeout 900 python bench.py --batch $B --no-cpu-baseline --no-roofline > $out/bench_pdl_b$B.json 2> $out/bench_pdl_b$B.err
+  tail -c 600 $out/bench_pdl_b$B.json; tail -3 $out/bench_pdl_b$B.err
   GB_BWD_WINDOW=1 timeout 900 python bench.py --batch $B --no-cpu-baseline --no-roofline > $out/bench_bwdwin_b$B.json 2> $out/bench_bwdwin_b$B.err
   tail -c 600 $out/bench_bwdwin_b$B.json; tail -3 $out/bench_bwdwin_b$B.err ;;
 shapes)
