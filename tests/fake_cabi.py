@@ -394,6 +394,34 @@ class FakeLib:
             _flat(grad, n, torch.float32).copy_(torch.sign(d) / n)
         return 0
 
+    def _nce_logits(self, q, k, B, P, D, T):
+        qq, kk = _flat(q, B * P * D, torch.float32).view(B, P, D), _flat(k, B * P * D, torch.float32).view(B, P, D)
+        l_pos = (qq * kk).sum(-1, keepdim=True)                       # own key
+        l_neg = torch.bmm(qq, kk.transpose(1, 2))                      # keys of the same image
+        l_neg = l_neg.masked_fill(torch.eye(P, dtype=torch.bool)[None], -10.0)
+        return torch.cat([l_pos, l_neg], dim=2).view(B * P, P + 1) / T, kk
+
+    def gb_patchnce_fwd(self, q, k, B, P, D, T, loss, probs, stream):
+        self._count("gb_patchnce_fwd")
+        lg, _ = self._nce_logits(q, k, B, P, D, T)
+        lse = torch.logsumexp(lg, dim=1)
+        _flat(loss, B * P, torch.float32).copy_(lse - lg[:, 0])
+        if probs:
+            _flat(probs, B * P * (P + 1), torch.float32).view(B * P, P + 1).copy_(torch.exp(lg - lse[:, None]))
+        return 0
+
+    def gb_patchnce_bwd(self, k, probs, dloss, B, P, D, T, dq, stream):
+        self._count("gb_patchnce_bwd")
+        kk = _flat(k, B * P * D, torch.float32).view(B, P, D)
+        c = _flat(probs, B * P * (P + 1), torch.float32).view(B, P, P + 1).clone()
+        c[:, :, 0] -= 1.0
+        idx = torch.arange(P)
+        c[:, idx, 1 + idx] = 0.0                                       # the masked diagonal is a constant
+        c = c * (_flat(dloss, B * P, torch.float32).view(B, P, 1) / T)
+        out = c[:, :, :1] * kk + torch.bmm(c[:, :, 1:], kk)
+        _flat(dq, B * P * D, torch.float32).view(B, P, D).copy_(out)
+        return 0
+
     # ------------------------------------------------------------------ layout / padding
     def gb_nchw_to_cl(self, src, Cc, dst, pre, dst_fp32, stream):
         self._count("gb_nchw_to_cl")

@@ -280,3 +280,73 @@ def test_bringup_cases_through_fake_backend(monkeypatch):
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     bad = [i for i, case in enumerate(gpu_bringup.CASES[:-1]) if not case()]  # (the last entry is the loss kernels)
     assert not bad, bad
+
+
+def _cpu_recipe(monkeypatch):
+    fake_cabi.install(monkeypatch)
+    from ganslate_b200.nn.gans import base
+    monkeypatch.setattr(base.BaseGAN, "_specify_device", lambda self: torch.device("cpu"))
+
+
+def test_pix2pix_iteration_host_logic(monkeypatch):
+    """Pix2PixConditionalGAN (paired recipe, discriminator on cat[A, B]) with the Resnet2D generator, one iteration
+    through the fake backend against OraclePix2Pix (same cases as tests/test_pix2pix_gpu.py, smaller)."""
+    _cpu_recipe(monkeypatch)
+    from ganslate_b200.presets import pix2pix_resnet2d
+    from ganslate_b200.utils.builders import build_gan
+    from oracle import torch_oracle as O
+    oracle = O.OraclePix2Pix(lambda_pix2pix=30.0, n_residual_blocks=1, n_layers=3, seed=0)
+    torch.manual_seed(0)
+    ours = build_gan(pix2pix_resnet2d(batch_size=1, n_layers=3, n_residual_blocks=1))
+    for name in ("G", "D"):
+        for (k1, p1), (k2, p2) in zip(oracle.networks[name].state_dict().items(), ours.networks[name].state_dict().items()):
+            assert k1 == k2 and torch.equal(p1, p2), (name, k1)
+    a, b = O.synthetic_batch(1, 3, 64, seed=1, width=96)
+    lo = oracle.optimize_parameters(a, b, step_optimizers=False)
+    for o in ours.optimizers.values():
+        monkeypatch.setattr(o, "step", lambda *args, **kw: None)
+    ours.set_input({"A": a, "B": b})
+    ours.optimize_parameters()
+    for k, v in lo.items():
+        assert abs(float(ours.losses[k].detach()) - v) <= 2e-2 * abs(v), (k, v, float(ours.losses[k].detach()))
+    assert rel_l2(ours.visuals["fake_B"], oracle.visuals["fake_B"]) < 3e-2
+    for name in ("G", "D"):
+        po, pg = dict(oracle.networks[name].named_parameters()), dict(ours.networks[name].named_parameters())
+        for k in po:
+            if k.endswith("weight") and po[k].dim() > 1:
+                assert cosine(pg[k].grad, po[k].grad) > 0.9, (name, k, cosine(pg[k].grad, po[k].grad))
+
+
+def test_cut_iteration_host_logic(monkeypatch):
+    """CUT (PatchNCE over encoder feature taps + FeaturePatchMLP), one iteration through the fake backend against
+    OracleCUT with injected patch ids (same protocol as tests/test_cut_gpu.py, smaller)."""
+    _cpu_recipe(monkeypatch)
+    from ganslate_b200.presets import cut_resnet2d
+    from ganslate_b200.utils.builders import build_gan
+    from oracle import torch_oracle as O
+    torch.manual_seed(0)
+    oracle = O.OracleCUT(n_residual_blocks=9, num_patches=64, seed=0)
+    torch.manual_seed(0)
+    conf = cut_resnet2d()
+    conf.train.gan.optimizer.num_patches = 64
+    ours = build_gan(conf)
+    for name in ("G", "D", "mlp"):
+        for (k1, p1), (k2, p2) in zip(oracle.networks[name].state_dict().items(), ours.networks[name].state_dict().items()):
+            assert k1 == k2 and torch.equal(p1, p2), (name, k1)
+    a, b = O.synthetic_batch(1, 3, 64, seed=1)
+    g = torch.Generator().manual_seed(5)
+    sizes = [70 * 70, 32 * 32, 16 * 16, 16 * 16, 16 * 16]
+    ids = [torch.randperm(s, generator=g)[:64] for s in sizes]
+    lo, _ = oracle.optimize_parameters(a, b, patch_ids=ids, step_optimizers=False)
+    ours.fixed_patch_ids = ids
+    for o in ours.optimizers.values():
+        monkeypatch.setattr(o, "step", lambda *args, **kw: None)
+    ours.set_input({"A": a, "B": b})
+    ours.optimize_parameters()
+    for k, v in lo.items():
+        assert abs(float(ours.losses[k].detach()) - v) <= 2e-2 * abs(v), (k, v, float(ours.losses[k].detach()))
+    for name in ("mlp", "G", "D"):
+        po, pg = dict(oracle.networks[name].named_parameters()), dict(ours.networks[name].named_parameters())
+        for k in po:
+            if k.endswith("weight") and po[k].grad is not None and po[k].dim() > 1:
+                assert cosine(pg[k].grad, po[k].grad) > 0.85, (name, k, cosine(pg[k].grad, po[k].grad))
