@@ -22,3 +22,19 @@ extern "C" int gb_debug_knob(int knob, int value) {
   return old;
 }
 extern "C" unsigned long long gb_launch_count(void) { return g_gb_launches; }
+
+extern "C" int gb_workspace_bytes(int op, const void* params, int64_t* bytes) {
+  GB_CHECK(params != nullptr && bytes != nullptr, "gb_workspace_bytes: null pointer");
+  if (op == GB_WS_WGRAD) {
+    const gb_wgrad_params* p = static_cast<const gb_wgrad_params*>(params);
+    GB_CHECK(p->rows >= 1 && p->kpad >= 64 && p->kpad % 64 == 0, "gb_workspace_bytes: bad rows / kpad %d / %d", p->rows, p->kpad);
+    *bytes = (int64_t)((p->rows + 127) / 128 * 128) * p->kpad * 4;
+    return 0;
+  }
+  if (op == GB_WS_IN_BWD) {
+    const gb_view* x = static_cast<const gb_view*>(params);
+    *bytes = ((int64_t)x->N * x->C * 2 + 4) * 4;
+    return 0;
+  }
+  GB_CHECK(false, "gb_workspace_bytes: unknown operator %d", op);
+}

@@ -275,6 +275,16 @@ const char* gb_last_error(void);
 unsigned long long gb_launch_count(void);
 /* 1 when the driver accepts the overlapping-stride tensor map that pixel-window views need (gb_conv_params.in_c_valid) */
 int gb_tma_window_supported(void);
+/* Size of the caller-allocated, zero-initialised FP32 workspace of an operator (the library owns no device memory):
+ *   GB_WS_WGRAD  (params = const gb_wgrad_params*): the `dw` matrix gb_conv_wgrad accumulates into,
+ *                rows rounded up to 128 x kpad floats;
+ *   GB_WS_IN_BWD (params = const gb_view* x): gb_in_bwd_params.bstats, N x C x 2 floats + 4 words for the grid barrier
+ *                of the single-launch path.
+ * Host arithmetic only. */
+#define GB_WS_WGRAD 0
+#define GB_WS_IN_BWD 1
+int gb_workspace_bytes(int op, const void* params, int64_t* bytes);
+
 /* Host-only replay of the work decomposition of the persistent convolution kernels (csrc/igemm_cg2.cu; mode 1 = CTA
  * pair, 2 = single CTA): see the definition.  Used by the CPU tests; touches no device. */
 int gb_debug_cg2_plan(const gb_conv_params* p, int mode, int32_t* info, int32_t* out, int64_t out_ints);

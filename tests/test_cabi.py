@@ -66,3 +66,21 @@ def test_product_path_does_not_import_oracle():
             if f.endswith(".py"):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_workspace_sizes_match_what_the_host_allocates():
+    """gb_workspace_bytes (host arithmetic) against the buffers ops.py allocates for gb_conv_wgrad / gb_in_bwd."""
+    import ctypes as C
+    from ganslate_b200 import _cabi, ops
+    lib = _cabi.lib()
+    n = C.c_int64(0)
+    for cin, cout, k in [(256, 256, (1, 3, 3)), (3, 64, (1, 7, 7)), (64, 3, (1, 7, 7)), (16, 32, (5, 5, 5))]:
+        op = ops.ConvOp(cin, cout, k, (1, 1, 1), (0, 0, 0))
+        p = _cabi.WgradParams()
+        p.rows, p.kpad = op.wg_rows, op.wg_kpad
+        assert lib.gb_workspace_bytes(0, C.byref(p), C.byref(n)) == 0
+        assert n.value == op.wg_rows_pad * op.wg_kpad * 4
+    v = _cabi.View()
+    v.N, v.C = 8, 256
+    assert lib.gb_workspace_bytes(1, C.byref(v), C.byref(n)) == 0 and n.value == (8 * 256 * 2 + 4) * 4
+    assert lib.gb_workspace_bytes(7, C.byref(v), C.byref(n)) != 0 and b"unknown operator" in lib.gb_last_error()
