@@ -350,3 +350,88 @@ def test_cut_iteration_host_logic(monkeypatch):
         for k in po:
             if k.endswith("weight") and po[k].grad is not None and po[k].dim() > 1:
                 assert cosine(pg[k].grad, po[k].grad) > 0.85, (name, k, cosine(pg[k].grad, po[k].grad))
+
+
+def _random_conv_cases(n, seed):
+    import random
+    rng = random.Random(seed)
+    cases = []
+    while len(cases) < n:
+        dims = rng.choice([2, 2, 3])
+        transposed = rng.random() < 0.35
+        k = tuple(rng.choice([1, 2, 3, 4, 5]) for _ in range(dims))
+        s = tuple(rng.choice([1, 1, 2, 3]) for _ in range(dims))
+        p = tuple(rng.randint(0, max(0, kk - 1) // 1 if kk > 1 else 0) for kk in k)
+        p = tuple(min(pp, kk - 1) for pp, kk in zip(p, k))
+        op = tuple(rng.randint(0, ss - 1) for ss in s) if transposed else (0,) * dims
+        cin, cout = rng.choice([1, 3, 8, 12, 16, 40, 64]), rng.choice([1, 3, 8, 24, 64, 72])
+        ext = tuple(rng.randint(max(kk, 2), 9) for kk in k)
+        ntaps = 1
+        for kk in k:
+            ntaps *= kk
+        if ntaps > 64 or (transposed and any(pp > kk - 1 for pp, kk in zip(p, k))):
+            continue
+        cases.append(dict(dims=dims, transposed=transposed, k=k, s=s, p=p, op=op, cin=cin, cout=cout, ext=ext,
+                          N=rng.choice([1, 2]), bias=rng.random() < 0.7))
+    return cases
+
+
+@pytest.mark.parametrize("case", _random_conv_cases(36, 2024), ids=lambda c: "{}{}d k{} s{} p{} {}->{}".format(
+    "T" if c["transposed"] else "", c["dims"], "x".join(map(str, c["k"])), "x".join(map(str, c["s"])),
+    "x".join(map(str, c["p"])), c["cin"], c["cout"]))
+def test_random_convolutions_through_the_host_path(monkeypatch, case):
+    """Randomly drawn (transposed) convolutions, 2-D and 3-D, odd channel counts, strides up to 3, output padding:
+    forward, data gradient, weight and bias gradient of layers.Conv* through ConvOp's class / tap specs, packing and
+    weight-gradient plans (fake backend) against torch -- the geometry cases no network of the suite happens to use."""
+    fake_cabi.install(monkeypatch)
+    from ganslate_b200.nn import layers
+    from parity_util import max_rel
+    torch.manual_seed(7)
+    c = case
+    if c["transposed"]:
+        cls = layers.ConvTranspose3d if c["dims"] == 3 else layers.ConvTranspose2d
+        conv = cls(c["cin"], c["cout"], c["k"], stride=c["s"], padding=c["p"], output_padding=c["op"], bias=c["bias"])
+        fn = torch.nn.functional.conv_transpose3d if c["dims"] == 3 else torch.nn.functional.conv_transpose2d
+        kw = dict(stride=c["s"], padding=c["p"], output_padding=c["op"])
+    else:
+        cls = layers.Conv3d if c["dims"] == 3 else layers.Conv2d
+        conv = cls(c["cin"], c["cout"], c["k"], stride=c["s"], padding=c["p"], bias=c["bias"])
+        fn = torch.nn.functional.conv3d if c["dims"] == 3 else torch.nn.functional.conv2d
+        kw = dict(stride=c["s"], padding=c["p"])
+    with torch.no_grad():
+        conv.weight.copy_((torch.randn_like(conv.weight) * 0.1).to(torch.bfloat16).float())
+        if c["bias"]:
+            conv.bias.copy_(torch.randn_like(conv.bias) * 0.1)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = torch.nn.Sequential(conv)
+
+        def forward(self, t):
+            return layers.run_network(self, list(self.model), t)
+
+    nclass = 1
+    for ss in c["s"]:
+        nclass *= ss
+    if nclass > 8:  # documented limit (GB_MAX_CLASSES parity classes): refused loudly, never computed wrongly
+        with pytest.raises(ValueError, match="parity classes"):
+            conv.conv_op()
+        return
+    x = torch.randn((c["N"], c["cin"]) + c["ext"]).to(torch.bfloat16).float().requires_grad_(True)
+    xr = x.detach().clone().requires_grad_(True)
+    wr = conv.weight.detach().clone().requires_grad_(True)
+    br = conv.bias.detach().clone().requires_grad_(True) if c["bias"] else None
+    yr = fn(xr, wr, br, **kw)
+    if min(yr.shape) == 0:
+        pytest.skip("empty output")
+    y = Net()(x)
+    assert y.shape == yr.shape
+    g = torch.randn_like(yr).to(torch.bfloat16).float()
+    y.backward(g)
+    yr.backward(g)
+    assert max_rel(y, yr) < 1e-2, max_rel(y, yr)
+    assert max_rel(x.grad, xr.grad) < 1e-2, max_rel(x.grad, xr.grad)
+    assert max_rel(conv.weight.grad, wr.grad) < 1e-2, max_rel(conv.weight.grad, wr.grad)
+    if c["bias"]:
+        assert max_rel(conv.bias.grad, br.grad) < 1e-2
