@@ -1,7 +1,7 @@
 """Randomly drawn (transposed) convolutions on the GPU against torch on the same bf16-valued inputs -- the GPU twin of
 tests/test_host_networks_cpu.py::test_random_convolutions_through_the_host_path (same generator, other seed).
 The kernels are the verified ones; the SHAPES are new (odd channel counts, strides up to 3, anisotropic 3-D kernels,
-output padding), so the group is collected last (`unverified`)."""
+output padding): `experimental` until its first GPU visit (GB_EXPERIMENTAL=1; tools/gpu_round.sh ... exp runs it)."""
 import os
 import sys
 
@@ -11,7 +11,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from test_host_networks_cpu import _random_conv_cases  # noqa: E402
 
-pytestmark = [pytest.mark.gpu, pytest.mark.unverified]
+pytestmark = [pytest.mark.gpu, pytest.mark.experimental]
 
 
 @pytest.mark.parametrize("case", _random_conv_cases(24, 31337), ids=lambda c: "{}{}d k{} s{} p{} {}->{}".format(

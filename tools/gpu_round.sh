@@ -21,7 +21,7 @@ bench)
 exp)
   # opt-in kernel paths that have not run on a B200 yet (cta_group::2 convolution, gradient-side pixel windows):
   # every case in its own process under a timeout (tests/test_cg2_gpu.py), then the A/B microbench and a bench line
-  GB_EXPERIMENTAL=1 timeout 1500 python -m pytest tests/test_cg2_gpu.py tests/test_strided_window_gpu.py -m gpu -q \
+  GB_EXPERIMENTAL=1 timeout 1500 python -m pytest tests/test_cg2_gpu.py tests/test_strided_window_gpu.py tests/test_random_conv_gpu.py -m gpu -q \
      > $out/pytest_exp.log 2>&1; echo "pytest exit $?" >> $out/pytest_exp.log; tail -15 $out/pytest_exp.log
   timeout 600 python tools/conv_microbench.py 8 --layers 0,1,2,3,4,5 --variants 2,7,8,9,10 --what fwd,dgrad > $out/microbench_cg2.txt 2>&1
   tail -40 $out/microbench_cg2.txt
