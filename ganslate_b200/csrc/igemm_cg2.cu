@@ -74,6 +74,8 @@ struct Cg2Geom {
   int nb;                                // column blocks
   int nitems;                            // nclass * nb * npairs
   int nstages;
+  int wd_mclk;                           // watchdog limit in millions of clocks (0 = off)
+  int* wd;                               // host-mapped report buffer (8 ints) or NULL
 };
 
 // ---------------------------------------------------------------- cluster / cta_group::2 primitives
@@ -108,6 +110,46 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
       "r"(parity)
       : "memory");
 }
+// Bring-up watchdog (knob 21 = limit in millions of clocks, 0 = off): a wait that exceeds the limit records WHO waited for
+// WHAT in a host-mapped buffer (readable after the context died: gb_debug_cg2_watchdog) and traps, so a protocol or
+// hardware-semantics mistake costs one failed launch with a diagnosis instead of a hang until the caller's timeout.
+struct WaitTag {
+  int role;   // 0 producer/empty, 1 mma/tempty, 2 mma/full, 3 epilogue/tfull
+  int index;  // stage or accumulator
+  int item;
+};
+template <bool CLUSTER>
+__device__ __forceinline__ void wait_wd(uint32_t bar, uint32_t parity, unsigned long long limit, int* wd, uint32_t rank,
+                                        const WaitTag& tag) {
+  if (limit == 0ull) {
+    if constexpr (CLUSTER) mbar_wait_cluster(bar, parity);
+    else mbar_wait(bar, parity);
+    return;
+  }
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    if constexpr (CLUSTER) {
+      asm volatile(
+          "{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } else {
+      asm volatile(
+          "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+    if (done) return;
+    if ((unsigned long long)(clock64() - t0) > limit) {
+      if (wd != nullptr && atomicCAS(wd, 0, 1) == 0) {  // first reporter wins
+        wd[1] = tag.role; wd[2] = tag.index; wd[3] = tag.item; wd[4] = (int)parity; wd[5] = (int)rank;
+        wd[6] = (int)blockIdx.x; wd[7] = (int)threadIdx.x;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+
 // TMA loads of a CTA pair: destination = this CTA's shared memory, completion = `cluster_bar` (a shared::cluster
 // address, the leader's full barrier)
 __device__ __forceinline__ void tma2_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1,
@@ -224,6 +266,7 @@ __device__ __forceinline__ void cg_body(const gb_conv_params& p, const CUtensorM
   const uint32_t cluster_id = PAIR ? blockIdx.x >> 1 : blockIdx.x;
   const uint32_t nclusters = PAIR ? gridDim.x >> 1 : gridDim.x;
   const int chunks = p.in.C >> 6;
+  const unsigned long long wd_limit = (unsigned long long)g.wd_mclk * 1000000ull;
 
   const uint32_t full_bar = smem_u32(bars);
   const uint32_t empty_bar = smem_u32(bars + MAXS);
@@ -267,7 +310,7 @@ __device__ __forceinline__ void cg_body(const gb_conv_params& p, const CUtensorM
           const int8_t* tp = taps_s + 4 * (cc.tap_begin + tl);
           const int dz = tp[0], dy = tp[1], dx = tp[2];
           for (int c = 0; c < chunks; ++c) {
-            if (round > 0) mbar_wait(empty_bar + 8 * s, (round - 1) & 1);
+            if (round > 0) wait_wd<false>(empty_bar + 8 * s, (round - 1) & 1, wd_limit, g.wd, rank, WaitTag{0, s, (int)item});
             const uint32_t a_s = base + s * C::STAGE_BYTES;
             const uint32_t b_s = a_s + A_BYTES;
             if (leader) mbar_expect_tx(full_bar + 8 * s, tx_bytes);
@@ -303,13 +346,12 @@ __device__ __forceinline__ void cg_body(const gb_conv_params& p, const CUtensorM
         const int KB = cc.ntaps * chunks;
         const uint32_t a = acc_it & 1u, use = acc_it >> 1;
         if (use > 0) {  // the epilogue warps of both CTAs have drained the previous use of this accumulator
-          if constexpr (PAIR) mbar_wait_cluster(tempty_bar + 8 * a, (use - 1) & 1);
-          else mbar_wait(tempty_bar + 8 * a, (use - 1) & 1);
+          wait_wd<PAIR>(tempty_bar + 8 * a, (use - 1) & 1, wd_limit, g.wd, rank, WaitTag{1, (int)a, (int)item});
           tc_fence_after();
         }
         const uint32_t d_tmem = tmem_base + a * BN;
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(full_bar + 8 * s, round & 1);
+          wait_wd<false>(full_bar + 8 * s, round & 1, wd_limit, g.wd, rank, WaitTag{2, s, (int)item});
           tc_fence_after();
           const uint32_t a_s = base + s * C::STAGE_BYTES;
           const uint32_t b_s = a_s + A_BYTES;
@@ -358,7 +400,7 @@ __device__ __forceinline__ void cg_body(const gb_conv_params& p, const CUtensorM
       if (row_ok)
         ooff = gb_pix_offset(p.out, it.n, it.z0 * p.out_mul[0] + cc.off[0], qy * p.out_mul[1] + cc.off[1],
                              qx * p.out_mul[2] + cc.off[2]);
-      mbar_wait(tfull_bar + 8 * a, use & 1);
+      wait_wd<false>(tfull_bar + 8 * a, use & 1, wd_limit, g.wd, rank, WaitTag{3, (int)a, (int)item});
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(lg * 32) << 16) + a * BN;
       constexpr int CH = 32;
@@ -480,9 +522,30 @@ igemm_persist_kernel(const __grid_constant__ gb_conv_params p, const __grid_cons
   cg_body<BN, false>(p, map_a, map_b, g);
 }
 
+int* g_wd_host = nullptr;   // host-mapped watchdog report (8 ints), allocated on first use
+int* g_wd_dev = nullptr;
+
+void watchdog_setup(Cg2Geom& g) {
+  g.wd_mclk = g_gb_knobs[21] > 0 ? g_gb_knobs[21] : 0;
+  g.wd = nullptr;
+  if (g.wd_mclk == 0) return;
+  if (g_wd_host == nullptr) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&g_wd_host), 8 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_wd_dev), g_wd_host, 0) != cudaSuccess) {
+      cudaGetLastError();
+      g_wd_host = g_wd_dev = nullptr;
+      g.wd_mclk = 0;
+      return;
+    }
+    for (int i = 0; i < 8; ++i) g_wd_host[i] = 0;
+  }
+  g.wd = g_wd_dev;
+}
+
 template <int BN, bool PAIR>
 int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb, Cg2Geom g, cudaStream_t st) {
   using C = CCfg<BN, PAIR>;
+  watchdog_setup(g);
   static bool attr_set = false;
   static int max_groups = 0;  // co-resident clusters (PAIR) or CTAs
   if (!attr_set) {
@@ -581,6 +644,8 @@ static int cg2_geometry(const gb_conv_params& p, bool pair, Cg2Geom* gout, int* 
   g.div_pairs = gb_make_fastdiv((uint32_t)g.npairs);
   g.div_nb = gb_make_fastdiv((uint32_t)g.nb);
   g.nstages = 0;
+  g.wd_mclk = 0;
+  g.wd = nullptr;
   *gout = g;
   *bn_out = bn;
   *kpad_out = kpad;
@@ -615,6 +680,15 @@ int gb_conv_data_cg2(const gb_conv_params& p, cudaStream_t st) {
     }
   }
   return -1;
+}
+
+// The watchdog's report after a trapped launch (knob 21): out[0] = 1 when a wait timed out, then {role (0 producer waits
+// for an empty stage, 1 MMA issuer waits for a drained accumulator, 2 MMA issuer waits for a full stage, 3 epilogue
+// waits for a complete accumulator), stage / accumulator index, item, parity, CTA rank in the pair, blockIdx.x,
+// threadIdx.x}.  Reads host memory only, so it works after the CUDA context has been lost.  Returns out[0].
+extern "C" int gb_debug_cg2_watchdog(int32_t* out) {
+  for (int i = 0; i < 8; ++i) out[i] = g_wd_host ? g_wd_host[i] : 0;
+  return out[0];
 }
 
 // Host replay of the persistent kernels' work decomposition (no device needed): for item i and CTA rank r of the pair

@@ -289,6 +289,10 @@ int gb_workspace_bytes(int op, const void* params, int64_t* bytes);
  * pair, 2 = single CTA): see the definition.  Used by the CPU tests; touches no device. */
 int gb_debug_cg2_plan(const gb_conv_params* p, int mode, int32_t* info, int32_t* out, int64_t out_ints);
 
+/* Report of the persistent kernels' bring-up watchdog (gb_debug_knob(21, limit in millions of clocks)): see the
+ * definition in csrc/igemm_cg2.cu.  out: 8 ints. */
+int gb_debug_cg2_watchdog(int32_t* out);
+
 /* debug knobs for bring-up (e.g. descriptor variants); returns previous value */
 int gb_debug_knob(int knob, int value);
 

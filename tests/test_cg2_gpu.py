@@ -35,7 +35,7 @@ CASES = [
 ]
 
 DRIVER = r"""
-import json, sys
+import ctypes, json, sys, traceback
 sys.path.insert(0, {here!r})
 import torch
 import gpu_bringup
@@ -43,15 +43,26 @@ from ganslate_b200 import _cabi
 lib = _cabi.lib()
 kind, kw, mode = json.loads(sys.argv[1])
 lib.gb_debug_knob(16, mode)
+lib.gb_debug_knob(21, 400)   # watchdog: a wait longer than 4e8 clocks (~0.2 s) reports who waited for what and traps
 lib.gb_debug_knob(19, 0)
 lib.gb_debug_knob(15, 0)
-if kind == "conv":
-    ok = gpu_bringup.conv_case(**kw)
-elif kind == "resblock":
-    ok = gpu_bringup.resblock_case()
-else:
-    ok = gpu_bringup.in_case(kw["name"], kw["C"], kw["H"], kw["W"], kw["N"], kw["act"], kw["reflect_next"])
-torch.cuda.synchronize()
+ROLES = ["producer waits for an empty stage", "MMA issuer waits for a drained accumulator",
+         "MMA issuer waits for a full stage", "epilogue waits for a complete accumulator"]
+try:
+    if kind == "conv":
+        ok = gpu_bringup.conv_case(**kw)
+    elif kind == "resblock":
+        ok = gpu_bringup.resblock_case()
+    else:
+        ok = gpu_bringup.in_case(kw["name"], kw["C"], kw["H"], kw["W"], kw["N"], kw["act"], kw["reflect_next"])
+    torch.cuda.synchronize()
+except Exception:
+    traceback.print_exc()
+    wd = (ctypes.c_int32 * 8)()
+    if lib.gb_debug_cg2_watchdog(wd):
+        print("WATCHDOG: %s; stage/accumulator %d, item %d, parity %d, CTA rank %d, block %d, thread %d"
+              % (ROLES[wd[1]] if 0 <= wd[1] < 4 else wd[1], wd[2], wd[3], wd[4], wd[5], wd[6], wd[7]))
+    sys.exit(3)
 print("RESULT", json.dumps(dict(ok=bool(ok), last_data_path=lib.gb_debug_knob(15, 0), cg2_launches=lib.gb_debug_knob(19, 0))))
 """
 
