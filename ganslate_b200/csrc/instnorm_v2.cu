@@ -1,0 +1,170 @@
+// Second-generation fused InstanceNorm backward, opt-in (gb_debug_knob(22, v)): v = 1 -> 4 pixels (192 bytes) in
+// flight per thread (3 with a residual gradient), v = 2 -> 2 pixels; two 256-thread blocks per SM (128 registers
+// each, no spills) either way.  0 (default) keeps the
+// first-generation kernels of instnorm_fast.cu, which are the ones measured in profiles/.  Knob 6 = 1 forces the
+// two-launch form (no grid barrier), as for the first generation.
+//
+// The per-thread streaming body lives in instnorm_v2_core.h (compiled for the host as well: the CPU test-suite runs
+// it thread by thread against torch, tests/test_in_bwd_v2_emul.py).  This file adds what only exists on the device:
+// the block reduction of the partial sums, the atomics, the grid barrier of the single-launch form and the launch
+// geometry (one co-resident wave, blocks of an image own equal pixel ranges).
+#include "gb_common.cuh"
+#include "instnorm_v2_core.h"
+
+namespace {
+
+using gbv2::Geom;
+using gbv2::THREADS;
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// partial sums of the block's threads -> one atomic per channel (and moment); red: [slots][C][2] floats
+template <int PASS>
+__device__ __forceinline__ void block_reduce(const gb_in_bwd_params& p, int n, const float (&acc1)[8], const float (&acc2)[8],
+                                             float* red, bool active) {
+  const int C = p.x.C;
+  const int C8 = C >> 3;
+  const int slots = THREADS / C8;
+  const int cgp = threadIdx.x % C8, slot = threadIdx.x / C8;
+  if (!active) return;  // uniform over the block
+  if (slot < slots) {
+    float4* dst = reinterpret_cast<float4*>(red + ((size_t)slot * C + cgp * 8) * 2);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) dst[h] = make_float4(acc1[2 * h], acc2[2 * h], acc1[2 * h + 1], acc2[2 * h + 1]);
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += THREADS) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < slots; ++k) {
+      const float2 t = *reinterpret_cast<const float2*>(red + ((size_t)k * C + ch) * 2);
+      s1 += t.x;
+      s2 += t.y;
+    }
+    if (PASS == 0) {
+      atomicAdd(p.bstats + ((int64_t)n * C + ch) * 2 + 0, s1);
+      atomicAdd(p.bstats + ((int64_t)n * C + ch) * 2 + 1, s2);
+    } else {
+      atomicAdd(p.dbias + ch, s1);
+    }
+  }
+}
+
+// PASS 0 / 1: the two passes as separate launches, PASS 2: both in one launch around a grid barrier
+template <bool RES, int U, int MINB, int PASS>
+__global__ void __launch_bounds__(THREADS, MINB)
+in_bwd_v2_kernel(const __grid_constant__ gb_in_bwd_params p, const __grid_constant__ Geom g, float neg_slope) {
+  gb_pdl_enter();
+  extern __shared__ float red[];
+  const int n = blockIdx.y;
+  float acc1[8], acc2[8];
+  if (PASS == 0 || PASS == 2) {
+    gbv2::stream_pass<RES, U, 0>(p, g, neg_slope, threadIdx.x, blockIdx.x, n, acc1, acc2);
+    block_reduce<0>(p, n, acc1, acc2, red, true);
+  }
+  if (PASS == 2) {
+    unsigned int* counter = reinterpret_cast<unsigned int*>(p.bstats + (int64_t)p.x.N * p.x.C * 2);
+    grid_barrier(counter, (unsigned int)g.total_blocks);  // also orders the reuse of `red`
+  }
+  if (PASS == 1 || PASS == 2) {
+    gbv2::stream_pass<RES, U, 1>(p, g, neg_slope, threadIdx.x, blockIdx.x, n, acc1, acc2);
+    block_reduce<1>(p, n, acc1, acc2, red, p.dbias != nullptr);
+  }
+}
+
+bool row_addressable(const gb_view& v) { return v.D == 1 || (v.pad == 0 && v.sz == (int64_t)v.H * v.sy); }
+bool small_offsets(const gb_view& v) {
+  return ((int64_t)v.D * v.H + 2 * v.pad) * v.sy + (int64_t)(v.W + 2 * v.pad) * v.sx < (1ll << 31) &&
+         (int64_t)v.D * v.H < (1 << 20) && v.W < (1 << 20);
+}
+bool aligned(const gb_view& v, int elem_bytes, int vec) {
+  return ((uintptr_t)v.ptr % (elem_bytes * vec)) == 0 && v.sx % vec == 0 && v.sy % vec == 0 && v.sz % vec == 0 &&
+         v.sn % vec == 0;
+}
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <bool RES, int U, int MINB>
+int launch(const gb_in_bwd_params& p, float neg_slope, cudaStream_t st) {
+  const size_t smem = sizeof(float) * 2 * gbv2::slots_of(p.x.C) * p.x.C;
+  static int occ = -1;  // co-resident blocks per SM of the single-launch kernel (per instantiation)
+  static size_t occ_smem = 0;
+  if (occ < 0 || occ_smem != smem) {
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, in_bwd_v2_kernel<RES, U, MINB, 2>, THREADS, smem) != cudaSuccess) o = 0;
+    cudaGetLastError();
+    occ = o;
+    occ_smem = smem;
+  }
+  bool fits = false;
+  const Geom g = gbv2::plan(p.x.N, p.x.D, p.x.H, p.x.W, p.x.C, num_sms() * (occ > 0 ? occ : MINB), &fits);
+  const dim3 grid(g.nblocks, p.x.N);
+  if (occ > 0 && fits && g_gb_knobs[6] == 0) {
+    float ns = neg_slope;
+    Geom gg = g;
+    void* args[] = {(void*)&p, (void*)&gg, (void*)&ns};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)in_bwd_v2_kernel<RES, U, MINB, 2>, grid, dim3(THREADS), args,
+                                                smem, st);
+    if (e == cudaSuccess) {
+      __atomic_fetch_add(&g_gb_launches, 1ull, __ATOMIC_RELAXED);
+      return 0;
+    }
+    cudaGetLastError();  // cooperative launch not possible here: two launches
+  }
+  gb_klaunch(in_bwd_v2_kernel<RES, U, MINB, 0>, grid, THREADS, smem, st, p, g, neg_slope);
+  GB_LAUNCH_CHECK();
+  gb_klaunch(in_bwd_v2_kernel<RES, U, MINB, 1>, grid, THREADS, smem, st, p, g, neg_slope);
+  GB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+// -1: not covered (caller falls back to the first-generation / general kernels), 0: launched, > 0: error
+int gb_in_bwd_fast_v2(const gb_in_bwd_params& p, cudaStream_t st) {
+  const int variant = g_gb_knobs[22];
+  if (variant != 1 && variant != 2) return -1;
+  float ns;
+  switch (p.act) {
+    case GB_ACT_NONE: ns = 1.f; break;
+    case GB_ACT_RELU: ns = 0.f; break;
+    case GB_ACT_LEAKY: ns = p.act_slope; break;
+    default: return -1;
+  }
+  if (p.stats == nullptr || p.bstats == nullptr) return -1;
+  if (p.dy_a.ptr != nullptr || p.dy_b.ptr == nullptr) return -1;
+  if (p.res_before_act || p.dx_fp32_acc || p.dprelu != nullptr) return -1;
+  if (p.out_scale != 0.f && p.out_scale != 1.f) return -1;
+  const bool has_res = p.dy_sum.ptr != nullptr;
+  if (has_res && !p.dy_sum_acc) return -1;
+  const gb_view& x = p.x;
+  if (x.C % 8 != 0 || x.C / 8 > THREADS || (int64_t)x.D * x.H * x.W >= (1ll << 31)) return -1;
+  if (!aligned(x, 2, 8) || !aligned(p.dx, 2, 8) || !aligned(p.dy_b, 4, 4) || (has_res && !aligned(p.dy_sum, 4, 4))) return -1;
+  if ((uintptr_t)p.stats % 16 != 0 || (uintptr_t)p.bstats % 16 != 0) return -1;
+  if (!row_addressable(x) || !row_addressable(p.dx) || !row_addressable(p.dy_b) || (has_res && !row_addressable(p.dy_sum)))
+    return -1;
+  if (!small_offsets(x) || !small_offsets(p.dx) || !small_offsets(p.dy_b) || (has_res && !small_offsets(p.dy_sum))) return -1;
+  if (p.dy_b.pad > 0 && (p.dy_b.D != 1 || p.dy_b.H <= 2 * p.dy_b.pad + 1 || p.dy_b.W <= 2 * p.dy_b.pad + 1)) return -1;
+  // (the residual form holds two more fp32 vectors per pixel: one pixel less in flight keeps it free of spills)
+  if (variant == 1) return has_res ? launch<true, 3, 2>(p, ns, st) : launch<false, 4, 2>(p, ns, st);
+  return has_res ? launch<true, 2, 2>(p, ns, st) : launch<false, 2, 2>(p, ns, st);
+}

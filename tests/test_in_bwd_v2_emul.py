@@ -1,0 +1,127 @@
+"""Host run of the second-generation fused InstanceNorm backward (ganslate_b200/csrc/instnorm_v2_core.h, opt-in on
+the GPU through gb_debug_knob(22, 1 | 2)): the per-thread body that nvcc compiles into `in_bwd_v2_kernel` is compiled
+with g++ (tests/emul/in_bwd_v2_emul.cpp) and every thread of every block is run on the CPU, against the pointer-level
+restatement of gb_in_bwd (tests/fake_cabi.py, which follows include/ganslate_b200.h).  Covers what can go wrong
+without a GPU in the loop: row-segment walking with ragged block ranges, the reflection fold (rows, columns,
+corners; border 1 and 2), channel groups that do not fill the block, 3-D row-linear views, interior views of
+bordered buffers, the residual-gradient accumulation happening exactly once, every dx element written exactly once,
+the FMA-form algebra and the bf16 packing.  The block reduction, atomics and grid barrier are device-only and are
+what the GPU tests of knob 22 (tests/test_ops_gpu.py cases under GB_KNOBS=22=1) add."""
+import ctypes as C
+import os
+import subprocess
+
+import pytest
+import torch
+
+from ganslate_b200 import _cabi
+from ganslate_b200._cabi import ACT_LEAKY, ACT_NONE, ACT_RELU
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    out = tmp_path_factory.mktemp("emul") / "in_bwd_v2_emul.so"
+    cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", os.path.join(HERE, "emul", "in_bwd_v2_emul.cpp"),
+           "-o", str(out)]
+    res = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT)
+    assert res.returncode == 0, res.stderr
+    lib = C.CDLL(str(out))
+    lib.in_bwd_v2_emulate.argtypes = [C.POINTER(_cabi.InBwdParams), C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int)]
+    lib.in_bwd_v2_emulate.restype = C.c_int
+    return lib
+
+
+def _view(t, pad, N, D, H, W, Cc, c0=0):
+    """gb_view of the interior of a (N, D, H + 2 pad, W + 2 pad, Ctot) channels-last tensor, channels c0 .. c0 + Cc."""
+    v = _cabi.View()
+    sn, sz, sy, sx, _ = t.stride()
+    v.ptr = t.data_ptr() + (pad * sy + pad * sx + c0) * t.element_size()
+    v.sn, v.sz, v.sy, v.sx = sn, sz, sy, sx
+    v.N, v.D, v.H, v.W, v.C, v.pad = N, D, H, W, Cc, pad
+    return v
+
+
+CASES = [
+    # N, D, H,  W,  C,   gpad, act,       res,   cap, U, x_border, c_slice
+    (2, 1, 12, 10, 64, 1, ACT_RELU, False, 7, 4, 0, False),     # ragged block ranges, 8 slots... of 32
+    (1, 1, 9, 7, 8, 0, ACT_LEAKY, False, 5, 2, 0, False),       # one channel group: 256 pixels per step > image
+    (3, 1, 8, 8, 256, 1, ACT_NONE, True, 10, 3, 1, False),      # resblock tail: residual gradient, x inside a border
+    (2, 3, 5, 6, 16, 0, ACT_RELU, False, 9, 4, 0, False),       # 3-D, row-linear
+    (1, 1, 11, 13, 24, 1, ACT_LEAKY, False, 4, 4, 0, False),    # 3 channel groups: 85 slots, one idle thread
+    (2, 1, 8, 9, 32, 2, ACT_RELU, True, 6, 2, 2, False),        # border 2: two mirrored rows / columns per side
+    (1, 1, 16, 16, 64, 1, ACT_RELU, False, 1, 4, 0, False),     # a single block per image walks 16 whole rows
+    (2, 1, 6, 20, 40, 1, ACT_NONE, False, 64, 3, 0, True),      # more blocks than rows; channel slice of a wider buffer
+    (5, 1, 7, 7, 16, 1, ACT_RELU, False, 3, 4, 0, False),       # more images than co-resident blocks (two-launch form)
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"N{c[0]}D{c[1]}H{c[2]}W{c[3]}C{c[4]}p{c[5]}a{c[6]}r{int(c[7])}cap{c[8]}U{c[9]}" for c in CASES])
+def test_v2_thread_body_matches_the_abi_restatement(emul, case):
+    import fake_cabi
+    N, D, H, W, Cc, gpad, act, res, cap, U, xb, c_slice = case
+    torch.manual_seed(hash(case) % 1000)
+    Ctot = Cc + 16 if c_slice else Cc
+    c0 = 8 if c_slice else 0
+    x_t = (torch.randn(N, D, H + 2 * xb, W + 2 * xb, Ctot) * 1.5 + 0.7).to(torch.bfloat16)
+    dy_t = torch.randn(N, D, H + 2 * gpad, W + 2 * gpad, Ctot)
+    xv = _view(x_t, xb, N, D, H, W, Cc, c0)
+    xi = x_t[:, :, xb:xb + H, xb:xb + W, c0:c0 + Cc].float()
+    stats = torch.stack([xi.sum(dim=(1, 2, 3)), (xi * xi).sum(dim=(1, 2, 3))], dim=-1).contiguous()
+    slope = 0.2 if act == ACT_LEAKY else 0.0
+    ns = {ACT_NONE: 1.0, ACT_RELU: 0.0, ACT_LEAKY: slope}[act]
+    sum0 = torch.randn(N, D, H, W, Ctot) if res else None
+
+    def params(dx_t, dysum_t, bstats, dbias):
+        p = _cabi.InBwdParams()
+        p.x = xv
+        p.dy_b = _view(dy_t, gpad, N, D, H, W, Cc, c0)
+        p.dx = _view(dx_t, xb, N, D, H, W, Cc, c0)
+        if dysum_t is not None:
+            p.dy_sum = _view(dysum_t, 0, N, D, H, W, Cc, c0)
+            p.dy_sum_acc = 1
+        p.stats, p.bstats, p.dbias = stats.data_ptr(), bstats.data_ptr(), dbias.data_ptr()
+        p.eps, p.act, p.act_slope = 1e-5, act, slope
+        return p
+
+    outs = []
+    for which in ("ref", "v2"):
+        dx_t = torch.full(x_t.shape, float("nan")).to(torch.bfloat16)
+        dysum_t = sum0.clone() if res else None
+        bstats = torch.zeros(N * Cc * 2 + 4)
+        dbias = torch.zeros(Cc)
+        p = params(dx_t, dysum_t, bstats, dbias)
+        if which == "ref":
+            assert fake_cabi.FakeLib().gb_in_bwd(p, None) == 0
+        else:
+            grid = (C.c_int * 2)()
+            assert emul.in_bwd_v2_emulate(C.byref(p), cap, U, ns, grid) == 0
+            assert grid[0] >= 1 and grid[0] * grid[1] >= D * H * W
+        outs.append((dx_t, dysum_t, dbias))
+    (dx_r, sum_r, db_r), (dx_v, sum_v, db_v) = outs
+    # dx: interior written everywhere (no NaN sentinel left), nothing outside the interior / channel slice touched
+    inner = dx_v[:, :, xb:xb + H, xb:xb + W, c0:c0 + Cc].float()
+    assert not torch.isnan(inner).any()
+    mask = torch.ones_like(dx_v, dtype=torch.bool)
+    mask[:, :, xb:xb + H, xb:xb + W, c0:c0 + Cc] = False
+    assert torch.isnan(dx_v.float()[mask]).all()
+    ref = dx_r[:, :, xb:xb + H, xb:xb + W, c0:c0 + Cc].float()
+    # same algebra in a different association: agreement to bf16 rounding of values of the gradient's scale
+    scale = ref.abs().max().item()
+    assert (inner - ref).abs().max().item() <= 2.0 ** -7 * scale
+    assert (inner - ref).abs().mean().item() <= 2.0 ** -10 * scale
+    assert torch.allclose(db_v, db_r, rtol=1e-3, atol=1e-3 * max(1.0, db_r.abs().max().item()))
+    if res:
+        assert torch.allclose(sum_v, sum_r, rtol=1e-5, atol=1e-5)
+        assert torch.equal(sum_v[..., :c0], sum0[..., :c0]) and torch.equal(sum_v[..., c0 + Cc:], sum0[..., c0 + Cc:])
+
+
+def test_v2_plan_covers_every_pixel_once():
+    """gbv2::plan restated: equal pixel ranges per block, the last one ragged, never more blocks than `cap`."""
+    for N, P, cap in [(8, 4096, 296), (8, 65536, 296), (1, 900, 296), (3, 17, 296), (300, 64, 296), (2, 1, 10)]:
+        nb = max(cap // N, 1)
+        ppb = max((P + nb - 1) // nb, 1)
+        nblocks = (P + ppb - 1) // ppb
+        assert nblocks <= nb and (nblocks - 1) * ppb < P <= nblocks * ppb

@@ -1,0 +1,88 @@
+"""Second-generation fused InstanceNorm backward (ganslate_b200/csrc/instnorm_v2.cu, gb_debug_knob(22, 1 | 2)) on the
+GPU.  Written after round 1's GPU budget was spent: `experimental` (GB_EXPERIMENTAL=1 runs it; tools/gpu_round.sh
+<tag> in2).  Its per-thread body already runs on the CPU (tests/test_in_bwd_v2_emul.py); what this adds is the block
+reduction, the atomics and the grid barrier of the single-launch form -- a barrier that is mis-counted spins
+forever, so every variant runs in its own process under a timeout.
+
+Each case calls gb_in_bwd three times on the same inputs: general kernel (knob 7 = 1), first-generation fast kernel
+(default) and the variant under test, and compares dx / bias gradient / residual gradient (tolerance: bf16 rounding
+of values of the gradient's scale -- the algebra is associated differently) and checks the variant was really served
+by the new kernel (knob 23 counts its launches)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+pytestmark = [pytest.mark.gpu, pytest.mark.experimental]
+
+DRIVER = r"""
+import ctypes as C, json, sys
+sys.path.insert(0, {here!r})
+import torch
+from ganslate_b200 import _cabi, ops
+from ganslate_b200._cabi import ACT_LEAKY, ACT_NONE, ACT_RELU
+lib = _cabi.lib()
+variant, two_launch = json.loads(sys.argv[1])
+dev = "cuda"
+# N, D, H, W, C, gradient border, act, residual gradient
+CASES = [(2, 1, 12, 10, 64, 1, ACT_RELU, False), (1, 1, 9, 7, 8, 0, ACT_LEAKY, False), (3, 1, 8, 8, 256, 1, ACT_NONE, True),
+         (2, 3, 5, 6, 16, 0, ACT_RELU, False), (1, 1, 11, 13, 24, 1, ACT_LEAKY, False), (2, 1, 8, 9, 32, 2, ACT_RELU, True),
+         (8, 1, 64, 64, 256, 1, ACT_RELU, False), (8, 1, 64, 64, 256, 1, ACT_NONE, True), (4, 1, 128, 128, 64, 3, ACT_RELU, False),
+         (2, 1, 31, 31, 512, 0, ACT_LEAKY, False), (600, 1, 7, 7, 16, 1, ACT_RELU, False)]
+bad = 0
+for (N, D, H, W, Cc, gp, act, res) in CASES:
+    torch.manual_seed(N * 1000 + Cc)
+    x = (torch.randn(N, D, H, W, Cc, device=dev) * 1.5 + 0.7).to(torch.bfloat16)
+    dy = torch.randn(N, D, H + 2 * gp, W + 2 * gp, Cc, device=dev)
+    xf = x.float()
+    stats = torch.stack([xf.sum(dim=(1, 2, 3)), (xf * xf).sum(dim=(1, 2, 3))], dim=-1).contiguous()
+    sum0 = torch.randn(N, D, H, W, Cc, device=dev)
+    outs = []
+    for knobs in ({{7: 1, 22: 0, 6: 0}}, {{7: 0, 22: 0, 6: 0}}, {{7: 0, 22: variant, 6: two_launch}}):
+        for k, v in knobs.items():
+            lib.gb_debug_knob(k, v)
+        lib.gb_debug_knob(23, 0)
+        dx = torch.full_like(x, float("nan"))
+        dsum = sum0.clone()
+        bstats = torch.zeros(N * Cc * 2 + 4, device=dev)
+        dbias = torch.zeros(Cc, device=dev)
+        p = _cabi.InBwdParams()
+        p.x, p.dy_b, p.dx = ops.make_view(x), ops.make_view(dy, gp), ops.make_view(dx)
+        if res:
+            p.dy_sum, p.dy_sum_acc = ops.make_view(dsum), 1
+        p.stats, p.bstats, p.dbias = stats.data_ptr(), bstats.data_ptr(), dbias.data_ptr()
+        p.eps, p.act, p.act_slope = 1e-5, act, 0.2 if act == ACT_LEAKY else 0.0
+        _cabi.check(lib.gb_in_bwd(C.byref(p), torch.cuda.current_stream().cuda_stream), "gb_in_bwd")
+        torch.cuda.synchronize()
+        outs.append((dx.float(), dbias, dsum, lib.gb_debug_knob(23, 0)))
+    ref, gen1, gen2 = outs
+    scale = ref[0].abs().max().item()
+    e1 = (gen1[0] - ref[0]).abs().max().item() / scale
+    e2 = (gen2[0] - ref[0]).abs().max().item() / scale
+    ok = (not torch.isnan(gen2[0]).any().item()) and e2 <= 2.0 ** -7
+    ok = ok and torch.allclose(gen2[1], ref[1], rtol=2e-3, atol=2e-3 * max(1.0, ref[1].abs().max().item()))
+    ok = ok and (not res or torch.allclose(gen2[2], ref[2], rtol=1e-5, atol=1e-5))
+    ok = ok and gen2[3] == 1 and gen1[3] == 0
+    print(("OK  " if ok else "FAIL"), (N, D, H, W, Cc, gp, act, res), "rel dx err gen1 %.2e gen2 %.2e served %d" % (e1, e2, gen2[3]))
+    bad += 0 if ok else 1
+print("RESULT", json.dumps(dict(bad=bad)))
+sys.exit(1 if bad else 0)
+"""
+
+
+@pytest.mark.parametrize("variant,two_launch", [(1, 0), (1, 1), (2, 0), (2, 1)],
+                         ids=["U4-fused", "U4-two-launch", "U2-fused", "U2-two-launch"])
+def test_in_bwd_v2_variant(variant, two_launch):
+    code = DRIVER.format(here=HERE)
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(HERE) + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    try:
+        res = subprocess.run([sys.executable, "-c", code, json.dumps([variant, two_launch])], capture_output=True,
+                             text=True, timeout=300, env=env)
+    except subprocess.TimeoutExpired as e:
+        out = e.stdout.decode(errors="replace") if isinstance(e.stdout, bytes) else (e.stdout or "")
+        pytest.fail(f"hung (killed after 300 s), output so far:\n{out[-3000:]}")
+    print(res.stdout[-4000:])
+    assert res.returncode == 0, res.stdout[-4000:] + "\n" + res.stderr[-3000:]

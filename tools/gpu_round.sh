@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box visit: parity tests, bench line, ncu launch list, ncu --set full of the top kernels.
-# Usage (under gpurun): [BATCH=8] bash tools/gpu_round.sh <tag> [tests|smoke|bench|benchref|exp|shapes|launches|full ...]
+# Usage (under gpurun): [BATCH=8] bash tools/gpu_round.sh <tag> [tests|smoke|bench|benchref|exp|in2|shapes|launches|full ...]
 tag=${1:-r01}; shift
 what=${*:-tests bench launches full}
 B=${BATCH:-1}
@@ -36,6 +36,16 @@ exp)
   tail -c 600 $out/bench_pdl_b$B.json; tail -3 $out/bench_pdl_b$B.err
   GB_BWD_WINDOW=1 timeout 900 python bench.py --batch $B --no-cpu-baseline --no-roofline > $out/bench_bwdwin_b$B.json 2> $out/bench_bwdwin_b$B.err
   tail -c 600 $out/bench_bwdwin_b$B.json; tail -3 $out/bench_bwdwin_b$B.err ;;
+in2)
+  # second-generation InstanceNorm backward (knob 22; tests/test_in_bwd_v2_emul.py already runs its thread body on the CPU):
+  # parity per variant in its own process, A/B table, then the whole suite and a bench line with it as the default
+  GB_EXPERIMENTAL=1 timeout 1500 python -m pytest tests/test_in_bwd_v2_gpu.py -m gpu -q -s > $out/pytest_in2.log 2>&1; echo "pytest exit $?" >> $out/pytest_in2.log
+  grep -E "OK  |FAIL|passed|failed|exit" $out/pytest_in2.log | tail -60
+  timeout 900 python tools/in_microbench.py 8 > $out/in_microbench_b8.txt 2>&1; tail -45 $out/in_microbench_b8.txt
+  GB_KNOBS=22=1 timeout 1500 python -m pytest tests -m gpu -q -x > $out/pytest_in2_suite.log 2>&1; echo "pytest exit $?" >> $out/pytest_in2_suite.log
+  tail -4 $out/pytest_in2_suite.log
+  GB_KNOBS=22=1 timeout 900 python bench.py --batch $B --no-cpu-baseline --no-roofline > $out/bench_in2_b$B.json 2> $out/bench_in2_b$B.err
+  tail -c 600 $out/bench_in2_b$B.json; tail -3 $out/bench_in2_b$B.err ;;
 shapes)
   # throughput of every BASELINE.json configuration (one short bench line each; not the headline number)
   for wl in pix2pix_resnet pix2pix_unet cut cyclegan3d revgan3d revgan_piresnet3d; do
