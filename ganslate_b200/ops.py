@@ -764,7 +764,10 @@ def norm_act_backward(xv: View, stats, dyv: View, dxv: View, norm, act, slope, e
     else:
         p.act = ACT_NONE  # only the residual branch needs the (folded) gradient
     n = xv.N * xv.D * xv.H * xv.W * xv.C
-    nbytes = n * ((6 if norm else 0) + 8 + (4 if dresv is not None else 0))
+    # ALGORITHMIC bytes (read dy, read the saved x, write dx; dy is carried in fp32 here): 4 + 2 + 2 per
+    # element, + 8 for the read-modify-write of a fused residual gradient.  The two-pass kernels read dy and x twice
+    # (the second time mostly from L2), which is traffic, not work, and is not counted.
+    nbytes = n * (8 + (8 if dresv is not None else 0))
     _call("in_bwd", nbytes, "byte", "gb_in_bwd", lib.gb_in_bwd, C.byref(p), _stream())
 
 
