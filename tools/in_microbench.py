@@ -6,7 +6,8 @@ into profiles/ by hand).  Every variant's dx / bias gradient / residual gradient
 
     python tools/in_microbench.py [batch]
 
-variants: knob 22 = 0 first generation (instnorm_fast.cu, 4 channels per thread), 1 / 2 second generation
+variants: knob 24 = 1 / 2 on-chip cluster kernel (instnorm_v3.cu: every byte read once; 2 = half-size stash, two CTAs
+per SM; maps of more than 8192 pixels are declined and fall through to the knob-22 choice); knob 22 = 0 first generation (instnorm_fast.cu, 4 channels per thread), 1 / 2 second generation
 (instnorm_v2.cu, 8 channels per thread, 4 / 2 pixels in flight); knob 6 = 1 two launches instead of one launch around
 a grid barrier.  GB/s = algorithmic bytes (fp32 gradient read once + bf16 x read once + bf16 dx written, + 8 B per
 element read-modify-write of the residual gradient) / time; the kernels read the gradient and x twice, so the
@@ -24,7 +25,8 @@ from ganslate_b200._cabi import ACT_LEAKY, ACT_NONE, ACT_RELU
 
 dev = "cuda"
 VARIANTS = [("gen1 fused", {22: 0, 6: 0}), ("gen1 2-launch", {22: 0, 6: 1}), ("gen2 U4 fused", {22: 1, 6: 0}),
-            ("gen2 U4 2-launch", {22: 1, 6: 1}), ("gen2 U2 fused", {22: 2, 6: 0})]
+            ("gen2 U4 2-launch", {22: 1, 6: 1}), ("gen2 U2 fused", {22: 2, 6: 0}), ("on-chip cluster", {24: 1}),
+            ("on-chip half stash", {24: 2})]
 
 
 def make(name, N, Cc, H, W, act, gpad, res):
@@ -88,17 +90,20 @@ def main():
         make("D l4       512ch 31x31 leaky", B, 512, 31, 31, ACT_LEAKY, 0, False),
     ]
     print(f"device: {torch.cuda.get_device_name(0)}  batch {B}")
-    print(f"{'layer':44s} {'variant':18s} {'cold us':>9s} {'GB/s':>8s} {'hot us':>9s} {'GB/s':>8s}  {'max|ddx|':>9s} served-by-gen2")
+    print(f"{'layer':44s} {'variant':18s} {'cold us':>9s} {'GB/s':>8s} {'hot us':>9s} {'GB/s':>8s}  {'max|ddx|':>9s} served-by")
     for L in layers:
         ref = None
         for vname, knobs in VARIANTS:
+            for k in (22, 6, 24):
+                lib.gb_debug_knob(k, 0)
             for k, v in knobs.items():
                 lib.gb_debug_knob(k, v)
             lib.gb_debug_knob(23, 0)
+            lib.gb_debug_knob(25, 0)
             out = fresh(L)
             launch(L, out)
             torch.cuda.synchronize()
-            served = lib.gb_debug_knob(23, 0)
+            served = f"gen2={lib.gb_debug_knob(23, 0)} onchip={lib.gb_debug_knob(25, 0)}"
             got = (out["dx"].float(), out["dbias"].clone(), out["dsum"].clone() if L["res"] else None)
             if ref is None:
                 ref, err = got, 0.0
@@ -111,7 +116,7 @@ def main():
                     print(f"MISMATCH {L['name']} {vname}: rel dx err {err:.3e}")
             tc, th = time_us(L, True), time_us(L, False)
             print(f"{L['name']:44s} {vname:18s} {tc:9.1f} {L['bytes'] / tc / 1e3:8.0f} {th:9.1f} {L['bytes'] / th / 1e3:8.0f}  {err:9.2e} {served}")
-        for k in (22, 6):
+        for k in (22, 6, 24):
             lib.gb_debug_knob(k, 0)
 
 
