@@ -25,7 +25,8 @@ class FlatGradSync:
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
-        self.stream = torch.cuda.Stream(device=device)
+        # NCCL runs on a side stream; with CPU tensors (gloo: the host-logic tests) everything is synchronous
+        self.stream = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
         self.world = dist.get_world_size()
         self._pending = False
 
@@ -37,17 +38,22 @@ class FlatGradSync:
         """Call after backward on the compute stream: pack and start the all-reduce on the side stream."""
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
         torch._foreach_copy_(self.views, grads)
-        self.stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self.stream):
+        if self.stream is None:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             self.flat.mul_(1.0 / self.world)
+        else:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+                self.flat.mul_(1.0 / self.world)
         self._pending = True
 
     def finish(self):
         """Call before the optimizer step: wait for the reduction and write the averaged gradients back."""
         if not self._pending:
             return
-        torch.cuda.current_stream().wait_stream(self.stream)
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
         grads = [p.grad for p in self.params if p.grad is not None]
         views = [v for p, v in zip(self.params, self.views) if p.grad is not None]
         torch._foreach_copy_(grads, views)

@@ -1,5 +1,6 @@
-"""world_size-2 gloo tests of the N>1 host path: process-group helpers and DDP gradient averaging as wired by
-BaseGAN.parallelize_networks (one DDP wrapper per network, broadcast_buffers=False)."""
+"""world_size-2 gloo tests of the N>1 host path: process-group helpers, DDP gradient averaging as wired by
+BaseGAN.parallelize_networks (one DDP wrapper per network, broadcast_buffers=False), and the flat-bucket gradient
+all-reduce that replaces DDP's hooks when the step is replayed as CUDA graphs (utils/grad_sync.py)."""
 import os
 import socket
 
@@ -42,7 +43,31 @@ def _worker(rank, world, port, q):
         gr = torch.Generator().manual_seed(100 + r)
         tot = tot + O.adversarial_lsgan(ref(torch.rand((1, 3, 32, 32), generator=gr)), True)
     (tot / world).backward()
-    q.put((rank, seed, float(red["a"]), float(red["b"]), float((grad - ref.model[0].weight.grad).abs().max())))
+    # flat-bucket sync (the CUDA-graph path's replacement of DDP): rank-0 parameters at start, gradients averaged over
+    # ranks, a parameter shared by two groups counted once, a parameter without gradient reduced as zero
+    from ganslate_b200.utils.grad_sync import FlatGradSync
+    torch.manual_seed(10 + rank)  # different initial weights per rank: broadcast must make them rank 0's
+    net2 = O.init_weights(O.OraclePatchGAN2D(3, 8, 2))
+    params = list(net2.parameters())
+    sync = FlatGradSync(params + params[:2], torch.device("cpu"))
+    sync.broadcast_parameters()
+    torch.manual_seed(10)
+    ref2 = O.init_weights(O.OraclePatchGAN2D(3, 8, 2))
+    bcast_err = max(float((a - b).abs().max()) for a, b in zip(net2.parameters(), ref2.parameters()))
+    O.adversarial_lsgan(net2(x), True).backward()
+    params[-1].grad = None  # e.g. a frozen / unused parameter on this rank
+    sync.finish()           # nothing pending: must be a no-op
+    sync.launch()
+    sync.finish()
+    tot = 0
+    for r in range(world):
+        gr = torch.Generator().manual_seed(100 + r)
+        tot = tot + O.adversarial_lsgan(ref2(torch.rand((1, 3, 32, 32), generator=gr)), True)
+    (tot / world).backward()
+    flat_err = max(float((a.grad - b.grad).abs().max()) for a, b in list(zip(net2.parameters(), ref2.parameters()))[:-1])
+    ok_none = params[-1].grad is None and len(sync.params) == len(params)
+    q.put((rank, seed, float(red["a"]), float(red["b"]), float((grad - ref.model[0].weight.grad).abs().max()), bcast_err,
+           flat_err, ok_none))
     comm.synchronize()
     dist.destroy_process_group()
 
@@ -63,3 +88,5 @@ def test_gloo_world2_helpers_and_ddp_average():
     assert res[0][1] == res[1][1]                      # shared seed agreed by broadcast
     assert res[0][2] == pytest.approx(1.5) and res[0][3] == pytest.approx(2.0)
     assert all(r[4] < 1e-6 for r in res)               # DDP average == single-process mean
+    assert all(r[5] == 0.0 for r in res)               # FlatGradSync: parameters are rank 0's after the broadcast
+    assert all(r[6] < 1e-6 and r[7] for r in res)      # flat-bucket average == single-process mean
