@@ -213,6 +213,10 @@ class BaseGAN(ABC):
             return
         for name in self.networks.keys():
             if torch.distributed.is_initialized():
+                from ganslate_b200 import ops
+                if ops.DIRECT_PARAM_GRAD:
+                    raise RuntimeError("GB_DIRECT_PARAM_GRAD=1 bypasses autograd's gradient hooks, which DistributedDataParallel "
+                                       "relies on: use it with train.cuda_graph (flat-bucket all-reduce) or on one GPU")
                 self.networks[name] = DistributedDataParallel(self.networks[name], device_ids=[self.device],
                                                               output_device=self.device, broadcast_buffers=False)
             elif self.conf[self.conf.mode].cuda and torch.cuda.device_count() > 1 and "WORLD_SIZE" in os.environ:

@@ -180,7 +180,7 @@ class Storage:
 
 class Buf:
     """Channel slice [c0, c0 + cw) of a Storage; `channels` logical channels (cw = channels rounded up to 8)."""
-    __slots__ = ("st", "c0", "cw", "channels", "is_3d", "needs_grad_flag", "want_dbias", "dbias", "stats")
+    __slots__ = ("st", "c0", "cw", "channels", "is_3d", "needs_grad_flag", "want_dbias", "dbias", "stats", "bias_param")
 
     def __init__(self, t, pad, channels, is_3d, raw=False, st=None, c0=0, cw=None):
         self.st = st if st is not None else Storage(t, pad, raw)
@@ -190,6 +190,7 @@ class Buf:
         self.needs_grad_flag = True  # False only for a network input that does not require grad
         self.want_dbias = False      # the producing conv's bias needs a gradient (fused into the consumer's backward)
         self.dbias = None
+        self.bias_param = None       # that bias (direct parameter gradients: ops.DIRECT_PARAM_GRAD)
         self.stats = None            # InstanceNorm statistics written by the producing convolution's epilogue
 
     # -- forward-side accessors
@@ -256,11 +257,37 @@ class Tape:
         self.input_needs_grad = input_needs_grad
         self.param_grads = {}
         self.unpack = ops.UnpackQueue()  # weight-gradient workspaces -> PyTorch layout, one launch per pass
+        self.direct = ops.DIRECT_PARAM_GRAD  # gradients go straight into param.grad (ops.DIRECT_PARAM_GRAD)
+        self._queued = set()             # direct mode: parameters whose first gradient waits in the unpack queue
 
     def needs(self, p):
         return p is not None and self.param_needs_grad.get(id(p), False)
 
+    def grad_target(self, p, numel=None):
+        """Direct mode: the existing `p.grad` a kernel may accumulate into (None: produce a fresh gradient)."""
+        if not self.direct or p is None:
+            return None
+        g = p.grad
+        if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape:
+            return None
+        if numel is not None and g.numel() != numel:
+            return None
+        if id(p) in self._queued:  # its first contribution has not left the queue yet: order the two launches
+            self.unpack.flush()
+            self._queued.clear()
+        return g
+
     def add_param_grad(self, p, g):
+        if self.direct:
+            if p.grad is None:
+                g = g.detach()
+                p.grad = g if (g.shape == p.shape and g.is_contiguous()) else g.reshape(p.shape).contiguous()
+                self._queued.add(id(p))
+            elif g.data_ptr() != p.grad.data_ptr():
+                self.unpack.flush()
+                self._queued.clear()
+                p.grad.add_(g.reshape(p.shape))
+            return  # (same storage: a kernel accumulated into p.grad already)
         k = id(p)
         if k in self.param_grads:
             self.unpack.flush()  # the earlier contribution may still be waiting in the queue
@@ -271,6 +298,7 @@ class Tape:
         for step in reversed(self.steps):
             step()
         self.unpack.flush()
+        self._queued.clear()
 
 
 def _is_norm(m):
@@ -325,6 +353,7 @@ def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0, want_stats=False, 
     out.stats = stats
     weight, bias = m.weight, m.bias
     out.want_dbias = tape is not None and tape.needs(bias)
+    out.bias_param = bias  # direct mode: the InstanceNorm backward adds its bias-gradient sums to bias.grad
     b.st.consumers += 1
 
     def bwd():
@@ -336,14 +365,18 @@ def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0, want_stats=False, 
         out.dbias = None
         if act != ACT_NONE or as_activation:
             if tape.needs(bias):
-                db = ops.zeros((y.shape[-1],), dev)
+                db = tape.grad_target(bias, y.shape[-1])
+                if db is None:
+                    db = ops.zeros((y.shape[-1],), dev)
             g = ops.act_backward(ops.make_view(g), y, act, slope, dbias=db)  # fp32 d_buf -> bf16 d_raw (+ bias grad)
         gv = ops.make_view(g)
         if op.bwd_window and (tape.needs(weight) or b.needs_grad_flag):
             # gradient-side pixel windows (ops.ConvOp.bwd_window): dOut rows with zero pixels on both sides
             gv = torch.nn.functional.pad(g, (0, 0, ops.BWD_BORDER, ops.BWD_BORDER))
         if tape.needs(weight):
-            tape.add_param_grad(weight, op.run_wgrad(b.plain_view(), gv, weight.shape, dev, pending=tape.unpack))
+            tgt = tape.grad_target(weight)
+            tape.add_param_grad(weight, op.run_wgrad(b.plain_view(), gv, weight.shape, dev, pending=tape.unpack,
+                                                     dw_out=tgt, accumulate=tgt is not None))
         if tape.needs(bias):
             tape.add_param_grad(bias, db[:op.cout] if db is not None else ops.colsum(g, op.cout))
         if b.needs_grad_flag:
@@ -411,7 +444,9 @@ def step_norm_act(tape: Tape, x: Buf, norm: bool, act: int, slope: float, out_pa
         dprelu = ops.zeros((x.cw,), dev) if (slopes is not None and tape.needs(slopes)) else None
         if x.raw:
             if x.want_dbias and need_dx:
-                x.dbias = ops.zeros((x.cw,), dev)
+                x.dbias = tape.grad_target(x.bias_param, x.cw)
+                if x.dbias is None:
+                    x.dbias = ops.zeros((x.cw,), dev)
             seeded = x.st.grad  # gradient that arrived through a feature tap on the raw convolution output
             draw = torch.empty_like(x.t)
             ops.norm_act_backward(x.view(), stats, gview, ops.make_view(draw), norm, act, slope, eps, dev,
@@ -423,7 +458,11 @@ def step_norm_act(tape: Tape, x: Buf, norm: bool, act: int, slope: float, out_pa
                 if seeded is not None:
                     draw = draw + seeded
                     if x.dbias is not None:
-                        x.dbias = x.dbias + seeded.float().sum(dim=(0, 1, 2, 3))
+                        bp = x.bias_param
+                        if bp is not None and bp.grad is not None and x.dbias.data_ptr() == bp.grad.data_ptr():
+                            x.dbias.add_(seeded.float().sum(dim=(0, 1, 2, 3)))  # direct mode: x.dbias IS bias.grad
+                        else:
+                            x.dbias = x.dbias + seeded.float().sum(dim=(0, 1, 2, 3))
                 x.st.grad = draw
         else:
             # activation input (copy / add / activation of existing buffers, or an InstanceNorm that is not fed by a

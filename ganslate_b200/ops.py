@@ -70,6 +70,15 @@ def zeros(shape, device):
     return torch.zeros(shape, dtype=torch.float32, device=device)
 
 
+# Opt-in (GB_DIRECT_PARAM_GRAD=1, not yet measured on a B200): the tape writes parameter gradients straight into
+# `param.grad` -- the first contribution of an optimizer step becomes `.grad`, later ones (a generator used twice in
+# one backward, both discriminator passes) are ACCUMULATED BY THE KERNELS (unpack accumulate flag, bias-gradient
+# atomics) instead of being handed to autograd, whose AccumulateGrad then adds them with one ATen kernel per
+# parameter (145 launches per CycleGAN step, profiles/r01p_launches_b8.md).  Autograd's gradient hooks do not fire in
+# this mode, so it is refused under DistributedDataParallel (BaseGAN.parallelize_networks); the CUDA-graph path's
+# flat-bucket all-reduce reads `.grad` directly and is unaffected.
+DIRECT_PARAM_GRAD = os.environ.get("GB_DIRECT_PARAM_GRAD", "0") == "1"
+
 # Optional per-launch timing (bench.py roofline): a list that receives (family, work, unit, event0, event1).
 PROFILE = None
 
@@ -441,11 +450,13 @@ class ConvOp:
         wv.C, wv.W = 64, xv.W - self.kernel[2] + 1
         return wv
 
-    def run_wgrad(self, xv: View, dyv: View, weight_shape, device, pending=None, dw_out=None):
+    def run_wgrad(self, xv: View, dyv: View, weight_shape, device, pending=None, dw_out=None, accumulate=False):
         """fp32 weight gradient in the PyTorch layout of `weight_shape` (xv: plain input view, dyv: bf16 d_raw).
-        dw_out: existing destination (a depth slice `dw[:, :, dz]` of a larger kernel's gradient, SlabConv)."""
+        dw_out: existing destination (a depth slice `dw[:, :, dz]` of a larger kernel's gradient, SlabConv; or
+        `weight.grad` with accumulate=True: dw_out += gradient, DIRECT_PARAM_GRAD)."""
+        assert not accumulate or dw_out is not None
         if self.window or self.bwd_window:
-            return self._run_wgrad_window(xv, dyv, weight_shape, device, pending, dw_out)
+            return self._run_wgrad_window(xv, dyv, weight_shape, device, pending, dw_out, accumulate)
         plan = self.wgrad_plan()
         plain, gathered = (xv, dyv) if plan["plain_is_input"] else (dyv, xv)
         ws = zeros((self.wg_rows_pad, self.wg_kpad), device)
@@ -465,9 +476,16 @@ class ConvOp:
               _cabi.lib().gb_conv_wgrad, C.byref(p), _stream())
         dw = torch.empty(weight_shape, dtype=torch.float32, device=device) if dw_out is None else dw_out
         u = plan["unpack"]
+        if pending is None and accumulate:
+            pending = own = UnpackQueue()
+        else:
+            own = None
         if pending is not None:
             # the workspace -> PyTorch-layout copies of a whole backward pass go out in one launch (UnpackQueue)
-            pending.add(ws, dw, u["dsr"], u["dsc"], u["dst_t"], u["rows"], u["chans"], u["chans_pad"], u["ntaps"], u["kpad"])
+            pending.add(ws, dw, u["dsr"], u["dsc"], u["dst_t"], u["rows"], u["chans"], u["chans_pad"], u["ntaps"], u["kpad"],
+                        accumulate=accumulate)
+            if own is not None:
+                own.flush()
             return dw
         _cabi.check(_cabi.lib().gb_unpack_wgrad(ws.data_ptr(), dw.data_ptr(), u["dsr"], u["dsc"], u["dst_t"], u["rows"],
                                                 u["chans"], u["chans_pad"], u["ntaps"], u["kpad"], _stream()),
@@ -480,7 +498,7 @@ def _at(t: torch.Tensor, off: int) -> torch.Tensor:
     return t.as_strided((1,), (1,), t.storage_offset() + off)
 
 
-def _conv_op_window_wgrad(self, xv, dyv, weight_shape, device, pending, dw_out=None):
+def _conv_op_window_wgrad(self, xv, dyv, weight_shape, device, pending, dw_out=None, accumulate=False):
     """Weight gradient of a pixel-window convolution: dW[r][(dz,dy)*64 + dx*8 + c] = sum_q dOut[q][r] * window[q + (dz,dy)]
     [dx*8 + c]; one unpack item per (dz, dy) K block copies its kw x cin columns into the PyTorch layout."""
     kd, kh, kw = self.kernel
@@ -508,7 +526,7 @@ def _conv_op_window_wgrad(self, xv, dyv, weight_shape, device, pending, dw_out=N
     wsf = ws.view(-1)
     for it in self.window_unpack_items():
         own.add(wsf[it["ws_off"]:], _at(dw, it["dst_off"]), it["dsr"], it["dsc"], it["dst_t"], it["rows"], it["chans"],
-                it["chans_pad"], it["ntaps"], it["kpad"], keep=(ws, dw))
+                it["chans_pad"], it["ntaps"], it["kpad"], accumulate=accumulate, keep=(ws, dw))
     if pending is None:
         own.flush()
     return dw
@@ -597,10 +615,11 @@ class SlabConv:
         for dz, slab in enumerate(self.slabs):
             slab.run_dgrad(dyv, weight[:, :, dz], _shift_z(outv, dz, dyv.D, 4), accumulate=True)
 
-    def run_wgrad(self, xv: View, dyv: View, weight_shape, device, pending=None):
-        dw = torch.empty(weight_shape, dtype=torch.float32, device=device)
+    def run_wgrad(self, xv: View, dyv: View, weight_shape, device, pending=None, dw_out=None, accumulate=False):
+        dw = torch.empty(weight_shape, dtype=torch.float32, device=device) if dw_out is None else dw_out
         for dz, slab in enumerate(self.slabs):
-            slab.run_wgrad(_shift_z(xv, dz, dyv.D, 2), dyv, weight_shape, device, pending, dw_out=dw[:, :, dz])
+            slab.run_wgrad(_shift_z(xv, dz, dyv.D, 2), dyv, weight_shape, device, pending, dw_out=dw[:, :, dz],
+                           accumulate=accumulate)
         return dw
 
 

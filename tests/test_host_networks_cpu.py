@@ -435,3 +435,41 @@ def test_random_convolutions_through_the_host_path(monkeypatch, case):
     assert max_rel(conv.weight.grad, wr.grad) < 1e-2, max_rel(conv.weight.grad, wr.grad)
     if c["bias"]:
         assert max_rel(conv.bias.grad, br.grad) < 1e-2
+
+
+def test_direct_parameter_gradients_equal_autograd_accumulation(monkeypatch):
+    """ops.DIRECT_PARAM_GRAD (opt-in): the tape writes / accumulates parameter gradients in `param.grad` itself
+    (unpack accumulate flag, bias-gradient sums added in place) instead of returning them to autograd.  One whole
+    CycleGAN iteration -- every generator is used twice in backward_G, every discriminator sees a real and a fake batch
+    -- must leave the same gradients in both modes, and no gradient may reach autograd's AccumulateGrad in direct mode."""
+    import random
+    fake_cabi.install(monkeypatch)
+    from ganslate_b200 import ops
+    from ganslate_b200.nn.gans import base
+    from ganslate_b200.presets import cyclegan_resnet2d
+    from ganslate_b200.utils.builders import build_gan
+    from oracle import torch_oracle as O
+    monkeypatch.setattr(base.BaseGAN, "_specify_device", lambda self: torch.device("cpu"))
+    a, b = O.synthetic_batch(1, 3, 64, seed=1)
+    grads, hooks = {}, {}
+    for direct in (False, True):
+        monkeypatch.setattr(ops, "DIRECT_PARAM_GRAD", direct)
+        random.seed(0)
+        torch.manual_seed(0)
+        gan = build_gan(cyclegan_resnet2d(batch_size=1, n_residual_blocks=1))
+        for o in gan.optimizers.values():
+            monkeypatch.setattr(o, "step", lambda *args, **kw: None)
+        fired = []
+        for name, net in gan.networks.items():
+            for k, p in net.named_parameters():
+                p.register_hook(lambda g, key=(name, k): fired.append(key) if g is not None else None)
+        gan.set_input({"A": a, "B": b})
+        gan.optimize_parameters()
+        grads[direct] = {(n, k): p.grad.clone() for n, net in gan.networks.items() for k, p in net.named_parameters()}
+        hooks[direct] = len(fired)
+    assert hooks[False] > 0 and hooks[True] == 0
+    assert grads[False].keys() == grads[True].keys()
+    for key, g in grads[False].items():
+        d = grads[True][key]
+        assert d.shape == g.shape
+        assert torch.allclose(d, g, rtol=1e-5, atol=1e-6 * max(1.0, float(g.abs().max()))), (key, float((d - g).abs().max()))

@@ -35,7 +35,12 @@ exp)
   GB_KNOBS=20=1 timeout 900 python bench.py --batch $B --no-cpu-baseline --no-roofline > $out/bench_pdl_b$B.json 2> $out/bench_pdl_b$B.err
   tail -c 600 $out/bench_pdl_b$B.json; tail -3 $out/bench_pdl_b$B.err
   GB_BWD_WINDOW=1 timeout 900 python bench.py --batch $B --no-cpu-baseline --no-roofline > $out/bench_bwdwin_b$B.json 2> $out/bench_bwdwin_b$B.err
-  tail -c 600 $out/bench_bwdwin_b$B.json; tail -3 $out/bench_bwdwin_b$B.err ;;
+  tail -c 600 $out/bench_bwdwin_b$B.json; tail -3 $out/bench_bwdwin_b$B.err
+  # parameter gradients accumulated by the kernels into param.grad (no AccumulateGrad add launches)
+  GB_DIRECT_PARAM_GRAD=1 timeout 1500 python -m pytest tests -m gpu -q -x > $out/pytest_direct.log 2>&1; echo "pytest exit $?" >> $out/pytest_direct.log
+  tail -4 $out/pytest_direct.log
+  GB_DIRECT_PARAM_GRAD=1 timeout 900 python bench.py --batch $B --no-cpu-baseline --no-roofline > $out/bench_direct_b$B.json 2> $out/bench_direct_b$B.err
+  tail -c 600 $out/bench_direct_b$B.json; tail -3 $out/bench_direct_b$B.err ;;
 in2)
   # second-generation InstanceNorm backward (knob 22; tests/test_in_bwd_v2_emul.py already runs its thread body on the CPU):
   # parity per variant in its own process, A/B table, then the whole suite and a bench line with it as the default
