@@ -248,17 +248,27 @@ def run_b200(args):
     t, t_e2e = times.tolist()
 
     roof = None
+    aux_errors = {}
     if not args.no_roofline and (world == 1 or args.roofline_all_ranks):
         # per-kernel roofline: reported at N=1 (the kernels are the same at any N).  The profiled eager steps contain
         # the gradient all-reduce, so at N>1 EVERY rank must run them (a rank-0-only run dead-locks NCCL: r01m);
         # --roofline-all-ranks does that
-        roof = profiler.conv_roofline(model, a_dev, b_dev, steps=3, with_traffic=default_wl)
+        # (the throughput numbers above are already measured: a failure of an auxiliary leg must not lose the line)
+        try:
+            roof = profiler.conv_roofline(model, a_dev, b_dev, steps=3, with_traffic=default_wl)
+        except Exception as e:  # noqa: BLE001
+            if world > 1:
+                raise  # the other ranks are inside the same collective sequence
+            aux_errors["roofline"] = f"{type(e).__name__}: {e}"
         barrier()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, med, cores = cpu_step_rate(args.size, args.batch, steps=3, warmup=1)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"3 full CycleGAN steps (batch {args.batch}) of the CPU oracle after 1 warm-up, median"}
+        try:
+            rate, med, cores = cpu_step_rate(args.size, args.batch, steps=3, warmup=1)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"3 full CycleGAN steps (batch {args.batch}) of the CPU oracle after 1 warm-up, median"}
+        except Exception as e:  # noqa: BLE001
+            aux_errors["cpu_baseline"] = f"{type(e).__name__}: {e}"
     if rank == 0:
         imgs = args.batch * world * args.steps
         in_bytes = 2 * a_host.numel() * 4
@@ -278,6 +288,8 @@ def run_b200(args):
             line["roofline_detail"] = roof["detail"]
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if aux_errors:
+            line["aux_errors"] = aux_errors
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
