@@ -6,6 +6,9 @@ what=${*:-tests bench launches full}
 B=${BATCH:-1}
 out=gpurun_out/$tag
 mkdir -p $out
+# parity subset used to validate an opt-in variant (whole iterations incl. CUDA-graph replay, every operator case, the
+# pair kernel); FULLSUITE=1 runs the whole -m gpu suite under each variant instead
+if [ "${FULLSUITE:-0}" = "1" ]; then CORE="tests"; else CORE="tests/test_ops_gpu.py tests/test_cyclegan_gpu.py tests/test_pair_gpu.py tests/test_pix2pix_gpu.py"; fi
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $out/gpu.txt 2>&1
 python -c "import os;print('cpus',os.cpu_count())" >> $out/gpu.txt
 for w in $what; do
@@ -30,14 +33,14 @@ exp)
   GB_KNOBS=16=2 timeout 900 python bench.py --batch $B --no-cpu-baseline > $out/bench_persist_b$B.json 2> $out/bench_persist_b$B.err
   tail -c 1500 $out/bench_persist_b$B.json; tail -3 $out/bench_persist_b$B.err
   # programmatic dependent launch (knob 20): the whole parity suite under it, then a bench line
-  GB_KNOBS=20=1 timeout 1500 python -m pytest tests -m gpu -q -x > $out/pytest_pdl.log 2>&1; echo "pytest exit $?" >> $out/pytest_pdl.log
+  GB_KNOBS=20=1 timeout 1500 python -m pytest $CORE -m gpu -q -x > $out/pytest_pdl.log 2>&1; echo "pytest exit $?" >> $out/pytest_pdl.log
   tail -4 $out/pytest_pdl.log
   GB_KNOBS=20=1 timeout 900 python bench.py --batch $B --no-cpu-baseline --no-roofline > $out/bench_pdl_b$B.json 2> $out/bench_pdl_b$B.err
   tail -c 600 $out/bench_pdl_b$B.json; tail -3 $out/bench_pdl_b$B.err
   GB_BWD_WINDOW=1 timeout 900 python bench.py --batch $B --no-cpu-baseline --no-roofline > $out/bench_bwdwin_b$B.json 2> $out/bench_bwdwin_b$B.err
   tail -c 600 $out/bench_bwdwin_b$B.json; tail -3 $out/bench_bwdwin_b$B.err
   # parameter gradients accumulated by the kernels into param.grad (no AccumulateGrad add launches)
-  GB_DIRECT_PARAM_GRAD=1 timeout 1500 python -m pytest tests -m gpu -q -x > $out/pytest_direct.log 2>&1; echo "pytest exit $?" >> $out/pytest_direct.log
+  GB_DIRECT_PARAM_GRAD=1 timeout 1500 python -m pytest $CORE -m gpu -q -x > $out/pytest_direct.log 2>&1; echo "pytest exit $?" >> $out/pytest_direct.log
   tail -4 $out/pytest_direct.log
   GB_DIRECT_PARAM_GRAD=1 timeout 900 python bench.py --batch $B --no-cpu-baseline --no-roofline > $out/bench_direct_b$B.json 2> $out/bench_direct_b$B.err
   tail -c 600 $out/bench_direct_b$B.json; tail -3 $out/bench_direct_b$B.err ;;
@@ -47,12 +50,12 @@ in2)
   GB_EXPERIMENTAL=1 timeout 1500 python -m pytest tests/test_in_bwd_v2_gpu.py -m gpu -q -s > $out/pytest_in2.log 2>&1; echo "pytest exit $?" >> $out/pytest_in2.log
   grep -E "OK  |FAIL|passed|failed|exit" $out/pytest_in2.log | tail -60
   timeout 900 python tools/in_microbench.py 8 > $out/in_microbench_b8.txt 2>&1; tail -45 $out/in_microbench_b8.txt
-  GB_KNOBS=22=1 timeout 1500 python -m pytest tests -m gpu -q -x > $out/pytest_in2_suite.log 2>&1; echo "pytest exit $?" >> $out/pytest_in2_suite.log
+  GB_KNOBS=22=1 timeout 1500 python -m pytest $CORE -m gpu -q -x > $out/pytest_in2_suite.log 2>&1; echo "pytest exit $?" >> $out/pytest_in2_suite.log
   tail -4 $out/pytest_in2_suite.log
   GB_KNOBS=22=1 timeout 900 python bench.py --batch $B --no-cpu-baseline --no-roofline > $out/bench_in2_b$B.json 2> $out/bench_in2_b$B.err
   tail -c 600 $out/bench_in2_b$B.json; tail -3 $out/bench_in2_b$B.err
   # on-chip cluster kernel (knob 24) for maps of <= 8192 pixels, second generation for the rest
-  GB_KNOBS=24=1,22=1 timeout 1500 python -m pytest tests -m gpu -q -x > $out/pytest_in3_suite.log 2>&1; echo "pytest exit $?" >> $out/pytest_in3_suite.log
+  GB_KNOBS=24=1,22=1 timeout 1500 python -m pytest $CORE -m gpu -q -x > $out/pytest_in3_suite.log 2>&1; echo "pytest exit $?" >> $out/pytest_in3_suite.log
   tail -4 $out/pytest_in3_suite.log
   GB_KNOBS=24=1,22=1 timeout 900 python bench.py --batch $B --no-cpu-baseline > $out/bench_in3_b$B.json 2> $out/bench_in3_b$B.err
   tail -c 2500 $out/bench_in3_b$B.json; tail -3 $out/bench_in3_b$B.err ;;
