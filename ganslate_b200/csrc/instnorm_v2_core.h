@@ -108,13 +108,25 @@ V2_HD void unpack8(const uint4& u, float (&f)[8]) {
   f[4] = as_float(u.z << 16); f[5] = as_float(u.z & 0xFFFF0000u);
   f[6] = as_float(u.w << 16); f[7] = as_float(u.w & 0xFFFF0000u);
 }
-V2_HD float4 ld_stream4(const float* p) {  // written by an earlier kernel (or pass), read once: L2 only
+V2_HD float4 ld_stream4(const float* p) {  // written during this launch by other blocks (bstats): L2 only
 #if defined(__CUDA_ARCH__)
   return __ldcg(reinterpret_cast<const float4*>(p));
 #else
   return *reinterpret_cast<const float4*>(p);
 #endif
 }
+// the incoming gradient: read-only for the whole launch, so the non-coherent path (L1-allocating) is safe -- and wanted:
+// a thread's two 16-byte loads of a pixel are the two halves of the same 32-byte sectors, the second one hits L1
+// instead of fetching the sectors from L2 again
+V2_HD float4 ld_grad4(const float* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(reinterpret_cast<const float4*>(p));
+#else
+  return *reinterpret_cast<const float4*>(p);
+#endif
+}
+// the residual gradient: read and rewritten by this thread only (ordinary cached load, same two-halves argument)
+V2_HD float4 ld_own4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 V2_HD uint4 ld_bf16x8(const uint16_t* p) {
 #if defined(__CUDA_ARCH__)
   return __ldg(reinterpret_cast<const uint4*>(p));
@@ -205,13 +217,13 @@ V2_HD void stream_pass(const gb_in_bwd_params& p, const Geom& g, float neg_slope
         const int pxu = px + u * slots;
         if (pxu < xe) {
           const float* gp = gb + og + pxu * gsx;
-          g0[u] = ld_stream4(gp);
-          g1[u] = ld_stream4(gp + 4);
+          g0[u] = ld_grad4(gp);
+          g1[u] = ld_grad4(gp + 4);
           xv[u] = ld_bf16x8(xb + ox + pxu * xsx);
           if (do_res) {
             const float* rp = sb + os + pxu * ssx;
-            q0[u] = ld_stream4(rp);
-            q1[u] = ld_stream4(rp + 4);
+            q0[u] = ld_own4(rp);
+            q1[u] = ld_own4(rp + 4);
           }
         }
       }
@@ -229,17 +241,17 @@ V2_HD void stream_pass(const gb_in_bwd_params& p, const Geom& g, float neg_slope
               const int mx = col_edge ? mirror_of(pxu, W, gpad) : NO_MIRROR;
               if (my != NO_MIRROR) {
                 const float* q = gb + my * gsy + pxu * gsx;
-                add4(gg, 0, ld_stream4(q));
-                add4(gg, 4, ld_stream4(q + 4));
+                add4(gg, 0, ld_grad4(q));
+                add4(gg, 4, ld_grad4(q + 4));
               }
               if (mx != NO_MIRROR) {
                 const float* q = gb + og + mx * gsx;
-                add4(gg, 0, ld_stream4(q));
-                add4(gg, 4, ld_stream4(q + 4));
+                add4(gg, 0, ld_grad4(q));
+                add4(gg, 4, ld_grad4(q + 4));
                 if (my != NO_MIRROR) {
                   const float* qc = gb + my * gsy + mx * gsx;
-                  add4(gg, 0, ld_stream4(qc));
-                  add4(gg, 4, ld_stream4(qc + 4));
+                  add4(gg, 0, ld_grad4(qc));
+                  add4(gg, 4, ld_grad4(qc + 4));
                 }
               }
             }

@@ -112,13 +112,13 @@ V2_HD void load_pass(const gb_in_bwd_params& p, const Geom& g, float neg_slope, 
         yy[u] = (int)y;
         xx[u] = (int)(pix - y * (uint32_t)W);
         const float* gp = gb + yy[u] * gsy + xx[u] * gsx;
-        g0[u] = gbv2::ld_stream4(gp);
-        g1[u] = gbv2::ld_stream4(gp + 4);
+        g0[u] = gbv2::ld_grad4(gp);
+        g1[u] = gbv2::ld_grad4(gp + 4);
         xv[u] = gbv2::ld_bf16x8(xb + yy[u] * (int)x.sy + xx[u] * (int)x.sx);
         if (RES) {
           const float* rp = sb + yy[u] * (int)p.dy_sum.sy + xx[u] * (int)p.dy_sum.sx;
-          q0[u] = gbv2::ld_stream4(rp);
-          q1[u] = gbv2::ld_stream4(rp + 4);
+          q0[u] = gbv2::ld_own4(rp);
+          q1[u] = gbv2::ld_own4(rp + 4);
         }
       }
     }
@@ -133,17 +133,17 @@ V2_HD void load_pass(const gb_in_bwd_params& p, const Geom& g, float neg_slope, 
         const int my = gbv2::mirror_of(y, dy.H, gpad), mx = gbv2::mirror_of(px, W, gpad);
         if (my != gbv2::NO_MIRROR) {
           const float* q = gb + my * gsy + px * gsx;
-          gbv2::add4(gg, 0, gbv2::ld_stream4(q));
-          gbv2::add4(gg, 4, gbv2::ld_stream4(q + 4));
+          gbv2::add4(gg, 0, gbv2::ld_grad4(q));
+          gbv2::add4(gg, 4, gbv2::ld_grad4(q + 4));
         }
         if (mx != gbv2::NO_MIRROR) {
           const float* q = gb + y * gsy + mx * gsx;
-          gbv2::add4(gg, 0, gbv2::ld_stream4(q));
-          gbv2::add4(gg, 4, gbv2::ld_stream4(q + 4));
+          gbv2::add4(gg, 0, gbv2::ld_grad4(q));
+          gbv2::add4(gg, 4, gbv2::ld_grad4(q + 4));
           if (my != gbv2::NO_MIRROR) {
             const float* qc = gb + my * gsy + mx * gsx;
-            gbv2::add4(gg, 0, gbv2::ld_stream4(qc));
-            gbv2::add4(gg, 4, gbv2::ld_stream4(qc + 4));
+            gbv2::add4(gg, 0, gbv2::ld_grad4(qc));
+            gbv2::add4(gg, 4, gbv2::ld_grad4(qc + 4));
           }
         }
       }
