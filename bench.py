@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--workload", default="cyclegan2d", choices=sorted(WORKLOADS),
                     help="which BASELINE.json configuration to time (default: the CycleGAN headline configuration)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--graph", action="store_true", help="CUDA-graph replay also for the workloads that default to eager "
+                                                         "launches (CUT: capture path not yet verified on a B200)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--roofline-all-ranks", action="store_true", help="N>1: profile the per-kernel roofline too")
@@ -184,8 +186,8 @@ def run_b200(args):
     default_wl = args.workload == "cyclegan2d"
     if shape is None:
         shape = (3, args.size, args.size)
-    if not graph_ok:
-        args.no_graph = True  # CUT / RevGAN recipes run eagerly (their step is not captured)
+    if not graph_ok and not args.graph:
+        args.no_graph = True  # CUT / RevGAN recipes run eagerly by default (--graph: CUT's segmented capture)
     conf = getattr(presets, preset)(batch_size=args.batch, cuda_graph=not args.no_graph)
     model = build_gan(conf)
     # synthetic inputs U(-1, 1) (images are normalised to [-1, 1] in the reference); each rank draws its own shard

@@ -78,18 +78,60 @@ class CUT(BaseGAN):
         super().save_checkpoint(iter_idx)  # the reference drops the mlp optimizer as well (base.py:244-245)
 
     def optimize_parameters(self):
+        """One iteration in the reference's order (cut.py:113-137).  With `train.cuda_graph` the two phases (forward + D
+        step, G + patch-MLP step) are captured once and replayed; the discriminator is stepped BEFORE the second phase
+        (the generator's adversarial loss goes through the updated discriminator).  The patch ids are drawn on the
+        device inside the captured region (torch.randperm under the graph-safe Philox generator), so every replay
+        samples new patches.  Data parallel + graphs: explicit flat-bucket all-reduces between the segments, as in
+        CycleGAN.  (The capture path has not run on a B200 yet: bench.py keeps CUT eager unless --graph is given.)"""
+        sync = self.grad_syncs
+        if self.graph_mode('step'):
+            if self.use_equivariance_flip:
+                raise RuntimeError("train.cuda_graph cannot replay use_equivariance_flip (a host-side coin flip per "
+                                   "iteration changes the captured program)")
+            self.run_graphed('D', lambda: self._phase_D(step=sync is None))
+            if sync:
+                sync['D'].launch()
+                sync['D'].finish()
+                self.run_graphed('stepD', self.optimizers['D'].step)
+            self.run_graphed('G', lambda: self._phase_G(step=sync is None))
+            if sync:
+                sync['G'].launch()
+                sync['mlp'].launch()
+                sync['G'].finish()
+                self.run_graphed('stepG', self.optimizers['G'].step)
+                sync['mlp'].finish()
+                self.run_graphed('stepMLP', self.optimizers['mlp'].step)
+            return
         with self.eager_stream():
-            self.forward()
-            # ---- D
-            self.set_requires_grad(self.networks['D'], True)
-            self.optimizers['D'].zero_grad(set_to_none=True)
-            self.backward_D()
+            self._phase_D(step=sync is None)
+            if sync:
+                sync['D'].launch()
+                sync['D'].finish()
+                self.optimizers['D'].step()
+            self._phase_G(step=sync is None)
+            if sync:
+                sync['G'].launch()
+                sync['mlp'].launch()
+                sync['G'].finish()
+                self.optimizers['G'].step()
+                sync['mlp'].finish()
+                self.optimizers['mlp'].step()
+
+    def _phase_D(self, step=True):
+        self.forward()
+        self.set_requires_grad(self.networks['D'], True)
+        self.optimizers['D'].zero_grad(set_to_none=True)
+        self.backward_D()
+        if step:
             self.optimizers['D'].step()
-            # ---- G and the patch MLP
-            self.set_requires_grad(self.networks['D'], False)
-            self.optimizers['G'].zero_grad(set_to_none=True)
-            self.optimizers['mlp'].zero_grad(set_to_none=True)
-            self.backward_G_and_mlp()
+
+    def _phase_G(self, step=True):
+        self.set_requires_grad(self.networks['D'], False)
+        self.optimizers['G'].zero_grad(set_to_none=True)
+        self.optimizers['mlp'].zero_grad(set_to_none=True)
+        self.backward_G_and_mlp()
+        if step:
             self.optimizers['G'].step()
             self.optimizers['mlp'].step()
 

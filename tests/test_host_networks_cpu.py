@@ -473,3 +473,43 @@ def test_direct_parameter_gradients_equal_autograd_accumulation(monkeypatch):
         d = grads[True][key]
         assert d.shape == g.shape
         assert torch.allclose(d, g, rtol=1e-5, atol=1e-6 * max(1.0, float(g.abs().max()))), (key, float((d - g).abs().max()))
+
+
+def test_cut_graph_segments_follow_the_eager_order(monkeypatch):
+    """CUT with `train.cuda_graph`: the iteration is split into the segments that are captured (forward + D phase, D
+    step, G + patch-MLP phase, their steps).  With the capture itself replaced by a direct call, the segmented path must
+    run the same program as the eager one: same losses, same gradients, optimizers stepped in the reference's order
+    (D before the generator phase: cut.py:121-125)."""
+    _cpu_recipe(monkeypatch)
+    from ganslate_b200.nn.gans import base
+    from ganslate_b200.presets import cut_resnet2d
+    from ganslate_b200.utils.builders import build_gan
+    from oracle import torch_oracle as O
+    a, b = O.synthetic_batch(1, 3, 64, seed=1)
+    g = torch.Generator().manual_seed(5)
+    ids = [torch.randperm(s, generator=g)[:64] for s in [70 * 70, 32 * 32, 16 * 16, 16 * 16, 16 * 16]]
+    results = {}
+    for mode in ("eager", "segments"):
+        torch.manual_seed(0)
+        conf = cut_resnet2d()
+        conf.train.gan.optimizer.num_patches = 64
+        gan = build_gan(conf)
+        order = []
+        for name, o in gan.optimizers.items():
+            monkeypatch.setattr(o, "step", lambda *args, _n=name, **kw: order.append(_n))
+        if mode == "segments":
+            seen = []
+            monkeypatch.setattr(gan, "graph_mode", lambda key: True)
+            monkeypatch.setattr(gan, "run_graphed", lambda name, fn: (seen.append(name), fn())[1])
+        gan.fixed_patch_ids = ids
+        gan.set_input({"A": a, "B": b})
+        gan.optimize_parameters()
+        results[mode] = ({k: float(v.detach()) for k, v in gan.losses.items() if v is not None},
+                         {(n, k): p.grad.clone() for n, net in gan.networks.items() for k, p in net.named_parameters()
+                          if p.grad is not None}, list(order))
+    assert seen == ["D", "G"]
+    assert results["eager"][2] == results["segments"][2] == ["D", "G", "mlp"]
+    assert results["eager"][0] == results["segments"][0]
+    assert results["eager"][1].keys() == results["segments"][1].keys()
+    for k, v in results["eager"][1].items():
+        assert torch.equal(v, results["segments"][1][k]), k

@@ -64,7 +64,10 @@ shapes)
   for wl in pix2pix_resnet pix2pix_unet cut cyclegan3d revgan3d revgan_piresnet3d; do
     timeout 900 python bench.py --workload $wl --steps 5 --warmup 3 --no-roofline > $out/bench_$wl.json 2> $out/bench_$wl.err
     tail -c 700 $out/bench_$wl.json; tail -2 $out/bench_$wl.err
-  done ;;
+  done
+  # CUT as replayed CUDA-graph segments (capture path written without a GPU: first run)
+  timeout 900 python bench.py --workload cut --graph --steps 5 --warmup 3 --no-roofline > $out/bench_cut_graph.json 2> $out/bench_cut_graph.err
+  tail -c 700 $out/bench_cut_graph.json; tail -3 $out/bench_cut_graph.err ;;
 benchref)
   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 --batch $B > $out/bench_ref_b$B.json 2>> $out/bench_b$B.err; cat $out/bench_ref_b$B.json ;;
 launches)
