@@ -62,8 +62,19 @@ in2)
 shapes)
   # throughput of every BASELINE.json configuration (one short bench line each; not the headline number)
   for wl in pix2pix_resnet pix2pix_unet cut cyclegan3d revgan3d revgan_piresnet3d; do
-    timeout 900 python bench.py --workload $wl --steps 5 --warmup 3 --no-roofline > $out/bench_$wl.json 2> $out/bench_$wl.err
-    tail -c 700 $out/bench_$wl.json; tail -2 $out/bench_$wl.err
+    # (with the per-kernel-family breakdown: roofline_detail says where each workload's time goes)
+    timeout 900 python bench.py --workload $wl --steps 5 --warmup 3 > $out/bench_$wl.json 2> $out/bench_$wl.err
+    python - "$out/bench_$wl.json" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(d["metric"], round(d["value"], 2), d["unit"], "ms/step", round(d["ms_per_step"], 2), "e2e", round(d["e2e"]["value"], 2))
+    for k, v in sorted(d.get("roofline_detail", {}).items(), key=lambda kv: -kv[1]["share_of_kernel_time"]):
+        print("   %-12s share %.3f  %8.1f %s (%.2f of peak)  %d launches/step avg %.1f us" % (k, v["share_of_kernel_time"], v["achieved"], v["unit"], v["frac"], v["launches_per_step"], v["avg_us"]))
+except Exception as e:
+    print("no bench line:", e)
+PY
+    tail -2 $out/bench_$wl.err
   done
   # CUT as replayed CUDA-graph segments (capture path written without a GPU: first run)
   timeout 900 python bench.py --workload cut --graph --steps 5 --warmup 3 --no-roofline > $out/bench_cut_graph.json 2> $out/bench_cut_graph.err
