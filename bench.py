@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--graph", action="store_true", help="CUDA-graph replay also for the workloads that default to eager "
                                                          "launches (CUT: capture path not yet verified on a B200)")
+    ap.add_argument("--e2e-pipeline", action="store_true",
+                    help="opt-in, not yet verified on a B200: e2e leg with the inputs' H2D copy on its own stream "
+                         "(train.input_prefetch) and the loss of step i read after step i+1 was enqueued")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--roofline-all-ranks", action="store_true", help="N>1: profile the per-kernel roofline too")
@@ -188,7 +191,8 @@ def run_b200(args):
         shape = (3, args.size, args.size)
     if not graph_ok and not args.graph:
         args.no_graph = True  # CUT / RevGAN recipes run eagerly by default (--graph: CUT's segmented capture)
-    conf = getattr(presets, preset)(batch_size=args.batch, cuda_graph=not args.no_graph)
+    conf = getattr(presets, preset)(batch_size=args.batch, cuda_graph=not args.no_graph,
+                                    **({"input_prefetch": True} if args.e2e_pipeline else {}))
     model = build_gan(conf)
     # synthetic inputs U(-1, 1) (images are normalised to [-1, 1] in the reference); each rank draws its own shard
     gen = torch.Generator(device="cpu").manual_seed(1 + rank)
@@ -210,15 +214,28 @@ def run_b200(args):
             model.set_input({"A": a_host, "B": b_host})  # H2D from pinned memory inside the timed region
         model.optimize_parameters()
 
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+
     def timed(n, resident):
         evs = []
-        for _ in range(n):
+        pending = None  # --e2e-pipeline: event after the D2H copy of the previous step's loss
+        for i in range(n):
             flush.zero_()  # evict L2 between timed iterations
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             step(resident)
             if not resident:
-                _ = float(next(iter(model.losses.values())))  # D2H read of a step result
+                if args.e2e_pipeline:
+                    # every step's loss still travels to the host, but the host waits for step i-1's copy only after
+                    # step i has been enqueued (a tracker that logs with one step of lag), so the GPU never idles
+                    loss_host[i & 1].copy_(next(iter(model.losses.values())).detach().reshape(()), non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    if pending is not None:
+                        pending.synchronize()
+                    pending = ev
+                else:
+                    _ = float(next(iter(model.losses.values())))  # D2H read of a step result
             e1.record()
             evs.append((e0, e1))
         torch.cuda.synchronize()
@@ -283,6 +300,8 @@ def run_b200(args):
             "gpu_launches": int(launches), "clocks": clocks,
             "cuda_graph": not args.no_graph,
         }
+        if args.e2e_pipeline:
+            line["e2e"]["pipeline"] = "H2D of step i+1 on a copy stream; loss of step i read after step i+1 is enqueued"
         if default_wl and args.size == 256:
             line["conv_tflops_step"] = conv_flops_per_step(args.batch) * args.steps / t / 1e12
         if roof is not None:

@@ -50,6 +50,10 @@ class BaseGAN(ABC):
         self.graph_warmup_iters = int(conf[conf.mode].get("cuda_graph_warmup", 11)) if self.is_train else 0
         self._graphs, self._static, self._graph_calls = {}, {}, 0
         self.grad_syncs = None  # {optimizer name: FlatGradSync} when graphs + data parallel
+        self.input_copy_stream = None  # train.input_prefetch (graph mode): H2D of pinned inputs on its own stream
+        if self.use_cuda_graph and bool(conf[conf.mode].get("input_prefetch", False)) and self.device.type == "cuda":
+            self.input_copy_stream = torch.cuda.Stream(device=self.device)
+        self._staging = {}
         self.graph_launches_per_step = 0
 
     def init_networks(self):
@@ -140,6 +144,26 @@ class BaseGAN(ABC):
                 raise RuntimeError("input shape changed after CUDA-graph capture")
             buf = torch.empty(tensor.shape, dtype=torch.float32, device=self.device)
             self._static[name] = buf
+        if self.input_copy_stream is not None and tensor.device.type == "cpu" and tensor.is_pinned():
+            # opt-in (train.input_prefetch): the host -> device copy runs on its own stream into one of two staging
+            # buffers, so it overlaps with whatever the compute stream still has queued (the previous iteration, when
+            # the caller does not synchronise in between); the compute stream then only does a device-to-device copy
+            # into the buffer the graphs read.  Two staging buffers: the copy of iteration i+1 never overwrites data
+            # the compute stream has not consumed yet (its D2D copy of iteration i was enqueued before).
+            stg = self._staging.setdefault(name, {"buf": [None, None], "read": [None, None], "k": 0})
+            k = stg["k"] = stg["k"] ^ 1
+            if stg["buf"][k] is None or stg["buf"][k].shape != tensor.shape:
+                stg["buf"][k] = torch.empty(tensor.shape, dtype=torch.float32, device=self.device)
+            cur = torch.cuda.current_stream()
+            with torch.cuda.stream(self.input_copy_stream):
+                if stg["read"][k] is not None:  # the compute stream's D2D copy out of this buffer, two iterations ago
+                    self.input_copy_stream.wait_event(stg["read"][k])
+                stg["buf"][k].copy_(tensor, non_blocking=True)
+            cur.wait_stream(self.input_copy_stream)
+            buf.copy_(stg["buf"][k], non_blocking=True)
+            stg["read"][k] = torch.cuda.Event()
+            stg["read"][k].record(cur)
+            return buf
         buf.copy_(tensor, non_blocking=True)
         return buf
 

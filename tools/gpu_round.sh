@@ -43,7 +43,10 @@ exp)
   GB_DIRECT_PARAM_GRAD=1 timeout 1500 python -m pytest $CORE -m gpu -q -x > $out/pytest_direct.log 2>&1; echo "pytest exit $?" >> $out/pytest_direct.log
   tail -4 $out/pytest_direct.log
   GB_DIRECT_PARAM_GRAD=1 timeout 900 python bench.py --batch $B --no-cpu-baseline --no-roofline > $out/bench_direct_b$B.json 2> $out/bench_direct_b$B.err
-  tail -c 600 $out/bench_direct_b$B.json; tail -3 $out/bench_direct_b$B.err ;;
+  tail -c 600 $out/bench_direct_b$B.json; tail -3 $out/bench_direct_b$B.err
+  # e2e leg with input prefetch on a copy stream and lagged loss read-back (train.input_prefetch)
+  timeout 900 python bench.py --batch $B --e2e-pipeline --no-cpu-baseline --no-roofline > $out/bench_e2epipe_b$B.json 2> $out/bench_e2epipe_b$B.err
+  tail -c 700 $out/bench_e2epipe_b$B.json; tail -3 $out/bench_e2epipe_b$B.err ;;
 in2)
   # second-generation InstanceNorm backward (knob 22; tests/test_in_bwd_v2_emul.py already runs its thread body on the CPU):
   # parity per variant in its own process, A/B table, then the whole suite and a bench line with it as the default
