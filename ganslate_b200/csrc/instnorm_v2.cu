@@ -30,19 +30,17 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
-// partial sums of the block's threads -> one atomic per channel (and moment); red: [slots][C][2] floats
-template <int PASS>
-__device__ __forceinline__ void block_reduce(const gb_in_bwd_params& p, int n, const float (&acc1)[8], const float (&acc2)[8],
-                                             float* red, bool active) {
-  const int C = p.x.C;
+// partial sums (a, b) of the block's threads -> per-channel totals handed to `emit(channel, sum_a, sum_b)`;
+// red: [slots][C][2] floats; ends with a block barrier so that `red` can be reused at once
+template <typename Emit>
+__device__ __forceinline__ void block_reduce(int C, const float (&a)[8], const float (&b)[8], float* red, Emit emit) {
   const int C8 = C >> 3;
   const int slots = THREADS / C8;
   const int cgp = threadIdx.x % C8, slot = threadIdx.x / C8;
-  if (!active) return;  // uniform over the block
   if (slot < slots) {
     float4* dst = reinterpret_cast<float4*>(red + ((size_t)slot * C + cgp * 8) * 2);
 #pragma unroll
-    for (int h = 0; h < 4; ++h) dst[h] = make_float4(acc1[2 * h], acc2[2 * h], acc1[2 * h + 1], acc2[2 * h + 1]);
+    for (int h = 0; h < 4; ++h) dst[h] = make_float4(a[2 * h], b[2 * h], a[2 * h + 1], b[2 * h + 1]);
   }
   __syncthreads();
   for (int ch = threadIdx.x; ch < C; ch += THREADS) {
@@ -52,34 +50,43 @@ __device__ __forceinline__ void block_reduce(const gb_in_bwd_params& p, int n, c
       s1 += t.x;
       s2 += t.y;
     }
-    if (PASS == 0) {
-      atomicAdd(p.bstats + ((int64_t)n * C + ch) * 2 + 0, s1);
-      atomicAdd(p.bstats + ((int64_t)n * C + ch) * 2 + 1, s2);
-    } else {
-      atomicAdd(p.dbias + ch, s1);
-    }
+    emit(ch, s1, s2);
   }
+  __syncthreads();
 }
 
-// PASS 0 / 1: the two passes as separate launches, PASS 2: both in one launch around a grid barrier
-template <bool RES, int U, int MINB, int PASS>
+// PASS 0 / 1: the two passes as separate launches, PASS 2: both in one launch around a grid barrier.
+// GEN: PReLU / residual before the activation / scaled output (instnorm_v2_core.h).
+template <bool RES, int U, int MINB, int PASS, bool GEN>
 __global__ void __launch_bounds__(THREADS, MINB)
 in_bwd_v2_kernel(const __grid_constant__ gb_in_bwd_params p, const __grid_constant__ Geom g, float neg_slope) {
   gb_pdl_enter();
   extern __shared__ float red[];
   const int n = blockIdx.y;
-  float acc1[8], acc2[8];
+  const int C = p.x.C;
+  float acc1[8], acc2[8], acc3[8];
   if (PASS == 0 || PASS == 2) {
-    gbv2::stream_pass<RES, U, 0>(p, g, neg_slope, threadIdx.x, blockIdx.x, n, acc1, acc2);
-    block_reduce<0>(p, n, acc1, acc2, red, true);
+    gbv2::stream_pass<RES, U, 0, GEN>(p, g, neg_slope, threadIdx.x, blockIdx.x, n, acc1, acc2, acc3);
+    float* bs = p.bstats + (int64_t)n * C * 2;
+    block_reduce(C, acc1, acc2, red, [bs](int ch, float s1, float s2) {
+      atomicAdd(bs + ch * 2 + 0, s1);
+      atomicAdd(bs + ch * 2 + 1, s2);
+    });
+    if (GEN && p.dprelu != nullptr) {  // uniform over the grid
+      float* dp = p.dprelu;
+      block_reduce(C, acc3, acc3, red, [dp](int ch, float s1, float) { atomicAdd(dp + ch, s1); });
+    }
   }
   if (PASS == 2) {
-    unsigned int* counter = reinterpret_cast<unsigned int*>(p.bstats + (int64_t)p.x.N * p.x.C * 2);
-    grid_barrier(counter, (unsigned int)g.total_blocks);  // also orders the reuse of `red`
+    unsigned int* counter = reinterpret_cast<unsigned int*>(p.bstats + (int64_t)p.x.N * C * 2);
+    grid_barrier(counter, (unsigned int)g.total_blocks);
   }
   if (PASS == 1 || PASS == 2) {
-    gbv2::stream_pass<RES, U, 1>(p, g, neg_slope, threadIdx.x, blockIdx.x, n, acc1, acc2);
-    block_reduce<1>(p, n, acc1, acc2, red, p.dbias != nullptr);
+    gbv2::stream_pass<RES, U, 1, GEN>(p, g, neg_slope, threadIdx.x, blockIdx.x, n, acc1, acc2, acc3);
+    if (p.dbias != nullptr) {  // uniform over the grid
+      float* db = p.dbias;
+      block_reduce(C, acc1, acc1, red, [db](int ch, float s1, float) { atomicAdd(db + ch, s1); });
+    }
   }
 }
 
@@ -103,14 +110,14 @@ int num_sms() {
   return n;
 }
 
-template <bool RES, int U, int MINB>
+template <bool RES, int U, int MINB, bool GEN>
 int launch(const gb_in_bwd_params& p, float neg_slope, cudaStream_t st) {
   const size_t smem = sizeof(float) * 2 * gbv2::slots_of(p.x.C) * p.x.C;
   static int occ = -1;  // co-resident blocks per SM of the single-launch kernel (per instantiation)
   static size_t occ_smem = 0;
   if (occ < 0 || occ_smem != smem) {
     int o = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, in_bwd_v2_kernel<RES, U, MINB, 2>, THREADS, smem) != cudaSuccess) o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, in_bwd_v2_kernel<RES, U, MINB, 2, GEN>, THREADS, smem) != cudaSuccess) o = 0;
     cudaGetLastError();
     occ = o;
     occ_smem = smem;
@@ -122,7 +129,7 @@ int launch(const gb_in_bwd_params& p, float neg_slope, cudaStream_t st) {
     float ns = neg_slope;
     Geom gg = g;
     void* args[] = {(void*)&p, (void*)&gg, (void*)&ns};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)in_bwd_v2_kernel<RES, U, MINB, 2>, grid, dim3(THREADS), args,
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)in_bwd_v2_kernel<RES, U, MINB, 2, GEN>, grid, dim3(THREADS), args,
                                                 smem, st);
     if (e == cudaSuccess) {
       __atomic_fetch_add(&g_gb_launches, 1ull, __ATOMIC_RELAXED);
@@ -130,9 +137,9 @@ int launch(const gb_in_bwd_params& p, float neg_slope, cudaStream_t st) {
     }
     cudaGetLastError();  // cooperative launch not possible here: two launches
   }
-  gb_klaunch(in_bwd_v2_kernel<RES, U, MINB, 0>, grid, THREADS, smem, st, p, g, neg_slope);
+  gb_klaunch(in_bwd_v2_kernel<RES, U, MINB, 0, GEN>, grid, THREADS, smem, st, p, g, neg_slope);
   GB_LAUNCH_CHECK();
-  gb_klaunch(in_bwd_v2_kernel<RES, U, MINB, 1>, grid, THREADS, smem, st, p, g, neg_slope);
+  gb_klaunch(in_bwd_v2_kernel<RES, U, MINB, 1, GEN>, grid, THREADS, smem, st, p, g, neg_slope);
   GB_LAUNCH_CHECK();
   return 0;
 }
@@ -148,12 +155,17 @@ int gb_in_bwd_fast_v2(const gb_in_bwd_params& p, cudaStream_t st) {
     case GB_ACT_NONE: ns = 1.f; break;
     case GB_ACT_RELU: ns = 0.f; break;
     case GB_ACT_LEAKY: ns = p.act_slope; break;
+    case GB_ACT_PRELU: ns = 0.f; break;  // per-channel slopes from p.prelu
     default: return -1;
   }
+  if (p.act == GB_ACT_PRELU && p.prelu == nullptr) return -1;
   if (p.stats == nullptr || p.bstats == nullptr) return -1;
   if (p.dy_a.ptr != nullptr || p.dy_b.ptr == nullptr) return -1;
-  if (p.res_before_act || p.dx_fp32_acc || p.dprelu != nullptr) return -1;
-  if (p.out_scale != 0.f && p.out_scale != 1.f) return -1;
+  if (p.dx_fp32_acc) return -1;
+  const bool rba = p.res_before_act != 0 && p.res.ptr != nullptr;
+  // the general form: PReLU (+ its gradient), residual before the activation, scaled output
+  const bool gen = p.act == GB_ACT_PRELU || rba || (p.out_scale != 0.f && p.out_scale != 1.f);
+  if (!gen && p.dprelu != nullptr) return -1;
   const bool has_res = p.dy_sum.ptr != nullptr;
   if (has_res && !p.dy_sum_acc) return -1;
   const gb_view& x = p.x;
@@ -164,7 +176,9 @@ int gb_in_bwd_fast_v2(const gb_in_bwd_params& p, cudaStream_t st) {
     return -1;
   if (!small_offsets(x) || !small_offsets(p.dx) || !small_offsets(p.dy_b) || (has_res && !small_offsets(p.dy_sum))) return -1;
   if (p.dy_b.pad > 0 && (p.dy_b.D != 1 || p.dy_b.H <= 2 * p.dy_b.pad + 1 || p.dy_b.W <= 2 * p.dy_b.pad + 1)) return -1;
+  if (rba && (!aligned(p.res, 2, 8) || !row_addressable(p.res) || !small_offsets(p.res))) return -1;
+  if (gen) return has_res ? launch<true, 2, 2, true>(p, ns, st) : launch<false, 2, 2, true>(p, ns, st);
   // (the residual form holds two more fp32 vectors per pixel: one pixel less in flight keeps it free of spills)
-  if (variant == 1) return has_res ? launch<true, 3, 2>(p, ns, st) : launch<false, 4, 2>(p, ns, st);
-  return has_res ? launch<true, 2, 2>(p, ns, st) : launch<false, 2, 2>(p, ns, st);
+  if (variant == 1) return has_res ? launch<true, 3, 2, false>(p, ns, st) : launch<false, 4, 2, false>(p, ns, st);
+  return has_res ? launch<true, 2, 2, false>(p, ns, st) : launch<false, 2, 2, false>(p, ns, st);
 }

@@ -144,9 +144,13 @@ V2_HD void add4(float (&f)[8], int o, const float4& t) {
 //   PASS 1: dx is written; acc1 = partial sum of the fp32 dx (bias gradient); reads bstats (totals of pass 0)
 // g = gradient on the (reflection-padded when dy_b.pad > 0) output domain folded onto the interior, times the
 // activation's derivative (xhat > 0 ? 1 : neg_slope).
-template <bool RES, int U, int PASS>
+// GEN adds what the V-Net layers need (ganslate/nn/generators/vnet/vnet3d.py:160-168,193-203): per-channel PReLU
+// slopes (p.prelu) and their gradient (acc3 = partial sum of g * pre over the negative side, PASS 0), a residual added
+// BEFORE the activation (pre = xhat + res: the mask depends on it and dy_sum receives the MASKED gradient) and a
+// scaled output (out_scale, the inverse of an additive coupling).
+template <bool RES, int U, int PASS, bool GEN>
 V2_HD void stream_pass(const gb_in_bwd_params& p, const Geom& g, float neg_slope, int tid, int bx, int n,
-                       float (&acc1)[8], float (&acc2)[8]) {
+                       float (&acc1)[8], float (&acc2)[8], float (&acc3)[8]) {
   const gb_view& x = p.x;
   const gb_view& dy = p.dy_b;
   const int C8 = x.C >> 3;
@@ -154,7 +158,7 @@ V2_HD void stream_pass(const gb_in_bwd_params& p, const Geom& g, float neg_slope
   const int cgp = tid % C8;
   const int slot = tid / C8;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc1[e] = acc2[e] = 0.f;
+  for (int e = 0; e < 8; ++e) acc1[e] = acc2[e] = acc3[e] = 0.f;
   if (slot >= slots) return;
   const int c = cgp * 8;
   const int W = x.W;
@@ -191,6 +195,14 @@ V2_HD void stream_pass(const gb_in_bwd_params& p, const Geom& g, float neg_slope
   }
   const bool want_dbias = PASS == 1 && p.dbias != nullptr;
   const bool do_res = RES && PASS == 0;  // the residual gradient is accumulated exactly once
+  const bool rba = GEN && p.res_before_act != 0 && p.res.ptr != nullptr;
+  const bool want_dprelu = GEN && PASS == 0 && p.dprelu != nullptr;
+  const float oscale = (GEN && p.out_scale != 0.f) ? p.out_scale : 1.f;
+  float ns[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) ns[e] = (GEN && p.prelu != nullptr) ? p.prelu[c + e] : neg_slope;
+  const uint16_t* rb = rba ? reinterpret_cast<const uint16_t*>(p.res.ptr) + (int64_t)n * p.res.sn + c : nullptr;
+  const int rsx = rba ? (int)p.res.sx : 0;
   const float* gb = reinterpret_cast<const float*>(dy.ptr) + (int64_t)n * dy.sn + c;
   const uint16_t* xb = reinterpret_cast<const uint16_t*>(x.ptr) + (int64_t)n * x.sn + c;
   float* sb = RES ? reinterpret_cast<float*>(p.dy_sum.ptr) + (int64_t)n * p.dy_sum.sn + c : nullptr;
@@ -209,9 +221,10 @@ V2_HD void stream_pass(const gb_in_bwd_params& p, const Geom& g, float neg_slope
     const int my = gpad > 0 ? mirror_of(y, dy.H, gpad) : NO_MIRROR;
     const int og = y * gsy, ox = y * (int)x.sy, od = y * (int)p.dx.sy;
     const int os = RES ? y * (int)p.dy_sum.sy : 0;
+    const int orr = rba ? y * (int)p.res.sy : 0;
     for (int px = xa + slot; px < xe; px += slots * U) {
       float4 g0[U], g1[U], q0[U], q1[U];
-      uint4 xv[U];
+      uint4 xv[U], rv[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int pxu = px + u * slots;
@@ -220,6 +233,7 @@ V2_HD void stream_pass(const gb_in_bwd_params& p, const Geom& g, float neg_slope
           g0[u] = ld_grad4(gp);
           g1[u] = ld_grad4(gp + 4);
           xv[u] = ld_bf16x8(xb + ox + pxu * xsx);
+          if (rba) rv[u] = ld_bf16x8(rb + orr + pxu * rsx);
           if (do_res) {
             const float* rp = sb + os + pxu * ssx;
             q0[u] = ld_own4(rp);
@@ -256,7 +270,7 @@ V2_HD void stream_pass(const gb_in_bwd_params& p, const Geom& g, float neg_slope
               }
             }
           }
-          if (do_res) {
+          if (do_res && !rba) {  // residual added after the activation: it receives the unmasked gradient
             float* rp = sb + os + pxu * ssx;
             float4 o0, o1;
             o0.x = q0[u].x + gg[0]; o0.y = q0[u].y + gg[1]; o0.z = q0[u].z + gg[2]; o0.w = q0[u].w + gg[3];
@@ -264,12 +278,23 @@ V2_HD void stream_pass(const gb_in_bwd_params& p, const Geom& g, float neg_slope
             *reinterpret_cast<float4*>(rp) = o0;
             *reinterpret_cast<float4*>(rp + 4) = o1;
           }
-          float d[8];
+          float d[8], rf[8];
+          if (rba) unpack8(rv[u], rf);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const float xh = fma_(xf[e], a[e], b[e]);
             float ge = gg[e];
-            if (!(xh > 0.f)) ge *= neg_slope;
+            if (GEN) {
+              const float pre = rba ? xh + rf[e] : xh;
+              ge *= oscale;
+              if (!(pre > 0.f)) {
+                if (want_dprelu) acc3[e] = fma_(ge, pre, acc3[e]);
+                ge *= ns[e];
+              }
+              gg[e] = ge;  // masked gradient (residual before the activation)
+            } else {
+              if (!(xh > 0.f)) ge *= neg_slope;
+            }
             if (PASS == 0) {
               acc1[e] += ge;
               acc2[e] = fma_(ge, xh, acc2[e]);
@@ -277,6 +302,14 @@ V2_HD void stream_pass(const gb_in_bwd_params& p, const Geom& g, float neg_slope
               d[e] = fma_(-xh, k2[e], fma_(a[e], ge, -k1[e]));
               if (want_dbias) acc1[e] += d[e];  // sum of the fp32 dx, not of its bf16 rounding (see instnorm.cu)
             }
+          }
+          if (do_res && rba) {
+            float* rp = sb + os + pxu * ssx;
+            float4 o0, o1;
+            o0.x = q0[u].x + gg[0]; o0.y = q0[u].y + gg[1]; o0.z = q0[u].z + gg[2]; o0.w = q0[u].w + gg[3];
+            o1.x = q1[u].x + gg[4]; o1.y = q1[u].y + gg[5]; o1.z = q1[u].z + gg[6]; o1.w = q1[u].w + gg[7];
+            *reinterpret_cast<float4*>(rp) = o0;
+            *reinterpret_cast<float4*>(rp + 4) = o1;
           }
           if (PASS == 1) {
             uint4 o;

@@ -6,7 +6,7 @@
 
 namespace {
 
-template <bool RES, int U>
+template <bool RES, int U, bool GEN>
 int run(const gb_in_bwd_params& p, int cap, float neg_slope, int* grid_out) {
   bool fits = false;
   const gbv2::Geom g = gbv2::plan(p.x.N, p.x.D, p.x.H, p.x.W, p.x.C, cap, &fits);
@@ -14,19 +14,20 @@ int run(const gb_in_bwd_params& p, int cap, float neg_slope, int* grid_out) {
   grid_out[1] = g.ppb;
   const int C = p.x.C, C8 = C >> 3;
   const int slots = gbv2::slots_of(C);
-  float acc1[8], acc2[8];
+  float acc1[8], acc2[8], acc3[8];
   for (int pass = 0; pass < 2; ++pass)
     for (int n = 0; n < p.x.N; ++n)
       for (int bx = 0; bx < g.nblocks; ++bx)
         for (int tid = 0; tid < gbv2::THREADS; ++tid) {
-          if (pass == 0) gbv2::stream_pass<RES, U, 0>(p, g, neg_slope, tid, bx, n, acc1, acc2);
-          else gbv2::stream_pass<RES, U, 1>(p, g, neg_slope, tid, bx, n, acc1, acc2);
+          if (pass == 0) gbv2::stream_pass<RES, U, 0, GEN>(p, g, neg_slope, tid, bx, n, acc1, acc2, acc3);
+          else gbv2::stream_pass<RES, U, 1, GEN>(p, g, neg_slope, tid, bx, n, acc1, acc2, acc3);
           if (tid / C8 >= slots) continue;
           const int c = (tid % C8) * 8;
           for (int e = 0; e < 8; ++e) {
             if (pass == 0) {
               p.bstats[((int64_t)n * C + c + e) * 2 + 0] += acc1[e];
               p.bstats[((int64_t)n * C + c + e) * 2 + 1] += acc2[e];
+              if (GEN && p.dprelu != nullptr) p.dprelu[c + e] += acc3[e];
             } else if (p.dbias != nullptr) {
               p.dbias[c + e] += acc1[e];
             }
@@ -37,12 +38,14 @@ int run(const gb_in_bwd_params& p, int cap, float neg_slope, int* grid_out) {
 
 }  // namespace
 
+// U: pixels in flight per thread; + 10 selects the general form (PReLU, residual before the activation, scaled output)
 extern "C" int in_bwd_v2_emulate(const gb_in_bwd_params* p, int cap, int U, float neg_slope, int* grid_out) {
   const bool res = p->dy_sum.ptr != nullptr;
   switch (U) {
-    case 2: return res ? run<true, 2>(*p, cap, neg_slope, grid_out) : run<false, 2>(*p, cap, neg_slope, grid_out);
-    case 3: return res ? run<true, 3>(*p, cap, neg_slope, grid_out) : run<false, 3>(*p, cap, neg_slope, grid_out);
-    case 4: return res ? run<true, 4>(*p, cap, neg_slope, grid_out) : run<false, 4>(*p, cap, neg_slope, grid_out);
+    case 2: return res ? run<true, 2, false>(*p, cap, neg_slope, grid_out) : run<false, 2, false>(*p, cap, neg_slope, grid_out);
+    case 3: return res ? run<true, 3, false>(*p, cap, neg_slope, grid_out) : run<false, 3, false>(*p, cap, neg_slope, grid_out);
+    case 4: return res ? run<true, 4, false>(*p, cap, neg_slope, grid_out) : run<false, 4, false>(*p, cap, neg_slope, grid_out);
+    case 12: return res ? run<true, 2, true>(*p, cap, neg_slope, grid_out) : run<false, 2, true>(*p, cap, neg_slope, grid_out);
   }
   return 1;
 }

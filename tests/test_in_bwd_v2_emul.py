@@ -15,7 +15,7 @@ import pytest
 import torch
 
 from ganslate_b200 import _cabi
-from ganslate_b200._cabi import ACT_LEAKY, ACT_NONE, ACT_RELU
+from ganslate_b200._cabi import ACT_LEAKY, ACT_NONE, ACT_PRELU, ACT_RELU
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -74,8 +74,9 @@ def test_v2_thread_body_matches_the_abi_restatement(emul, case):
 
 def _check(case, run):
     import fake_cabi
-    N, D, H, W, Cc, gpad, act, res, cap, U, xb, c_slice = case
-    torch.manual_seed(hash(case) % 1000)
+    N, D, H, W, Cc, gpad, act, res, cap, U, xb, c_slice = case[:12]
+    gen = case[12] if len(case) > 12 else {}
+    torch.manual_seed(sum(int(v) for v in case[:12]) % 1000)
     Ctot = Cc + 16 if c_slice else Cc
     c0 = 8 if c_slice else 0
     x_t = (torch.randn(N, D, H + 2 * xb, W + 2 * xb, Ctot) * 1.5 + 0.7).to(torch.bfloat16)
@@ -84,10 +85,12 @@ def _check(case, run):
     xi = x_t[:, :, xb:xb + H, xb:xb + W, c0:c0 + Cc].float()
     stats = torch.stack([xi.sum(dim=(1, 2, 3)), (xi * xi).sum(dim=(1, 2, 3))], dim=-1).contiguous()
     slope = 0.2 if act == ACT_LEAKY else 0.0
-    ns = {ACT_NONE: 1.0, ACT_RELU: 0.0, ACT_LEAKY: slope}[act]
+    ns = {ACT_NONE: 1.0, ACT_RELU: 0.0, ACT_LEAKY: slope, ACT_PRELU: 0.0}[act]
     sum0 = torch.randn(N, D, H, W, Ctot) if res else None
+    prelu = (torch.rand(Cc) * 0.5 + 0.05) if act == ACT_PRELU else None
+    res_t = (torch.randn(N, D, H, W, Ctot) * 0.8).to(torch.bfloat16) if gen.get("rba") else None
 
-    def params(dx_t, dysum_t, bstats, dbias):
+    def params(dx_t, dysum_t, bstats, dbias, dprelu=None):
         p = _cabi.InBwdParams()
         p.x = xv
         p.dy_b = _view(dy_t, gpad, N, D, H, W, Cc, c0)
@@ -97,6 +100,14 @@ def _check(case, run):
             p.dy_sum_acc = 1
         p.stats, p.bstats, p.dbias = stats.data_ptr(), bstats.data_ptr(), dbias.data_ptr()
         p.eps, p.act, p.act_slope = 1e-5, act, slope
+        if prelu is not None:
+            p.prelu = prelu.data_ptr()
+            if dprelu is not None:
+                p.dprelu = dprelu.data_ptr()
+        if res_t is not None:
+            p.res = _view(res_t, 0, N, D, H, W, Cc, c0)
+            p.res_before_act = 1
+        p.out_scale = gen.get("oscale", 0.0)
         return p
 
     outs = []
@@ -105,13 +116,16 @@ def _check(case, run):
         dysum_t = sum0.clone() if res else None
         bstats = torch.zeros(N * Cc * 2 + 4)
         dbias = torch.zeros(Cc)
-        p = params(dx_t, dysum_t, bstats, dbias)
+        dprelu = torch.zeros(Cc) if gen.get("dprelu") else None
+        p = params(dx_t, dysum_t, bstats, dbias, dprelu)
         if which == "ref":
             assert fake_cabi.FakeLib().gb_in_bwd(p, None) == 0
         else:
             run(p, cap, U, ns)
-        outs.append((dx_t, dysum_t, dbias))
-    (dx_r, sum_r, db_r), (dx_v, sum_v, db_v) = outs
+        outs.append((dx_t, dysum_t, dbias, dprelu))
+    (dx_r, sum_r, db_r, dp_r), (dx_v, sum_v, db_v, dp_v) = outs
+    if dp_r is not None:
+        assert torch.allclose(dp_v, dp_r, rtol=1e-3, atol=1e-3 * max(1.0, dp_r.abs().max().item()))
     # dx: interior written everywhere (no NaN sentinel left), nothing outside the interior / channel slice touched
     inner = dx_v[:, :, xb:xb + H, xb:xb + W, c0:c0 + Cc].float()
     assert not torch.isnan(inner).any()
@@ -127,6 +141,25 @@ def _check(case, run):
     if res:
         assert torch.allclose(sum_v, sum_r, rtol=1e-5, atol=1e-5)
         assert torch.equal(sum_v[..., :c0], sum0[..., :c0]) and torch.equal(sum_v[..., c0 + Cc:], sum0[..., c0 + Cc:])
+
+
+# the general form of the second generation (V-Net layers): U = 12 selects it in the emulator
+CASES_GEN = [
+    (2, 3, 6, 7, 16, 0, ACT_PRELU, False, 9, 12, 0, False, dict(dprelu=True)),                   # PReLU + its gradient
+    (1, 2, 9, 8, 32, 0, ACT_PRELU, True, 5, 12, 0, False, dict(dprelu=True, rba=True)),          # V-Net: act(IN(x) + res)
+    (2, 1, 8, 9, 24, 1, ACT_RELU, True, 6, 12, 1, False, dict(rba=True)),                        # masked residual gradient, 2-D fold
+    (1, 4, 5, 5, 16, 0, ACT_PRELU, True, 7, 12, 0, True, dict(oscale=-1.0, dprelu=True)),        # inverse coupling: -act(IN(x)) + res
+    (3, 1, 7, 6, 8, 0, ACT_NONE, False, 4, 12, 0, False, dict(oscale=0.5)),
+    (2, 1, 12, 10, 64, 1, ACT_LEAKY, True, 7, 12, 0, False, dict()),                             # the plain cases through the general form
+]
+
+
+@pytest.mark.parametrize("case", CASES_GEN, ids=_ids(CASES_GEN))
+def test_v2_general_form_matches_the_abi_restatement(emul, case):
+    def run(p, cap, U, ns):
+        grid = (C.c_int * 2)()
+        assert emul.in_bwd_v2_emulate(C.byref(p), cap, U, ns, grid) == 0
+    _check(case, run)
 
 
 # the on-chip kernel (instnorm_v3_core.h): clusters of K CTAs own (image, 32 channels); `cap` is the SM count here

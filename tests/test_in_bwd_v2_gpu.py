@@ -24,7 +24,7 @@ import ctypes as C, json, sys
 sys.path.insert(0, {here!r})
 import torch
 from ganslate_b200 import _cabi, ops
-from ganslate_b200._cabi import ACT_LEAKY, ACT_NONE, ACT_RELU
+from ganslate_b200._cabi import ACT_LEAKY, ACT_NONE, ACT_PRELU, ACT_RELU
 lib = _cabi.lib()
 variant_knobs = {{int(k): v for k, v in json.loads(sys.argv[1]).items()}}
 counter = 25 if 24 in variant_knobs else 23
@@ -35,14 +35,26 @@ CASES = [(2, 1, 12, 10, 64, 1, ACT_RELU, False), (1, 1, 9, 7, 8, 0, ACT_LEAKY, F
          (8, 1, 64, 64, 256, 1, ACT_RELU, False), (8, 1, 64, 64, 256, 1, ACT_NONE, True), (4, 1, 128, 128, 64, 3, ACT_RELU, False),
          (2, 1, 31, 31, 512, 0, ACT_LEAKY, False), (600, 1, 7, 7, 16, 1, ACT_RELU, False),
          (1, 1, 90, 91, 32, 1, ACT_LEAKY, False), (8, 1, 32, 32, 256, 0, ACT_LEAKY, False), (2, 1, 64, 64, 128, 0, ACT_LEAKY, True)]
+# the general form of the second generation (V-Net layers): (prelu gradient, residual before the activation, out_scale)
+GEN = {{}}
+if counter == 23:
+    for case, gen in [((2, 8, 16, 16, 16, 0, ACT_PRELU, False), (True, False, 0.0)), ((1, 4, 32, 32, 32, 0, ACT_PRELU, True), (True, True, 0.0)),
+                      ((2, 1, 24, 20, 64, 1, ACT_RELU, True), (False, True, 0.0)), ((1, 6, 12, 12, 16, 0, ACT_PRELU, True), (True, False, -1.0)),
+                      ((1, 16, 64, 64, 32, 0, ACT_PRELU, True), (True, True, 0.0))]:
+        CASES.append(case)
+        GEN[case] = gen
 bad = 0
-for (N, D, H, W, Cc, gp, act, res) in CASES:
+for case in CASES:
+    (N, D, H, W, Cc, gp, act, res) = case
+    want_dprelu, rba, oscale = GEN.get(case, (False, False, 0.0))
     torch.manual_seed(N * 1000 + Cc)
     x = (torch.randn(N, D, H, W, Cc, device=dev) * 1.5 + 0.7).to(torch.bfloat16)
     dy = torch.randn(N, D, H + 2 * gp, W + 2 * gp, Cc, device=dev)
     xf = x.float()
     stats = torch.stack([xf.sum(dim=(1, 2, 3)), (xf * xf).sum(dim=(1, 2, 3))], dim=-1).contiguous()
     sum0 = torch.randn(N, D, H, W, Cc, device=dev)
+    prelu = (torch.rand(Cc, device=dev) * 0.5 + 0.05) if act == ACT_PRELU else None
+    res_t = (torch.randn(N, D, H, W, Cc, device=dev) * 0.8).to(torch.bfloat16) if rba else None
     outs = []
     for knobs in ({{7: 1, 22: 0, 6: 0, 24: 0}}, {{7: 0, 22: 0, 6: 0, 24: 0}}, {{**{{7: 0, 22: 0, 6: 0, 24: 0}}, **variant_knobs}}):
         for k, v in knobs.items():
@@ -58,9 +70,17 @@ for (N, D, H, W, Cc, gp, act, res) in CASES:
             p.dy_sum, p.dy_sum_acc = ops.make_view(dsum), 1
         p.stats, p.bstats, p.dbias = stats.data_ptr(), bstats.data_ptr(), dbias.data_ptr()
         p.eps, p.act, p.act_slope = 1e-5, act, 0.2 if act == ACT_LEAKY else 0.0
+        dprelu = torch.zeros(Cc, device=dev)
+        if prelu is not None:
+            p.prelu = prelu.data_ptr()
+            if want_dprelu:
+                p.dprelu = dprelu.data_ptr()
+        if res_t is not None:
+            p.res, p.res_before_act = ops.make_view(res_t), 1
+        p.out_scale = oscale
         _cabi.check(lib.gb_in_bwd(C.byref(p), torch.cuda.current_stream().cuda_stream), "gb_in_bwd")
         torch.cuda.synchronize()
-        outs.append((dx.float(), dbias, dsum, lib.gb_debug_knob(counter, 0)))
+        outs.append((dx.float(), dbias, dsum, lib.gb_debug_knob(counter, 0), dprelu))
     ref, gen1, gen2 = outs
     scale = ref[0].abs().max().item()
     e1 = (gen1[0] - ref[0]).abs().max().item() / scale
@@ -70,6 +90,7 @@ for (N, D, H, W, Cc, gp, act, res) in CASES:
     ok = ok and (not res or torch.allclose(gen2[2], ref[2], rtol=1e-5, atol=1e-5))
     eligible = counter == 23 or (Cc % 32 == 0 and D * H * W <= 8192)   # the on-chip kernel declines the rest
     ok = ok and gen2[3] == (1 if eligible else 0) and gen1[3] == 0
+    ok = ok and torch.allclose(gen2[4], ref[4], rtol=2e-3, atol=2e-3 * max(1.0, ref[4].abs().max().item()))
     print(("OK  " if ok else "FAIL"), (N, D, H, W, Cc, gp, act, res), "rel dx err gen1 %.2e gen2 %.2e served %d" % (e1, e2, gen2[3]))
     bad += 0 if ok else 1
 print("RESULT", json.dumps(dict(bad=bad)))
