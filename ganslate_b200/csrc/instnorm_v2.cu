@@ -144,7 +144,44 @@ int launch(const gb_in_bwd_params& p, float neg_slope, cudaStream_t st) {
   return 0;
 }
 
+template <int U, bool GEN>
+__global__ void __launch_bounds__(THREADS, GEN ? 2 : 3)  // the general form keeps PReLU slopes + a residual vector per pixel
+in_fwd_v2_kernel(const __grid_constant__ gb_in_fwd_params p, const __grid_constant__ Geom g, float neg_slope) {
+  gb_pdl_enter();
+  gbv2::fwd_pass<U, GEN>(p, g, neg_slope, threadIdx.x, blockIdx.x, blockIdx.y);
+}
+
 }  // namespace
+
+// Forward, opt-in (gb_debug_knob(26, 1)): -1 = not covered, 0 = launched
+int gb_in_fwd_fast_v2(const gb_in_fwd_params& p, cudaStream_t st) {
+  if (g_gb_knobs[26] != 1) return -1;
+  float ns;
+  switch (p.act) {
+    case GB_ACT_NONE: ns = 1.f; break;
+    case GB_ACT_RELU: ns = 0.f; break;
+    case GB_ACT_LEAKY: ns = p.act_slope; break;
+    case GB_ACT_PRELU: ns = 0.f; break;
+    default: return -1;
+  }
+  if (p.act == GB_ACT_PRELU && p.prelu == nullptr) return -1;
+  const gb_view& x = p.x;
+  const bool has_res = p.res.ptr != nullptr;
+  const bool gen = p.act == GB_ACT_PRELU || (has_res && p.res_before_act != 0) || (p.out_scale != 0.f && p.out_scale != 1.f);
+  if (x.C % 8 != 0 || x.C / 8 > THREADS || (int64_t)x.D * x.H * x.W >= (1ll << 31) || x.N > 65535) return -1;
+  if (!aligned(x, 2, 8) || !aligned(p.y, 2, 8) || (has_res && !aligned(p.res, 2, 8))) return -1;
+  if (p.stats != nullptr && (uintptr_t)p.stats % 16 != 0) return -1;
+  if (!row_addressable(x) || !row_addressable(p.y) || (has_res && !row_addressable(p.res))) return -1;
+  if (!small_offsets(x) || !small_offsets(p.y) || (has_res && !small_offsets(p.res))) return -1;
+  if (p.y.pad > 0 && (p.y.D != 1 || p.y.H <= 2 * p.y.pad + 1 || p.y.W <= 2 * p.y.pad + 1)) return -1;
+  bool fits = false;
+  const Geom g = gbv2::plan(x.N, x.D, x.H, x.W, x.C, num_sms() * (gen ? 2 : 3), &fits);
+  const dim3 grid(g.nblocks, x.N);
+  if (gen) gb_klaunch(in_fwd_v2_kernel<4, true>, grid, THREADS, 0, st, p, g, ns);
+  else gb_klaunch(in_fwd_v2_kernel<4, false>, grid, THREADS, 0, st, p, g, ns);
+  GB_LAUNCH_CHECK();
+  return 0;
+}
 
 // -1: not covered (caller falls back to the first-generation / general kernels), 0: launched, > 0: error
 int gb_in_bwd_fast_v2(const gb_in_bwd_params& p, cudaStream_t st) {

@@ -329,3 +329,120 @@ V2_HD void stream_pass(const gb_in_bwd_params& p, const Geom& g, float neg_slope
 }
 
 }  // namespace gbv2
+
+// ------------------------------------------------------------------------------------------------ forward
+// y = [out_scale *] act(xhat [+ res]) [+ res] incl. the reflection border of y (y.pad > 0, 2-D): same walk as the
+// backward (row segments, 8 channels per thread, U pixels in flight).  GEN: PReLU slopes, residual before the
+// activation, scaled output -- the V-Net forms, which the first-generation fast kernel leaves to the general one.
+namespace gbv2 {
+
+V2_HD void st_bf16x8(uint16_t* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+template <int U, bool GEN>
+V2_HD void fwd_pass(const gb_in_fwd_params& p, const Geom& g, float neg_slope, int tid, int bx, int n) {
+  const gb_view& x = p.x;
+  const gb_view& yv = p.y;
+  const int C8 = x.C >> 3;
+  const int slots = THREADS / C8;
+  const int cgp = tid % C8;
+  const int slot = tid / C8;
+  if (slot >= slots) return;
+  const int c = cgp * 8;
+  const int W = x.W;
+  const uint32_t P = (uint32_t)x.D * (uint32_t)x.H * (uint32_t)x.W;
+  const uint32_t p0 = (uint32_t)bx * (uint32_t)g.ppb;
+  const uint32_t p1 = (p0 + (uint32_t)g.ppb < P) ? p0 + (uint32_t)g.ppb : P;
+  if (p0 >= p1) return;
+  float a[8], b[8], ns[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    a[e] = 1.f;
+    b[e] = 0.f;
+    ns[e] = (GEN && p.prelu != nullptr) ? p.prelu[c + e] : neg_slope;
+  }
+  if (p.stats != nullptr) {
+    const float invP = 1.f / (float)P;
+    const float* sp = p.stats + ((int64_t)n * x.C + c) * 2;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float4 s = *reinterpret_cast<const float4*>(sp + 4 * h);
+      const float m0 = s.x * invP, m1 = s.z * invP;
+      const float v0 = s.y * invP - m0 * m0, v1 = s.w * invP - m1 * m1;
+      const float r0 = rsqrt_((v0 > 0.f ? v0 : 0.f) + p.eps), r1 = rsqrt_((v1 > 0.f ? v1 : 0.f) + p.eps);
+      a[2 * h] = r0;
+      a[2 * h + 1] = r1;
+      b[2 * h] = -m0 * r0;
+      b[2 * h + 1] = -m1 * r1;
+    }
+  }
+  const bool has_res = p.res.ptr != nullptr;
+  const bool rba = GEN && has_res && p.res_before_act != 0;
+  const float oscale = (GEN && p.out_scale != 0.f) ? p.out_scale : 1.f;
+  const uint16_t* xb = reinterpret_cast<const uint16_t*>(x.ptr) + (int64_t)n * x.sn + c;
+  const uint16_t* rb = has_res ? reinterpret_cast<const uint16_t*>(p.res.ptr) + (int64_t)n * p.res.sn + c : nullptr;
+  uint16_t* yb = reinterpret_cast<uint16_t*>(yv.ptr) + (int64_t)n * yv.sn + c;
+  const int ypad = yv.pad;
+  const int xsx = (int)x.sx, ysx = (int)yv.sx, ysy = (int)yv.sy, rsx = has_res ? (int)p.res.sx : 0;
+
+  int y = (int)(p0 / (uint32_t)W);
+  int xa = (int)(p0 - (uint32_t)y * (uint32_t)W);
+  uint32_t pix = p0;
+  while (pix < p1) {
+    const int left = (int)(p1 - pix);
+    const int seg = left < W - xa ? left : W - xa;
+    const int xe = xa + seg;
+    const int my = ypad > 0 ? mirror_of(y, yv.H, ypad) : NO_MIRROR;
+    const int ox = y * (int)x.sy, oy = y * ysy, orr = has_res ? y * (int)p.res.sy : 0;
+    for (int px = xa + slot; px < xe; px += slots * U) {
+      uint4 xv[U], rv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pxu = px + u * slots;
+        if (pxu < xe) {
+          xv[u] = ld_bf16x8(xb + ox + pxu * xsx);
+          if (has_res) rv[u] = ld_bf16x8(rb + orr + pxu * rsx);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pxu = px + u * slots;
+        if (pxu < xe) {
+          float f[8], r[8];
+          unpack8(xv[u], f);
+          if (has_res) unpack8(rv[u], r);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float v = fma_(f[e], a[e], b[e]);
+            if (rba) v += r[e];
+            v = v > 0.f ? v : v * ns[e];
+            if (GEN) v *= oscale;
+            if (has_res && !rba) v += r[e];
+            f[e] = v;
+          }
+          uint4 o;
+          o.x = pack2(f[0], f[1]);
+          o.y = pack2(f[2], f[3]);
+          o.z = pack2(f[4], f[5]);
+          o.w = pack2(f[6], f[7]);
+          st_bf16x8(yb + oy + pxu * ysx, o);
+          if (ypad > 0) {
+            const bool col_edge = (unsigned)(pxu - 1) < (unsigned)ypad || (unsigned)(W - 2 - pxu) < (unsigned)ypad;
+            if (my != NO_MIRROR || col_edge) {
+              const int mx = col_edge ? mirror_of(pxu, W, ypad) : NO_MIRROR;
+              if (my != NO_MIRROR) st_bf16x8(yb + my * ysy + pxu * ysx, o);
+              if (mx != NO_MIRROR) {
+                st_bf16x8(yb + oy + mx * ysx, o);
+                if (my != NO_MIRROR) st_bf16x8(yb + my * ysy + mx * ysx, o);
+              }
+            }
+          }
+        }
+      }
+    }
+    pix += (uint32_t)seg;
+    ++y;
+    xa = 0;
+  }
+}
+
+}  // namespace gbv2

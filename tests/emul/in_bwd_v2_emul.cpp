@@ -49,3 +49,18 @@ extern "C" int in_bwd_v2_emulate(const gb_in_bwd_params* p, int cap, int U, floa
   }
   return 1;
 }
+
+// forward: every thread of every block through gbv2::fwd_pass; U + 10 = the general form
+extern "C" int in_fwd_v2_emulate(const gb_in_fwd_params* p, int cap, int U, float neg_slope) {
+  bool fits = false;
+  const gbv2::Geom g = gbv2::plan(p->x.N, p->x.D, p->x.H, p->x.W, p->x.C, cap, &fits);
+  for (int n = 0; n < p->x.N; ++n)
+    for (int bx = 0; bx < g.nblocks; ++bx)
+      for (int tid = 0; tid < gbv2::THREADS; ++tid) {
+        if (U == 4) gbv2::fwd_pass<4, false>(*p, g, neg_slope, tid, bx, n);
+        else if (U == 2) gbv2::fwd_pass<2, false>(*p, g, neg_slope, tid, bx, n);
+        else if (U == 14) gbv2::fwd_pass<4, true>(*p, g, neg_slope, tid, bx, n);
+        else return 1;
+      }
+  return 0;
+}

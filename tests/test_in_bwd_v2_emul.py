@@ -32,6 +32,8 @@ def emul(tmp_path_factory):
     for fn in (lib.in_bwd_v2_emulate, lib.in_bwd_v3_emulate):
         fn.argtypes = [C.POINTER(_cabi.InBwdParams), C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int)]
         fn.restype = C.c_int
+    lib.in_fwd_v2_emulate.argtypes = [C.POINTER(_cabi.InFwdParams), C.c_int, C.c_int, C.c_float]
+    lib.in_fwd_v2_emulate.restype = C.c_int
     return lib
 
 
@@ -209,3 +211,53 @@ def test_v2_plan_covers_every_pixel_once():
         ppb = max((P + nb - 1) // nb, 1)
         nblocks = (P + ppb - 1) // ppb
         assert nblocks <= nb and (nblocks - 1) * ppb < P <= nblocks * ppb
+
+
+# forward (gbv2::fwd_pass): N, D, H, W, C, y border, act, residual, cap, U (14 = general form), x border, options
+CASES_FWD = [
+    (2, 1, 12, 10, 64, 1, ACT_RELU, False, 7, 4, 0, {}),
+    (3, 1, 8, 8, 256, 1, ACT_NONE, True, 10, 2, 1, {}),                       # resblock tail: + residual, border for the next pad
+    (1, 1, 11, 13, 24, 3, ACT_LEAKY, False, 4, 4, 0, {}),                     # border 3 (the 7x7 output layer's input)
+    (2, 3, 5, 6, 16, 0, ACT_RELU, False, 9, 4, 0, {}),                        # 3-D
+    (1, 1, 9, 7, 8, 0, ACT_RELU, False, 5, 2, 0, dict(no_norm=True)),         # activation only (stats == NULL)
+    (2, 2, 6, 7, 16, 0, ACT_PRELU, False, 9, 14, 0, {}),                      # V-Net: PReLU
+    (1, 2, 9, 8, 32, 0, ACT_PRELU, True, 5, 14, 0, dict(rba=True)),           # V-Net: act(IN(x) + res)
+    (1, 4, 5, 5, 16, 0, ACT_PRELU, True, 7, 14, 0, dict(oscale=-1.0)),        # inverse coupling: res - act(IN(x))
+    (2, 1, 8, 9, 24, 2, ACT_RELU, True, 6, 14, 0, dict(rba=True)),            # general form with a 2-D border
+]
+
+
+@pytest.mark.parametrize("case", CASES_FWD, ids=[f"N{c[0]}D{c[1]}H{c[2]}W{c[3]}C{c[4]}p{c[5]}a{c[6]}r{int(c[7])}U{c[9]}" for c in CASES_FWD])
+def test_v2_forward_thread_body_matches_the_abi_restatement(emul, case):
+    import fake_cabi
+    N, D, H, W, Cc, ypad, act, res, cap, U, xb, opt = case
+    torch.manual_seed(sum(int(v) for v in case[:11]))
+    x_t = (torch.randn(N, D, H + 2 * xb, W + 2 * xb, Cc) * 1.5 + 0.7).to(torch.bfloat16)
+    xv = _view(x_t, xb, N, D, H, W, Cc)
+    xi = x_t[:, :, xb:xb + H, xb:xb + W].float()
+    stats = torch.stack([xi.sum(dim=(1, 2, 3)), (xi * xi).sum(dim=(1, 2, 3))], dim=-1).contiguous()
+    slope = 0.2 if act == ACT_LEAKY else 0.0
+    ns = {ACT_NONE: 1.0, ACT_RELU: 0.0, ACT_LEAKY: slope, ACT_PRELU: 0.0}[act]
+    prelu = (torch.rand(Cc) * 0.5 + 0.05) if act == ACT_PRELU else None
+    res_t = (torch.randn(N, D, H, W, Cc) * 0.8).to(torch.bfloat16) if res else None
+    outs = []
+    for which in ("ref", "v2"):
+        y_t = torch.full((N, D, H + 2 * ypad, W + 2 * ypad, Cc), float("nan")).to(torch.bfloat16)
+        p = _cabi.InFwdParams()
+        p.x, p.y = xv, _view(y_t, ypad, N, D, H, W, Cc)
+        if res_t is not None:
+            p.res = _view(res_t, 0, N, D, H, W, Cc)
+            p.res_before_act = 1 if opt.get("rba") else 0
+        p.stats = None if opt.get("no_norm") else stats.data_ptr()
+        p.prelu = prelu.data_ptr() if prelu is not None else None
+        p.eps, p.act, p.act_slope, p.out_scale = 1e-5, act, slope, opt.get("oscale", 0.0)
+        if which == "ref":
+            assert fake_cabi.FakeLib().gb_in_fwd(p, None) == 0
+        else:
+            assert emul.in_fwd_v2_emulate(C.byref(p), cap, U, ns) == 0
+        outs.append(y_t.float())
+    ref, got = outs
+    assert not torch.isnan(got).any()           # interior and the whole reflection border written
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() <= 2.0 ** -7 * scale     # one bf16 rounding of a differently associated value
+    assert (got - ref).abs().mean().item() <= 2.0 ** -10 * scale

@@ -112,3 +112,68 @@ def test_in_bwd_variant(knobs):
         pytest.fail(f"hung (killed after 300 s), output so far:\n{out[-3000:]}")
     print(res.stdout[-4000:])
     assert res.returncode == 0, res.stdout[-4000:] + "\n" + res.stderr[-3000:]
+
+
+FWD_DRIVER = r"""
+import ctypes as C, json, sys
+sys.path.insert(0, {here!r})
+import torch
+from ganslate_b200 import _cabi, ops
+from ganslate_b200._cabi import ACT_LEAKY, ACT_NONE, ACT_PRELU, ACT_RELU
+lib = _cabi.lib()
+dev = "cuda"
+# N, D, H, W, C, border of y, act, residual, (residual before the activation, out_scale, no normalisation)
+CASES = [(2, 1, 12, 10, 64, 1, ACT_RELU, False, (False, 0.0, False)), (3, 1, 8, 8, 256, 1, ACT_NONE, True, (False, 0.0, False)),
+         (1, 1, 11, 13, 24, 3, ACT_LEAKY, False, (False, 0.0, False)), (2, 3, 5, 6, 16, 0, ACT_RELU, False, (False, 0.0, False)),
+         (1, 1, 9, 7, 8, 0, ACT_RELU, False, (False, 0.0, True)), (8, 1, 64, 64, 256, 1, ACT_RELU, False, (False, 0.0, False)),
+         (8, 1, 64, 64, 256, 1, ACT_NONE, True, (False, 0.0, False)), (4, 1, 128, 128, 64, 3, ACT_RELU, False, (False, 0.0, False)),
+         (2, 2, 6, 7, 16, 0, ACT_PRELU, False, (False, 0.0, False)), (1, 2, 9, 8, 32, 0, ACT_PRELU, True, (True, 0.0, False)),
+         (1, 4, 5, 5, 16, 0, ACT_PRELU, True, (False, -1.0, False)), (1, 16, 64, 64, 32, 0, ACT_PRELU, True, (True, 0.0, False)),
+         (600, 1, 7, 7, 16, 1, ACT_RELU, False, (False, 0.0, False))]
+bad = 0
+for (N, D, H, W, Cc, yp, act, res, (rba, oscale, no_norm)) in CASES:
+    torch.manual_seed(N * 1000 + Cc)
+    x = (torch.randn(N, D, H, W, Cc, device=dev) * 1.5 + 0.7).to(torch.bfloat16)
+    xf = x.float()
+    stats = torch.stack([xf.sum(dim=(1, 2, 3)), (xf * xf).sum(dim=(1, 2, 3))], dim=-1).contiguous()
+    prelu = (torch.rand(Cc, device=dev) * 0.5 + 0.05) if act == ACT_PRELU else None
+    res_t = (torch.randn(N, D, H, W, Cc, device=dev) * 0.8).to(torch.bfloat16) if res else None
+    outs = []
+    for knobs in ({{7: 1, 26: 0}}, {{7: 0, 26: 1}}):
+        for k, v in knobs.items():
+            lib.gb_debug_knob(k, v)
+        lib.gb_debug_knob(27, 0)
+        y = torch.full((N, D, H + 2 * yp, W + 2 * yp, Cc), float("nan"), device=dev).to(torch.bfloat16)
+        p = _cabi.InFwdParams()
+        p.x, p.y = ops.make_view(x), ops.make_view(y, yp)
+        if res_t is not None:
+            p.res, p.res_before_act = ops.make_view(res_t), 1 if rba else 0
+        p.stats = None if no_norm else stats.data_ptr()
+        p.prelu = prelu.data_ptr() if prelu is not None else None
+        p.eps, p.act, p.act_slope, p.out_scale = 1e-5, act, 0.2 if act == ACT_LEAKY else 0.0, oscale
+        _cabi.check(lib.gb_in_fwd(C.byref(p), torch.cuda.current_stream().cuda_stream), "gb_in_fwd")
+        torch.cuda.synchronize()
+        outs.append((y.float(), lib.gb_debug_knob(27, 0)))
+    (ref, _), (got, served) = outs
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item() / scale
+    ok = (not torch.isnan(got).any().item()) and err <= 2.0 ** -7 and served == 1
+    print(("OK  " if ok else "FAIL"), (N, D, H, W, Cc, yp, act, res, rba, oscale, no_norm), "rel err %.2e served %d" % (err, served))
+    bad += 0 if ok else 1
+print("RESULT", json.dumps(dict(bad=bad)))
+sys.exit(1 if bad else 0)
+"""
+
+
+def test_in_fwd_v2():
+    """Second-generation forward (gb_debug_knob(26, 1)): plain and V-Net forms against the general kernel, incl. the
+    reflection border of the result."""
+    code = FWD_DRIVER.format(here=HERE)
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(HERE) + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    try:
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    except subprocess.TimeoutExpired as e:
+        out = e.stdout.decode(errors="replace") if isinstance(e.stdout, bytes) else (e.stdout or "")
+        pytest.fail(f"hung (killed after 300 s), output so far:\n{out[-3000:]}")
+    print(res.stdout[-4000:])
+    assert res.returncode == 0, res.stdout[-4000:] + "\n" + res.stderr[-3000:]

@@ -57,10 +57,10 @@ in2)
   tail -4 $out/pytest_in2_suite.log
   GB_KNOBS=22=1 timeout 900 python bench.py --batch $B --no-cpu-baseline --no-roofline > $out/bench_in2_b$B.json 2> $out/bench_in2_b$B.err
   tail -c 600 $out/bench_in2_b$B.json; tail -3 $out/bench_in2_b$B.err
-  # on-chip cluster kernel (knob 24) for maps of <= 8192 pixels, second generation for the rest
-  GB_KNOBS=24=1,22=1 timeout 1500 python -m pytest $CORE -m gpu -q -x > $out/pytest_in3_suite.log 2>&1; echo "pytest exit $?" >> $out/pytest_in3_suite.log
+  # on-chip cluster kernel (knob 24) for maps of <= 8192 pixels, second generation backward (22) and forward (26) for the rest
+  GB_KNOBS=24=1,22=1,26=1 timeout 1500 python -m pytest $CORE -m gpu -q -x > $out/pytest_in3_suite.log 2>&1; echo "pytest exit $?" >> $out/pytest_in3_suite.log
   tail -4 $out/pytest_in3_suite.log
-  GB_KNOBS=24=1,22=1 timeout 900 python bench.py --batch $B --no-cpu-baseline > $out/bench_in3_b$B.json 2> $out/bench_in3_b$B.err
+  GB_KNOBS=24=1,22=1,26=1 timeout 900 python bench.py --batch $B --no-cpu-baseline > $out/bench_in3_b$B.json 2> $out/bench_in3_b$B.err
   tail -c 2500 $out/bench_in3_b$B.json; tail -3 $out/bench_in3_b$B.err ;;
 shapes)
   # throughput of every BASELINE.json configuration (one short bench line each; not the headline number)
