@@ -120,5 +120,66 @@ def main():
             lib.gb_debug_knob(k, 0)
 
 
+def fwd_table(B):
+    """Forward: first-generation fast kernel against the second generation (knob 26); 4 B per element algorithmic
+    (+ 2 B residual, + the border of the result)."""
+    lib = _cabi.lib()
+    shapes = [("G c7 / u2   64ch 256x256 relu", 64, 256, 256, ACT_RELU, 0, False), ("G u2->out   64ch 256x256 relu border3", 64, 256, 256, ACT_RELU, 3, False),
+              ("G d1 / u1  128ch 128x128 relu", 128, 128, 128, ACT_RELU, 0, False), ("G resblock 256ch 64x64 relu border1", 256, 64, 64, ACT_RELU, 1, False),
+              ("G resblock 256ch 64x64 none border1 +res", 256, 64, 64, ACT_NONE, 1, True), ("D l2       128ch 64x64 leaky", 128, 64, 64, ACT_LEAKY, 0, False)]
+    print(f"\n{'forward layer':44s} {'variant':10s} {'cold us':>9s} {'GB/s':>8s} {'hot us':>9s} {'GB/s':>8s}  {'max|dy|':>9s} served-by-gen2")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for name, Cc, H, W, act, yp, res in shapes:
+        x = (torch.randn(B, 1, H, W, Cc, device=dev) * 1.3 + 0.4).to(torch.bfloat16)
+        xf = x.float()
+        stats = torch.stack([xf.sum(dim=(1, 2, 3)), (xf * xf).sum(dim=(1, 2, 3))], dim=-1).contiguous()
+        r = torch.randn(B, 1, H, W, Cc, device=dev).to(torch.bfloat16) if res else None
+        y = torch.empty(B, 1, H + 2 * yp, W + 2 * yp, Cc, device=dev, dtype=torch.bfloat16)
+        nbytes = x.numel() * 2 * (3 if res else 2)
+
+        def launch():
+            p = _cabi.InFwdParams()
+            p.x, p.y = ops.make_view(x), ops.make_view(y, yp)
+            if res:
+                p.res = ops.make_view(r)
+            p.stats, p.eps, p.act, p.act_slope = stats.data_ptr(), 1e-5, act, 0.2 if act == ACT_LEAKY else 0.0
+            _cabi.check(lib.gb_in_fwd(C.byref(p), torch.cuda.current_stream().cuda_stream), "gb_in_fwd")
+
+        ref = None
+        for vname, k26 in (("gen1", 0), ("gen2", 1)):
+            lib.gb_debug_knob(26, k26)
+            lib.gb_debug_knob(27, 0)
+            y.fill_(float("nan"))
+            launch()
+            torch.cuda.synchronize()
+            served = lib.gb_debug_knob(27, 0)
+            got = y.float().clone()
+            err = 0.0 if ref is None else (got - ref).abs().max().item() / ref.abs().max().item()
+            if ref is None:
+                ref = got
+            elif not (err <= 2.0 ** -7):
+                print(f"MISMATCH forward {name} {vname}: {err:.3e}")
+            ts = {}
+            for cold in (True, False):
+                t = []
+                for i in range(23):
+                    if cold:
+                        flush.zero_()
+                    else:
+                        x.mul_(1.0)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    launch()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    if i >= 3:
+                        t.append(e0.elapsed_time(e1) * 1e3)
+                t.sort()
+                ts[cold] = t[len(t) // 2]
+            print(f"{name:44s} {vname:10s} {ts[True]:9.1f} {nbytes / ts[True] / 1e3:8.0f} {ts[False]:9.1f} {nbytes / ts[False] / 1e3:8.0f}  {err:9.2e} {served}")
+        lib.gb_debug_knob(26, 0)
+
+
 if __name__ == "__main__":
     main()
+    fwd_table(int(sys.argv[1]) if len(sys.argv) > 1 else 8)
