@@ -248,13 +248,13 @@ def run_b200(args):
     for _ in range(n_warm):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # one poller: rank 0's GPU is the one reported
     l0 = lib.gb_launch_count()
     barrier()
     t = timed(args.steps, True)
     barrier()
     launches = lib.gb_launch_count() - l0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler is not None else None
     if getattr(model, "graph_launches_per_step", None):
         launches = model.graph_launches_per_step * args.steps
     # e2e: host buffers in, loss scalar out
