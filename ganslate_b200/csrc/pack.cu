@@ -106,6 +106,9 @@ __global__ void colsum_kernel(gb_view x, float* __restrict__ out, int pix_per_bl
 
 }  // namespace
 
+int gb_pack_weights_multi_v2(const gb_pack_params* table_dev, int count, int64_t max_elems, cudaStream_t st);  // pack_v2.cu
+int gb_unpack_wgrad_multi_v2(const gb_unpack_batch* b, int64_t max_total, cudaStream_t st);                       // (knob 28)
+
 extern "C" int gb_pack_weights(const gb_pack_params* pp, void* stream) {
   const gb_pack_params& p = *pp;
   GB_CHECK(p.src && p.dst, "gb_pack_weights: null pointer");
@@ -126,6 +129,10 @@ extern "C" int gb_pack_weights(const gb_pack_params* pp, void* stream) {
 
 extern "C" int gb_pack_weights_multi(const gb_pack_params* table_dev, int count, int64_t max_elems, void* stream) {
   GB_CHECK(table_dev && count >= 1 && count <= 65535, "gb_pack_weights_multi: bad table (%d entries)", count);
+  if (g_gb_knobs[28] != 0) {
+    const int r = gb_pack_weights_multi_v2(table_dev, count, max_elems, (cudaStream_t)stream);
+    if (r >= 0) return r;
+  }
   int blocks = (int)((max_elems + 1023) / 1024);
   if (blocks > 592) blocks = 592;
   if (blocks < 1) blocks = 1;
@@ -142,6 +149,10 @@ extern "C" int gb_unpack_wgrad_multi(const gb_unpack_batch* b, void* stream) {
     GB_CHECK(it.dw && it.dst, "gb_unpack_wgrad_multi: null pointer in item %d", i);
     const int64_t total = (int64_t)it.rows * it.chans * it.ntaps;
     mx = total > mx ? total : mx;
+  }
+  if (g_gb_knobs[28] != 0) {
+    const int r = gb_unpack_wgrad_multi_v2(b, mx, (cudaStream_t)stream);
+    if (r >= 0) return r;
   }
   int blocks = (int)((mx + 1023) / 1024);
   if (blocks > 592) blocks = 592;

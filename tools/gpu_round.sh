@@ -44,6 +44,18 @@ exp)
   tail -4 $out/pytest_direct.log
   GB_DIRECT_PARAM_GRAD=1 timeout 900 python bench.py --batch $B --no-cpu-baseline --no-roofline > $out/bench_direct_b$B.json 2> $out/bench_direct_b$B.err
   tail -c 600 $out/bench_direct_b$B.json; tail -3 $out/bench_direct_b$B.err
+  # second-generation weight pack / weight-gradient unpack (32-bit index math, 16-byte stores)
+  GB_KNOBS=28=1 timeout 1500 python -m pytest $CORE -m gpu -q -x > $out/pytest_pack2.log 2>&1; echo "pytest exit $?" >> $out/pytest_pack2.log
+  tail -4 $out/pytest_pack2.log
+  GB_KNOBS=28=1 timeout 900 python bench.py --batch $B --no-cpu-baseline > $out/bench_pack2_b$B.json 2> $out/bench_pack2_b$B.err
+  python - "$out/bench_pack2_b$B.json" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print("pack2:", round(d["value"], 1), d["unit"], {k: (v["avg_us"], v["launches_per_step"]) for k, v in d.get("roofline_detail", {}).items() if k in ("pack", "unpack")})
+except Exception as e:
+    print("no bench line:", e)
+PY
   # e2e leg with input prefetch on a copy stream and lagged loss read-back (train.input_prefetch)
   timeout 900 python bench.py --batch $B --e2e-pipeline --no-cpu-baseline --no-roofline > $out/bench_e2epipe_b$B.json 2> $out/bench_e2epipe_b$B.err
   tail -c 700 $out/bench_e2epipe_b$B.json; tail -3 $out/bench_e2epipe_b$B.err ;;
