@@ -116,4 +116,5 @@ full)
   done ;;
 esac
 done
+python tools/summarize_round.py $out > $out/SUMMARY.txt 2>&1; cat $out/SUMMARY.txt
 du -sh gpurun_out
