@@ -90,3 +90,88 @@ def test_gloo_world2_helpers_and_ddp_average():
     assert all(r[4] < 1e-6 for r in res)               # DDP average == single-process mean
     assert all(r[5] == 0.0 for r in res)               # FlatGradSync: parameters are rank 0's after the broadcast
     assert all(r[6] < 1e-6 and r[7] for r in res)      # flat-bucket average == single-process mean
+
+
+def _graph_path_worker(rank, world, port, q):
+    """The data-parallel CUDA-graph code path of CycleGAN.optimize_parameters (explicit flat-bucket all-reduces between
+    the captured segments) on two gloo ranks through the pointer-level CPU restatement of the ABI; the capture itself
+    is replaced by a direct call.  Each rank trains on its own batch; the gradients it ends up with must be the mean of
+    the two single-rank gradients, and the optimizers must step in the reference's order."""
+    import contextlib
+    import random
+    import sys
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import fake_cabi
+    from ganslate_b200 import _cabi, ops
+    from ganslate_b200.nn.gans import base
+    from ganslate_b200.presets import cyclegan_resnet2d
+    from ganslate_b200.utils import communication as comm
+    from ganslate_b200.utils.builders import build_gan
+    from oracle import torch_oracle as O
+
+    class MP:  # monkeypatch stand-in (the process ends with the test)
+        def setattr(self, o, n, v, raising=True):
+            setattr(o, n, v)
+
+    fake_cabi.install(MP())
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // world))
+    base.BaseGAN._specify_device = lambda self: torch.device("cpu")
+    base.BaseGAN.eager_stream = lambda self: contextlib.nullcontext()
+    comm.init_distributed()
+
+    def run(distributed, batch_seed, mode):
+        random.seed(0)
+        torch.manual_seed(0)
+        if not distributed:  # single-rank reference: no gradient sync objects are created
+            saved = dist.is_initialized
+            torch.distributed.is_initialized = lambda: False
+        try:
+            gan = build_gan(cyclegan_resnet2d(batch_size=1, n_residual_blocks=1, cuda_graph=True,
+                                              cuda_graph_warmup=0 if mode == "segments" else 100))
+        finally:
+            if not distributed:
+                torch.distributed.is_initialized = saved
+        order = []
+        for name, o in gan.optimizers.items():
+            o.step = lambda *a, _n=name, **k: order.append(_n)
+        if mode == "segments":
+            gan.run_graphed = lambda name, fn: fn()
+        a, b = O.synthetic_batch(1, 3, 48, seed=batch_seed)
+        gan.set_input({"A": a, "B": b})
+        gan.optimize_parameters()
+        grads = {(n, k): p.grad.clone() for n, net in gan.networks.items() for k, p in net.named_parameters()}
+        return grads, order, gan.grad_syncs is not None
+
+    singles = [run(False, 10 + r, "eager")[0] for r in range(world)]  # (the unsynchronised iteration is the same in both modes)
+    assert any(not torch.equal(singles[0][k], singles[1][k]) for k in singles[0])  # the ranks really see different data
+    out = {}
+    for mode in ("eager", "segments"):
+        synced, order, has_sync = run(True, 10 + rank, mode)
+        assert has_sync and order == ["G", "D"], (order, has_sync)
+        err = 0.0
+        for key, g in synced.items():
+            ref = sum(s[key] for s in singles) / world
+            err = max(err, float((g - ref).abs().max()) / max(1e-12, float(ref.abs().max())))
+        out[mode] = err
+    q.put((rank, out["eager"], out["segments"]))
+    comm.synchronize()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_gloo_world2_cyclegan_graph_path_averages_gradients():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_graph_path_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=500) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, e_eager, e_seg in res:
+        assert e_eager < 1e-5 and e_seg < 1e-5, res
