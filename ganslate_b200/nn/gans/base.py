@@ -37,6 +37,9 @@ class TrainingMetricsLite:
 
 
 class BaseGAN(ABC):
+    # True for recipes whose optimize_parameters() drives `self.grad_syncs` (explicit gradient all-reduce between the
+    # CUDA-graph segments); for the others data parallelism + train.cuda_graph falls back to eager DDP
+    graph_sync = False
 
     def __init__(self, conf):
         self.logger = logging.getLogger("ganslate_b200")
@@ -225,6 +228,10 @@ class BaseGAN(ABC):
     def parallelize_networks(self):
         """base.py:172-189: one DistributedDataParallel wrapper per network, broadcast_buffers=False; the
         bucketed NCCL all-reduce of the gradients overlaps with the rest of backward."""
+        if torch.distributed.is_initialized() and self.use_cuda_graph and not self.graph_sync:
+            self.logger.warning("%s does not synchronise gradients between CUDA-graph segments: train.cuda_graph is "
+                                "switched off for the data-parallel run (eager DistributedDataParallel)", type(self).__name__)
+            self.use_cuda_graph = False
         if torch.distributed.is_initialized() and self.use_cuda_graph:
             # graph-replayed steps: explicit flat-bucket all-reduce per optimizer group instead of DDP's hooks
             # (utils/grad_sync.py); same semantics -- rank-0 parameters at start, gradients averaged over ranks

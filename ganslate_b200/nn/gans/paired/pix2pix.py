@@ -43,26 +43,59 @@ class Pix2PixConditionalGAN(BaseGAN):
         self.visuals['real_A'] = self.stage_input('real_A', input['A'])
         self.visuals['real_B'] = self.stage_input('real_B', input['B'])
 
+    graph_sync = True  # optimize_parameters issues the flat-bucket all-reduces itself (BaseGAN.parallelize_networks)
+
     def optimize_parameters(self):
+        """One iteration in the reference's order (pix2pix.py:76-101).  Data parallel + CUDA graphs: DDP's hooks are not
+        captured, so the gradients are averaged explicitly between the segments, as in CycleGAN: the discriminator
+        phase reads neither the generator's weights nor anything produced after `forward()`, so it runs while the
+        generator bucket is being reduced and both optimizers step afterwards -- same result as the reference order."""
+        sync = self.grad_syncs
+        if sync is None:
+            if self.graph_mode('step'):
+                self.run_graphed('step', self._step)
+                return
+            with self.eager_stream():
+                self._step()
+            return
         if self.graph_mode('step'):
-            self.run_graphed('step', self._step)
+            self.run_graphed('G', self._phase_G)
+            sync['G'].launch()
+            self.run_graphed('D', self._phase_D)
+            sync['D'].launch()
+            sync['G'].finish()
+            self.run_graphed('stepG', self.optimizers['G'].step)
+            sync['D'].finish()
+            self.run_graphed('stepD', self.optimizers['D'].step)
             return
         with self.eager_stream():
-            self._step()
+            self._phase_G()
+            sync['G'].launch()
+            self._phase_D()
+            sync['D'].launch()
+            sync['G'].finish()
+            self.optimizers['G'].step()
+            sync['D'].finish()
+            self.optimizers['D'].step()
 
-    def _step(self):
+    def _phase_G(self):
         self.forward()
         self.metrics.update(self.training_metrics.compute_metrics_G(self.visuals))
         # ---- G (D frozen: its weight-gradient kernels are skipped)
         self.set_requires_grad(self.networks['D'], False)
         self.optimizers['G'].zero_grad(set_to_none=True)
         self.backward_G()
-        self.optimizers['G'].step()
-        # ---- D
+
+    def _phase_D(self):
         self.set_requires_grad(self.networks['D'], True)
         self.optimizers['D'].zero_grad(set_to_none=True)
         self.backward_D()
         self.metrics.update(self.training_metrics.compute_metrics_D('D', self.pred_real, self.pred_fake))
+
+    def _step(self):
+        self._phase_G()
+        self.optimizers['G'].step()
+        self._phase_D()
         self.optimizers['D'].step()
 
     def backward_G(self):

@@ -77,6 +77,8 @@ class CUT(BaseGAN):
     def save_checkpoint(self, iter_idx):
         super().save_checkpoint(iter_idx)  # the reference drops the mlp optimizer as well (base.py:244-245)
 
+    graph_sync = True  # optimize_parameters issues the flat-bucket all-reduces itself (BaseGAN.parallelize_networks)
+
     def optimize_parameters(self):
         """One iteration in the reference's order (cut.py:113-137).  With `train.cuda_graph` the two phases (forward + D
         step, G + patch-MLP step) are captured once and replayed; the discriminator is stepped BEFORE the second phase

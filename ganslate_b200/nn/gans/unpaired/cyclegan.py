@@ -55,6 +55,8 @@ class CycleGAN(BaseGAN):
         self.visuals['real_A'] = self.stage_input('real_A', input['A'])
         self.visuals['real_B'] = self.stage_input('real_B', input['B'])
 
+    graph_sync = True  # optimize_parameters issues the flat-bucket all-reduces itself (BaseGAN.parallelize_networks)
+
     def optimize_parameters(self):
         """One iteration in the reference's order (cyclegan.py:92-124).  With `train.cuda_graph` the two halves
         (forward + G step, D steps) are captured once and replayed; the ImagePool stays host logic in between."""

@@ -92,7 +92,7 @@ def test_gloo_world2_helpers_and_ddp_average():
     assert all(r[6] < 1e-6 and r[7] for r in res)      # flat-bucket average == single-process mean
 
 
-def _graph_path_worker(rank, world, port, q):
+def _graph_path_worker(rank, world, port, q, recipe="cyclegan"):
     """The data-parallel CUDA-graph code path of CycleGAN.optimize_parameters (explicit flat-bucket all-reduces between
     the captured segments) on two gloo ranks through the pointer-level CPU restatement of the ABI; the capture itself
     is replaced by a direct call.  Each rank trains on its own batch; the gradients it ends up with must be the mean of
@@ -106,7 +106,7 @@ def _graph_path_worker(rank, world, port, q):
     import fake_cabi
     from ganslate_b200 import _cabi, ops
     from ganslate_b200.nn.gans import base
-    from ganslate_b200.presets import cyclegan_resnet2d
+    from ganslate_b200.presets import cyclegan_resnet2d, pix2pix_resnet2d
     from ganslate_b200.utils import communication as comm
     from ganslate_b200.utils.builders import build_gan
     from oracle import torch_oracle as O
@@ -128,8 +128,8 @@ def _graph_path_worker(rank, world, port, q):
             saved = dist.is_initialized
             torch.distributed.is_initialized = lambda: False
         try:
-            gan = build_gan(cyclegan_resnet2d(batch_size=1, n_residual_blocks=1, cuda_graph=True,
-                                              cuda_graph_warmup=0 if mode == "segments" else 100))
+            kw = dict(batch_size=1, n_residual_blocks=1, cuda_graph=True, cuda_graph_warmup=0 if mode == "segments" else 100)
+            gan = build_gan(cyclegan_resnet2d(**kw) if recipe == "cyclegan" else pix2pix_resnet2d(n_layers=3, **kw))
         finally:
             if not distributed:
                 torch.distributed.is_initialized = saved
@@ -161,12 +161,13 @@ def _graph_path_worker(rank, world, port, q):
 
 
 @pytest.mark.timeout(600)
-def test_gloo_world2_cyclegan_graph_path_averages_gradients():
+@pytest.mark.parametrize("recipe", ["cyclegan", "pix2pix"])
+def test_gloo_world2_graph_path_averages_gradients(recipe):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_graph_path_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_graph_path_worker, args=(r, world, port, q, recipe)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=500) for _ in range(world))
