@@ -106,7 +106,7 @@ def _graph_path_worker(rank, world, port, q, recipe="cyclegan"):
     import fake_cabi
     from ganslate_b200 import _cabi, ops
     from ganslate_b200.nn.gans import base
-    from ganslate_b200.presets import cyclegan_resnet2d, pix2pix_resnet2d
+    from ganslate_b200.presets import cut_resnet2d, cyclegan_resnet2d, pix2pix_resnet2d
     from ganslate_b200.utils import communication as comm
     from ganslate_b200.utils.builders import build_gan
     from oracle import torch_oracle as O
@@ -129,7 +129,15 @@ def _graph_path_worker(rank, world, port, q, recipe="cyclegan"):
             torch.distributed.is_initialized = lambda: False
         try:
             kw = dict(batch_size=1, n_residual_blocks=1, cuda_graph=True, cuda_graph_warmup=0 if mode == "segments" else 100)
-            gan = build_gan(cyclegan_resnet2d(**kw) if recipe == "cyclegan" else pix2pix_resnet2d(n_layers=3, **kw))
+            if recipe == "cut":  # (its feature taps need the 9-block encoder)
+                kw["n_residual_blocks"] = 9
+                conf = cut_resnet2d(**kw)
+                conf.train.gan.optimizer.num_patches = 16
+                gan = build_gan(conf)
+                g5 = torch.Generator().manual_seed(5)
+                gan.fixed_patch_ids = [torch.randperm(n, generator=g5)[:16] for n in [54 * 54, 24 * 24, 12 * 12, 12 * 12, 12 * 12]]
+            else:
+                gan = build_gan(cyclegan_resnet2d(**kw) if recipe == "cyclegan" else pix2pix_resnet2d(n_layers=3, **kw))
         finally:
             if not distributed:
                 torch.distributed.is_initialized = saved
@@ -149,7 +157,7 @@ def _graph_path_worker(rank, world, port, q, recipe="cyclegan"):
     out = {}
     for mode in ("eager", "segments"):
         synced, order, has_sync = run(True, 10 + rank, mode)
-        assert has_sync and order == ["G", "D"], (order, has_sync)
+        assert has_sync and order == (["D", "G", "mlp"] if recipe == "cut" else ["G", "D"]), (order, has_sync)
         err = 0.0
         for key, g in synced.items():
             ref = sum(s[key] for s in singles) / world
@@ -161,7 +169,7 @@ def _graph_path_worker(rank, world, port, q, recipe="cyclegan"):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("recipe", ["cyclegan", "pix2pix"])
+@pytest.mark.parametrize("recipe", ["cyclegan", "pix2pix", "cut"])
 def test_gloo_world2_graph_path_averages_gradients(recipe):
     world = 2
     ctx = mp.get_context("spawn")
