@@ -66,6 +66,16 @@ def _worker(rank, world, port, q):
     (tot / world).backward()
     flat_err = max(float((a.grad - b.grad).abs().max()) for a, b in list(zip(net2.parameters(), ref2.parameters()))[:-1])
     ok_none = params[-1].grad is None and len(sync.params) == len(params)
+    # bf16 wire format (GB_SYNC_BF16): same average to bf16 accuracy
+    g32 = [p.grad.clone() for p in params[:-1]]
+    net3 = O.init_weights(O.OraclePatchGAN2D(3, 8, 2))
+    net3.load_state_dict(ref2.state_dict())
+    O.adversarial_lsgan(net3(x), True).backward()
+    sync16 = FlatGradSync(list(net3.parameters()), torch.device("cpu"), dtype=torch.bfloat16)
+    sync16.launch()
+    sync16.finish()
+    bf16_err = max(float((a.grad - b).abs().max()) / max(1e-12, float(b.abs().max())) for a, b in zip(list(net3.parameters())[:-1], g32))
+    ok_none = ok_none and bf16_err < 2.0 ** -6 and all(p.grad.dtype == torch.float32 for p in net3.parameters())
     q.put((rank, seed, float(red["a"]), float(red["b"]), float((grad - ref.model[0].weight.grad).abs().max()), bcast_err,
            flat_err, ok_none))
     comm.synchronize()
