@@ -37,3 +37,30 @@ def test_preset_runs_one_iteration_of_host_logic(monkeypatch, name, kw, shape, e
     for net_name, net in gan.networks.items():
         got = [p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in net.parameters()]
         assert all(got), (net_name, got.count(False))
+
+
+def test_direct_parameter_gradients_on_a_shared_reversible_generator(monkeypatch):
+    """ops.DIRECT_PARAM_GRAD on RevGAN + Vnet3D: ONE generator serves both directions (forward and inverse) and is used
+    four times per backward, with retain_graph between the generator and discriminator passes -- the kernels'
+    accumulation into `param.grad` must leave exactly the gradients autograd's accumulation leaves."""
+    fake_cabi.install(monkeypatch)
+    from ganslate_b200 import ops, presets
+    from ganslate_b200.nn.gans import base
+    from ganslate_b200.utils.builders import build_gan
+    monkeypatch.setattr(base.BaseGAN, "_specify_device", lambda self: torch.device("cpu"))
+    grads = {}
+    for direct in (False, True):
+        monkeypatch.setattr(ops, "DIRECT_PARAM_GRAD", direct)
+        torch.manual_seed(0)
+        random.seed(0)
+        gan = build_gan(presets.revgan_vnet3d(channels=2, first_layer_channels=8, ndf=8))
+        for o in gan.optimizers.values():
+            monkeypatch.setattr(o, "step", lambda *a, **k: None)
+        g = torch.Generator().manual_seed(3)
+        a, b = torch.rand((1, 2, 32, 32, 32), generator=g) * 2 - 1, torch.rand((1, 2, 32, 32, 32), generator=g) * 2 - 1
+        gan.set_input({"A": a, "B": b})
+        gan.optimize_parameters()
+        grads[direct] = {(n, k): p.grad.clone() for n, net in gan.networks.items() for k, p in net.named_parameters()}
+    assert grads[False].keys() == grads[True].keys() and len(grads[True]) > 100
+    for k, v in grads[False].items():
+        assert torch.allclose(grads[True][k], v, rtol=1e-5, atol=1e-7 * max(1.0, float(v.abs().max()))), k
