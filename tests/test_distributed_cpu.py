@@ -131,6 +131,12 @@ def _graph_path_worker(rank, world, port, q, recipe="cyclegan"):
     base.BaseGAN.eager_stream = lambda self: contextlib.nullcontext()
     comm.init_distributed()
 
+    # eager data parallelism wraps every network in DistributedDataParallel(device_ids=[device]) as the reference does
+    # (base.py:180-183); CPU modules take no device_ids
+    real_ddp = base.DistributedDataParallel
+    base.DistributedDataParallel = lambda net, device_ids=None, output_device=None, broadcast_buffers=False: real_ddp(
+        net, broadcast_buffers=broadcast_buffers)
+
     def run(distributed, batch_seed, mode):
         random.seed(0)
         torch.manual_seed(0)
@@ -138,7 +144,7 @@ def _graph_path_worker(rank, world, port, q, recipe="cyclegan"):
             saved = dist.is_initialized
             torch.distributed.is_initialized = lambda: False
         try:
-            kw = dict(batch_size=1, n_residual_blocks=1, cuda_graph=True, cuda_graph_warmup=0 if mode == "segments" else 100)
+            kw = dict(batch_size=1, n_residual_blocks=1, cuda_graph=mode != "ddp", cuda_graph_warmup=0 if mode == "segments" else 100)
             if recipe == "cut":  # (its feature taps need the 9-block encoder)
                 kw["n_residual_blocks"] = 9
                 conf = cut_resnet2d(**kw)
@@ -159,13 +165,14 @@ def _graph_path_worker(rank, world, port, q, recipe="cyclegan"):
         a, b = O.synthetic_batch(1, 3, 48, seed=batch_seed)
         gan.set_input({"A": a, "B": b})
         gan.optimize_parameters()
-        grads = {(n, k): p.grad.clone() for n, net in gan.networks.items() for k, p in net.named_parameters()}
-        return grads, order, gan.grad_syncs is not None
+        grads = {(n, k.replace("module.", "", 1)): p.grad.clone() for n, net in gan.networks.items() for k, p in net.named_parameters()}
+        wrapped = all(isinstance(n, real_ddp) for n in gan.networks.values())
+        return grads, order, (wrapped if mode == "ddp" else gan.grad_syncs is not None)
 
     singles = [run(False, 10 + r, "eager")[0] for r in range(world)]  # (the unsynchronised iteration is the same in both modes)
     assert any(not torch.equal(singles[0][k], singles[1][k]) for k in singles[0])  # the ranks really see different data
     out = {}
-    for mode in ("eager", "segments"):
+    for mode in ("eager", "segments") + (("ddp",) if recipe == "cyclegan" else ()):
         synced, order, has_sync = run(True, 10 + rank, mode)
         assert has_sync and order == (["D", "G", "mlp"] if recipe == "cut" else ["G", "D"]), (order, has_sync)
         err = 0.0
@@ -173,9 +180,18 @@ def _graph_path_worker(rank, world, port, q, recipe="cyclegan"):
             ref = sum(s[key] for s in singles) / world
             err = max(err, float((g - ref).abs().max()) / max(1e-12, float(ref.abs().max())))
         out[mode] = err
-    q.put((rank, out["eager"], out["segments"]))
+    q.put((rank, out["eager"], out["segments"], out.get("ddp", 0.0)))
     comm.synchronize()
     dist.destroy_process_group()
+
+
+def _graph_path_guarded(rank, world, port, q, recipe):
+    try:
+        _graph_path_worker(rank, world, port, q, recipe)
+    except BaseException:  # report instead of leaving the parent waiting for its queue time-out
+        import traceback
+        q.put((rank, "error", traceback.format_exc()[-3000:], 0.0))
+        raise
 
 
 @pytest.mark.timeout(600)
@@ -185,12 +201,15 @@ def test_gloo_world2_graph_path_averages_gradients(recipe):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_graph_path_worker, args=(r, world, port, q, recipe)) for r in range(world)]
+    procs = [ctx.Process(target=_graph_path_guarded, args=(r, world, port, q, recipe)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=500) for _ in range(world))
+    res = sorted((q.get(timeout=240) for _ in range(world)), key=lambda r: r[0])
+    for rank, e_eager, e_seg, e_ddp in res:
+        assert e_eager != "error", e_seg
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    for rank, e_eager, e_seg in res:
-        assert e_eager < 1e-5 and e_seg < 1e-5, res
+    for rank, e_eager, e_seg, e_ddp in res:
+        assert e_eager != "error", e_seg
+        assert e_eager < 1e-5 and e_seg < 1e-5 and e_ddp < 1e-5, res
