@@ -12,8 +12,8 @@ import fake_cabi
 
 CASES = [
     ("pix2pix_unet2d", dict(batch_size=1, num_downs=5, ngf=8, n_layers=3), (3, 64, 96), {"G", "D", "pix2pix"}),
-    ("cyclegan_vnet3d", dict(first_layer_channels=8, ndf=8), (1, 32, 32, 32), {"G_AB", "G_BA", "D_A", "D_B", "cycle_A", "cycle_B"}),
-    ("revgan_vnet3d", dict(channels=2, first_layer_channels=8, ndf=8), (2, 32, 32, 32), {"G_AB", "G_BA", "D_A", "D_B", "cycle_A", "cycle_B"}),
+    ("cyclegan_vnet3d", dict(first_layer_channels=8, ndf=8, n_layers=2), (1, 16, 32, 32), {"G_AB", "G_BA", "D_A", "D_B", "cycle_A", "cycle_B"}),
+    ("revgan_vnet3d", dict(channels=2, first_layer_channels=8, ndf=8, n_layers=2), (2, 16, 32, 32), {"G_AB", "G_BA", "D_A", "D_B", "cycle_A", "cycle_B"}),
 ]
 
 
@@ -53,11 +53,11 @@ def test_direct_parameter_gradients_on_a_shared_reversible_generator(monkeypatch
         monkeypatch.setattr(ops, "DIRECT_PARAM_GRAD", direct)
         torch.manual_seed(0)
         random.seed(0)
-        gan = build_gan(presets.revgan_vnet3d(channels=2, first_layer_channels=8, ndf=8))
+        gan = build_gan(presets.revgan_vnet3d(channels=2, first_layer_channels=8, ndf=8, n_layers=2))
         for o in gan.optimizers.values():
             monkeypatch.setattr(o, "step", lambda *a, **k: None)
         g = torch.Generator().manual_seed(3)
-        a, b = torch.rand((1, 2, 32, 32, 32), generator=g) * 2 - 1, torch.rand((1, 2, 32, 32, 32), generator=g) * 2 - 1
+        a, b = torch.rand((1, 2, 16, 32, 32), generator=g) * 2 - 1, torch.rand((1, 2, 16, 32, 32), generator=g) * 2 - 1
         gan.set_input({"A": a, "B": b})
         gan.optimize_parameters()
         grads[direct] = {(n, k): p.grad.clone() for n, net in gan.networks.items() for k, p in net.named_parameters()}
