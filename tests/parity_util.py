@@ -58,7 +58,7 @@ def step_report(size=256, batch=1, n_blocks=9, step_optimizers=False, lambda_ide
             o.step = lambda *a, **k: None
         ours.optimize_parameters()
     torch.cuda.synchronize()
-    rep["losses"] = {k: (lo[k], float(ours.losses[k])) for k in lo}
+    rep["losses"] = {k: (lo[k], float(ours.losses[k].detach())) for k in lo}
     rep["visuals"] = {k: (rel_l2(ours.visuals[k], oracle.visuals[k]), max_rel(ours.visuals[k], oracle.visuals[k]))
                       for k in ("fake_B", "rec_A", "fake_A", "rec_B")}
     grads = {}

@@ -99,7 +99,7 @@ def test_revgan_step_vs_oracle():
     ours.optimize_parameters()
     torch.cuda.synchronize()
     for k, v in lo.items():
-        assert abs(float(ours.losses[k]) - v) <= 2e-2 * abs(v) + 1e-4, (k, v, float(ours.losses[k]))
+        assert abs(float(ours.losses[k].detach()) - v) <= 2e-2 * abs(v) + 1e-4, (k, v, float(ours.losses[k].detach()))
     for k, tol in (("fake_B", 3e-2), ("fake_A", 3e-2), ("rec_A", 1.2e-1), ("rec_B", 1.2e-1)):
         assert rel_l2(ours.visuals[k], oracle.visuals[k]) <= tol, (k, rel_l2(ours.visuals[k], oracle.visuals[k]))
     bad = []

@@ -74,7 +74,7 @@ def test_cut_step_vs_oracle():
     ours.optimize_parameters()
     torch.cuda.synchronize()
     for k, v in lo.items():
-        assert abs(float(ours.losses[k]) - v) <= 2e-2 * abs(v), (k, v, float(ours.losses[k]))
+        assert abs(float(ours.losses[k].detach()) - v) <= 2e-2 * abs(v), (k, v, float(ours.losses[k].detach()))
     # MLP gradients come through the fused PatchNCE backward; generator gradients through the feature taps
     for name in ("mlp", "G", "D"):
         po, pg = dict(oracle.networks[name].named_parameters()), dict(ours.networks[name].named_parameters())

@@ -52,7 +52,7 @@ def test_cyclegan_step_vs_oracles(size, blocks):
     ours.optimize_parameters()
     torch.cuda.synchronize()
     for k, v in l32.items():
-        assert abs(float(ours.losses[k]) - v) <= 1e-2 * abs(v), (k, v, float(ours.losses[k]))
+        assert abs(float(ours.losses[k].detach()) - v) <= 1e-2 * abs(v), (k, v, float(ours.losses[k].detach()))
     for k, tol in (("fake_B", 3e-2), ("fake_A", 3e-2), ("rec_A", 1.2e-1), ("rec_B", 1.2e-1)):
         assert rel_l2(ours.visuals[k], fp32.visuals[k]) <= tol, k
     e_ours = _grad_errors(ours.networks, fp32.networks)
@@ -114,7 +114,7 @@ def test_second_iteration_uses_updated_weights():
         ours.set_input({"A": a, "B": b})
         ours.optimize_parameters()
         torch.cuda.synchronize()
-        got = {k: float(ours.losses[k]) for k in lo}
+        got = {k: float(ours.losses[k].detach()) for k in lo}
         if it == 0:
             first = dict(lo)
         for k in lo:
