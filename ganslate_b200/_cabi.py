@@ -114,6 +114,7 @@ _SIGNATURES = {
     "gb_version": [],
     "gb_tma_window_supported": [],
     "gb_debug_knob": [C.c_int, C.c_int],
+    "gb_debug_timeline": [C.c_void_p, C.c_longlong],
     "gb_debug_cg2_watchdog": [C.c_void_p],
     "gb_workspace_bytes": [C.c_int, C.c_void_p, C.POINTER(C.c_int64)],
     "gb_debug_cg2_plan": [C.POINTER(ConvParams), C.c_int, C.c_void_p, C.c_void_p, C.c_int64],

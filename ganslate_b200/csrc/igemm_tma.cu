@@ -46,7 +46,17 @@ struct TileGeom {
   int ntx, nty;
   int ntiles;                            // per class (max over classes is the grid)
   int nstages;                           // depth of the smem ring (<= TCfg::STAGES); small rings let two CTAs share an SM
+  // bring-up instrumentation (tools/conv_timeline.py; both 0 in every ordinary launch):
+  int mode;                              // knob 30 (bits): 1 = producer skips the loads, 2 = issuer skips the MMAs, 4 = no epilogue
+  unsigned long long* ts;                // gb_debug_timeline(): 8 words per CTA (smid, globaltimer, 6 clock64 stamps)
 };
+
+__device__ __forceinline__ void ts_put(const TileGeom& tg, int slot) {
+  if (tg.ts != nullptr) {
+    const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    tg.ts[8ull * cta + slot] = (unsigned long long)clock64();
+  }
+}
 
 
 template <int BN>
@@ -90,6 +100,16 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
   const int n0 = blockIdx.y * BN;
   const int chunks = p.in.C >> 6;
   const int KB = cc.ntaps * chunks;
+  if (tg.ts != nullptr && tid == 0) {
+    const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    unsigned smid;
+    unsigned long long gt;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    tg.ts[8ull * cta + 0] = smid;
+    tg.ts[8ull * cta + 1] = gt;
+    tg.ts[8ull * cta + 2] = (unsigned long long)clock64();
+  }
 
   const uint32_t full_bar = smem_u32(bars);
   const uint32_t empty_bar = smem_u32(bars + MAXS);
@@ -110,6 +130,7 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 64) ts_put(tg, 3);   // setup done
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one lane)
@@ -123,9 +144,13 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
           const uint32_t a_s = base + s * C::STAGE_BYTES;
           const uint32_t b_s = a_s + A_BYTES;
           const uint32_t bar = full_bar + 8 * s;
-          mbar_expect_tx(bar, (uint32_t)(tg.tw * tg.th * 128 + C::B_BYTES));
-          tma_load_5d(a_s, &map_a, bar, c * 64, x0 * p.in_mul[2] + dx, y0 * p.in_mul[1] + dy, z0 * p.in_mul[0] + dz, n);
-          tma_load_2d(b_s, &map_b, bar, tl * p.in.C + c * 64, cls * p.npad + n0);
+          if (tg.mode & 1) {
+            mbar_arrive(bar);
+          } else {
+            mbar_expect_tx(bar, (uint32_t)(tg.tw * tg.th * 128 + C::B_BYTES));
+            tma_load_5d(a_s, &map_a, bar, c * 64, x0 * p.in_mul[2] + dx, y0 * p.in_mul[1] + dy, z0 * p.in_mul[0] + dz, n);
+            tma_load_2d(b_s, &map_b, bar, tl * p.in.C + c * 64, cls * p.npad + n0);
+          }
           if (++s == STAGES) {
             s = 0;
             ++it;
@@ -141,7 +166,10 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
     for (int kb = 0; kb < KB; ++kb) {
       mbar_wait(full_bar + 8 * s, it & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (kb == 0 && lane == 0) ts_put(tg, 4);   // first operands have landed
+      if (tg.mode == 2) {
+        if (lane == 0) mbar_arrive(empty_bar + 8 * s);
+      } else if (lane == 0) {
         const uint32_t a_s = base + s * C::STAGE_BYTES;
         const uint32_t b_s = a_s + A_BYTES;
         const uint64_t adesc = make_smem_desc(a_s, 16, 1024);
@@ -157,7 +185,10 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
         ++it;
       }
     }
-    if (lane == 0 && KB > 0) umma_commit(accum_bar);
+    if (lane == 0) ts_put(tg, 5);                // every MMA issued
+    if (lane == 0 && KB > 0) {
+      if (tg.mode == 2) mbar_arrive(accum_bar); else umma_commit(accum_bar);
+    }
     __syncwarp();
   }
 
@@ -166,7 +197,8 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
     mbar_wait(accum_bar, 0);
     tc_fence_after();
   }
-  {
+  if (tid == 64) ts_put(tg, 6);                  // accumulator complete
+  if (!(tg.mode & 4)) {
     const int row = (warp & 3) * 32 + lane;
     const int h = (int)gb_div((uint32_t)row, tg.div_tw), w = row - h * tg.tw;
     const int qy = y0 + h, qx = x0 + w;
@@ -180,8 +212,12 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 64) ts_put(tg, 7);                  // epilogue done
   if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
+
+unsigned long long* g_timeline = nullptr;
+long long g_timeline_ctas = 0;
 
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -281,6 +317,13 @@ extern "C" int gb_tma_window_supported(void) {
   return cached = (r == CUDA_SUCCESS ? 1 : 0);
 }
 
+// Bring-up: per-CTA time stamps of the TMA-fed data kernel (buf: device memory, 8 x u64 per CTA; nullptr = off).
+extern "C" int gb_debug_timeline(void* buf, long long max_ctas) {
+  g_timeline = static_cast<unsigned long long*>(buf);
+  g_timeline_ctas = buf != nullptr ? max_ctas : 0;
+  return 0;
+}
+
 namespace {
 
 template <int BN>
@@ -304,6 +347,8 @@ int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb
   if (BN <= 128 && ctas >= 2 * 148 && kb_max <= 18 && shallow >= 3 && g_gb_knobs[8] == 0) ns = ns < shallow ? ns : shallow;
   if (ns < 1) ns = 1;
   tgl.nstages = ns;
+  tgl.mode = g_gb_knobs[30];
+  tgl.ts = (g_timeline != nullptr && ctas <= g_timeline_ctas) ? g_timeline : nullptr;
   gb_klaunch(igemm_tma_kernel<BN>, grid, 256, ns * C::STAGE_BYTES + 2048, st, p, ma, mb, tgl);
   g_gb_knobs[15] = 2;
   GB_LAUNCH_CHECK();

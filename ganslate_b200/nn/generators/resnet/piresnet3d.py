@@ -64,7 +64,7 @@ class Piresnet3D(nn.Module):
     def _run(self, tape, b0, inverse):
         down, up = (self.downconv_ba, self.upconv_ba) if inverse else (self.downconv_ab, self.upconv_ab)
         b = layers.run_sequence(tape, list(down), b0)
-        b = self.core.gb_run(tape, b, inverse)
+        b = self.core.gb_run_coupling(tape, b, inverse)
         b = layers.run_sequence(tape, list(up)[:-1], b)  # the trailing Tanh is evaluated in fp32 while exporting
         return b, ACT_TANH
 

@@ -134,7 +134,7 @@ class DownBlock(nn.Module):
 
     def gb_run(self, tape, b, inverse=False):
         down = _conv_norm_prelu(tape, b, self.down_conv_ba if inverse else self.down_conv_ab)
-        out = self.core.gb_run(tape, down, inverse)
+        out = self.core.gb_run_coupling(tape, down, inverse)
         # PReLU(out + down)
         return layers.step_norm_act(tape, out, False, ACT_PRELU, 0.0, 0, 1e-5, residual=down, prelu=self.relu,
                                     res_before_act=True)
@@ -169,7 +169,7 @@ class UpBlock(nn.Module):
                           self.out_channels, raw.is_3d)
         layers.step_norm_act(tape, raw, True, ACT_PRELU, 0.0, 0, seq[1].eps, prelu=seq[2], out=xcat.slice(0, half))
         layers.step_norm_act(tape, skip, False, ACT_NONE, 0.0, 0, 1e-5, out=xcat.slice(half, half))
-        out = self.core.gb_run(tape, xcat, inverse)
+        out = self.core.gb_run_coupling(tape, xcat, inverse)
         return layers.step_norm_act(tape, out, False, ACT_PRELU, 0.0, 0, 1e-5, residual=xcat, prelu=self.relu,
                                     res_before_act=True)
 

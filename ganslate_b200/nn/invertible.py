@@ -3,9 +3,18 @@ memcnn (`...core.sequence.{i}.invertible_block._fn.{Fm,Gm}.{0,2}.*`).
 
 memcnn.AdditiveCoupling: y1 = x1 + Fm(x2); y2 = x2 + Gm(y1) on a channel split in halves, inverse
 x2 = y2 - Gm(y1); x1 = y1 - Fm(x2) (memcnn is an unpinned dependency absent from this image; its published
-algorithm is restated).  memcnn.InvertibleModuleWrapper only changes WHEN activations are
-stored (it frees the input and recomputes it in backward); on a 180 GB part the activations are simply kept, so
-`keep_input` is accepted and ignored -- values and gradients are identical.
+algorithm is restated).
+
+memcnn.InvertibleModuleWrapper decides WHEN activations exist: it runs the coupling without recording anything,
+frees the block's INPUT unless `keep_input` (ganslate/nn/invertible.py:41-46 forces keep_input on the first block of
+a sequence, whose input other layers still read), and in backward rebuilds that input from the block's OUTPUT with
+the inverse coupling, re-runs the coupling with recording on and back-propagates through it.  `recompute_coupling`
+below does exactly that on the tape (`use_memory_saving=True` -> `keep_input=False`, vnet3d.py:52): per sequence
+only the first block's input and the last block's output stay allocated between forward and backward -- every
+other block input and every intermediate of every block (raw convolution outputs, statistics) is transient.
+Values: the rebuilt input is `bf16(y - F(.))` of `y = bf16(x + F(.))`, i.e. equal to the original up to one bf16
+rounding per block (the reference's fp32 rebuild is off by one fp32 rounding in the same place); the gradients of the
+two modes agree to that level (tests/test_host_networks_cpu.py::test_vnet3d_memory_saving_*, tests/test_3d_gpu.py).
 
 The classes hold parameters only; the compute is `coupling_forward` / `coupling_inverse` below, built from the fused
 step primitives on channel-slice views (no split / cat copies)."""
@@ -48,12 +57,62 @@ class InvertibleSequence(nn.Module):
         super().__init__()
         self.sequence = nn.Sequential(*[InvertibleBlock(block, keep_input, disable) for _ in range(n_blocks)])
 
-    def gb_run(self, tape, x, inverse=False):
+    def gb_run_coupling(self, tape, x, inverse=False):
+        """(not `gb_run`: layers.run_sequence's protocol passes a border as the third argument)"""
         blocks = list(reversed(self.sequence)) if inverse else list(self.sequence)
-        for blk in blocks:
-            fn = blk.invertible_block._fn
-            x = coupling_inverse(tape, x, fn) if inverse else coupling_forward(tape, x, fn)
+        for i, blk in enumerate(blocks):
+            wrap = blk.invertible_block
+            fn = wrap._fn
+            keep = wrap.keep_input_inverse if inverse else wrap.keep_input
+            if tape is None or wrap.disable or keep:
+                # nothing to save (no backward will run) or the caller keeps every activation
+                x = coupling_inverse(tape, x, fn) if inverse else coupling_forward(tape, x, fn)
+            else:
+                # ganslate/nn/invertible.py:41-46: the first block of a sequence keeps its input
+                x = recompute_coupling(tape, x, fn, inverse, free_input=(i > 0))
         return x
+
+
+RECOMPUTE_STATS = {"blocks": 0, "rebuilt_inputs": 0}  # counters for the tests (how often the backward path below ran)
+
+
+def recompute_coupling(tape, x, fn, inverse, free_input):
+    """memcnn.InvertibleModuleWrapper(keep_input=False) on the tape: forward without recording; backward =
+    [rebuild the input from the output with the inverse coupling] + recorded re-run + its backward."""
+    fwd, inv = (coupling_inverse, coupling_forward) if inverse else (coupling_forward, coupling_inverse)
+    x_st = x.st
+    n_cons = x_st.consumers
+    y = fwd(None, x, fn)                 # intermediates die here
+    x_st.consumers = n_cons + 1
+    shape = tuple(x_st.t.shape)
+    if free_input:
+        x_st.t = None                    # the input's memory goes back to the allocator (memcnn: storage().resize_(0))
+
+    def bwd():
+        if not y.has_grad():
+            return
+        g = y.st.grad
+        y.st.grad = None
+        RECOMPUTE_STATS["blocks"] += 1
+        if x_st.t is None:
+            n_y = y.st.consumers
+            xr = inv(None, y, fn)        # rebuilt from the output (which the next block's backward rebuilt before)
+            y.st.consumers = n_y
+            assert tuple(xr.st.t.shape) == shape
+            x_st.t = xr.st.t
+            RECOMPUTE_STATS["rebuilt_inputs"] += 1
+        sub = layers.Tape(tape.param_needs_grad, tape.input_needs_grad)
+        sub.param_grads, sub.unpack, sub._queued = tape.param_grads, tape.unpack, tape._queued
+        n_cons = x_st.consumers
+        y2 = fwd(sub, x, fn)
+        x_st.consumers = n_cons
+        y2.st.grad = g
+        for step in reversed(sub.steps):
+            step()
+        sub.steps = []
+
+    tape.steps.append(bwd)
+    return y
 
 
 def _branch(tape, src, seq, residual, out, out_scale):

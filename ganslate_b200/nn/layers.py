@@ -163,6 +163,17 @@ class PReLU(_Marker, nn.PReLU):
     """Per-channel learnable slopes (V-Net, ganslate/nn/generators/vnet/vnet3d.py:160,196,231,251)."""
 
 
+# Storages that received a gradient during the backward pass that is running: the pass clears them when it ends, so
+# no fp32 gradient buffer outlives its backward and a second backward over the same tape (retain_graph=True with
+# RELEASE_TAPE off) starts from clean gradients instead of accumulating onto the previous pass's.
+_LIVE_GRADS = []
+
+# After its backward a network's tape (the closures that hold every bf16 activation of the forward pass) is dropped,
+# as autograd frees its saved tensors: a second backward through the same forward then raises, like torch's
+# "Trying to backward through the graph a second time".  Set to False to keep tapes (retain_graph=True users).
+RELEASE_TAPE = True
+
+
 class Storage:
     """One channels-last bf16 allocation (N, D, H+2*pad, W+2*pad, C) plus, during backward, its gradient.
 
@@ -170,12 +181,43 @@ class Storage:
     in one piece by the consumer's backward.  Every other buffer is an activation: its gradient is an FP32 tensor of
     the same shape into which every consumer ACCUMULATES (convolution dgrad epilogues, residual branches, channel
     slices of concatenations), so arbitrary fan-out / channel splits need no extra add kernels."""
-    __slots__ = ("t", "pad", "raw", "grad", "consumers")
+    __slots__ = ("t", "pad", "raw", "_grad", "consumers")
 
     def __init__(self, t, pad, raw=False):
         self.t, self.pad, self.raw = t, pad, raw
-        self.grad = None
+        self._grad = None
         self.consumers = 0  # how many tape steps read this storage (decides zero-init vs overwrite in backward)
+
+    @property
+    def grad(self):
+        return self._grad
+
+    @grad.setter
+    def grad(self, g):
+        if g is not None and self._grad is None:
+            _LIVE_GRADS.append(self)
+        self._grad = g
+
+
+def _end_backward(ctx):
+    """Common tail of the three Functions' backward: drop every gradient buffer of the pass and (RELEASE_TAPE) the
+    tape with the activations it holds."""
+    for st in _LIVE_GRADS:
+        st._grad = None
+    del _LIVE_GRADS[:]
+    if RELEASE_TAPE:
+        ctx.tape.steps = None
+        ctx.tape = ctx.b0 = ctx.b_last = None
+        if hasattr(ctx, "sink"):
+            ctx.sink = None
+
+
+def _begin_backward(ctx):
+    if ctx.tape is None or ctx.tape.steps is None:
+        raise RuntimeError("ganslate_b200: backward through a network a second time -- its tape was released after "
+                           "the first backward (set ganslate_b200.nn.layers.RELEASE_TAPE = False to keep tapes "
+                           "for retain_graph=True)")
+    del _LIVE_GRADS[:]
 
 
 class Buf:
@@ -636,6 +678,7 @@ class NetworkFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        _begin_backward(ctx)
         tape, b0, b = ctx.tape, ctx.b0, ctx.b_last
         tape.param_grads = {}
         ops.arena_begin(("bwd",) + ctx.arena_key, dy.device)
@@ -649,6 +692,7 @@ class NetworkFn(torch.autograd.Function):
         ops.arena_end(("bwd",) + ctx.arena_key)
         grads = [tape.param_grads.get(id(p)) for p in ctx.params]
         tape.param_grads = {}
+        _end_backward(ctx)
         return (None, dx, *grads)
 
 
@@ -676,6 +720,7 @@ class RunnerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        _begin_backward(ctx)
         tape, b0, b = ctx.tape, ctx.b0, ctx.b_last
         tape.param_grads = {}
         ops.arena_begin(("run_bwd",) + ctx.arena_key, dy.device)
@@ -689,6 +734,7 @@ class RunnerFn(torch.autograd.Function):
         ops.arena_end(("run_bwd",) + ctx.arena_key)
         grads = [tape.param_grads.get(id(p)) for p in ctx.params]
         tape.param_grads = {}
+        _end_backward(ctx)
         return (None, None, dx, *grads)
 
 
@@ -763,6 +809,7 @@ class EncoderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *douts):
+        _begin_backward(ctx)
         tape, b0 = ctx.tape, ctx.b0
         tape.param_grads = {}
         ops.arena_begin(("enc_bwd",) + ctx.arena_key, douts[0].device if douts[0] is not None else b0.t.device)
@@ -779,6 +826,7 @@ class EncoderFn(torch.autograd.Function):
         ops.arena_end(("enc_bwd",) + ctx.arena_key)
         grads = [tape.param_grads.get(id(p)) for p in ctx.params]
         tape.param_grads = {}
+        _end_backward(ctx)
         return (None, None, dx, *grads)
 
 

@@ -78,7 +78,7 @@ def cut_resnet2d(batch_size=1, n_residual_blocks=9, **train_overrides):
 
 
 def _vnet3d_conf(target, channels, use_inverse, batch_size, first_layer_channels, down_blocks, up_blocks, ndf, n_layers,
-                 train_overrides, generator=None):
+                 train_overrides, generator=None, use_memory_saving=False):
     conf = {
         "mode": "train",
         "train": {
@@ -86,7 +86,7 @@ def _vnet3d_conf(target, channels, use_inverse, batch_size, first_layer_channels
             "gan": {
                 "_target_": target,
                 "pool_size": 50,
-                "generator": {"_target_": "ganslate_b200.nn.generators.Vnet3D", "use_memory_saving": False,
+                "generator": {"_target_": "ganslate_b200.nn.generators.Vnet3D", "use_memory_saving": use_memory_saving,
                               "use_inverse": use_inverse, "first_layer_channels": first_layer_channels,
                               "down_blocks": list(down_blocks), "up_blocks": list(up_blocks),
                               "in_out_channels": {"AB": [channels, channels]}},
@@ -112,17 +112,19 @@ def cyclegan_vnet3d(channels=1, batch_size=1, first_layer_channels=16, down_bloc
 
 
 def revgan_vnet3d(channels=4, batch_size=1, first_layer_channels=16, down_blocks=(1, 2, 3, 2), up_blocks=(2, 2, 1, 1),
-                  ndf=64, n_layers=3, **train_overrides):
-    """BASELINE config 5: RevGAN, one partially invertible Vnet3D (use_inverse) + PatchGAN3D on 4x128^3 patches."""
+                  ndf=64, n_layers=3, use_memory_saving=True, **train_overrides):
+    """BASELINE config 5: RevGAN, one partially invertible Vnet3D (use_inverse, inverse-recompute backward =
+    use_memory_saving, the Vnet3D default -- vnet3d.py:36) + PatchGAN3D on 4x128^3 patches."""
     return _vnet3d_conf("ganslate_b200.nn.gans.unpaired.RevGAN", channels, True, batch_size, first_layer_channels,
-                        down_blocks, up_blocks, ndf, n_layers, train_overrides)
+                        down_blocks, up_blocks, ndf, n_layers, train_overrides, use_memory_saving=use_memory_saving)
 
 
-def revgan_piresnet3d(channels=1, batch_size=1, depth=5, first_layer_channels=32, ndf=64, n_layers=2, **train_overrides):
+def revgan_piresnet3d(channels=1, batch_size=1, depth=5, first_layer_channels=32, ndf=64, n_layers=2,
+                      use_memory_saving=True, **train_overrides):
     """The shipped BraTS RevGAN experiment (projects/brats_mri_sequence_translation/experiments/revgan.yaml:25-39):
     RevGAN with one partially invertible Piresnet3D (depth 5, Piresnet3DConfig default first_layer_channels 32) and
     PatchGAN3D(n_layers 2) on 1x32x176x176 patches."""
-    gen = {"_target_": "ganslate_b200.nn.generators.Piresnet3D", "use_memory_saving": False, "use_inverse": True,
+    gen = {"_target_": "ganslate_b200.nn.generators.Piresnet3D", "use_memory_saving": use_memory_saving, "use_inverse": True,
            "first_layer_channels": first_layer_channels, "depth": depth, "in_out_channels": {"AB": [channels, channels]}}
     return _vnet3d_conf("ganslate_b200.nn.gans.unpaired.RevGAN", channels, True, batch_size, first_layer_channels, (), (),
                         ndf, n_layers, train_overrides, generator=gen)

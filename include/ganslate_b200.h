@@ -295,6 +295,10 @@ int gb_debug_cg2_watchdog(int32_t* out);
 
 /* debug knobs for bring-up (e.g. descriptor variants); returns previous value */
 int gb_debug_knob(int knob, int value);
+/* Bring-up: per-CTA time stamps of the TMA-fed data kernel. buf = device memory of 8 x uint64 per CTA (SM id,
+   globaltimer, clock64 at: start, setup done, first operands landed, last MMA issued, accumulator complete, epilogue
+   done); launches with more CTAs than max_ctas are not recorded; NULL switches it off. tools/conv_timeline.py. */
+int gb_debug_timeline(void* buf, long long max_ctas);
 
 #ifdef __cplusplus
 }

@@ -379,12 +379,28 @@ def _flatten(mods):
     return out
 
 
+# Noise floor of ANY bf16 implementation: with SUMMATION_VARIANT set, every convolution of forward_bf16_points adds
+# its input channels in the reverse order -- mathematically the same network with the same rounding points, differing
+# only in fp32 summation order (1e-7 relative).  Each bf16 rounding turns a difference d << ulp into sqrt(ulp * d), so
+# after a few layers the two realisations are as far apart as two independent bf16 runs; the distance between them is
+# the resolution at which an end-to-end comparison with the bf16-point oracle can detect anything
+# (tests/test_cyclegan_gpu.py::test_cyclegan_step_vs_matched_oracle_noise_floor).
+SUMMATION_VARIANT = False
+
 TRACE = None  # debugging aid: list receiving ("raw"|"act", tensor) for every conv group of forward_bf16_points
+
+
+TRACE_LIVE = False  # True: TRACE receives the live tensors (retain_grad) so that their gradients can be read too
 
 
 def _trace(kind, t):
     if TRACE is not None:
-        TRACE.append((kind, t.detach().clone()))
+        if TRACE_LIVE:
+            if t.requires_grad:
+                t.retain_grad()
+            TRACE.append((kind, t))
+        else:
+            TRACE.append((kind, t.detach().clone()))
 
 
 def _seq_bf16(mods, h, residual=None):
@@ -399,14 +415,19 @@ def _seq_bf16(mods, h, residual=None):
             continue
         if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d, nn.Conv3d, nn.ConvTranspose3d)):
             w = _rb(m.weight)
+            hh = h
+            if SUMMATION_VARIANT:
+                # the same sum in another order: input channels reversed in both operands (see SUMMATION_VARIANT)
+                tr = isinstance(m, (nn.ConvTranspose2d, nn.ConvTranspose3d))
+                hh, w = h.flip(1), w.flip(0 if tr else 1)
             if isinstance(m, nn.ConvTranspose2d):
-                raw = F.conv_transpose2d(h, w, m.bias, m.stride, m.padding, m.output_padding)
+                raw = F.conv_transpose2d(hh, w, m.bias, m.stride, m.padding, m.output_padding)
             elif isinstance(m, nn.ConvTranspose3d):
-                raw = F.conv_transpose3d(h, w, m.bias, m.stride, m.padding, m.output_padding)
+                raw = F.conv_transpose3d(hh, w, m.bias, m.stride, m.padding, m.output_padding)
             elif isinstance(m, nn.Conv3d):
-                raw = F.conv3d(h, w, m.bias, m.stride, m.padding)
+                raw = F.conv3d(hh, w, m.bias, m.stride, m.padding)
             else:
-                raw = F.conv2d(h, w, m.bias, m.stride, m.padding)
+                raw = F.conv2d(hh, w, m.bias, m.stride, m.padding)
             j = i + 1
             norm = j < n and isinstance(mods[j], (nn.InstanceNorm2d, nn.InstanceNorm3d))
             if norm:
@@ -417,8 +438,9 @@ def _seq_bf16(mods, h, residual=None):
             last = j >= n
             if isinstance(act, nn.Tanh) and last:
                 # generator output: bf16 pre-activation, tanh evaluated in fp32 on export
-                _trace("raw", _rb(raw))
-                return torch.tanh(_GradRound.apply(_rb(raw)))
+                raw = _GradRound.apply(_rb(raw))
+                _trace("raw", raw)
+                return torch.tanh(raw)
             followed_by_pad = j < n and (isinstance(mods[j], nn.ReflectionPad2d) or isinstance(mods[j], OracleResBlock))
             if norm or (last and residual is not None) or followed_by_pad:
                 raw = _GradRound.apply(_rb(raw))                       # conv epilogue stores bf16

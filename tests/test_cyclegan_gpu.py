@@ -8,6 +8,10 @@ Stated tolerances:
   bias gradients in front of an InstanceNorm (mathematically zero): absolute <= 5e-3 * max|weight grad| of the net;
                    the other bias gradients (nearly cancelling sums over all pixels): as the weights, or that
                    absolute bound
+  vs the bf16-point (matched) oracle: losses <= 5e-3; visuals and every weight gradient within 1.5 x the noise floor
+                   of bf16 itself (a second realisation of the same oracle in another summation order), + 0.02
+  teacher-forced per-layer parity at the BASELINE shapes with north_star's 1e-2 max-relative bound:
+                   tests/test_forced_parity_gpu.py
   size-independent property at the full 256x256 / 9-block size: the generator Adam step moves every weight by
   lr * sign(g) on the first step, so |w_after - w_before| == lr wherever |g| is not tiny.
 """
@@ -75,6 +79,52 @@ def test_cyclegan_step_vs_oracles(size, blocks):
             if cos < 0.9 and l2 > 1.5 * e_bf16[k][0] + 0.05 and absmax > 5e-3 * wmax[net]:
                 bad.append((k, "bias", l2, cos, e_bf16[k][0], absmax, wmax[net]))
     assert not bad, bad
+
+
+@pytest.mark.parametrize("size,blocks", [(64, 3), (256, 9)])
+def test_cyclegan_step_vs_matched_oracle_noise_floor(size, blocks):
+    """The whole iteration against the bf16-point (matched) oracle, judged against the NOISE FLOOR of bf16 itself:
+    the same oracle with every convolution summed in another channel order (oracle.torch_oracle.SUMMATION_VARIANT)
+    is a second, equally valid realisation of this path's arithmetic; the B200 path must be no further from the
+    matched oracle than 1.5 x that realisation is (+ 0.02 absolute on relative-L2 figures that are tiny), per visual
+    and per weight-gradient tensor.  (256, 9) is BASELINE config 1's shape.  Measured (gpurun r02a): ours 1.1-1.4 x
+    the floor -- e.g. 64 px / 3 blocks: fake_B 0.009 vs 0.0066, rec_A 0.041 vs 0.034, weight gradients 0.21 vs 0.19."""
+    from oracle import torch_oracle as O
+    from parity_util import build_pair, rel_l2
+    random.seed(0)
+    matched, ours = build_pair(size, 1, blocks, matched=True)
+    a, b = O.synthetic_batch(1, 3, size, seed=1)
+    lm = matched.optimize_parameters(a, b, step_optimizers=False)
+    O.SUMMATION_VARIANT = True
+    try:
+        random.seed(0)
+        other = O.OracleCycleGANBf16(O.default_cyclegan_conf(n_residual_blocks=blocks), seed=0)
+        other.optimize_parameters(a, b, step_optimizers=False)
+    finally:
+        O.SUMMATION_VARIANT = False
+    for o in ours.optimizers.values():
+        o.step = lambda *a, **k: None
+    ours.set_input({"A": a, "B": b})
+    ours.optimize_parameters()
+    torch.cuda.synchronize()
+    for k, v in lm.items():
+        assert abs(float(ours.losses[k].detach()) - v) <= 5e-3 * abs(v), (k, v, float(ours.losses[k].detach()))
+    bad = []
+    for k in ("fake_B", "fake_A", "rec_A", "rec_B"):
+        e, floor = rel_l2(ours.visuals[k], matched.visuals[k]), rel_l2(other.visuals[k], matched.visuals[k])
+        if e > 1.5 * floor + 0.02:
+            bad.append((k, e, floor))
+    e_ours = _grad_errors(ours.networks, matched.networks)
+    e_floor = _grad_errors(other.networks, matched.networks)
+    ratios = []
+    for k, (l2, cos, refmax, absmax) in e_ours.items():
+        if k.endswith("weight"):
+            ratios.append(l2 / max(e_floor[k][0], 1e-3))
+            if l2 > 1.5 * e_floor[k][0] + 0.02:
+                bad.append((k, l2, e_floor[k][0]))
+    assert not bad, bad
+    ratios.sort()
+    print("weight-gradient error / noise floor: median %.2f max %.2f" % (ratios[len(ratios) // 2], ratios[-1]))
 
 
 def test_first_adam_step_moves_weights_by_lr_at_full_size():
