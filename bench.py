@@ -56,6 +56,7 @@ def parse():
                          "(train.input_prefetch) and the loss of step i read after step i+1 was enqueued")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-batch1", action="store_true", help="skip the extra batch-1 leg of the headline workload")
     ap.add_argument("--roofline-all-ranks", action="store_true", help="N>1: profile the per-kernel roofline too")
     args = ap.parse_args()
     if args.workload != "cyclegan2d" and "--batch" not in sys.argv and "GB_BENCH_BATCH" not in os.environ:
@@ -113,7 +114,9 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{steps} full CycleGAN steps (batch {args.batch}) of oracle/torch_oracle.py on the "
-                                   f"host CPU; the Python reference cannot travel to the GPU box"},
+                                   f"host CPU (capped at 5 steps whatever --steps says); ONE {args.batch}-image CPU "
+                                   f"process at every --gpus N (the CPU path has no multi-GPU form); the Python "
+                                   f"reference cannot travel to the GPU box"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -191,80 +194,88 @@ def run_b200(args):
         shape = (3, args.size, args.size)
     if not graph_ok and not args.graph:
         args.no_graph = True  # CUT / RevGAN recipes run eagerly by default (--graph: CUT's segmented capture)
-    conf = getattr(presets, preset)(batch_size=args.batch, cuda_graph=not args.no_graph,
-                                    **({"input_prefetch": True} if args.e2e_pipeline else {}))
-    model = build_gan(conf)
-    # synthetic inputs U(-1, 1) (images are normalised to [-1, 1] in the reference); each rank draws its own shard
-    gen = torch.Generator(device="cpu").manual_seed(1 + rank)
-    a_host = torch.rand((args.batch,) + tuple(shape), generator=gen) * 2 - 1
-    b_host = torch.rand((args.batch,) + tuple(shape), generator=gen) * 2 - 1
-    a_host, b_host = a_host.pin_memory(), b_host.pin_memory()
-    a_dev, b_dev = a_host.to(dev), b_host.to(dev)
     flush = torch.empty(2 * 126 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(resident=True):
-        if resident:
-            model.set_input({"A": a_dev, "B": b_dev})
-        else:
-            model.set_input({"A": a_host, "B": b_host})  # H2D from pinned memory inside the timed region
-        model.optimize_parameters()
+    def measure(batch, with_clocks):
+        """Build the workload at `batch` per GPU and time args.steps resident steps, then args.steps e2e steps."""
+        conf = getattr(presets, preset)(batch_size=batch, cuda_graph=not args.no_graph,
+                                        **({"input_prefetch": True} if args.e2e_pipeline else {}))
+        model = build_gan(conf)
+        # synthetic inputs U(-1, 1) (images are normalised to [-1, 1] in the reference); each rank draws its own shard
+        gen = torch.Generator(device="cpu").manual_seed(1 + rank)
+        a_host = torch.rand((batch,) + tuple(shape), generator=gen) * 2 - 1
+        b_host = torch.rand((batch,) + tuple(shape), generator=gen) * 2 - 1
+        a_host, b_host = a_host.pin_memory(), b_host.pin_memory()
+        a_dev, b_dev = a_host.to(dev), b_host.to(dev)
 
-    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        def step(resident=True):
+            if resident:
+                model.set_input({"A": a_dev, "B": b_dev})
+            else:
+                model.set_input({"A": a_host, "B": b_host})  # H2D from pinned memory inside the timed region
+            model.optimize_parameters()
 
-    def timed(n, resident):
-        evs = []
-        pending = None  # --e2e-pipeline: event after the D2H copy of the previous step's loss
-        for i in range(n):
-            flush.zero_()  # evict L2 between timed iterations
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            step(resident)
-            if not resident:
-                if args.e2e_pipeline:
-                    # every step's loss still travels to the host, but the host waits for step i-1's copy only after
-                    # step i has been enqueued (a tracker that logs with one step of lag), so the GPU never idles
-                    loss_host[i & 1].copy_(next(iter(model.losses.values())).detach().reshape(()), non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record()
-                    if pending is not None:
-                        pending.synchronize()
-                    pending = ev
-                else:
-                    _ = float(next(iter(model.losses.values())))  # D2H read of a step result
-            e1.record()
-            evs.append((e0, e1))
-        torch.cuda.synchronize()
-        return sum(e0.elapsed_time(e1) for e0, e1 in evs) / 1e3
+        def timed(n, resident):
+            evs = []
+            pending = None  # --e2e-pipeline: event after the D2H copy of the previous step's loss
+            for i in range(n):
+                flush.zero_()  # evict L2 between timed iterations
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                step(resident)
+                if not resident:
+                    if args.e2e_pipeline:
+                        # every step's loss still travels to the host, but the host waits for step i-1's copy only
+                        # after step i has been enqueued (a tracker that logs with one step of lag)
+                        loss_host[i & 1].copy_(next(iter(model.losses.values())).detach().reshape(()), non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record()
+                        if pending is not None:
+                            pending.synchronize()
+                        pending = ev
+                    else:
+                        _ = float(next(iter(model.losses.values())).detach())  # D2H read of a step result
+                e1.record()
+                evs.append((e0, e1))
+            torch.cuda.synchronize()
+            return sum(e0.elapsed_time(e1) for e0, e1 in evs) / 1e3
 
-    # graph mode: 11 eager iterations precede the capture (PyTorch's DDP + CUDA-graph recipe), then 2 replays
-    n_warm = max(args.warmup, 3) + (0 if args.no_graph else model.graph_warmup_iters + 2)
+        # graph mode: 11 eager iterations precede the capture (PyTorch's DDP + CUDA-graph recipe), then 2 replays
+        n_warm = max(args.warmup, 3) + (0 if args.no_graph else model.graph_warmup_iters + 2)
+        for _ in range(n_warm):
+            step()
+        barrier()
+        sampler = ClockSampler(local_rank) if (rank == 0 and with_clocks) else None  # rank 0's GPU is the one reported
+        l0 = lib.gb_launch_count()
+        barrier()
+        t = timed(args.steps, True)
+        barrier()
+        launches = lib.gb_launch_count() - l0
+        clocks = sampler.stop() if sampler is not None else None
+        if getattr(model, "graph_launches_per_step", None):
+            launches = model.graph_launches_per_step * args.steps
+        # e2e: host buffers in, loss scalar out
+        barrier()
+        t_e2e = timed(args.steps, False)
+        barrier()
+        times = torch.tensor([t, t_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        t, t_e2e = times.tolist()
+        return dict(model=model, a_dev=a_dev, b_dev=b_dev, t=t, t_e2e=t_e2e, launches=launches, clocks=clocks,
+                    n_warm=n_warm, in_bytes=2 * a_host.numel() * 4)
+
     if not default_wl:
         args.no_cpu_baseline = True  # the CPU leg times the headline configuration only
-    for _ in range(n_warm):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None  # one poller: rank 0's GPU is the one reported
-    l0 = lib.gb_launch_count()
-    barrier()
-    t = timed(args.steps, True)
-    barrier()
-    launches = lib.gb_launch_count() - l0
-    clocks = sampler.stop() if sampler is not None else None
-    if getattr(model, "graph_launches_per_step", None):
-        launches = model.graph_launches_per_step * args.steps
-    # e2e: host buffers in, loss scalar out
-    barrier()
-    t_e2e = timed(args.steps, False)
-    barrier()
-    times = torch.tensor([t, t_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t, t_e2e = times.tolist()
+    m = measure(args.batch, True)
+    model, a_dev, b_dev, t, t_e2e = m["model"], m["a_dev"], m["b_dev"], m["t"], m["t_e2e"]
+    launches, clocks, n_warm = m["launches"], m["clocks"], m["n_warm"]
 
     roof = None
     aux_errors = {}
@@ -288,9 +299,23 @@ def run_b200(args):
                    "sample": f"3 full CycleGAN steps (batch {args.batch}) of the CPU oracle after 1 warm-up, median"}
         except Exception as e:  # noqa: BLE001
             aux_errors["cpu_baseline"] = f"{type(e).__name__}: {e}"
+    batch1 = None
+    if world == 1 and default_wl and args.batch != 1 and not args.no_batch1:
+        # BASELINE config 1 is quoted at batch 1: the same workload at batch 1 per GPU, same harness, as extra keys
+        try:
+            del model
+            m1 = measure(1, False)
+            batch1 = {"value": args.steps / m1["t"], "unit": UNIT, "ms_per_step": m1["t"] / args.steps * 1e3,
+                      "e2e": args.steps / m1["t_e2e"], "global_batch": 1}
+            if args.size == 256:
+                peaks = profiler.measured_peaks()
+                batch1["conv_tflops_step"] = conv_flops_per_step(1) * args.steps / m1["t"] / 1e12
+                batch1["frac_of_sustained_bf16_step"] = batch1["conv_tflops_step"] / peaks["bf16_tflops_sustained"]
+        except Exception as e:  # noqa: BLE001
+            aux_errors["batch1"] = f"{type(e).__name__}: {e}"
     if rank == 0:
         imgs = args.batch * world * args.steps
-        in_bytes = 2 * a_host.numel() * 4
+        in_bytes = m["in_bytes"]
         line = {
             "metric": metric, "value": imgs / t, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True,
@@ -309,6 +334,8 @@ def run_b200(args):
             line["roofline_detail"] = roof["detail"]
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if batch1 is not None:
+            line["batch1"] = batch1
         if aux_errors:
             line["aux_errors"] = aux_errors
         print(json.dumps(line), flush=True)

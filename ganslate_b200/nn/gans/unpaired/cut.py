@@ -10,7 +10,7 @@ import torch
 from torch import nn
 from torch.nn.parallel import DistributedDataParallel
 
-from ganslate_b200 import configs
+from ganslate_b200 import configs, ops
 from ganslate_b200.nn import layers
 from ganslate_b200.nn.gans.base import BaseGAN
 from ganslate_b200.nn.losses.adversarial_loss import AdversarialLoss
@@ -198,7 +198,9 @@ class CUT(BaseGAN):
 
 class FeaturePatchMLP(nn.Module):
     """cut.py:229-282: gather `num_patches` positions (same ids for every batch item), 2-layer MLP, L2 normalise.
-    The two Linear layers are plain library GEMMs on 256 rows (cuBLAS through torch.nn.Linear)."""
+    The nn.Linear modules are parameter containers (same state_dict keys `mlps.{i}.{0,2}.{weight,bias}` and init as
+    the reference); gather + both layers + the normalisation run as ONE fused sm_100a launch per feature
+    (ops.PatchMlpFn -> csrc/patch_mlp.cu), fp32 FMAs, no library GEMM."""
 
     def __init__(self, channels_per_feature, num_patches=256, nc=256):
         super().__init__()
@@ -211,20 +213,18 @@ class FeaturePatchMLP(nn.Module):
         device = feats[0].device
         return_feats, return_ids = [], []
         for i, feat in enumerate(feats):
-            if feat.dim() == 5:
-                feat = feat.permute(0, 2, 3, 4, 1).flatten(1, 3)
-            else:
-                feat = feat.permute(0, 2, 3, 1).flatten(1, 2)
+            n_pos = feat[0, 0].numel()
             if self.num_patches > 0:
                 if patch_ids is not None:
                     patch_id = patch_ids[i]
                 else:
-                    patch_id = torch.randperm(feat.shape[1], device=device)
+                    patch_id = torch.randperm(n_pos, device=device)
                     patch_id = patch_id[:int(min(self.num_patches, len(patch_id)))]
-                feat_patch = feat[:, patch_id, :]
+                ids = patch_id
             else:
-                feat_patch, patch_id = feat, []
-            feat_patch = self.l2norm(self.mlps[i](feat_patch.flatten(0, 1)))
+                patch_id, ids = [], torch.arange(n_pos, device=device)
+            lin1, lin2 = self.mlps[i][0], self.mlps[i][2]
+            feat_patch = ops.PatchMlpFn.apply(feat, ids, lin1.weight, lin1.bias, lin2.weight, lin2.bias)
             return_feats.append(feat_patch)
             return_ids.append(patch_id)
         return return_feats, return_ids

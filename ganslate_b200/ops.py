@@ -962,3 +962,52 @@ class PatchNCEFn(torch.autograd.Function):
         _cabi.check(_cabi.lib().gb_patchnce_bwd(k.data_ptr(), probs.data_ptr(), dloss.data_ptr(), batch, P, D, T,
                                                 dq.data_ptr(), _stream()), "gb_patchnce_bwd")
         return dq, None, None, None
+
+
+class PatchMlpFn(torch.autograd.Function):
+    """CUT's FeaturePatchMLP for one feature (ganslate/nn/gans/unpaired/cut.py:262-276): gather the positions `ids`
+    of feat (N, C, *spatial), Linear + ReLU + Linear, L2-normalise -- one fused launch forward (gb_patch_mlp_fwd), the
+    row pass + two parameter-gradient launches backward (gb_patch_mlp_bwd).  fp32 FMA arithmetic, no library GEMM."""
+
+    @staticmethod
+    def forward(ctx, feat, ids, w1, b1, w2, b2):
+        _require_cuda(feat, "feature map")
+        f = feat.contiguous().float()
+        N, Cc = f.shape[:2]
+        F = f.numel() // (N * Cc)
+        ids = ids.to(device=f.device, dtype=torch.int64).contiguous()
+        P, nc = ids.numel(), w1.shape[0]
+        assert w1.shape == (nc, Cc) and w2.shape == (nc, nc), (w1.shape, w2.shape, Cc)
+        w1c, b1c, w2c, b2c = (t.detach().contiguous().float() for t in (w1, b1, w2, b2))
+        R = N * P
+        xg = torch.empty((R, Cc), dtype=torch.float32, device=f.device)
+        h = torch.empty((R, nc), dtype=torch.float32, device=f.device)
+        z = torch.empty((R, nc), dtype=torch.float32, device=f.device)
+        y = torch.empty((R, nc), dtype=torch.float32, device=f.device)
+        _call("patch_mlp", 0, "byte", "gb_patch_mlp_fwd", _cabi.lib().gb_patch_mlp_fwd, f.data_ptr(), ids.data_ptr(), N, Cc,
+              F, P, w1c.data_ptr(), b1c.data_ptr(), w2c.data_ptr(), b2c.data_ptr(), nc, xg.data_ptr(), h.data_ptr(),
+              z.data_ptr(), y.data_ptr(), _stream())
+        ctx.save_for_backward(xg, h, z, ids, w1c, w2c)
+        ctx.geom = (N, Cc, F, P, nc, tuple(feat.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xg, h, z, ids, w1c, w2c = ctx.saved_tensors
+        N, Cc, F, P, nc, fshape = ctx.geom
+        dev = xg.device
+        dy = dy.contiguous().float()
+        R = N * P
+        dz = torch.empty((R, nc), dtype=torch.float32, device=dev)
+        dh = torch.empty((R, nc), dtype=torch.float32, device=dev)
+        dfeat = torch.zeros(fshape, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        need_w = any(ctx.needs_input_grad[2:])
+        dw1 = torch.empty_like(w1c) if need_w else None
+        db1 = torch.empty(nc, dtype=torch.float32, device=dev) if need_w else None
+        dw2 = torch.empty_like(w2c) if need_w else None
+        db2 = torch.empty(nc, dtype=torch.float32, device=dev) if need_w else None
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        _call("patch_mlp", 0, "byte", "gb_patch_mlp_bwd", _cabi.lib().gb_patch_mlp_bwd, dy.data_ptr(), xg.data_ptr(),
+              h.data_ptr(), z.data_ptr(), ids.data_ptr(), N, Cc, F, P, w1c.data_ptr(), w2c.data_ptr(), nc, dz.data_ptr(),
+              dh.data_ptr(), ptr(dfeat), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), _stream())
+        return dfeat, None, dw1, db1, dw2, db2

@@ -84,7 +84,8 @@ def conv_roofline(model, a_dev, b_dev, steps=3, with_traffic=True):
     dominant = {
         "bound": "tensor", "achieved": round(w_conv / t_conv / 1e12, 2), "peak": peaks["bf16_tflops_sustained"],
         "unit": "TFLOP/s", "frac": round(w_conv / t_conv / 1e12 / peaks["bf16_tflops_sustained"], 4), "traffic": None,
-        "kernel": "igemm_data_kernel / igemm_wgrad_kernel (all conv fwd+dgrad+wgrad launches of a step)",
+        "kernel": "all convolution launches of a step: igemm_tma_kernel / igemm_pair_kernel (forward, data gradient) + "
+                  "igemm_wgrad_kernel (weight gradient), plus the halo / gather kernels of the 3-channel layers",
         "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
         "avg_launch_us": round(t_conv / n_conv * 1e6, 2), "launches_per_step": n_conv // steps,
         "share_of_kernel_time": round(t_conv / total_t, 4),

@@ -245,6 +245,19 @@ int gb_patchnce_fwd(const float* q, const float* k, int B, int P, int D, float T
 int gb_patchnce_bwd(const float* k, const float* probs, const float* dloss, int B, int P, int D, float T, float* dq,
                     void* stream);
 
+/* FeaturePatchMLP (CUT, ganslate/nn/gans/unpaired/cut.py:229-294): for a feature map feat (N, C, F) fp32 (F = flattened
+ * spatial positions) and P position ids shared by every image: x = feat[:, :, ids] as rows (N*P, C),
+ * h = relu(x W1^T + b1), z = h W2^T + b2, y = z / (||z||_2 + 1e-7); W1 (nc, C), W2 (nc, nc) in torch.nn.Linear layout.
+ * Forward saves x (xg), h, z for the backward; replaces feat[:, patch_id, :] + nn.Linear x 2 + LNorm (cut.py:262-276).
+ * Backward: dy (N*P, nc) -> dfeat (N, C, F), zero-initialised by the caller (NULL: not needed), and dW1, db1, dW2,
+ * db2 (NULL: not needed); dz, dh are (N*P, nc) scratch. fp32 CUDA-core arithmetic, deterministic. */
+int gb_patch_mlp_fwd(const float* feat, const int64_t* ids, int N, int C, int64_t F, int P, const float* W1,
+                     const float* b1, const float* W2, const float* b2, int nc, float* xg, float* h, float* z,
+                     float* y, void* stream);
+int gb_patch_mlp_bwd(const float* dy, const float* xg, const float* h, const float* z, const int64_t* ids, int N,
+                     int C, int64_t F, int P, const float* W1, const float* W2, int nc, float* dz, float* dh,
+                     float* dfeat, float* dW1, float* db1, float* dW2, float* db2, void* stream);
+
 /* ---- optimizer -------------------------------------------------------------------------------
  * Multi-tensor Adam step with torch.optim.Adam semantics (betas, eps; no weight decay / amsgrad), replacing the
  * optimizer.step() calls at ganslate/nn/gans/unpaired/cyclegan.py:108,121 (optimizers built at :76-82).

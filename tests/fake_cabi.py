@@ -422,6 +422,44 @@ class FakeLib:
         _flat(dq, B * P * D, torch.float32).view(B, P, D).copy_(out)
         return 0
 
+    def gb_patch_mlp_fwd(self, feat, ids, N, C, F, P, W1, b1, W2, b2, nc, xg, h, z, y, stream):
+        self._count("gb_patch_mlp_fwd")
+        f = _flat(feat, N * C * F, torch.float32).view(N, C, F)
+        idx = _flat(ids, P, torch.int64)
+        x = f[:, :, idx].permute(0, 2, 1).reshape(N * P, C)
+        w1, w2 = _flat(W1, nc * C, torch.float32).view(nc, C), _flat(W2, nc * nc, torch.float32).view(nc, nc)
+        hh = torch.relu(x @ w1.t() + _flat(b1, nc, torch.float32))
+        zz = hh @ w2.t() + _flat(b2, nc, torch.float32)
+        yy = zz / (zz.pow(2).sum(1, keepdim=True).sqrt() + 1e-7)
+        for dst, src, n in ((xg, x, N * P * C), (h, hh, N * P * nc), (z, zz, N * P * nc), (y, yy, N * P * nc)):
+            _flat(dst, n, torch.float32).copy_(src.reshape(-1))
+        return 0
+
+    def gb_patch_mlp_bwd(self, dy, xg, h, z, ids, N, C, F, P, W1, W2, nc, dz, dh, dfeat, dW1, db1, dW2, db2, stream):
+        self._count("gb_patch_mlp_bwd")
+        R = N * P
+        g = _flat(dy, R * nc, torch.float32).view(R, nc)
+        x, hh, zz = (_flat(xg, R * C, torch.float32).view(R, C), _flat(h, R * nc, torch.float32).view(R, nc),
+                     _flat(z, R * nc, torch.float32).view(R, nc))
+        w1, w2 = _flat(W1, nc * C, torch.float32).view(nc, C), _flat(W2, nc * nc, torch.float32).view(nc, nc)
+        nrm = zz.pow(2).sum(1, keepdim=True).sqrt()
+        inv = 1.0 / (nrm + 1e-7)
+        gz = g * inv - zz * ((g * zz).sum(1, keepdim=True) * inv * inv / nrm)
+        gh = (gz @ w2) * (hh > 0)
+        _flat(dz, R * nc, torch.float32).copy_(gz.reshape(-1))
+        _flat(dh, R * nc, torch.float32).copy_(gh.reshape(-1))
+        if dfeat:
+            idx = _flat(ids, P, torch.int64)
+            d = _flat(dfeat, N * C * F, torch.float32).view(N, C, F)
+            d[:, :, idx] = (gh @ w1).view(N, P, C).permute(0, 2, 1)
+        if dW2:
+            _flat(dW2, nc * nc, torch.float32).copy_((gz.t() @ hh).reshape(-1))
+            _flat(db2, nc, torch.float32).copy_(gz.sum(0))
+        if dW1:
+            _flat(dW1, nc * C, torch.float32).copy_((gh.t() @ x).reshape(-1))
+            _flat(db1, nc, torch.float32).copy_(gh.sum(0))
+        return 0
+
     # ------------------------------------------------------------------ layout / padding
     def gb_nchw_to_cl(self, src, Cc, dst, pre, dst_fp32, stream):
         self._count("gb_nchw_to_cl")

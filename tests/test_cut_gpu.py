@@ -81,3 +81,37 @@ def test_cut_step_vs_oracle():
         for k in po:
             if k.endswith("weight") and po[k].grad is not None:
                 assert cosine(pg[k].grad, po[k].grad) > 0.85, (name, k, cosine(pg[k].grad, po[k].grad))
+
+
+@pytest.mark.parametrize("shape,P,nc", [((1, 3, 70, 70), 256, 256), ((2, 128, 32, 32), 256, 256), ((1, 256, 16, 16), 256, 256),
+                                        ((1, 24, 6, 9, 7), 100, 64), ((3, 256, 64, 64), 256, 256)])
+def test_patch_mlp_kernels_match_torch(shape, P, nc):
+    """csrc/patch_mlp.cu (gather + Linear + ReLU + Linear + L2 norm, fp32 FMAs) against the reference's module chain
+    (cut.py:262-276) evaluated by torch in fp32 on the CPU: outputs and every gradient <= 1e-4 max-relative."""
+    from ganslate_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    C = shape[1]
+    feat = torch.randn(shape, generator=g)
+    n_pos = feat[0, 0].numel()
+    ids = torch.randperm(n_pos, generator=g)[:P]
+    w1, b1 = torch.randn(nc, C, generator=g) * 0.1, torch.randn(nc, generator=g) * 0.1
+    w2, b2 = torch.randn(nc, nc, generator=g) * 0.05, torch.randn(nc, generator=g) * 0.1
+    dy = torch.randn(shape[0] * P, nc, generator=g)
+
+    def ref(f, w1, b1, w2, b2):
+        x = f.flatten(2).permute(0, 2, 1)[:, ids, :].flatten(0, 1)
+        z = torch.relu(x @ w1.t() + b1) @ w2.t() + b2
+        return z / (z.pow(2).sum(1, keepdim=True).pow(0.5) + 1e-7)
+
+    tr = [t.clone().requires_grad_(True) for t in (feat, w1, b1, w2, b2)]
+    yr = ref(*tr)
+    yr.backward(dy)
+    to = [t.clone().cuda().requires_grad_(True) for t in (feat, w1, b1, w2, b2)]
+    yo = ops.PatchMlpFn.apply(to[0], ids.cuda(), *to[1:])
+    yo.backward(dy.cuda())
+    torch.cuda.synchronize()
+    def mr(a, b):
+        return ((a.cpu() - b).abs().max() / (b.abs().max() + 1e-30)).item()
+    assert mr(yo.detach(), yr.detach()) <= 1e-4
+    for name, a, b in zip(("dfeat", "dW1", "db1", "dW2", "db2"), to, tr):
+        assert mr(a.grad, b.grad) <= 1e-4, (name, mr(a.grad, b.grad))

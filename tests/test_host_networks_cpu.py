@@ -648,6 +648,7 @@ def test_teacher_forced_parity_harness_on_the_fake_backend(monkeypatch):
     free = summarize(forced_network_parity(ours, ref, x, force=False))
     assert forced["fwd_max_rel"] <= 1e-2 and forced["bwd_max_rel"] <= 1e-2 and forced["wgrad_max_rel"] <= 1e-4, forced
     assert free["bwd_rel_l2"] > 20 * forced["bwd_rel_l2"] and free["wgrad_rel_l2"] > 1e-2, (free, forced)
+    assert forced["bwd_outlier_frac"] <= 1e-5 and free["bwd_outlier_frac"] > 1e-3, (free, forced)
     refd = O.init_weights(O.OraclePatchGAN2D(3, 16, 2))
     oursd = PatchGAN2D(3, 16, 2, (4, 4), "instance")
     _load(oursd, refd)
