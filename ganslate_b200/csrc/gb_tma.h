@@ -11,7 +11,29 @@ bool gb_tma_available();
 // the 64-wide box zero-fills the rest).  Returns 0 on success (maps are cached by view + box + strides).
 int gb_tma_activation_map(const gb_view& v, int tw, int th, CUtensorMap* out, const int* mul = nullptr, int c_valid = 0);
 
+// 5-D map {C, W, H, D, N} of a channels-last OUTPUT view (bf16, or fp32 when `fp32` is set) for the TMA-store epilogue:
+// box {128 bytes of channels (64 bf16 / 32 fp32), tw * mul_x, th * mul_y, mul_z, 1} with traversal strides `mul` (the
+// output multiplier of a parity-class decomposed convolution: the box scatters to pixels c, c + mul, ...), 128B
+// swizzle.  Stores clip at the tensor's extents, so tiles that overhang the image need no masking.
+int gb_tma_store_map(const gb_view& v, int tw, int th, const int* mul, int fp32, CUtensorMap* out);
+
 #ifdef __CUDACC__
+// smem (128B-swizzled tile, written by the generic proxy + fence.proxy.async) -> global, clipped at the tensor bounds
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+// same, global += smem (fp32 add performed at the L2)
+__device__ __forceinline__ void tma_reduce_add_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3,
+                                                  int c4) {
+  asm volatile("cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// until the bulk stores of this thread have READ their shared-memory source (the CTA may then reuse / release it)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }

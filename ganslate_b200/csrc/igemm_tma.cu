@@ -46,6 +46,8 @@ struct TileGeom {
   int ntx, nty;
   int ntiles;                            // per class (max over classes is the grid)
   int nstages;                           // depth of the smem ring (<= TCfg::STAGES); small rings let two CTAs share an SM
+  int store_mode;                        // 0 = per-thread global stores (gb_conv_epilogue); TMA-store epilogue: 1 = bf16,
+                                         // 2 = fp32, 3 = fp32 accumulated into the destination (bulk reduce-add)
   // bring-up instrumentation (tools/conv_timeline.py; both 0 in every ordinary launch):
   int mode;                              // knob 30 (bits): 1 = producer skips the loads, 2 = issuer skips the MMAs, 4 = no epilogue
   unsigned long long* ts;                // gb_debug_timeline(): 8 words per CTA (smid, globaltimer, 6 clock64 stamps)
@@ -59,10 +61,128 @@ __device__ __forceinline__ void ts_put(const TileGeom& tg, int slot) {
 }
 
 
+// ---------------------------------------------------------------------------------------------- TMA-store epilogue
+// TMEM accumulator -> registers (+bias, activation) -> 128B-swizzled staging tiles in the (now idle) operand ring ->
+// ONE bulk tensor store per 128-byte channel group, issued by one thread.  The hardware writes whole 128-byte rows and
+// clips the tile at the image bounds; the per-thread version (gb_conv_epilogue) issues 16-byte stores 512 B apart and
+// measured 6.2 K (bf16) / 10.4 K (fp32) cycles per 128 x 256 tile against an 18.4 K cycle main loop
+// (profiles/r02b_conv_timeline_b8.txt).  InstanceNorm statistics are summed from the staged bf16 tile: 16-byte reads,
+// eight channels per thread, shared-memory atomics, one global atomic per channel and CTA.
+//   staging layout: sub-tile s (64 bf16 / 32 fp32 channels) at s * 16 KB; row r (pixel h * tw + w) at r * 128 B; its
+//   16-byte chunk j at ((j ^ (r & 7)) << 4) -- what CU_TENSOR_MAP_SWIZZLE_128B expects, and conflict-free for a warp
+//   whose lanes are consecutive rows.
+template <int BN>
+__device__ __forceinline__ void tma_store_epilogue(const gb_conv_params& p, const TileGeom& tg, const CUtensorMap* map_o,
+                                                   uint32_t tmem_base, int warp, int lane, bool have_acc, bool row_ok,
+                                                   int n0, const float* bias_s, uint8_t* stage, float* sacc,
+                                                   int cx, int cy, int cz, int n) {
+  const int tid = warp * 32 + lane;
+  const int lg = warp & 3, half = warp >> 2;
+  const int row = lg * 32 + lane;
+  const bool fp32 = tg.store_mode >= 2;
+  const bool want_stats = !fp32 && p.stats != nullptr;
+  constexpr int CH = 32;
+  constexpr int COLS_PER_HALF = BN / 2;
+  static_assert(BN >= 64, "TMA-store epilogue needs BN >= 64");
+  if (want_stats)
+    for (int i = tid; i < BN * 2; i += 256) sacc[i] = 0.f;
+  const uint32_t rsw = (uint32_t)(row & 7);
+#pragma unroll 1
+  for (int c0 = half * COLS_PER_HALF; c0 < (half + 1) * COLS_PER_HALF; c0 += CH) {
+    uint32_t acc[CH];
+    if (have_acc) {
+      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, acc);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int i = 0; i < CH; ++i) acc[i] = 0u;
+    }
+    float v[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      float t = __uint_as_float(acc[i]) + bias_s[c0 + i];
+      if (p.act == GB_ACT_TANH) t = tanhf(t);
+      else if (p.act == GB_ACT_LEAKY) t = t > 0.f ? t : t * p.act_slope;
+      else if (p.act == GB_ACT_RELU) t = fmaxf(t, 0.f);
+      v[i] = (row_ok || fp32) ? t : 0.f;   // rows outside the image: zeros for the statistics (the store clips them)
+    }
+    if (fp32) {
+      // 32 fp32 columns = one 128-byte row of sub-tile c0 / 32
+      uint8_t* dst = stage + (size_t)(c0 >> 5) * 16384 + (size_t)row * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(dst + (((uint32_t)j ^ rsw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      // 32 bf16 columns = half a 128-byte row (chunks jb .. jb + 3) of sub-tile c0 / 64
+      uint8_t* dst = stage + (size_t)(c0 >> 6) * 16384 + (size_t)row * 128;
+      const uint32_t jb = (uint32_t)((c0 & 63) >> 3);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+        o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        *reinterpret_cast<uint4*>(dst + (((jb + (uint32_t)j) ^ rsw) << 4)) = o;
+      }
+    }
+  }
+  fence_proxy_async();   // staging writes (generic proxy) -> visible to the bulk store (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    const int inner = fp32 ? 32 : 64;
+    const uint32_t s0 = smem_u32(stage);
+    for (int sub = 0; sub * inner < BN; ++sub) {
+      const int c = n0 + sub * inner;
+      if (c >= p.out.C) break;
+      if (tg.store_mode == 3) tma_reduce_add_5d(map_o, s0 + sub * 16384, c, cx, cy, cz, n);
+      else tma_store_5d(map_o, s0 + sub * 16384, c, cx, cy, cz, n);
+    }
+    tma_store_commit();
+  }
+  if (want_stats) {
+    // thread -> (16-byte chunk cg of a row = 8 channels, row group rg); rows rg, rg + RG, ... of the tile
+    constexpr int CPR = BN / 8;        // chunks per row over all sub-tiles
+    constexpr int RG = 256 / CPR;      // row groups
+    const int cg = tid % CPR, rg = tid / CPR;
+    const uint8_t* src = stage + (size_t)(cg >> 3) * 16384;
+    const uint32_t jc = (uint32_t)(cg & 7);
+    float s1[8], s2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
+    const int rows = tg.tw * tg.th;
+    for (int r = rg; r < rows; r += RG) {
+      const uint4 q4 = *reinterpret_cast<const uint4*>(src + (size_t)r * 128 + ((jc ^ (uint32_t)(r & 7)) << 4));
+      float2 f;
+      f = unpack_bf16x2(q4.x); s1[0] += f.x; s2[0] = fmaf(f.x, f.x, s2[0]); s1[1] += f.y; s2[1] = fmaf(f.y, f.y, s2[1]);
+      f = unpack_bf16x2(q4.y); s1[2] += f.x; s2[2] = fmaf(f.x, f.x, s2[2]); s1[3] += f.y; s2[3] = fmaf(f.y, f.y, s2[3]);
+      f = unpack_bf16x2(q4.z); s1[4] += f.x; s2[4] = fmaf(f.x, f.x, s2[4]); s1[5] += f.y; s2[5] = fmaf(f.y, f.y, s2[5]);
+      f = unpack_bf16x2(q4.w); s1[6] += f.x; s2[6] = fmaf(f.x, f.x, s2[6]); s1[7] += f.y; s2[7] = fmaf(f.y, f.y, s2[7]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&sacc[(cg * 8 + e) * 2 + 0], s1[e]);
+      atomicAdd(&sacc[(cg * 8 + e) * 2 + 1], s2[e]);
+    }
+    __syncthreads();
+    for (int i = tid; i < BN; i += 256) {
+      const int col = n0 + i;
+      if (col < p.ncols) {
+        float* dst = p.stats + ((int64_t)n * p.out.C + col) * 2;
+        atomicAdd(dst, sacc[i * 2]);
+        atomicAdd(dst + 1, sacc[i * 2 + 1]);
+      }
+    }
+  }
+  if (tid == 0) tma_store_wait_read();
+}
+
 template <int BN>
 __global__ void __launch_bounds__(256, TCfg<BN>::MIN_CTAS)
 igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant__ CUtensorMap map_a,
-                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TileGeom tg) {
+                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o,
+                 const __grid_constant__ TileGeom tg) {
   gb_pdl_enter();
   using C = TCfg<BN>;
   constexpr int MAXS = 8;  // barrier slots (TCfg::STAGES <= 8)
@@ -76,6 +196,7 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 144);
   int8_t* taps_s = reinterpret_cast<int8_t*>(tail + 192);
   __shared__ float bias_s[BN];
+  __shared__ float stat_s[BN >= 64 ? 2 * BN : 2];   // TMA-store epilogue: per-channel (sum, sum^2) of this tile
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -203,12 +324,24 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
     const int h = (int)gb_div((uint32_t)row, tg.div_tw), w = row - h * tg.tw;
     const int qy = y0 + h, qx = x0 + w;
     const bool row_ok = h < tg.th && qy < q[1] && qx < q[2];
-    int64_t ooff = 0;
-    if (row_ok)
-      ooff = gb_pix_offset(p.out, n, z0 * p.out_mul[0] + cc.off[0], qy * p.out_mul[1] + cc.off[1],
-                           qx * p.out_mul[2] + cc.off[2]);
-    // (stage 0 of the ring is free once the accumulator is complete: scratch of the CTA-level statistics sum)
-    gb_conv_epilogue<BN>(p, tmem_base, warp, lane, KB > 0, row_ok, ooff, n0, bias_s, n, reinterpret_cast<float*>(smem));
+    bool done = false;
+    if constexpr (BN >= 64) {
+      if (tg.store_mode != 0) {
+        // (the operand ring is idle once the accumulator is complete: staging tiles of the bulk store)
+        tma_store_epilogue<BN>(p, tg, &map_o, tmem_base, warp, lane, KB > 0, row_ok, n0, bias_s, smem, stat_s,
+                               x0 * p.out_mul[2] + cc.off[2], y0 * p.out_mul[1] + cc.off[1],
+                               z0 * p.out_mul[0] + cc.off[0], n);
+        done = true;
+      }
+    }
+    if (!done) {
+      int64_t ooff = 0;
+      if (row_ok)
+        ooff = gb_pix_offset(p.out, n, z0 * p.out_mul[0] + cc.off[0], qy * p.out_mul[1] + cc.off[1],
+                             qx * p.out_mul[2] + cc.off[2]);
+      // (stage 0 of the ring is free once the accumulator is complete: scratch of the CTA-level statistics sum)
+      gb_conv_epilogue<BN>(p, tmem_base, warp, lane, KB > 0, row_ok, ooff, n0, bias_s, n, reinterpret_cast<float*>(smem));
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -300,6 +433,33 @@ int gb_tma_weight_map(const void* w, int kpad, int rows, int bn, CUtensorMap* ou
   return 0;
 }
 
+int gb_tma_store_map(const gb_view& v, int tw, int th, const int* mul, int fp32, CUtensorMap* out) {
+  const int m[3] = {mul ? mul[0] : 1, mul ? mul[1] : 1, mul ? mul[2] : 1};
+  const int esz = fp32 ? 4 : 2;
+  std::string key("store", 5);
+  key.append(reinterpret_cast<const char*>(&v), sizeof(gb_view));
+  key.append(reinterpret_cast<const char*>(&tw), sizeof(int)).append(reinterpret_cast<const char*>(&th), sizeof(int));
+  key.append(reinterpret_cast<const char*>(m), sizeof(m)).append(reinterpret_cast<const char*>(&fp32), sizeof(int));
+  std::lock_guard<std::mutex> lk(g_map_mutex);
+  auto it = g_map_cache.find(key);
+  if (it != g_map_cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  cuuint64_t dims[5] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.D, (cuuint64_t)v.N};
+  cuuint64_t strides[4] = {(cuuint64_t)v.sx * esz, (cuuint64_t)v.sy * esz, (cuuint64_t)v.sz * esz, (cuuint64_t)v.sn * esz};
+  cuuint32_t box[5] = {(cuuint32_t)(128 / esz), (cuuint32_t)(tw * m[2]), (cuuint32_t)(th * m[1]), (cuuint32_t)m[0], 1};
+  cuuint32_t es[5] = {1, (cuuint32_t)m[2], (cuuint32_t)m[1], (cuuint32_t)m[0], 1};
+  GB_CHECK(box[1] <= 256 && box[2] <= 256 && box[3] <= 256, "TMA store box too large for the output stride");
+  CUresult r = encode_fn()(out, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, v.ptr, dims,
+                           strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(output) failed: %d", (int)r);
+  if (g_map_cache.size() > 4096) g_map_cache.clear();
+  g_map_cache[key] = *out;
+  return 0;
+}
+
 // Pixel-window views (8 pixels x 8 channels read as one 64-channel "pixel", pixel stride 16 B) need a tensor map
 // whose pixel stride is smaller than its channel extent; probe once whether the driver encodes it.
 extern "C" int gb_tma_window_supported(void) {
@@ -327,7 +487,8 @@ extern "C" int gb_debug_timeline(void* buf, long long max_ctas) {
 namespace {
 
 template <int BN>
-int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb, const TileGeom& tg, cudaStream_t st) {
+int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const TileGeom& tg,
+           cudaStream_t st) {
   using C = TCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -345,11 +506,19 @@ int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb
   const int64_t ctas = (int64_t)grid.x * grid.y * grid.z;
   const int shallow = (100 * 1024) / C::STAGE_BYTES;
   if (BN <= 128 && ctas >= 2 * 148 && kb_max <= 18 && shallow >= 3 && g_gb_knobs[8] == 0) ns = ns < shallow ? ns : shallow;
+  if (g_gb_knobs[8] >= 2 && ns > g_gb_knobs[8]) ns = g_gb_knobs[8];  // bring-up: force a ring of knob-8 stages
   if (ns < 1) ns = 1;
   tgl.nstages = ns;
   tgl.mode = g_gb_knobs[30];
   tgl.ts = (g_timeline != nullptr && ctas <= g_timeline_ctas) ? g_timeline : nullptr;
-  gb_klaunch(igemm_tma_kernel<BN>, grid, 256, ns * C::STAGE_BYTES + 2048, st, p, ma, mb, tgl);
+  // the TMA-store epilogue stages the whole output tile (bf16: BN * 256 B, fp32: BN * 512 B) in the operand ring
+  size_t ring = (size_t)ns * C::STAGE_BYTES;
+  if (tgl.store_mode != 0) {
+    const size_t staging = (size_t)BN * 128 * (tgl.store_mode >= 2 ? 4 : 2);
+    if (staging > (size_t)C::SMEM - 2048) tgl.store_mode = 0;
+    else if (ring < staging) ring = staging;
+  }
+  gb_klaunch(igemm_tma_kernel<BN>, grid, 256, ring + 2048, st, p, ma, mb, mo, tgl);
   g_gb_knobs[15] = 2;
   GB_LAUNCH_CHECK();
   return 0;
@@ -433,16 +602,35 @@ int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st) {
     bn = best_bn;
   }
   if (bn > p.nclass * p.npad) return -1;  // keep every TMA box inside its tensor
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mo;
   if (tw * p.in_mul[2] > 256 || th * p.in_mul[1] > 256) return -1;
   if (gb_tma_activation_map(p.in, tw, th, &ma, p.in_mul, p.in_c_valid)) return 1;
   if (gb_tma_weight_map(p.wpacked, kpad, p.nclass * p.npad, bn, &mb)) return 1;
+  // TMA-store epilogue (knob 29 = 1: per-thread stores): whole 128-byte channel groups of a plain, 16-byte aligned view
+  tg.store_mode = 0;
+  tg.mode = 0;
+  tg.ts = nullptr;
+  {
+    const int esz = p.out_fp32 ? 4 : 2;
+    const int inner = 128 / esz;
+    const bool ok = g_gb_knobs[29] == 0 && bn >= 64 && p.out.pad == 0 && p.out.C % inner == 0 &&
+                    ((uintptr_t)p.out.ptr % 16) == 0 && (p.out.sx * esz) % 16 == 0 && (p.out.sy * esz) % 16 == 0 &&
+                    (p.out.sz * esz) % 16 == 0 && (p.out.sn * esz) % 16 == 0 && tw * p.out_mul[2] <= 256 &&
+                    th * p.out_mul[1] <= 256 && p.out_mul[0] <= 256 && (p.out_fp32 || !p.accumulate);
+    if (ok) {
+      if (gb_tma_store_map(p.out, tw, th, p.out_mul, p.out_fp32, &mo)) return 1;
+      tg.store_mode = p.out_fp32 ? (p.accumulate ? 3 : 2) : 1;
+    } else {
+      mo = ma;  // unused
+    }
+  }
+  g_gb_knobs[31] = tg.store_mode;  // READ-BACK (knob 31): epilogue of the last TMA-fed launch
   switch (bn) {
-    case 16: return launch<16>(p, ma, mb, tg, st);
-    case 32: return launch<32>(p, ma, mb, tg, st);
-    case 64: return launch<64>(p, ma, mb, tg, st);
-    case 128: return launch<128>(p, ma, mb, tg, st);
-    case 256: return launch<256>(p, ma, mb, tg, st);
+    case 16: return launch<16>(p, ma, mb, mo, tg, st);
+    case 32: return launch<32>(p, ma, mb, mo, tg, st);
+    case 64: return launch<64>(p, ma, mb, mo, tg, st);
+    case 128: return launch<128>(p, ma, mb, mo, tg, st);
+    case 256: return launch<256>(p, ma, mb, mo, tg, st);
   }
   return -1;
 }

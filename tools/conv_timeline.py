@@ -28,7 +28,9 @@ def main():
         for what in ("fwd", "dgrad"):
             fn = mb.run(L, what)
             print(f"=== {L['name']} {what}  ({L['flops'] / 1e9:.2f} GFLOP)")
-            for label, knobs in (("per-tap kernel", {9: 1}), ("no loads", {9: 1, 30: 1}), ("no MMAs", {9: 1, 30: 2}),
+            for label, knobs in (("per-tap kernel", {9: 1}), ("per-thread store epilogue", {9: 1, 29: 1}),
+                                 ("2-stage ring", {9: 1, 8: 2}), ("3-stage ring", {9: 1, 8: 3}),
+                                 ("no loads", {9: 1, 30: 1}), ("no MMAs", {9: 1, 30: 2}),
                                  ("no epilogue", {9: 1, 30: 4}), ("no loads, no epilogue", {9: 1, 30: 5}),
                                  ("no stats epilogue", {9: 1, 31: 1})):
                 if knobs.get(31):
@@ -45,30 +47,33 @@ def main():
                 finally:
                     for k, v in old.items():
                         lib.gb_debug_knob(k, v)
-            # time stamps of one ordinary launch (per-tap kernel, L2 warm from the launches above)
-            old = lib.gb_debug_knob(9, 1)
-            ts.zero_()
-            lib.gb_debug_timeline(ts.data_ptr(), cap)
-            fn()
-            torch.cuda.synchronize()
-            lib.gb_debug_timeline(None, 0)
-            lib.gb_debug_knob(9, old)
-            t = ts.view(-1, 8).cpu()
-            t = t[t[:, 2] != 0]
-            if len(t) == 0:
-                print("  (no stamps: launch not served by igemm_tma_kernel)")
-                continue
-            g0 = int(t[:, 1].min())
-            d = lambda a, b: (t[:, b] - t[:, a]).float()
-            print(f"  {len(t)} CTAs on {len(set(t[:, 0].tolist()))} SMs; clock cycles, mean [min, max]:")
-            for name, a, b in (("setup (barriers, TMEM alloc, taps)", 2, 3), ("first operands land", 3, 4),
-                               ("main loop (first data -> last MMA issued)", 4, 5), ("last MMA issued -> accumulator done", 5, 6),
-                               ("epilogue", 6, 7), ("whole CTA", 2, 7)):
-                x = d(a, b)
-                print(f"    {name:44s} {x.mean():9.0f} [{x.min():7.0f}, {x.max():7.0f}]")
-            start = (t[:, 1] - g0).float() / 1e3
-            print(f"    CTA start times (globaltimer): median {start.median():.1f} us, max {start.max():.1f} us; "
-                  f"CTAs starting after 5 us: {(start > 5).sum().item()}")
+            for tl_label, tl_knobs in (("TMA-store epilogue", {9: 1}), ("per-thread store epilogue", {9: 1, 29: 1})):
+                # time stamps of one ordinary launch (per-tap kernel, L2 warm from the launches above)
+                old = {k: lib.gb_debug_knob(k, v) for k, v in tl_knobs.items()}
+                ts.zero_()
+                lib.gb_debug_timeline(ts.data_ptr(), cap)
+                fn()
+                torch.cuda.synchronize()
+                lib.gb_debug_timeline(None, 0)
+                for k, v in old.items():
+                    lib.gb_debug_knob(k, v)
+                print(f"  -- {tl_label} (epilogue mode read back: {lib.gb_debug_knob(31, 0)})")
+                t = ts.view(-1, 8).cpu()
+                t = t[t[:, 2] != 0]
+                if len(t) == 0:
+                    print("  (no stamps: launch not served by igemm_tma_kernel)")
+                    continue
+                g0 = int(t[:, 1].min())
+                d = lambda a, b: (t[:, b] - t[:, a]).float()
+                print(f"  {len(t)} CTAs on {len(set(t[:, 0].tolist()))} SMs; clock cycles, mean [min, max]:")
+                for name, a, b in (("setup (barriers, TMEM alloc, taps)", 2, 3), ("first operands land", 3, 4),
+                                   ("main loop (first data -> last MMA issued)", 4, 5), ("last MMA issued -> accumulator done", 5, 6),
+                                   ("epilogue", 6, 7), ("whole CTA", 2, 7)):
+                    x = d(a, b)
+                    print(f"    {name:44s} {x.mean():9.0f} [{x.min():7.0f}, {x.max():7.0f}]")
+                start = (t[:, 1] - g0).float() / 1e3
+                print(f"    CTA start times (globaltimer): median {start.median():.1f} us, max {start.max():.1f} us; "
+                      f"CTAs starting after 5 us: {(start > 5).sum().item()}")
 
 
 if __name__ == "__main__":
