@@ -50,43 +50,42 @@ struct TileGeom {
                                          // 2 = fp32, 3 = fp32 accumulated into the destination (bulk reduce-add)
   // bring-up instrumentation (tools/conv_timeline.py; both 0 in every ordinary launch):
   int mode;                              // knob 30 (bits): 1 = producer skips the loads, 2 = issuer skips the MMAs, 4 = no epilogue
-  unsigned long long* ts;                // gb_debug_timeline(): 8 words per CTA (smid, globaltimer, 6 clock64 stamps)
+  unsigned long long* ts;                // gb_debug_timeline(): 16 words per CTA (smid, globaltimer, clock64 stamps)
 };
 
 __device__ __forceinline__ void ts_put(const TileGeom& tg, int slot) {
   if (tg.ts != nullptr) {
     const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    tg.ts[8ull * cta + slot] = (unsigned long long)clock64();
+    tg.ts[16ull * cta + slot] = (unsigned long long)clock64();
   }
 }
 
 
-// ---------------------------------------------------------------------------------------------- TMA-store epilogue
+// ------------------------------------------------------------------------------------------------- staged epilogue
 // TMEM accumulator -> registers (+bias, activation) -> 128B-swizzled staging tiles in the (now idle) operand ring ->
-// ONE bulk tensor store per 128-byte channel group, issued by one thread.  The hardware writes whole 128-byte rows and
-// clips the tile at the image bounds; the per-thread version (gb_conv_epilogue) issues 16-byte stores 512 B apart and
+// global memory as whole 128-byte rows, either by the warps (lane = 16-byte chunk of a row, four rows per warp
+// instruction: store modes 4 / 5 / 6) or by ONE bulk tensor store per 128-byte channel group (modes 1 / 2 / 3).
+// The per-thread version (gb_conv_epilogue, mode 0) issues 16-byte stores 512 B apart from 110-register threads and
 // measured 6.2 K (bf16) / 10.4 K (fp32) cycles per 128 x 256 tile against an 18.4 K cycle main loop
 // (profiles/r02b_conv_timeline_b8.txt).  InstanceNorm statistics are summed from the staged bf16 tile: 16-byte reads,
 // eight channels per thread, shared-memory atomics, one global atomic per channel and CTA.
 //   staging layout: sub-tile s (64 bf16 / 32 fp32 channels) at s * 16 KB; row r (pixel h * tw + w) at r * 128 B; its
-//   16-byte chunk j at ((j ^ (r & 7)) << 4) -- what CU_TENSOR_MAP_SWIZZLE_128B expects, and conflict-free for a warp
-//   whose lanes are consecutive rows.
-template <int BN>
-__device__ __forceinline__ void tma_store_epilogue(const gb_conv_params& p, const TileGeom& tg, const CUtensorMap* map_o,
-                                                   uint32_t tmem_base, int warp, int lane, bool have_acc, bool row_ok,
-                                                   int n0, const float* bias_s, uint8_t* stage, float* sacc,
-                                                   int cx, int cy, int cz, int n) {
-  const int tid = warp * 32 + lane;
-  const int lg = warp & 3, half = warp >> 2;
+//   16-byte chunk j at ((j ^ (r & 7)) << 4) -- what CU_TENSOR_MAP_SWIZZLE_128B expects, and conflict-free both for a
+//   warp whose lanes are consecutive rows (staging) and for one whose lanes are the chunks of four rows (write-out).
+struct EpiCoord {
+  int x0, y0, n;          // first q-grid pixel of the tile, image
+  int oz;                 // output z coordinate
+  int qh, qw;             // q-grid extents (rows / columns that exist)
+  int cx, cy;             // output coordinates of the tile's first pixel (TMA store)
+};
+
+template <int BN, int ACT, bool FP32>
+__device__ __forceinline__ void stage_tile(const gb_conv_params& p, uint32_t tmem_base, int lg, int half, int lane,
+                                           bool have_acc, bool row_ok, const float* bias_s, uint8_t* stage) {
   const int row = lg * 32 + lane;
-  const bool fp32 = tg.store_mode >= 2;
-  const bool want_stats = !fp32 && p.stats != nullptr;
+  const uint32_t rsw = (uint32_t)(row & 7);
   constexpr int CH = 32;
   constexpr int COLS_PER_HALF = BN / 2;
-  static_assert(BN >= 64, "TMA-store epilogue needs BN >= 64");
-  if (want_stats)
-    for (int i = tid; i < BN * 2; i += 256) sacc[i] = 0.f;
-  const uint32_t rsw = (uint32_t)(row & 7);
 #pragma unroll 1
   for (int c0 = half * COLS_PER_HALF; c0 < (half + 1) * COLS_PER_HALF; c0 += CH) {
     uint32_t acc[CH];
@@ -98,49 +97,125 @@ __device__ __forceinline__ void tma_store_epilogue(const gb_conv_params& p, cons
       for (int i = 0; i < CH; ++i) acc[i] = 0u;
     }
     float v[CH];
+    const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      float t = __uint_as_float(acc[i]) + bias_s[c0 + i];
-      if (p.act == GB_ACT_TANH) t = tanhf(t);
-      else if (p.act == GB_ACT_LEAKY) t = t > 0.f ? t : t * p.act_slope;
-      else if (p.act == GB_ACT_RELU) t = fmaxf(t, 0.f);
-      v[i] = (row_ok || fp32) ? t : 0.f;   // rows outside the image: zeros for the statistics (the store clips them)
+    for (int jq = 0; jq < CH / 4; ++jq) {
+      const float4 b = b4[jq];
+      v[4 * jq + 0] = __uint_as_float(acc[4 * jq + 0]) + b.x;
+      v[4 * jq + 1] = __uint_as_float(acc[4 * jq + 1]) + b.y;
+      v[4 * jq + 2] = __uint_as_float(acc[4 * jq + 2]) + b.z;
+      v[4 * jq + 3] = __uint_as_float(acc[4 * jq + 3]) + b.w;
     }
-    if (fp32) {
+    if constexpr (ACT != GB_ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        if constexpr (ACT == GB_ACT_TANH) v[i] = tanhf(v[i]);
+        else if constexpr (ACT == GB_ACT_LEAKY) v[i] = v[i] > 0.f ? v[i] : v[i] * p.act_slope;
+        else v[i] = fmaxf(v[i], 0.f);
+      }
+    }
+    if constexpr (FP32) {
       // 32 fp32 columns = one 128-byte row of sub-tile c0 / 32
       uint8_t* dst = stage + (size_t)(c0 >> 5) * 16384 + (size_t)row * 128;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(dst + (((uint32_t)j ^ rsw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int jq = 0; jq < 8; ++jq)
+        *reinterpret_cast<float4*>(dst + (((uint32_t)jq ^ rsw) << 4)) =
+            make_float4(v[4 * jq], v[4 * jq + 1], v[4 * jq + 2], v[4 * jq + 3]);
     } else {
+      if (!row_ok) {   // rows outside the image: zeros for the statistics (never written to global memory)
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] = 0.f;
+      }
       // 32 bf16 columns = half a 128-byte row (chunks jb .. jb + 3) of sub-tile c0 / 64
       uint8_t* dst = stage + (size_t)(c0 >> 6) * 16384 + (size_t)row * 128;
       const uint32_t jb = (uint32_t)((c0 & 63) >> 3);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int jq = 0; jq < 4; ++jq) {
         uint4 o;
-        o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-        o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-        o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-        o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-        *reinterpret_cast<uint4*>(dst + (((jb + (uint32_t)j) ^ rsw) << 4)) = o;
+        o.x = pack_bf16x2(v[8 * jq + 0], v[8 * jq + 1]);
+        o.y = pack_bf16x2(v[8 * jq + 2], v[8 * jq + 3]);
+        o.z = pack_bf16x2(v[8 * jq + 4], v[8 * jq + 5]);
+        o.w = pack_bf16x2(v[8 * jq + 6], v[8 * jq + 7]);
+        *reinterpret_cast<uint4*>(dst + (((jb + (uint32_t)jq) ^ rsw) << 4)) = o;
       }
     }
   }
-  fence_proxy_async();   // staging writes (generic proxy) -> visible to the bulk store (async proxy)
+}
+
+template <int BN>
+__device__ __forceinline__ void staged_epilogue(const gb_conv_params& p, const TileGeom& tg, const CUtensorMap* map_o,
+                                                uint32_t tmem_base, int warp, int lane, bool have_acc, bool row_ok,
+                                                int n0, const float* bias_s, uint8_t* stage, float* sacc,
+                                                const EpiCoord& ec, const gb_conv_class& cc) {
+  const int tid = warp * 32 + lane;
+  const int lg = warp & 3, half = warp >> 2;
+  const int mode = tg.store_mode;
+  const bool fp32 = (mode == 2 || mode == 3 || mode == 5 || mode == 6);
+  const bool use_tma = mode <= 3;
+  const bool want_stats = !fp32 && p.stats != nullptr;
+  static_assert(BN >= 64, "staged epilogue needs BN >= 64");
+  if (want_stats)
+    for (int i = tid; i < BN * 2; i += 256) sacc[i] = 0.f;
+  if (fp32) {
+    stage_tile<BN, GB_ACT_NONE, true>(p, tmem_base, lg, half, lane, have_acc, row_ok, bias_s, stage);
+  } else {
+    switch (p.act) {
+      case GB_ACT_TANH: stage_tile<BN, GB_ACT_TANH, false>(p, tmem_base, lg, half, lane, have_acc, row_ok, bias_s, stage); break;
+      case GB_ACT_LEAKY: stage_tile<BN, GB_ACT_LEAKY, false>(p, tmem_base, lg, half, lane, have_acc, row_ok, bias_s, stage); break;
+      case GB_ACT_RELU: stage_tile<BN, GB_ACT_RELU, false>(p, tmem_base, lg, half, lane, have_acc, row_ok, bias_s, stage); break;
+      default: stage_tile<BN, GB_ACT_NONE, false>(p, tmem_base, lg, half, lane, have_acc, row_ok, bias_s, stage); break;
+    }
+  }
+  if (tid == 64) ts_put(tg, 8);    // tile staged
+  if (use_tma) fence_proxy_async();   // staging writes (generic proxy) -> visible to the bulk store (async proxy)
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) {
-    const int inner = fp32 ? 32 : 64;
-    const uint32_t s0 = smem_u32(stage);
-    for (int sub = 0; sub * inner < BN; ++sub) {
-      const int c = n0 + sub * inner;
-      if (c >= p.out.C) break;
-      if (tg.store_mode == 3) tma_reduce_add_5d(map_o, s0 + sub * 16384, c, cx, cy, cz, n);
-      else tma_store_5d(map_o, s0 + sub * 16384, c, cx, cy, cz, n);
+  if (tid == 64) ts_put(tg, 9);
+  const int rows = tg.tw * tg.th;
+  if (use_tma) {
+    if (tid == 0) {
+      const int inner = fp32 ? 32 : 64;
+      const uint32_t s0 = smem_u32(stage);
+      for (int sub = 0; sub * inner < BN; ++sub) {
+        const int c = n0 + sub * inner;
+        if (c >= p.out.C) break;
+        if (mode == 3) tma_reduce_add_5d(map_o, s0 + sub * 16384, c, ec.cx, ec.cy, ec.oz, ec.n);
+        else tma_store_5d(map_o, s0 + sub * 16384, c, ec.cx, ec.cy, ec.oz, ec.n);
+      }
+      tma_store_commit();
     }
-    tma_store_commit();
+  } else {
+    // write-out by the warps: lane = (row of a quad, 16-byte chunk); a warp instruction moves four whole 128-byte rows
+    const int lr = lane >> 3;
+    const uint32_t jc = (uint32_t)(lane & 7);
+    const int esz = fp32 ? 4 : 2;
+    const int epc = 16 / esz;                  // elements per 16-byte chunk
+    const int inner = 128 / esz;               // channels per sub-tile
+    uint8_t* obase = reinterpret_cast<uint8_t*>(p.out.ptr);
+    for (int r = warp * 4 + lr; r < rows; r += 32) {
+      const int h = (int)gb_div((uint32_t)r, tg.div_tw), w = r - h * tg.tw;
+      const int qy = ec.y0 + h, qx = ec.x0 + w;
+      if (qy >= ec.qh || qx >= ec.qw) continue;
+      const int64_t off = gb_pix_offset(p.out, ec.n, ec.oz, qy * p.out_mul[1] + cc.off[1], qx * p.out_mul[2] + cc.off[2]);
+      const uint8_t* srow = stage + (size_t)r * 128 + ((jc ^ (uint32_t)(r & 7)) << 4);
+#pragma unroll 1
+      for (int sub = 0; sub * inner < BN; ++sub) {
+        const int col = n0 + sub * inner + (int)jc * epc;
+        if (col >= p.out.C) break;
+        const uint4 q4 = *reinterpret_cast<const uint4*>(srow + (size_t)sub * 16384);
+        uint8_t* dst = obase + (off + col) * esz;
+        if (mode == 6) {
+          float4 o = *reinterpret_cast<float4*>(dst);
+          o.x += __uint_as_float(q4.x); o.y += __uint_as_float(q4.y);
+          o.z += __uint_as_float(q4.z); o.w += __uint_as_float(q4.w);
+          *reinterpret_cast<float4*>(dst) = o;
+        } else {
+          *reinterpret_cast<uint4*>(dst) = q4;
+        }
+      }
+    }
   }
+  if (tid == 64) ts_put(tg, 10);   // write-out issued
   if (want_stats) {
     // thread -> (16-byte chunk cg of a row = 8 channels, row group rg); rows rg, rg + RG, ... of the tile
     constexpr int CPR = BN / 8;        // chunks per row over all sub-tiles
@@ -151,7 +226,6 @@ __device__ __forceinline__ void tma_store_epilogue(const gb_conv_params& p, cons
     float s1[8], s2[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
-    const int rows = tg.tw * tg.th;
     for (int r = rg; r < rows; r += RG) {
       const uint4 q4 = *reinterpret_cast<const uint4*>(src + (size_t)r * 128 + ((jc ^ (uint32_t)(r & 7)) << 4));
       float2 f;
@@ -169,13 +243,14 @@ __device__ __forceinline__ void tma_store_epilogue(const gb_conv_params& p, cons
     for (int i = tid; i < BN; i += 256) {
       const int col = n0 + i;
       if (col < p.ncols) {
-        float* dst = p.stats + ((int64_t)n * p.out.C + col) * 2;
+        float* dst = p.stats + ((int64_t)ec.n * p.out.C + col) * 2;
         atomicAdd(dst, sacc[i * 2]);
         atomicAdd(dst + 1, sacc[i * 2 + 1]);
       }
     }
   }
-  if (tid == 0) tma_store_wait_read();
+  if (tid == 64) ts_put(tg, 11);   // statistics done
+  if (use_tma && tid == 0) tma_store_wait_read();
 }
 
 template <int BN>
@@ -195,7 +270,7 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);  // full[STAGES], empty[STAGES], accum
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 144);
   int8_t* taps_s = reinterpret_cast<int8_t*>(tail + 192);
-  __shared__ float bias_s[BN];
+  __shared__ __align__(16) float bias_s[BN];
   __shared__ float stat_s[BN >= 64 ? 2 * BN : 2];   // TMA-store epilogue: per-channel (sum, sum^2) of this tile
 
   const int tid = threadIdx.x;
@@ -227,9 +302,9 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
     unsigned long long gt;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    tg.ts[8ull * cta + 0] = smid;
-    tg.ts[8ull * cta + 1] = gt;
-    tg.ts[8ull * cta + 2] = (unsigned long long)clock64();
+    tg.ts[16ull * cta + 0] = smid;
+    tg.ts[16ull * cta + 1] = gt;
+    tg.ts[16ull * cta + 2] = (unsigned long long)clock64();
   }
 
   const uint32_t full_bar = smem_u32(bars);
@@ -327,10 +402,12 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
     bool done = false;
     if constexpr (BN >= 64) {
       if (tg.store_mode != 0) {
-        // (the operand ring is idle once the accumulator is complete: staging tiles of the bulk store)
-        tma_store_epilogue<BN>(p, tg, &map_o, tmem_base, warp, lane, KB > 0, row_ok, n0, bias_s, smem, stat_s,
-                               x0 * p.out_mul[2] + cc.off[2], y0 * p.out_mul[1] + cc.off[1],
-                               z0 * p.out_mul[0] + cc.off[0], n);
+        // (the operand ring is idle once the accumulator is complete: staging tiles of the write-out)
+        EpiCoord ec;
+        ec.x0 = x0, ec.y0 = y0, ec.n = n, ec.oz = z0 * p.out_mul[0] + cc.off[0];
+        ec.qh = q[1], ec.qw = q[2];
+        ec.cx = x0 * p.out_mul[2] + cc.off[2], ec.cy = y0 * p.out_mul[1] + cc.off[1];
+        staged_epilogue<BN>(p, tg, &map_o, tmem_base, warp, lane, KB > 0, row_ok, n0, bias_s, smem, stat_s, ec, cc);
         done = true;
       }
     }
@@ -514,7 +591,8 @@ int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb
   // the TMA-store epilogue stages the whole output tile (bf16: BN * 256 B, fp32: BN * 512 B) in the operand ring
   size_t ring = (size_t)ns * C::STAGE_BYTES;
   if (tgl.store_mode != 0) {
-    const size_t staging = (size_t)BN * 128 * (tgl.store_mode >= 2 ? 4 : 2);
+    const bool f32 = tgl.store_mode == 2 || tgl.store_mode == 3 || tgl.store_mode >= 5;
+    const size_t staging = (size_t)BN * 128 * (f32 ? 4 : 2);
     if (staging > (size_t)C::SMEM - 2048) tgl.store_mode = 0;
     else if (ring < staging) ring = staging;
   }
@@ -606,22 +684,25 @@ int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st) {
   if (tw * p.in_mul[2] > 256 || th * p.in_mul[1] > 256) return -1;
   if (gb_tma_activation_map(p.in, tw, th, &ma, p.in_mul, p.in_c_valid)) return 1;
   if (gb_tma_weight_map(p.wpacked, kpad, p.nclass * p.npad, bn, &mb)) return 1;
-  // TMA-store epilogue (knob 29 = 1: per-thread stores): whole 128-byte channel groups of a plain, 16-byte aligned view
+  // staged epilogue (knob 29: 0 = default, 1 = per-thread stores, 2 = bulk tensor store, 3 = coalesced warp stores):
+  // whole 128-byte channel groups of a plain, 16-byte aligned view
   tg.store_mode = 0;
   tg.mode = 0;
   tg.ts = nullptr;
+  mo = ma;  // (unused unless a bulk-store mode is chosen)
   {
     const int esz = p.out_fp32 ? 4 : 2;
     const int inner = 128 / esz;
-    const bool ok = g_gb_knobs[29] == 0 && bn >= 64 && p.out.pad == 0 && p.out.C % inner == 0 &&
+    const int want = g_gb_knobs[29] == 0 ? 3 : g_gb_knobs[29];
+    const bool ok = want >= 2 && bn >= 64 && p.out.pad == 0 && p.out.C % inner == 0 &&
                     ((uintptr_t)p.out.ptr % 16) == 0 && (p.out.sx * esz) % 16 == 0 && (p.out.sy * esz) % 16 == 0 &&
-                    (p.out.sz * esz) % 16 == 0 && (p.out.sn * esz) % 16 == 0 && tw * p.out_mul[2] <= 256 &&
-                    th * p.out_mul[1] <= 256 && p.out_mul[0] <= 256 && (p.out_fp32 || !p.accumulate);
-    if (ok) {
+                    (p.out.sz * esz) % 16 == 0 && (p.out.sn * esz) % 16 == 0 && (p.out_fp32 || !p.accumulate);
+    const bool tma_ok = ok && tw * p.out_mul[2] <= 256 && th * p.out_mul[1] <= 256 && p.out_mul[0] <= 256;
+    if (ok && want == 2 && tma_ok) {
       if (gb_tma_store_map(p.out, tw, th, p.out_mul, p.out_fp32, &mo)) return 1;
       tg.store_mode = p.out_fp32 ? (p.accumulate ? 3 : 2) : 1;
-    } else {
-      mo = ma;  // unused
+    } else if (ok && want == 3) {
+      tg.store_mode = p.out_fp32 ? (p.accumulate ? 6 : 5) : 4;
     }
   }
   g_gb_knobs[31] = tg.store_mode;  // READ-BACK (knob 31): epilogue of the last TMA-fed launch

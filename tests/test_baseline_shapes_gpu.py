@@ -189,7 +189,7 @@ def test_revgan_step_with_inverse_recompute_backward():
 
 def test_memory_saving_lowers_peak_memory_and_keeps_gradients():
     """Vnet3D(use_memory_saving=True) vs (False) on the GPU: same forward (to the run-to-run level of the fp32 statistics
-    atomics, <= 5e-3 relative L2), gradients within the stated 5e-2 relative L2 per tensor (rounding of the rebuilt
+    atomics and what bf16 makes of it, <= 2e-2 relative L2), gradients within the stated 5e-2 relative L2 per tensor (rounding of the rebuilt
     inputs, tests/test_host_networks_cpu.py), lower peak memory."""
     from ganslate_b200.nn.generators import Vnet3D
     from oracle import torch_oracle3d as O3
@@ -217,7 +217,7 @@ def test_memory_saving_lowers_peak_memory_and_keeps_gradients():
         outs[name] = y.detach()
         grads[name] = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
         del y
-    assert rel_l2(outs["save"], outs["keep"]) <= 5e-3
+    assert rel_l2(outs["save"], outs["keep"]) <= 2e-2
     worst = max(rel_l2(grads["save"][k], v) for k, v in grads["keep"].items() if v.dim() > 1 and v.abs().max() > 0)
     assert worst <= 5e-2, worst
     assert peak["save"] < 0.9 * peak["keep"], peak

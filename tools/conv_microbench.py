@@ -102,8 +102,8 @@ def main():
         ("cg2 3-stage ring", {16: 1, 17: 3}),
         ("persistent 1-CTA (knob 16 = 2)", {16: 2}),
         ("per-tap, per-thread store epilogue", {9: 1, 29: 1}),
-        ("per-tap, 2-stage ring", {9: 1, 8: 2}),
-        ("default, per-thread store epilogue", {29: 1}),
+        ("per-tap, bulk-store epilogue", {9: 1, 29: 2}),
+        ("per-tap, coalesced-store epilogue", {9: 1, 29: 3}),
     ]
     if args.layers:
         layers = [layers[int(i)] for i in args.layers.split(",")]

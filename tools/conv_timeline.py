@@ -23,13 +23,13 @@ def main():
         mb.layer("up convT 3x3 s2 256->128 64->128", 256, 128, 3, 2, 1, 64, 64, B, transposed=True, op_pad=1),
     ]
     cap = 1 << 16
-    ts = torch.zeros(cap * 8, dtype=torch.int64, device="cuda")
+    ts = torch.zeros(cap * 16, dtype=torch.int64, device="cuda")
     for L in layers:
         for what in ("fwd", "dgrad"):
             fn = mb.run(L, what)
             print(f"=== {L['name']} {what}  ({L['flops'] / 1e9:.2f} GFLOP)")
             for label, knobs in (("per-tap kernel", {9: 1}), ("per-thread store epilogue", {9: 1, 29: 1}),
-                                 ("2-stage ring", {9: 1, 8: 2}), ("3-stage ring", {9: 1, 8: 3}),
+                                 ("bulk-store epilogue", {9: 1, 29: 2}), ("coalesced-store epilogue", {9: 1, 29: 3}),
                                  ("no loads", {9: 1, 30: 1}), ("no MMAs", {9: 1, 30: 2}),
                                  ("no epilogue", {9: 1, 30: 4}), ("no loads, no epilogue", {9: 1, 30: 5}),
                                  ("no stats epilogue", {9: 1, 31: 1})):
@@ -47,7 +47,8 @@ def main():
                 finally:
                     for k, v in old.items():
                         lib.gb_debug_knob(k, v)
-            for tl_label, tl_knobs in (("TMA-store epilogue", {9: 1}), ("per-thread store epilogue", {9: 1, 29: 1})):
+            for tl_label, tl_knobs in (("coalesced-store epilogue", {9: 1, 29: 3}), ("bulk-store epilogue", {9: 1, 29: 2}),
+                                       ("per-thread store epilogue", {9: 1, 29: 1})):
                 # time stamps of one ordinary launch (per-tap kernel, L2 warm from the launches above)
                 old = {k: lib.gb_debug_knob(k, v) for k, v in tl_knobs.items()}
                 ts.zero_()
@@ -58,7 +59,7 @@ def main():
                 for k, v in old.items():
                     lib.gb_debug_knob(k, v)
                 print(f"  -- {tl_label} (epilogue mode read back: {lib.gb_debug_knob(31, 0)})")
-                t = ts.view(-1, 8).cpu()
+                t = ts.view(-1, 16).cpu()
                 t = t[t[:, 2] != 0]
                 if len(t) == 0:
                     print("  (no stamps: launch not served by igemm_tma_kernel)")
@@ -68,7 +69,11 @@ def main():
                 print(f"  {len(t)} CTAs on {len(set(t[:, 0].tolist()))} SMs; clock cycles, mean [min, max]:")
                 for name, a, b in (("setup (barriers, TMEM alloc, taps)", 2, 3), ("first operands land", 3, 4),
                                    ("main loop (first data -> last MMA issued)", 4, 5), ("last MMA issued -> accumulator done", 5, 6),
-                                   ("epilogue", 6, 7), ("whole CTA", 2, 7)):
+                                   ("epilogue", 6, 7), ("  TMEM -> staged tile", 6, 8), ("  barrier", 8, 9),
+                                   ("  write-out issued", 9, 10), ("  statistics", 10, 11), ("  tail (bulk-store wait, barrier)", 11, 7),
+                                   ("whole CTA", 2, 7)):
+                    if (t[:, a] == 0).all() or (t[:, b] == 0).all():
+                        continue
                     x = d(a, b)
                     print(f"    {name:44s} {x.mean():9.0f} [{x.min():7.0f}, {x.max():7.0f}]")
                 start = (t[:, 1] - g0).float() / 1e3
