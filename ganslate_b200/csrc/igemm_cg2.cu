@@ -656,7 +656,7 @@ static int cg2_geometry(const gb_conv_params& p, bool pair, Cg2Geom* gout, int* 
 // CTA), 0 on success, >0 on error.
 int gb_conv_data_cg2(const gb_conv_params& p, cudaStream_t st) {
   const int mode = g_gb_knobs[16];
-  if (mode == 0 || g_gb_knobs[3] != 0) return -1;
+  if (mode == 0 || mode >= 3 || g_gb_knobs[3] != 0) return -1;   // (3 = igemm_pers_kernel in igemm_tma.cu)
   const bool pair = mode == 1;
   if (!gb_tma_available()) return -1;
   Cg2Geom g;

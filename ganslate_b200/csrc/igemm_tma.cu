@@ -426,6 +426,365 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
   if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
+// ============================================================================================ persistent kernel
+// One CTA per SM walks a CONTIGUOUS range of (class, column block, pixel tile) items.  The per-CTA fixed costs of the
+// kernel above (barrier init, TMEM allocation, first-load latency: ~2.5 K cycles) are paid once, and the epilogue of
+// item i -- bounded by the 64 B/clk TMEM read and the ~32 B/clk an SM can write to L2: 4 - 7 K cycles for a 128 x 256
+// tile, as long as the 18.4 K cycle main loop of a residual-block tile and longer than the whole main loop of the
+// short-K layers (profiles/r02d_conv_timeline_b8.txt) -- runs under the main loop of item i + 1:
+//   warp 0      TMA producer, operand ring continuous across items
+//   warp 1      MMA issuer; two TMEM accumulators (acc_full / acc_empty barriers)
+//   warps 2-9   epilogue: TMEM -> registers (+bias, activation, bf16) -> 16 KB staging tile -> coalesced 128-byte rows.
+//               Two warps share each TMEM lane group (32 rows) and split the columns; a "round" stages 128 bytes of
+//               channels per row, the pair meets at a 64-thread named barrier and writes its 32 rows out, four rows
+//               per warp instruction.  InstanceNorm statistics: butterfly column sums of the bf16-rounded values kept
+//               in REGISTERS across the items of one image (lane = column), flushed with one atomic per column when
+//               the image / column block changes -- consecutive items of a CTA are neighbouring tiles of one image.
+template <int BN>
+struct PCfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGING = 16384;
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 8 ? 8 : (200 * 1024 / STAGE_BYTES);
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + STAGING + 2048;
+};
+
+struct PersGeom {
+  TileGeom tg;
+  int ncb;                    // column blocks of BN output channels
+  int total;                  // items = nclass * ncb * tg.ntiles
+  gb_fastdiv div_tiles, div_ncb;
+};
+
+struct PItem {
+  int cls, n0, n, z0, y0, x0, KB, qh, qw;
+};
+
+__device__ __forceinline__ bool pers_decode(const gb_conv_params& p, const PersGeom& pg, int item, int bn, PItem& it) {
+  uint32_t t = (uint32_t)item;
+  uint32_t u = gb_div(t, pg.div_tiles);
+  uint32_t tile = t - u * pg.div_tiles.d;
+  uint32_t c = gb_div(u, pg.div_ncb);
+  it.n0 = (int)(u - c * pg.div_ncb.d) * bn;
+  it.cls = (int)c;
+  int q[3];
+  gb_class_extents(p, it.cls, q);
+  t = tile;
+  u = gb_div(t, pg.tg.tiles_x);
+  it.x0 = (int)(t - u * pg.tg.tiles_x.d) * pg.tg.tw;
+  t = u;
+  u = gb_div(t, pg.tg.tiles_y);
+  it.y0 = (int)(t - u * pg.tg.tiles_y.d) * pg.tg.th;
+  t = u;
+  u = gb_div(t, pg.tg.tiles_z);
+  it.z0 = (int)(t - u * pg.tg.tiles_z.d);
+  it.n = (int)u;
+  it.qh = q[1];
+  it.qw = q[2];
+  it.KB = p.cls[it.cls].ntaps * (p.in.C >> 6);
+  return it.n < p.in.N && it.z0 < q[0] && it.y0 < q[1] && it.x0 < q[2];
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// one item's epilogue for one warp.  FP32: rounds of 32 fp32 columns (16 per warp), else rounds of 64 bf16 columns (32
+// per warp).  st1 / st2: running column sums of this warp's columns (bf16 path with statistics).
+template <int BN, int ACT, bool FP32, bool ACCUM>
+__device__ __forceinline__ void pers_epilogue_item(const gb_conv_params& p, const PersGeom& pg, const PItem& it,
+                                                   uint32_t tmem_acc, uint32_t acc_empty_bar, int lg, int half, int lane,
+                                                   uint8_t* stage, bool want_stats, float (&st1)[BN / 64],
+                                                   float (&st2)[BN / 64]) {
+  constexpr int ROUNDS = FP32 ? BN / 32 : BN / 64;
+  constexpr int ESZ = FP32 ? 4 : 2;
+  const gb_conv_class& cc = p.cls[it.cls];
+  const int row = lg * 32 + lane;
+  const uint32_t rsw = (uint32_t)(row & 7);
+  const int h = (int)gb_div((uint32_t)row, pg.tg.div_tw), w = row - h * pg.tg.tw;
+  const bool row_ok = h < pg.tg.th && it.y0 + h < it.qh && it.x0 + w < it.qw;
+  uint8_t* srow = stage + (size_t)row * 128;
+  // write-out role of this thread: chunk j of rows (t2 >> 3) + 8k of the pair's 32 rows
+  const int t2 = half * 32 + lane;
+  const uint32_t jc = (uint32_t)(t2 & 7);
+  int64_t woff[4];
+  bool wok[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r2 = lg * 32 + (t2 >> 3) + 8 * k;
+    const int h2 = (int)gb_div((uint32_t)r2, pg.tg.div_tw), w2 = r2 - h2 * pg.tg.tw;
+    const int qy = it.y0 + h2, qx = it.x0 + w2;
+    wok[k] = h2 < pg.tg.th && qy < it.qh && qx < it.qw;
+    woff[k] = wok[k] ? gb_pix_offset(p.out, it.n, it.z0 * p.out_mul[0] + cc.off[0], qy * p.out_mul[1] + cc.off[1],
+                                     qx * p.out_mul[2] + cc.off[2])
+                     : 0;
+  }
+  uint8_t* obase = reinterpret_cast<uint8_t*>(p.out.ptr);
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    if constexpr (FP32) {
+      const int c0 = r * 32 + half * 16;
+      uint32_t acc[16];
+      tmem_ld16(tmem_acc + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, acc);
+      tmem_ld_wait();
+      if (r == ROUNDS - 1) {   // this warp has read its part of the accumulator: hand it back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty_bar);
+      }
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        v[i] = __uint_as_float(acc[i]);
+        if (p.bias != nullptr && it.n0 + c0 + i < p.ncols) v[i] += __ldg(p.bias + it.n0 + c0 + i);
+      }
+#pragma unroll
+      for (int jq = 0; jq < 4; ++jq)
+        *reinterpret_cast<float4*>(srow + (((uint32_t)(4 * half + jq)) ^ rsw) * 16) =
+            make_float4(v[4 * jq], v[4 * jq + 1], v[4 * jq + 2], v[4 * jq + 3]);
+    } else {
+      const int c0 = r * 64 + half * 32;
+      uint32_t acc[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, acc);
+      tmem_ld_wait();
+      if (r == ROUNDS - 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty_bar);
+      }
+      float v[32];
+      if (p.bias != nullptr) {
+        if (it.n0 + c0 + 32 <= p.ncols) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + it.n0 + c0);
+#pragma unroll
+          for (int jq = 0; jq < 8; ++jq) {
+            const float4 b = __ldg(b4 + jq);
+            v[4 * jq + 0] = __uint_as_float(acc[4 * jq + 0]) + b.x;
+            v[4 * jq + 1] = __uint_as_float(acc[4 * jq + 1]) + b.y;
+            v[4 * jq + 2] = __uint_as_float(acc[4 * jq + 2]) + b.z;
+            v[4 * jq + 3] = __uint_as_float(acc[4 * jq + 3]) + b.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            v[i] = __uint_as_float(acc[i]) + (it.n0 + c0 + i < p.ncols ? __ldg(p.bias + it.n0 + c0 + i) : 0.f);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+      }
+      if constexpr (ACT != GB_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if constexpr (ACT == GB_ACT_TANH) v[i] = tanhf(v[i]);
+          else if constexpr (ACT == GB_ACT_LEAKY) v[i] = v[i] > 0.f ? v[i] : v[i] * p.act_slope;
+          else v[i] = fmaxf(v[i], 0.f);
+        }
+      }
+      uint32_t o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+      if (want_stats) {
+        float sv[32], sq[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 f = unpack_bf16x2(o[i]);
+          sv[2 * i] = f.x;
+          sv[2 * i + 1] = f.y;
+        }
+        if (!row_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sq[i] = sv[i] * sv[i];
+        st1[r] += gb_warp_colsum<32>(sv, lane);
+        st2[r] += gb_warp_colsum<32>(sq, lane);
+      }
+#pragma unroll
+      for (int jq = 0; jq < 4; ++jq)
+        *reinterpret_cast<uint4*>(srow + (((uint32_t)(4 * half + jq)) ^ rsw) * 16) =
+            make_uint4(o[4 * jq], o[4 * jq + 1], o[4 * jq + 2], o[4 * jq + 3]);
+    }
+    named_bar_sync(1 + lg, 64);   // the pair's 32 rows x 128 bytes are staged
+    const int col = it.n0 + r * (128 / ESZ) + (int)jc * (16 / ESZ);
+    if (col < p.out.C) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (wok[k]) {
+          const int r2 = lg * 32 + (t2 >> 3) + 8 * k;
+          const uint4 q4 = *reinterpret_cast<const uint4*>(stage + (size_t)r2 * 128 + ((jc ^ (uint32_t)(r2 & 7)) << 4));
+          uint8_t* dst = obase + (woff[k] + col) * ESZ;
+          if constexpr (ACCUM) {
+            float4 a = *reinterpret_cast<float4*>(dst);
+            a.x += __uint_as_float(q4.x); a.y += __uint_as_float(q4.y);
+            a.z += __uint_as_float(q4.z); a.w += __uint_as_float(q4.w);
+            *reinterpret_cast<float4*>(dst) = a;
+          } else {
+            *reinterpret_cast<uint4*>(dst) = q4;
+          }
+        }
+      }
+    }
+    named_bar_sync(1 + lg, 64);   // the rows have been read: the next round may overwrite them
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(320, 1)
+igemm_pers_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant__ CUtensorMap map_a,
+                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ PersGeom pg) {
+  gb_pdl_enter();
+  using C = PCfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint8_t* stage = smem + STAGES * C::STAGE_BYTES;
+  uint8_t* tail = stage + C::STAGING;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);  // full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 8 * (2 * STAGES + 4));
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int it_begin = (int)((int64_t)blockIdx.x * pg.total / gridDim.x);
+  const int it_end = (int)((int64_t)(blockIdx.x + 1) * pg.total / gridDim.x);
+  const uint32_t full_bar = smem_u32(bars);
+  const uint32_t empty_bar = smem_u32(bars + STAGES);
+  const uint32_t accf_bar = smem_u32(bars + 2 * STAGES);
+  const uint32_t acce_bar = smem_u32(bars + 2 * STAGES + 2);
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    mbar_init(accf_bar, 1);
+    mbar_init(accf_bar + 8, 1);
+    mbar_init(acce_bar, 8);
+    mbar_init(acce_bar + 8, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int chunks = p.in.C >> 6;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one lane)
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int item = it_begin; item < it_end; ++item) {
+        PItem it;
+        if (!pers_decode(p, pg, item, BN, it)) continue;
+        const gb_conv_class& cc = p.cls[it.cls];
+        for (int tl = 0; tl < cc.ntaps; ++tl) {
+          const int dz = p.taps[cc.tap_begin + tl][0], dy = p.taps[cc.tap_begin + tl][1], dx = p.taps[cc.tap_begin + tl][2];
+          for (int c = 0; c < chunks; ++c, ++g) {
+            const uint32_t s = g % STAGES, itn = g / STAGES;
+            if (itn > 0) mbar_wait(empty_bar + 8 * s, (itn - 1) & 1);
+            const uint32_t a_s = base + s * C::STAGE_BYTES;
+            const uint32_t bar = full_bar + 8 * s;
+            mbar_expect_tx(bar, (uint32_t)(pg.tg.tw * pg.tg.th * 128 + C::B_BYTES));
+            tma_load_5d(a_s, &map_a, bar, c * 64, it.x0 * p.in_mul[2] + dx, it.y0 * p.in_mul[1] + dy,
+                        it.z0 * p.in_mul[0] + dz, it.n);
+            tma_load_2d(a_s + A_BYTES, &map_b, bar, tl * p.in.C + c * 64, it.cls * p.npad + it.n0);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BN, 0, 0);
+    uint32_t g = 0;
+    int li = 0;
+    for (int item = it_begin; item < it_end; ++item) {
+      PItem it;
+      if (!pers_decode(p, pg, item, BN, it)) continue;
+      const int bsel = li & 1, use = li >> 1;
+      if (use > 0) {
+        mbar_wait(acce_bar + 8 * bsel, (use - 1) & 1);
+        tc_fence_after();
+      }
+      const uint32_t tacc = tmem_base + (uint32_t)(bsel * BN);
+      for (int kb = 0; kb < it.KB; ++kb, ++g) {
+        const uint32_t s = g % STAGES, itn = g / STAGES;
+        mbar_wait(full_bar + 8 * s, itn & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_s = base + s * C::STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc(a_s, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(a_s + A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_commit(empty_bar + 8 * s);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) umma_commit(accf_bar + 8 * bsel);
+      __syncwarp();
+      ++li;
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int lg = warp & 3, half = (warp - 2) >> 2;
+    const bool fp32 = p.out_fp32 != 0;
+    const bool want_stats = !fp32 && p.stats != nullptr;
+    float st1[BN / 64], st2[BN / 64];
+#pragma unroll
+    for (int r = 0; r < BN / 64; ++r) st1[r] = st2[r] = 0.f;
+    int cur_n = -1, cur_n0 = -1;
+    auto flush = [&]() {
+      if (cur_n < 0) return;
+#pragma unroll
+      for (int r = 0; r < BN / 64; ++r) {
+        const int col = cur_n0 + r * 64 + half * 32 + lane;
+        if (col < p.ncols) {
+          float* dst = p.stats + ((int64_t)cur_n * p.out.C + col) * 2;
+          atomicAdd(dst, st1[r]);
+          atomicAdd(dst + 1, st2[r]);
+        }
+        st1[r] = st2[r] = 0.f;
+      }
+    };
+    int li = 0;
+    for (int item = it_begin; item < it_end; ++item) {
+      PItem it;
+      if (!pers_decode(p, pg, item, BN, it)) continue;
+      const int bsel = li & 1, use = li >> 1;
+      if (want_stats && (it.n != cur_n || it.n0 != cur_n0)) {
+        flush();
+        cur_n = it.n;
+        cur_n0 = it.n0;
+      }
+      mbar_wait(accf_bar + 8 * bsel, use & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(bsel * BN);
+      const uint32_t aeb = acce_bar + 8 * bsel;
+      if (fp32) {
+        if (p.accumulate) pers_epilogue_item<BN, GB_ACT_NONE, true, true>(p, pg, it, tacc, aeb, lg, half, lane, stage, false, st1, st2);
+        else pers_epilogue_item<BN, GB_ACT_NONE, true, false>(p, pg, it, tacc, aeb, lg, half, lane, stage, false, st1, st2);
+      } else {
+        switch (p.act) {
+          case GB_ACT_TANH: pers_epilogue_item<BN, GB_ACT_TANH, false, false>(p, pg, it, tacc, aeb, lg, half, lane, stage, want_stats, st1, st2); break;
+          case GB_ACT_LEAKY: pers_epilogue_item<BN, GB_ACT_LEAKY, false, false>(p, pg, it, tacc, aeb, lg, half, lane, stage, want_stats, st1, st2); break;
+          case GB_ACT_RELU: pers_epilogue_item<BN, GB_ACT_RELU, false, false>(p, pg, it, tacc, aeb, lg, half, lane, stage, want_stats, st1, st2); break;
+          default: pers_epilogue_item<BN, GB_ACT_NONE, false, false>(p, pg, it, tacc, aeb, lg, half, lane, stage, want_stats, st1, st2); break;
+        }
+      }
+      ++li;
+    }
+    if (want_stats) flush();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
 unsigned long long* g_timeline = nullptr;
 long long g_timeline_ctas = 0;
 
@@ -602,6 +961,42 @@ int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb
   return 0;
 }
 
+int pers_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN>
+int launch_pers(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb, const TileGeom& tg, cudaStream_t st) {
+  using C = PCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GB_CUDA(cudaFuncSetAttribute(igemm_pers_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  PersGeom pg;
+  pg.tg = tg;
+  pg.ncb = gb_cdiv(p.ncols, BN);
+  const int64_t total = (int64_t)tg.ntiles * pg.ncb * p.nclass;
+  if (total >= (1ll << 31)) return -1;
+  pg.total = (int)total;
+  pg.div_tiles = gb_make_fastdiv((uint32_t)tg.ntiles);
+  pg.div_ncb = gb_make_fastdiv((uint32_t)pg.ncb);
+  int grid = pers_num_sms();
+  if (g_gb_knobs[18] > 0 && g_gb_knobs[18] < grid) grid = g_gb_knobs[18];
+  if (total < grid) grid = (int)total;
+  gb_klaunch(igemm_pers_kernel<BN>, dim3(grid), 320, C::SMEM, st, p, ma, mb, pg);
+  g_gb_knobs[15] = 7;
+  GB_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 
 // Returns -1 when this path does not apply (caller falls back to the gather kernel), 0 on success, >0 on error.
@@ -684,6 +1079,33 @@ int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st) {
   if (tw * p.in_mul[2] > 256 || th * p.in_mul[1] > 256) return -1;
   if (gb_tma_activation_map(p.in, tw, th, &ma, p.in_mul, p.in_c_valid)) return 1;
   if (gb_tma_weight_map(p.wpacked, kpad, p.nclass * p.npad, bn, &mb)) return 1;
+  // persistent kernel (knob 16 = 3; see igemm_pers_kernel): widest column block, coalesced row stores
+  if (g_gb_knobs[16] == 3) {
+    bool ok = p.out.pad == 0 && (p.out_fp32 || !p.accumulate);
+    const int esz = p.out_fp32 ? 4 : 2;
+    ok = ok && ((uintptr_t)p.out.ptr % 16) == 0 && (p.out.sx * esz) % 16 == 0 && (p.out.sy * esz) % 16 == 0 &&
+         (p.out.sz * esz) % 16 == 0 && (p.out.sn * esz) % 16 == 0;
+    for (int c = 0; c < p.nclass; ++c) ok = ok && p.cls[c].ntaps >= 1;
+    int pbn = 64;
+    while (pbn < p.ncols && pbn < 256) pbn *= 2;
+    if (g_gb_knobs[1] >= 64) pbn = g_gb_knobs[1];
+    ok = ok && pbn <= p.nclass * p.npad;
+    if (ok) {
+      CUtensorMap mbp;
+      if (gb_tma_weight_map(p.wpacked, kpad, p.nclass * p.npad, pbn, &mbp)) return 1;
+      tg.store_mode = 0;
+      tg.mode = 0;
+      tg.ts = nullptr;
+      tg.nstages = 0;
+      int r = -1;
+      switch (pbn) {
+        case 64: r = launch_pers<64>(p, ma, mbp, tg, st); break;
+        case 128: r = launch_pers<128>(p, ma, mbp, tg, st); break;
+        case 256: r = launch_pers<256>(p, ma, mbp, tg, st); break;
+      }
+      if (r >= 0) return r;
+    }
+  }
   // staged epilogue (knob 29: 0 = default, 1 = per-thread stores, 2 = bulk tensor store, 3 = coalesced warp stores):
   // whole 128-byte channel groups of a plain, 16-byte aligned view
   tg.store_mode = 0;
@@ -693,7 +1115,10 @@ int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st) {
   {
     const int esz = p.out_fp32 ? 4 : 2;
     const int inner = 128 / esz;
-    const int want = g_gb_knobs[29] == 0 ? 3 : g_gb_knobs[29];
+    // default (measured, profiles/r02d_conv_microbench_epilogues_b8.txt): fp32 destinations (data gradients) through the
+    // staged tile + bulk store (50.1 -> 45.9 us on the residual-block layer), bf16 destinations keep the per-thread
+    // stores (their statistics from the staged tile cost more shared-memory atomics than the butterfly sums)
+    const int want = g_gb_knobs[29] == 0 ? (p.out_fp32 ? 2 : 1) : g_gb_knobs[29];
     const bool ok = want >= 2 && bn >= 64 && p.out.pad == 0 && p.out.C % inner == 0 &&
                     ((uintptr_t)p.out.ptr % 16) == 0 && (p.out.sx * esz) % 16 == 0 && (p.out.sy * esz) % 16 == 0 &&
                     (p.out.sz * esz) % 16 == 0 && (p.out.sn * esz) % 16 == 0 && (p.out_fp32 || !p.accumulate);

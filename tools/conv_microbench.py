@@ -104,6 +104,8 @@ def main():
         ("per-tap, per-thread store epilogue", {9: 1, 29: 1}),
         ("per-tap, bulk-store epilogue", {9: 1, 29: 2}),
         ("per-tap, coalesced-store epilogue", {9: 1, 29: 3}),
+        ("persistent (knob 16 = 3)", {9: 1, 16: 3}),
+        ("persistent, 74 CTAs", {9: 1, 16: 3, 18: 74}),
     ]
     if args.layers:
         layers = [layers[int(i)] for i in args.layers.split(",")]
