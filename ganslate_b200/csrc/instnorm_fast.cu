@@ -355,6 +355,193 @@ in_bwd_fast_kernel(const __grid_constant__ gb_in_bwd_params p, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------ backward, lean
+// Third generation of the fused backward (knob 22 = 4, then the default): the same two passes around a grid barrier,
+// written for instruction count -- the first generation is ISSUE-bound, not memory-bound (29 instructions per element
+// and pass, identical time with a cold and a warm L2: profiles/r02b_in_microbench_b8.txt).  Eight channels per thread
+// (16 B of bf16 x, 2 x 16 B of fp32 dy: per-pixel index arithmetic is shared by twice as many elements), U pixels in
+// flight per thread with all their loads issued first, x-hat as one FMA (x * rstd - mean * rstd), the mirrored
+// border positions of a reflection-padded gradient behind one unsigned compare per axis.
+constexpr int LTHREADS = 256;
+constexpr int LBLOCKS_PER_SM = 2;
+
+__device__ __forceinline__ bool near_edge(int i, int n, int g) {
+  // true for the interior indices that have a mirror image in a border of width g: 1..g and n-1-g..n-2
+  return (unsigned)(i - 1) < (unsigned)g || (unsigned)(i - (n - 1 - g)) < (unsigned)g;
+}
+
+__device__ __forceinline__ void add_mirrors8(const gb_view& v, const float* img, int y, int x, int H, int W, int g,
+                                             float (&f)[8]) {
+  const int my = mirror_of(y, H, g), mx = mirror_of(x, W, g);
+  auto add = [&](const float* q) {
+    const float4 a = __ldcg(reinterpret_cast<const float4*>(q)), b = __ldcg(reinterpret_cast<const float4*>(q) + 1);
+    f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+  };
+  if (my != NO_MIRROR) add(img + my * (int)v.sy + x * (int)v.sx);
+  if (mx != NO_MIRROR) add(img + y * (int)v.sy + mx * (int)v.sx);
+  if (my != NO_MIRROR && mx != NO_MIRROR) add(img + my * (int)v.sy + mx * (int)v.sx);
+}
+
+template <bool RES, int PASS>
+__device__ __forceinline__ void in_bwd_lean_pass(const gb_in_bwd_params& p, const FastGeom& g, float neg_slope, float* red,
+                                                 bool sync_first) {
+  constexpr int U = RES && PASS == 0 ? 2 : 4;
+  const gb_view& x = p.x;
+  const gb_view& dy = p.dy_b;
+  const int C8 = x.C >> 3;
+  const int slots = LTHREADS / C8;
+  const int cg = threadIdx.x % C8;
+  const int slot = threadIdx.x / C8;
+  const int c = cg * 8;
+  const int n = blockIdx.y;
+  const int W = x.W, H = dy.H;
+  const uint32_t P = (uint32_t)x.D * x.H * x.W;
+  const uint32_t p0 = blockIdx.x * (uint32_t)g.ppb;
+  const uint32_t p1 = min(P, p0 + (uint32_t)g.ppb);
+  const float invP = 1.f / (float)P;
+  float ka[8], kb[8], m1[8], m2[8], s1[8], s2[8];   // x-hat = x * ka + kb
+  {
+    const float4* sp = reinterpret_cast<const float4*>(p.stats + ((int64_t)n * x.C + c) * 2);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float4 a = sp[h];
+      const float mu0 = a.x * invP, mu1 = a.z * invP;
+      const float r0 = rsqrtf(fmaxf(a.y * invP - mu0 * mu0, 0.f) + p.eps);
+      const float r1 = rsqrtf(fmaxf(a.w * invP - mu1 * mu1, 0.f) + p.eps);
+      ka[2 * h] = r0; kb[2 * h] = -mu0 * r0;
+      ka[2 * h + 1] = r1; kb[2 * h + 1] = -mu1 * r1;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) m1[e] = m2[e] = s1[e] = s2[e] = 0.f;
+  if (PASS == 1) {
+    const float4* bp = reinterpret_cast<const float4*>(p.bstats + ((int64_t)n * x.C + c) * 2);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float4 a = __ldcg(bp + h);
+      m1[2 * h] = a.x * invP; m2[2 * h] = a.y * invP; m1[2 * h + 1] = a.z * invP; m2[2 * h + 1] = a.w * invP;
+    }
+  }
+  const bool want_dbias = PASS == 1 && p.dbias != nullptr;
+  const float* gb = reinterpret_cast<const float*>(dy.ptr) + (int64_t)n * dy.sn + c;
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x.ptr) + (int64_t)n * x.sn + c;
+  float* sb = RES ? reinterpret_cast<float*>(p.dy_sum.ptr) + (int64_t)n * p.dy_sum.sn + c : nullptr;
+  __nv_bfloat16* db = reinterpret_cast<__nv_bfloat16*>(p.dx.ptr) + (int64_t)n * p.dx.sn + c;
+  const int gpad = dy.pad;
+  const int gsy = (int)dy.sy, gsx = (int)dy.sx, xsy = (int)x.sy, xsx = (int)x.sx;
+  if (slot < slots) {
+    int cy, cx;
+    {
+      const uint32_t pix = p0 + (uint32_t)slot;
+      cy = (int)(pix / (uint32_t)W);
+      cx = (int)(pix - (uint32_t)cy * (uint32_t)W);
+    }
+    for (uint32_t base = p0 + slot; base < p1; base += (uint32_t)(U * slots)) {
+      float4 ga[U], gb2[U];
+      uint4 lx[U];
+      int py[U], px[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        py[u] = cy;
+        px[u] = cx;
+        if (base + (uint32_t)(u * slots) < p1) {
+          const float4* gp = reinterpret_cast<const float4*>(gb + cy * gsy + cx * gsx);
+          ga[u] = __ldcg(gp);
+          gb2[u] = __ldcg(gp + 1);
+          lx[u] = __ldg(reinterpret_cast<const uint4*>(xb + cy * xsy + cx * xsx));
+        }
+        cx += slots;
+        while (cx >= W) {
+          cx -= W;
+          ++cy;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (base + (uint32_t)(u * slots) < p1) {
+          float gg[8] = {ga[u].x, ga[u].y, ga[u].z, ga[u].w, gb2[u].x, gb2[u].y, gb2[u].z, gb2[u].w};
+          float xv[8];
+          unpack8(lx[u], xv);
+          if (gpad > 0 && (near_edge(py[u], H, gpad) || near_edge(px[u], W, gpad)))
+            add_mirrors8(dy, gb, py[u], px[u], H, W, gpad, gg);
+          if (RES && PASS == 0) {
+            float4* rp = reinterpret_cast<float4*>(sb + py[u] * (int)p.dy_sum.sy + px[u] * (int)p.dy_sum.sx);
+            float4 a = __ldcg(rp), b = __ldcg(rp + 1);
+            a.x += gg[0]; a.y += gg[1]; a.z += gg[2]; a.w += gg[3];
+            b.x += gg[4]; b.y += gg[5]; b.z += gg[6]; b.w += gg[7];
+            rp[0] = a;
+            rp[1] = b;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float xh = fmaf(xv[e], ka[e], kb[e]);
+            gg[e] = xh > 0.f ? gg[e] : gg[e] * neg_slope;
+            xv[e] = xh;
+          }
+          if (PASS == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              s1[e] += gg[e];
+              s2[e] = fmaf(gg[e], xv[e], s2[e]);
+            }
+          } else {
+            float d[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d[e] = ka[e] * (gg[e] - m1[e] - xv[e] * m2[e]);
+            *reinterpret_cast<uint4*>(db + py[u] * (int)p.dx.sy + px[u] * (int)p.dx.sx) = pack8(d);
+            if (want_dbias) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) s1[e] += d[e];
+            }
+          }
+        }
+      }
+    }
+  }
+  // block reduction over the pixel slots, then one atomic per channel and block
+  if (PASS == 0 || want_dbias) {
+    if (sync_first) __syncthreads();  // `red` may still be read by the previous pass
+    if (slot < slots) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        red[(slot * x.C + c + e) * 2 + 0] = s1[e];
+        red[(slot * x.C + c + e) * 2 + 1] = s2[e];
+      }
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < x.C; ch += LTHREADS) {
+      float a = 0.f, b = 0.f;
+      for (int k = 0; k < slots; ++k) {
+        a += red[(k * x.C + ch) * 2 + 0];
+        b += red[(k * x.C + ch) * 2 + 1];
+      }
+      if (PASS == 0) {
+        atomicAdd(p.bstats + ((int64_t)n * x.C + ch) * 2 + 0, a);
+        atomicAdd(p.bstats + ((int64_t)n * x.C + ch) * 2 + 1, b);
+      } else {
+        atomicAdd(p.dbias + ch, a);
+      }
+    }
+  }
+}
+
+template <bool RES, int PASS>
+__global__ void __launch_bounds__(LTHREADS, LBLOCKS_PER_SM)
+in_bwd_lean_kernel(const __grid_constant__ gb_in_bwd_params p, const __grid_constant__ FastGeom g, float neg_slope) {
+  gb_pdl_enter();
+  extern __shared__ float red[];  // [slots][C][2]
+  if (PASS == 2) {
+    in_bwd_lean_pass<RES, 0>(p, g, neg_slope, red, false);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(p.bstats + (int64_t)p.x.N * p.x.C * 2);
+    grid_barrier(counter, (unsigned int)g.total_blocks);
+    in_bwd_lean_pass<RES, 1>(p, g, neg_slope, red, true);
+  } else if (PASS == 0) {
+    in_bwd_lean_pass<RES, 0>(p, g, neg_slope, red, false);
+  } else {
+    in_bwd_lean_pass<RES, 1>(p, g, neg_slope, red, false);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 // rows = D*H lines of W pixels with one row stride: any 2-D view, 3-D views whose planes are row-contiguous
 bool row_addressable(const gb_view& v) { return v.D == 1 || (v.pad == 0 && v.sz == (int64_t)v.H * v.sy); }
@@ -440,6 +627,39 @@ int launch_bwd(const gb_in_bwd_params& p, float neg_slope, cudaStream_t st) {
   return 0;
 }
 
+template <bool RES>
+int launch_bwd_lean(const gb_in_bwd_params& p, float neg_slope, cudaStream_t st) {
+  const int C8 = p.x.C / 8;
+  const int slots = LTHREADS / C8;
+  const size_t smem = sizeof(float) * 2 * slots * p.x.C;
+  static int occ = -1;  // co-resident blocks per SM of the single-launch kernel (per instantiation)
+  static size_t occ_smem = 0;
+  if (occ < 0 || occ_smem != smem) {
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, in_bwd_lean_kernel<RES, 2>, LTHREADS, smem) != cudaSuccess) o = 0;
+    cudaGetLastError();
+    occ = o;
+    occ_smem = smem;
+  }
+  bool fits = false;
+  FastGeom g = plan(p.x, num_sms() * (occ > 0 ? occ : LBLOCKS_PER_SM), &fits, 8);
+  const dim3 grid(g.nblocks, p.x.N);
+  if (occ > 0 && fits && g_gb_knobs[6] == 0) {
+    void* args[] = {(void*)&p, (void*)&g, (void*)&neg_slope};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)in_bwd_lean_kernel<RES, 2>, grid, dim3(LTHREADS), args, smem, st);
+    if (e == cudaSuccess) {
+      __atomic_fetch_add(&g_gb_launches, 1ull, __ATOMIC_RELAXED);
+      return 0;
+    }
+    cudaGetLastError();  // cooperative launch not possible here: fall through to two launches
+  }
+  gb_klaunch(in_bwd_lean_kernel<RES, 0>, grid, LTHREADS, smem, st, p, g, neg_slope);
+  GB_LAUNCH_CHECK();
+  gb_klaunch(in_bwd_lean_kernel<RES, 1>, grid, LTHREADS, smem, st, p, g, neg_slope);
+  GB_LAUNCH_CHECK();
+  return 0;
+}
+
 bool act_to_slope(int act, float slope, float* out) {
   switch (act) {
     case GB_ACT_NONE: *out = 1.f; return true;
@@ -488,5 +708,13 @@ int gb_in_bwd_fast(const gb_in_bwd_params& p, cudaStream_t st) {
   if (!small_offsets(x) || !small_offsets(p.dx) || !small_offsets(p.dy_b) || (has_res && !small_offsets(p.dy_sum))) return -1;
   // (x, dx and dy_sum may be interior views of bordered buffers: only their interior is touched)
   if (p.dy_b.pad > 0 && (p.dy_b.D != 1 || p.dy_b.H <= 2 * p.dy_b.pad + 1 || p.dy_b.W <= 2 * p.dy_b.pad + 1)) return -1;
+  // third generation (8 channels per thread): knob 22 = 4 opts in, 5 opts out once it is the default
+  const int C8 = x.C / 8;
+  const bool lean_ok = x.C % 8 == 0 && C8 <= LTHREADS && LTHREADS % C8 == 0 && aligned(x, 2, 8) && aligned(p.dx, 2, 8) &&
+                       aligned(p.dy_b, 4, 8) && (!has_res || aligned(p.dy_sum, 4, 8));
+  if (lean_ok && g_gb_knobs[22] == 4) {
+    ++g_gb_knobs[23];
+    return has_res ? launch_bwd_lean<true>(p, ns, st) : launch_bwd_lean<false>(p, ns, st);
+  }
   return has_res ? launch_bwd<true>(p, ns, st) : launch_bwd<false>(p, ns, st);
 }
