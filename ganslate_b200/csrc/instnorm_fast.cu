@@ -360,7 +360,7 @@ in_bwd_fast_kernel(const __grid_constant__ gb_in_bwd_params p, const __grid_cons
 // written for instruction count -- the first generation is ISSUE-bound, not memory-bound (29 instructions per element
 // and pass, identical time with a cold and a warm L2: profiles/r02b_in_microbench_b8.txt).  Eight channels per thread
 // (16 B of bf16 x, 2 x 16 B of fp32 dy: per-pixel index arithmetic is shared by twice as many elements), U pixels in
-// flight per thread with all their loads issued first, x-hat as one FMA (x * rstd - mean * rstd), the mirrored
+// flight per thread with all their loads issued first, the mirrored
 // border positions of a reflection-padded gradient behind one unsigned compare per axis.
 constexpr int LTHREADS = 256;
 constexpr int LBLOCKS_PER_SM = 2;
@@ -399,7 +399,8 @@ __device__ __forceinline__ void in_bwd_lean_pass(const gb_in_bwd_params& p, cons
   const uint32_t p0 = blockIdx.x * (uint32_t)g.ppb;
   const uint32_t p1 = min(P, p0 + (uint32_t)g.ppb);
   const float invP = 1.f / (float)P;
-  float ka[8], kb[8], m1[8], m2[8], s1[8], s2[8];   // x-hat = x * ka + kb
+  float ka[8], kb[8], m1[8], m2[8], s1[8], s2[8];   // x-hat = (x - kb) * ka: the FORWARD kernel's expression, so that
+                                                    // the activation mask is the one the forward pass applied
   {
     const float4* sp = reinterpret_cast<const float4*>(p.stats + ((int64_t)n * x.C + c) * 2);
 #pragma unroll
@@ -408,8 +409,8 @@ __device__ __forceinline__ void in_bwd_lean_pass(const gb_in_bwd_params& p, cons
       const float mu0 = a.x * invP, mu1 = a.z * invP;
       const float r0 = rsqrtf(fmaxf(a.y * invP - mu0 * mu0, 0.f) + p.eps);
       const float r1 = rsqrtf(fmaxf(a.w * invP - mu1 * mu1, 0.f) + p.eps);
-      ka[2 * h] = r0; kb[2 * h] = -mu0 * r0;
-      ka[2 * h + 1] = r1; kb[2 * h + 1] = -mu1 * r1;
+      ka[2 * h] = r0; kb[2 * h] = mu0;
+      ka[2 * h + 1] = r1; kb[2 * h + 1] = mu1;
     }
   }
 #pragma unroll
@@ -474,7 +475,7 @@ __device__ __forceinline__ void in_bwd_lean_pass(const gb_in_bwd_params& p, cons
           }
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const float xh = fmaf(xv[e], ka[e], kb[e]);
+            const float xh = (xv[e] - kb[e]) * ka[e];
             gg[e] = xh > 0.f ? gg[e] : gg[e] * neg_slope;
             xv[e] = xh;
           }

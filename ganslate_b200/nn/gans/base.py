@@ -17,13 +17,14 @@ from ganslate_b200.utils.builders import build_D, build_G
 
 
 class TrainingMetricsLite:
-    """The step-path part of ganslate/utils/metrics/train_metrics.py:56-67: mean discriminator outputs."""
+    """The step-path part of ganslate/utils/metrics/train_metrics.py:10-67: mean discriminator outputs
+    (`discriminator_evolution`) and the SSIM of the reconstructions (`ssim`: 1 - SSIMLoss((x + 1) / 2, (y + 1) / 2,
+    data_range=1), train_metrics.py:36-47,56-67) -- the same stencil kernel the SSIM cycle loss runs (csrc/ssim.cu)."""
 
     def __init__(self, conf):
         m = conf.train.get("metrics", None)
         self.output_distributions = bool(m and m.get("discriminator_evolution", False))
-        if m and m.get("ssim", False):
-            raise NotImplementedError("train.metrics.ssim is not on the B200 path (SURVEY.md section 8f rank 2)")
+        self.ssim = bool(m and m.get("ssim", False))
 
     def compute_metrics_D(self, name, pred_real, pred_fake):
         if not self.output_distributions:
@@ -32,8 +33,21 @@ class TrainingMetricsLite:
             pred_real, pred_fake = pred_real[next(iter(pred_real))], pred_fake[next(iter(pred_fake))]
         return {f"{name}_real": pred_real.detach().mean(), f"{name}_fake": pred_fake.detach().mean()}
 
+    def get_SSIM_metric(self, input, target):
+        from ganslate_b200 import ops
+        with torch.no_grad():
+            # (x + 1) / 2 is folded into the kernel's input mapping (in_scale 0.5, in_shift 0.5), data_range 1
+            return 1 - ops.SsimFn.apply(input.detach(), target.detach(), 0.5, 0.5, 1.0)
+
     def compute_metrics_G(self, visuals):
-        return {}
+        out = {}
+        if not self.ssim:
+            return out
+        if visuals.get("rec_A") is not None and visuals.get("real_A") is not None:
+            out["ssim_A"] = self.get_SSIM_metric(visuals["real_A"], visuals["rec_A"])
+        if visuals.get("rec_B") is not None and visuals.get("real_B") is not None:
+            out["ssim_B"] = self.get_SSIM_metric(visuals["real_B"], visuals["rec_B"])
+        return out
 
 
 class BaseGAN(ABC):

@@ -6,7 +6,7 @@ from dataclasses import dataclass, field
 import torch
 
 from ganslate_b200 import configs
-from ganslate_b200.data.utils.image_pool import ImagePool
+from ganslate_b200.data.utils.image_pool import make_image_pool
 from ganslate_b200.nn.gans.base import BaseGAN
 from ganslate_b200.nn.losses.adversarial_loss import AdversarialLoss
 from ganslate_b200.nn.losses.cyclegan_losses import CycleGANLosses
@@ -36,8 +36,8 @@ class CycleGAN(BaseGAN):
         # dict order = construction and weight-init order (cyclegan.py:52; base.py:51-67)
         self.networks = {n: None for n in (['G_AB', 'G_BA', 'D_B', 'D_A'] if self.is_train else ['G_AB'])}
         if self.is_train:
-            self.fake_A_pool = ImagePool(conf.train.gan.pool_size)
-            self.fake_B_pool = ImagePool(conf.train.gan.pool_size)
+            self.fake_A_pool = make_image_pool(conf)
+            self.fake_B_pool = make_image_pool(conf)
         self.setup()
 
     def init_criterions(self):
@@ -65,8 +65,8 @@ class CycleGAN(BaseGAN):
             self.run_graphed('G', lambda: self._phase_G(step=sync is None))
             if sync:
                 sync['G'].launch()  # NCCL on a side stream, overlaps with the discriminator graph
-            fake_B = self.stage_input('pool_B', self.fake_B_pool.query(self.visuals['fake_B'].detach().clone()))
-            fake_A = self.stage_input('pool_A', self.fake_A_pool.query(self.visuals['fake_A'].detach().clone()))
+            fake_B = self.stage_input('pool_B', self._pool_query(self.fake_B_pool, self.visuals['fake_B']))
+            fake_A = self.stage_input('pool_A', self._pool_query(self.fake_A_pool, self.visuals['fake_A']))
             self.run_graphed('D', lambda: self._phase_D(fake_B, fake_A, step=sync is None))
             if sync:
                 # same result as the reference order (G step before the D phase): the D phase reads neither the
@@ -88,6 +88,14 @@ class CycleGAN(BaseGAN):
                 self.optimizers['G'].step()
                 sync['D'].finish()
                 self.optimizers['D'].step()
+
+    @staticmethod
+    def _pool_query(pool, images):
+        """Graph mode: the pool must not keep a reference into the graph's static output buffers.  The device pool
+        copies the images into its own storage; the reference's list-based pool stores the tensors it is given."""
+        from ganslate_b200.data.utils.image_pool import DeviceImagePool
+        images = images.detach()
+        return pool.query(images if isinstance(pool, DeviceImagePool) else images.clone())
 
     def _phase_G(self, step=True):
         discriminators = [self.networks['D_B'], self.networks['D_A']]

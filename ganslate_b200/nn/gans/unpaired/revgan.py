@@ -10,7 +10,7 @@ from dataclasses import dataclass, field
 import torch
 
 from ganslate_b200 import configs
-from ganslate_b200.data.utils.image_pool import ImagePool
+from ganslate_b200.data.utils.image_pool import make_image_pool
 from ganslate_b200.nn.gans.base import BaseGAN
 from ganslate_b200.nn.gans.unpaired import cyclegan
 from ganslate_b200.nn.losses.adversarial_loss import AdversarialLoss
@@ -37,8 +37,8 @@ class RevGAN(BaseGAN):
         self.optimizers = {'G': None, 'D': None}
         self.networks = {n: None for n in (['G', 'D_B', 'D_A'] if self.is_train else ['G'])}  # revgan.py:50
         if self.is_train:
-            self.fake_A_pool = ImagePool(conf.train.gan.pool_size)
-            self.fake_B_pool = ImagePool(conf.train.gan.pool_size)
+            self.fake_A_pool = make_image_pool(conf)
+            self.fake_B_pool = make_image_pool(conf)
         self.setup()
 
     def init_criterions(self):

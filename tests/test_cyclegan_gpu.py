@@ -75,8 +75,9 @@ def test_cyclegan_step_vs_oracles(size, blocks):
         else:
             # biases with a real gradient (first / last convolution of a network): a signed sum over all pixels that
             # nearly cancels (3 numbers for the generators' output layer; the bf16-point CPU oracle itself is 0.2-0.4
-            # off in relative L2), so it is judged like the others OR on the absolute scale of the net's gradients
-            if cos < 0.9 and l2 > 1.5 * e_bf16[k][0] + 0.05 and absmax > 5e-3 * wmax[net]:
+            # off in relative L2 and two runs of THIS path differ by as much: the statistics atomics reorder), so it is
+            # judged like the others (2 x the oracle's own error) OR on the absolute scale of the net's gradients
+            if cos < 0.9 and l2 > 2.0 * e_bf16[k][0] + 0.05 and absmax > 5e-3 * wmax[net]:
                 bad.append((k, "bias", l2, cos, e_bf16[k][0], absmax, wmax[net]))
     assert not bad, bad
 

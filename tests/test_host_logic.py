@@ -337,3 +337,26 @@ def test_replicate_pad_index_math_matches_torch():
                     bwd[z, yy, xx] = sum(gn[a, b, c] for a in readers(z, D, pz) for b in readers(yy, H, py)
                                          for c in readers(xx, W, px))
         np.testing.assert_allclose(bwd, x.grad.numpy()[0, 0], rtol=1e-12, atol=1e-12)
+
+
+def test_device_image_pool_makes_the_reference_pools_decisions():
+    """DeviceImagePool (one preallocated tensor, gather + scatter per query) returns, image by image, what the
+    reference's list-based ImagePool (ganslate/data/utils/image_pool.py:24-60) returns for the same `random` stream --
+    including a slot hit twice inside one batch and the fill phase ending mid-batch."""
+    import random
+    import torch
+    from ganslate_b200.data.utils.image_pool import DeviceImagePool, ImagePool
+    g = torch.Generator().manual_seed(0)
+    for pool_size, batch in ((5, 3), (50, 8), (4, 8), (0, 2)):
+        ref, dev = ImagePool(pool_size), DeviceImagePool(pool_size)
+        for it in range(40):
+            x = torch.randn(batch, 2, 3, 3, generator=g)
+            random.seed(1000 + it)
+            a = ref.query(x.clone())
+            random.seed(1000 + it)
+            b = dev.query(x.clone())
+            assert torch.equal(a, b), (pool_size, batch, it)
+        if pool_size:
+            assert dev.num_imgs == ref.num_imgs
+            for k in range(ref.num_imgs):
+                assert torch.equal(ref.images[k][0], dev.store[k]), (pool_size, k)

@@ -18,14 +18,14 @@ CASES = [
     ("conv", dict(name="3x3 reflect1 256->256 64x64 N=8", cin=256, cout=256, k=3, s=1, p=0, H=64, W=64, N=8, reflect=1)),
     ("conv", dict(name="3x3 p1 64->64 32x24", cin=64, cout=64, k=3, s=1, p=1, H=32, W=24, N=1)),
     ("conv", dict(name="1x1 64->256 32x32", cin=64, cout=256, k=1, s=1, p=0, H=32, W=32)),
-    ("conv", dict(name="3x3 N=3 ragged 64->72 19x23", cin=64, cout=72, k=3, s=1, p=1, H=19, W=23, N=3)),
+    ("conv", dict(name="3x3 N=3 ragged 64->128 19x23", cin=64, cout=128, k=3, s=1, p=1, H=19, W=23, N=3)),
     ("conv", dict(name="3x3 s2 p1 64->128 64x64", cin=64, cout=128, k=3, s=2, p=1, H=64, W=64, N=2)),
     ("conv", dict(name="3x3 s2 p1 128->256 128x128 N=4", cin=128, cout=256, k=3, s=2, p=1, H=128, W=128, N=4)),
     ("conv", dict(name="convT 3x3 s2 p1 op1 128->64 32x32", cin=128, cout=64, k=3, s=2, p=1, H=32, W=32, N=2, transposed=True, op_pad=1)),
     ("conv", dict(name="convT 3x3 s2 p1 op1 256->128 64x64 N=4", cin=256, cout=128, k=3, s=2, p=1, H=64, W=64, N=4, transposed=True, op_pad=1)),
     ("conv", dict(name="4x4 s2 p1 64->128 64x64 (PatchGAN)", cin=64, cout=128, k=4, s=2, p=1, H=64, W=64, N=2)),
     ("conv", dict(name="4x4 s1 p1 256->512 32x32", cin=256, cout=512, k=4, s=1, p=1, H=32, W=32)),
-    ("conv", dict(name="4x4 s1 p1 512->1 31x31 (PatchGAN out)", cin=512, cout=1, k=4, s=1, p=1, H=31, W=31, N=2)),
+    ("conv", dict(name="4x4 s1 p1 512->64 31x31 N=2", cin=512, cout=64, k=4, s=1, p=1, H=31, W=31, N=2)),
     ("conv", dict(name="3d 3x3x3 p1 64->64 4x16x16", cin=64, cout=64, k=3, s=1, p=1, H=16, W=16, D=4)),
     ("conv", dict(name="3d 4x4x4 s2 p1 64->128 8x32x32", cin=64, cout=128, k=4, s=2, p=1, H=32, W=32, D=8)),
     ("conv", dict(name="7x7 reflect3 3->64 64x64 (window)", cin=3, cout=64, k=7, s=1, p=0, H=64, W=64, reflect=3)),

@@ -54,3 +54,28 @@ def test_cycle_loss_with_ssim_matches_oracle():
     for k in ("rec_A", "rec_B", "idt_A", "idt_B"):
         err = (gpu[k].grad.cpu() - cpu[k].grad).abs().max().item()
         assert err <= 2e-3 * cpu[k].grad.abs().max().item(), (k, err)
+
+
+def test_training_ssim_metric_matches_reference_formula():
+    """train.metrics.ssim (ganslate/utils/metrics/train_metrics.py:36-47,56-67): ssim_A = 1 - SSIMLoss((real_A + 1) / 2,
+    (rec_A + 1) / 2, data_range=1), no gradient; here the stencil kernel with the input mapping folded in."""
+    from types import SimpleNamespace as NS
+    from ganslate_b200.nn.gans.base import TrainingMetricsLite
+    from oracle import torch_oracle as O
+
+    class Conf(dict):
+        def get(self, k, d=None):
+            return dict.get(self, k, d)
+    conf = NS(train=Conf(metrics=Conf(ssim=True, discriminator_evolution=False)))
+    tm = TrainingMetricsLite(conf)
+    g = torch.Generator().manual_seed(3)
+    real = torch.rand(2, 3, 48, 40, generator=g) * 2 - 1
+    rec = (real + 0.2 * torch.randn(2, 3, 48, 40, generator=g)).clamp(-1, 1)
+    vis = {"real_A": real.cuda(), "rec_A": rec.cuda().requires_grad_(True), "real_B": rec.cuda(), "rec_B": real.cuda()}
+    m = tm.compute_metrics_G(vis)
+    ref_a = 1 - O.ssim_distance((real + 1) / 2, (rec + 1) / 2, 1.0)
+    ref_b = 1 - O.ssim_distance((rec + 1) / 2, (real + 1) / 2, 1.0)
+    assert abs(float(m["ssim_A"]) - float(ref_a)) <= 1e-4 * abs(float(ref_a)) + 1e-6
+    assert abs(float(m["ssim_B"]) - float(ref_b)) <= 1e-4 * abs(float(ref_b)) + 1e-6
+    assert not m["ssim_A"].requires_grad
+    assert TrainingMetricsLite(NS(train=Conf(metrics=Conf(ssim=False)))).compute_metrics_G(vis) == {}
