@@ -17,7 +17,16 @@ int gb_tma_activation_map(const gb_view& v, int tw, int th, CUtensorMap* out, co
 // swizzle.  Stores clip at the tensor's extents, so tiles that overhang the image need no masking.
 int gb_tma_store_map(const gb_view& v, int tw, int th, const int* mul, int fp32, CUtensorMap* out);
 
+// 2-D fp32 map {cols, rows} (row pitch = cols * 4 bytes) with box {32 floats = 128 bytes, box_rows}, 128B swizzle: the
+// weight-gradient workspace as the destination of bulk reduce-adds.
+int gb_tma_f32_matrix_map(const void* ptr, int cols, int rows, int box_rows, CUtensorMap* out);
+
 #ifdef __CUDACC__
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
 // smem (128B-swizzled tile, written by the generic proxy + fence.proxy.async) -> global, clipped at the tensor bounds
 __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
   asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"

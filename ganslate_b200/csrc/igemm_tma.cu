@@ -154,8 +154,7 @@ __device__ __forceinline__ void staged_epilogue(const gb_conv_params& p, const T
   const bool use_tma = mode <= 3;
   const bool want_stats = !fp32 && p.stats != nullptr;
   static_assert(BN >= 64, "staged epilogue needs BN >= 64");
-  if (want_stats)
-    for (int i = tid; i < BN * 2; i += 256) sacc[i] = 0.f;
+  (void)sacc;
   if (fp32) {
     stage_tile<BN, GB_ACT_NONE, true>(p, tmem_base, lg, half, lane, have_acc, row_ok, bias_s, stage);
   } else {
@@ -234,18 +233,26 @@ __device__ __forceinline__ void staged_epilogue(const gb_conv_params& p, const T
       f = unpack_bf16x2(q4.z); s1[4] += f.x; s2[4] = fmaf(f.x, f.x, s2[4]); s1[5] += f.y; s2[5] = fmaf(f.y, f.y, s2[5]);
       f = unpack_bf16x2(q4.w); s1[6] += f.x; s2[6] = fmaf(f.x, f.x, s2[6]); s1[7] += f.y; s2[7] = fmaf(f.y, f.y, s2[7]);
     }
+    // partial sums of the RG row groups -> scratch behind the staged tile (plain stores: every (rg, channel) has one
+    // owner), then one thread per channel adds the RG partials and issues the CTA's single atomic per moment
+    float* part = reinterpret_cast<float*>(stage + (size_t)(BN / 64) * 16384);   // [RG][BN][2]
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      atomicAdd(&sacc[(cg * 8 + e) * 2 + 0], s1[e]);
-      atomicAdd(&sacc[(cg * 8 + e) * 2 + 1], s2[e]);
-    }
+    for (int e = 0; e < 8; e += 2)
+      *reinterpret_cast<float4*>(part + ((size_t)rg * BN + cg * 8 + e) * 2) = make_float4(s1[e], s2[e], s1[e + 1], s2[e + 1]);
     __syncthreads();
     for (int i = tid; i < BN; i += 256) {
       const int col = n0 + i;
       if (col < p.ncols) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int k = 0; k < RG; ++k) {
+          const float2 v = *reinterpret_cast<const float2*>(part + ((size_t)k * BN + i) * 2);
+          a += v.x;
+          b += v.y;
+        }
         float* dst = p.stats + ((int64_t)ec.n * p.out.C + col) * 2;
-        atomicAdd(dst, sacc[i * 2]);
-        atomicAdd(dst + 1, sacc[i * 2 + 1]);
+        atomicAdd(dst, a);
+        atomicAdd(dst + 1, b);
       }
     }
   }
@@ -896,6 +903,31 @@ int gb_tma_store_map(const gb_view& v, int tw, int th, const int* mul, int fp32,
   return 0;
 }
 
+int gb_tma_f32_matrix_map(const void* ptr, int cols, int rows, int box_rows, CUtensorMap* out) {
+  struct {
+    const void* w;
+    int cols, rows, br, tag;
+  } k = {ptr, cols, rows, box_rows, 0x66333264};
+  std::string key(reinterpret_cast<const char*>(&k), sizeof(k));
+  std::lock_guard<std::mutex> lk(g_map_mutex);
+  auto it = g_map_cache.find(key);
+  if (it != g_map_cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = encode_fn()(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(fp32 matrix) failed: %d", (int)r);
+  if (g_map_cache.size() > 4096) g_map_cache.clear();
+  g_map_cache[key] = *out;
+  return 0;
+}
+
 // Pixel-window views (8 pixels x 8 channels read as one 64-channel "pixel", pixel stride 16 B) need a tensor map
 // whose pixel stride is smaller than its channel extent; probe once whether the driver encodes it.
 extern "C" int gb_tma_window_supported(void) {
@@ -951,7 +983,8 @@ int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb
   size_t ring = (size_t)ns * C::STAGE_BYTES;
   if (tgl.store_mode != 0) {
     const bool f32 = tgl.store_mode == 2 || tgl.store_mode == 3 || tgl.store_mode >= 5;
-    const size_t staging = (size_t)BN * 128 * (f32 ? 4 : 2);
+    // (bf16: + 16 KB behind the tile for the partial statistics of the row groups)
+    const size_t staging = (size_t)BN * 128 * (f32 ? 4 : 2) + (f32 ? 0 : 16384);
     if (staging > (size_t)C::SMEM - 2048) tgl.store_mode = 0;
     else if (ring < staging) ring = staging;
   }

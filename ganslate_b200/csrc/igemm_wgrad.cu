@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(256, WCfg<BN, RT>::MIN_CTAS) igemm_wgrad_kerne
                                                                               const __grid_constant__ PixDivs divs,
                                                                               const __grid_constant__ CUtensorMap map_p,
                                                                               const __grid_constant__ CUtensorMap map_g,
-                                                                              int blocks_per_split) {
+                                                                              const __grid_constant__ CUtensorMap map_d,
+                                                                              int blocks_per_split, int bulk_epilogue) {
   gb_pdl_enter();
   using C = WCfg<BN, RT>;
   static_assert(RT == 1 || TMA, "two row tiles per CTA only on the TMA-fed path");
@@ -259,6 +260,45 @@ __global__ void __launch_bounds__(256, WCfg<BN, RT>::MIN_CTAS) igemm_wgrad_kerne
 
   mbar_wait(accum_bar, 0);
   tc_fence_after();
+  if (TMA && bulk_epilogue) {
+    // staged epilogue: the accumulator tile goes through 128B-swizzled [128 rows][32 floats] sub-tiles in the (idle)
+    // operand ring and leaves as BN / 32 bulk reduce-adds into the fp32 workspace -- instead of 8192 16-byte
+    // red.global.add per CTA whose lanes are 4 * kpad bytes apart (same move as the data kernel's fp32 epilogue:
+    // 10.4 K -> 6.6 K cycles per tile, profiles/r02d_conv_timeline_b8.txt)
+#pragma unroll 1
+    for (int r = 0; r < RT; ++r) {
+      const int lg = warp & 3;
+      const int half = warp >> 2;
+      const int row = lg * 32 + lane;
+      const uint32_t rsw = (uint32_t)(row & 7);
+      if (r > 0) {  // the previous row tile's bulk stores must have read the staging area
+        if (tid == 0) tma_store_wait_read();
+        __syncthreads();
+      }
+#pragma unroll 1
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(r * BN + c0), acc);
+        tmem_ld_wait();
+        uint8_t* dst = smem + (size_t)(c0 >> 5) * 16384 + (size_t)row * 128;
+#pragma unroll
+        for (int jq = 0; jq < 8; ++jq)
+          *reinterpret_cast<uint4*>(dst + (((uint32_t)jq ^ rsw) << 4)) =
+              make_uint4(acc[4 * jq], acc[4 * jq + 1], acc[4 * jq + 2], acc[4 * jq + 3]);
+      }
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        for (int sub = 0; sub * 32 < BN; ++sub) {
+          const int col = kt * BN + sub * 32;
+          if (col >= p.kpad) break;
+          tma_reduce_add_2d(&map_d, base + sub * 16384, col, rt + r * BM);
+        }
+        tma_store_commit();
+      }
+    }
+    if (tid == 0) tma_store_wait_read();
+  } else {
 #pragma unroll 1
   for (int r = 0; r < RT; ++r) {
     const int lg = warp & 3;
@@ -281,6 +321,7 @@ __global__ void __launch_bounds__(256, WCfg<BN, RT>::MIN_CTAS) igemm_wgrad_kerne
         }
       }
     }
+  }
   }
   tc_fence_before();
   __syncthreads();
@@ -308,9 +349,10 @@ int launch(const gb_wgrad_params& p, cudaStream_t st) {
   bool tma = g_gb_knobs[3] == 0 && gb_tma_available() && p.gathered.C % 64 == 0 && p.plain.C % 64 == 0 &&
              (unit || (g_gb_knobs[0] != 2 && p.mul[0] <= 4 && p.mul[1] <= 4 && p.mul[2] <= 4)) && p.plain.pad == 0 &&
              p.gathered.pad == 0;
-  CUtensorMap map_p, map_g;
+  CUtensorMap map_p, map_g, map_d;
   memset(&map_p, 0, sizeof(map_p));
   memset(&map_g, 0, sizeof(map_g));
+  memset(&map_d, 0, sizeof(map_d));
   if (tma) {
     int tw = 8;
     while (tw < p.plain.W && tw < 64) tw *= 2;
@@ -328,6 +370,10 @@ int launch(const gb_wgrad_params& p, cudaStream_t st) {
         gb_tma_activation_map(p.gathered, tw, th, &map_g, p.mul, p.gathered_c_valid))
       return 1;
   }
+  // bulk reduce-add epilogue (knob 12 = 4: per-thread red.global.add): the staged tile needs BN * 512 bytes of the ring
+  const int rows_pad = gb_cdiv(p.rows, BM) * BM;
+  const int bulk = tma && g_gb_knobs[12] != 4 && (size_t)BN * 512 <= (size_t)C::STAGES * C::STAGE_BYTES ? 1 : 0;
+  if (bulk && gb_tma_f32_matrix_map(p.dw, p.kpad, rows_pad, BM, &map_d)) return 1;
   const int nblk = tma ? divs.ntiles : gb_cdiv(Mq, BP);
   // two row tiles per CTA: knob 12 = 2 only.  Measured slower than one (42.5 us vs 37.7 us on the residual-block
   // layer at batch 8): the launch is bound by the MMA's shared-memory operand reads, which RT = 2 does not reduce,
@@ -351,11 +397,11 @@ int launch(const gb_wgrad_params& p, cudaStream_t st) {
   divs.f[2] = gb_make_fastdiv((uint32_t)p.plain.W);
   GB_CHECK(tma || p.gathered_c_valid == 0, "gb_conv_wgrad: gathered_c_valid (pixel-window views) needs the TMA path");
   if (rt2)
-    gb_klaunch(igemm_wgrad_kernel<256, true, 2>, grid, 256, WCfg<256, 2>::SMEM, st, p, divs, map_p, map_g, bps);
+    gb_klaunch(igemm_wgrad_kernel<256, true, 2>, grid, 256, WCfg<256, 2>::SMEM, st, p, divs, map_p, map_g, map_d, bps, bulk);
   else if (tma)
-    gb_klaunch(igemm_wgrad_kernel<BN, true>, grid, 256, C::SMEM, st, p, divs, map_p, map_g, bps);
+    gb_klaunch(igemm_wgrad_kernel<BN, true>, grid, 256, C::SMEM, st, p, divs, map_p, map_g, map_d, bps, bulk);
   else
-    gb_klaunch(igemm_wgrad_kernel<BN, false>, grid, 256, C::SMEM, st, p, divs, map_p, map_g, bps);
+    gb_klaunch(igemm_wgrad_kernel<BN, false>, grid, 256, C::SMEM, st, p, divs, map_p, map_g, map_d, bps, 0);
   g_gb_knobs[14] = rt2 ? 2 : (tma ? 1 : 0);  // read-back slot: which wgrad variant served the last call (tests)
   GB_LAUNCH_CHECK();
   return 0;

@@ -106,6 +106,7 @@ def main():
         ("per-tap, coalesced-store epilogue", {9: 1, 29: 3}),
         ("persistent (knob 16 = 3)", {9: 1, 16: 3}),
         ("persistent, 74 CTAs", {9: 1, 16: 3, 18: 74}),
+        ("wgrad per-thread red.global.add epilogue", {12: 4}),
     ]
     if args.layers:
         layers = [layers[int(i)] for i in args.layers.split(",")]
