@@ -1148,10 +1148,11 @@ int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st) {
   {
     const int esz = p.out_fp32 ? 4 : 2;
     const int inner = 128 / esz;
-    // default (measured, profiles/r02d_conv_microbench_epilogues_b8.txt): fp32 destinations (data gradients) through the
-    // staged tile + bulk store (50.1 -> 45.9 us on the residual-block layer), bf16 destinations keep the per-thread
-    // stores (their statistics from the staged tile cost more shared-memory atomics than the butterfly sums)
-    const int want = g_gb_knobs[29] == 0 ? (p.out_fp32 ? 2 : 1) : g_gb_knobs[29];
+    // default (measured: profiles/r02d_conv_microbench_epilogues_b8.txt, r02i_*): the staged tile + bulk store for both
+    // destination types -- fp32 data gradients 50.1 -> 45.9 us on the residual-block layer; bf16 forward outputs (their
+    // statistics summed from the staged tile through a partial-sum scratch) 56 -> 46 / 39 -> 35 / 50 -> 41 us on the
+    // stride-2 and transposed layers; whole step 352.9 -> 358.1 img/s
+    const int want = g_gb_knobs[29] == 0 ? 2 : g_gb_knobs[29];
     const bool ok = want >= 2 && bn >= 64 && p.out.pad == 0 && p.out.C % inner == 0 &&
                     ((uintptr_t)p.out.ptr % 16) == 0 && (p.out.sx * esz) % 16 == 0 && (p.out.sy * esz) % 16 == 0 &&
                     (p.out.sz * esz) % 16 == 0 && (p.out.sn * esz) % 16 == 0 && (p.out_fp32 || !p.accumulate);

@@ -165,7 +165,7 @@ class UpBlock(nn.Module):
         raw = layers.step_conv_any(tape, b, seq[0], want_stats=True)
         # torch.cat((up, skipx), 1) without a cat kernel: both halves are written into one buffer
         N, D, H, W, _ = raw.t.shape
-        xcat = layers.Buf(torch.empty((N, D, H, W, self.out_channels), dtype=torch.bfloat16, device=raw.t.device), 0,
+        xcat = layers.Buf(torch.empty((N, D, H, W, self.out_channels), dtype=raw.t.dtype, device=raw.t.device), 0,
                           self.out_channels, raw.is_3d)
         layers.step_norm_act(tape, raw, True, ACT_PRELU, 0.0, 0, seq[1].eps, prelu=seq[2], out=xcat.slice(0, half))
         layers.step_norm_act(tape, skip, False, ACT_NONE, 0.0, 0, 1e-5, out=xcat.slice(half, half))

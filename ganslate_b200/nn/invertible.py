@@ -107,9 +107,9 @@ def recompute_coupling(tape, x, fn, inverse, free_input):
         y2 = fwd(sub, x, fn)
         x_st.consumers = n_cons
         y2.st.grad = g
-        for step in reversed(sub.steps):
-            step()
-        sub.steps = []
+        steps, sub.steps = sub.steps, None
+        while steps:
+            steps.pop()()
 
     tape.steps.append(bwd)
     return y

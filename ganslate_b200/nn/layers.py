@@ -18,8 +18,11 @@ import torch
 from torch import nn
 from torch.nn.modules.utils import _triple
 
+import sys
+
 from .. import ops
 from .._cabi import ACT_LEAKY, ACT_NONE, ACT_PRELU, ACT_RELU, ACT_TANH
+from . import fp32_mode
 
 
 def _t3(v):
@@ -337,8 +340,15 @@ class Tape:
         self.param_grads[k] = g
 
     def backward(self):
-        for step in reversed(self.steps):
-            step()
+        if RELEASE_TAPE:
+            # pop as we go: a step's closure (and with it the activations only it still references) dies as soon as
+            # its gradient has been propagated, as autograd frees saved tensors node by node
+            steps, self.steps = self.steps, None
+            while steps:
+                steps.pop()()
+        else:
+            for step in reversed(self.steps):
+                step()
         self.unpack.flush()
         self._queued.clear()
 
@@ -386,6 +396,8 @@ def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0, want_stats=False, 
     accumulated by the convolution epilogue (Buf.stats) instead of a separate pass over the output.
     as_activation: the output feeds another convolution directly (SeparableConv3d: depthwise -> pointwise), so it
     is an activation buffer whose FP32 gradient the consumer accumulates and this step converts to the bf16 operand."""
+    if ops.FP32_MODE:
+        return fp32_mode.step_conv(sys.modules[__name__], tape, b, m, act, slope, want_stats, as_activation)
     op = m.conv_op()
     dev = b.t.device
     ops._require_cuda(b.t, "convolution input")
@@ -449,6 +461,9 @@ def step_norm_act(tape: Tape, x: Buf, norm: bool, act: int, slope: float, out_pa
 
     x: raw convolution output, or (norm=False) any activation Buf; out: optional existing Buf (channel slice of a
     concatenation buffer) to write into instead of a fresh allocation; prelu: nn.PReLU module for learnable slopes."""
+    if ops.FP32_MODE:
+        return fp32_mode.step_norm_act(sys.modules[__name__], tape, x, norm, act, slope, out_pad, eps, residual, prelu,
+                                       res_before_act, out_scale, out)
     dev = x.t.device
     ops._require_cuda(x.t, "normalisation input")
     if norm and not x.raw and (residual is not None and res_before_act):
@@ -515,6 +530,8 @@ def step_norm_act(tape: Tape, x: Buf, norm: bool, act: int, slope: float, out_pa
                                   dres_acc=True, dx_fp32_acc=True, out_scale=out_scale, need_dx=need_dx)
         if dprelu is not None:
             tape.add_param_grad(slopes, dprelu[:slopes.numel()].reshape(slopes.shape))
+        if out.full:
+            out.st.grad = None   # (a channel slice of a concatenation buffer shares its gradient with other producers)
 
     if tape is not None:
         tape.steps.append(bwd)
@@ -524,6 +541,8 @@ def step_norm_act(tape: Tape, x: Buf, norm: bool, act: int, slope: float, out_pa
 def step_replicate_pad(tape: Tape, b: Buf, pads) -> Buf:
     """ReplicationPad3d(b) as a new plain buffer (N, D+2pz, H+2py, W+2px, C); backward folds the FP32 gradient of the
     padded buffer onto `b`'s gradient (accumulated, like every other consumer of an activation buffer)."""
+    if ops.FP32_MODE:
+        return fp32_mode.step_replicate_pad(sys.modules[__name__], tape, b, pads)
     pz, py, px = pads
     if b.raw:
         raise NotImplementedError("replicate padding of a raw convolution output")
@@ -651,6 +670,29 @@ def run_sequence(tape: Tape, mods: Sequence[nn.Module], b: Buf, final_pad: int =
     return b
 
 
+# network-boundary layout conversions (fp32 validation mode: plain torch ops on fp32 buffers)
+def _to_cl(x, pad):
+    return fp32_mode.to_channels_last(x, pad) if ops.FP32_MODE else ops.to_channels_last(x, pad)
+
+
+def _from_cl(b, act):
+    if ops.FP32_MODE:
+        return fp32_mode.from_channels_last(b.t, b.channels, b.is_3d, act)
+    return ops.from_channels_last(b.t, b.channels, b.is_3d, act)
+
+
+def _from_cl_backward(dy, b, act):
+    if ops.FP32_MODE:
+        return fp32_mode.from_channels_last_backward(dy, b.t, b.channels, act)
+    return ops.from_channels_last_backward(dy, b.t.shape, b.channels, pre=b.t if act == ACT_TANH else None, fp32=not b.raw)
+
+
+def _to_cl_backward(b0, in_shape):
+    if ops.FP32_MODE:
+        return fp32_mode.to_channels_last_backward(b0.st.grad, b0.pad, in_shape)
+    return ops.to_channels_last_backward(b0.st.grad, b0.pad, in_shape)
+
+
 class NetworkFn(torch.autograd.Function):
     """One network = one autograd node. forward(x NC(D)HW fp32) -> NC(D)HW fp32."""
 
@@ -665,12 +707,12 @@ class NetworkFn(torch.autograd.Function):
         pad = first_pad(mods)
         ctx.arena_key = (id(mods[0]) if len(mods) else 0, tuple(x.shape), tuple(ctx.needs_input_grad))
         ops.arena_begin(("fwd",) + ctx.arena_key, x.device)
-        b0 = Buf(ops.to_channels_last(x, pad), pad, x.shape[1], x.dim() == 5)
+        b0 = Buf(_to_cl(x, pad), pad, x.shape[1], x.dim() == 5)
         b0.needs_grad_flag = bool(ctx.needs_input_grad[1])
         b = run_sequence(tape, mods, b0)
         if b.pad != 0:
             raise RuntimeError("cannot export a bordered buffer")
-        y = ops.from_channels_last(b.t, b.channels, b.is_3d, act)
+        y = _from_cl(b, act)
         ops.arena_end(("fwd",) + ctx.arena_key)
         ctx.tape, ctx.params, ctx.b0, ctx.b_last, ctx.act = tape, params, b0, b, act
         ctx.in_shape = tuple(x.shape)
@@ -682,12 +724,11 @@ class NetworkFn(torch.autograd.Function):
         tape, b0, b = ctx.tape, ctx.b0, ctx.b_last
         tape.param_grads = {}
         ops.arena_begin(("bwd",) + ctx.arena_key, dy.device)
-        b.st.grad = ops.from_channels_last_backward(dy, b.t.shape, b.channels,
-                                                    pre=b.t if ctx.act == ACT_TANH else None, fp32=not b.raw)
+        b.st.grad = _from_cl_backward(dy, b, ctx.act)
         tape.backward()
         dx = None
         if ctx.needs_input_grad[1] and b0.st.grad is not None:
-            dx = ops.to_channels_last_backward(b0.st.grad, b0.pad, ctx.in_shape)
+            dx = _to_cl_backward(b0, ctx.in_shape)
         b0.st.grad = None
         ops.arena_end(("bwd",) + ctx.arena_key)
         grads = [tape.param_grads.get(id(p)) for p in ctx.params]
@@ -707,12 +748,12 @@ class RunnerFn(torch.autograd.Function):
         tape = Tape(needs, ctx.needs_input_grad[2]) if record else None
         ctx.arena_key = (key, tuple(x.shape), tuple(ctx.needs_input_grad))
         ops.arena_begin(("run_fwd",) + ctx.arena_key, x.device)
-        b0 = Buf(ops.to_channels_last(x, 0), 0, x.shape[1], x.dim() == 5)
+        b0 = Buf(_to_cl(x, 0), 0, x.shape[1], x.dim() == 5)
         b0.needs_grad_flag = bool(ctx.needs_input_grad[2])
         b, act = runner(tape, b0)
         if b.pad != 0 or not b.full:
             raise RuntimeError("cannot export a bordered / sliced buffer")
-        y = ops.from_channels_last(b.t, b.channels, b.is_3d, act)
+        y = _from_cl(b, act)
         ops.arena_end(("run_fwd",) + ctx.arena_key)
         ctx.tape, ctx.params, ctx.b0, ctx.b_last, ctx.act = tape, params, b0, b, act
         ctx.in_shape = tuple(x.shape)
@@ -724,12 +765,11 @@ class RunnerFn(torch.autograd.Function):
         tape, b0, b = ctx.tape, ctx.b0, ctx.b_last
         tape.param_grads = {}
         ops.arena_begin(("run_bwd",) + ctx.arena_key, dy.device)
-        b.st.grad = ops.from_channels_last_backward(dy, b.t.shape, b.channels,
-                                                    pre=b.t if ctx.act == ACT_TANH else None, fp32=not b.raw)
+        b.st.grad = _from_cl_backward(dy, b, ctx.act)
         tape.backward()
         dx = None
         if ctx.needs_input_grad[2] and b0.st.grad is not None:
-            dx = ops.to_channels_last_backward(b0.st.grad, b0.pad, ctx.in_shape)
+            dx = _to_cl_backward(b0, ctx.in_shape)
         b0.st.grad = None
         ops.arena_end(("run_bwd",) + ctx.arena_key)
         grads = [tape.param_grads.get(id(p)) for p in ctx.params]
@@ -744,7 +784,7 @@ def step_channel_repeat(tape: Tape, b: Buf, n_repeats: int) -> Buf:
     c = b.channels
     out_c = c * n_repeats
     src = b.t[..., b.c0:b.c0 + c]
-    t = torch.zeros(b.t.shape[:-1] + (ops.pad8(out_c),), dtype=torch.bfloat16, device=b.t.device)
+    t = torch.zeros(b.t.shape[:-1] + (ops.pad8(out_c),), dtype=b.t.dtype, device=b.t.device)
     t[..., :out_c] = src.repeat(1, 1, 1, 1, n_repeats)
     out = Buf(t, 0, out_c, b.is_3d)
     b.st.consumers += 1
@@ -764,7 +804,7 @@ def step_channel_repeat(tape: Tape, b: Buf, n_repeats: int) -> Buf:
 def new_like(b: Buf, channels: int) -> Buf:
     """Fresh activation buffer with the spatial shape of `b` and `channels` channels (concatenation target)."""
     N, D, Hb, Wb, _ = b.t.shape
-    t = torch.empty((N, D, Hb, Wb, ops.pad8(channels)), dtype=torch.bfloat16, device=b.t.device)
+    t = torch.empty((N, D, Hb, Wb, ops.pad8(channels)), dtype=b.t.dtype, device=b.t.device)
     return Buf(t, b.pad, channels, b.is_3d)
 
 
@@ -783,6 +823,8 @@ class EncoderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mods, taps, x, *params):
+        if ops.FP32_MODE:
+            raise NotImplementedError("fp32 validation mode does not cover feature taps (CUT)")
         needs = {id(p): ctx.needs_input_grad[3 + k] for k, p in enumerate(params)}
         record = any(ctx.needs_input_grad[2:])
         tape = Tape(needs, ctx.needs_input_grad[2]) if record else None

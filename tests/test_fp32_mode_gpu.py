@@ -1,0 +1,118 @@
+"""fp32 validation mode on the GPU (ganslate_b200/nn/fp32_mode.py, ops.FP32_MODE): north_star's "tf32-off fp32" bound.
+
+Every convolution runs on the tcgen05 / TMA kernels with 3-way bf16-split operands (six products, fp32 accumulation in
+TMEM and in the fp32 epilogue), activations and gradients are fp32, norm / activation steps are fp32 torch ops.
+Stated tolerance vs the fp32 CPU oracle: max |ours - ref| / max |ref| <= 1e-4 on outputs, losses and every
+per-parameter gradient (biases in front of an InstanceNorm -- mathematically zero -- absolute: 1e-4 x the network's
+largest weight gradient).  Measured values are written to gpurun_out/fp32_mode.json."""
+import json
+import os
+import random
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-4
+
+
+@pytest.fixture()
+def fp32_mode():
+    from ganslate_b200 import ops
+    old = ops.FP32_MODE
+    ops.FP32_MODE = True
+    yield
+    ops.FP32_MODE = old
+
+
+def _record(name, **kw):
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        path = os.path.join(out, "fp32_mode.json")
+        data = json.load(open(path)) if os.path.exists(path) else {}
+        data[name] = kw
+        json.dump(data, open(path, "w"), indent=1)
+    print(name, kw)
+
+
+def _param_errors(ours_nets, ref_nets):
+    from parity_util import max_rel
+    worst, worst_name, bias_abs = 0.0, None, 0.0
+    for n in ref_nets:
+        po, pg = dict(ref_nets[n].named_parameters()), dict(ours_nets[n].named_parameters())
+        wmax = max(p.grad.abs().max().item() for p in po.values() if p.grad is not None and p.dim() > 1)
+        for k, p in po.items():
+            if p.grad is None:
+                continue
+            if p.dim() > 1 or p.grad.abs().max().item() > 1e-3 * wmax:
+                e = max_rel(pg[k].grad, p.grad)
+                if e > worst:
+                    worst, worst_name = e, f"{n}.{k}"
+            else:
+                bias_abs = max(bias_abs, (pg[k].grad.cpu() - p.grad).abs().max().item() / wmax)
+    return worst, worst_name, bias_abs
+
+
+@pytest.mark.parametrize("size,blocks", [(64, 3), (128, 9)])
+def test_cyclegan_iteration_fp32_mode_vs_fp32_oracle(fp32_mode, size, blocks):
+    from oracle import torch_oracle as O
+    from parity_util import build_pair, max_rel
+    random.seed(0)
+    oracle, ours = build_pair(size, 1, blocks)
+    a, b = O.synthetic_batch(1, 3, size, seed=1)
+    lo = oracle.optimize_parameters(a, b, step_optimizers=False)
+    for o in ours.optimizers.values():
+        o.step = lambda *a, **k: None
+    ours.set_input({"A": a, "B": b})
+    ours.optimize_parameters()
+    torch.cuda.synchronize()
+    lrel = {k: abs(float(ours.losses[k].detach()) - v) / abs(v) for k, v in lo.items()}
+    vis = {k: max_rel(ours.visuals[k], oracle.visuals[k]) for k in ("fake_B", "rec_A", "fake_A", "rec_B")}
+    worst, name, bias_abs = _param_errors(ours.networks, oracle.networks)
+    _record(f"cyclegan_{size}px_{blocks}blk", loss_rel_max=max(lrel.values()), visuals_max_rel=max(vis.values()),
+            param_grad_max_rel=worst, worst_param=name, zero_bias_abs_over_wmax=bias_abs)
+    assert max(lrel.values()) <= TOL, lrel
+    assert max(vis.values()) <= TOL, vis
+    assert worst <= TOL, (name, worst)
+    assert bias_abs <= TOL, bias_abs
+
+
+def test_networks_fp32_mode_vs_fp32_oracle(fp32_mode):
+    """Unet2D, Vnet3D (both directions) and PatchGAN3D forward + backward."""
+    from ganslate_b200.nn.discriminators import PatchGAN3D
+    from ganslate_b200.nn.generators import Unet2D, Vnet3D
+    from oracle import torch_oracle as O
+    from oracle import torch_oracle3d as O3
+    from parity_util import max_rel
+    torch.manual_seed(0)
+    cases = []
+    refu, oursu = O.init_weights(O.OracleUnet2D(3, 3, 6, ngf=32)), Unet2D(3, 3, 6, "instance", ngf=32)
+    cases.append(("unet2d", refu, oursu, torch.rand(2, 3, 128, 64) * 2 - 1, {}))
+    small = dict(first_layer_channels=8, down_blocks=(1, 2), up_blocks=(2, 1))
+    refv, oursv = O.init_weights(O3.OracleVnet3D(1, 1, use_inverse=True, **small)), Vnet3D(1, 1, "instance", use_memory_saving=False, use_inverse=True, **small)
+    xv, _ = O3.synthetic_volume(1, 1, 16, 32, seed=3)
+    cases.append(("vnet3d", refv, oursv, xv, dict(inverse=False)))
+    cases.append(("vnet3d_inverse", refv, oursv, xv, dict(inverse=True)))
+    ref3, ours3 = O.init_weights(O3.OraclePatchGAN3D(1, 16, 2, (4, 4, 4))), PatchGAN3D(1, 16, 2, (4, 4, 4), "instance")
+    x3, _ = O3.synthetic_volume(2, 1, 16, 32, seed=5)
+    cases.append(("patchgan3d", ref3, ours3, x3, {}))
+    rec = {}
+    for name, ref, ours, x, kw in cases:
+        ours.load_state_dict(ref.state_dict())
+        ours = ours.cuda()
+        xr, xo = x.clone().requires_grad_(True), x.clone().cuda().requires_grad_(True)
+        yr, yo = ref(xr, **kw), ours(xo, **kw)
+        g = torch.randn(yr.shape, generator=torch.Generator().manual_seed(7))
+        ref.zero_grad()
+        ours.zero_grad()
+        yr.backward(g)
+        yo.backward(g.cuda())
+        torch.cuda.synchronize()
+        worst, pname, bias_abs = _param_errors({"n": ours}, {"n": ref})
+        rec[name] = dict(out=max_rel(yo, yr), dx=max_rel(xo.grad, xr.grad), param_grad_max_rel=worst, worst_param=pname,
+                         zero_bias_abs_over_wmax=bias_abs)
+        assert rec[name]["out"] <= TOL and rec[name]["dx"] <= TOL and worst <= TOL and bias_abs <= TOL, (name, rec[name])
+    _record("networks", **rec)

@@ -660,3 +660,66 @@ def test_teacher_forced_parity_harness_on_the_fake_backend(monkeypatch):
     x3, _ = O3.synthetic_volume(1, 1, 16, 16, seed=5)
     s = summarize(forced_network_parity(ours3, ref3, x3))
     assert s["fwd_max_rel"] <= 1e-2 and s["bwd_max_rel"] <= 1e-2 and s["wgrad_max_rel"] <= 1e-4, s
+
+
+def _fp32_compare(ref, ours, x, call=None, tol=2e-5):
+    call = call or (lambda m, t: m(t))
+    xr, xo = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    yr, yo = call(ref, xr), call(ours, xo)
+    from parity_util import max_rel
+    assert yo.shape == yr.shape and max_rel(yo, yr) <= tol, max_rel(yo, yr)
+    g = torch.randn(yr.shape, generator=torch.Generator().manual_seed(9))
+    ref.zero_grad()
+    ours.zero_grad()
+    yr.backward(g)
+    yo.backward(g)
+    assert max_rel(xo.grad, xr.grad) <= tol, max_rel(xo.grad, xr.grad)
+    po = dict(ours.named_parameters())
+    wmax = max(p.grad.abs().max().item() for k, p in ref.named_parameters() if p.grad is not None and p.dim() > 1)
+    for k, p in ref.named_parameters():
+        if p.grad is None:
+            continue
+        if p.dim() > 1 or p.grad.abs().max() > 1e-3 * wmax:
+            assert max_rel(po[k].grad, p.grad) <= tol, (k, max_rel(po[k].grad, p.grad))
+        else:   # bias in front of an InstanceNorm: mathematically zero
+            assert (po[k].grad - p.grad).abs().max().item() <= 1e-4 * wmax, k
+
+
+def test_fp32_validation_mode_matches_the_fp32_oracle_to_1e_5(monkeypatch):
+    """ops.FP32_MODE (nn/fp32_mode.py): 3-way bf16-split operands through the same conv entry points (six launches per
+    product, fp32 accumulation), fp32 buffers, fp32 norm / activation steps.  Through the fake backend the whole
+    forward + backward of every network family agrees with the fp32 oracle to 2e-5 max-relative -- three orders of
+    magnitude below the bf16 path, so one switch separates a kernel / wiring bug from rounding noise."""
+    lib = fake_cabi.install(monkeypatch)
+    from ganslate_b200 import ops
+    from ganslate_b200.nn.discriminators import PatchGAN2D, PatchGAN3D
+    from ganslate_b200.nn.generators import Resnet2D, Unet2D, Vnet3D
+    from oracle import torch_oracle as O
+    from oracle import torch_oracle3d as O3
+    monkeypatch.setattr(ops, "FP32_MODE", True)
+    torch.manual_seed(0)
+    ref = O.init_weights(O.OracleResnet2D(3, 3, n_residual_blocks=2))
+    ours = Resnet2D(3, 3, "instance", n_residual_blocks=2)
+    _load(ours, ref)
+    n0 = lib.calls.get("gb_conv_data", 0)
+    _fp32_compare(ref, ours, torch.rand(1, 3, 32, 32) * 2 - 1)
+    assert lib.calls["gb_conv_data"] - n0 >= 6 * 2 * 9      # six split products per convolution and direction
+    refd = O.init_weights(O.OraclePatchGAN2D(3, 16, 2))
+    oursd = PatchGAN2D(3, 16, 2, (4, 4), "instance")
+    _load(oursd, refd)
+    _fp32_compare(refd, oursd, torch.rand(2, 3, 32, 32) * 2 - 1)
+    refu = O.init_weights(O.OracleUnet2D(3, 2, 5, ngf=8))
+    oursu = Unet2D(3, 2, 5, "instance", ngf=8)
+    _load(oursu, refu)
+    _fp32_compare(refu, oursu, torch.rand(1, 3, 32, 64) * 2 - 1)
+    refv = O.init_weights(O3.OracleVnet3D(1, 1, use_inverse=True, **SMALL))
+    oursv = Vnet3D(1, 1, "instance", use_memory_saving=False, use_inverse=True, **SMALL)
+    _load(oursv, refv)
+    xv, _ = O3.synthetic_volume(1, 1, 8, 16, seed=3)
+    for inverse in (False, True):
+        _fp32_compare(refv, oursv, xv, call=lambda m, t: m(t, inverse=inverse), tol=5e-5)
+    ref3 = O.init_weights(O3.OraclePatchGAN3D(1, 16, 2, (4, 4, 4)))
+    ours3 = PatchGAN3D(1, 16, 2, (4, 4, 4), "instance")
+    _load(ours3, ref3)
+    x3, _ = O3.synthetic_volume(1, 1, 16, 16, seed=5)
+    _fp32_compare(ref3, ours3, x3)
