@@ -56,6 +56,8 @@ def parse():
                          "(train.input_prefetch) and the loss of step i read after step i+1 was enqueued")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--multi-stream", action="store_true",
+                    help="opt-in: the two cycle chains / the two discriminators on two CUDA streams (train.multi_stream)")
     ap.add_argument("--no-batch1", action="store_true", help="skip the extra batch-1 leg of the headline workload")
     ap.add_argument("--roofline-all-ranks", action="store_true", help="N>1: profile the per-kernel roofline too")
     args = ap.parse_args()
@@ -205,7 +207,8 @@ def run_b200(args):
     def measure(batch, with_clocks):
         """Build the workload at `batch` per GPU and time args.steps resident steps, then args.steps e2e steps."""
         conf = getattr(presets, preset)(batch_size=batch, cuda_graph=not args.no_graph,
-                                        **({"input_prefetch": True} if args.e2e_pipeline else {}))
+                                        **({"input_prefetch": True} if args.e2e_pipeline else {}),
+                                        **({"multi_stream": True} if args.multi_stream else {}))
         model = build_gan(conf)
         # synthetic inputs U(-1, 1) (images are normalised to [-1, 1] in the reference); each rank draws its own shard
         gen = torch.Generator(device="cpu").manual_seed(1 + rank)

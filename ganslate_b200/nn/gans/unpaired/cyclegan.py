@@ -12,6 +12,10 @@ from ganslate_b200.nn.losses.adversarial_loss import AdversarialLoss
 from ganslate_b200.nn.losses.cyclegan_losses import CycleGANLosses
 
 
+def cut_unwrap(net):
+    return net.module if hasattr(net, 'module') and isinstance(net, torch.nn.parallel.DistributedDataParallel) else net
+
+
 @dataclass
 class OptimizerConfig(configs.base.BaseOptimizerConfig):
     lambda_AB: float = 10.0
@@ -112,23 +116,83 @@ class CycleGAN(BaseGAN):
         discriminators = [self.networks['D_B'], self.networks['D_A']]
         self.set_requires_grad(discriminators, True)
         self.optimizers['D'].zero_grad(set_to_none=True)
-        self.backward_D('D_B', fake_B)
-        self.metrics.update(self.training_metrics.compute_metrics_D('D_B', self.pred_real, self.pred_fake))
-        self.backward_D('D_A', fake_A)
-        self.metrics.update(self.training_metrics.compute_metrics_D('D_A', self.pred_real, self.pred_fake))
+        if self._streams() is not None:
+            self._prepack(['D_B', 'D_A'])
+
+            def one(name, fake):
+                self.backward_D(name, fake)
+                return self.training_metrics.compute_metrics_D(name, self.pred_real, self.pred_fake)
+
+            m_B, m_A = self._fork_join(lambda: one('D_B', fake_B), lambda: one('D_A', fake_A))
+            self.metrics.update(m_B)
+            self.metrics.update(m_A)
+        else:
+            self.backward_D('D_B', fake_B)
+            self.metrics.update(self.training_metrics.compute_metrics_D('D_B', self.pred_real, self.pred_fake))
+            self.backward_D('D_A', fake_A)
+            self.metrics.update(self.training_metrics.compute_metrics_D('D_A', self.pred_real, self.pred_fake))
         if step:
             self.optimizers['D'].step()
 
+    # ---- two-stream execution (train.multi_stream, opt-in) ---------------------------------------------------
+    # The A -> B -> A and B -> A -> B cycles are independent until the losses are summed, and so are the two
+    # discriminators.  With `train.multi_stream` each chain is ENQUEUED on its own CUDA stream (forked from and
+    # joined to the current stream, so the CUDA-graph capture records two parallel branches): a kernel of one chain
+    # fills the SMs the other chain's kernel leaves idle (second wave of a 256-tile convolution, latency-bound
+    # InstanceNorm launches, everything at batch 1).  Autograd replays every node's backward on the stream its
+    # forward ran on, so the backward pass forks the same way.  Every network's packed weights are refreshed on the
+    # parent stream first (a chain must not launch the pack kernel the other chain depends on).
+    def _streams(self):
+        if not bool(self.conf.train.get("multi_stream", False)) or self.device.type != "cuda":
+            return None
+        st = self.__dict__.get("_chain_streams")
+        if st is None:
+            st = self.__dict__["_chain_streams"] = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        return st
+
+    def _prepack(self, names):
+        from ganslate_b200 import ops
+        for n in names:
+            ops.ensure_packed(cut_unwrap(self.networks[n]))
+
+    def _fork_join(self, fn1, fn2):
+        """Run fn1 and fn2 on the two chain streams (or back to back without `train.multi_stream`)."""
+        st = self._streams()
+        if st is None:
+            return fn1(), fn2()
+        cur = torch.cuda.current_stream()
+        st[0].wait_stream(cur)
+        st[1].wait_stream(cur)
+        with torch.cuda.stream(st[0]):
+            r1 = fn1()
+        with torch.cuda.stream(st[1]):
+            r2 = fn2()
+        cur.wait_stream(st[0])
+        cur.wait_stream(st[1])
+        for r in (r1, r2):
+            for t in (r if isinstance(r, (tuple, list)) else (r,)):
+                if torch.is_tensor(t):
+                    t.record_stream(cur)
+        return r1, r2
+
     def forward(self):
         real_A, real_B = self.visuals['real_A'], self.visuals['real_B']
-        fake_B = self.networks['G_AB'](real_A)
-        rec_A = self.networks['G_BA'](fake_B)
-        fake_A = self.networks['G_BA'](real_B)
-        rec_B = self.networks['G_AB'](fake_A)
+        G_AB, G_BA = self.networks['G_AB'], self.networks['G_BA']
+        if self._streams() is not None:
+            self._prepack(['G_AB', 'G_BA'])
+
+        def chain_A():
+            fake_B = G_AB(real_A)
+            return fake_B, G_BA(fake_B)
+
+        def chain_B():
+            fake_A = G_BA(real_B)
+            return fake_A, G_AB(fake_A)
+
+        (fake_B, rec_A), (fake_A, rec_B) = self._fork_join(chain_A, chain_B)
         idt_B, idt_A = None, None
         if self.criterion_G.is_using_identity():
-            idt_B = self.networks['G_AB'](real_B)
-            idt_A = self.networks['G_BA'](real_A)
+            idt_B, idt_A = self._fork_join(lambda: G_AB(real_B), lambda: G_BA(real_A))
         self.visuals.update({'fake_B': fake_B, 'rec_A': rec_A, 'idt_A': idt_A, 'fake_A': fake_A, 'rec_B': rec_B,
                              'idt_B': idt_B})
 
@@ -150,8 +214,10 @@ class CycleGAN(BaseGAN):
         self.backward(loss=self.losses[discriminator], optimizer=self.optimizers['D'], loss_id=2)
 
     def backward_G(self):
-        pred_B = self.networks['D_B'](self.visuals['fake_B'])
-        pred_A = self.networks['D_A'](self.visuals['fake_A'])
+        if self._streams() is not None:
+            self._prepack(['D_B', 'D_A'])
+        pred_B, pred_A = self._fork_join(lambda: self.networks['D_B'](self.visuals['fake_B']),
+                                         lambda: self.networks['D_A'](self.visuals['fake_A']))
         self.losses['G_AB'] = self.criterion_adv(pred_B, target_is_real=True)
         self.losses['G_BA'] = self.criterion_adv(pred_A, target_is_real=True)
         losses_G = self.criterion_G(self.visuals)

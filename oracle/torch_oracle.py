@@ -333,11 +333,18 @@ def synthetic_batch(batch, channels=3, size=256, seed=1, device="cpu", width=Non
 # the same CPU restatement can be run with round-to-bf16 inserted at exactly the points where the B200 path
 # rounds (DESIGN.md "Precision"): conv operands, conv outputs, fused norm/activation outputs, and the gradients
 # wrt conv outputs.  Everything else (accumulation, statistics, losses, weight gradients, Adam) stays fp32.
+# ROUND_BF16 = False turns every rounding point of forward_bf16_points into the identity: the same walk (and the same
+# TRACE points) in plain fp32 -- the oracle of the fp32 validation mode's teacher-forced test.
+ROUND_BF16 = True
+
+
 class _RoundSTE(torch.autograd.Function):
     """forward: round to bf16; backward: identity."""
 
     @staticmethod
     def forward(ctx, x):
+        if not ROUND_BF16:
+            return x.view_as(x)
         return x.to(torch.bfloat16).to(torch.float32)
 
     @staticmethod
@@ -354,6 +361,8 @@ class _GradRound(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        if not ROUND_BF16:
+            return g
         return g.to(torch.bfloat16).to(torch.float32)
 
 

@@ -73,9 +73,10 @@ def _fold(g, p):
 class Forcer:
     """Context manager that patches layers.step_conv / step_norm_act for ONE network evaluation."""
 
-    def __init__(self, trace, force=True):
+    def __init__(self, trace, force=True, fp32=False):
         self.trace = trace          # [(kind, live oracle tensor)] from O.TRACE with TRACE_LIVE
         self.force = force
+        self.fp32 = fp32            # fp32 validation mode: fp32 buffers, no bf16 rounding of the reference gradients
         self.i = 0
         self.fwd, self.bwd = [], []  # (index, kind, shape, rel_l2, max_rel, outlier fraction)
 
@@ -105,7 +106,7 @@ class Forcer:
             if p:
                 r = F.pad(r, (p, p, p, p), mode="reflect")
             r5 = _from_ref_layout(r, out.is_3d).to(dev)
-            out.st.t[..., out.c0:out.c0 + out.channels] = r5.to(torch.bfloat16)
+            out.st.t[..., out.c0:out.c0 + out.channels] = r5.to(out.st.t.dtype)
             if out.stats is not None:
                 v = ref.detach().double()
                 dims = tuple(range(2, v.dim()))
@@ -119,7 +120,7 @@ class Forcer:
                 g = out.st.grad
                 if g is not None and ref.grad is not None:
                     rg = ref.grad.detach()
-                    if kind == "raw":
+                    if kind == "raw" and not self.fp32:
                         rg = rg.to(torch.bfloat16).float()       # the oracle rounds d_raw when it propagates it
                     p = out.st.pad
                     mine = _to_ref_layout(_fold(g.float(), p)[..., out.c0:out.c0 + out.channels], out.is_3d)
@@ -134,10 +135,12 @@ class Forcer:
         return out
 
 
-def forced_network_parity(ours, ref, x, dy=None, force=True):
+def forced_network_parity(ours, ref, x, dy=None, force=True, fp32=False):
     """Evaluate `ours` (cuda / fake backend) and `ref` (oracle module, same weights) on x with teacher forcing.
+    fp32: the fp32 validation mode (ops.FP32_MODE must be on) against the oracle walked WITHOUT rounding.
     Returns dict(fwd=[...], bwd=[...], out=(rel_l2, max_rel), dx=..., params={name: (rel_l2, max_rel, |ref|max)})."""
     O.TRACE, O.TRACE_LIVE = [], True
+    O.ROUND_BF16 = not fp32
     try:
         xr = x.clone().requires_grad_(True)
         yr = O.forward_bf16_points(ref, xr)
@@ -148,10 +151,13 @@ def forced_network_parity(ours, ref, x, dy=None, force=True):
         g = torch.Generator().manual_seed(1234)
         dy = torch.randn(yr.shape, generator=g)
     ref.zero_grad()
-    yr.backward(dy)
+    try:
+        yr.backward(dy)
+    finally:
+        O.ROUND_BF16 = True
     dev = next(ours.parameters()).device
     xo = x.clone().to(dev).requires_grad_(True)
-    with Forcer(trace, force) as f:
+    with Forcer(trace, force, fp32) as f:
         yo = ours(xo)
         assert f.i == len(trace), (f.i, len(trace))
         ours.zero_grad()

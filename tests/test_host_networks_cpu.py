@@ -723,3 +723,7 @@ def test_fp32_validation_mode_matches_the_fp32_oracle_to_1e_5(monkeypatch):
     _load(ours3, ref3)
     x3, _ = O3.synthetic_volume(1, 1, 16, 16, seed=5)
     _fp32_compare(ref3, ours3, x3)
+    # and teacher-forced against the oracle walked without rounding (tests/test_fp32_mode_gpu.py does this on the GPU)
+    from forced_parity import forced_network_parity, summarize
+    sm = summarize(forced_network_parity(ours, ref, torch.rand(1, 3, 32, 32) * 2 - 1, fp32=True))
+    assert sm["fwd_max_rel"] <= 2e-5 and sm["bwd_max_rel"] <= 2e-5 and sm["wgrad_max_rel"] <= 2e-5, sm
