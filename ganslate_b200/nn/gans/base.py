@@ -236,6 +236,49 @@ class BaseGAN(ABC):
             self.graph_launches_per_step += _cabi.lib().gb_launch_count() - n0
         g.replay()
 
+    # ---- two-stream execution (train.multi_stream, opt-in; GB_MULTI_STREAM=1 sets the default) -----------------
+    # The A -> B -> A and B -> A -> B cycles are independent until the losses are summed, and so are the two
+    # discriminators.  With `train.multi_stream` each chain is ENQUEUED on its own CUDA stream (forked from and
+    # joined to the current stream, so the CUDA-graph capture records two parallel branches): a kernel of one chain
+    # fills the SMs the other chain's kernel leaves idle (second wave of a 256-tile convolution, latency-bound
+    # InstanceNorm launches, everything at batch 1).  Autograd replays every node's backward on the stream its
+    # forward ran on, so the backward pass forks the same way.  Every network's packed weights are refreshed on the
+    # parent stream first (a chain must not launch the pack kernel the other chain depends on).
+    def _streams(self):
+        default = os.environ.get("GB_MULTI_STREAM", "0") == "1"
+        if not bool(self.conf.train.get("multi_stream", default)) or self.device.type != "cuda":
+            return None
+        st = self.__dict__.get("_chain_streams")
+        if st is None:
+            st = self.__dict__["_chain_streams"] = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        return st
+
+    def _prepack(self, names):
+        from ganslate_b200 import ops
+        for n in names:
+            net = self.networks[n]
+            ops.ensure_packed(net.module if isinstance(net, DistributedDataParallel) else net)
+
+    def _fork_join(self, fn1, fn2):
+        """Run fn1 and fn2 on the two chain streams (or back to back without `train.multi_stream`)."""
+        st = self._streams()
+        if st is None:
+            return fn1(), fn2()
+        cur = torch.cuda.current_stream()
+        st[0].wait_stream(cur)
+        st[1].wait_stream(cur)
+        with torch.cuda.stream(st[0]):
+            r1 = fn1()
+        with torch.cuda.stream(st[1]):
+            r2 = fn2()
+        cur.wait_stream(st[0])
+        cur.wait_stream(st[1])
+        for r in (r1, r2):
+            for t in (r if isinstance(r, (tuple, list)) else (r,)):
+                if torch.is_tensor(t):
+                    t.record_stream(cur)
+        return r1, r2
+
     def backward(self, loss, optimizer=None, retain_graph=False, loss_id=0):
         loss.backward(retain_graph=retain_graph)
 
