@@ -56,13 +56,17 @@ def parse():
                          "(train.input_prefetch) and the loss of step i read after step i+1 was enqueued")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
-    ap.add_argument("--multi-stream", action="store_true",
-                    help="opt-in: the two cycle chains / the two discriminators on two CUDA streams (train.multi_stream)")
+    ap.add_argument("--multi-stream", action="store_true", default=None,
+                    help="the two cycle chains / the two discriminators on two CUDA streams (train.multi_stream); default "
+                         "for the CycleGAN workloads (measured r02k: 352 -> 376 img/s at batch 8, 108 -> 124 at batch 1)")
+    ap.add_argument("--single-stream", action="store_true", help="switch train.multi_stream off")
     ap.add_argument("--no-batch1", action="store_true", help="skip the extra batch-1 leg of the headline workload")
     ap.add_argument("--roofline-all-ranks", action="store_true", help="N>1: profile the per-kernel roofline too")
     args = ap.parse_args()
     if args.workload != "cyclegan2d" and "--batch" not in sys.argv and "GB_BENCH_BATCH" not in os.environ:
         args.batch = WORKLOADS[args.workload][2]
+    if args.multi_stream is None:
+        args.multi_stream = args.workload in ("cyclegan2d", "cyclegan3d") and not args.single_stream
     return args
 
 
@@ -75,7 +79,8 @@ def workload_config(args, world):
                 "l2_policy": "2 x 126 MB flush buffer written between timed steps"}
     return {
         "workload": f"CycleGAN Resnet2D-9blk + PatchGAN2D(n_layers 3), synthetic 3x{args.size}x{args.size}, "
-                    f"batch {args.batch}/GPU, lambda 10, lsgan, Adam(2e-4, 0.5/0.999)",
+                    f"batch {args.batch}/GPU, lambda 10, lsgan, Adam(2e-4, 0.5/0.999)"
+                    + (", the two cycle chains on two CUDA streams" if args.multi_stream else ""),
         "global_batch": args.batch * world, "image": [3, args.size, args.size],
         "parallelism": f"dp{world}", "l2_policy": "activations+gradients per step exceed nothing cached across "
                                                   "steps: 2 x 126 MB flush buffer written between timed steps",

@@ -4,7 +4,7 @@ from ganslate_b200.configs.utils import init_config
 
 def cyclegan_resnet2d(batch_size=1, lambda_identity=0.0, n_residual_blocks=9, **train_overrides):
     """projects/horse2zebra/experiments/default.yaml:28-49 -- Resnet2D-9 + PatchGAN2D(n_layers 3), lambda 10,
-    proportion_ssim 0, lsgan, lr 2e-4."""
+    proportion_ssim 0, lsgan, lr 2e-4.  (`multi_stream=True` as a train override: the two cycle chains on two streams.)"""
     conf = {
         "mode": "train",
         "train": {

@@ -230,12 +230,24 @@ def test_two_stream_step_equals_single_stream_step():
         m.set_input({"A": a, "B": b})
         m.optimize_parameters()
         torch.cuda.synchronize()
-        return {k: float(v.detach()) for k, v in m.losses.items() if v is not None}
+        out = {k: float(v.detach()) for k, v in m.losses.items() if v is not None}
+        out["_vis"] = {k: m.visuals[k].detach().clone() for k in ("fake_B", "fake_A", "rec_A", "rec_B")}
+        return out
+
+    from parity_util import rel_l2
+    # bounds: two runs of the SAME mode differ by the reordering of the fp32 statistics atomics put through bf16
+    # (test_cyclegan_step_vs_matched_oracle_noise_floor: images 1e-2 / 4e-2, losses up to 1e-2 on this 2-block network)
+    LOSS, FAKE, REC = 2e-2, 2e-2, 8e-2
+
+    def close(tag, ref, got):
+        for k, v in ref.items():
+            if k != "_vis":
+                assert abs(got[k] - v) <= LOSS * abs(v) + 1e-4, (tag, k, v, got[k])
+        for k, v in ref["_vis"].items():
+            assert rel_l2(got["_vis"][k], v) <= (FAKE if k.startswith("fake") else REC), (tag, k, rel_l2(got["_vis"][k], v))
 
     # eager: first iteration from the common initial state
-    ls, lt = one_step_from(None), one_step_from(None, multi_stream=True)
-    for k, v in ls.items():
-        assert abs(lt[k] - v) <= 5e-3 * abs(v) + 1e-4, ("eager", k, v, lt[k])
+    close("eager", one_step_from(None, multi_stream=False), one_step_from(None, multi_stream=True))
     # graph replay with two captured branches: replay one iteration from a snapshot, compare with a single-stream eager
     # iteration from the same snapshot
     torch.manual_seed(0)
@@ -251,6 +263,5 @@ def test_two_stream_step_equals_single_stream_step():
     mg.optimize_parameters()
     torch.cuda.synchronize()
     lg = {k: float(v.detach()) for k, v in mg.losses.items() if v is not None}
-    le = one_step_from(state)
-    for k, v in le.items():
-        assert abs(lg[k] - v) <= 5e-3 * abs(v) + 1e-4, ("graph", k, v, lg[k])
+    lg["_vis"] = {k: mg.visuals[k].detach().clone() for k in ("fake_B", "fake_A", "rec_A", "rec_B")}
+    close("graph", one_step_from(state, multi_stream=False), lg)

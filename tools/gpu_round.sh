@@ -98,7 +98,7 @@ benchref)
   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 --batch $B > $out/bench_ref_b$B.json 2>> $out/bench_b$B.err; cat $out/bench_ref_b$B.json ;;
 launches)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file $out/launches_b$B.csv \
-     python bench.py --batch $B --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-roofline > $out/launches_run.log 2>&1
+     python bench.py --batch $B --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-roofline --no-batch1 --single-stream > $out/launches_run.log 2>&1
   python tools/launch_summary.py $out/launches_b$B.csv 5 --md > $out/launch_summary_b$B.md 2>&1; head -42 $out/launch_summary_b$B.md ;;
 full)
   # FULLSPECS="regex:skip:count ..." -- one ncu --set full capture per spec (kept small: reports come home)
@@ -108,7 +108,7 @@ full)
     rx=${spec%%:*}; rest=${spec#*:}; sk=${rest%%:*}; ct=${rest#*:}
     rep=$out/full${i}_b$B
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$rx" --launch-skip $sk -c $ct -o $rep -f \
-       python bench.py --batch $B --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-roofline > $out/full_run.log 2>&1
+       python bench.py --batch $B --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-roofline --no-batch1 --single-stream > $out/full_run.log 2>&1
     python tools/ncu_summary.py $rep.ncu-rep > $rep.md 2>&1
     sz=$(stat -c %s $rep.ncu-rep 2>/dev/null || echo 0)
     if [ "$sz" -gt 30000000 ]; then rm -f $rep.ncu-rep; echo "ncu-rep too large ($sz), removed" ; fi
