@@ -168,8 +168,12 @@ def test_oracle_losses_equal_reference_classes():
     assert torch.allclose(m["Pix2PixLoss"](conf)(v["fake_B"], v["real_B"]), 30.0 * torch.nn.functional.l1_loss(v["fake_B"], v["real_B"]))
 
 
-def test_b200_cut_modules_match_oracle_structure():
-    """FeaturePatchMLP state_dict keys / init order equal the oracle's (and hence the reference's cut.py:244-250)."""
+def test_b200_cut_modules_match_oracle_structure(monkeypatch):
+    """FeaturePatchMLP state_dict keys / init order equal the oracle's (and hence the reference's cut.py:244-250); its
+    forward (the fused gather + MLP + L2-norm entry point, here through the CPU restatement of the ABI) equals the
+    oracle's module chain."""
+    import fake_cabi
+    fake_cabi.install(monkeypatch)
     from ganslate_b200.nn.gans.unpaired.cut import FeaturePatchMLP
     from ganslate_b200.nn.utils import init_weights
     torch.manual_seed(3)
