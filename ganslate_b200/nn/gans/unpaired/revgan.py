@@ -74,14 +74,22 @@ class RevGAN(BaseGAN):
     def forward(self):
         G = self.networks['G']
         real_A, real_B = self.visuals['real_A'], self.visuals['real_B']
-        fake_B = G(real_A)
-        rec_A = G(fake_B, inverse=True)
-        fake_A = G(real_B, inverse=True)
-        rec_B = G(fake_A)
+        if self._streams() is not None:
+            self._prepack(['G'])
+
+        # the two cycles are independent chains through the one generator (train.multi_stream: two CUDA streams)
+        def chain_A():
+            fake_B = G(real_A)
+            return fake_B, G(fake_B, inverse=True)
+
+        def chain_B():
+            fake_A = G(real_B, inverse=True)
+            return fake_A, G(fake_A)
+
+        (fake_B, rec_A), (fake_A, rec_B) = self._fork_join(chain_A, chain_B)
         idt_B, idt_A = None, None
         if self.criterion_G.is_using_identity():
-            idt_B = G(real_B)
-            idt_A = G(real_A, inverse=True)
+            idt_B, idt_A = self._fork_join(lambda: G(real_B), lambda: G(real_A, inverse=True))
         self.visuals.update({'fake_B': fake_B, 'rec_A': rec_A, 'idt_A': idt_A, 'fake_A': fake_A, 'rec_B': rec_B,
                              'idt_B': idt_B})
 
@@ -101,8 +109,11 @@ class RevGAN(BaseGAN):
                       loss_id=0 if discriminator == 'D_B' else 1)
 
     def backward_G(self):
-        pred_B = self.networks['D_B'](self.visuals['fake_A'])  # the reference's pairing (revgan.py:196-197)
-        pred_A = self.networks['D_A'](self.visuals['fake_B'])
+        if self._streams() is not None:
+            self._prepack(['D_B', 'D_A'])
+        # the reference's pairing (revgan.py:196-197): D_B sees fake_A, D_A sees fake_B
+        pred_B, pred_A = self._fork_join(lambda: self.networks['D_B'](self.visuals['fake_A']),
+                                         lambda: self.networks['D_A'](self.visuals['fake_B']))
         self.losses['G_AB'] = self.criterion_adv(pred_B, target_is_real=True)
         self.losses['G_BA'] = self.criterion_adv(pred_A, target_is_real=True)
         losses_G = self.criterion_G(self.visuals)
