@@ -110,6 +110,8 @@ def recompute_coupling(tape, x, fn, inverse, free_input):
         steps, sub.steps = sub.steps, None
         while steps:
             steps.pop()()
+        if "_side" in sub.__dict__:          # weight gradients on a side stream: the enclosing pass joins it
+            tape.__dict__["_side"] = sub.__dict__.pop("_side")
 
     tape.steps.append(bwd)
     return y

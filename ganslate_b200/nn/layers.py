@@ -170,6 +170,7 @@ class PReLU(_Marker, nn.PReLU):
 # no fp32 gradient buffer outlives its backward and a second backward over the same tape (retain_graph=True with
 # RELEASE_TAPE off) starts from clean gradients instead of accumulating onto the previous pass's.
 _LIVE_GRADS = []
+_WGRAD_STREAMS = {}   # compute stream -> its weight-gradient side stream (ops.WGRAD_STREAM)
 
 # After its backward a network's tape (the closures that hold every bf16 activation of the forward pass) is dropped,
 # as autograd frees its saved tensors: a second backward through the same forward then raises, like torch's
@@ -308,6 +309,20 @@ class Tape:
     def needs(self, p):
         return p is not None and self.param_needs_grad.get(id(p), False)
 
+    def wgrad_stream(self, device):
+        """Opt-in (GB_WGRAD_STREAM=1): weight gradients run on a side stream of the stream the backward pass is on.
+        Nothing in the backward chain waits for a weight gradient -- only the parameter gradients handed back at the
+        end do -- so its one-wave kernel overlaps the data-gradient / InstanceNorm kernels of the layers that follow.
+        The pass joins the side stream before it flushes the weight-gradient copies (Tape.backward)."""
+        if not ops.WGRAD_STREAM or torch.device(device).type != "cuda":
+            return None
+        cur = torch.cuda.current_stream()
+        side = _WGRAD_STREAMS.get(cur.cuda_stream)
+        if side is None:
+            side = _WGRAD_STREAMS[cur.cuda_stream] = torch.cuda.Stream(device)
+        self._side = (cur, side)
+        return side
+
     def grad_target(self, p, numel=None):
         """Direct mode: the existing `p.grad` a kernel may accumulate into (None: produce a fresh gradient)."""
         if not self.direct or p is None:
@@ -349,6 +364,9 @@ class Tape:
         else:
             for step in reversed(self.steps):
                 step()
+        side = self.__dict__.pop("_side", None)
+        if side is not None:
+            side[0].wait_stream(side[1])
         self.unpack.flush()
         self._queued.clear()
 
@@ -429,8 +447,19 @@ def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0, want_stats=False, 
             gv = torch.nn.functional.pad(g, (0, 0, ops.BWD_BORDER, ops.BWD_BORDER))
         if tape.needs(weight):
             tgt = tape.grad_target(weight)
-            tape.add_param_grad(weight, op.run_wgrad(b.plain_view(), gv, weight.shape, dev, pending=tape.unpack,
-                                                     dw_out=tgt, accumulate=tgt is not None))
+            side = tape.wgrad_stream(dev) if tgt is None else None
+            if side is not None:
+                cur = torch.cuda.current_stream()
+                side.wait_stream(cur)           # the gradient `g` (and everything before it) is ready
+                with torch.cuda.stream(side):
+                    dw = op.run_wgrad(b.plain_view(), gv, weight.shape, dev, pending=tape.unpack)
+                for t in (g, b.st.t):           # read on the side stream: their memory must not be reused before it is done
+                    if torch.is_tensor(t):
+                        t.record_stream(side)
+                tape.add_param_grad(weight, dw)
+            else:
+                tape.add_param_grad(weight, op.run_wgrad(b.plain_view(), gv, weight.shape, dev, pending=tape.unpack,
+                                                         dw_out=tgt, accumulate=tgt is not None))
         if tape.needs(bias):
             tape.add_param_grad(bias, db[:op.cout] if db is not None else ops.colsum(g, op.cout))
         if b.needs_grad_flag:

@@ -79,6 +79,9 @@ def zeros(shape, device):
 # flat-bucket all-reduce reads `.grad` directly and is unaffected.
 DIRECT_PARAM_GRAD = os.environ.get("GB_DIRECT_PARAM_GRAD", "0") == "1"
 
+# Opt-in (GB_WGRAD_STREAM=1): weight-gradient launches of a backward pass on a side stream (nn/layers.py, Tape.wgrad_stream)
+WGRAD_STREAM = os.environ.get("GB_WGRAD_STREAM", "0") == "1"
+
 # fp32 validation mode (nn/fp32_mode.py): fp32 buffers, every convolution on the same kernels with 3-way bf16-split
 # operands accumulated in fp32, norm / activation steps in fp32 torch ops.  GB_FP32=1 or set at run time (tests).
 FP32_MODE = os.environ.get("GB_FP32", "0") == "1"
