@@ -125,7 +125,7 @@ int launch(const gb_in_bwd_params& p, float neg_slope, cudaStream_t st) {
   bool fits = false;
   const Geom g = gbv2::plan(p.x.N, p.x.D, p.x.H, p.x.W, p.x.C, num_sms() * (occ > 0 ? occ : MINB), &fits);
   const dim3 grid(g.nblocks, p.x.N);
-  if (occ > 0 && fits && g_gb_knobs[6] == 0) {
+  if (occ > 0 && fits && g_gb_knobs[6] == 2) {
     float ns = neg_slope;
     Geom gg = g;
     void* args[] = {(void*)&p, (void*)&gg, (void*)&ns};

@@ -129,7 +129,7 @@ extern "C" int gb_pack_weights(const gb_pack_params* pp, void* stream) {
 
 extern "C" int gb_pack_weights_multi(const gb_pack_params* table_dev, int count, int64_t max_elems, void* stream) {
   GB_CHECK(table_dev && count >= 1 && count <= 65535, "gb_pack_weights_multi: bad table (%d entries)", count);
-  if (g_gb_knobs[28] != 0) {
+  if (g_gb_knobs[28] != 2) {   // second-generation pack / unpack by default (r02a: +0.9 %, r02n: +2.4 %); knob 28 = 2: first generation
     const int r = gb_pack_weights_multi_v2(table_dev, count, max_elems, (cudaStream_t)stream);
     if (r >= 0) return r;
   }
@@ -150,7 +150,7 @@ extern "C" int gb_unpack_wgrad_multi(const gb_unpack_batch* b, void* stream) {
     const int64_t total = (int64_t)it.rows * it.chans * it.ntaps;
     mx = total > mx ? total : mx;
   }
-  if (g_gb_knobs[28] != 0) {
+  if (g_gb_knobs[28] != 2) {   // second-generation pack / unpack by default (r02a: +0.9 %, r02n: +2.4 %); knob 28 = 2: first generation
     const int r = gb_unpack_wgrad_multi_v2(b, mx, (cudaStream_t)stream);
     if (r >= 0) return r;
   }

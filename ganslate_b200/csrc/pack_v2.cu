@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256) unpack_multi_v2_kernel(const __grid_const
 // -1: not covered (first generation takes the call), 0: launched.  The host cannot read the device-resident table, so
 // the caller states what it guarantees: every class offset 16-byte aligned (w_offset % 8 == 0) and < 2^31 elements.
 int gb_pack_weights_multi_v2(const gb_pack_params* table_dev, int count, int64_t max_elems, cudaStream_t st) {
-  if (g_gb_knobs[28] != 1 || max_elems >= (1ll << 31)) return -1;
+  if (g_gb_knobs[28] == 2 || max_elems >= (1ll << 31)) return -1;
   int blocks = (int)((max_elems / 8 + 255) / 256);
   if (blocks > 592) blocks = 592;
   if (blocks < 1) blocks = 1;
@@ -38,7 +38,7 @@ int gb_pack_weights_multi_v2(const gb_pack_params* table_dev, int count, int64_t
 }
 
 int gb_unpack_wgrad_multi_v2(const gb_unpack_batch* b, int64_t max_total, cudaStream_t st) {
-  if (g_gb_knobs[28] != 1 || max_total >= (1ll << 31)) return -1;
+  if (g_gb_knobs[28] == 2 || max_total >= (1ll << 31)) return -1;
   int blocks = (int)((max_total + 1023) / 1024);
   if (blocks > 592) blocks = 592;
   if (blocks < 1) blocks = 1;

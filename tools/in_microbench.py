@@ -24,9 +24,9 @@ from ganslate_b200 import _cabi, ops
 from ganslate_b200._cabi import ACT_LEAKY, ACT_NONE, ACT_RELU
 
 dev = "cuda"
-VARIANTS = [("gen1 fused", {22: 0, 6: 0}), ("gen1 2-launch", {22: 0, 6: 1}), ("lean fused", {22: 4, 6: 0}),
-            ("lean 2-launch", {22: 4, 6: 1}), ("gen2 U4 fused", {22: 1, 6: 0}),
-            ("gen2 U4 2-launch", {22: 1, 6: 1}), ("gen2 U2 fused", {22: 2, 6: 0}), ("on-chip cluster", {24: 1}),
+VARIANTS = [("gen1 fused", {22: 0, 6: 2}), ("gen1 2-launch", {22: 0, 6: 1}), ("lean fused", {22: 4, 6: 2}),
+            ("lean 2-launch", {22: 4, 6: 1}), ("gen2 U4 fused", {22: 1, 6: 2}),
+            ("gen2 U4 2-launch", {22: 1, 6: 1}), ("gen2 U2 fused", {22: 2, 6: 2}), ("on-chip cluster", {24: 1}),
             ("on-chip half stash", {24: 2})]
 
 
