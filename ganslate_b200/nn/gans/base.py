@@ -244,13 +244,17 @@ class BaseGAN(ABC):
     # InstanceNorm launches, everything at batch 1).  Autograd replays every node's backward on the stream its
     # forward ran on, so the backward pass forks the same way.  Every network's packed weights are refreshed on the
     # parent stream first (a chain must not launch the pack kernel the other chain depends on).
-    def _streams(self):
+    def _streams(self, tag="chain"):
+        """The two child streams of the CURRENT stream for `tag` (None: single-stream execution).  Keyed by the parent, so
+        forks nest: a discriminator's real / fake passes fork again inside the stream of that discriminator."""
         default = os.environ.get("GB_MULTI_STREAM", "0") == "1"
         if not bool(self.conf.train.get("multi_stream", default)) or self.device.type != "cuda":
             return None
-        st = self.__dict__.get("_chain_streams")
+        pool = self.__dict__.setdefault("_chain_streams", {})
+        key = (torch.cuda.current_stream().cuda_stream, tag)
+        st = pool.get(key)
         if st is None:
-            st = self.__dict__["_chain_streams"] = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+            st = pool[key] = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
         return st
 
     def _prepack(self, names):
@@ -259,9 +263,9 @@ class BaseGAN(ABC):
             net = self.networks[n]
             ops.ensure_packed(net.module if isinstance(net, DistributedDataParallel) else net)
 
-    def _fork_join(self, fn1, fn2):
-        """Run fn1 and fn2 on the two chain streams (or back to back without `train.multi_stream`)."""
-        st = self._streams()
+    def _fork_join(self, fn1, fn2, tag="chain"):
+        """Run fn1 and fn2 on two child streams of the current stream (back to back without `train.multi_stream`)."""
+        st = self._streams(tag)
         if st is None:
             return fn1(), fn2()
         cur = torch.cuda.current_stream()

@@ -162,8 +162,8 @@ class CycleGAN(BaseGAN):
             fake = self.fake_A_pool.query(self.visuals['fake_A']) if fake is None else fake
         else:
             raise ValueError('The discriminator has to be either "D_A" or "D_B".')
-        self.pred_real = self.networks[discriminator](real)
-        self.pred_fake = self.networks[discriminator](fake.detach())
+        D = self.networks[discriminator]
+        self.pred_real, self.pred_fake = self._fork_join(lambda: D(real), lambda: D(fake.detach()), tag="real-fake")
         loss_real = self.criterion_adv(self.pred_real, target_is_real=True)
         loss_fake = self.criterion_adv(self.pred_fake, target_is_real=False)
         self.losses[discriminator] = loss_real + loss_fake
@@ -172,8 +172,10 @@ class CycleGAN(BaseGAN):
     def backward_G(self):
         if self._streams() is not None:
             self._prepack(['D_B', 'D_A'])
+        # (their own stream pair: in the backward pass a discriminator's data gradient then runs beside the second
+        #  generator of the same chain instead of in front of it)
         pred_B, pred_A = self._fork_join(lambda: self.networks['D_B'](self.visuals['fake_B']),
-                                         lambda: self.networks['D_A'](self.visuals['fake_A']))
+                                         lambda: self.networks['D_A'](self.visuals['fake_A']), tag="D")
         self.losses['G_AB'] = self.criterion_adv(pred_B, target_is_real=True)
         self.losses['G_BA'] = self.criterion_adv(pred_A, target_is_real=True)
         losses_G = self.criterion_G(self.visuals)

@@ -44,6 +44,12 @@ def conv_roofline(model, a_dev, b_dev, steps=3, with_traffic=True):
     was_graph = getattr(model, "use_cuda_graph", False)
     if was_graph:
         model.use_cuda_graph = False
+    # per-launch durations are only meaningful when launches do not share the SMs with another stream's kernel: the
+    # profiled steps run single-stream (train.multi_stream off), whatever the timed steps used
+    train = model.conf.train
+    had_ms = "multi_stream" in train
+    old_ms = train.get("multi_stream", None)
+    train["multi_stream"] = False
     # one un-timed eager step so packed weights / allocator are warm
     model.set_input({"A": a_dev, "B": b_dev})
     model.optimize_parameters()
@@ -59,6 +65,10 @@ def conv_roofline(model, a_dev, b_dev, steps=3, with_traffic=True):
         ops.PROFILE = None
         if was_graph:
             model.use_cuda_graph = True
+        if had_ms:
+            train["multi_stream"] = old_ms
+        else:
+            train._d.pop("multi_stream", None)
     agg = defaultdict(lambda: [0.0, 0.0, 0, ""])
     for fam, work, unit, e0, e1 in records:
         a = agg[fam]
@@ -89,7 +99,7 @@ def conv_roofline(model, a_dev, b_dev, steps=3, with_traffic=True):
         "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
         "avg_launch_us": round(t_conv / n_conv * 1e6, 2), "launches_per_step": n_conv // steps,
         "share_of_kernel_time": round(t_conv / total_t, 4),
-        "how": "algorithmic FLOPs (SURVEY 8d) / CUDA-event time around each launch, eager steps",
+        "how": "algorithmic FLOPs (SURVEY 8d) / CUDA-event time around each launch, eager single-stream steps",
     }
     traffic, src = ncu_traffic("conv", int(a_dev.shape[0])) if with_traffic else (None, None)
     if traffic is not None:
