@@ -107,8 +107,13 @@ class Pix2PixConditionalGAN(BaseGAN):
 
     def backward_D(self):
         real_A, real_B, fake_B = self.visuals['real_A'], self.visuals['real_B'], self.visuals['fake_B']
-        self.pred_real = self.networks['D'](torch.cat([real_A, real_B], dim=1))
-        self.pred_fake = self.networks['D'](torch.cat([real_A, fake_B.detach()], dim=1))
+        D = self.networks['D']
+        if self._streams("real-fake") is not None:
+            self._prepack(['D'])
+        # the real and the fake pass are independent (train.multi_stream: two CUDA streams, forward and backward)
+        self.pred_real, self.pred_fake = self._fork_join(lambda: D(torch.cat([real_A, real_B], dim=1)),
+                                                         lambda: D(torch.cat([real_A, fake_B.detach()], dim=1)),
+                                                         tag="real-fake")
         loss_real = self.criterion_adv(self.pred_real, target_is_real=True)
         loss_fake = self.criterion_adv(self.pred_fake, target_is_real=False)
         self.losses['D'] = loss_real + loss_fake
