@@ -66,7 +66,8 @@ def parse():
     if args.workload != "cyclegan2d" and "--batch" not in sys.argv and "GB_BENCH_BATCH" not in os.environ:
         args.batch = WORKLOADS[args.workload][2]
     if args.multi_stream is None:
-        args.multi_stream = args.workload in ("cyclegan2d", "cyclegan3d") and not args.single_stream   # (RevGAN: opt-in)
+        args.multi_stream = (args.workload in ("cyclegan2d", "cyclegan3d", "pix2pix_resnet", "pix2pix_unet", "revgan3d")
+                             and not args.single_stream)
     return args
 
 
@@ -74,7 +75,8 @@ def workload_config(args, world):
     if args.workload != "cyclegan2d":
         metric, preset, _, shape, graph = WORKLOADS[args.workload]
         return {"workload": f"{metric.replace(' train img/s', '').replace(' train patches/s', '')} "
-                            f"(ganslate_b200.presets.{preset}), synthetic {'x'.join(map(str, shape))}, batch {args.batch}/GPU",
+                            f"(ganslate_b200.presets.{preset}), synthetic {'x'.join(map(str, shape))}, batch {args.batch}/GPU"
+                            + (", independent passes on two CUDA streams" if args.multi_stream else ""),
                 "global_batch": args.batch * world, "image": list(shape), "parallelism": f"dp{world}",
                 "l2_policy": "2 x 126 MB flush buffer written between timed steps"}
     return {
