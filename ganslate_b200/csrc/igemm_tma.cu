@@ -679,6 +679,17 @@ igemm_pers_kernel(const __grid_constant__ gb_conv_params p, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int chunks = p.in.C >> 6;
+  unsigned long long* tsb = pg.tg.ts != nullptr ? pg.tg.ts + 16ull * blockIdx.x : nullptr;   // gb_debug_timeline
+  if (tsb != nullptr && tid == 0) {
+    unsigned smid;
+    unsigned long long gt;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    tsb[0] = smid;
+    tsb[1] = gt;
+    tsb[3] = (unsigned long long)clock64();
+    tsb[2] = tsb[3];
+  }
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one lane)
@@ -722,6 +733,7 @@ igemm_pers_kernel(const __grid_constant__ gb_conv_params p, const __grid_constan
         const uint32_t s = g % STAGES, itn = g / STAGES;
         mbar_wait(full_bar + 8 * s, itn & 1);
         tc_fence_after();
+        if (tsb != nullptr && kb == 0 && lane == 0 && li < 2) tsb[4 + 2 * li] = (unsigned long long)clock64();
         if (lane == 0) {
           const uint32_t a_s = base + s * C::STAGE_BYTES;
           const uint64_t adesc = make_smem_desc(a_s, 16, 1024);
@@ -733,6 +745,7 @@ igemm_pers_kernel(const __grid_constant__ gb_conv_params p, const __grid_constan
         __syncwarp();
       }
       if (lane == 0) umma_commit(accf_bar + 8 * bsel);
+      if (tsb != nullptr && lane == 0 && li < 2) tsb[5 + 2 * li] = (unsigned long long)clock64();
       __syncwarp();
       ++li;
     }
@@ -770,6 +783,7 @@ igemm_pers_kernel(const __grid_constant__ gb_conv_params p, const __grid_constan
       }
       mbar_wait(accf_bar + 8 * bsel, use & 1);
       tc_fence_after();
+      if (tsb != nullptr && warp == 2 && lane == 0 && li < 2) tsb[8 + 2 * li] = (unsigned long long)clock64();
       const uint32_t tacc = tmem_base + (uint32_t)(bsel * BN);
       const uint32_t aeb = acce_bar + 8 * bsel;
       if (fp32) {
@@ -783,12 +797,14 @@ igemm_pers_kernel(const __grid_constant__ gb_conv_params p, const __grid_constan
           default: pers_epilogue_item<BN, GB_ACT_NONE, false, false>(p, pg, it, tacc, aeb, lg, half, lane, stage, want_stats, st1, st2); break;
         }
       }
+      if (tsb != nullptr && warp == 2 && lane == 0 && li < 2) tsb[9 + 2 * li] = (unsigned long long)clock64();
       ++li;
     }
     if (want_stats) flush();
   }
   tc_fence_before();
   __syncthreads();
+  if (tsb != nullptr && tid == 0) tsb[12] = (unsigned long long)clock64();
   if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
@@ -1015,6 +1031,7 @@ int launch_pers(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMa
   }
   PersGeom pg;
   pg.tg = tg;
+  pg.tg.ts = (g_timeline != nullptr && pers_num_sms() <= g_timeline_ctas) ? g_timeline : nullptr;
   pg.ncb = gb_cdiv(p.ncols, BN);
   const int64_t total = (int64_t)tg.ntiles * pg.ncb * p.nclass;
   if (total >= (1ll << 31)) return -1;
