@@ -804,7 +804,12 @@ igemm_pers_kernel(const __grid_constant__ gb_conv_params p, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (tsb != nullptr && tid == 0) tsb[12] = (unsigned long long)clock64();
+  if (tsb != nullptr && tid == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    tsb[12] = (unsigned long long)clock64();
+    tsb[13] = gt;
+  }
   if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
@@ -1132,6 +1137,13 @@ int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st) {
   // persistent kernel (knob 16 = 3; see igemm_pers_kernel): widest column block, coalesced row stores
   if (g_gb_knobs[16] == 3) {
     bool ok = p.out.pad == 0 && (p.out_fp32 || !p.accumulate);
+    // knob 17 (with knob 16 = 3): which launches the persistent kernel takes -- bit 0 bf16 destinations, bit 1 fp32
+    // destinations with unit output stride, bit 2 fp32 destinations of parity-class (strided-output) launches; 0 = all
+    if (g_gb_knobs[17] != 0) {
+      const bool strided = p.out_mul[0] != 1 || p.out_mul[1] != 1 || p.out_mul[2] != 1;
+      const int cls = !p.out_fp32 ? 1 : (strided ? 4 : 2);
+      ok = ok && (g_gb_knobs[17] & cls) != 0;
+    }
     const int esz = p.out_fp32 ? 4 : 2;
     ok = ok && ((uintptr_t)p.out.ptr % 16) == 0 && (p.out.sx * esz) % 16 == 0 && (p.out.sy * esz) % 16 == 0 &&
          (p.out.sz * esz) % 16 == 0 && (p.out.sn * esz) % 16 == 0;

@@ -78,18 +78,23 @@ def conv_backward(op, x32, g32, weight, want_dx, want_dw, dx32=None):
     gs = split3(g32)
     ws = _split_weight(weight)
     parts = _part_ops(op)
+    if parts[0].bwd_window:
+        # gradient-side pixel windows (ops.ConvOp.bwd_window): dOut rows with zero pixels on both sides, passed as tensors
+        gops = [F.pad(g, (0, 0, ops.BWD_BORDER, ops.BWD_BORDER)) for g in gs]
+    else:
+        gops = [ops.make_view(g) for g in gs]
     dw = None
     if want_dw:
         xs = split3(x32)
         for ix, ig in _TERMS:
-            t = parts[0].run_wgrad(ops.make_view(xs[ix]), ops.make_view(gs[ig]), weight.shape, dev)
+            t = parts[0].run_wgrad(ops.make_view(xs[ix]), gops[ig], weight.shape, dev)
             dw = t if dw is None else dw + t
     if want_dx:
         if dx32 is None:
             dx32 = torch.zeros(x32.shape, dtype=torch.float32, device=dev)
         dxv = ops.make_view(dx32)
         for ig, iw in _TERMS:
-            parts[iw].run_dgrad(ops.make_view(gs[ig]), ws[iw], dxv, accumulate=True)
+            parts[iw].run_dgrad(gops[ig], ws[iw], dxv, accumulate=True)
     return dx32, dw
 
 

@@ -250,6 +250,9 @@ class BaseGAN(ABC):
         default = os.environ.get("GB_MULTI_STREAM", "0") == "1"
         if not bool(self.conf.train.get("multi_stream", default)) or self.device.type != "cuda":
             return None
+        from ganslate_b200 import ops
+        if ops.DIRECT_PARAM_GRAD:
+            return None   # (that opt-in mode adds into param.grad outside autograd's stream bookkeeping: single stream)
         pool = self.__dict__.setdefault("_chain_streams", {})
         key = (torch.cuda.current_stream().cuda_stream, tag)
         st = pool.get(key)

@@ -98,10 +98,10 @@ PROFILE = None
 # Pixel-window formulation of small-channel unit-stride convolutions (ConvOp.window / .bwd_window); tests switch it
 # off for A/B.
 WINDOW_CONV = True
-# The gradient-side windows (ConvOp.bwd_window) are verified on the CPU against torch (tests/test_host_logic.py) but
-# have not run on a B200 yet: opt-in (GB_BWD_WINDOW=1, or WINDOW_CONV = "force") until the GPU parity tests
-# (tests/test_strided_window_gpu.py::test_gradient_side_pixel_windows, GB_EXPERIMENTAL=1) have passed there.
-BWD_WINDOW_CONV = os.environ.get("GB_BWD_WINDOW", "0") == "1"
+# The gradient-side windows (ConvOp.bwd_window: data gradient and operand-swapped weight gradient of the 7x7 -> 3 output
+# layer on the TMA-fed kernels) are the default since r02t: data gradient 170 -> 115 us, weight gradient 158 -> 123 us,
+# whole step 393.8 -> 405.2 img/s.  GB_BWD_WINDOW=0 switches them off.
+BWD_WINDOW_CONV = os.environ.get("GB_BWD_WINDOW", "1") == "1"
 BWD_BORDER = 8  # zero pixels left and right of every dOut row in bwd_window mode (>= kw - 1)
 
 
@@ -205,9 +205,11 @@ class ConvOp:
     which is what the reference builds its networks from (e.g. ganslate/nn/generators/resnet/resnet2d.py:24-57).
     """
 
-    def __init__(self, cin, cout, kernel, stride, padding, transposed=False, output_padding=(0, 0, 0), weight_taps=None):
+    def __init__(self, cin, cout, kernel, stride, padding, transposed=False, output_padding=(0, 0, 0), weight_taps=None,
+                 allow_bwd_window=True):
         """weight_taps: taps per (row, channel) of the PARAMETER's layout when this op reads a depth slice
-        `weight[:, :, dz]` of a larger kernel (SlabConv); default = this op's own tap count."""
+        `weight[:, :, dz]` of a larger kernel (SlabConv); default = this op's own tap count.
+        allow_bwd_window: False for ops whose caller hands the gradient over as a view (SlabConv's depth slabs)."""
         self.cin, self.cout = cin, cout
         self.kernel, self.stride, self.padding = tuple(kernel), tuple(stride), tuple(padding)
         self.transposed, self.output_padding = transposed, tuple(output_padding)
@@ -277,7 +279,7 @@ class ConvOp:
         # through the taps p - r, i.e. kw consecutive pixels of a dOut row per (dz, dy) -- with dOut copied into a
         # buffer that has BWD_BORDER zero pixels left and right of every row, the window never leaves the row and both
         # GEMMs run on the TMA-fed kernels (K blocks (j, co), j = window position <-> rx = kw - 1 - j).
-        self.bwd_window = (bool(WINDOW_CONV) and (BWD_WINDOW_CONV or WINDOW_CONV == "force") and self.wg_swap and not transposed and all(s == 1 for s in self.stride)
+        self.bwd_window = (allow_bwd_window and bool(WINDOW_CONV) and (BWD_WINDOW_CONV or WINDOW_CONV == "force") and self.wg_swap and not transposed and all(s == 1 for s in self.stride)
                            and self.cout_pad == 8 and 1 < kernel[2] <= 8 and self.cin_pad % 64 == 0
                            and self.padding[2] <= 1 and kernel[0] * kernel[1] <= _cabi.GB_MAX_TAPS // 8
                            and (WINDOW_CONV == "force" or _cabi.lib().gb_tma_window_supported() == 1))
@@ -595,7 +597,8 @@ class SlabConv:
         self.cin, self.cout, self.kernel = cin, cout, tuple(kernel)
         self.cin_pad, self.cout_pad = pad8(cin), pad8(cout)
         self.T = kd * kh * kw
-        self.slabs = [ConvOp(cin, cout, (1, kh, kw), (1, 1, 1), (0, padding[1], padding[2]), weight_taps=self.T)
+        self.slabs = [ConvOp(cin, cout, (1, kh, kw), (1, 1, 1), (0, padding[1], padding[2]), weight_taps=self.T,
+                             allow_bwd_window=False)
                       for _ in range(kd)]
 
     def out_extent(self, ext):

@@ -99,7 +99,6 @@ BWD_WINDOW = [
 ]
 
 
-@pytest.mark.experimental
 @pytest.mark.parametrize("case", BWD_WINDOW, ids=[c["name"] for c in BWD_WINDOW])
 def test_gradient_side_pixel_windows(case):
     """Output layers with <= 8 channels: data gradient and operand-swapped weight gradient through 7-pixel windows of

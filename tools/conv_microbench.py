@@ -32,6 +32,30 @@ def time_us(fn, reps=20, warm=3):
     return ts[len(ts) // 2]
 
 
+def time_us_graph(fn, n=10, reps=5):
+    """Per-launch time of `n` back-to-back launches replayed from a CUDA graph: no host launch latency inside the timed
+    region (time_us brackets ONE eager launch with events, and the ~20 us of Python between `e0.record()` and the kernel
+    reaching the stream are then part of the number whenever the GPU is idle -- it is, after the L2 flush).  Warm L2:
+    what a layer sees inside a step."""
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            fn()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3 / n)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
 def layer(name, cin, cout, k, stride, pad, H, W, N, border=0, transposed=False, op_pad=0):
     """border: materialised reflection border of the input buffer (the conv itself then has padding 0)."""
     op = ops.ConvOp(cin, cout, (1, k, k), (1, stride, stride), (0, pad, pad), transposed=transposed,
@@ -74,6 +98,8 @@ def main():
     ap.add_argument("--what", default="fwd,dgrad,wgrad")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--no-stats", action="store_true", help="forward without the InstanceNorm statistics epilogue")
+    ap.add_argument("--graph", action="store_true", help="time 10 back-to-back launches replayed from a CUDA graph (no host "
+                                                         "launch latency in the number; warm L2)")
     args = ap.parse_args()
     B = args.batch
     global NO_STATS
@@ -112,7 +138,8 @@ def main():
         layers = [layers[int(i)] for i in args.layers.split(",")]
     if args.variants:
         variants = [variants[int(i)] for i in args.variants.split(",")]
-    print(f"batch {B}; us per launch (median of {args.reps}, L2 flushed), TFLOP/s algorithmic")
+    print(f"batch {B}; us per launch, TFLOP/s algorithmic; " + ("10 launches back to back from a CUDA graph, warm L2" if args.graph
+          else f"median of {args.reps} single eager launches, L2 flushed (includes host launch latency when the GPU idles)"))
     for L in layers:
         print(f"--- {L['name']}  ({L['flops'] / 1e9:.2f} GFLOP)")
         for vname, knobs in variants:
@@ -122,7 +149,7 @@ def main():
                 for what in args.what.split(","):
                     lib.gb_debug_knob(15, 0)
                     lib.gb_debug_knob(14, 0)
-                    t = time_us(run(L, what), reps=args.reps, warm=1 if args.reps < 5 else 3)
+                    t = time_us_graph(run(L, what)) if args.graph else time_us(run(L, what), reps=args.reps, warm=1 if args.reps < 5 else 3)
                     path = lib.gb_debug_knob(14, 0) if what == "wgrad" else lib.gb_debug_knob(15, 0)
                     row.append(f"{what} {t:7.1f}us {L['flops'] / t / 1e6:6.0f}TF [k{path}]")
                 print(f"  {vname:32s} " + "  ".join(row), flush=True)

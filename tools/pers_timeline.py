@@ -40,6 +40,12 @@ def main():
             two = t[t[:, 7] != 0]     # CTAs that processed two items
             one = t[t[:, 7] == 0]
             print(f"    CTAs with two items: {len(two)}, with one: {len(one)}")
+            g0 = int(t[:, 1].min())
+            start, end = (t[:, 1] - g0).float() / 1e3, (t[:, 13] - g0).float() / 1e3
+            wall = (t[:, 13] - t[:, 1]).float() / 1e3
+            cyc = (t[:, 12] - t[:, 2]).float()
+            print(f"    globaltimer: first CTA start 0, last CTA start {start.max():.1f} us, last CTA end {end.max():.1f} us; "
+                  f"per-CTA wall {wall.mean():.1f} us for {cyc.mean():.0f} cycles = {cyc.mean() / wall.mean() / 1e3:.2f} GHz")
             d = lambda tt, a, b: (tt[:, b] - tt[:, a]).float()
             for name, tt, a, b in (("setup -> first operands of item 0", t, 3, 4), ("main loop item 0 (first data -> last MMA issued)", t, 4, 5),
                                    ("main loop item 1", two, 6, 7), ("item 0: last MMA issued -> accumulator seen by the epilogue", t, 5, 8),
