@@ -29,7 +29,7 @@ WORKLOADS = {
     "cyclegan2d": ("CycleGAN train img/s", "cyclegan_resnet2d", 8, None, True),
     "pix2pix_resnet": ("Pix2Pix Resnet2D train img/s", "pix2pix_resnet2d", 8, (3, 256, 512), True),
     "pix2pix_unet": ("Pix2Pix Unet2D train img/s", "pix2pix_unet2d", 8, (3, 256, 512), True),
-    "cut": ("CUT train img/s", "cut_resnet2d", 1, (3, 256, 256), False),
+    "cut": ("CUT train img/s", "cut_resnet2d", 1, (3, 256, 256), True),   # graph segments (r02b: 27.4 eager -> 75.9 img/s)
     "cyclegan3d": ("CycleGAN 3D Vnet3D train patches/s", "cyclegan_vnet3d", 1, (1, 32, 256, 256), False),
     "revgan3d": ("RevGAN 3D Vnet3D train patches/s", "revgan_vnet3d", 1, (4, 128, 128, 128), False),
     "revgan_piresnet3d": ("RevGAN 3D Piresnet3D train patches/s", "revgan_piresnet3d", 1, (1, 32, 176, 176), False),

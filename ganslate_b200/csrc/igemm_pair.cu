@@ -257,13 +257,14 @@ int launch(const gb_conv_params& p, const CUtensorMap& ma, const CUtensorMap& mb
 int gb_tma_weight_map(const void* w, int kpad, int rows, int bn, CUtensorMap* out);  // igemm_tma.cu
 
 // -1: not applicable (the caller tries the per-tap TMA kernel next), 0: launched, >0: error.
-// knob 9: 0 / 1 = never use this kernel (default since r02: timed from a CUDA graph the per-tap kernel with the staged
-// bulk-store epilogue is faster on the one launch class this kernel was kept for -- residual-block forward at batch 8:
-// 35.3 us vs 39.1 us, profiles/r02u_conv_microbench_graph_b8.txt), 2 = use it whenever it applies (tests), 3 = round 1's
-// window (exactly one wave of 256-wide pair CTAs); knob 10: 1 = halo pitch 16 instead of kw + 7; knob 11: force the
-// tile width; knob 13: force the number of activation stages.
+// knob 9: 1 = never use this kernel, 2 = use it whenever it applies (tests), 0 = its window (exactly one wave of 256-wide
+// pair CTAs: the residual-block forward at batch 8).  Timed alone from a CUDA graph the per-tap kernel with the staged
+// bulk-store epilogue is the faster one there (35.3 vs 39.1 us, profiles/r02u_conv_microbench_graph_b8.txt), but inside
+// the two-stream step the 128-CTA launch leaves 20 SMs to the other chain and the step is 0.7 % faster with it
+// (r02v: 396.1 / 400.1 vs 393.3 / 397.6 img/s), so the window stays.  knob 10: 1 = halo pitch 16 instead of kw + 7;
+// knob 11: force the tile width; knob 13: force the number of activation stages.
 int gb_conv_data_pair(const gb_conv_params& p, cudaStream_t st) {
-  if (g_gb_knobs[9] < 2 || g_gb_knobs[3] != 0 || p.in_c_valid != 0) return -1;
+  if (g_gb_knobs[9] == 1 || g_gb_knobs[3] != 0 || p.in_c_valid != 0) return -1;
   if (p.in.C % 64 != 0 || p.in.pad != 0 || !gb_tma_available()) return -1;
   for (int d = 0; d < 3; ++d)
     if (p.in_mul[d] != 1) return -1;

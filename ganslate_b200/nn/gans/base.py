@@ -156,9 +156,12 @@ class BaseGAN(ABC):
         if not self.use_cuda_graph:
             return tensor.to(self.device, non_blocking=True)
         buf = self._static.get(name)
+        if buf is not None and buf.shape != tensor.shape and self._graphs:
+            # a batch of another shape after capture (last partial batch, other patch size): this iteration runs
+            # eagerly on the tensor itself, the captured graphs and their static buffers stay as they are
+            self._eager_once = True
+            return tensor.to(self.device, non_blocking=True)
         if buf is None or buf.shape != tensor.shape:
-            if buf is not None and self._graphs:
-                raise RuntimeError("input shape changed after CUDA-graph capture")
             buf = torch.empty(tensor.shape, dtype=torch.float32, device=self.device)
             self._static[name] = buf
         if self.input_copy_stream is not None and tensor.device.type == "cpu" and tensor.is_pinned():
@@ -190,6 +193,17 @@ class BaseGAN(ABC):
             return False
         if key == 'step':
             self._graph_calls += 1
+            if self.__dict__.pop("_eager_once", False):
+                # stage_input saw a shape the graphs were not captured for.  The eager iteration rebinds the entries
+                # of visuals / losses / metrics to fresh tensors; the graphs keep writing the ones bound at capture:
+                # remember those and bind them again before the next replay.
+                if self._graphs and "_graph_bound" not in self.__dict__:
+                    self._graph_bound = tuple(dict(d) for d in (self.visuals, self.losses, self.metrics))
+                return False
+            bound = self.__dict__.pop("_graph_bound", None)
+            if bound is not None:
+                for d, saved in zip((self.visuals, self.losses, self.metrics), bound):
+                    d.update({k: v for k, v in saved.items() if not k.startswith("real")})
         return self._graph_calls > self.graph_warmup_iters
 
     def eager_stream(self):

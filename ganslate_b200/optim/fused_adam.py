@@ -33,6 +33,17 @@ class FusedAdam(torch.optim.Adam):
             ent[1] = val
         return ent[0]
 
+    def state_dict(self):
+        """torch.optim.Adam's layout with ONE `step` PER PARAMETER (a CPU scalar, as torch writes it): the shared device
+        scalar of a group must not survive into a checkpoint -- torch.optim.Adam (the reference, or
+        `train.fused_adam: False`) would add 1 to the shared tensor once per parameter and step."""
+        sd = super().state_dict()
+        for st in sd["state"].values():
+            s = st.get("step")
+            if torch.is_tensor(s):
+                st["step"] = torch.tensor(float(s), dtype=torch.float32)
+        return sd
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None

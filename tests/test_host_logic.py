@@ -360,3 +360,24 @@ def test_device_image_pool_makes_the_reference_pools_decisions():
             assert dev.num_imgs == ref.num_imgs
             for k in range(ref.num_imgs):
                 assert torch.equal(ref.images[k][0], dev.store[k]), (pool_size, k)
+
+
+def test_fused_adam_state_dict_has_one_step_per_parameter():
+    """the shared device `step` scalar of a FusedAdam group must not reach a checkpoint -- torch.optim.Adam
+    restored from it would advance `step` once per parameter.  state_dict() emits per-parameter CPU scalars."""
+    import torch
+    from ganslate_b200.optim.fused_adam import FusedAdam
+    ps = [torch.nn.Parameter(torch.randn(3)) for _ in range(4)]
+    opt = FusedAdam(ps, lr=1e-3)
+    shared = torch.tensor(5.0)
+    for p in ps:                       # the state FusedAdam.step() leaves behind (one tensor shared by the group)
+        opt.state[p] = {"exp_avg": torch.zeros_like(p), "exp_avg_sq": torch.zeros_like(p), "step": shared}
+    sd = opt.state_dict()
+    steps = [st["step"] for st in sd["state"].values()]
+    assert all(float(s) == 5.0 for s in steps) and len({s.data_ptr() for s in steps}) == 4
+    ref = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in ps], lr=1e-3)
+    ref.load_state_dict(sd)
+    for p in ref.param_groups[0]["params"]:
+        p.grad = torch.ones_like(p)
+    ref.step()
+    assert all(float(st["step"]) == 6.0 for st in ref.state.values())
