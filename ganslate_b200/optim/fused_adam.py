@@ -38,10 +38,13 @@ class FusedAdam(torch.optim.Adam):
         scalar of a group must not survive into a checkpoint -- torch.optim.Adam (the reference, or
         `train.fused_adam: False`) would add 1 to the shared tensor once per parameter and step."""
         sd = super().state_dict()
+        read = {}   # one device -> host read per shared scalar, not per parameter
         for st in sd["state"].values():
             s = st.get("step")
             if torch.is_tensor(s):
-                st["step"] = torch.tensor(float(s), dtype=torch.float32)
+                if id(s) not in read:
+                    read[id(s)] = float(s)
+                st["step"] = torch.tensor(read[id(s)], dtype=torch.float32)
         return sd
 
     @torch.no_grad()

@@ -84,7 +84,8 @@ def test_cut_step_vs_oracle():
 
 
 @pytest.mark.parametrize("shape,P,nc", [((1, 3, 70, 70), 256, 256), ((2, 128, 32, 32), 256, 256), ((1, 256, 16, 16), 256, 256),
-                                        ((1, 24, 6, 9, 7), 100, 64), ((3, 256, 64, 64), 256, 256)])
+                                        ((1, 24, 6, 9, 7), 100, 64), ((3, 256, 64, 64), 256, 256),
+                                        ((1, 40, 12, 12), 77, 320)])
 def test_patch_mlp_kernels_match_torch(shape, P, nc):
     """csrc/patch_mlp.cu (gather + Linear + ReLU + Linear + L2 norm, fp32 FMAs) against the reference's module chain
     (cut.py:262-276) evaluated by torch in fp32 on the CPU: outputs and every gradient <= 1e-4 max-relative."""

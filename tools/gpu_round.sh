@@ -97,8 +97,9 @@ PY
 benchref)
   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 --batch $B > $out/bench_ref_b$B.json 2>> $out/bench_b$B.err; cat $out/bench_ref_b$B.json ;;
 launches)
+  # (WORKLOAD=cut ... lists another configuration's step; BATCH then is that workload's batch)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file $out/launches_b$B.csv \
-     python bench.py --batch $B --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-roofline --no-batch1 --single-stream > $out/launches_run.log 2>&1
+     python bench.py --workload ${WORKLOAD:-cyclegan2d} --batch $B --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-roofline --no-batch1 --single-stream > $out/launches_run.log 2>&1
   python tools/launch_summary.py $out/launches_b$B.csv 5 --md > $out/launch_summary_b$B.md 2>&1; head -42 $out/launch_summary_b$B.md ;;
 full)
   # FULLSPECS="regex:skip:count ..." -- one ncu --set full capture per spec (kept small: reports come home)
