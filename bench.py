@@ -66,7 +66,7 @@ def parse():
     if args.workload != "cyclegan2d" and "--batch" not in sys.argv and "GB_BENCH_BATCH" not in os.environ:
         args.batch = WORKLOADS[args.workload][2]
     if args.multi_stream is None:
-        args.multi_stream = (args.workload in ("cyclegan2d", "cyclegan3d", "pix2pix_resnet", "pix2pix_unet", "revgan3d")
+        args.multi_stream = (args.workload in ("cyclegan2d", "cyclegan3d", "pix2pix_resnet", "pix2pix_unet", "revgan3d", "cut")
                              and not args.single_stream)
     return args
 

@@ -151,13 +151,22 @@ class CUT(BaseGAN):
                 real_A = real_A.flip(-1)
                 if using_idt:
                     real_B = real_B.flip(-1)
-        self.visuals['fake_B'] = self.networks['G'](real_A)
-        if using_idt:
-            self.visuals['idt_B'] = self.networks['G'](real_B)
+        G = self.networks['G']
+        if not using_idt:
+            self.visuals['fake_B'] = G(real_A)
+            return
+        # the translation and the identity pass are independent (train.multi_stream: two CUDA streams, forward and
+        # backward -- at CUT's batch 1 a single chain leaves most SMs idle)
+        if self._streams() is not None:
+            self._prepack(['G'])
+        self.visuals['fake_B'], self.visuals['idt_B'] = self._fork_join(lambda: G(real_A), lambda: G(real_B))
 
     def backward_D(self):
-        pred_real = self.networks['D'](self.visuals['real_B'])
-        pred_fake = self.networks['D'](self.visuals['fake_B'].detach())
+        D = self.networks['D']
+        if self._streams("real-fake") is not None:
+            self._prepack(['D'])
+        pred_real, pred_fake = self._fork_join(lambda: D(self.visuals['real_B']),
+                                               lambda: D(self.visuals['fake_B'].detach()), tag="real-fake")
         loss_real = self.criterion_adv(pred_real, True).mean()
         loss_fake = self.criterion_adv(pred_fake, False).mean()
         self.losses['D'] = loss_real + loss_fake
@@ -173,18 +182,25 @@ class CUT(BaseGAN):
             self.losses['G'] = adversarial_loss
         nce_loss = 0
         if self.lambda_nce > 0:
-            nce_loss = self._calculate_nce_loss(real_A, fake_B)
+            if self._streams("nce") is not None:
+                self._prepack(['G'])
+            if self.lambda_nce_idt > 0:
+                # (the two contrastive terms are independent: two CUDA streams with train.multi_stream)
+                nce_loss, nce_idt = self._fork_join(lambda: self._calculate_nce_loss(real_A, fake_B),
+                                                    lambda: self._calculate_nce_loss(real_B, idt_B), tag="nce")
+            else:
+                nce_loss = self._calculate_nce_loss(real_A, fake_B)
             self.losses['NCE'] = nce_loss
             if self.lambda_nce_idt > 0:
-                nce_idt_loss = self.lambda_nce_idt * self._calculate_nce_loss(real_B, idt_B)
+                nce_idt_loss = self.lambda_nce_idt * nce_idt
                 nce_loss = (1 - self.lambda_nce_idt) * nce_loss + nce_idt_loss
                 self.losses['NCE_idt'] = nce_idt_loss
         self.backward(loss=adversarial_loss + nce_loss, optimizer=(self.optimizers['G'], self.optimizers['mlp']), loss_id=1)
 
     def _calculate_nce_loss(self, source, target):
         G = _unwrap(self.networks['G'])
-        source_feats = extract_features(source, G, self.nce_layers)
-        target_feats = extract_features(target, G, self.nce_layers)
+        source_feats, target_feats = self._fork_join(lambda: extract_features(source, G, self.nce_layers),
+                                                     lambda: extract_features(target, G, self.nce_layers), tag="feats")
         if self.is_flipped:
             target_feats = [feat.flip(-1) for feat in target_feats]
         source_pool, patch_ids = self.networks['mlp'](source_feats, self.fixed_patch_ids)

@@ -50,7 +50,10 @@ def test_encoder_taps_match_reference_semantics():
         assert ((a.cpu() - b).norm() / b.norm()).item() < tol
 
 
-def test_cut_step_vs_oracle():
+@pytest.mark.parametrize("multi_stream", [False, True])
+def test_cut_step_vs_oracle(multi_stream):
+    """(multi_stream: the translation / identity passes, the real / fake discriminator passes, the two contrastive terms
+    and their two encoder passes each fork onto two CUDA streams -- same losses and gradients.)"""
     from ganslate_b200.presets import cut_resnet2d
     from ganslate_b200.utils.builders import build_gan
     from oracle import torch_oracle as O
@@ -58,7 +61,7 @@ def test_cut_step_vs_oracle():
     torch.manual_seed(0)
     oracle = O.OracleCUT(n_residual_blocks=9, num_patches=256, seed=0)
     torch.manual_seed(0)
-    ours = build_gan(cut_resnet2d())
+    ours = build_gan(cut_resnet2d(multi_stream=multi_stream))
     for name in ("G", "D", "mlp"):
         for (k1, p1), (k2, p2) in zip(oracle.networks[name].state_dict().items(), ours.networks[name].state_dict().items()):
             assert k1 == k2 and torch.equal(p1, p2.cpu()), (name, k1)
@@ -116,3 +119,27 @@ def test_patch_mlp_kernels_match_torch(shape, P, nc):
     assert mr(yo.detach(), yr.detach()) <= 1e-4
     for name, a, b in zip(("dfeat", "dW1", "db1", "dW2", "db2"), to, tr):
         assert mr(a.grad, b.grad) <= 1e-4, (name, mr(a.grad, b.grad))
+
+
+def test_cut_graph_replay_with_streams():
+    """CUT with train.cuda_graph + train.multi_stream: the forked branches are captured into the two graph segments and
+    replayed; losses stay finite, every network's weights move, and the replayed iteration draws new patch ids."""
+    from ganslate_b200.presets import cut_resnet2d
+    from ganslate_b200.utils.builders import build_gan
+    from oracle import torch_oracle as O
+    torch.manual_seed(0)
+    m = build_gan(cut_resnet2d(multi_stream=True, cuda_graph=True, cuda_graph_warmup=2))
+    a, b = O.synthetic_batch(1, 3, 64, seed=1)
+    w0 = {n: next(net.parameters()).detach().clone() for n, net in m.networks.items()}
+    hist = []
+    for _ in range(5):
+        m.set_input({"A": a, "B": b})
+        m.optimize_parameters()
+        torch.cuda.synchronize()
+        hist.append({k: float(v) for k, v in m.losses.items() if v is not None})
+    assert len(m._graphs) == 2
+    import math
+    assert all(math.isfinite(v) for h in hist for v in h.values())
+    for n, net in m.networks.items():
+        assert (next(net.parameters()).detach() - w0[n]).abs().max().item() > 0, n
+    assert hist[-1]["NCE"] != hist[-2]["NCE"]
