@@ -871,6 +871,33 @@ int gb_tma_activation_map(const gb_view& v, int tw, int th, CUtensorMap* out, co
   return 0;
 }
 
+// 5-D activation map {C, W, H, D, N} of a view with 16 or 32 channels per pixel: box {cbox, tw, th, 1, 1}, the swizzle
+// whose span is one pixel (SWIZZLE_32B / SWIZZLE_64B) -- igemm_halo_narrow.cu
+int gb_tma_activation_map_narrow(const gb_view& v, int cbox, int tw, int th, CUtensorMap* out) {
+  GB_CHECK(cbox == 16 || cbox == 32, "narrow activation map: 16 or 32 channels per pixel");
+  const int tag = -7;
+  std::string key(reinterpret_cast<const char*>(&v), sizeof(gb_view));
+  key.append(reinterpret_cast<const char*>(&tw), sizeof(int)).append(reinterpret_cast<const char*>(&th), sizeof(int));
+  key.append(reinterpret_cast<const char*>(&cbox), sizeof(int)).append(reinterpret_cast<const char*>(&tag), sizeof(int));
+  std::lock_guard<std::mutex> lk(g_map_mutex);
+  auto it = g_map_cache.find(key);
+  if (it != g_map_cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  cuuint64_t dims[5] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.D, (cuuint64_t)v.N};
+  cuuint64_t strides[4] = {(cuuint64_t)v.sx * 2, (cuuint64_t)v.sy * 2, (cuuint64_t)v.sz * 2, (cuuint64_t)v.sn * 2};
+  cuuint32_t box[5] = {(cuuint32_t)cbox, (cuuint32_t)tw, (cuuint32_t)th, 1, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode_fn()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, v.ptr, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, cbox == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(narrow activation) failed: %d", (int)r);
+  if (g_map_cache.size() > 4096) g_map_cache.clear();
+  g_map_cache[key] = *out;
+  return 0;
+}
+
 // 2-D weight map {kpad, nclass*npad}, box {64, bn}; all classes of one conv share kpad on this path
 int gb_tma_weight_map(const void* w, int kpad, int rows, int bn, CUtensorMap* out) {
   struct {

@@ -414,6 +414,8 @@ int64_t view_max_offset(const gb_view& v) {
 
 }  // namespace
 
+int gb_conv_wgrad_narrow(const gb_wgrad_params& p, cudaStream_t st);  // igemm_wgrad_narrow.cu: -1 = not applicable
+
 extern "C" int gb_conv_wgrad(const gb_wgrad_params* pp, void* stream) {
   const gb_wgrad_params& p = *pp;
   GB_CHECK(p.plain.ptr && p.gathered.ptr && p.dw, "gb_conv_wgrad: null pointer");
@@ -428,6 +430,10 @@ extern "C" int gb_conv_wgrad(const gb_wgrad_params* pp, void* stream) {
   GB_CHECK(((uintptr_t)p.plain.ptr & 15) == 0 && ((uintptr_t)p.gathered.ptr & 15) == 0 && ((uintptr_t)p.dw & 15) == 0,
            "gb_conv_wgrad: pointers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const int r = gb_conv_wgrad_narrow(p, st);  // 16 / 32 channels on both sides, dense tap box: igemm_wgrad_narrow.cu
+    if (r >= 0) return r;
+  }
   int bn = p.kpad >= 256 ? 256 : (p.kpad >= 128 ? 128 : 64);
   if (g_gb_knobs[2] > 0) bn = g_gb_knobs[2];
   switch (bn) {

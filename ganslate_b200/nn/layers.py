@@ -420,7 +420,13 @@ def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0, want_stats=False, 
     dev = b.t.device
     ops._require_cuda(b.t, "convolution input")
     stats = ops.zeros((b.t.shape[0], op.cout_pad, 2), dev) if (want_stats and act == ACT_NONE) else None
-    y = op.run_fwd(b.plain_view(), dev, m.weight, m.bias, act, slope, stats=stats)
+    xin = None
+    if getattr(op, "widen_input", False):
+        # ops.WIDEN_INPUT: the layer reads a copy of its 8-channel operand with 8 zero channels appended (kept for the
+        # weight gradient); one streaming pass over a 1-4 channel network input
+        xin = torch.nn.functional.pad(b.st.t[..., b.c0:b.c0 + b.cw], (0, op.cin_pad - b.cw))
+    in_view = (lambda: ops.make_view(xin)) if xin is not None else b.plain_view
+    y = op.run_fwd(in_view(), dev, m.weight, m.bias, act, slope, stats=stats)
     out = Buf(y, 0, m.out_channels, b.is_3d, raw=(act == ACT_NONE and not as_activation))
     out.stats = stats
     weight, bias = m.weight, m.bias
@@ -452,13 +458,13 @@ def step_conv(tape: Tape, b: Buf, m, act=ACT_NONE, slope=0.0, want_stats=False, 
                 cur = torch.cuda.current_stream()
                 side.wait_stream(cur)           # the gradient `g` (and everything before it) is ready
                 with torch.cuda.stream(side):
-                    dw = op.run_wgrad(b.plain_view(), gv, weight.shape, dev, pending=tape.unpack)
-                for t in (g, b.st.t):           # read on the side stream: their memory must not be reused before it is done
+                    dw = op.run_wgrad(in_view(), gv, weight.shape, dev, pending=tape.unpack)
+                for t in (g, b.st.t, xin):      # read on the side stream: their memory must not be reused before it is done
                     if torch.is_tensor(t):
                         t.record_stream(side)
                 tape.add_param_grad(weight, dw)
             else:
-                tape.add_param_grad(weight, op.run_wgrad(b.plain_view(), gv, weight.shape, dev, pending=tape.unpack,
+                tape.add_param_grad(weight, op.run_wgrad(in_view(), gv, weight.shape, dev, pending=tape.unpack,
                                                          dw_out=tgt, accumulate=tgt is not None))
         if tape.needs(bias):
             tape.add_param_grad(bias, db[:op.cout] if db is not None else ops.colsum(g, op.cout))

@@ -102,6 +102,11 @@ WINDOW_CONV = True
 # layer on the TMA-fed kernels) are the default since r02t: data gradient 170 -> 115 us, weight gradient 158 -> 123 us,
 # whole step 393.8 -> 405.2 img/s.  GB_BWD_WINDOW=0 switches them off.
 BWD_WINDOW_CONV = os.environ.get("GB_BWD_WINDOW", "1") == "1"
+# Few input channels under a true 3-D kernel with many taps (the V-Net input block: 1 -> 16 channels, 5x5x5, on the full
+# volume): the layer reads a 16-channel copy of its input (zero channels appended by the caller, layers.step_conv), which
+# puts forward and weight gradient on the halo kernels for 32-byte pixels (csrc/igemm_halo_narrow.cu,
+# igemm_wgrad_narrow.cu) instead of one 16-byte gather per pixel and tap.  GB_WIDEN_INPUT=0 keeps the 8-channel operand.
+WIDEN_INPUT = os.environ.get("GB_WIDEN_INPUT", "1") == "1"
 BWD_BORDER = 8  # zero pixels left and right of every dOut row in bwd_window mode (>= kw - 1)
 
 
@@ -216,6 +221,11 @@ class ConvOp:
         self.cin_pad, self.cout_pad = pad8(cin), pad8(cout)
         self.T = kernel[0] * kernel[1] * kernel[2]
         self.wT = wT = int(weight_taps) if weight_taps else self.T  # tap extent of the parameter's memory layout
+        # (see WIDEN_INPUT) the gradient wrt the input keeps the 8-channel buffer: only `ncols = cin` columns are written
+        self.widen_input = (WIDEN_INPUT and not FP32_MODE and not transposed and weight_taps is None and self.cin_pad == 8
+                            and kernel[0] > 1 and self.T >= 27 and all(s == 1 for s in stride) and self.cout_pad in (16, 32))
+        if self.widen_input:
+            self.cin_pad = 16
         if transposed:
             self.fwd = transposed_spec(kernel, stride, padding)
             self.dgrad = strided_spec(kernel, stride, padding)
@@ -427,7 +437,8 @@ class ConvOp:
         zero-bordered TENSOR (see bwd_window_view)."""
         if self.bwd_window:
             dyv = self.bwd_window_view(dyv)
-        assert (self.bwd_window or dyv.C == self.cout_pad) and outv.C == self.cin_pad and outv.pad == 0
+        assert (self.bwd_window or dyv.C == self.cout_pad) and outv.pad == 0
+        assert outv.C == (pad8(self.cin) if self.widen_input else self.cin_pad), (outv.C, self.cin_pad)
         p = self._params("dgrad")
         p.in_c_valid = self.kernel[2] * 8 if self.bwd_window else 0
         p.out_fp32, p.accumulate = 1, 1 if accumulate else 0

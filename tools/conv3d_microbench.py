@@ -24,7 +24,7 @@ def layer3d(name, cin, cout, k, ext, N=1):
     D, H, W = ext
     x = torch.randn(N, D, H, W, op.cin_pad, device=dev).to(torch.bfloat16)
     dy = torch.randn(N, D, H, W, op.cout_pad, device=dev).to(torch.bfloat16)
-    dx = torch.zeros(N, D, H, W, op.cin_pad, device=dev, dtype=torch.float32)
+    dx = torch.zeros(N, D, H, W, ops.pad8(cin), device=dev, dtype=torch.float32)  # (a widened input keeps its 8-channel gradient)
     stats = torch.zeros(N, op.cout_pad, 2, device=dev)
     return dict(name=name, op=op, w=w, bias=bias, xv=ops.make_view(x), dyv=ops.make_view(dy), dxv=ops.make_view(dx),
                 stats=stats, flops=op.flops(ext, N), keep=(x, dy, dx))
