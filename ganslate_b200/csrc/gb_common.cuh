@@ -123,6 +123,33 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate, single CTA.
+// True in exactly one lane of the (converged) warp.  Unlike `lane == 0`, `elect.sync` tells the compiler that the
+// region it guards runs in a single thread: descriptor arithmetic stays in the uniform datapath and a tcgen05.mma is
+// one UTCHMMA, without the per-instruction "elect / issue / branch-if-any-left" loop that thread-divergent code gets
+// (22 instructions per MMA in the first igemm_halo_narrow build, where one MMA lasts ~17 cycles).
+__device__ __forceinline__ bool gb_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// tcgen05.mma with the accumulate flag as a compile-time constant (no predicate register to materialise per MMA)
+template <int ACC>
+__device__ __forceinline__ void umma_bf16_c(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACC)
+      : "memory");
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(

@@ -108,7 +108,7 @@ igemm_wgrad_narrow_kernel(const __grid_constant__ gb_wgrad_params p, const __gri
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (gb_elect_one()) {
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES, it = kb / STAGES;
         if (it > 0) mbar_wait(empty_bar + 8 * s, (it - 1) & 1);
@@ -131,32 +131,39 @@ igemm_wgrad_narrow_kernel(const __grid_constant__ gb_wgrad_params p, const __gri
     }
     __syncwarp();
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(CP, 1, 1);
-    for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % STAGES, it = kb / STAGES;
-      mbar_wait(full_bar + 8 * s, it & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_s = base + s * C::STAGE_BYTES;
-        const uint32_t p_s = a_s + C::A_BYTES_MAX;
+    // One thread issues every MMA (~17-32 cycles each): descriptors advance by additions only, and the region is
+    // guarded by elect.sync so that they stay in the uniform datapath (gb_elect_one).
+    if (gb_elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(CP, 1, 1);
+      const uint64_t adesc0 = make_desc_mn<C::LAYOUT_G>(base, C::RBG, HW * C::RBG);
+      const uint64_t bdesc0 = make_desc_mn<C::LAYOUT_P>(base + C::A_BYTES_MAX, 16, TW * C::RBP);
+      constexpr uint64_t A_ROW = (HW * C::RBG) >> 4;          // one halo row (descriptor units of 16 bytes)
+      constexpr uint64_t A_GRP = (C::APT * C::RBG) >> 4;      // the next tile of the same kernel row: APT pixels on
+      constexpr uint64_t B_KS = (2 * TW * C::RBP) >> 4;       // two patch rows
+      const int kh = wg.kh;
+      uint32_t accumulate = 0;
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES, it = kb / STAGES;
+        mbar_wait(full_bar + 8 * s, it & 1);
+        tc_fence_after();
+        const uint64_t a_st = adesc0 + (uint64_t)((s * C::STAGE_BYTES) >> 4);
+        const uint64_t b_st = bdesc0 + (uint64_t)((s * C::STAGE_BYTES) >> 4);
 #pragma unroll 1
         for (int ks = 0; ks < TH / 2; ++ks) {   // K = 16 pixels: rows 2 ks and 2 ks + 1 of the patch
-          const uint64_t bdesc = make_desc_mn<C::LAYOUT_P>(p_s + (uint32_t)(2 * ks * TW) * C::RBP, 16, TW * C::RBP);
-          const uint32_t acc = (kb | ks) ? 1u : 0u;
-          for (int dyi = 0; dyi < wg.kh; ++dyi) {
+          const uint64_t bdesc = b_st + (uint64_t)ks * B_KS;
+          uint64_t adesc = a_st + (uint64_t)(2 * ks) * A_ROW;
+          uint32_t tcol = tmem_base;
+#pragma unroll 1
+          for (int dyi = 0; dyi < kh; ++dyi, adesc += A_ROW) {
 #pragma unroll
-            for (int gx = 0; gx < C::GPR; ++gx) {
-              const uint32_t a_t = a_s + (uint32_t)((2 * ks + dyi) * HW + gx * C::APT) * C::RBG;
-              const uint64_t adesc = make_desc_mn<C::LAYOUT_G>(a_t, C::RBG, HW * C::RBG);
-              umma_bf16(tmem_base + (uint32_t)((dyi * C::GPR + gx) * CP), adesc, bdesc, idesc, acc);
-            }
+            for (int gx = 0; gx < C::GPR; ++gx, tcol += CP) umma_bf16(tcol, adesc + gx * A_GRP, bdesc, idesc, accumulate);
           }
+          accumulate = 1;
         }
         umma_commit(empty_bar + 8 * s);
       }
-      __syncwarp();
+      umma_commit(accum_bar);
     }
-    if (lane == 0) umma_commit(accum_bar);
     __syncwarp();
   }
 

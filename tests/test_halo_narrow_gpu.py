@@ -50,6 +50,19 @@ def test_ragged_image_and_batch():
     _case(expect_wgrad=WG_NARROW, name="3d k5 p2 16->16 7x46x38", cin=16, cout=16, k=5, s=1, p=2, H=46, W=38, D=7)
 
 
+def test_four_patch_columns():
+    """Images that columns of four 16 x 8 patches fit (the V-Net shapes): NP = 4 accumulators per CTA, single-buffered
+    halo for 32 channels, ragged last column, every column-tile width."""
+    _case(expect_wgrad=WG_NARROW, name="3d k5 p2 32->32 4x64x16", cin=32, cout=32, k=5, s=1, p=2, H=64, W=16, D=4)
+    _case(expect_wgrad=WG_NARROW, name="3d k5 p2 16->16 3x120x24 N=2", cin=16, cout=16, k=5, s=1, p=2, H=120, W=24, D=3, N=2)
+    _case(expect_wgrad=WG_NARROW, name="3d k5 p2 32->16 6x128x40", cin=32, cout=16, k=5, s=1, p=2, H=128, W=40, D=6)
+    _case(expect_last=None, name="3d k5 p2 32->64 3x64x16", cin=32, cout=64, k=5, s=1, p=2, H=64, W=16, D=3)
+    _case(expect_last=None, name="3d k5 p2 16->64 3x64x16", cin=16, cout=64, k=5, s=1, p=2, H=64, W=16, D=3)
+    _case(expect_wgrad=WG_NARROW, name="2d k7 p3 16->32 128x32", cin=16, cout=32, k=7, s=1, p=3, H=128, W=32)
+    _case(expect_wgrad=WG_NARROW, knobs={13: 3}, name="3d k5 p2 32->32 4x64x16 (one patch per CTA)", cin=32, cout=32, k=5, s=1,
+          p=2, H=64, W=16, D=4)
+
+
 def test_k3_and_2d_windows():
     _case(expect_wgrad=WG_NARROW, name="3d k3 p1 32->32 5x32x32", cin=32, cout=32, k=3, s=1, p=1, H=32, W=32, D=5)
     _case(expect_wgrad=WG_NARROW, name="2d k5 p2 32->32 48x40", cin=32, cout=32, k=5, s=1, p=2, H=48, W=40)
