@@ -2,16 +2,23 @@
 // 5x5x5 layers of the V-Net generators at the two finest resolutions -- the launches igemm_wgrad.cu served worst (its
 // 128-row tiles are 3/4 padding for 32 output channels and the gathered operand travelled once per tap).
 //
-//   dW[(tap, cin)][cout] += sum_pixels  x[pixel + tap][cin] * dOut[pixel][cout]
+//   dW[(dz, dy, dx)][cin][cout] = sum_p  x[p + (dz, dy, dx)][cin] * dOut[p][cout]
 //
-// Output-stationary over the taps of ONE depth offset dz: a CTA keeps kh x (1 or 2) accumulator tiles of
-// 128 x Cout in TMEM (rows = 4 or 8 x-adjacent taps x Cin) and walks 16 x 8 pixel patches.  Per patch it loads one
-// halo box of x (16 px pitch, 16 + kh - 1 rows) and the patch of dOut, both with the swizzle whose span is a pixel, and
-// reads them MN-major: the reduction index of the MMA is the pixel (two 8-pixel row segments per K = 16), the A rows
-// of a tile are `taps x channels`, and consecutive taps of a tile are consecutive PIXELS of the halo -- the descriptor's
-// leading-dimension stride is one pixel, so the four (eight) 64-byte (32-byte) atoms of a tile overlap in shared memory
-// and no data is moved per tap.  x is read 5 times (once per dz) instead of 125 times.
-// Taps beyond kw inside a tile (dx = 5..7 of a 5-wide kernel) accumulate garbage rows that the epilogue drops.
+// Output-stationary over the taps of ONE depth offset dz; the CTA walks 16 x 8 pixel patches.  Per patch it loads one
+// halo box of x and one (x-extended) box of dOut, both with the swizzle whose span is a pixel, and reads them MN-major:
+// the reduction index of the MMA is the pixel (two 8-pixel row segments per K = 16).
+//   * M (rows of A) = `dy taps x Cin`: the atoms of a tile are consecutive ROWS of the halo (the descriptor's
+//     leading-dimension stride is one halo row), 4 (Cin = 32) or 8 (Cin = 16) dy taps per 128-row tile.
+//   * N (columns of B) = `dx taps x Cout`: the atoms are dOut shifted by 0, 1, ... kw - 1 PIXELS (leading-dimension
+//     stride one pixel, so the atoms overlap in shared memory) against x read at the right-most tap:
+//       D[(dy, ci)][(j, co)] = sum_p' x[p' + (dz, dy, dx_max)][ci] * dOut[p' + j][co] = dW[(dz, dy, dx_max - j)][ci][co].
+//     Every (x pixel, dOut pixel) pair must meet in exactly one patch, so the patch grid starts kw - 1 pixels left of
+//     the image (TMA zero-fills what lies outside).
+// One MMA is 128 x (kw * Cout) x 16: with N = 160 / 80 columns the instruction is paced by the tensor math (or nearly),
+// not by its shared-memory A fetch as N = 16 / 32 instructions are (~55 cycles whatever N; the first version of this
+// kernel put the dx taps in M and issued 10 such MMAs per K step where this one issues 2).  No data moves per tap; x is
+// read once per depth offset (5x) instead of once per tap (125x).  Rows of dy taps beyond kh accumulate garbage that
+// the epilogue drops.
 // Epilogue: TMEM -> registers -> red.global.add.f32 into the fp32 workspace dw[cout][tap * Cin + cin] (a warp's 32 lanes
 // are 32 consecutive floats of one row); the pixel range is split over blockIdx.y.
 #include <cuda.h>
@@ -22,18 +29,19 @@
 
 namespace {
 
-constexpr int TW = 8, TH = 16, HW = 16;  // patch 16 rows x 8 pixels; halo pitch 16 pixels
-constexpr int MAX_KH = 7, MAX_HH = TH + MAX_KH - 1;
+constexpr int TW = 8, TH = 16, HW = 16;  // patch 16 rows x 8 pixels; both boxes have a pitch of 16 pixels
+constexpr int HH = TH + 7;               // halo rows: a tile's atoms reach 7 rows below the patch row
+constexpr int MAX_KW = 8;                // dOut shifts 0 .. kw - 1 stay inside the 16-pixel pitch
 constexpr int STAGES = 4;
 
 template <int CG, int CP>
 struct WNCfg {
   static constexpr int RBG = CG * 2, RBP = CP * 2;         // bytes per pixel
-  static constexpr int APT = 128 / CG;                     // taps (atoms) per accumulator tile: 4 / 8
-  static constexpr int GPR = 8 / APT;                      // tiles per kernel row (dx 0..7): 2 / 1
-  static constexpr int A_BYTES_MAX = HW * MAX_HH * RBG;    // multiple of 1 KB
-  static constexpr int P_BYTES = TH * TW * RBP;
-  static constexpr int STAGE_BYTES = A_BYTES_MAX + P_BYTES;
+  static constexpr int APT = 128 / CG;                     // dy taps (atoms) per accumulator tile: 4 / 8
+  static constexpr int A_BYTES = HW * HH * RBG;
+  static constexpr int A_STRIDE = (A_BYTES + 1023) / 1024 * 1024;
+  static constexpr int P_BYTES = TH * HW * RBP;            // multiple of 1 KB
+  static constexpr int STAGE_BYTES = A_STRIDE + P_BYTES;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 1024;
   static constexpr uint64_t LAYOUT_G = CG == 32 ? 4 : 6;   // SWIZZLE_64B / SWIZZLE_32B
   static constexpr uint64_t LAYOUT_P = CP == 32 ? 4 : 6;
@@ -42,8 +50,10 @@ struct WNCfg {
 struct WNGeom {
   gb_fastdiv tiles_x, tiles_y, tiles_z;
   int npatches, per_split;
-  int kh, kw, hh, a_bytes;
-  int dy_min, dx_min;
+  int kh, kw;
+  int dy_min, dx_min, dx_max;
+  int ntile;        // accumulator tiles: ceil(kh / APT)
+  int ncol;         // columns of a tile: kw * Cout
   int ngroups;
   int8_t group_dz[16];
 };
@@ -74,7 +84,7 @@ igemm_wgrad_narrow_kernel(const __grid_constant__ gb_wgrad_params p, const __gri
   uint8_t* tail = smem + STAGES * C::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 128);
-  int16_t* lut = reinterpret_cast<int16_t*>(tail + 192);   // [kh][8]: tap index of (dy, dx) in this depth group, -1 = none
+  int16_t* lut = reinterpret_cast<int16_t*>(tail + 192);   // [16 dy][8 dx]: tap index in this depth group, -1 = none
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -98,7 +108,7 @@ igemm_wgrad_narrow_kernel(const __grid_constant__ gb_wgrad_params p, const __gri
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(smem_u32(tmem_slot));
-  for (int i = tid; i < MAX_KH * 8; i += 256) lut[i] = -1;
+  for (int i = tid; i < 16 * 8; i += 256) lut[i] = -1;
   __syncthreads();
   for (int t = tid; t < p.ntaps; t += 256)
     if (p.taps[t][0] == dz) lut[(p.taps[t][1] - wg.dy_min) * 8 + (p.taps[t][2] - wg.dx_min)] = (int16_t)t;
@@ -114,7 +124,7 @@ igemm_wgrad_narrow_kernel(const __grid_constant__ gb_wgrad_params p, const __gri
         if (it > 0) mbar_wait(empty_bar + 8 * s, (it - 1) & 1);
         uint32_t t = (uint32_t)(b0 + kb);
         uint32_t u = gb_div(t, wg.tiles_x);
-        const int x0 = (int)(t - u * wg.tiles_x.d) * TW;
+        const int x0 = (int)(t - u * wg.tiles_x.d) * TW - (wg.kw - 1);   // the patch grid starts left of the image
         t = u;
         u = gb_div(t, wg.tiles_y);
         const int y0 = (int)(t - u * wg.tiles_y.d) * TH;
@@ -124,23 +134,26 @@ igemm_wgrad_narrow_kernel(const __grid_constant__ gb_wgrad_params p, const __gri
         const int n = (int)u;
         const uint32_t a_s = base + s * C::STAGE_BYTES;
         const uint32_t bar = full_bar + 8 * s;
-        mbar_expect_tx(bar, (uint32_t)(wg.a_bytes + C::P_BYTES));
-        tma_load_5d(a_s, &map_g, bar, 0, x0 + wg.dx_min, y0 + wg.dy_min, z0 + dz, n);
-        tma_load_5d(a_s + C::A_BYTES_MAX, &map_p, bar, 0, x0, y0, z0, n);
+        mbar_expect_tx(bar, (uint32_t)(C::A_BYTES + C::P_BYTES));
+        // x at the right-most tap: box pixel i <-> x = x0 + dx_max + i;  dOut: box pixel i <-> x = x0 + i
+        tma_load_5d(a_s, &map_g, bar, 0, x0 + wg.dx_max, y0 + wg.dy_min, z0 + dz, n);
+        tma_load_5d(a_s + C::A_STRIDE, &map_p, bar, 0, x0, y0, z0, n);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // One thread issues every MMA (~17-32 cycles each): descriptors advance by additions only, and the region is
-    // guarded by elect.sync so that they stay in the uniform datapath (gb_elect_one).
+    // One thread issues every MMA; the region is guarded by elect.sync so that the descriptor arithmetic stays in the
+    // uniform datapath (gb_elect_one).
     if (gb_elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(CP, 1, 1);
-      const uint64_t adesc0 = make_desc_mn<C::LAYOUT_G>(base, C::RBG, HW * C::RBG);
-      const uint64_t bdesc0 = make_desc_mn<C::LAYOUT_P>(base + C::A_BYTES_MAX, 16, TW * C::RBP);
+      const uint32_t idesc = make_idesc_bf16(wg.ncol, 1, 1);
+      // A: atoms = dy taps (one halo row apart), 8-pixel groups = patch rows (one halo row apart)
+      const uint64_t adesc0 = make_desc_mn<C::LAYOUT_G>(base, HW * C::RBG, HW * C::RBG);
+      // B: atoms = dOut shifted by one more pixel each, 8-pixel groups = patch rows
+      const uint64_t bdesc0 = make_desc_mn<C::LAYOUT_P>(base + C::A_STRIDE, C::RBP, HW * C::RBP);
       constexpr uint64_t A_ROW = (HW * C::RBG) >> 4;          // one halo row (descriptor units of 16 bytes)
-      constexpr uint64_t A_GRP = (C::APT * C::RBG) >> 4;      // the next tile of the same kernel row: APT pixels on
-      constexpr uint64_t B_KS = (2 * TW * C::RBP) >> 4;       // two patch rows
-      const int kh = wg.kh;
+      constexpr uint64_t B_ROW = (HW * C::RBP) >> 4;
+      const int ntile = wg.ntile;
+      const uint32_t ncol = (uint32_t)wg.ncol;
       uint32_t accumulate = 0;
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES, it = kb / STAGES;
@@ -150,14 +163,11 @@ igemm_wgrad_narrow_kernel(const __grid_constant__ gb_wgrad_params p, const __gri
         const uint64_t b_st = bdesc0 + (uint64_t)((s * C::STAGE_BYTES) >> 4);
 #pragma unroll 1
         for (int ks = 0; ks < TH / 2; ++ks) {   // K = 16 pixels: rows 2 ks and 2 ks + 1 of the patch
-          const uint64_t bdesc = b_st + (uint64_t)ks * B_KS;
+          const uint64_t bdesc = b_st + (uint64_t)(2 * ks) * B_ROW;
           uint64_t adesc = a_st + (uint64_t)(2 * ks) * A_ROW;
           uint32_t tcol = tmem_base;
-#pragma unroll 1
-          for (int dyi = 0; dyi < kh; ++dyi, adesc += A_ROW) {
-#pragma unroll
-            for (int gx = 0; gx < C::GPR; ++gx, tcol += CP) umma_bf16(tcol, adesc + gx * A_GRP, bdesc, idesc, accumulate);
-          }
+          for (int ti = 0; ti < ntile; ++ti, adesc += C::APT * A_ROW, tcol += ncol)
+            umma_bf16(tcol, adesc, bdesc, idesc, accumulate);
           accumulate = 1;
         }
         umma_commit(empty_bar + 8 * s);
@@ -171,18 +181,20 @@ igemm_wgrad_narrow_kernel(const __grid_constant__ gb_wgrad_params p, const __gri
   tc_fence_after();
   {
     const int lg = warp & 3;
-    const int m = lg * 32 + lane;           // accumulator row: tap a of the tile, channel c
+    const int m = lg * 32 + lane;           // accumulator row: dy atom a of the tile, input channel c
     const int a = m / CG, c = m - a * CG;
-    const int ntile = wg.kh * C::GPR;
-    for (int ti = (warp >> 2); ti < ntile; ti += 2) {
-      const int dyi = ti / C::GPR, gx = ti - dyi * C::GPR;
-      const int dxi = gx * C::APT + a;
-      const int tl = lut[dyi * 8 + dxi];
+    // work items (tile, dx shift j): the two warp groups take alternate items
+    const int nitem = wg.ntile * wg.kw;
+    for (int item = (warp >> 2); item < nitem; item += 2) {
+      const int ti = item / wg.kw, j = item - ti * wg.kw;
+      const int dyi = ti * C::APT + a;
+      const int tl = dyi < 16 ? lut[dyi * 8 + (wg.kw - 1 - j)] : -1;   // column block j <-> dx = dx_max - j
       uint32_t acc[CP];
-      if constexpr (CP == 32) tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ti * CP), acc);
-      else tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ti * CP), acc);
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ti * wg.ncol + j * CP);
+      if constexpr (CP == 32) tmem_ld32(taddr, acc);
+      else tmem_ld16(taddr, acc);
       tmem_ld_wait();
-      if (tl >= 0 && c < p.gathered.C) {
+      if (tl >= 0) {
         float* dst = p.dw + (int64_t)tl * CG + c;
 #pragma unroll
         for (int nn = 0; nn < CP; ++nn)
@@ -243,30 +255,32 @@ int gb_conv_wgrad_narrow(const gb_wgrad_params& p, cudaStream_t st) {
   }
   wg.kh = dy_max - dy_min + 1;
   wg.kw = dx_max - dx_min + 1;
-  if (wg.kw > 8 || wg.kh > MAX_KH) return -1;
-  const int gpr = cg == 32 ? 2 : 1;
-  if (wg.kh * gpr * cp > 512) return -1;
+  const int apt = 128 / cg;
+  wg.ntile = gb_cdiv(wg.kh, apt);
+  wg.ncol = wg.kw * cp;
+  // dOut shifts inside the 16-pixel pitch; one MMA's N <= 256; the accumulators inside the TMEM; every atom of a tile
+  // inside the halo box (garbage rows included)
+  if (wg.kw > MAX_KW || wg.ncol > 256 || wg.ncol % 16 != 0 || wg.ntile * wg.ncol > 512 || wg.ntile * apt > 8) return -1;
   wg.dy_min = dy_min;
   wg.dx_min = dx_min;
-  wg.hh = TH + wg.kh - 1;
-  wg.a_bytes = HW * wg.hh * cg * 2;
-  const int ntx = gb_cdiv(p.plain.W, TW), nty = gb_cdiv(p.plain.H, TH);
-  if ((int64_t)ntx * TW * nty * TH * 100 > (int64_t)p.plain.W * p.plain.H * 150) return -1;  // patches must fit the image
+  wg.dx_max = dx_max;
+  const int ntx = gb_cdiv(p.plain.W + wg.kw - 1, TW), nty = gb_cdiv(p.plain.H, TH);
+  if ((int64_t)ntx * TW * nty * TH * 100 > (int64_t)p.plain.W * p.plain.H * 175) return -1;  // patches must fit the image
   const int64_t np = (int64_t)ntx * nty * p.plain.D * p.plain.N;
   if (np <= 0 || np >= (1ll << 31)) return -1;
   wg.tiles_x = gb_make_fastdiv((uint32_t)ntx);
   wg.tiles_y = gb_make_fastdiv((uint32_t)nty);
   wg.tiles_z = gb_make_fastdiv((uint32_t)p.plain.D);
   wg.npatches = (int)np;
-  // one CTA per SM (the accumulators take the whole TMEM): one wave, at least two patches per CTA
+  // one CTA per SM (the accumulators take most of the TMEM): one wave, at least two patches per CTA
   int splits = p.splits > 0 ? p.splits : 148 / wg.ngroups;
   if (splits > np / 2) splits = (int)(np / 2);
   if (splits < 1) splits = 1;
   wg.per_split = gb_cdiv(np, splits);
   splits = gb_cdiv(np, wg.per_split);
   CUtensorMap mg, mp;
-  if (gb_tma_activation_map_narrow(p.gathered, cg, HW, wg.hh, &mg)) return 1;
-  if (gb_tma_activation_map_narrow(p.plain, cp, TW, TH, &mp)) return 1;
+  if (gb_tma_activation_map_narrow(p.gathered, cg, HW, HH, &mg)) return 1;
+  if (gb_tma_activation_map_narrow(p.plain, cp, HW, TH, &mp)) return 1;
   if (cg == 32) return cp == 32 ? launch<32, 32>(p, mg, mp, wg, splits, st) : launch<32, 16>(p, mg, mp, wg, splits, st);
   return cp == 32 ? launch<16, 32>(p, mg, mp, wg, splits, st) : launch<16, 16>(p, mg, mp, wg, splits, st);
 }
