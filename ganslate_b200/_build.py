@@ -7,7 +7,7 @@ ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIB_DIR = ROOT / "_lib"
 LIB_PATH = LIB_DIR / "libganslate_b200.so"
-SOURCES = ["api.cu", "pack.cu", "pack_v2.cu", "layout.cu", "pad.cu", "loss.cu", "instnorm.cu", "instnorm_fast.cu", "instnorm_v2.cu", "instnorm_v3.cu", "igemm_data.cu", "igemm_tma.cu", "igemm_halo.cu", "igemm_halo_narrow.cu", "igemm_pair.cu", "igemm_cg2.cu", "igemm_wgrad.cu", "igemm_wgrad_narrow.cu", "patchnce.cu", "patch_mlp.cu",
+SOURCES = ["api.cu", "pack.cu", "pack_v2.cu", "layout.cu", "pad.cu", "loss.cu", "instnorm.cu", "instnorm_fast.cu", "instnorm_v2.cu", "instnorm_v3.cu", "igemm_data.cu", "igemm_tma.cu", "igemm_halo.cu", "igemm_halo_narrow.cu", "igemm_xsplit.cu", "igemm_pair.cu", "igemm_cg2.cu", "igemm_wgrad.cu", "igemm_wgrad_narrow.cu", "patchnce.cu", "patch_mlp.cu",
            "adam.cu", "ssim.cu"]
 
 NVCC_FLAGS = [

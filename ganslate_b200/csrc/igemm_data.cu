@@ -276,6 +276,7 @@ int64_t view_max_offset(const gb_view& v) {
 int gb_conv_data_tma(const gb_conv_params& p, cudaStream_t st);   // igemm_tma.cu: -1 = not applicable
 int gb_conv_data_halo(const gb_conv_params& p, cudaStream_t st);  // igemm_halo.cu: -1 = not applicable
 int gb_conv_data_halo_narrow(const gb_conv_params& p, cudaStream_t st);  // igemm_halo_narrow.cu: -1 = not applicable
+int gb_conv_data_xsplit(const gb_conv_params& p, cudaStream_t st);       // igemm_xsplit.cu: -1 = not applicable
 int gb_conv_data_pair(const gb_conv_params& p, cudaStream_t st);  // igemm_pair.cu: -1 = not applicable
 int gb_conv_data_cg2(const gb_conv_params& p, cudaStream_t st);   // igemm_cg2.cu: -1 = not applicable / switched off
 
@@ -313,7 +314,9 @@ extern "C" int gb_conv_data(const gb_conv_params* pp, void* stream) {
   {
     int r = gb_conv_data_halo(p, st);   // halo-reuse TMA kernel (dense tap windows, single class)
     if (r >= 0) return r;
-    r = gb_conv_data_halo_narrow(p, st);  // same for 16 / 32 input channels (the 5x5x5 V-Net layers)
+    r = gb_conv_data_xsplit(p, st);       // 16 / 32 channels in, <= 32 out: the dx taps as columns of one MMA
+    if (r >= 0) return r;
+    r = gb_conv_data_halo_narrow(p, st);  // 16 / 32 input channels, one MMA per tap (what x-split does not take)
     if (r >= 0) return r;
     r = gb_conv_data_cg2(p, st);        // CTA-pair persistent kernel (opt-in: knob 16)
     if (r >= 0) return r;

@@ -898,6 +898,34 @@ int gb_tma_activation_map_narrow(const gb_view& v, int cbox, int tw, int th, CUt
   return 0;
 }
 
+// 2-D weight map {kpad, rows} with box {cbox k, bn rows}, cbox = 16 / 32 -> SWIZZLE_32B / SWIZZLE_64B: one tap's
+// weights as a K-major tile whose rows are one pixel's channels (igemm_xsplit.cu)
+int gb_tma_weight_map_narrow(const void* w, int kpad, int rows, int cbox, int bn, CUtensorMap* out) {
+  GB_CHECK(cbox == 16 || cbox == 32, "narrow weight map: 16 or 32 channels per tap");
+  struct {
+    const void* w;
+    int kpad, rows, cbox, bn, tag;
+  } k = {w, kpad, rows, cbox, bn, -9};
+  std::string key(reinterpret_cast<const char*>(&k), sizeof(k));
+  std::lock_guard<std::mutex> lk(g_map_mutex);
+  auto it = g_map_cache.find(key);
+  if (it != g_map_cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
+  cuuint32_t box[2] = {(cuuint32_t)cbox, (cuuint32_t)bn};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = encode_fn()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, cbox == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(narrow weights) failed: %d", (int)r);
+  if (g_map_cache.size() > 4096) g_map_cache.clear();
+  g_map_cache[key] = *out;
+  return 0;
+}
+
 // 2-D weight map {kpad, nclass*npad}, box {64, bn}; all classes of one conv share kpad on this path
 int gb_tma_weight_map(const void* w, int kpad, int rows, int bn, CUtensorMap* out) {
   struct {

@@ -15,10 +15,11 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 NARROW = 8      # knob 15 read-back: igemm_halo_narrow
+XSPLIT = 9      # knob 15 read-back: igemm_xsplit (takes the layers with <= 32 output rows first)
 WG_NARROW = 3   # knob 14 read-back: igemm_wgrad_narrow
 
 
-def _case(expect_last=NARROW, knobs=None, expect_wgrad=None, **case):
+def _case(expect_last=XSPLIT, knobs=None, expect_wgrad=None, **case):
     import gpu_bringup
     from ganslate_b200 import _cabi
     lib = _cabi.lib()
@@ -50,6 +51,15 @@ def test_ragged_image_and_batch():
     _case(expect_wgrad=WG_NARROW, name="3d k5 p2 16->16 7x46x38", cin=16, cout=16, k=5, s=1, p=2, H=46, W=38, D=7)
 
 
+@pytest.mark.parametrize("cin,cout", [(32, 32), (16, 16), (32, 16), (16, 32)])
+def test_one_mma_per_tap_kernel_when_xsplit_is_off(cin, cout):
+    """knob 4 = 4: the same layers on igemm_halo_narrow (which otherwise only serves what x-split declines)."""
+    _case(expect_last=NARROW, knobs={4: 4}, name=f"3d k5 p2 {cin}->{cout} 4x64x24 (narrow halo)", cin=cin, cout=cout, k=5,
+          s=1, p=2, H=64, W=24, D=4)
+    _case(expect_last=NARROW, knobs={4: 4}, name=f"3d k5 p2 {cin}->{cout} 3x30x22 (narrow halo)", cin=cin, cout=cout, k=5,
+          s=1, p=2, H=30, W=22, D=3)
+
+
 def test_four_patch_columns():
     """Images that columns of four 16 x 8 patches fit (the V-Net shapes): NP = 4 accumulators per CTA, single-buffered
     halo for 32 channels, ragged last column, every column-tile width."""
@@ -59,8 +69,8 @@ def test_four_patch_columns():
     _case(expect_last=None, name="3d k5 p2 32->64 3x64x16", cin=32, cout=64, k=5, s=1, p=2, H=64, W=16, D=3)
     _case(expect_last=None, name="3d k5 p2 16->64 3x64x16", cin=16, cout=64, k=5, s=1, p=2, H=64, W=16, D=3)
     _case(expect_wgrad=WG_NARROW, name="2d k7 p3 16->32 128x32", cin=16, cout=32, k=7, s=1, p=3, H=128, W=32)
-    _case(expect_wgrad=WG_NARROW, knobs={13: 3}, name="3d k5 p2 32->32 4x64x16 (one patch per CTA)", cin=32, cout=32, k=5, s=1,
-          p=2, H=64, W=16, D=4)
+    _case(expect_last=NARROW, expect_wgrad=WG_NARROW, knobs={13: 3, 4: 4}, name="3d k5 p2 32->32 4x64x16 (one patch per CTA)",
+          cin=32, cout=32, k=5, s=1, p=2, H=64, W=16, D=4)
 
 
 def test_k3_and_2d_windows():
@@ -79,7 +89,7 @@ def test_column_tiles_and_partial_channels():
 
 
 @pytest.mark.parametrize("cin,cout", [(32, 32), (16, 16), (32, 64), (16, 64)])
-def test_forward_is_served_by_the_narrow_kernel(cin, cout):
+def test_forward_is_served_by_the_narrow_kernels(cin, cout):
     """Forward only, through ConvOp.run_fwd: path read-back + values + InstanceNorm statistics of the epilogue."""
     from ganslate_b200 import _cabi, ops
     lib = _cabi.lib()
@@ -92,7 +102,7 @@ def test_forward_is_served_by_the_narrow_kernel(cin, cout):
     lib.gb_debug_knob(15, 0)
     y = op.run_fwd(ops.make_view(x), "cuda", w, b, stats=stats)
     torch.cuda.synchronize()
-    assert lib.gb_debug_knob(15, 0) == NARROW
+    assert lib.gb_debug_knob(15, 0) == (XSPLIT if cout <= 32 else NARROW)
     ref = torch.nn.functional.conv3d(x[..., :cin].float().permute(0, 4, 1, 2, 3), w, b, padding=2)
     got = y[..., :cout].float().permute(0, 4, 1, 2, 3)
     assert ((got - ref).abs().max() / ref.abs().max()).item() <= 1e-2
