@@ -288,9 +288,16 @@ int gb_tma_weight_map_narrow(const void* w, int kpad, int rows, int cbox, int bn
 
 // -1: not applicable, 0: launched, > 0: error.  Unit-stride single-class convolutions over exactly 16 or 32 input
 // channels with a complete kd x kh x kw tap box (kh, kw <= 5 x 5 boxes per depth offset, kw >= 2) and 16 / 32 packed
-// output rows.  knob 4 = 2 switches every halo kernel off, knob 4 = 4 this one only (igemm_halo_narrow then serves).
+// output rows.  knob 4 = 2 switches every halo kernel off, knob 4 = 4 this one only (igemm_halo_narrow then serves),
+// knob 4 = 5 widens it from its default (16 -> 16 layers) to everything it supports.
 int gb_conv_data_xsplit(const gb_conv_params& p, cudaStream_t st) {
   if (g_gb_knobs[4] == 2 || g_gb_knobs[4] == 3 || g_gb_knobs[4] == 4 || g_gb_knobs[3] != 0 || p.in_c_valid != 0) return -1;
+  // Measured (profiles/r02ae_conv3d_microbench_xsplit.txt): an MMA's operand fetch grows with M + N rows (~125 cycles for
+  // 128 x 160 x 16), and with the accumulators of three tiles in TMEM only one CTA fits an SM, so prologue and epilogue
+  // are exposed.  16 -> 16 layers: 375 / 341 us against 404 / 392 us on igemm_halo_narrow (forward / data gradient on
+  // 32 x 256 x 256 voxels); 32 -> 32 layers: 876 / 853 us against 722 / 768 us.  Default: the 16 -> 16 case only;
+  // knob 4 = 5 takes every layer this kernel supports.
+  if (g_gb_knobs[4] != 5 && !(p.in.C == 16 && p.npad == 16)) return -1;
   if (!(p.in.C == 16 || p.in.C == 32) || !(p.npad == 16 || p.npad == 32) || p.in.pad != 0 || !gb_tma_available()) return -1;
   if (p.nclass != 1 || p.ncols > p.npad) return -1;
   for (int d = 0; d < 3; ++d)

@@ -19,7 +19,7 @@ XSPLIT = 9      # knob 15 read-back: igemm_xsplit (takes the layers with <= 32 o
 WG_NARROW = 3   # knob 14 read-back: igemm_wgrad_narrow
 
 
-def _case(expect_last=XSPLIT, knobs=None, expect_wgrad=None, **case):
+def _case(expect_last="auto", knobs=None, expect_wgrad=None, **case):
     import gpu_bringup
     from ganslate_b200 import _cabi
     lib = _cabi.lib()
@@ -34,6 +34,8 @@ def _case(expect_last=XSPLIT, knobs=None, expect_wgrad=None, **case):
         for k, v in old.items():
             lib.gb_debug_knob(k, v)
     assert ok
+    if expect_last == "auto":   # the data gradient reads cout channels and writes cin: x-split takes 16 -> 16 by default
+        expect_last = XSPLIT if (case["cin"] == 16 and case["cout"] == 16) else NARROW
     if expect_last is not None:
         assert path == expect_last, f"last gb_conv_data call (the data gradient) was served by kernel path {path}"
     if expect_wgrad is not None:
@@ -52,6 +54,18 @@ def test_ragged_image_and_batch():
 
 
 @pytest.mark.parametrize("cin,cout", [(32, 32), (16, 16), (32, 16), (16, 32)])
+def test_xsplit_on_every_layer_it_supports(cin, cout):
+    """knob 4 = 5: the dx taps as columns of one MMA + shift-and-add epilogue, all four channel combinations, three /
+    four tiles per CTA, ragged images."""
+    _case(expect_last=XSPLIT, knobs={4: 5}, name=f"3d k5 p2 {cin}->{cout} 4x64x24 (x-split)", cin=cin, cout=cout, k=5, s=1,
+          p=2, H=64, W=24, D=4)
+    _case(expect_last=XSPLIT, knobs={4: 5}, name=f"3d k5 p2 {cin}->{cout} 3x30x22 N=2 (x-split)", cin=cin, cout=cout, k=5,
+          s=1, p=2, H=30, W=22, D=3, N=2)
+    _case(expect_last=XSPLIT, knobs={4: 5}, name=f"3d k3 p1 {cin}->{cout} 5x40x28 (x-split)", cin=cin, cout=cout, k=3, s=1,
+          p=1, H=40, W=28, D=5)
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 32), (16, 16), (32, 16), (16, 32)])
 def test_one_mma_per_tap_kernel_when_xsplit_is_off(cin, cout):
     """knob 4 = 4: the same layers on igemm_halo_narrow (which otherwise only serves what x-split declines)."""
     _case(expect_last=NARROW, knobs={4: 4}, name=f"3d k5 p2 {cin}->{cout} 4x64x24 (narrow halo)", cin=cin, cout=cout, k=5,
@@ -64,7 +78,7 @@ def test_four_patch_columns():
     """Images that columns of four 16 x 8 patches fit (the V-Net shapes): NP = 4 accumulators per CTA, single-buffered
     halo for 32 channels, ragged last column, every column-tile width."""
     _case(expect_wgrad=WG_NARROW, name="3d k5 p2 32->32 4x64x16", cin=32, cout=32, k=5, s=1, p=2, H=64, W=16, D=4)
-    _case(expect_wgrad=WG_NARROW, name="3d k5 p2 16->16 3x120x24 N=2", cin=16, cout=16, k=5, s=1, p=2, H=120, W=24, D=3, N=2)
+    _case(expect_last=NARROW, knobs={4: 4}, expect_wgrad=WG_NARROW, name="3d k5 p2 16->16 3x120x24 N=2", cin=16, cout=16, k=5, s=1, p=2, H=120, W=24, D=3, N=2)
     _case(expect_wgrad=WG_NARROW, name="3d k5 p2 32->16 6x128x40", cin=32, cout=16, k=5, s=1, p=2, H=128, W=40, D=6)
     _case(expect_last=None, name="3d k5 p2 32->64 3x64x16", cin=32, cout=64, k=5, s=1, p=2, H=64, W=16, D=3)
     _case(expect_last=None, name="3d k5 p2 16->64 3x64x16", cin=16, cout=64, k=5, s=1, p=2, H=64, W=16, D=3)
@@ -76,7 +90,7 @@ def test_four_patch_columns():
 def test_k3_and_2d_windows():
     _case(expect_wgrad=WG_NARROW, name="3d k3 p1 32->32 5x32x32", cin=32, cout=32, k=3, s=1, p=1, H=32, W=32, D=5)
     _case(expect_wgrad=WG_NARROW, name="2d k5 p2 32->32 48x40", cin=32, cout=32, k=5, s=1, p=2, H=48, W=40)
-    _case(expect_wgrad=WG_NARROW, name="2d k7 p3 16->16 32x32", cin=16, cout=16, k=7, s=1, p=3, H=32, W=32)
+    _case(expect_last=None, expect_wgrad=WG_NARROW, name="2d k7 p3 16->16 32x32", cin=16, cout=16, k=7, s=1, p=3, H=32, W=32)
 
 
 def test_column_tiles_and_partial_channels():
@@ -102,7 +116,7 @@ def test_forward_is_served_by_the_narrow_kernels(cin, cout):
     lib.gb_debug_knob(15, 0)
     y = op.run_fwd(ops.make_view(x), "cuda", w, b, stats=stats)
     torch.cuda.synchronize()
-    assert lib.gb_debug_knob(15, 0) == (XSPLIT if cout <= 32 else NARROW)
+    assert lib.gb_debug_knob(15, 0) == (XSPLIT if (cin == 16 and cout == 16) else NARROW)
     ref = torch.nn.functional.conv3d(x[..., :cin].float().permute(0, 4, 1, 2, 3), w, b, padding=2)
     got = y[..., :cout].float().permute(0, 4, 1, 2, 3)
     assert ((got - ref).abs().max() / ref.abs().max()).item() <= 1e-2
