@@ -130,7 +130,7 @@ igemm_halo_kernel(const __grid_constant__ gb_conv_params p, const __grid_constan
   const int total_mma_groups = hg.ngroups * chunks;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (gb_elect_one()) {
       int ai = 0, bi = 0;
       for (int g = 0; g < hg.ngroups; ++g) {
         const int dz = hg.group_dz[g];
@@ -166,7 +166,7 @@ igemm_halo_kernel(const __grid_constant__ gb_conv_params p, const __grid_constan
           const int nt = min(TG, hg.group_begin[g + 1] - tl);
           mbar_wait(b_full + 8 * bs, bit & 1);
           tc_fence_after();
-          if (lane == 0) {
+          if (gb_elect_one()) {
             for (int j = 0; j < nt; ++j) {
               const int ry = taps_s[4 * (tl + j) + 1] - hg.dy_min, rx = taps_s[4 * (tl + j) + 2] - hg.dx_min;
               const uint32_t a_s = a_base + as * C::A_BYTES_MAX + (uint32_t)(ry * HW + rx) * 128u;

@@ -125,8 +125,8 @@ igemm_pair_kernel(const __grid_constant__ gb_conv_params p, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (one lane)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (one lane, see gb_elect_one)
+    if (gb_elect_one()) {
       int as = 0, ait = 0, bs = 0, bit = 0;
       for (int g = 0; g < pg.ngroups; ++g) {
         const int dz = pg.group_dz[g];
@@ -166,7 +166,7 @@ igemm_pair_kernel(const __grid_constant__ gb_conv_params p, const __grid_constan
         for (int tl = pg.group_begin[g]; tl < pg.group_begin[g + 1]; ++tl) {
           mbar_wait(b_full + 8 * bs, bit & 1);
           tc_fence_after();
-          if (lane == 0) {
+          if (gb_elect_one()) {
             const int ry = taps_s[4 * tl + 1] - pg.dy_min, rx = taps_s[4 * tl + 2] - pg.dx_min;
             const uint64_t bdesc = make_smem_desc(b_base + bs * B_BYTES, 16, 1024);
 #pragma unroll

@@ -336,8 +336,9 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
   if (tid == 64) ts_put(tg, 3);   // setup done
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (one lane)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (one lane; elect.sync keeps the
+    // descriptor / coordinate arithmetic of the region in the uniform datapath, see gb_elect_one)
+    if (gb_elect_one()) {
       // packed weights of this class start at row (w_offset / kpad) of the 2-D weight map built per class
       int s = 0, it = 0;
       for (int tl = 0; tl < cc.ntaps; ++tl) {
@@ -372,7 +373,7 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
       if (kb == 0 && lane == 0) ts_put(tg, 4);   // first operands have landed
       if (tg.mode == 2) {
         if (lane == 0) mbar_arrive(empty_bar + 8 * s);
-      } else if (lane == 0) {
+      } else if (gb_elect_one()) {
         const uint32_t a_s = base + s * C::STAGE_BYTES;
         const uint32_t b_s = a_s + A_BYTES;
         const uint64_t adesc = make_smem_desc(a_s, 16, 1024);

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256, WCfg<BN, RT>::MIN_CTAS) igemm_wgrad_kerne
 
   if (TMA && warp < 4) {
     // ------------------------------------------------------------------ TMA producer: one lane, (2 + NG) boxes/stage
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && gb_elect_one()) {   // (elect.sync in warp 0 only: the && short-circuits per warp)
       const int Cg = p.gathered.C;
       int g_c0[NG], g_dz[NG], g_dy[NG], g_dx[NG];
       bool g_ok[NG];
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256, WCfg<BN, RT>::MIN_CTAS) igemm_wgrad_kerne
       const int it = kb / STAGES;
       mbar_wait(full_bar + 8 * s, it & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (gb_elect_one()) {
         const uint32_t p_s = base + s * C::STAGE_BYTES;
         const uint32_t g_s = p_s + C::P_BYTES;
         // MN-major: LBO = stride between 64-wide atoms, SBO = stride between groups of 8 pixels (k)
