@@ -30,9 +30,11 @@ WORKLOADS = {
     "pix2pix_resnet": ("Pix2Pix Resnet2D train img/s", "pix2pix_resnet2d", 8, (3, 256, 512), True),
     "pix2pix_unet": ("Pix2Pix Unet2D train img/s", "pix2pix_unet2d", 8, (3, 256, 512), True),
     "cut": ("CUT train img/s", "cut_resnet2d", 1, (3, 256, 256), True),   # graph segments (r02b: 27.4 eager -> 75.9 img/s)
-    "cyclegan3d": ("CycleGAN 3D Vnet3D train patches/s", "cyclegan_vnet3d", 1, (1, 32, 256, 256), False),
-    "revgan3d": ("RevGAN 3D Vnet3D train patches/s", "revgan_vnet3d", 1, (4, 128, 128, 128), False),
-    "revgan_piresnet3d": ("RevGAN 3D Piresnet3D train patches/s", "revgan_piresnet3d", 1, (1, 32, 176, 176), False),
+    "cyclegan3d": ("CycleGAN 3D Vnet3D train patches/s", "cyclegan_vnet3d", 1, (1, 32, 256, 256), True),   # r02al: 14.0 eager -> 15.8
+    # (RevGAN replays two captured phases on one GPU -- r02am: 11.6 -> 12.7 and 27.3 -> 31.8 patches/s; a data-parallel
+    #  run uses eager DistributedDataParallel: BaseGAN.parallelize_networks switches the capture off)
+    "revgan3d": ("RevGAN 3D Vnet3D train patches/s", "revgan_vnet3d", 1, (4, 128, 128, 128), True),
+    "revgan_piresnet3d": ("RevGAN 3D Piresnet3D train patches/s", "revgan_piresnet3d", 1, (1, 32, 176, 176), True),
 }
 
 
@@ -66,7 +68,7 @@ def parse():
     if args.workload != "cyclegan2d" and "--batch" not in sys.argv and "GB_BENCH_BATCH" not in os.environ:
         args.batch = WORKLOADS[args.workload][2]
     if args.multi_stream is None:
-        args.multi_stream = (args.workload in ("cyclegan2d", "cyclegan3d", "pix2pix_resnet", "pix2pix_unet", "revgan3d", "cut")
+        args.multi_stream = (args.workload in ("cyclegan2d", "cyclegan3d", "pix2pix_resnet", "pix2pix_unet", "revgan3d", "revgan_piresnet3d", "cut")
                              and not args.single_stream)
     return args
 
@@ -202,7 +204,7 @@ def run_b200(args):
     if shape is None:
         shape = (3, args.size, args.size)
     if not graph_ok and not args.graph:
-        args.no_graph = True  # CUT / RevGAN recipes run eagerly by default (--graph: CUT's segmented capture)
+        args.no_graph = True  # (a workload marked eager-by-default in WORKLOADS; --graph overrides)
     flush = torch.empty(2 * 126 * 1024 * 1024, dtype=torch.uint8, device=dev)
     loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
 
@@ -333,7 +335,8 @@ def run_b200(args):
             "config": workload_config(args, world),
             "e2e": {"value": imgs / t_e2e, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": clocks,
-            "cuda_graph": not args.no_graph,
+            # (what the model actually did: a data-parallel RevGAN switches its capture off, BaseGAN.parallelize_networks)
+            "cuda_graph": bool(getattr(m["model"], "use_cuda_graph", not args.no_graph)),
         }
         if args.e2e_pipeline:
             line["e2e"]["pipeline"] = "H2D of step i+1 on a copy stream; loss of step i read after step i+1 is enqueued"

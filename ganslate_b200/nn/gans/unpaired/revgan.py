@@ -56,6 +56,21 @@ class RevGAN(BaseGAN):
         self.visuals['real_B'] = self.stage_input('real_B', input['B'])
 
     def optimize_parameters(self):
+        """One iteration in the reference's order (revgan.py:89-116).  With `train.cuda_graph` (one GPU; a data-parallel
+        run falls back to eager DistributedDataParallel, BaseGAN.parallelize_networks) the generator phase and the
+        discriminator phase are captured once and replayed; the image pools stay host logic in between, as in CycleGAN."""
+        if self.graph_mode('step'):
+            self.run_graphed('G', self._phase_G)
+            pool_query = cyclegan.CycleGAN._pool_query
+            fake_B = self.stage_input('pool_B', pool_query(self.fake_B_pool, self.visuals['fake_B']))
+            fake_A = self.stage_input('pool_A', pool_query(self.fake_A_pool, self.visuals['fake_A']))
+            self.run_graphed('D', lambda: self._phase_D(fake_B, fake_A))
+            return
+        with self.eager_stream():
+            self._phase_G()
+            self._phase_D(None, None)
+
+    def _phase_G(self):
         discriminators = [self.networks['D_B'], self.networks['D_A']]
         self.forward()
         self.metrics.update(self.training_metrics.compute_metrics_G(self.visuals))
@@ -63,11 +78,14 @@ class RevGAN(BaseGAN):
         self.optimizers['G'].zero_grad(set_to_none=True)
         self.backward_G()
         self.optimizers['G'].step()
-        self.set_requires_grad(discriminators, True)
+
+    def _phase_D(self, fake_B, fake_A):
+        """fake_B / fake_A: pooled fakes already staged (graph replay), or None: query the pools here."""
+        self.set_requires_grad([self.networks['D_B'], self.networks['D_A']], True)
         self.optimizers['D'].zero_grad(set_to_none=True)
-        self.backward_D('D_B')
+        self.backward_D('D_B', fake_B)
         self.metrics.update(self.training_metrics.compute_metrics_D('D_B', self.pred_real, self.pred_fake))
-        self.backward_D('D_A')
+        self.backward_D('D_A', fake_A)
         self.metrics.update(self.training_metrics.compute_metrics_D('D_A', self.pred_real, self.pred_fake))
         self.optimizers['D'].step()
 
@@ -93,11 +111,13 @@ class RevGAN(BaseGAN):
         self.visuals.update({'fake_B': fake_B, 'rec_A': rec_A, 'idt_A': idt_A, 'fake_A': fake_A, 'rec_B': rec_B,
                              'idt_B': idt_B})
 
-    def backward_D(self, discriminator):
+    def backward_D(self, discriminator, pooled_fake=None):
         if discriminator == 'D_B':
-            real, fake = self.visuals['real_B'], self.fake_B_pool.query(self.visuals['fake_B'])
+            real = self.visuals['real_B']
+            fake = pooled_fake if pooled_fake is not None else self.fake_B_pool.query(self.visuals['fake_B'])
         elif discriminator == 'D_A':
-            real, fake = self.visuals['real_A'], self.fake_A_pool.query(self.visuals['fake_A'])
+            real = self.visuals['real_A']
+            fake = pooled_fake if pooled_fake is not None else self.fake_A_pool.query(self.visuals['fake_A'])
         else:
             raise ValueError('The discriminator has to be either "D_A" or "D_B".')
         self.pred_real = self.networks[discriminator](real)

@@ -111,3 +111,37 @@ def test_revgan_step_vs_oracle():
                 if c < 0.9:
                     bad.append((name, k, c))
     assert not bad, bad
+
+
+def test_revgan_graph_replay_equals_eager_step():
+    """RevGAN with train.cuda_graph (+ two-stream execution, inverse-recompute backward): a replayed iteration computes what
+    an eager iteration computes from the same weights and inputs (losses within the run-to-run noise of the bf16 path)."""
+    from ganslate_b200.presets import revgan_vnet3d
+    from ganslate_b200.utils.builders import build_gan
+    from oracle import torch_oracle3d as O3
+    a, b = O3.synthetic_volume(1, 2, 16, 32, seed=1)
+    torch.manual_seed(0)
+    random.seed(0)
+    mg = build_gan(revgan_vnet3d(channels=2, ndf=16, n_layers=2, cuda_graph=True, cuda_graph_warmup=2, multi_stream=True, **SMALL))
+    for _ in range(4):   # 2 eager warm-up iterations, capture, one more replay
+        mg.set_input({"A": a, "B": b})
+        mg.optimize_parameters()
+    torch.cuda.synchronize()
+    assert len(mg._graphs) == 2 and mg.graph_launches_per_step > 100
+    state = {n: {k: v.detach().clone() for k, v in net.state_dict().items()} for n, net in mg.networks.items()}
+    mg.set_input({"A": a, "B": b})
+    mg.optimize_parameters()
+    torch.cuda.synchronize()
+    lg = {k: float(v) for k, v in mg.losses.items() if v is not None}
+    torch.manual_seed(0)
+    me = build_gan(revgan_vnet3d(channels=2, ndf=16, n_layers=2, **SMALL))
+    for n, net in me.networks.items():
+        net.load_state_dict(state[n])
+    me.set_input({"A": a, "B": b})
+    me.optimize_parameters()
+    torch.cuda.synchronize()
+    le = {k: float(v) for k, v in me.losses.items() if v is not None}
+    for k in le:
+        assert abs(le[k] - lg[k]) <= 3e-2 * abs(le[k]) + 1e-3, (k, le[k], lg[k])
+    w = next(iter(mg.networks["G"].parameters()))
+    assert (w.detach() - next(iter(state["G"].values()))).abs().max().item() > 0   # the replay stepped the optimizer
