@@ -269,6 +269,42 @@ def test_revgan_piresnet3d_iteration_host_logic(monkeypatch):
     assert not bad, bad
 
 
+def test_revgan_graph_phases_follow_the_eager_order(monkeypatch):
+    """RevGAN with `train.cuda_graph`: generator phase and discriminator phase are the captured units, the image pools are
+    queried in between.  With the capture replaced by a direct call the phased path must run the eager program: same
+    losses, same gradients, G stepped before the discriminators (revgan.py:89-116), pooled fakes handed to backward_D."""
+    import random
+    _cpu_recipe(monkeypatch)
+    from ganslate_b200.presets import revgan_piresnet3d
+    from ganslate_b200.utils.builders import build_gan
+    from oracle import torch_oracle3d as O3
+    a, b = O3.synthetic_volume(1, 1, 16, 32, seed=1)
+    results = {}
+    for mode in ("eager", "phases"):
+        torch.manual_seed(0)
+        random.seed(0)
+        gan = build_gan(revgan_piresnet3d(channels=1, depth=2, first_layer_channels=16, ndf=16, n_layers=2))
+        order = []
+        for name, o in gan.optimizers.items():
+            monkeypatch.setattr(o, "step", lambda *args, _n=name, **kw: order.append(_n))
+        seen = []
+        if mode == "phases":
+            monkeypatch.setattr(gan, "graph_mode", lambda key: True)
+            monkeypatch.setattr(gan, "run_graphed", lambda name, fn: (seen.append(name), fn())[1])
+            monkeypatch.setattr(gan, "stage_input", lambda name, t: (seen.append(name), t)[1])
+        gan.set_input({"A": a, "B": b})
+        gan.optimize_parameters()
+        results[mode] = ({k: float(v.detach()) for k, v in gan.losses.items() if v is not None},
+                         {(n, k): p.grad.clone() for n, net in gan.networks.items() for k, p in net.named_parameters()
+                          if p.grad is not None}, list(order), list(seen))
+    assert results["phases"][3] == ["real_A", "real_B", "G", "pool_B", "pool_A", "D"]
+    assert results["eager"][2] == results["phases"][2] == ["G", "D"]
+    assert results["eager"][0] == results["phases"][0]
+    assert results["eager"][1].keys() == results["phases"][1].keys()
+    for k, v in results["eager"][1].items():
+        assert torch.equal(v, results["phases"][1][k]), k
+
+
 def test_bringup_cases_through_fake_backend(monkeypatch):
     """Every single-operator case of tests/gpu_bringup.py (the cases the GPU suite runs against torch: 1x1 ... 7x7,
     strided, transposed, 3-D convolutions incl. pixel windows; InstanceNorm groups with and without borders; residual
