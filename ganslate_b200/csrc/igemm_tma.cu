@@ -279,6 +279,10 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
   int8_t* taps_s = reinterpret_cast<int8_t*>(tail + 192);
   __shared__ __align__(16) float bias_s[BN];
   __shared__ float stat_s[BN >= 64 ? 2 * BN : 2];   // TMA-store epilogue: per-channel (sum, sum^2) of this tile
+  // Narrow tiles (BN < 64): the InstanceNorm statistics of the four row warps meet here and leave the CTA as one atomic
+  // per column and moment.  Measured (tools/tiny_k_probe.py): the 64 -> 16 transposed convolution of the V-Net on
+  // 32 x 256 x 256 voxels takes 346 us with per-warp global atomics (2 M of them on 32 addresses), 125 us without any.
+  __shared__ float sst_narrow[BN < 64 ? 2 * BN : 2];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -329,6 +333,8 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
   for (int i = tid; i < cc.ntaps; i += 256)
     *reinterpret_cast<uint32_t*>(taps_s + 4 * i) = *reinterpret_cast<const uint32_t*>(p.taps[cc.tap_begin + i]);
   for (int i = tid; i < BN; i += 256) bias_s[i] = (p.bias != nullptr && n0 + i < p.ncols) ? p.bias[n0 + i] : 0.f;
+  if (BN < 64)
+    for (int i = tid; i < 2 * BN; i += 256) sst_narrow[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -425,11 +431,16 @@ igemm_tma_kernel(const __grid_constant__ gb_conv_params p, const __grid_constant
         ooff = gb_pix_offset(p.out, n, z0 * p.out_mul[0] + cc.off[0], qy * p.out_mul[1] + cc.off[1],
                              qx * p.out_mul[2] + cc.off[2]);
       // (stage 0 of the ring is free once the accumulator is complete: scratch of the CTA-level statistics sum)
-      gb_conv_epilogue<BN>(p, tmem_base, warp, lane, KB > 0, row_ok, ooff, n0, bias_s, n, reinterpret_cast<float*>(smem));
+      gb_conv_epilogue<BN>(p, tmem_base, warp, lane, KB > 0, row_ok, ooff, n0, bias_s, n, reinterpret_cast<float*>(smem),
+                           (BN < 64 && p.stats != nullptr && !p.out_fp32) ? sst_narrow : nullptr);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (BN < 64 && p.stats != nullptr && !p.out_fp32 && !(tg.mode & 4)) {
+    for (int i = tid; i < 2 * BN; i += 256)
+      if (n0 + (i >> 1) < p.ncols) atomicAdd(p.stats + ((int64_t)n * p.out.C + n0 + (i >> 1)) * 2 + (i & 1), sst_narrow[i]);
+  }
   if (tid == 64) ts_put(tg, 7);                  // epilogue done
   if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
