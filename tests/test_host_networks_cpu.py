@@ -763,3 +763,50 @@ def test_fp32_validation_mode_matches_the_fp32_oracle_to_1e_5(monkeypatch):
     from forced_parity import forced_network_parity, summarize
     sm = summarize(forced_network_parity(ours, ref, torch.rand(1, 3, 32, 32) * 2 - 1, fp32=True))
     assert sm["fwd_max_rel"] <= 2e-5 and sm["bwd_max_rel"] <= 2e-5 and sm["wgrad_max_rel"] <= 2e-5, sm
+
+
+def test_widened_few_channel_input_through_fake_backend(monkeypatch):
+    """ops.WIDEN_INPUT: a 1 -> 16 channel 5x5x5 layer reads a 16-channel copy of its 8-channel operand (packing, weight-
+    gradient plan and unpack then work on cin_pad = 16, the data gradient still writes the 8-channel buffer).  Same
+    outputs and gradients as torch, and as the same layer with the switch off."""
+    fake_cabi.install(monkeypatch)
+    import gpu_bringup
+    from ganslate_b200 import ops
+    monkeypatch.setattr(gpu_bringup, "dev", "cpu")
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    for widen in (True, False):
+        monkeypatch.setattr(ops, "WIDEN_INPUT", widen)
+        op = ops.ConvOp(1, 16, (5, 5, 5), (1, 1, 1), (2, 2, 2))
+        assert op.widen_input == widen and op.cin_pad == (16 if widen else 8)
+        assert gpu_bringup.conv_case(f"3d k5 p2 1->16 4x12x10 widen={widen}", 1, 16, 5, 1, 2, 12, 10, D=4)
+        assert gpu_bringup.conv_case(f"3d k5 p2 4->16 3x9x11 N=2 widen={widen}", 4, 16, 5, 1, 2, 9, 11, N=2, D=3)
+    # not widened: 2-D kernels, strided layers, wide outputs, depth slabs of a larger kernel
+    monkeypatch.setattr(ops, "WIDEN_INPUT", True)
+    assert not ops.ConvOp(3, 16, (1, 7, 7), (1, 1, 1), (0, 3, 3)).widen_input
+    assert not ops.ConvOp(1, 16, (4, 4, 4), (2, 2, 2), (1, 1, 1)).widen_input
+    assert not ops.ConvOp(1, 64, (5, 5, 5), (1, 1, 1), (2, 2, 2)).widen_input
+    assert not ops.ConvOp(1, 16, (1, 7, 7), (1, 1, 1), (0, 3, 3), weight_taps=343).widen_input
+
+
+def test_other_batch_shape_after_capture_host_logic(monkeypatch):
+    """BaseGAN.stage_input / graph_mode: a batch whose shape differs from the captured one runs ONE eager iteration on the
+    tensor itself; the entries of visuals / losses the graphs were bound to are restored before the next replay."""
+    _cpu_recipe(monkeypatch)
+    from ganslate_b200.presets import cyclegan_resnet2d
+    from ganslate_b200.utils.builders import build_gan
+    gan = build_gan(cyclegan_resnet2d(n_residual_blocks=1))
+    gan.use_cuda_graph, gan.graph_warmup_iters, gan._graph_calls = True, 0, 5
+    a = torch.zeros(2, 3, 32, 32)
+    buf = gan.stage_input("real_A", a)               # before any capture: allocates the static buffer
+    assert buf is gan._static["real_A"] and buf.shape == a.shape
+    gan._graphs = {"G": object(), "D": object()}     # "captured"
+    bound_fake, bound_loss = torch.ones(1), torch.ones(())
+    gan.visuals["fake_B"], gan.losses["G_AB"] = bound_fake, bound_loss
+    small = torch.zeros(1, 3, 32, 32)
+    got = gan.stage_input("real_A", small)           # partial batch
+    assert got.shape == small.shape and gan._static["real_A"].shape == a.shape
+    assert gan.graph_mode("step") is False           # this iteration is eager ...
+    gan.visuals["fake_B"], gan.losses["G_AB"] = torch.zeros(1), torch.zeros(())   # ... and rebinds the entries
+    assert gan.stage_input("real_A", a) is gan._static["real_A"]
+    assert gan.graph_mode("step") is True            # next full batch: graphs again
+    assert gan.visuals["fake_B"] is bound_fake and gan.losses["G_AB"] is bound_loss
